@@ -1,0 +1,45 @@
+// Shared helpers for libmobgt (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/mobgt.h"
+
+namespace mobgt {
+
+void set_error(const char *fmt, ...);
+
+inline int32_t cuda_fail(cudaError_t e, const char *what) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return MOBGT_ERR_CUDA;
+}
+
+#define MOBGT_CUDA_OK(expr)                                        \
+    do {                                                           \
+        cudaError_t _e = (expr);                                   \
+        if (_e != cudaSuccess) return ::mobgt::cuda_fail(_e, #expr); \
+    } while (0)
+
+#define MOBGT_LAUNCH_OK(name)                                            \
+    do {                                                                 \
+        cudaError_t _e = cudaGetLastError();                             \
+        if (_e != cudaSuccess) return ::mobgt::cuda_fail(_e, "launch " name); \
+    } while (0)
+
+#define MOBGT_REQUIRE(cond, code, ...)   \
+    do {                                 \
+        if (!(cond)) {                   \
+            ::mobgt::set_error(__VA_ARGS__); \
+            return (code);               \
+        }                                \
+    } while (0)
+
+constexpr int kNumSMs = 148;
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+}  // namespace mobgt

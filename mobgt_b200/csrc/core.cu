@@ -1,0 +1,32 @@
+// Library-wide state: version, thread-local error string, device check.
+#include "common.cuh"
+
+namespace mobgt {
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace mobgt
+
+extern "C" int32_t mobgt_version(void) { return 100; }
+
+extern "C" int32_t mobgt_last_error(char *buf, size_t buflen) {
+    if (!buf || buflen == 0) return MOBGT_ERR_NULL;
+    strncpy(buf, mobgt::g_err, buflen - 1);
+    buf[buflen - 1] = 0;
+    return MOBGT_OK;
+}
+
+extern "C" int32_t mobgt_device_check(void) {
+    int dev = 0;
+    MOBGT_CUDA_OK(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    MOBGT_CUDA_OK(cudaGetDeviceProperties(&p, dev));
+    MOBGT_REQUIRE(p.major == 10, MOBGT_ERR_CUDA, "libmobgt is built for sm_100a only; device is sm_%d%d", p.major,
+                  p.minor);
+    return MOBGT_OK;
+}

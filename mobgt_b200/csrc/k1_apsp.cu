@@ -1,0 +1,416 @@
+// K1 — batched all-pairs shortest paths + path-edge extraction (sm_100a).
+//
+// Replaces the reference's Cython preprocessing, bit-exactly:
+//   algos.floyd_warshall   /root/reference/graphormer/algos.pyx:9-54
+//   algos.get_all_edges    algos.pyx:57-62
+//   algos.gen_edge_input   algos.pyx:65-96
+// as driven by preprocess_item (wrapper.py:42-61,99) and sliced by the collators
+// (collator.py:323).
+//
+// Design:
+//   * one thread-block CLUSTER per graph; the cluster's C CTAs (C = 1,2,4,8) each own a
+//     slice of W columns of the n x n state, kept in shared memory as packed uint16
+//     (M = distance, X = next-hop; optionally P = the reference's `path` matrix);
+//   * Floyd-Warshall runs k strictly ascending (the reference's relaxation order decides
+//     `path`, algos.pyx:35-45); inside one k the n*n relaxations are order-free because row k
+//     and column k are fixed points of step k (M[k][k] == 0, strict '>');
+//     column k of M and X is broadcast to every CTA through distributed shared memory by the
+//     thread that just relaxed it, so a step costs ONE (cluster) barrier;
+//   * 8 cells per 128-bit shared-memory access, 2 cells per ALU op (__vminu2/__vcmpltu2);
+//   * the reference's recursive in-order expansion get_all_edges(i,j) is replaced by the
+//     next-hop matrix X maintained inside FW:  X[i][j] = j initially, X[i][j] = X[i][k] on a
+//     strict improvement through k != 0 (k == 0 leaves X alone: this reproduces the reference's
+//     "path == 0 means direct" short-circuit, algos.pyx:59-60).  DESIGN.md proves that
+//     walking cur = X[cur][j] emits exactly the reference's hop sequence;
+//   * the walk writes only the first `hops` hop slots (collator.py:323 slices the rest away),
+//     staged per warp in shared memory and stored as coalesced 32-bit words.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace mobgt {
+
+struct K1Params {
+    const uint8_t *feat;
+    const int32_t *n;
+    const int64_t *sq_off;
+    const int32_t *gids;
+    int hops;
+    int shift;
+    int16_t *dist;
+    int16_t *path;
+    uint8_t *edge_in;
+    int32_t *maxdist;
+};
+
+constexpr uint32_t kInf = MOBGT_UNREACHABLE;
+constexpr uint16_t kNoWalk = 0xFFFFu;
+
+__device__ __forceinline__ uint32_t pick16(const uint4 &v, int e) {
+    const int w = e >> 1;
+    const uint32_t x = (w == 0) ? v.x : (w == 1) ? v.y : (w == 2) ? v.z : v.w;
+    return (e & 1) ? (x >> 16) : (x & 0xFFFFu);
+}
+
+// one packed relaxation of 2 cells: returns the "strictly improved" half-word mask
+__device__ __forceinline__ uint32_t relax2(uint32_t &m, uint32_t rk, uint32_t mik2) {
+    const uint32_t cost = rk + mik2;  // halves are <= 1020: no carry across the half-word boundary
+    const uint32_t lt = __vcmpltu2(cost, m);
+    m = __vminu2(m, cost);
+    return lt;
+}
+
+__host__ __device__ inline int k1_W(int n, int C) { return round_up(ceil_div(n, C), 8); }
+
+__host__ inline size_t k1_smem_bytes(int n, int C, bool with_path, int nthreads, int hops) {
+    const int W = k1_W(n, C);
+    const int n8 = round_up(n, 8);
+    size_t b = (size_t)n * W * 2 * (with_path ? 3 : 2);
+    b += (size_t)4 * n8 * 2;                       // colM[2][n8], colX[2][n8]
+    b += (size_t)(nthreads / 32) * 32 * hops;      // per-warp walk staging
+    return b + 16;
+}
+
+template <bool WITH_PATH>
+__global__ void __launch_bounds__(512) k1_apsp_kernel(const K1Params p, const int C) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (C > 1) ? (int)cluster.block_rank() : 0;
+    const int gl = blockIdx.x / C;
+    const int g = p.gids ? p.gids[gl] : gl;
+    const int n = p.n[g];
+    const int64_t off = p.sq_off[g];
+    const int W = k1_W(n, C);
+    const int c0 = crank * W;
+    const int wc = max(0, min(W, n - c0));  // valid columns owned by this CTA
+    const int n8 = round_up(n, 8);
+    const int cpr = W >> 3;  // 8-cell chunks per row
+    const int tid = threadIdx.x, NT = blockDim.x;
+
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint16_t *Msh = reinterpret_cast<uint16_t *>(smem_raw);
+    uint16_t *Xsh = Msh + (size_t)n * W;
+    uint16_t *Psh = Xsh + (size_t)n * W;
+    uint16_t *colM = WITH_PATH ? (Psh + (size_t)n * W) : Psh;  // [2][n8]
+    uint16_t *colX = colM + 2 * n8;                             // [2][n8]
+    uint8_t *stage = reinterpret_cast<uint8_t *>(colX + 2 * n8);
+
+    const uint8_t *feat = p.feat + off;
+    const int ntask = n * cpr;
+
+    // ---- init (algos.pyx:27-32): diag 0, edge 1, else 510; X[i][j] = j; P = 0 ----------------
+    for (int t = tid; t < ntask; t += NT) {
+        const int i = t / cpr, q = t - i * cpr;
+        uint32_t mw[4], xw[4];
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+            uint32_t mm[2], xx[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = c0 + q * 8 + e2 * 2 + h;
+                uint32_t m = kInf;
+                if (j < n) {
+                    const uint8_t f = __ldg(feat + (size_t)i * n + j);
+                    m = (i == j) ? 0u : (f ? 1u : kInf);
+                }
+                mm[h] = m;
+                xx[h] = (uint32_t)j & 0xFFFFu;
+            }
+            mw[e2] = mm[0] | (mm[1] << 16);
+            xw[e2] = xx[0] | (xx[1] << 16);
+        }
+        *reinterpret_cast<uint4 *>(Msh + (size_t)i * W + q * 8) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+        *reinterpret_cast<uint4 *>(Xsh + (size_t)i * W + q * 8) = make_uint4(xw[0], xw[1], xw[2], xw[3]);
+        if (WITH_PATH) *reinterpret_cast<uint4 *>(Psh + (size_t)i * W + q * 8) = make_uint4(0, 0, 0, 0);
+    }
+    // column 0 of M and X for step k = 0: every CTA derives it from the input itself
+    for (int i = tid; i < n; i += NT) {
+        const uint8_t f = __ldg(feat + (size_t)i * n);
+        colM[i] = (uint16_t)((i == 0) ? 0u : (f ? 1u : kInf));
+        colX[i] = 0;
+    }
+    if (C > 1) cluster.sync(); else __syncthreads();
+
+    // ---- Floyd-Warshall, k strictly ascending (algos.pyx:35-45) ---------------------------------
+    const int dr = NT / cpr, dq = NT - dr * cpr;
+    const int i0 = tid / cpr, q0 = tid - i0 * cpr;
+    for (int k = 0; k < n; ++k) {
+        const uint16_t *cM = colM + (k & 1) * n8;
+        const uint16_t *cX = colX + (k & 1) * n8;
+        const int nb = ((k + 1) & 1) * n8;
+        const int kn = k + 1;
+        const bool own_next = (kn < n) && (kn >= c0) && (kn < c0 + W);
+        const int qn = own_next ? ((kn - c0) >> 3) : -1;
+        const int en = (kn - c0) & 7;
+        const uint32_t k2 = (uint32_t)k * 0x10001u;
+        const uint16_t *rowk = Msh + (size_t)k * W;
+
+        int i = i0, q = q0;
+        for (int t = tid; t < ntask; t += NT) {
+            const uint32_t mik = cM[i];
+            const bool pub = (q == qn);
+            if (mik < kInf || pub) {
+                uint16_t *mp = Msh + (size_t)i * W + q * 8;
+                uint16_t *xp = Xsh + (size_t)i * W + q * 8;
+                uint4 m4 = *reinterpret_cast<const uint4 *>(mp);
+                uint4 x4;
+                bool have_x = false;
+                if (mik < kInf) {
+                    const uint4 r4 = *reinterpret_cast<const uint4 *>(rowk + q * 8);
+                    const uint32_t mik2 = mik * 0x10001u;
+                    const uint32_t l0 = relax2(m4.x, r4.x, mik2);
+                    const uint32_t l1 = relax2(m4.y, r4.y, mik2);
+                    const uint32_t l2 = relax2(m4.z, r4.z, mik2);
+                    const uint32_t l3 = relax2(m4.w, r4.w, mik2);
+                    if (l0 | l1 | l2 | l3) {
+                        *reinterpret_cast<uint4 *>(mp) = m4;
+                        if (k != 0) {  // k == 0: path stays 0 == "direct" (algos.pyx:59-60) -> X untouched
+                            x4 = *reinterpret_cast<const uint4 *>(xp);
+                            const uint32_t xik2 = (uint32_t)cX[i] * 0x10001u;
+                            x4.x = (x4.x & ~l0) | (xik2 & l0);
+                            x4.y = (x4.y & ~l1) | (xik2 & l1);
+                            x4.z = (x4.z & ~l2) | (xik2 & l2);
+                            x4.w = (x4.w & ~l3) | (xik2 & l3);
+                            *reinterpret_cast<uint4 *>(xp) = x4;
+                            have_x = true;
+                            if (WITH_PATH) {
+                                uint16_t *pp = Psh + (size_t)i * W + q * 8;
+                                uint4 p4 = *reinterpret_cast<const uint4 *>(pp);
+                                p4.x = (p4.x & ~l0) | (k2 & l0);
+                                p4.y = (p4.y & ~l1) | (k2 & l1);
+                                p4.z = (p4.z & ~l2) | (k2 & l2);
+                                p4.w = (p4.w & ~l3) | (k2 & l3);
+                                *reinterpret_cast<uint4 *>(pp) = p4;
+                            }
+                        }
+                    }
+                }
+                if (pub) {  // broadcast column k+1 (post-step-k values) to every CTA of the cluster
+                    if (!have_x) x4 = *reinterpret_cast<const uint4 *>(xp);
+                    const uint16_t mv = (uint16_t)pick16(m4, en);
+                    const uint16_t xv = (uint16_t)pick16(x4, en);
+                    if (C > 1) {
+                        for (int r = 0; r < C; ++r) {
+                            cluster.map_shared_rank(colM, r)[nb + i] = mv;
+                            cluster.map_shared_rank(colX, r)[nb + i] = xv;
+                        }
+                    } else {
+                        colM[nb + i] = mv;
+                        colX[nb + i] = xv;
+                    }
+                }
+            }
+            q += dq;
+            i += dr;
+            if (q >= cpr) { q -= cpr; ++i; }
+        }
+        if (C > 1) cluster.sync(); else __syncthreads();
+    }
+
+    // ---- finalize (algos.pyx:48-52) + dist / path / maxdist outputs -----------------------------
+    int local_max = 0;
+    for (int t = tid; t < ntask; t += NT) {
+        const int i = t / cpr, q = t - i * cpr;
+        const uint4 m4 = *reinterpret_cast<const uint4 *>(Msh + (size_t)i * W + q * 8);
+        uint4 x4 = *reinterpret_cast<const uint4 *>(Xsh + (size_t)i * W + q * 8);
+        uint4 p4 = make_uint4(0, 0, 0, 0);
+        if (WITH_PATH) p4 = *reinterpret_cast<const uint4 *>(Psh + (size_t)i * W + q * 8);
+        uint32_t xo[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int j = c0 + q * 8 + e;
+            const uint32_t m = pick16(m4, e);
+            const bool unreach = (m >= kInf) || (j >= n);
+            if (unreach || i == j) {
+                xo[e >> 1] |= (e & 1) ? 0xFFFF0000u : 0x0000FFFFu;  // kNoWalk
+            }
+            if (j < n) {
+                const size_t o = (size_t)off + (size_t)i * n + j;
+                p.dist[o] = (int16_t)(m + p.shift);
+                if (WITH_PATH) p.path[o] = (int16_t)(unreach ? kInf : pick16(p4, e));
+                local_max = max(local_max, (int)m);
+            }
+        }
+        *reinterpret_cast<uint4 *>(Xsh + (size_t)i * W + q * 8) = make_uint4(xo[0], xo[1], xo[2], xo[3]);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, s));
+    if ((tid & 31) == 0 && ntask > 0) atomicMax(p.maxdist + g, local_max);
+    __syncthreads();
+
+    // ---- walk: first `hops` hops of the reference's in-order expansion (algos.pyx:85-94) -----
+    if (p.edge_in != nullptr && wc > 0) {
+        const int hops = p.hops;
+        const int lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+        uint8_t *st = stage + (size_t)warp * 32 * hops;
+        const uint32_t none4 = (uint32_t)((p.shift - 1) & 0xFF) * 0x01010101u;
+        const int hopw = hops >> 2;
+        const int ngrp = ceil_div(wc, 32);
+        const int nwt = n * ngrp;
+        for (int wt = warp; wt < nwt; wt += nwarps) {
+            const int i = wt / ngrp, cgp = wt - i * ngrp;
+            const int jl = cgp * 32 + lane;
+            const int j = c0 + jl;
+            uint32_t *stw = reinterpret_cast<uint32_t *>(st) + lane * hopw;
+            for (int w = 0; w < hopw; ++w) stw[w] = none4;
+            if (jl < wc && Xsh[(size_t)i * W + jl] != kNoWalk) {
+                int cur = i;
+                for (int h = 0; h < hops; ++h) {
+                    const int nx = Xsh[(size_t)cur * W + jl];
+                    st[lane * hops + h] = (uint8_t)(__ldg(feat + (size_t)cur * n + nx) + p.shift);
+                    cur = nx;
+                    if (cur == j) break;
+                }
+            }
+            __syncwarp();
+            const int npair = min(32, wc - cgp * 32);
+            const int nwords = npair * hopw;
+            uint32_t *dst = reinterpret_cast<uint32_t *>(p.edge_in + ((size_t)off + (size_t)i * n + c0 + cgp * 32) * hops);
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(st);
+            for (int w = lane; w < nwords; w += 32) dst[w] = src[w];
+            __syncwarp();
+        }
+    }
+}
+
+// Stand-alone gen_edge_input from a floyd_warshall `path` matrix: hop h+1 of (cur -> j) is found
+// by the leftmost descent of the reference's recursion (algos.pyx:57-62): t = j; while path[cur][t]
+// != 0: t = path[cur][t].  One thread per ordered pair; not a hot path (API mirror).
+__global__ void k1_walk_from_path_kernel(const int16_t *__restrict__ path, const uint8_t *__restrict__ feat,
+                                         const int32_t *__restrict__ n_arr, const int64_t *__restrict__ sq_off,
+                                         int hops, int shift, uint8_t *__restrict__ edge_in) {
+    const int g = blockIdx.y;
+    const int n = n_arr[g];
+    const int64_t off = sq_off[g];
+    const uint8_t none = (uint8_t)(shift - 1);
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n * n; c += gridDim.x * blockDim.x) {
+        const int i = c / n, j = c - i * n;
+        uint8_t *out = edge_in + ((size_t)off + c) * hops;
+        int h = 0;
+        const int pij = path[off + c];
+        if (i != j && pij != (int)kInf) {
+            int cur = i;
+            for (; h < hops; ++h) {
+                int t = j;
+                for (int guard = 0; guard < n; ++guard) {
+                    const int k = path[off + (size_t)cur * n + t];
+                    if (k == 0) break;
+                    t = k;
+                }
+                out[h] = (uint8_t)(feat[off + (size_t)cur * n + t] + shift);
+                cur = t;
+                if (cur == j) { ++h; break; }
+            }
+        }
+        for (; h < hops; ++h) out[h] = none;
+    }
+}
+
+// in_degree = row sums, out_degree = column sums of the bool adjacency (wrapper.py:97-98).
+__global__ void k1_degree_kernel(const uint8_t *__restrict__ feat, const int32_t *__restrict__ n_arr,
+                                 const int64_t *__restrict__ sq_off, const int64_t *__restrict__ node_off, int shift,
+                                 int16_t *__restrict__ in_deg, int16_t *__restrict__ out_deg) {
+    const int g = blockIdx.x;
+    const int n = n_arr[g];
+    const uint8_t *f = feat + sq_off[g];
+    const int64_t no = node_off[g];
+    for (int v = threadIdx.x; v < n; v += blockDim.x) {
+        int r = 0, c = 0;
+        for (int u = 0; u < n; ++u) {
+            r += f[(size_t)v * n + u] != 0;
+            c += f[(size_t)u * n + v] != 0;
+        }
+        in_deg[no + v] = (int16_t)(r + shift);
+        out_deg[no + v] = (int16_t)(c + shift);
+    }
+}
+
+static int pick_cluster(int n, bool with_path, int hops, int *nthreads_out, size_t *smem_out) {
+    for (int C = 1; C <= 8; C *= 2) {
+        const int W = k1_W(n, C);
+        const int ntask = n * (W / 8);
+        const int nt = ntask <= 32 ? 32 : ntask <= 128 ? 64 : ntask <= 512 ? 128 : ntask <= 2048 ? 256 : 512;
+        const size_t sm = k1_smem_bytes(n, C, with_path, nt, hops);
+        if (sm <= 200 * 1024) {
+            *nthreads_out = nt;
+            *smem_out = sm;
+            return C;
+        }
+    }
+    return -1;
+}
+
+}  // namespace mobgt
+
+using namespace mobgt;
+
+extern "C" int32_t mobgt_apsp_edge_input(const uint8_t *feat, const int32_t *n, const int64_t *sq_off,
+                                         const int32_t *gids, int32_t G_launch, int32_t n_max_host, int32_t hops,
+                                         int32_t shift, int16_t *dist, int16_t *path, uint8_t *edge_in,
+                                         int32_t *maxdist, void *stream) {
+    MOBGT_REQUIRE(feat && n && sq_off && dist && maxdist, MOBGT_ERR_NULL, "mobgt_apsp_edge_input: null pointer");
+    MOBGT_REQUIRE(G_launch >= 0, MOBGT_ERR_BAD_SHAPE, "mobgt_apsp_edge_input: G_launch=%d", G_launch);
+    MOBGT_REQUIRE(n_max_host >= 1 && n_max_host <= MOBGT_MAX_NODES, MOBGT_ERR_BAD_SHAPE,
+                  "mobgt_apsp_edge_input: n_max=%d outside [1,%d]", n_max_host, MOBGT_MAX_NODES);
+    MOBGT_REQUIRE(shift == 0 || shift == 1, MOBGT_ERR_BAD_SHAPE, "mobgt_apsp_edge_input: shift must be 0 or 1");
+    if (edge_in) {
+        MOBGT_REQUIRE(hops >= 4 && hops <= MOBGT_MAX_HOPS && hops % 4 == 0, MOBGT_ERR_UNSUPPORTED,
+                      "mobgt_apsp_edge_input: hops=%d must be a multiple of 4 in [4,%d]", hops, MOBGT_MAX_HOPS);
+    } else {
+        hops = 4;
+    }
+    if (G_launch == 0) return MOBGT_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool with_path = path != nullptr;
+    int nt = 0;
+    size_t smem = 0;
+    const int C = pick_cluster(n_max_host, with_path, hops, &nt, &smem);
+    MOBGT_REQUIRE(C > 0, MOBGT_ERR_UNSUPPORTED, "mobgt_apsp_edge_input: no shared-memory plan for n=%d", n_max_host);
+
+    K1Params p{feat, n, sq_off, gids, hops, shift, dist, path, edge_in, maxdist};
+    auto kern = with_path ? k1_apsp_kernel<true> : k1_apsp_kernel<false>;
+    MOBGT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)G_launch * C);
+    cfg.blockDim = dim3(nt);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MOBGT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p, C));
+    return MOBGT_OK;
+}
+
+extern "C" int32_t mobgt_gen_edge_input(const int16_t *path, const uint8_t *feat, const int32_t *n,
+                                        const int64_t *sq_off, int32_t G, int32_t n_max_host, int32_t hops,
+                                        int32_t shift, uint8_t *edge_in, void *stream) {
+    MOBGT_REQUIRE(path && feat && n && sq_off && edge_in, MOBGT_ERR_NULL, "mobgt_gen_edge_input: null pointer");
+    MOBGT_REQUIRE(hops >= 1 && hops <= MOBGT_UNREACHABLE, MOBGT_ERR_BAD_SHAPE, "mobgt_gen_edge_input: hops=%d", hops);
+    MOBGT_REQUIRE(n_max_host >= 1 && n_max_host <= MOBGT_MAX_NODES, MOBGT_ERR_BAD_SHAPE,
+                  "mobgt_gen_edge_input: n_max=%d", n_max_host);
+    if (G <= 0) return MOBGT_OK;
+    const int cells = n_max_host * n_max_host;
+    dim3 grid((unsigned)min(64, ceil_div(cells, 256)), (unsigned)G);
+    k1_walk_from_path_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(path, feat, n, sq_off, hops, shift,
+                                                                                 edge_in);
+    MOBGT_LAUNCH_OK("k1_walk_from_path_kernel");
+    return MOBGT_OK;
+}
+
+extern "C" int32_t mobgt_degrees(const uint8_t *feat, const int32_t *n, const int64_t *sq_off,
+                                 const int64_t *node_off, int32_t G, int32_t shift, int16_t *in_degree,
+                                 int16_t *out_degree, void *stream) {
+    MOBGT_REQUIRE(feat && n && sq_off && node_off && in_degree && out_degree, MOBGT_ERR_NULL,
+                  "mobgt_degrees: null pointer");
+    if (G <= 0) return MOBGT_OK;
+    k1_degree_kernel<<<G, 128, 0, static_cast<cudaStream_t>(stream)>>>(feat, n, sq_off, node_off, shift, in_degree,
+                                                                      out_degree);
+    MOBGT_LAUNCH_OK("k1_degree_kernel");
+    return MOBGT_OK;
+}
