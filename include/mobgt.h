@@ -87,6 +87,64 @@ int32_t mobgt_degrees(const uint8_t *feat, const int32_t *n, const int64_t *sq_o
                       const int64_t *node_off, int32_t G, int32_t shift,
                       int16_t *in_degree, int16_t *out_degree, void *stream);
 
+/* poi_pos (collator.py:428-437): distance bin 1..num_bins-1 between the POIs of every ordered node pair, from a
+ * device-resident [P,2] coordinate table (stand-in for the reference's P x P distance pickle + np.digitize).
+ * x i32 [sum n] = 1-based POI id per packed node; poi_pos i16 [sum n^2]. */
+int32_t mobgt_poi_pos(const int32_t *x, const int32_t *n, const int64_t *sq_off, const int64_t *node_off,
+                      const float *latlon, float dist_max, int32_t num_bins, int32_t G, int32_t n_max_host,
+                      int16_t *poi_pos, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2 — attention-bias build.  Replaces model_fqandtoyo.py:1143-1216 (fp32 statement model.py:126-190).
+ * Packed index inputs as written by K1 with shift = 1 (rel_pos = M+1, edge_in = e+1) plus
+ * poi_pos (collator.py:428-437), all per ordered node pair of each graph.
+ *   bias [B,H,T,Tp] (f32 or bf16; Tp = row pitch, multiple of 8): only rows/cols < n[g]+1 are written;
+ *   padding columns are masked inside the attention kernel from the sequence lengths.
+ *   tables: R [512,H] rel_pos_encoder, Ppos [bins,H] poi_pos_encoder, E [128,H] edge_encoder,
+ *           W [>=hops*H*H] edge_dis_encoder (viewed [k,h',h]), tvd [H] graph_token_virtual_distance.
+ *   workspace: hops*128*H floats (the E.W table; also the dEW scratch of the backward).
+ * Backward: dBias f32 [B,H,T,Tp] (sum over layers) -> dR [512,H], dPpos [bins,H], dE [128,H],
+ * dW [hops*H*H], dtvd [H]  (all overwritten).
+ * ------------------------------------------------------------------------------------------ */
+int32_t mobgt_bias_fwd(const int32_t *n, const int64_t *sq_off, const int16_t *rel_pos, const int16_t *poi_pos,
+                       const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t H,
+                       int32_t rel_pos_max, const float *R, const float *Ppos, const float *E, const float *W,
+                       const float *tvd, void *workspace, void *out, int32_t out_dtype, void *stream);
+int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const int16_t *rel_pos, const int16_t *poi_pos,
+                       const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t H,
+                       int32_t rel_pos_max, int32_t num_bins, const float *dBias, const float *E, const float *W,
+                       void *workspace, float *dR, float *dPpos, float *dE, float *dW, float *dtvd, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3 — biased multi-head attention (tcgen05 / TMEM / TMA).  Replaces the core of
+ * MultiHeadAttention.forward, model_fqandtoyo.py:1693-1706, for packed var-len graphs:
+ * graph g owns token rows tok_off[g]..tok_off[g+1] (row 0 = graph token).  head dim is 24.
+ *   q,k,v  bf16 [ntok, H*24] with a common row stride (elements) — usually slices of one fused projection
+ *   bias   bf16 [B,H,T,Tp] from mobgt_bias_fwd ;  out bf16 [ntok, H*24] ;  lse f32 [ntok, H]
+ * ------------------------------------------------------------------------------------------ */
+int32_t mobgt_attn_fwd(const void *q, const void *k, const void *v, int64_t qkv_row_stride, const void *bias,
+                       const int32_t *tok_off, int32_t B, int32_t H, int32_t ntok, int32_t T, int32_t Tp,
+                       int32_t t_max_host, float scale, void *out, float *lse, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4 — node-embedding gather / sum and the deterministic segmented scatter-add backward.
+ * Replaces model_fqandtoyo.py:1257-1269 (per-node table look-ups) and :1288-1344 (degree encoders,
+ * positional rows, graph token).  Packed nodes / tokens, no padding rows.
+ *   gather: out[v] = Gd[x[v]-1] | Tm[slot[v]] | Gc[cat_of_poi[x[v]-1]-1]   (widths Dp | Dt | Dc)
+ *   sum:    tok[r] = pos==0 ? graph_token + pe[0] : nf[node] + Din[in_deg] + Dout[out_deg] + pe[pos]
+ *   segment_sum: table[key] = sum of src rows with that key, in the order of a stable sort
+ *                (perm, keys_sorted); no atomics -> bitwise reproducible.
+ * ------------------------------------------------------------------------------------------ */
+int32_t mobgt_embed_gather_fwd(const int32_t *x, const int32_t *slot, const int32_t *cat_of_poi, const float *Gd,
+                               const float *Tm, const float *Gc, int32_t nnode, int32_t Dp, int32_t Dt, int32_t Dc,
+                               void *out, int32_t out_dtype, void *stream);
+int32_t mobgt_embed_sum_fwd(const void *nf, const int32_t *tok_graph, const int32_t *tok_pos, const int32_t *in_deg,
+                            const int32_t *out_deg, const float *Din, const float *Dout, const float *pe,
+                            const float *graph_token, int32_t ntok, int32_t D, void *tok, int32_t dtype, void *stream);
+int32_t mobgt_segment_sum(const void *src, int32_t src_dtype, int64_t src_stride, int32_t col0, int32_t D,
+                          const int32_t *perm, const int32_t *keys_sorted, int32_t nrows, float *table, int32_t nkeys,
+                          void *workspace, int64_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Test hooks (tests/test_umma_selftest.py): exercise the tcgen05 / TMA building blocks in isolation.
  * out[128,N] (f32) = A * B, bf16 operands; a_mn / b_mn select MN-major operands

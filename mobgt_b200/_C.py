@@ -25,6 +25,15 @@ SIGNATURES = {
     "mobgt_apsp_edge_input": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p],
     "mobgt_gen_edge_input": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p],
     "mobgt_degrees": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_p, c_p, c_p],
+    "mobgt_poi_pos": [c_p, c_p, c_p, c_p, c_p, c_f32, c_i32, c_i32, c_i32, c_p, c_p],
+    "mobgt_bias_fwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
+                       c_i32, c_p],
+    "mobgt_bias_bwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p,
+                       c_p, c_p, c_p, c_p, c_p],
+    "mobgt_attn_fwd": [c_p, c_p, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_p, c_p, c_p],
+    "mobgt_embed_gather_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],
+    "mobgt_embed_sum_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p],
+    "mobgt_segment_sum": [c_p, c_i32, c_i64, c_i32, c_i32, c_p, c_p, c_i32, c_p, c_i32, c_p, c_i64, c_p],
     "mobgt_selftest_umma": [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p],
 }
 

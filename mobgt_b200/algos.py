@@ -101,8 +101,9 @@ def gen_edge_input(max_dist, path, edge_feat):
     f8 = torch.from_numpy(np.ascontiguousarray(edge_feat[..., 0], dtype=np.uint8).reshape(-1)).cuda()
     nn, sq, _ = pack_graphs([n])
     e = torch.empty((n * n, max_dist), dtype=torch.uint8, device="cuda")
-    _C.call("mobgt_gen_edge_input", _C.ptr(p16), _C.ptr(f8), _C.ptr(torch.from_numpy(nn).cuda()),
-            _C.ptr(torch.from_numpy(sq).cuda()), 1, n, max_dist, 0, _C.ptr(e), _C.stream_ptr())
+    n_dev, sq_dev = torch.from_numpy(nn).cuda(), torch.from_numpy(sq).cuda()   # keep alive across the call
+    _C.call("mobgt_gen_edge_input", _C.ptr(p16), _C.ptr(f8), _C.ptr(n_dev), _C.ptr(sq_dev), 1, n, max_dist, 0,
+            _C.ptr(e), _C.stream_ptr())
     raw = e.cpu().numpy()
     out = raw.astype(np.float32)
     out[raw == 255] = -1.0          # 255 == (uint8)(-1): "no hop"

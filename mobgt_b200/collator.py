@@ -1,0 +1,216 @@
+"""Collation: raw dataset items -> `Batch1`, the reference's batch type (collator.py:149-215), B200-first.
+
+The reference's POI collators (collator_foursquare / _gowalla / _toyota, collator.py:310-748) run Floyd-Warshall and
+the path walk per item on the CPU, pad everything to the batch maximum as int64, and loop over node pairs in
+Python.  Here the host only packs the raw edge lists; the per-pair work runs on the GPU through libmobgt
+(K1 + poi_pos), and the batch keeps COMPACT PACKED device tensors (i16 / u8, no padding).  Every reference field
+name (`rel_pos` (= `spatial_pos`), `edge_input`, `attn_bias`, `attn_edge_type`, `in_degree`, `out_degree`, `x`, `y`,
+`adj`, `adj1`, `time`, `time_normal`, `user`, `cat`, `poi_pos`, `idx`) is still available: it is materialised on
+first access with the reference's dtype, shape, "+1" shifts and -inf padding columns.
+`feature_matrix` (the Laplacian eigenvectors of collator.py:394-410) is never read by the reference forward and
+is not produced (None).
+"""
+import numpy as np
+import torch
+
+from . import _C
+from .algos import apsp_edge_input_packed
+
+
+def _to_np(a, dtype=None):
+    if isinstance(a, torch.Tensor):
+        a = a.cpu().numpy()
+    a = np.asarray(a)
+    return a.astype(dtype) if dtype is not None else a
+
+
+class Batch1:
+    """Same public surface as collator.py:149-215 (attributes, .to(device), len()); packed storage inside."""
+
+    _REF_FIELDS = ("attn_bias", "attn_edge_type", "rel_pos", "spatial_pos", "in_degree", "out_degree", "x",
+                   "edge_input", "adj", "adj1", "time", "time_normal", "cat", "poi_pos")
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+        self.feature_matrix = None
+        self._dense = {}
+
+    def __len__(self):
+        return int(self.B)
+
+    def to(self, device):
+        dev = torch.device(device)
+        for k, v in list(self.__dict__.items()):
+            if isinstance(v, torch.Tensor) and v.device != dev:
+                self.__dict__[k] = v.to(dev, non_blocking=True)
+        self._dense = {k: v.to(dev) for k, v in self._dense.items()}
+        return self
+
+    # ---- reference-shaped dense views (materialised lazily) ---------------------------------------
+    def __getattr__(self, name):
+        if name in Batch1._REF_FIELDS:
+            d = self.__dict__.setdefault("_dense", {})
+            if name not in d:
+                d[name] = self._materialise(name)
+            return d[name]
+        raise AttributeError(name)
+
+    def _sq_index(self):
+        """(g, i, j) of every packed cell, as device int64 tensors."""
+        if "_sqidx" not in self.__dict__:
+            n = self.n.long()
+            cells = n * n
+            g = torch.repeat_interleave(torch.arange(self.B, device=n.device), cells)
+            local = torch.arange(int(cells.sum()), device=n.device) - self.sq_off[:-1][g]
+            self.__dict__["_sqidx"] = (g, local // n[g], local % n[g])
+        return self.__dict__["_sqidx"]
+
+    def _node_index(self):
+        if "_nidx" not in self.__dict__:
+            n = self.n.long()
+            g = torch.repeat_interleave(torch.arange(self.B, device=n.device), n)
+            q = torch.arange(int(n.sum()), device=n.device) - self.node_off[:-1][g]
+            self.__dict__["_nidx"] = (g, q)
+        return self.__dict__["_nidx"]
+
+    def _materialise(self, name):
+        B, N, dev = self.B, self.N, self.n.device
+        if name in ("rel_pos", "spatial_pos", "poi_pos"):
+            src = self.rel_pos16 if name != "poi_pos" else self.poi_pos16
+            out = torch.zeros(B, N, N, dtype=torch.long, device=dev)
+            g, i, j = self._sq_index()
+            out[g, i, j] = src.long()
+            return out
+        if name == "edge_input":
+            # hop axis = min(multi_hop_max_dist, max_g max(M_g))  (collator.py:323,366)
+            dmax = int(min(self.hops, int(self.maxdist.max()))) if B else 0
+            out = torch.zeros(B, N, N, dmax, 1, dtype=torch.long, device=dev)
+            g, i, j = self._sq_index()
+            out[g, i, j] = self.edge_in8[:, :dmax].long().unsqueeze(-1)
+            return out
+        if name == "attn_edge_type":
+            out = torch.zeros(B, N + 1, N + 1, 1, dtype=torch.long, device=dev)
+            g, i, j = self._sq_index()
+            out[g, i, j, 0] = self.feat8.long()
+            return out
+        if name in ("adj", "adj1"):
+            T = N + 1 if name == "adj" else N
+            out = torch.zeros(B, T, T, dtype=torch.bool, device=dev)
+            g, i, j = self._sq_index()
+            out[g, i, j] = self.feat8 != 0
+            if name == "adj":          # wrapper.py:79-81: the virtual token row/col sits at index n_g
+                ar = torch.arange(B, device=dev)
+                n = self.n.long()
+                for gi in range(B):
+                    out[gi, n[gi], :n[gi] + 1] = True
+                    out[gi, :n[gi] + 1, n[gi]] = True
+                del ar
+            return out
+        if name == "attn_bias":
+            T = N + 1
+            out = torch.zeros(B, T, T, dtype=torch.float, device=dev)
+            col = torch.arange(T, device=dev).view(1, 1, T)
+            out.masked_fill_(col > self.n.long().view(B, 1, 1), float("-inf"))            # collator.py:57-64
+            if self.rel_pos_max <= 510:
+                g, i, j = self._sq_index()
+                m = (self.rel_pos16.long() - 1) >= self.rel_pos_max                      # collator.py:354-358
+                out[g[m], i[m] + 1, j[m] + 1] = float("-inf")
+            return out
+        g, q = self._node_index()
+        if name in ("in_degree", "out_degree"):
+            out = torch.zeros(B, N, dtype=torch.long, device=dev)
+            out[g, q] = (self.in_deg if name == "in_degree" else self.out_deg).long()
+            return out
+        if name in ("x", "time", "cat"):
+            src = {"x": self.x_nodes, "time": self.time_nodes, "cat": self.cat_nodes}[name]
+            out = torch.zeros(B, N, 1, dtype=torch.long, device=dev)
+            out[g, q, 0] = src.long()
+            return out
+        if name == "time_normal":
+            out = torch.zeros(B, N, 1, dtype=torch.float, device=dev)
+            out[g, q, 0] = self.time_normal_nodes
+            return out
+        raise AttributeError(name)
+
+
+def collate_packed(items, world=None, latlon_dev=None, max_node=512, multi_hop_max_dist=20, rel_pos_max=1024,
+                   device="cuda", want_path=False):
+    """Shared body of the three POI collators.  items: raw dataset items (owndata.py:340-349 fields; numpy or
+    torch).  Returns a device-resident Batch1."""
+    _C.require_cuda()
+    items = [it for it in items if it is not None and len(_to_np(it.x)) <= max_node]     # collator.py:313
+    B = len(items)
+    ns = np.array([len(_to_np(it.x)) for it in items], np.int32)
+    sq = np.zeros(B + 1, np.int64)
+    np.cumsum(ns.astype(np.int64) ** 2, out=sq[1:])
+    no = np.zeros(B + 1, np.int64)
+    np.cumsum(ns.astype(np.int64), out=no[1:])
+    Nn, cells = int(no[-1]), int(sq[-1])
+    feat = np.zeros(cells, np.uint8)
+    indeg = np.zeros(Nn, np.int32)
+    outdeg = np.zeros(Nn, np.int32)
+    for g, it in enumerate(items):
+        ei = _to_np(it.edge_index, np.int64)
+        ea = _to_np(it.edge_attr, np.int64).reshape(-1)
+        n = int(ns[g])
+        feat[sq[g] + ei[0] * n + ei[1]] = ea + 2          # wrapper.py:49-53: convert_to_single_emb(+1) then +1
+        indeg[no[g]:no[g + 1]] = np.bincount(ei[0], minlength=n)    # wrapper.py:97: adj.sum(dim=1)
+        outdeg[no[g]:no[g + 1]] = np.bincount(ei[1], minlength=n)   # wrapper.py:98: adj.sum(dim=0)
+    x_nodes = np.concatenate([_to_np(it.x, np.int64).reshape(-1) for it in items]).astype(np.int32)
+    tn = np.concatenate([_to_np(it.time_normal, np.float32).reshape(-1) for it in items])
+    time_nodes = np.concatenate([_to_np(it.time, np.int64).reshape(-1) for it in items]).astype(np.int32)
+    cat_nodes = np.concatenate([_to_np(it.cat, np.int64).reshape(-1) for it in items]).astype(np.int32)
+    slot = (tn * np.float32(48)).astype(np.int64).astype(np.int32)          # model_fqandtoyo.py:1262
+    user = np.array([int(_to_np(it.user).reshape(-1)[0]) + 1 for it in items], np.int64).reshape(B, 1)   # wrapper.py:39
+    y = np.array([int(_to_np(it.y).reshape(-1)[0]) for it in items], np.int64)                           # collator.py:367
+    idx = np.array([int(getattr(it, "idx", i)) for i, it in enumerate(items)], np.int64)
+    tok_off = (no + np.arange(B + 1)).astype(np.int32)
+    g_of_node = np.repeat(np.arange(B, dtype=np.int32), ns)
+    pos_of_node = (np.arange(Nn) - no[:-1][g_of_node] + 1).astype(np.int32)
+    Ntok = Nn + B
+    tok_graph = np.zeros(Ntok, np.int32)
+    tok_pos = np.zeros(Ntok, np.int32)
+    rows = np.arange(Nn) + g_of_node + 1
+    tok_graph[rows] = g_of_node
+    tok_pos[rows] = pos_of_node
+    tok_graph[tok_off[:-1]] = np.arange(B)
+
+    dev = torch.device(device)
+
+    def up(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().to(dev, non_blocking=True)
+
+    b = Batch1(
+        B=B, N=int(ns.max()) if B else 0, hops=int(multi_hop_max_dist), rel_pos_max=int(rel_pos_max), n_host=ns,
+        n=up(ns), sq_off=up(sq), node_off=up(no), tok_off=up(tok_off), tok_graph=up(tok_graph), tok_pos=up(tok_pos),
+        feat8=up(feat), x_nodes=up(x_nodes), slot=up(slot), time_nodes=up(time_nodes), time_normal_nodes=up(tn),
+        cat_nodes=up(cat_nodes), in_deg=up(indeg + 1), out_deg=up(outdeg + 1),       # pad_1d_unsqueeze "+1" (collator.py:12)
+        user=up(user), y=up(y), idx=up(idx), h2d_bytes=0)
+    b.h2d_bytes = int(sum(v.numel() * v.element_size() for v in b.__dict__.values() if isinstance(v, torch.Tensor)))
+    k1 = apsp_edge_input_packed(b.feat8, b.n, b.sq_off, ns, hops=int(multi_hop_max_dist), shift=1, want_path=want_path)
+    b.rel_pos16, b.edge_in8, b.maxdist, b.path16 = k1["dist"], k1["edge_in"], k1["maxdist"], k1["path"]
+    b.poi_pos16 = torch.empty(cells, dtype=torch.int16, device=dev)
+    if world is not None:
+        if latlon_dev is None:
+            latlon_dev = torch.from_numpy(world.latlon).to(dev)
+        b._latlon = latlon_dev
+        _C.call("mobgt_poi_pos", _C.ptr(b.x_nodes), _C.ptr(b.n), _C.ptr(b.sq_off), _C.ptr(b.node_off), _C.ptr(latlon_dev),
+                float(np.float32(world.dist_max)), int(world.num_bins), B, int(b.N), _C.ptr(b.poi_pos16), _C.stream_ptr())
+    else:
+        b.poi_pos16.fill_(1)
+    return b
+
+
+def collator_foursquare(items, max_node=512, multi_hop_max_dist=20, rel_pos_max=20, world=None, **kw):
+    """collator.py:310-458"""
+    return collate_packed(items, world, None, max_node, multi_hop_max_dist, rel_pos_max, **kw)
+
+
+def collator_gowalla(items, max_node=512, multi_hop_max_dist=20, rel_pos_max=20, world=None, **kw):
+    """collator.py:460-608"""
+    return collate_packed(items, world, None, max_node, multi_hop_max_dist, rel_pos_max, **kw)
+
+
+def collator_toyota(items, max_node=512, multi_hop_max_dist=20, rel_pos_max=20, world=None, **kw):
+    """collator.py:610-748"""
+    return collate_packed(items, world, None, max_node, multi_hop_max_dist, rel_pos_max, **kw)

@@ -222,13 +222,16 @@ __global__ void __launch_bounds__(512) k1_apsp_kernel(const K1Params p, const in
             const int j = c0 + q * 8 + e;
             const uint32_t m = pick16(m4, e);
             const bool unreach = (m >= kInf) || (j >= n);
-            if (unreach || i == j) {
+            // the reference skips a pair when path == 510 (algos.pyx:87-88); for n > 510 that also hits REACHABLE
+            // pairs whose last improving intermediate is node 510 -- reproduced here (P is kept whenever n > 510)
+            const bool skip510 = WITH_PATH && (pick16(p4, e) == kInf);
+            if (unreach || i == j || skip510) {
                 xo[e >> 1] |= (e & 1) ? 0xFFFF0000u : 0x0000FFFFu;  // kNoWalk
             }
             if (j < n) {
                 const size_t o = (size_t)off + (size_t)i * n + j;
                 p.dist[o] = (int16_t)(m + p.shift);
-                if (WITH_PATH) p.path[o] = (int16_t)(unreach ? kInf : pick16(p4, e));
+                if (WITH_PATH && p.path != nullptr) p.path[o] = (int16_t)(unreach ? kInf : pick16(p4, e));
                 local_max = max(local_max, (int)m);
             }
         }
@@ -332,7 +335,7 @@ static int pick_cluster(int n, bool with_path, int hops, int *nthreads_out, size
         const int ntask = n * (W / 8);
         const int nt = ntask <= 32 ? 32 : ntask <= 128 ? 64 : ntask <= 512 ? 128 : ntask <= 2048 ? 256 : 512;
         const size_t sm = k1_smem_bytes(n, C, with_path, nt, hops);
-        if (sm <= 200 * 1024) {
+        if (sm <= 227 * 1024) {
             *nthreads_out = nt;
             *smem_out = sm;
             return C;
@@ -362,7 +365,7 @@ extern "C" int32_t mobgt_apsp_edge_input(const uint8_t *feat, const int32_t *n, 
     }
     if (G_launch == 0) return MOBGT_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const bool with_path = path != nullptr;
+    const bool with_path = path != nullptr || n_max_host > MOBGT_UNREACHABLE;   // see skip510 in the kernel
     int nt = 0;
     size_t smem = 0;
     const int C = pick_cluster(n_max_host, with_path, hops, &nt, &smem);
@@ -412,5 +415,44 @@ extern "C" int32_t mobgt_degrees(const uint8_t *feat, const int32_t *n, const in
     k1_degree_kernel<<<G, 128, 0, static_cast<cudaStream_t>(stream)>>>(feat, n, sq_off, node_off, shift, in_degree,
                                                                       out_degree);
     MOBGT_LAUNCH_OK("k1_degree_kernel");
+    return MOBGT_OK;
+}
+
+// ---- collation helper: pairwise POI distance bin (collator.py:428-437 stand-in for the synthetic world) ----------
+// poi_pos[g,i,j] = 1 + min(int(dist(x_i, x_j) / dist_max * (num_bins-2)), num_bins-2), IEEE round-to-nearest single ops in
+// the same order as the numpy statement in mobgt_b200/synth.py (PoiWorld.poi_pos_bins), so the bins are bit-identical.
+namespace mobgt {
+__global__ void k1_poi_pos_kernel(const int32_t *__restrict__ x, const int32_t *__restrict__ n_arr,
+                                  const int64_t *__restrict__ sq_off, const int64_t *__restrict__ node_off,
+                                  const float *__restrict__ latlon, float dist_max, int num_bins,
+                                  int16_t *__restrict__ out) {
+    const int g = blockIdx.y;
+    const int n = n_arr[g];
+    const int64_t so = sq_off[g], no = node_off[g];
+    const float scale = (float)(num_bins - 2);
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n * n; c += gridDim.x * blockDim.x) {
+        const int i = c / n, j = c - i * n;
+        const int a = x[no + i] - 1, b = x[no + j] - 1;
+        const float dx = __fsub_rn(latlon[2 * a], latlon[2 * b]);
+        const float dy = __fsub_rn(latlon[2 * a + 1], latlon[2 * b + 1]);
+        const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+        const float q = __fmul_rn(__fdiv_rn(d, dist_max), scale);
+        long long bin = (long long)q;
+        if (bin > num_bins - 2) bin = num_bins - 2;
+        out[so + c] = (int16_t)(1 + bin);
+    }
+}
+}  // namespace mobgt
+
+extern "C" int32_t mobgt_poi_pos(const int32_t *x, const int32_t *n, const int64_t *sq_off, const int64_t *node_off,
+                                 const float *latlon, float dist_max, int32_t num_bins, int32_t G, int32_t n_max_host,
+                                 int16_t *poi_pos, void *stream) {
+    MOBGT_REQUIRE(x && n && sq_off && node_off && latlon && poi_pos, MOBGT_ERR_NULL, "mobgt_poi_pos: null pointer");
+    MOBGT_REQUIRE(num_bins >= 3 && dist_max > 0.f && n_max_host >= 1, MOBGT_ERR_BAD_SHAPE, "mobgt_poi_pos: bad arguments");
+    if (G <= 0) return MOBGT_OK;
+    dim3 grid((unsigned)min(64, mobgt::ceil_div(n_max_host * n_max_host, 256)), (unsigned)G);
+    mobgt::k1_poi_pos_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, sq_off, node_off, latlon, dist_max,
+                                                                                 num_bins, poi_pos);
+    MOBGT_LAUNCH_OK("k1_poi_pos_kernel");
     return MOBGT_OK;
 }

@@ -1,0 +1,307 @@
+// K3 (forward) — biased multi-head attention on tcgen05 / TMEM, fed by TMA (sm_100a).
+//
+// Replaces MultiHeadAttention.forward's core, model_fqandtoyo.py:1693-1706:
+//     q = q * scale ; x = q @ k^T + attn_bias ; x = softmax(x, dim=3) ; x = x @ v
+// for PACKED (var-len) graphs: graph g owns token rows tok_off[g] .. tok_off[g+1].  The padding-column
+// mask (the -inf columns of collator.py:57-64) is applied in-tile from the sequence lengths, the bias tile is
+// streamed by TMA, and the scores never touch HBM.
+//
+// One CTA per (graph, head); K and V of the graph stay resident in shared memory.
+//   S  = Q_i K_j^T      tcgen05.mma  M=128, N<=128, K=32 (d=24 zero-padded)      -> TMEM cols [0,128)
+//   P  = softmax tile   tcgen05.ld -> registers (+ bias tile from smem, online max/sum) -> bf16 -> smem
+//   O += P V_j          tcgen05.mma  M=128, N=32, K=kv                             -> TMEM cols [128,160)
+// Operands use the no-swizzle [chunk][row][8] layout of umma.cuh (3-D TMA boxes {8, 128 rows, 3 chunks});
+// the bias tile is two {64 x 128} boxes with the 128-byte TMA swizzle.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace mobgt {
+using namespace sm100;
+
+constexpr int kAttD = 24;        // head dim (192 / 8); padded to 32 for the MMA K / N granularity
+constexpr int kAttChunks = 3;    // 24 / 8
+constexpr int kTile = 128;       // query rows per tile == KV rows per box
+constexpr int kBoxBytes = 4 * kTile * 16;        // [4 chunks][128 rows][16 B]; chunk 3 stays zero
+constexpr int kBoxTxBytes = kAttChunks * kTile * 16;
+constexpr int kBiasTileBytes = 2 * kTile * 128;  // two 64-column halves, 128 B per row
+constexpr int kPBytes = 16 * kTile * 16;         // [16 chunks][128 rows][16 B]
+
+struct AttnFwdParams {
+    const int32_t *tok_off;  // [B+1]
+    __nv_bfloat16 *out;      // [Ntok, H*24]
+    float *lse;              // [Ntok, H]
+    int H;
+    float scale;
+    int max_boxes;           // ceil(Tmax / 128): K/V boxes provisioned in shared memory
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(128, 1)
+k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBias,
+                   const AttnFwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_q, bar_kv, bar_bias, bar_s, bar_o;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int g = blockIdx.x / p.H, h = blockIdx.x - g * p.H;
+    const int t0 = p.tok_off[g];
+    const int Tg = p.tok_off[g + 1] - t0;
+    const int NB = ceil_div(Tg, kTile);
+
+    uint8_t *sBias = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // 32 KB, 1024-aligned (swizzle atom)
+    uint8_t *sP = sBias + kBiasTileBytes;                    // 32 KB
+    uint8_t *sQ = sP + kPBytes;                              // 8 KB
+    uint8_t *sK = sQ + kBoxBytes;                            // max_boxes * 8 KB
+    uint8_t *sV = sK + (size_t)p.max_boxes * kBoxBytes;      // max_boxes * 8 KB
+
+    if (tid == 0) {
+        mbar_init(&bar_q, 1);
+        mbar_init(&bar_kv, 1);
+        mbar_init(&bar_bias, 1);
+        mbar_init(&bar_s, 1);
+        mbar_init(&bar_o, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        tma_prefetch_desc(&tmBias);
+    }
+    // zero the K-padding chunk (d = 24..31) of Q and of every K / V box: 128 rows x 16 B each
+    {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(sQ + 3 * kTile * 16 + tid * 16) = z;
+        for (int b = 0; b < NB; ++b) {
+            *reinterpret_cast<uint4 *>(sK + (size_t)b * kBoxBytes + 3 * kTile * 16 + tid * 16) = z;
+            *reinterpret_cast<uint4 *>(sV + (size_t)b * kBoxBytes + 3 * kTile * 16 + tid * 16) = z;
+        }
+    }
+    if (warp == 0) tmem_alloc<256>(&tmem_slot);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t tS = tmem, tO = tmem + 128;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+
+    if (tid == 0) {
+        mbar_expect_tx(&bar_kv, (uint32_t)(2 * NB * kBoxTxBytes));
+        for (int b = 0; b < NB; ++b) {
+            tma_load_3d(sK + (size_t)b * kBoxBytes, &tmK, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
+            tma_load_3d(sV + (size_t)b * kBoxBytes, &tmV, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
+        }
+    }
+    __syncwarp();
+    uint32_t ph_q = 0, ph_bias = 0, ph_s = 0, ph_o = 0;
+    const float sl2 = p.scale * 1.4426950408889634f;  // scale * log2(e)
+    constexpr float kL2e = 1.4426950408889634f;
+    const int plane = g * p.H + h;
+
+    for (int i = 0; i < NB; ++i) {
+        const int row = i * kTile + tid;       // query row inside the graph
+        const bool row_ok = row < Tg;
+        if (tid == 0) {
+            mbar_expect_tx(&bar_q, kBoxTxBytes);
+            tma_load_3d(sQ, &tmQ, &bar_q, 0, t0 + i * kTile, h * kAttChunks);
+            mbar_expect_tx(&bar_bias, kBiasTileBytes);
+            tma_load_3d(sBias, &tmBias, &bar_bias, 0, i * kTile, plane);
+            tma_load_3d(sBias + kTile * 128, &tmBias, &bar_bias, 64, i * kTile, plane);
+        }
+        __syncwarp();
+        float m_run = -INFINITY, l_run = 0.f;  // running max (in log2 units of the scaled score) and sum
+        for (int j = 0; j < NB; ++j) {
+            const int kv_valid = min(kTile, Tg - j * kTile);    // valid key columns in this block
+            const int nb = round_up(kv_valid, 16);              // MMA N / K extent
+            if (tid == 0) {
+                if (j == 0) {
+                    mbar_wait(&bar_q, ph_q);
+                    if (i == 0) mbar_wait(&bar_kv, 0);
+                }
+                tc_fence_after();
+                const uint32_t idesc = make_idesc_bf16(kTile, nb, 0, 0);
+                const uint32_t aq = smem_u32(sQ), bk = smem_u32(sK + (size_t)j * kBoxBytes);
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                    umma_bf16(tS, make_smem_desc(aq + ks * 2 * kTile * 16, kTile * 16, 128),
+                              make_smem_desc(bk + ks * 2 * kTile * 16, kTile * 16, 128), idesc, ks > 0);
+                umma_commit(&bar_s);
+            }
+            __syncwarp();
+            mbar_wait(&bar_s, ph_s);
+            ph_s ^= 1;
+            mbar_wait(&bar_bias, ph_bias);
+            ph_bias ^= 1;
+            tc_fence_after();
+
+            // ---- pass 1: row max of (scale * S + bias) over the valid columns, in log2 units
+            float m_blk = -INFINITY;
+            for (int c0 = 0; c0 < nb; c0 += 16) {
+                uint32_t sv[16];
+                tmem_ld16(tS + lane_off + c0, sv);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q8 = 0; q8 < 2; ++q8) {
+                    const int c8 = (c0 >> 3) + q8;             // 8-column chunk index inside the 128-wide tile
+                    const uint8_t *bp = sBias + (c8 >> 3) * (kTile * 128) + tid * 128 + (((c8 & 7) ^ (tid & 7)) << 4);
+                    const uint4 bv = *reinterpret_cast<const uint4 *>(bp);
+                    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int col = c8 * 8 + e;
+                        const float bias = __uint_as_float((e & 1) ? (bw[e >> 1] & 0xFFFF0000u) : (bw[e >> 1] << 16));
+                        const float s = __uint_as_float(sv[q8 * 8 + e]) * sl2 + bias * kL2e;
+                        if (col < kv_valid) m_blk = fmaxf(m_blk, s);
+                    }
+                }
+            }
+            const float m_new = fmaxf(m_run, m_blk);
+            const float m_use = row_ok ? m_new : 0.f;           // garbage rows: keep the arithmetic finite
+            const float alpha = (j == 0) ? 0.f : fast_exp2(m_run - m_use);
+            // ---- pass 2: p = 2^(s - m), row sum, bf16 P tile to shared memory ([chunk][row][8])
+            if (j > 0) {   // the previous P.V must be complete before P / O are touched again
+                mbar_wait(&bar_o, ph_o);
+                ph_o ^= 1;
+                tc_fence_after();
+            }
+            float l_blk = 0.f;
+            for (int c0 = 0; c0 < nb; c0 += 16) {
+                uint32_t sv[16];
+                tmem_ld16(tS + lane_off + c0, sv);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q8 = 0; q8 < 2; ++q8) {
+                    const int c8 = (c0 >> 3) + q8;
+                    const uint8_t *bp = sBias + (c8 >> 3) * (kTile * 128) + tid * 128 + (((c8 & 7) ^ (tid & 7)) << 4);
+                    const uint4 bv = *reinterpret_cast<const uint4 *>(bp);
+                    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+                    float pv[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int col = c8 * 8 + e;
+                        const float bias = __uint_as_float((e & 1) ? (bw[e >> 1] & 0xFFFF0000u) : (bw[e >> 1] << 16));
+                        const float s = __uint_as_float(sv[q8 * 8 + e]) * sl2 + bias * kL2e;
+                        float pe = (col < kv_valid && row_ok) ? fast_exp2(s - m_use) : 0.f;
+                        pv[e] = pe;
+                    }
+                    uint4 pk;
+                    pk.x = pack_bf16(pv[0], pv[1]);
+                    pk.y = pack_bf16(pv[2], pv[3]);
+                    pk.z = pack_bf16(pv[4], pv[5]);
+                    pk.w = pack_bf16(pv[6], pv[7]);
+                    // row sum in fp32 (P itself is rounded to bf16 only for the tensor-core operand)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) l_blk += pv[e];
+                    *reinterpret_cast<uint4 *>(sP + c8 * (kTile * 16) + tid * 16) = pk;
+                }
+            }
+            l_run = l_run * alpha + l_blk;
+            m_run = m_new;
+            if (j > 0) {   // rescale the running O accumulator
+                uint32_t ov[32];
+                tmem_ld32(tO + lane_off, ov);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+                tmem_st32(tO + lane_off, ov);
+                tmem_st_wait();
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t idesc = make_idesc_bf16(kTile, 32, 0, 1);
+                const uint32_t ap = smem_u32(sP), bv = smem_u32(sV + (size_t)j * kBoxBytes);
+                for (int ks = 0; ks < nb / 16; ++ks)
+                    umma_bf16(tO, make_smem_desc(ap + ks * 2 * kTile * 16, kTile * 16, 128),
+                              make_smem_desc(bv + ks * 256, 128, kTile * 16), idesc, (j > 0 || ks > 0));
+                umma_commit(&bar_o);
+                // the bias tile and (on the last block) Q are free again: prefetch the next tile
+                if (j + 1 < NB) {
+                    mbar_expect_tx(&bar_bias, kBiasTileBytes);
+                    tma_load_3d(sBias, &tmBias, &bar_bias, (j + 1) * kTile, i * kTile, plane);
+                    tma_load_3d(sBias + kTile * 128, &tmBias, &bar_bias, (j + 1) * kTile + 64, i * kTile, plane);
+                }
+            }
+            __syncwarp();
+        }
+        if (tid == 0) ph_q ^= 1;
+        // ---- epilogue of the query tile: O / l -> bf16, lse
+        mbar_wait(&bar_o, ph_o);
+        ph_o ^= 1;
+        tc_fence_after();
+        {
+            uint32_t ov[32];
+            tmem_ld32(tO + lane_off, ov);
+            tmem_ld_wait();
+            if (row_ok) {
+                const float inv = 1.0f / l_run;
+                uint32_t w[12];
+#pragma unroll
+                for (int e = 0; e < 12; ++e)
+                    w[e] = pack_bf16(__uint_as_float(ov[2 * e]) * inv, __uint_as_float(ov[2 * e + 1]) * inv);
+                uint4 *dst = reinterpret_cast<uint4 *>(p.out + (size_t)(t0 + row) * (p.H * kAttD) + h * kAttD);
+                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+                p.lse[(size_t)(t0 + row) * p.H + h] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();   // every thread is done with TMEM S/O and sQ/sBias before the next tile's loads
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+}  // namespace mobgt
+
+using namespace mobgt;
+
+// qkv: three bf16 matrices of [ntok, H*24] with a common row stride (elements); typically slices of one fused
+// [ntok, 3*H*24] projection.  bias: bf16 [B, H, T, Tp].  out: bf16 [ntok, H*24] (contiguous).  lse: f32 [ntok, H].
+extern "C" int32_t mobgt_attn_fwd(const void *q, const void *k, const void *v, int64_t qkv_row_stride, const void *bias,
+                                  const int32_t *tok_off, int32_t B, int32_t H, int32_t ntok, int32_t T, int32_t Tp,
+                                  int32_t t_max_host, float scale, void *out, float *lse, void *stream) {
+    MOBGT_REQUIRE(q && k && v && bias && tok_off && out && lse, MOBGT_ERR_NULL, "mobgt_attn_fwd: null pointer");
+    MOBGT_REQUIRE(H >= 1 && B >= 0 && ntok >= 0, MOBGT_ERR_BAD_SHAPE, "mobgt_attn_fwd: B=%d H=%d ntok=%d", B, H, ntok);
+    MOBGT_REQUIRE(qkv_row_stride % 8 == 0 && Tp % 8 == 0 && Tp >= T, MOBGT_ERR_BAD_SHAPE,
+                  "mobgt_attn_fwd: row stride %lld and Tp=%d must be multiples of 8", (long long)qkv_row_stride, Tp);
+    MOBGT_REQUIRE(t_max_host >= 1 && t_max_host <= T && T <= MOBGT_MAX_NODES + 1, MOBGT_ERR_BAD_SHAPE,
+                  "mobgt_attn_fwd: t_max=%d T=%d", t_max_host, T);
+    if (B == 0 || ntok == 0) return MOBGT_OK;
+    CUtensorMap tmQ, tmK, tmV, tmB;
+    const void *ptrs[3] = {q, k, v};
+    CUtensorMap *maps[3] = {&tmQ, &tmK, &tmV};
+    for (int i = 0; i < 3; ++i) {
+        uint64_t dims[3] = {8, (uint64_t)ntok, (uint64_t)H * kAttChunks};
+        uint64_t str[2] = {(uint64_t)qkv_row_stride * 2, 16};
+        uint32_t box[3] = {8, kTile, kAttChunks};
+        int32_t rc = encode_tmap_bf16(maps[i], ptrs[i], 3, dims, str, box, 0);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)Tp, (uint64_t)T, (uint64_t)B * H};
+        uint64_t str[2] = {(uint64_t)Tp * 2, (uint64_t)T * Tp * 2};
+        uint32_t box[3] = {64, kTile, 1};
+        int32_t rc = encode_tmap_bf16(&tmB, bias, 3, dims, str, box, 1);
+        if (rc) return rc;
+    }
+    const int max_boxes = ceil_div(t_max_host, kTile);
+    const size_t smem = (size_t)kBiasTileBytes + kPBytes + kBoxBytes + (size_t)2 * max_boxes * kBoxBytes + 1024;
+    MOBGT_CUDA_OK(cudaFuncSetAttribute(k3_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AttnFwdParams p{tok_off, static_cast<__nv_bfloat16 *>(out), lse, H, scale, max_boxes};
+    k3_attn_fwd_kernel<<<B * H, 128, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmB, p);
+    MOBGT_LAUNCH_OK("k3_attn_fwd_kernel");
+    return MOBGT_OK;
+}

@@ -1,0 +1,197 @@
+"""torch-facing wrappers of the libmobgt kernels: raw calls + autograd.Function pairs.
+
+PyTorch is plumbing here (device memory, streams, autograd graph); the arithmetic of the hot ops is in
+mobgt_b200/csrc/*.cu behind the C-ABI (include/mobgt.h).  No op has a torch/CPU fallback.
+"""
+import torch
+
+from . import _C
+
+F32, BF16 = 0, 1
+NUM_HEADS = 8
+HEAD_DIM = 24
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise _C.MobgtError(f"unsupported dtype {t.dtype}")
+
+
+def bias_pitch(T):
+    """Row pitch (elements) of the bias planes: a multiple of 8 so that rows are 16-byte aligned for TMA."""
+    return (T + 7) // 8 * 8
+
+
+# ----------------------------------------------------------------------------------------------- K2
+def bias_fwd_raw(batch, R, Ppos, E, W, tvd, out_dtype=torch.bfloat16, T=None, Tp=None):
+    B, H = batch.B, R.shape[1]
+    T = T or batch.N + 1
+    Tp = Tp or bias_pitch(T)
+    dev = R.device
+    out = torch.empty(B, H, T, Tp, dtype=out_dtype, device=dev)
+    ws = torch.empty(batch.hops * 128 * H, dtype=torch.float32, device=dev)
+    _C.call("mobgt_bias_fwd", _C.ptr(batch.n), _C.ptr(batch.sq_off), _C.ptr(batch.rel_pos16), _C.ptr(batch.poi_pos16),
+            _C.ptr(batch.edge_in8), B, T, Tp, batch.hops, H, batch.rel_pos_max, _C.ptr(R), _C.ptr(Ppos), _C.ptr(E), _C.ptr(W),
+            _C.ptr(tvd), _C.ptr(ws), _C.ptr(out), _dt(out), _C.stream_ptr())
+    return out
+
+
+def bias_bwd_raw(batch, dbias, E, W, num_bins):
+    B, H, T, Tp = dbias.shape
+    dev = dbias.device
+    hops = batch.hops
+    ws = torch.empty(hops * 128 * H, dtype=torch.float32, device=dev)
+    dR = torch.empty(512, H, dtype=torch.float32, device=dev)
+    dP = torch.empty(num_bins, H, dtype=torch.float32, device=dev)
+    dE = torch.empty(128, H, dtype=torch.float32, device=dev)
+    dW = torch.zeros(W.numel(), dtype=torch.float32, device=dev)
+    dt = torch.empty(H, dtype=torch.float32, device=dev)
+    _C.call("mobgt_bias_bwd", _C.ptr(batch.n), _C.ptr(batch.sq_off), _C.ptr(batch.rel_pos16), _C.ptr(batch.poi_pos16),
+            _C.ptr(batch.edge_in8), B, T, Tp, hops, H, batch.rel_pos_max, num_bins, _C.ptr(dbias), _C.ptr(E), _C.ptr(W),
+            _C.ptr(ws), _C.ptr(dR), _C.ptr(dP), _C.ptr(dE), _C.ptr(dW), _C.ptr(dt), _C.stream_ptr())
+    return dR, dP, dE, dW.view_as(W), dt
+
+
+class AttnBias(torch.autograd.Function):
+    """graph_attn_bias = f(rel_pos, poi_pos, edge_input; 5 tables)   (model_fqandtoyo.py:1143-1216).
+    The gradient arriving here is the fp32 dBias buffer the attention backward of all layers accumulated into."""
+
+    @staticmethod
+    def forward(ctx, batch, R, Ppos, E, W, tvd, out_dtype):
+        Rc, Pc, Ec, Wc, tc = (t.detach().float().contiguous() for t in (R, Ppos, E, W, tvd))
+        ctx.batch, ctx.num_bins = batch, Ppos.shape[0]
+        ctx.save_for_backward(Ec, Wc)
+        return bias_fwd_raw(batch, Rc, Pc, Ec, Wc.view(-1), tc.view(-1), out_dtype)
+
+    @staticmethod
+    def backward(ctx, dbias):
+        E, W = ctx.saved_tensors
+        dR, dP, dE, dW, dt = bias_bwd_raw(ctx.batch, dbias.float().contiguous(), E, W.view(-1), ctx.num_bins)
+        dR[0].zero_()          # padding_idx rows (never indexed by a packed pair anyway)
+        dP[0].zero_()
+        return None, dR, dP, dE, dW.view(-1, 1), dt.view(1, -1), None
+
+
+# ----------------------------------------------------------------------------------------------- K3
+def attn_fwd_raw(qkv, bias, batch, scale=None):
+    """qkv bf16 [ntok, 3*H*24] (fused projection) ; bias bf16 [B,H,T,Tp] -> (out bf16 [ntok, H*24], lse f32 [ntok,H])"""
+    ntok = qkv.shape[0]
+    B, H, T, Tp = bias.shape
+    D = H * HEAD_DIM
+    assert qkv.dtype == torch.bfloat16 and bias.dtype == torch.bfloat16 and qkv.shape[1] == 3 * D and qkv.is_contiguous()
+    out = torch.empty(ntok, D, dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty(ntok, H, dtype=torch.float32, device=qkv.device)
+    scale = float(HEAD_DIM ** -0.5) if scale is None else float(scale)
+    base = qkv.data_ptr()
+    _C.call("mobgt_attn_fwd", base, base + 2 * D, base + 4 * D, 3 * D, _C.ptr(bias), _C.ptr(batch.tok_off), B, H, ntok, T, Tp,
+            int(batch.N) + 1, scale, _C.ptr(out), _C.ptr(lse), _C.stream_ptr())
+    return out, lse
+
+
+# ----------------------------------------------------------------------------------------------- K4
+def embed_gather_raw(batch, cat_of_poi, Gd, Tm, Gc, out_dtype=torch.bfloat16):
+    nn_ = int(batch.x_nodes.numel())
+    Dp, Dt, Dc = Gd.shape[1], Tm.shape[1], Gc.shape[1]
+    out = torch.empty(nn_, Dp + Dt + Dc, dtype=out_dtype, device=Gd.device)
+    _C.call("mobgt_embed_gather_fwd", _C.ptr(batch.x_nodes), _C.ptr(batch.slot), _C.ptr(cat_of_poi), _C.ptr(Gd), _C.ptr(Tm),
+            _C.ptr(Gc), nn_, Dp, Dt, Dc, _C.ptr(out), _dt(out), _C.stream_ptr())
+    return out
+
+
+def embed_sum_raw(batch, nf, Din, Dout, pe, graph_token):
+    ntok = int(batch.tok_pos.numel())
+    D = nf.shape[1]
+    tok = torch.empty(ntok, D, dtype=nf.dtype, device=nf.device)
+    _C.call("mobgt_embed_sum_fwd", _C.ptr(nf), _C.ptr(batch.tok_graph), _C.ptr(batch.tok_pos), _C.ptr(batch.in_deg),
+            _C.ptr(batch.out_deg), _C.ptr(Din), _C.ptr(Dout), _C.ptr(pe), _C.ptr(graph_token), ntok, D, _C.ptr(tok), _dt(tok),
+            _C.stream_ptr())
+    return tok
+
+
+def sort_plan(keys):
+    """Stable sort of an int key stream -> (perm i32, keys_sorted i32): the fixed summation order of segment_sum."""
+    ks, perm = torch.sort(keys.long(), stable=True)
+    return perm.int().contiguous(), ks.int().contiguous()
+
+
+def segment_sum_raw(src, col0, D, plan, nkeys, out=None):
+    """table[key] = sum_{rows r: key_r == key} src[r, col0:col0+D]  (deterministic; fp32 out [nkeys, D])."""
+    perm, ks = plan
+    nrows = int(perm.numel())
+    assert src.dim() == 2 and src.stride(1) == 1
+    if out is None:
+        out = torch.zeros(nkeys, D, dtype=torch.float32, device=src.device)
+    nchunks = (nrows + 31) // 32
+    ws_bytes = 2 * nchunks * D * 4 + 2 * nchunks * 4
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=src.device)
+    _C.call("mobgt_segment_sum", _C.ptr(src) if src.is_contiguous() else src.data_ptr(), _dt(src), src.stride(0), col0, D,
+            _C.ptr(perm), _C.ptr(ks), nrows, _C.ptr(out), nkeys, _C.ptr(ws), ws_bytes, _C.stream_ptr())
+    return out
+
+
+class EmbedGather(torch.autograd.Function):
+    """[Gd[x-1] | Tm[slot] | Gc[cat_of_poi[x-1]-1]] per packed node (model_fqandtoyo.py:1259-1264)."""
+
+    @staticmethod
+    def forward(ctx, batch, cat_of_poi, Gd, Tm, Gc, out_dtype):
+        ctx.batch, ctx.cat_of_poi = batch, cat_of_poi
+        ctx.shapes = (Gd.shape, Tm.shape, Gc.shape)
+        return embed_gather_raw(batch, cat_of_poi, Gd.detach().float().contiguous(), Tm.detach().float().contiguous(),
+                                Gc.detach().float().contiguous(), out_dtype)
+
+    @staticmethod
+    def backward(ctx, dout):
+        b = ctx.batch
+        (P, Dp), (Tr, Dt), (C, Dc) = ctx.shapes
+        dout = dout.contiguous()
+        plans = b.__dict__.setdefault("_plans", {})
+        if "poi" not in plans:
+            poi = b.x_nodes.long() - 1
+            plans["poi"] = sort_plan(poi)
+            plans["slot"] = sort_plan(b.slot)
+            plans["cat"] = sort_plan(ctx.cat_of_poi[poi].long() - 1)
+        dGd = segment_sum_raw(dout, 0, Dp, plans["poi"], P)
+        dTm = segment_sum_raw(dout, Dp, Dt, plans["slot"], Tr)
+        dGc = segment_sum_raw(dout, Dp + Dt, Dc, plans["cat"], C)
+        return None, None, dGd, dTm, dGc, None
+
+
+class EmbedSum(torch.autograd.Function):
+    """tokens = nf + in_degree_encoder + out_degree_encoder + pe[q+1] ; graph token + pe[0]
+    (model_fqandtoyo.py:1288-1344).  Backward: d_nf = token-row gather; table grads by segment_sum."""
+
+    @staticmethod
+    def forward(ctx, batch, nf, Din, Dout, pe, graph_token):
+        ctx.batch = batch
+        ctx.shapes = (Din.shape, Dout.shape, pe.shape)
+        return embed_sum_raw(batch, nf.contiguous(), Din.detach().float().contiguous(), Dout.detach().float().contiguous(),
+                             pe.detach().float().contiguous(), graph_token.detach().float().contiguous().view(-1))
+
+    @staticmethod
+    def backward(ctx, dtok):
+        b = ctx.batch
+        dtok = dtok.contiguous()
+        D = dtok.shape[1]
+        plans = b.__dict__.setdefault("_plans", {})
+        if "pos" not in plans:
+            node_rows = (b.tok_pos > 0).nonzero().view(-1)
+            plans["node_rows"] = node_rows
+            plans["pos"] = sort_plan(b.tok_pos)
+            ind = torch.zeros_like(b.tok_pos)
+            ind[node_rows] = b.in_deg
+            outd = torch.zeros_like(b.tok_pos)
+            outd[node_rows] = b.out_deg
+            plans["ind"] = sort_plan(ind)
+            plans["outd"] = sort_plan(outd)
+        (ri, _), (ro, _), (rp, _) = ctx.shapes
+        d_nf = dtok.index_select(0, plans["node_rows"])
+        dDin = segment_sum_raw(dtok, 0, D, plans["ind"], ri)
+        dDout = segment_sum_raw(dtok, 0, D, plans["outd"], ro)
+        dpe = segment_sum_raw(dtok, 0, D, plans["pos"], rp)
+        dgt = dpe[0:1].clone()          # d graph_token = sum_g dtok[g, 0] = dpe[0]
+        dDin[0].zero_()                 # padding_idx rows / graph-token rows carry key 0
+        dDout[0].zero_()
+        return None, d_nf, dDin, dDout, dpe, dgt

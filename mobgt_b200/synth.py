@@ -109,7 +109,7 @@ class PoiWorld:
 
 
 def _row_norm_csr(P, rows, cols):
-    """\hat A = (D+I)^-1 (A+I) as CSR from an edge list (no self loops in input)."""
+    r"""\hat A = (D+I)^-1 (A+I) as CSR from an edge list (no self loops in input)."""
     rows = np.concatenate([rows, np.arange(P)])
     cols = np.concatenate([cols, np.arange(P)])
     key = rows.astype(np.int64) * P + cols

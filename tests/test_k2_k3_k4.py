@@ -1,0 +1,190 @@
+"""GPU: kernel-level parity of K2 (bias build fwd/bwd), K3 (tcgen05 attention fwd) and K4 (embedding gather / sum /
+deterministic segmented scatter-add) against the oracle restatement (oracle/model_oracle.py) and plain torch fp32."""
+import numpy as np
+import pytest
+import torch
+
+import model_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+
+def make_case(cfg="tiny", B=6, cap=12, seed=1, n_fixed=None, **world_kw):
+    from mobgt_b200 import collator, synth
+    w = synth.make_world(cfg, seed=seed, **world_kw)
+    items = synth.make_items(w, B, cap, seed=seed, n_fixed=n_fixed)
+    ob = mo.collate([mo.preprocess_item(it, hop_cap=20) for it in items], w, multi_hop_max_dist=20, rel_pos_max=1024)
+    b = collator.collator_toyota(items, max_node=512, multi_hop_max_dist=20, rel_pos_max=1024, world=w)
+    return w, items, ob, b
+
+
+def tables(H=8, bins=64, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    R = torch.randn(512, H, generator=g) * 0.3
+    Pp = torch.randn(bins, H, generator=g) * 0.3
+    E = torch.randn(128, H, generator=g) * 0.3
+    W = torch.randn(128 * H * H, 1, generator=g) * 0.3
+    t = torch.randn(1, H, generator=g) * 0.3
+    R[0] = 0
+    Pp[0] = 0
+    E[0] = 0
+    return R, Pp, E, W, t
+
+
+def oracle_bias(ob, R, Pp, E, W, t, H=8):
+    class M:
+        pass
+    m = mo.Graphormer.__new__(mo.Graphormer)
+    torch.nn.Module.__init__(m)
+    m.num_heads, m.multi_hop_max_dist = H, 20
+    m.rel_pos_encoder = torch.nn.Embedding.from_pretrained(R.clone(), freeze=False, padding_idx=0)
+    m.poi_pos_encoder = torch.nn.Embedding.from_pretrained(Pp.clone(), freeze=False, padding_idx=0)
+    m.edge_encoder = torch.nn.Embedding.from_pretrained(E.clone(), freeze=False, padding_idx=0)
+    m.edge_dis_encoder = torch.nn.Embedding.from_pretrained(W.clone(), freeze=False)
+    m.graph_token_virtual_distance = torch.nn.Embedding.from_pretrained(t.clone(), freeze=False)
+    return m, m.attn_bias_build(ob, "fp32")
+
+
+@pytest.mark.parametrize("cfg,B,cap,nfix", [("tiny", 6, 12, None), ("c1", 5, 40, None), ("c1", 3, 70, 70)])
+def test_collated_fields_match_oracle_collator(lib_built, cfg, B, cap, nfix):
+    """Batch1's reference-shaped views == the oracle's collator (collator.py restatement), bit-exact."""
+    w, items, ob, b = make_case(cfg, B, cap, n_fixed=nfix)
+    for name in ("x", "rel_pos", "edge_input", "in_degree", "out_degree", "attn_bias", "attn_edge_type", "adj1",
+                 "time", "time_normal", "cat", "poi_pos", "user", "y"):
+        got = getattr(b, name).cpu()
+        exp = getattr(ob, name)
+        assert got.shape == exp.shape, (name, got.shape, exp.shape)
+        assert got.dtype == exp.dtype, (name, got.dtype, exp.dtype)
+        assert torch.equal(got, exp), name
+    assert b.spatial_pos is b.rel_pos or torch.equal(b.spatial_pos, b.rel_pos)
+    assert len(b) == B
+
+
+@pytest.mark.parametrize("cfg,B,cap,nfix", [("tiny", 6, 12, None), ("c1", 8, 60, None), ("c1", 4, 128, 128)])
+def test_bias_fwd_fp32_and_bf16(lib_built, cfg, B, cap, nfix):
+    from mobgt_b200 import ops
+    w, items, ob, b = make_case(cfg, B, cap, n_fixed=nfix)
+    R, Pp, E, W, t = tables()
+    _, ref = oracle_bias(ob, R, Pp, E, W, t)
+    ref = ref.detach()
+    cu = [x.cuda().contiguous() for x in (R, Pp, E, W.view(-1), t.view(-1))]
+    out32 = ops.bias_fwd_raw(b, *cu, out_dtype=torch.float32).cpu()
+    out16 = ops.bias_fwd_raw(b, *cu, out_dtype=torch.bfloat16).float().cpu()
+    T = b.N + 1
+    n = b.n_host
+    for g in range(B):
+        Tg = int(n[g]) + 1
+        r = ref[g, :, :Tg, :Tg]
+        assert torch.isfinite(r).all()
+        # fp32 mode: 1e-5 relative (north_star tolerance)
+        assert torch.allclose(out32[g, :, :Tg, :Tg], r, rtol=1e-5, atol=1e-6), g
+        # bf16 mode: 2e-2 relative
+        assert torch.allclose(out16[g, :, :Tg, :Tg], r, rtol=2e-2, atol=2e-2), g
+        # padding columns of real rows are -inf in the reference; the kernels mask them from seqlens instead
+        assert (ref[g, :, :Tg, Tg:] == float("-inf")).all()
+
+
+def test_bias_bwd_matches_autograd_of_oracle(lib_built):
+    from mobgt_b200 import ops
+    w, items, ob, b = make_case("c1", 6, 50)
+    R, Pp, E, W, t = tables(seed=3)
+    m, ref = oracle_bias(ob, R, Pp, E, W, t)
+    B, H, T = ref.shape[0], 8, b.N + 1
+    Tp = ops.bias_pitch(T)
+    gen = torch.Generator().manual_seed(5)
+    dB = torch.zeros(B, H, T, Tp)
+    for g in range(B):
+        Tg = int(b.n_host[g]) + 1
+        dB[g, :, :Tg, :Tg] = torch.randn(H, Tg, Tg, generator=gen)
+    finite = torch.where(torch.isfinite(ref), ref, torch.zeros_like(ref))
+    (finite * dB[..., :T]).sum().backward()
+    dR, dP, dE, dW, dt = ops.bias_bwd_raw(b, dB.cuda(), E.cuda().contiguous(), W.view(-1).cuda().contiguous(), Pp.shape[0])
+    torch.cuda.synchronize()
+
+    def close(a, bb, name):
+        a, bb = a.cpu(), bb
+        scale = bb.abs().max().item() + 1e-6
+        assert (a - bb).abs().max().item() <= 2e-5 * scale + 1e-5, (name, (a - bb).abs().max().item(), scale)
+
+    close(dR, m.rel_pos_encoder.weight.grad, "dR")
+    close(dP, m.poi_pos_encoder.weight.grad, "dPpos")
+    close(dE, m.edge_encoder.weight.grad, "dE")
+    close(dW.view(-1, 1), m.edge_dis_encoder.weight.grad, "dW")
+    close(dt.view(1, -1), m.graph_token_virtual_distance.weight.grad, "dtvd")
+
+
+def torch_attention(qkv, bias, tok_off, H=8, d=24):
+    """fp32 reference of model_fqandtoyo.py:1693-1706 per packed graph (bias already restricted to real columns)."""
+    D = H * d
+    out = torch.zeros(qkv.shape[0], D)
+    lse = torch.zeros(qkv.shape[0], H)
+    for g in range(len(tok_off) - 1):
+        a, e = int(tok_off[g]), int(tok_off[g + 1])
+        T = e - a
+        q = qkv[a:e, :D].view(T, H, d).transpose(0, 1).float()
+        k = qkv[a:e, D:2 * D].view(T, H, d).transpose(0, 1).float()
+        v = qkv[a:e, 2 * D:].view(T, H, d).transpose(0, 1).float()
+        s = (q * d ** -0.5) @ k.transpose(1, 2) + bias[g, :, :T, :T].float()
+        lse[a:e] = torch.logsumexp(s, dim=-1).t()
+        out[a:e] = (torch.softmax(s, -1) @ v).transpose(0, 1).reshape(T, D)
+    return out, lse
+
+
+@pytest.mark.parametrize("cfg,B,cap,nfix", [("tiny", 6, 12, None), ("c1", 8, 60, None), ("c1", 5, 128, 128),
+                                            ("c1", 3, 300, 300), ("c1", 2, 512, 512)])
+def test_attention_fwd_matches_torch(lib_built, cfg, B, cap, nfix):
+    from mobgt_b200 import ops
+    w, items, ob, b = make_case(cfg, B, cap, n_fixed=nfix)
+    R, Pp, E, W, t = tables(seed=7)
+    cu = [x.cuda().contiguous() for x in (R, Pp, E, W.view(-1), t.view(-1))]
+    bias = ops.bias_fwd_raw(b, *cu, out_dtype=torch.bfloat16)
+    ntok = int(b.tok_pos.numel())
+    g = torch.Generator().manual_seed(11)
+    qkv = (torch.randn(ntok, 3 * 192, generator=g) * 1.5).to(torch.bfloat16)
+    out, lse = ops.attn_fwd_raw(qkv.cuda(), bias, b)
+    torch.cuda.synchronize()
+    ref, ref_lse = torch_attention(qkv, bias.cpu(), b.tok_off.cpu().numpy())
+    err = (out.float().cpu() - ref).abs().max().item()
+    assert err <= 2e-2 * max(1.0, ref.abs().max().item()), f"attention out max err {err}"
+    assert (lse.cpu() - ref_lse).abs().max().item() <= 2e-2
+
+
+def test_embed_gather_sum_and_segment_sum(lib_built):
+    from mobgt_b200 import ops
+    w, items, ob, b = make_case("c1", 7, 45)
+    g = torch.Generator().manual_seed(2)
+    P, C = w.P, w.C
+    Gd = torch.randn(P, 128, generator=g)
+    Tm = torch.randn(48, 32, generator=g)
+    Gc = torch.randn(C, 32, generator=g)
+    cop = torch.from_numpy(w.cat_of_poi).int().cuda()
+    out = ops.embed_gather_raw(b, cop, Gd.cuda(), Tm.cuda(), Gc.cuda(), torch.float32).cpu()
+    x = b.x_nodes.cpu().long()
+    exp = torch.cat([Gd[x - 1], Tm[b.slot.cpu().long()], Gc[torch.from_numpy(w.cat_of_poi)[x - 1] - 1]], 1)
+    assert torch.equal(out, exp)
+    # sum
+    Din = torch.randn(128, 192, generator=g)
+    Dout = torch.randn(128, 192, generator=g)
+    pe = torch.randn(2000, 192, generator=g)
+    gt = torch.randn(1, 192, generator=g)
+    nf = torch.randn(x.numel(), 192, generator=g)
+    tok = ops.embed_sum_raw(b, nf.cuda(), Din.cuda(), Dout.cuda(), pe.cuda(), gt.view(-1).cuda()).cpu()
+    tp, tg = b.tok_pos.cpu().long(), b.tok_graph.cpu().long()
+    node_rows = (tp > 0).nonzero().view(-1)
+    exp_tok = torch.zeros_like(tok)
+    exp_tok[tp == 0] = gt + pe[0]
+    exp_tok[node_rows] = ((nf + Din[b.in_deg.cpu().long()]) + Dout[b.out_deg.cpu().long()]) + pe[tp[node_rows]]
+    assert torch.allclose(tok, exp_tok, rtol=1e-6, atol=1e-6)
+    # deterministic segmented sum: == index_add in fp64, and bitwise reproducible
+    src = torch.randn(tok.shape[0], 192, generator=g).cuda()
+    for keys, nk in ((b.tok_pos, 2000), (b.tok_graph, b.B), (torch.zeros_like(b.tok_pos), 3)):
+        plan = ops.sort_plan(keys)
+        t1 = ops.segment_sum_raw(src, 0, 192, plan, nk)
+        t2 = ops.segment_sum_raw(src, 0, 192, plan, nk)
+        assert torch.equal(t1, t2)
+        ref = torch.zeros(nk, 192, dtype=torch.float64).index_add_(0, keys.cpu().long(), src.cpu().double())
+        assert torch.allclose(t1.cpu().double(), ref, rtol=1e-5, atol=1e-4)
+    plan = ops.sort_plan(b.tok_pos)
+    part = ops.segment_sum_raw(src, 64, 32, plan, 2000)
+    ref = torch.zeros(2000, 32, dtype=torch.float64).index_add_(0, b.tok_pos.cpu().long(), src[:, 64:96].cpu().double())
+    assert torch.allclose(part.cpu().double(), ref, rtol=1e-5, atol=1e-4)
