@@ -126,6 +126,16 @@ int32_t mobgt_attn_fwd(const void *q, const void *k, const void *v, int64_t qkv_
                        const int32_t *tok_off, int32_t B, int32_t H, int32_t ntok, int32_t T, int32_t Tp,
                        int32_t t_max_host, float scale, void *out, float *lse, void *stream);
 
+/* Backward of mobgt_attn_fwd.  o, dout: bf16 [ntok, H*24] contiguous; lse from the forward.
+ * dq, dk, dv: bf16 with a common row stride (usually slices of one [ntok, 3*H*24] buffer).
+ * dbias f32 [B,H,T,Tp] receives dS = d(scores) = d(bias): overwritten (accumulate = 0) or added to
+ * (accumulate = 1; the bias is shared by all encoder layers).  Scores / probabilities are recomputed
+ * in-tile and never stored in HBM. */
+int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, int64_t qkv_row_stride, const void *bias,
+                       const void *o, const void *dout, const float *lse, const int32_t *tok_off, int32_t B,
+                       int32_t H, int32_t ntok, int32_t T, int32_t Tp, int32_t t_max_host, float scale, void *dq,
+                       void *dk, void *dv, int64_t dqkv_row_stride, float *dbias, int32_t accumulate, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * K4 — node-embedding gather / sum and the deterministic segmented scatter-add backward.
  * Replaces model_fqandtoyo.py:1257-1269 (per-node table look-ups) and :1288-1344 (degree encoders,

@@ -1,0 +1,379 @@
+// K3 (backward) — biased multi-head attention backward on tcgen05 / TMEM, fed by TMA (sm_100a).
+//
+// Gradient of model_fqandtoyo.py:1693-1706 for packed var-len graphs (see k3_attn_fwd.cu):
+//   P  = exp(scale * Q K^T + bias - lse)            recomputed per tile, never stored in HBM
+//   dP = dO V^T ;  D = rowsum(dO * O) ;  dS = P * (dP - D)          (dS is also d(bias))
+//   dV = P^T dO ;  dK = scale * dS^T Q ;  dQ = scale * dS K
+// One CTA per (graph, head).  Five MMAs per (kv block j, query tile i):
+//   S, dP    M=128 (queries) N<=128 K=32           -> TMEM [0,128), [128,256)
+//   dV, dK   M=128 (keys)    N=32   K=128 queries  -> TMEM [256,288), [288,320)   (accumulate over i)
+//   dQ_i     M=128 (queries) N=32   K<=128 keys    -> TMEM [320+32 i, ...)        (accumulate over j)
+// P and dS are written once to shared memory as bf16 in the [chunk][row][8] layout; that single image is the
+// K-major A operand of dQ = dS.K and the MN-major (transposed) A operand of dV = P^T.dO / dK = dS^T.Q.
+// dS is streamed to the fp32 dBias buffer [B,H,T,Tp] (overwrite or accumulate across layers); the table gradients
+// are reduced from it by mobgt_bias_bwd.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace mobgt {
+using namespace sm100;
+
+namespace bwd {
+constexpr int kAttD = 24;
+constexpr int kAttChunks = 3;
+constexpr int kTile = 128;
+constexpr int kBoxBytes = 4 * kTile * 16;
+constexpr int kBoxTxBytes = kAttChunks * kTile * 16;
+constexpr int kBiasTileBytes = 2 * kTile * 128;
+constexpr int kPBytes = 16 * kTile * 16;
+constexpr int kMaxTiles = 5;   // T <= 513
+}  // namespace bwd
+using namespace bwd;
+
+struct AttnBwdParams {
+    const int32_t *tok_off;
+    const __nv_bfloat16 *o;    // [ntok, H*24]
+    const __nv_bfloat16 *dout; // [ntok, H*24]
+    const float *lse;          // [ntok, H]
+    __nv_bfloat16 *dq, *dk, *dv;  // [ntok, *] with row stride dqkv_stride (elements)
+    int64_t dqkv_stride;
+    float *dbias;              // [B,H,T,Tp] f32
+    int H, T, Tp;
+    float scale;
+    int max_boxes;
+    int accumulate;            // 0: overwrite dbias, 1: dbias += dS
+};
+
+__device__ __forceinline__ float bwd_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(128, 1)
+k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                   const __grid_constant__ CUtensorMap tmBias, const AttnBwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_qdo, bar_kv, bar_bias, bar_s, bar_mma;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float sLse[kMaxTiles * kTile], sDelta[kMaxTiles * kTile];
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int g = blockIdx.x / p.H, h = blockIdx.x - g * p.H;
+    const int t0 = p.tok_off[g];
+    const int Tg = p.tok_off[g + 1] - t0;
+    const int NB = ceil_div(Tg, kTile);
+    const int HD = p.H * kAttD;
+
+    uint8_t *sBias = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+    uint8_t *sP = sBias + kBiasTileBytes;
+    uint8_t *sdS = sP + kPBytes;
+    uint8_t *sQ = sdS + kPBytes;
+    uint8_t *sdO = sQ + kBoxBytes;
+    uint8_t *sK = sdO + kBoxBytes;
+    uint8_t *sV = sK + (size_t)p.max_boxes * kBoxBytes;
+
+    if (tid == 0) {
+        mbar_init(&bar_qdo, 1);
+        mbar_init(&bar_kv, 1);
+        mbar_init(&bar_bias, 1);
+        mbar_init(&bar_s, 1);
+        mbar_init(&bar_mma, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        tma_prefetch_desc(&tmdO);
+        tma_prefetch_desc(&tmBias);
+    }
+    {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(sQ + 3 * kTile * 16 + tid * 16) = z;
+        *reinterpret_cast<uint4 *>(sdO + 3 * kTile * 16 + tid * 16) = z;
+        for (int b = 0; b < NB; ++b) {
+            *reinterpret_cast<uint4 *>(sK + (size_t)b * kBoxBytes + 3 * kTile * 16 + tid * 16) = z;
+            *reinterpret_cast<uint4 *>(sV + (size_t)b * kBoxBytes + 3 * kTile * 16 + tid * 16) = z;
+        }
+    }
+    // lse (log2 units) and D = rowsum(dO * O) of every query row of this (graph, head)
+    for (int r = tid; r < NB * kTile; r += 128) {
+        float lse2 = 0.f, dl = 0.f;
+        if (r < Tg) {
+            lse2 = p.lse[(size_t)(t0 + r) * p.H + h] * 1.4426950408889634f;
+            const uint4 *po = reinterpret_cast<const uint4 *>(p.o + (size_t)(t0 + r) * HD + h * kAttD);
+            const uint4 *pd = reinterpret_cast<const uint4 *>(p.dout + (size_t)(t0 + r) * HD + h * kAttD);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const uint4 a = po[q], b = pd[q];
+                const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    dl += __uint_as_float(aw[e] << 16) * __uint_as_float(bw[e] << 16);
+                    dl += __uint_as_float(aw[e] & 0xFFFF0000u) * __uint_as_float(bw[e] & 0xFFFF0000u);
+                }
+            }
+        }
+        sLse[r] = lse2;
+        sDelta[r] = dl;
+    }
+    if (warp == 0) tmem_alloc<512>(&tmem_slot);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t tS = tmem, tdP = tmem + 128, tdK = tmem + 256, tdV = tmem + 288, tdQ = tmem + 320;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+
+    if (tid == 0) {
+        mbar_expect_tx(&bar_kv, (uint32_t)(2 * NB * kBoxTxBytes));
+        for (int b = 0; b < NB; ++b) {
+            tma_load_3d(sK + (size_t)b * kBoxBytes, &tmK, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
+            tma_load_3d(sV + (size_t)b * kBoxBytes, &tmV, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
+        }
+    }
+    __syncwarp();
+    uint32_t ph_qdo = 0, ph_bias = 0, ph_s = 0, ph_mma = 0;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    constexpr float kL2e = 1.4426950408889634f;
+    const int plane = g * p.H + h;
+    bool first = true;
+
+    for (int j = 0; j < NB; ++j) {
+        const int kv_valid = min(kTile, Tg - j * kTile);
+        const int nb = round_up(kv_valid, 16);
+        for (int i = 0; i < NB; ++i) {
+            const int q_valid = min(kTile, Tg - i * kTile);
+            const int qk = round_up(q_valid, 16);          // K extent (query rows) of the dV / dK MMAs
+            const int row = i * kTile + tid;
+            const bool row_ok = row < Tg;
+            if (!first) {   // the previous iteration's dV/dK/dQ MMAs read sP, sdS, sQ, sdO
+                mbar_wait(&bar_mma, ph_mma);
+                ph_mma ^= 1;
+                tc_fence_after();
+            }
+            first = false;
+            if (tid == 0) {
+                mbar_expect_tx(&bar_qdo, 2 * kBoxTxBytes);
+                tma_load_3d(sQ, &tmQ, &bar_qdo, 0, t0 + i * kTile, h * kAttChunks);
+                tma_load_3d(sdO, &tmdO, &bar_qdo, 0, t0 + i * kTile, h * kAttChunks);
+                mbar_expect_tx(&bar_bias, kBiasTileBytes);
+                tma_load_3d(sBias, &tmBias, &bar_bias, j * kTile, i * kTile, plane);
+                tma_load_3d(sBias + kTile * 128, &tmBias, &bar_bias, j * kTile + 64, i * kTile, plane);
+                mbar_wait(&bar_qdo, ph_qdo);
+                ph_qdo ^= 1;
+                if (j == 0 && i == 0) mbar_wait(&bar_kv, 0);
+                tc_fence_after();
+                const uint32_t idesc = make_idesc_bf16(kTile, nb, 0, 0);
+                const uint32_t aq = smem_u32(sQ), ado = smem_u32(sdO);
+                const uint32_t bk = smem_u32(sK + (size_t)j * kBoxBytes), bv = smem_u32(sV + (size_t)j * kBoxBytes);
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                    umma_bf16(tS, make_smem_desc(aq + ks * 2 * kTile * 16, kTile * 16, 128),
+                              make_smem_desc(bk + ks * 2 * kTile * 16, kTile * 16, 128), idesc, ks > 0);
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                    umma_bf16(tdP, make_smem_desc(ado + ks * 2 * kTile * 16, kTile * 16, 128),
+                              make_smem_desc(bv + ks * 2 * kTile * 16, kTile * 16, 128), idesc, ks > 0);
+                umma_commit(&bar_s);
+            }
+            __syncwarp();
+            mbar_wait(&bar_s, ph_s);
+            ph_s ^= 1;
+            mbar_wait(&bar_bias, ph_bias);
+            ph_bias ^= 1;
+            tc_fence_after();
+
+            const float lse2 = sLse[row < NB * kTile ? row : 0];
+            const float delta = sDelta[row < NB * kTile ? row : 0];
+            float *db_row = p.dbias + ((size_t)plane * p.T + row) * p.Tp + j * kTile;
+            for (int c0 = 0; c0 < nb; c0 += 16) {
+                uint32_t sv[16], dpv[16];
+                tmem_ld16(tS + lane_off + c0, sv);
+                tmem_ld16(tdP + lane_off + c0, dpv);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q8 = 0; q8 < 2; ++q8) {
+                    const int c8 = (c0 >> 3) + q8;
+                    const uint8_t *bp = sBias + (c8 >> 3) * (kTile * 128) + tid * 128 + (((c8 & 7) ^ (tid & 7)) << 4);
+                    const uint4 bvv = *reinterpret_cast<const uint4 *>(bp);
+                    const uint32_t bw[4] = {bvv.x, bvv.y, bvv.z, bvv.w};
+                    float pv[8], dsv[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int col = c8 * 8 + e;
+                        const float bias = __uint_as_float((e & 1) ? (bw[e >> 1] & 0xFFFF0000u) : (bw[e >> 1] << 16));
+                        const float s = __uint_as_float(sv[q8 * 8 + e]) * sl2 + bias * kL2e;
+                        const bool ok = row_ok && (col < kv_valid);
+                        const float pe = ok ? bwd_exp2(s - lse2) : 0.f;
+                        pv[e] = pe;
+                        dsv[e] = ok ? pe * (__uint_as_float(dpv[q8 * 8 + e]) - delta) : 0.f;
+                    }
+                    uint4 pk, dk;
+                    pk.x = pack_bf16(pv[0], pv[1]); pk.y = pack_bf16(pv[2], pv[3]);
+                    pk.z = pack_bf16(pv[4], pv[5]); pk.w = pack_bf16(pv[6], pv[7]);
+                    dk.x = pack_bf16(dsv[0], dsv[1]); dk.y = pack_bf16(dsv[2], dsv[3]);
+                    dk.z = pack_bf16(dsv[4], dsv[5]); dk.w = pack_bf16(dsv[6], dsv[7]);
+                    *reinterpret_cast<uint4 *>(sP + c8 * (kTile * 16) + tid * 16) = pk;
+                    *reinterpret_cast<uint4 *>(sdS + c8 * (kTile * 16) + tid * 16) = dk;
+                    if (row_ok) {   // d(bias) = dS, fp32, this thread's row
+                        const int colb = c8 * 8;
+                        if (colb + 8 <= kv_valid) {
+                            float4 *d4 = reinterpret_cast<float4 *>(db_row + colb);
+                            float4 v0 = make_float4(dsv[0], dsv[1], dsv[2], dsv[3]);
+                            float4 v1 = make_float4(dsv[4], dsv[5], dsv[6], dsv[7]);
+                            if (p.accumulate) {
+                                const float4 o0 = d4[0], o1 = d4[1];
+                                v0.x += o0.x; v0.y += o0.y; v0.z += o0.z; v0.w += o0.w;
+                                v1.x += o1.x; v1.y += o1.y; v1.z += o1.z; v1.w += o1.w;
+                            }
+                            d4[0] = v0;
+                            d4[1] = v1;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (colb + e < kv_valid) db_row[colb + e] = p.accumulate ? db_row[colb + e] + dsv[e] : dsv[e];
+                        }
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t aP = smem_u32(sP), aS = smem_u32(sdS), bQ = smem_u32(sQ), bdO = smem_u32(sdO);
+                const uint32_t bK = smem_u32(sK + (size_t)j * kBoxBytes);
+                const uint32_t id_t = make_idesc_bf16(kTile, 32, 1, 1);   // A = P^T / dS^T (MN-major), B MN-major
+                const uint32_t id_q = make_idesc_bf16(kTile, 32, 0, 1);   // A = dS (K-major),        B MN-major
+                for (int ks = 0; ks < qk / 16; ++ks)      // dV_j += P^T dO_i   (K = query rows)
+                    umma_bf16(tdV, make_smem_desc(aP + ks * 256, 128, kTile * 16),
+                              make_smem_desc(bdO + ks * 256, 128, kTile * 16), id_t, (i > 0 || ks > 0));
+                for (int ks = 0; ks < qk / 16; ++ks)      // dK_j += dS^T Q_i
+                    umma_bf16(tdK, make_smem_desc(aS + ks * 256, 128, kTile * 16),
+                              make_smem_desc(bQ + ks * 256, 128, kTile * 16), id_t, (i > 0 || ks > 0));
+                for (int ks = 0; ks < nb / 16; ++ks)      // dQ_i += dS K_j     (K = key rows)
+                    umma_bf16(tdQ + 32 * i, make_smem_desc(aS + ks * 2 * kTile * 16, kTile * 16, 128),
+                              make_smem_desc(bK + ks * 256, 128, kTile * 16), id_q, (j > 0 || ks > 0));
+                umma_commit(&bar_mma);
+            }
+            __syncwarp();
+        }
+        // ---- dK_j, dV_j complete: TMEM -> bf16 -> global (key row = j*128 + tid)
+        mbar_wait(&bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        first = true;   // the wait above already covered the last iteration's MMAs
+        {
+            uint32_t kvv[32];
+            const int krow = j * kTile + tid;
+            tmem_ld32(tdK + lane_off, kvv);
+            tmem_ld_wait();
+            if (krow < Tg) {
+                uint32_t w[12];
+#pragma unroll
+                for (int e = 0; e < 12; ++e)
+                    w[e] = pack_bf16(__uint_as_float(kvv[2 * e]) * p.scale, __uint_as_float(kvv[2 * e + 1]) * p.scale);
+                uint4 *dst = reinterpret_cast<uint4 *>(p.dk + (size_t)(t0 + krow) * p.dqkv_stride + h * kAttD);
+                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+            }
+            tmem_ld32(tdV + lane_off, kvv);
+            tmem_ld_wait();
+            if (krow < Tg) {
+                uint32_t w[12];
+#pragma unroll
+                for (int e = 0; e < 12; ++e) w[e] = pack_bf16(__uint_as_float(kvv[2 * e]), __uint_as_float(kvv[2 * e + 1]));
+                uint4 *dst = reinterpret_cast<uint4 *>(p.dv + (size_t)(t0 + krow) * p.dqkv_stride + h * kAttD);
+                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    // ---- dQ_i for every query tile
+    tc_fence_after();
+    for (int i = 0; i < NB; ++i) {
+        uint32_t qv[32];
+        const int row = i * kTile + tid;
+        tmem_ld32(tdQ + 32 * i + lane_off, qv);
+        tmem_ld_wait();
+        if (row < Tg) {
+            uint32_t w[12];
+#pragma unroll
+            for (int e = 0; e < 12; ++e)
+                w[e] = pack_bf16(__uint_as_float(qv[2 * e]) * p.scale, __uint_as_float(qv[2 * e + 1]) * p.scale);
+            uint4 *dst = reinterpret_cast<uint4 *>(p.dq + (size_t)(t0 + row) * p.dqkv_stride + h * kAttD);
+            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace mobgt
+
+using namespace mobgt;
+
+// Inputs as mobgt_attn_fwd plus o, dout (bf16 [ntok, H*24], contiguous) and lse.  Outputs dq, dk, dv: bf16 with a common
+// row stride (usually slices of one [ntok, 3*H*24] buffer, so the fused projection's backward gets a single tensor);
+// dbias f32 [B,H,T,Tp]: overwritten (accumulate = 0) or accumulated into (accumulate = 1).
+extern "C" int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, int64_t qkv_row_stride, const void *bias,
+                                  const void *o, const void *dout, const float *lse, const int32_t *tok_off, int32_t B,
+                                  int32_t H, int32_t ntok, int32_t T, int32_t Tp, int32_t t_max_host, float scale, void *dq,
+                                  void *dk, void *dv, int64_t dqkv_row_stride, float *dbias, int32_t accumulate, void *stream) {
+    MOBGT_REQUIRE(q && k && v && bias && o && dout && lse && tok_off && dq && dk && dv && dbias, MOBGT_ERR_NULL,
+                  "mobgt_attn_bwd: null pointer");
+    MOBGT_REQUIRE(qkv_row_stride % 8 == 0 && dqkv_row_stride % 8 == 0 && Tp % 8 == 0 && Tp >= T, MOBGT_ERR_BAD_SHAPE,
+                  "mobgt_attn_bwd: strides / Tp must be multiples of 8");
+    MOBGT_REQUIRE(t_max_host >= 1 && t_max_host <= T && T <= MOBGT_MAX_NODES + 1, MOBGT_ERR_BAD_SHAPE,
+                  "mobgt_attn_bwd: t_max=%d T=%d", t_max_host, T);
+    if (B == 0 || ntok == 0) return MOBGT_OK;
+    CUtensorMap tmQ, tmK, tmV, tmdO, tmB;
+    const void *ptrs[4] = {q, k, v, dout};
+    CUtensorMap *maps[4] = {&tmQ, &tmK, &tmV, &tmdO};
+    for (int i = 0; i < 4; ++i) {
+        uint64_t dims[3] = {8, (uint64_t)ntok, (uint64_t)H * kAttChunks};
+        uint64_t str[2] = {(uint64_t)(i < 3 ? qkv_row_stride : H * kAttD) * 2, 16};
+        uint32_t box[3] = {8, kTile, kAttChunks};
+        int32_t rc = encode_tmap_bf16(maps[i], ptrs[i], 3, dims, str, box, 0);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)Tp, (uint64_t)T, (uint64_t)B * H};
+        uint64_t str[2] = {(uint64_t)Tp * 2, (uint64_t)T * Tp * 2};
+        uint32_t box[3] = {64, kTile, 1};
+        int32_t rc = encode_tmap_bf16(&tmB, bias, 3, dims, str, box, 1);
+        if (rc) return rc;
+    }
+    const int max_boxes = ceil_div(t_max_host, kTile);
+    const size_t smem = (size_t)kBiasTileBytes + 2 * kPBytes + 2 * kBoxBytes + (size_t)2 * max_boxes * kBoxBytes + 1024;
+    MOBGT_CUDA_OK(cudaFuncSetAttribute(k3_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AttnBwdParams p{tok_off,
+                    static_cast<const __nv_bfloat16 *>(o),
+                    static_cast<const __nv_bfloat16 *>(dout),
+                    lse,
+                    static_cast<__nv_bfloat16 *>(dq),
+                    static_cast<__nv_bfloat16 *>(dk),
+                    static_cast<__nv_bfloat16 *>(dv),
+                    dqkv_row_stride,
+                    dbias,
+                    H,
+                    T,
+                    Tp,
+                    scale,
+                    max_boxes,
+                    accumulate};
+    k3_attn_bwd_kernel<<<B * H, 128, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmdO, tmB, p);
+    MOBGT_LAUNCH_OK("k3_attn_bwd_kernel");
+    return MOBGT_OK;
+}

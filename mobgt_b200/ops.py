@@ -91,6 +91,69 @@ def attn_fwd_raw(qkv, bias, batch, scale=None):
     return out, lse
 
 
+def attn_bwd_raw(qkv, bias, out, dout, lse, batch, dbias, accumulate, scale=None):
+    """-> dqkv bf16 [ntok, 3*H*24]; dbias (f32 [B,H,T,Tp]) is written / accumulated in place."""
+    ntok = qkv.shape[0]
+    B, H, T, Tp = bias.shape
+    D = H * HEAD_DIM
+    assert dout.is_contiguous() and out.is_contiguous() and dbias.dtype == torch.float32 and dbias.shape == bias.shape
+    dqkv = torch.empty_like(qkv)
+    scale = float(HEAD_DIM ** -0.5) if scale is None else float(scale)
+    base, dbase = qkv.data_ptr(), dqkv.data_ptr()
+    _C.call("mobgt_attn_bwd", base, base + 2 * D, base + 4 * D, 3 * D, _C.ptr(bias), _C.ptr(out), _C.ptr(dout), _C.ptr(lse),
+            _C.ptr(batch.tok_off), B, H, ntok, T, Tp, int(batch.N) + 1, scale, dbase, dbase + 2 * D, dbase + 4 * D, 3 * D,
+            _C.ptr(dbias), int(accumulate), _C.stream_ptr())
+    return dqkv
+
+
+class BiasedAttention(torch.autograd.Function):
+    """softmax(scale * q k^T + bias) v per packed graph and head (model_fqandtoyo.py:1693-1706).
+
+    `bias_slot` carries the bias tensor and the shared fp32 dBias accumulation buffer: the bias is one tensor
+    used by every encoder layer, so each layer's backward adds its dS into bias_slot.dbias in place (first
+    writer overwrites) and the gradient w.r.t. `bias` is delivered once, by BiasGradSink below."""
+
+    @staticmethod
+    def forward(ctx, qkv, bias_slot):
+        out, lse = attn_fwd_raw(qkv, bias_slot.bias, bias_slot.batch)
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.slot = bias_slot
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse = ctx.saved_tensors
+        slot = ctx.slot
+        if slot.dbias is None:
+            slot.dbias = torch.empty(slot.bias.shape, dtype=torch.float32, device=qkv.device)
+            acc = 0
+        else:
+            acc = 1
+        dqkv = attn_bwd_raw(qkv, slot.bias, out, dout.contiguous(), lse, slot.batch, slot.dbias, acc)
+        return dqkv, None
+
+
+class BiasSlot:
+    def __init__(self, bias, batch):
+        self.bias, self.batch, self.dbias = bias, batch, None
+
+
+class BiasGradSink(torch.autograd.Function):
+    """Identity on a token tensor in forward; in backward (which autograd runs after every encoder layer's backward,
+    because it sits before layer 0) it hands the accumulated dBias to the bias tensor's autograd edge."""
+
+    @staticmethod
+    def forward(ctx, tok, bias, slot):
+        ctx.slot = slot
+        return tok.view_as(tok)
+
+    @staticmethod
+    def backward(ctx, dtok):
+        slot = ctx.slot
+        db, slot.dbias = slot.dbias, None
+        return dtok, db, None
+
+
 # ----------------------------------------------------------------------------------------------- K4
 def embed_gather_raw(batch, cat_of_poi, Gd, Tm, Gc, out_dtype=torch.bfloat16):
     nn_ = int(batch.x_nodes.numel())

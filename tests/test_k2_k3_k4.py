@@ -188,3 +188,54 @@ def test_embed_gather_sum_and_segment_sum(lib_built):
     part = ops.segment_sum_raw(src, 64, 32, plan, 2000)
     ref = torch.zeros(2000, 32, dtype=torch.float64).index_add_(0, b.tok_pos.cpu().long(), src[:, 64:96].cpu().double())
     assert torch.allclose(part.cpu().double(), ref, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("cfg,B,cap,nfix", [("tiny", 6, 12, None), ("c1", 8, 60, None), ("c1", 5, 128, 128),
+                                            ("c1", 3, 300, 300), ("c1", 2, 512, 512)])
+def test_attention_bwd_matches_torch_autograd(lib_built, cfg, B, cap, nfix):
+    from mobgt_b200 import ops
+    w, items, ob, b = make_case(cfg, B, cap, n_fixed=nfix)
+    R, Pp, E, W, t = tables(seed=9)
+    cu = [x.cuda().contiguous() for x in (R, Pp, E, W.view(-1), t.view(-1))]
+    bias = ops.bias_fwd_raw(b, *cu, out_dtype=torch.bfloat16)
+    ntok = int(b.tok_pos.numel())
+    gen = torch.Generator().manual_seed(21)
+    qkv = (torch.randn(ntok, 3 * 192, generator=gen) * 1.2).to(torch.bfloat16)
+    dout = (torch.randn(ntok, 192, generator=gen)).to(torch.bfloat16)
+    out, lse = ops.attn_fwd_raw(qkv.cuda(), bias, b)
+    dbias = torch.full(bias.shape, float("nan"), dtype=torch.float32, device="cuda")
+    dqkv = ops.attn_bwd_raw(qkv.cuda(), bias, out, dout.cuda(), lse, b, dbias, 0)
+    dbias2 = dbias.clone()
+    ops.attn_bwd_raw(qkv.cuda(), bias, out, dout.cuda(), lse, b, dbias2, 1)      # accumulate: 2x
+    torch.cuda.synchronize()
+    # fp32 autograd reference on the same bf16-rounded inputs
+    tok_off = b.tok_off.cpu().numpy()
+    q32 = qkv.float().requires_grad_(True)
+    b32 = bias.float().cpu().requires_grad_(True)
+    ref, _ = torch_attention_diff(q32, b32, tok_off)
+    (ref * dout.float()).sum().backward()
+    gq = q32.grad
+    scale = gq.abs().max().item()
+    err = (dqkv.float().cpu() - gq).abs().max().item()
+    assert err <= 2e-2 * max(1.0, scale), f"dqkv max err {err} (scale {scale})"
+    for g in range(B):
+        Tg = int(tok_off[g + 1] - tok_off[g])
+        gb = b32.grad[g, :, :Tg, :Tg]
+        got = dbias[g, :, :Tg, :Tg].cpu()
+        assert torch.isfinite(got).all()
+        assert (got - gb).abs().max().item() <= 2e-2 * max(1.0, gb.abs().max().item())
+        assert torch.allclose(dbias2[g, :, :Tg, :Tg].cpu(), 2 * got, rtol=1e-6, atol=1e-7)
+
+
+def torch_attention_diff(qkv, bias, tok_off, H=8, d=24):
+    D = H * d
+    outs = []
+    for g in range(len(tok_off) - 1):
+        a, e = int(tok_off[g]), int(tok_off[g + 1])
+        T = e - a
+        q = qkv[a:e, :D].view(T, H, d).transpose(0, 1)
+        k = qkv[a:e, D:2 * D].view(T, H, d).transpose(0, 1)
+        v = qkv[a:e, 2 * D:].view(T, H, d).transpose(0, 1)
+        s = (q * d ** -0.5) @ k.transpose(1, 2) + bias[g, :, :T, :T]
+        outs.append((torch.softmax(s, -1) @ v).transpose(0, 1).reshape(T, D))
+    return torch.cat(outs), None
