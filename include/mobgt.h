@@ -45,6 +45,8 @@ extern "C" {
 int32_t mobgt_version(void);
 /* Copies the calling thread's last error message (NUL-terminated) into buf. */
 int32_t mobgt_last_error(char *buf, size_t buflen);
+/* Process-wide count of libmobgt kernel launches so far (bench.py reports the per-step delta). */
+int32_t mobgt_launch_count(int64_t *out);
 /* 0 if a CUDA device of compute capability 10.x is current, else MOBGT_ERR_CUDA. */
 int32_t mobgt_device_check(void);
 

@@ -22,6 +22,7 @@ SIGNATURES = {
     "mobgt_version": [],
     "mobgt_last_error": [ctypes.c_char_p, ctypes.c_size_t],
     "mobgt_device_check": [],
+    "mobgt_launch_count": [c_p],
     "mobgt_apsp_edge_input": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p],
     "mobgt_gen_edge_input": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p],
     "mobgt_degrees": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_p, c_p, c_p],
@@ -92,3 +93,10 @@ def require_cuda():
         raise MobgtError("the MobGT hot path runs on a B200 (sm_100a) only: no CUDA device is available "
                          "and there is no CPU fallback")
     call("mobgt_device_check")
+
+
+def launch_count():
+    """libmobgt kernels launched by this process so far."""
+    v = ctypes.c_int64(0)
+    call("mobgt_launch_count", ctypes.byref(v))
+    return int(v.value)

@@ -11,6 +11,7 @@
 namespace mobgt {
 
 void set_error(const char *fmt, ...);
+void count_launch();   // bumps the process-wide kernel-launch counter (mobgt_launch_count)
 
 inline int32_t cuda_fail(cudaError_t e, const char *what) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -27,6 +28,7 @@ inline int32_t cuda_fail(cudaError_t e, const char *what) {
     do {                                                                 \
         cudaError_t _e = cudaGetLastError();                             \
         if (_e != cudaSuccess) return ::mobgt::cuda_fail(_e, "launch " name); \
+        ::mobgt::count_launch();                                         \
     } while (0)
 
 #define MOBGT_REQUIRE(cond, code, ...)   \

@@ -1,8 +1,12 @@
 // Library-wide state: version, thread-local error string, device check.
 #include "common.cuh"
 
+#include <atomic>
+
 namespace mobgt {
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -28,5 +32,12 @@ extern "C" int32_t mobgt_device_check(void) {
     MOBGT_CUDA_OK(cudaGetDeviceProperties(&p, dev));
     MOBGT_REQUIRE(p.major == 10, MOBGT_ERR_CUDA, "libmobgt is built for sm_100a only; device is sm_%d%d", p.major,
                   p.minor);
+    return MOBGT_OK;
+}
+
+// Number of libmobgt kernels launched by this process so far (bench.py reports the per-step delta).
+extern "C" int32_t mobgt_launch_count(int64_t *out) {
+    if (!out) return MOBGT_ERR_NULL;
+    *out = mobgt::g_launches.load(std::memory_order_relaxed);
     return MOBGT_OK;
 }

@@ -387,6 +387,7 @@ extern "C" int32_t mobgt_apsp_edge_input(const uint8_t *feat, const int32_t *n, 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     MOBGT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p, C));
+    count_launch();
     return MOBGT_OK;
 }
 

@@ -1,0 +1,365 @@
+"""`Graphormer` — the MobGT network (reference: graphormer/model_fqandtoyo.py:580-1641), B200-native hot path.
+
+Drop-in surface kept from the reference:
+  * constructor hyper-parameters / flag names (model_fqandtoyo.py:581-603, 1619-1641, incl. the reference's own
+    spelling `intput_dropout_rate`);
+  * `forward(batched_data, perturb=None) -> [poi_logits, cat_logits]` (:1123, :1393-1428);
+  * `training_step`, `validation_step`, `test_step`, `test_epoch_end`, `configure_optimizers` (:1434-1616);
+  * parameter names (`state_dict` keys) of every module the live forward uses.
+The reference's host loops (per-graph embedding loop :1257-1269, per-token user fuse :1353-1358 — of which only token 0 is
+ever consumed, :1394-1396) are replaced by packed var-len tensors and the libmobgt kernels:
+  K2 AttnBias -> K4 EmbedGather / EmbedSum -> 6 x (fused QKV GEMM -> K3 BiasedAttention -> FFN) -> user fuse -> heads.
+Padding tokens are never materialised: their keys are masked (-inf columns) in every layer and only token 0 reaches
+the heads, so logits and all gradients are identical to the padded computation.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .lr import PolynomialDecayLR
+
+NODE_DIM = 2000    # model_fqandtoyo.py:567
+
+DATASET_TRAITS = {
+    # per-dataset constructor differences (model_fqandtoyo.py:636-779, 781-900, 902-1029)
+    "foursquaregraph": dict(time_rows=49, time_pad=0, user_extra=0, cat_extra=0, poi_extra=0, log_softmax=False),
+    "gowalla_nevda": dict(time_rows=48, time_pad=0, user_extra=0, cat_extra=1, poi_extra=1, log_softmax=False),
+    "gowalla_7day": dict(time_rows=48, time_pad=0, user_extra=0, cat_extra=1, poi_extra=1, log_softmax=False),
+    "toyotagraph": dict(time_rows=48, time_pad=None, user_extra=1, cat_extra=0, poi_extra=1, log_softmax=True),
+}
+
+
+class _SpMM(torch.autograd.Function):
+    """Y = A @ S for a fixed row-normalised sparse adjacency (modelGNN.py:40 `torch.spmm(adj, support)`); A^T is kept
+    so the backward is one more SpMM.  (cuSPARSE through torch: SURVEY.md §8f "next #1" — not yet a libmobgt kernel.)"""
+
+    @staticmethod
+    def forward(ctx, A, At, S):
+        ctx.At = At
+        return torch.sparse.mm(A, S)
+
+    @staticmethod
+    def backward(ctx, dY):
+        return None, None, torch.sparse.mm(ctx.At, dY.contiguous())
+
+
+class GraphConvolution(nn.Module):
+    """modelGNN.py:21-50"""
+
+    def __init__(self, in_features, out_features):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(in_features, out_features))
+        self.bias = nn.Parameter(torch.empty(out_features))
+        stdv = 1.0 / math.sqrt(out_features)
+        self.weight.data.uniform_(-stdv, stdv)
+        self.bias.data.uniform_(-stdv, stdv)
+
+    def forward(self, x, adj):
+        return _SpMM.apply(adj[0], adj[1], torch.mm(x, self.weight)) + self.bias
+
+
+class GCN(nn.Module):
+    """modelGNN.py:53-73"""
+
+    def __init__(self, ninput, nhid, noutput, dropout):
+        super().__init__()
+        ch = [ninput] + nhid + [noutput]
+        self.gcn = nn.ModuleList([GraphConvolution(ch[i], ch[i + 1]) for i in range(len(ch) - 1)])
+        self.dropout = dropout
+
+    def forward(self, x, adj):
+        for i in range(len(self.gcn) - 1):
+            x = F.leaky_relu(self.gcn[i](x, adj), 0.2)
+        x = F.dropout(x, self.dropout, training=self.training)
+        return self.gcn[-1](x, adj)
+
+
+class FuseEmbeddings(nn.Module):
+    """model_fqandtoyo.py:440-455"""
+
+    def __init__(self, d1, d2):
+        super().__init__()
+        self.fuse_embed = nn.Linear(d1 + d2, d1 + d2)
+
+    def forward(self, a, b):
+        return F.leaky_relu(self.fuse_embed(torch.cat((a, b), a.dim() - 1)), 0.2)
+
+
+class UserEmbeddings(nn.Module):
+    """model_fqandtoyo.py:411-422"""
+
+    def __init__(self, n, d):
+        super().__init__()
+        self.user_embedding = nn.Embedding(n, d)
+
+    def forward(self, i):
+        return self.user_embedding(i)
+
+
+class LearnablePositionalEncoding(nn.Module):
+    """model_fqandtoyo.py:330-358: pe[q+1] is added to node q ('node_reverse'), pe[0] to the graph token ('pos0');
+    both are fused into K4 (ops.EmbedSum); this module only owns the table (and the reference's Dropout(0.1))."""
+
+    def __init__(self, d_model, max_len, dropout=0.1):
+        super().__init__()
+        self.pe = nn.Parameter(torch.empty(d_model, max_len))
+        nn.init.uniform_(self.pe, -0.02, 0.02)
+        self.p = dropout
+
+
+class FeedForwardNetwork(nn.Module):
+    """model_fqandtoyo.py:1644-1656"""
+
+    def __init__(self, hidden_size, ffn_size, dropout_rate):
+        super().__init__()
+        self.layer1 = nn.Linear(hidden_size, ffn_size)
+        self.gelu = nn.GELU()
+        self.layer2 = nn.Linear(ffn_size, hidden_size)
+
+    def forward(self, x):
+        return self.layer2(self.gelu(self.layer1(x)))
+
+
+class MultiHeadAttention(nn.Module):
+    """model_fqandtoyo.py:1659-1711.  q/k/v projections run as ONE fused GEMM (their weights stay separate parameters
+    for state_dict compatibility); the core softmax(q k^T * scale + bias) v is K3 (ops.BiasedAttention)."""
+
+    def __init__(self, hidden_size, attention_dropout_rate, num_heads):
+        super().__init__()
+        self.num_heads = num_heads
+        self.att_size = hidden_size // num_heads
+        self.scale = self.att_size ** -0.5
+        self.linear_q = nn.Linear(hidden_size, num_heads * self.att_size)
+        self.linear_k = nn.Linear(hidden_size, num_heads * self.att_size)
+        self.linear_v = nn.Linear(hidden_size, num_heads * self.att_size)
+        self.attention_dropout_rate = attention_dropout_rate
+        self.output_layer = nn.Linear(num_heads * self.att_size, hidden_size)
+
+    def forward(self, x, bias_slot):
+        w = torch.cat([self.linear_q.weight, self.linear_k.weight, self.linear_v.weight], 0)
+        b = torch.cat([self.linear_q.bias, self.linear_k.bias, self.linear_v.bias], 0)
+        qkv = F.linear(x.to(torch.bfloat16), w.to(torch.bfloat16), b.to(torch.bfloat16))
+        a = ops.BiasedAttention.apply(qkv, bias_slot)
+        return F.linear(a, self.output_layer.weight.to(torch.bfloat16), self.output_layer.bias.to(torch.bfloat16))
+
+
+class EncoderLayer(nn.Module):
+    """model_fqandtoyo.py:1714-1743 (post-LN variant of the live model; `self_attention_norm` exists but is unused)."""
+
+    def __init__(self, hidden_size, ffn_size, dropout_rate, attention_dropout_rate, num_heads):
+        super().__init__()
+        self.self_attention_norm = nn.LayerNorm(hidden_size)
+        self.self_attention = MultiHeadAttention(hidden_size, attention_dropout_rate, num_heads)
+        self.self_attention_dropout = nn.Dropout(dropout_rate)
+        self.ffn_norm1 = nn.LayerNorm(hidden_size)
+        self.ffn_norm2 = nn.LayerNorm(hidden_size)
+        self.ffn = FeedForwardNetwork(hidden_size, ffn_size, dropout_rate)
+        self.ffn_dropout = nn.Dropout(dropout_rate)
+
+    def forward(self, x, bias_slot):
+        # residual stream and LayerNorms in fp32, GEMMs / attention in bf16 (the reference's --precision 16 AMP split)
+        y = self.self_attention(x, bias_slot)
+        x = x + self.self_attention_dropout(y).float()
+        y = self.ffn_norm1(x)
+        f = self.ffn
+        y = F.linear(F.gelu(F.linear(y.to(torch.bfloat16), f.layer1.weight.to(torch.bfloat16), f.layer1.bias.to(torch.bfloat16))),
+                     f.layer2.weight.to(torch.bfloat16), f.layer2.bias.to(torch.bfloat16))
+        x = x + self.ffn_dropout(y).float()
+        return self.ffn_norm2(x)
+
+
+def gradient_tail_loss(inputs, targets, alpha=0.25, beta=1, k=1):
+    """model_fqandtoyo.py:545-550 (`.to("cuda")` dropped: tensors already live on the device)."""
+    one_hot = torch.zeros_like(inputs)
+    one_hot.scatter_(1, targets[:len(inputs)].view(-1, 1), 1)
+    prob = torch.sigmoid(inputs)
+    loss = -alpha * (1 - prob) ** k * one_hot * torch.log(prob) - (1 - one_hot) * beta * prob ** k * torch.log(1 - prob)
+    return loss.mean()
+
+
+class Graphormer(nn.Module):
+    def __init__(self, n_layers, num_heads, hidden_dim, dropout_rate, intput_dropout_rate, weight_decay, ffn_dim,
+                 dataset_name, warmup_updates, tot_updates, peak_lr, end_lr, edge_type, multi_hop_max_dist,
+                 attention_dropout_rate, flag=False, flag_m=3, flag_step_size=1e-3, flag_mag=1e-3, lr_step=2, world=None):
+        super().__init__()
+        if world is None:
+            raise ValueError("Graphormer needs a PoiWorld (the dataset tables the reference reads from ../dataset/<name>/raw, "
+                             "model_fqandtoyo.py:791-832)")
+        if dataset_name not in DATASET_TRAITS:
+            raise NotImplementedError(f"dataset_name={dataset_name!r}: only the POI graph datasets are on the MobGT hot path")
+        if num_heads != ops.NUM_HEADS or (hidden_dim + 64) // num_heads != ops.HEAD_DIM:
+            raise NotImplementedError("libmobgt is built for the canonical MobGT shape: 8 heads, hidden 128 (+64) -> head dim 24")
+        if edge_type != "multi_hop":
+            raise NotImplementedError("edge_type must be 'multi_hop' (README.md:62)")
+        tr = DATASET_TRAITS[dataset_name]
+        self.traits, self.dataset_name = tr, dataset_name
+        self.num_virtual_tokens, self.num_heads, self.hidden_dim = 1, num_heads, hidden_dim
+        self.time_embed_dim = self.cat_embed_dim = 32
+        H, C, P = num_heads, world.C, world.P
+        D = hidden_dim + self.time_embed_dim + self.cat_embed_dim
+        self.edge_type, self.multi_hop_max_dist = edge_type, multi_hop_max_dist
+        self.edge_encoder = nn.Embedding(128, H, padding_idx=0)
+        self.edge_dis_encoder = nn.Embedding(128 * H * H, 1)
+        self.rel_pos_encoder = nn.Embedding(512, H, padding_idx=0)
+        self.poi_distance_model = GCN(3 + C, [16, 64], hidden_dim, 0.3)
+        self.poi_cat_model = GCN(C, [16, 64], self.cat_embed_dim, 0.1)
+        self.user_embed_model = UserEmbeddings(world.U + tr["user_extra"], hidden_dim)
+        self.time_embed_model_48 = nn.Embedding(tr["time_rows"], self.time_embed_dim, padding_idx=tr["time_pad"])
+        self.cat_decoder = nn.Linear(2 * hidden_dim + 64, C + tr["cat_extra"])
+        self.embed_fuse_model2 = FuseEmbeddings(hidden_dim, self.time_embed_dim)
+        self.embed_fuse_model3 = FuseEmbeddings(hidden_dim, D)
+        self.embed_fuse_model4 = FuseEmbeddings(hidden_dim + self.time_embed_dim, self.cat_embed_dim)
+        self.pos_embed = LearnablePositionalEncoding(NODE_DIM, D)
+        self.in_degree_encoder = nn.Embedding(128, D, padding_idx=0)
+        self.out_degree_encoder = nn.Embedding(128, D, padding_idx=0)
+        self.fre_embed_model = nn.Embedding(int(world.check_freq.max()) + 1, D, padding_idx=0)   # only row 0 (== 0) is ever read
+        self.poi_pos_encoder = nn.Embedding(world.num_bins, H, padding_idx=0)
+        self.input_dropout = nn.Dropout(intput_dropout_rate)
+        self.output_dropout = nn.Dropout(intput_dropout_rate)
+        self.layers = nn.ModuleList([EncoderLayer(D, ffn_dim, dropout_rate, attention_dropout_rate, H) for _ in range(n_layers)])
+        self.final_ln = nn.LayerNorm(2 * hidden_dim + 64)
+        self.out_proj = nn.Linear(2 * hidden_dim + 64, P + tr["poi_extra"])
+        self.ELU = nn.ELU()
+        self.graph_token = nn.Embedding(1, D)
+        self.graph_token_virtual_distance = nn.Embedding(1, H)
+        self.warmup_updates, self.tot_updates, self.peak_lr, self.end_lr = warmup_updates, tot_updates, peak_lr, end_lr
+        self.weight_decay, self.lr_step = weight_decay, lr_step
+        self.flag, self.flag_m, self.flag_step_size, self.flag_mag = flag, flag_m, flag_step_size, flag_mag
+        self.metric, self.cat_target = "NLLLoss", None
+        # dataset tables (non-trainable)
+        self.register_buffer("X", torch.from_numpy(world.X), persistent=False)
+        self.register_buffer("C_X", torch.from_numpy(world.C_X), persistent=False)
+        self.register_buffer("cat_of_poi", torch.from_numpy(world.cat_of_poi).int(), persistent=False)
+        for name, csr, n in (("D_A", world.D_A, P), ("C_A", world.C_A, C)):
+            crow, col, val = (torch.from_numpy(a) for a in csr)
+            A = torch.sparse_csr_tensor(crow, col, val, size=(n, n))
+            At = A.to_sparse_coo().t().coalesce().to_sparse_csr()
+            for suffix, m in (("", A), ("_t", At)):
+                self.register_buffer(f"{name}{suffix}_crow", m.crow_indices().clone(), persistent=False)
+                self.register_buffer(f"{name}{suffix}_col", m.col_indices().clone(), persistent=False)
+                self.register_buffer(f"{name}{suffix}_val", m.values().clone(), persistent=False)
+        self._sizes = dict(P=P, C=C)
+        self._adj_cache = {}
+
+    # ------------------------------------------------------------------------------------------
+    def _adj(self, name):
+        key = (name, self.X.device)
+        if key not in self._adj_cache:
+            n = self._sizes["P" if name == "D_A" else "C"]
+            mk = lambda s: torch.sparse_csr_tensor(getattr(self, f"{name}{s}_crow"), getattr(self, f"{name}{s}_col"),
+                                                   getattr(self, f"{name}{s}_val"), size=(n, n))
+            self._adj_cache[key] = (mk(""), mk("_t"))
+        return self._adj_cache[key]
+
+    def gcn_tables(self):
+        """model_fqandtoyo.py:1236-1237: recomputed every forward, like the reference."""
+        return (self.poi_distance_model(self.X, self._adj("D_A")), self.poi_cat_model(self.C_X, self._adj("C_A")))
+
+    def attn_bias(self, b, dtype=torch.bfloat16):
+        """K2 (model_fqandtoyo.py:1143-1216)"""
+        return ops.AttnBias.apply(b, self.rel_pos_encoder.weight, self.poi_pos_encoder.weight, self.edge_encoder.weight,
+                                  self.edge_dis_encoder.weight, self.graph_token_virtual_distance.weight, dtype)
+
+    def node_tokens(self, b, dtype=torch.bfloat16):
+        """K4 (model_fqandtoyo.py:1222-1344) -> packed tokens [ntok, 192]"""
+        Gd, Gc = self.gcn_tables()
+        e = ops.EmbedGather.apply(b, self.cat_of_poi, Gd, self.time_embed_model_48.weight, Gc, dtype)
+        hp = self.hidden_dim + self.time_embed_dim
+        f2, f4 = self.embed_fuse_model2.fuse_embed, self.embed_fuse_model4.fuse_embed
+        x = F.leaky_relu(F.linear(e[:, :hp], f2.weight.to(dtype), f2.bias.to(dtype)), 0.2)              # :1268
+        x = F.leaky_relu(F.linear(torch.cat([x, e[:, hp:]], 1), f4.weight.to(dtype), f4.bias.to(dtype)), 0.2)   # :1269
+        tok = ops.EmbedSum.apply(b, x, self.in_degree_encoder.weight, self.out_degree_encoder.weight, self.pos_embed.pe,
+                                 self.graph_token.weight)
+        return F.dropout(tok, self.pos_embed.p, self.training)                                           # :358
+
+    def forward(self, batched_data, perturb=None):
+        b = batched_data
+        if not hasattr(b, "rel_pos16"):
+            raise TypeError("Graphormer.forward expects a mobgt_b200.collator.Batch1 (packed); build it with "
+                            "mobgt_b200.collator.collator_* or Batch1-from-dense")
+        bias = self.attn_bias(b)
+        tok = self.node_tokens(b)
+        slot = ops.BiasSlot(bias, b)
+        x = ops.BiasGradSink.apply(self.input_dropout(tok).float(), bias, slot)                          # :1347
+        for layer in self.layers:                                                                        # :1348-1352
+            x = layer(x, slot)
+        z0 = x.index_select(0, b.tok_off[:-1].long()).float()                                            # output[:, 0, :]
+        user_embedding = self.user_embed_model(b.user.view(-1) - 1)                                      # :1239
+        z = self.embed_fuse_model3(z0, user_embedding)                                                   # :1356 (token 0 only)
+        z = self.output_dropout(self.ELU(self.final_ln(z)))                                              # :1360-1364
+        cat_output = self.cat_decoder(z)
+        output = self.out_proj(z)
+        if self.traits["log_softmax"]:
+            output = F.log_softmax(output, dim=1)                                                        # :1425
+        self.cat_target = self.cat_of_poi[b.y - 1].long() - 1                                            # :1265
+        return [output, cat_output]
+
+    # ------------------------------------------------------------------------------------------ steps
+    def training_step(self, batched_data, batch_idx=0):
+        """model_fqandtoyo.py:1434-1478"""
+        y_out = self(batched_data)
+        if self.dataset_name == "toyotagraph":
+            loss1 = gradient_tail_loss(y_out[1], self.cat_target, 0.1)
+            loss2 = F.nll_loss(y_out[0], batched_data.y, ignore_index=0)          # data.py:165 NLLLoss(ignore_index=0)
+            return loss1 + loss2
+        return gradient_tail_loss(y_out[0], batched_data.y - 1, 0.2)
+
+    def validation_step(self, batched_data, batch_idx=0):
+        return {"y_pred": self(batched_data), "y_true": batched_data.y - 1}
+
+    def test_step(self, batched_data, batch_idx=0):
+        return {"y_pred": self(batched_data), "y_true": batched_data.y - 1, "idx": batched_data.idx}
+
+    def test_epoch_end(self, outputs):
+        """model_fqandtoyo.py:1546-1597: Acc@{1,5,10,20}, NDCG@k, MRR over all batches; prints the reference's three lines."""
+        from .metrics import get_acc, MRR_metric
+        import numpy as np
+        tot = np.zeros(8)
+        mrr, n = 0.0, 0
+        for o in outputs:
+            acc, ndcg = get_acc(o["y_true"], o["y_pred"][0])
+            mrr += MRR_metric(o["y_true"], o["y_pred"][0])
+            tot += np.array([acc[2, 0], acc[1, 0], acc[0, 0], ndcg[2, 0], ndcg[1, 0], ndcg[0, 0], acc[3, 0], ndcg[3, 0]])
+            n += len(o["y_true"])
+        avg = tot / max(n, 1)
+        print(f"ACC @1: {round(avg[0], 4)}, @5: {round(avg[1], 4)}, @10: {round(avg[2], 4)}")
+        print(f"NDCG @1: {round(avg[3], 4)}, @5: {round(avg[4], 4)}, @10: {round(avg[5], 4)}")
+        print(f"MRR: {round(mrr / max(n, 1), 4)}")
+        return dict(acc1=avg[0], acc5=avg[1], acc10=avg[2], ndcg1=avg[3], ndcg5=avg[4], ndcg10=avg[5], acc20=avg[6],
+                    ndcg20=avg[7], mrr=mrr / max(n, 1))
+
+    def configure_optimizers(self):
+        """model_fqandtoyo.py:1599-1616"""
+        optimizer = torch.optim.AdamW(self.parameters(), lr=self.peak_lr, weight_decay=self.weight_decay, fused=True)
+        sched = PolynomialDecayLR(optimizer, warmup_updates=self.warmup_updates, tot_updates=self.tot_updates, lr=self.peak_lr,
+                                  end_lr=self.end_lr, power=1.0)
+        return [optimizer], [{"scheduler": sched, "name": "learning_rate", "interval": "step", "frequency": 1}]
+
+    @staticmethod
+    def add_model_specific_args(parent_parser):
+        """model_fqandtoyo.py:1618-1641 (same names, defaults and the reference's own typo)."""
+        parser = parent_parser.add_argument_group("Graphormer")
+        parser.add_argument("--n_layers", type=int, default=12)
+        parser.add_argument("--num_heads", type=int, default=32)
+        parser.add_argument("--hidden_dim", type=int, default=512)
+        parser.add_argument("--ffn_dim", type=int, default=512)
+        parser.add_argument("--intput_dropout_rate", type=float, default=0.1)
+        parser.add_argument("--dropout_rate", type=float, default=0.1)
+        parser.add_argument("--weight_decay", type=float, default=0.01)
+        parser.add_argument("--attention_dropout_rate", type=float, default=0.1)
+        parser.add_argument("--checkpoint_path", type=str, default="")
+        parser.add_argument("--warmup_updates", type=int, default=60000)
+        parser.add_argument("--tot_updates", type=int, default=1000000)
+        parser.add_argument("--peak_lr", type=float, default=2e-4)
+        parser.add_argument("--end_lr", type=float, default=1e-9)
+        parser.add_argument("--edge_type", type=str, default="multi_hop")
+        parser.add_argument("--validate", action="store_true", default=False)
+        parser.add_argument("--test", action="store_true", default=False)
+        parser.add_argument("--flag", action="store_true")
+        parser.add_argument("--flag_m", type=int, default=3)
+        parser.add_argument("--flag_step_size", type=float, default=1e-3)
+        parser.add_argument("--flag_mag", type=float, default=1e-3)
+        return parent_parser

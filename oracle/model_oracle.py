@@ -177,7 +177,10 @@ class GraphConvolution(nn.Module):
         self.bias.data.uniform_(-stdv, stdv)
 
     def forward(self, x, adj):
-        return torch.mm(adj, torch.mm(x, self.weight)) + self.bias     # torch.spmm(dense adj, .) == mm
+        s = torch.mm(x, self.weight)
+        # modelGNN.py:40 torch.spmm(adj, support): dense mm in the reference; a sparse COO adj gives the same sums without
+        # the P x P dense matrix (14 GB at P = 60 000) and is used for the large synthetic worlds
+        return (torch.sparse.mm(adj, s) if adj.is_sparse else torch.mm(adj, s)) + self.bias
 
 
 class GCN(nn.Module):
@@ -288,10 +291,13 @@ DATASET_TRAITS = {
 }
 
 
-def csr_to_dense(csr, n):
+def csr_to_dense(csr, n, sparse=False):
     crow, col, val = csr
-    a = torch.zeros(n, n)
     rows = np.repeat(np.arange(n), np.diff(crow))
+    if sparse:
+        idx = torch.from_numpy(np.stack([rows, np.asarray(col)]))
+        return torch.sparse_coo_tensor(idx, torch.from_numpy(np.asarray(val)), (n, n)).coalesce()
+    a = torch.zeros(n, n)
     a[torch.from_numpy(rows), torch.from_numpy(np.asarray(col))] = torch.from_numpy(np.asarray(val))
     return a
 
@@ -333,8 +339,8 @@ class Graphormer(nn.Module):
         # non-parameter tables (model_fqandtoyo.py:791-832, 1106-1108)
         self.register_buffer("X", torch.from_numpy(world.X))
         self.register_buffer("C_X", torch.from_numpy(world.C_X))
-        self.register_buffer("D_A", csr_to_dense(world.D_A, P))
-        self.register_buffer("C_A", csr_to_dense(world.C_A, C))
+        self.D_A = csr_to_dense(world.D_A, P, sparse=P > 10000)
+        self.C_A = csr_to_dense(world.C_A, C)
         self.register_buffer("cat_of_poi", torch.from_numpy(world.cat_of_poi))     # poi_idx2cat_idx_dict
 
     # -------------------------------------------------------------------- A2: attention bias
