@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py — MobGT training throughput (trajectory graphs / s) on N B200s, next to the reference's CPU path.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                       # this framework (libmobgt kernels)
+    python bench.py --impl reference --gpus 1 --steps K --warmup W       # the reference's CPU implementation of the path
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W                        # data parallel, one rank per GPU (weak scaling)
+
+Workload (BASELINE.json configs[1]): toyotagraph-shaped synthetic world (60 000 POIs, 300 categories, 995 users),
+hidden 128 (+64), 8 heads, 6 layers, ffn 1024, multi_hop_max_dist 20, batch 256 graphs per GPU, bf16 GEMMs/attention.
+`--workload c2-dense128` (default) = every graph at the 128-node cap (the stress variant SURVEY.md §8d quotes its byte
+counts on); `--workload c2-natural` = node counts drawn from the real Gowalla-Nevada histogram clipped to 128.
+One step = forward + loss + backward + (NCCL all-reduce) + AdamW over one batch; nothing is skipped or cached.
+
+value  = graphs/s with the collated batch already resident in HBM;
+e2e    = graphs/s through the public API from HOST buffers: raw items -> collator (pack, H2D, K1 APSP + path edges on
+         the GPU) -> training step -> loss read back, every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HP = dict(n_layers=6, num_heads=8, hidden_dim=128, dropout_rate=0.1, intput_dropout_rate=0.1, weight_decay=0.01, ffn_dim=1024,
+          warmup_updates=40000, tot_updates=400000, peak_lr=2e-4, end_lr=1e-9, edge_type="multi_hop", multi_hop_max_dist=20,
+          attention_dropout_rate=0.1)      # README.md:62 canonical flags
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tc=d["bf16_tflops"], src="measured")
+    return dict(hbm=6650.0, tc=1590.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        rows = [r for r in rows if len(r) >= 7]
+        if not rows:
+            return out
+        sm = [float(r[0]) for r in rows]
+        out["sm_mhz"] = float(np.median(sm))
+        out["sm_max_mhz"] = float(rows[0][1])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out["reasons"] = [n for i, n in enumerate(names) if any(r[3 + i].strip().lower().startswith("active") for r in rows)]
+        out["samples"] = len(rows)
+        return out
+
+
+def make_workload(workload, world, B, rank, seed=1):
+    from mobgt_b200 import synth
+    n_fixed = 128 if workload == "c2-dense128" else None
+    return synth.make_items(world, B, 128, seed=seed, cfg_id=2, n_fixed=n_fixed, start=rank * B)
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def cpu_reference_rate(workload, steps, warmup, sample=None, verbose=False):
+    """The reference's own CPU implementation of the path on the host cores: compiled algos.pyx (oracle/_ref) when present
+    (else the C port), the collator and model_fqandtoyo restatement (oracle/model_oracle.py), forward + loss + backward +
+    AdamW, torch threads = all cores.  Each step processes a bounded SAMPLE of the workload's batch."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import algos_oracle
+    import build_ref
+    import model_oracle as mo
+    from mobgt_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ref_algos = build_ref.load()
+    world = synth.make_world("c2", seed=1)
+    sample = sample or 4
+    items = make_workload(workload, world, sample, 0)
+    torch.manual_seed(1)
+    model = mo.Graphormer(world, n_layers=HP["n_layers"], ffn_dim=HP["ffn_dim"]).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=HP["peak_lr"], weight_decay=HP["weight_decay"])
+
+    def preprocess(it):
+        if ref_algos is None:
+            return mo.preprocess_item(it, hop_cap=None)
+        saved = (algos_oracle.floyd_warshall, algos_oracle.gen_edge_input)
+        algos_oracle.floyd_warshall = ref_algos.floyd_warshall
+        algos_oracle.gen_edge_input = lambda md, p, ef, hop_cap=None: ref_algos.gen_edge_input(md, p, ef)
+        try:
+            return mo.preprocess_item(it, hop_cap=None)          # full wrapper.py:55-60 cost, 510-deep hop axis included
+        finally:
+            algos_oracle.floyd_warshall, algos_oracle.gen_edge_input = saved
+
+    def step():
+        b = mo.collate([preprocess(it) for it in items], world, multi_hop_max_dist=20, rel_pos_max=1024)
+        loss = model.training_loss(b)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return dict(value=sample * steps / dt, ms_per_step=1e3 * dt / steps, cores=cores, sample_graphs=sample,
+                kind="reference+port" if ref_algos is not None else "port")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, min(args.steps, 12)), max(1, min(args.warmup, 2))
+    r = cpu_reference_rate(args.workload, steps, warm)
+    sample = (f"{r['sample_graphs']} graphs/step of the {args.workload} batch, {steps} timed steps after {warm} warm-up; "
+              f"compiled algos.pyx (oracle/_ref) + CPU restatement of collator/model_fqandtoyo, fwd+bwd+AdamW")
+    line = {"metric": "train_graphs_per_sec", "value": r["value"], "unit": "graphs/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": args.workload, "world": "toyotagraph-shaped P=60000 C=300 U=995", "hidden": 128, "layers": 6,
+                       "heads": 8, "ffn": 1024, "multi_hop_max_dist": 20, "graphs_per_step": r["sample_graphs"]},
+            "cpu_baseline": {"value": r["value"], "unit": "graphs/s", "cores": r["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": r["value"], "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ kernel micro-timing
+def time_kernel(fn, flush, iters=8):
+    """CUDA-event time of fn() on the current stream, L2 flushed before every launch; returns mean ms."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for _ in range(2):
+        fn()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+
+def kernel_report(model, batch, pk):
+    """Per-kernel device time at the workload's shapes + algorithmic bytes -> roofline."""
+    from mobgt_b200 import ops
+    from mobgt_b200.algos import apsp_edge_input_packed
+    dev = torch.device("cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    B, H, T = batch.B, 8, batch.N + 1
+    Tp = ops.bias_pitch(T)
+    n = batch.n_host.astype(np.int64)
+    cells, pairs_t, ntok = int((n * n).sum()), int(((n + 1) ** 2).sum()), int(batch.tok_pos.numel())
+    hops = batch.hops
+    tabs = [t.detach().float().contiguous() for t in (model.rel_pos_encoder.weight, model.poi_pos_encoder.weight,
+                                                       model.edge_encoder.weight, model.edge_dis_encoder.weight.view(-1),
+                                                       model.graph_token_virtual_distance.weight.view(-1))]
+    bias = ops.bias_fwd_raw(batch, *tabs)
+    qkv = torch.randn(ntok, 576, device=dev).to(torch.bfloat16)
+    out, lse = ops.attn_fwd_raw(qkv, bias, batch)
+    dout = torch.randn(ntok, 192, device=dev).to(torch.bfloat16)
+    dbias = torch.zeros(bias.shape, dtype=torch.float32, device=dev)
+    rep = {}
+
+    def add(name, ms, nbytes, per_step, flops=None):
+        rep[name] = dict(ms=ms, gbs=nbytes / ms / 1e6, frac_hbm=nbytes / ms / 1e6 / pk["hbm"], bytes=nbytes, launches_per_step=per_step)
+        if flops:
+            rep[name]["tflops"] = flops / ms / 1e9
+            rep[name]["frac_tc"] = flops / ms / 1e9 / pk["tc"]
+
+    add("k1_apsp_edge_input", time_kernel(lambda: apsp_edge_input_packed(batch.feat8, batch.n, batch.sq_off, batch.n_host, hops, 1), flush),
+        cells * (1 + 2 + hops), 0)
+    add("k2_bias_fwd", time_kernel(lambda: ops.bias_fwd_raw(batch, *tabs), flush), cells * (4 + hops) + H * pairs_t * 2, 1)
+    add("k2_bias_bwd", time_kernel(lambda: ops.bias_bwd_raw(batch, dbias, tabs[2], tabs[3], tabs[1].shape[0]), flush),
+        cells * (4 + hops) + H * pairs_t * 4, 1)
+    fl = 4.0 * H * pairs_t * 24
+    add("k3_attn_fwd", time_kernel(lambda: ops.attn_fwd_raw(qkv, bias, batch), flush), 4 * ntok * 192 * 2 + H * pairs_t * 2, 6, fl)
+    add("k3_attn_bwd", time_kernel(lambda: ops.attn_bwd_raw(qkv, bias, out, dout, lse, batch, dbias, 1), flush),
+        8 * ntok * 192 * 2 + H * pairs_t * 2 + H * pairs_t * 8, 6, 2.5 * fl)
+    Gd, Gc = model.gcn_tables()
+    Gd, Gc = Gd.detach(), Gc.detach()
+    Tm = model.time_embed_model_48.weight.detach()
+    nn_ = ntok - B
+    add("k4_embed_gather", time_kernel(lambda: ops.embed_gather_raw(batch, model.cat_of_poi, Gd, Tm, Gc), flush),
+        nn_ * (192 * 4 + 192 * 2 + 12), 1)
+    nf = torch.randn(nn_, 192, device=dev).to(torch.bfloat16)
+    pe, gt = model.pos_embed.pe.detach(), model.graph_token.weight.detach().view(-1)
+    Din, Dout = model.in_degree_encoder.weight.detach(), model.out_degree_encoder.weight.detach()
+    add("k4_embed_sum", time_kernel(lambda: ops.embed_sum_raw(batch, nf, Din, Dout, pe, gt), flush),
+        nn_ * (192 * 2 + 3 * 192 * 4 + 16) + ntok * 192 * 2, 1)
+    g = torch.randn(ntok, 192, device=dev).to(torch.bfloat16)
+    plan = ops.sort_plan(batch.tok_pos)
+    add("k4_segment_sum", time_kernel(lambda: ops.segment_sum_raw(g, 0, 192, plan, 2000), flush), ntok * (192 * 2 + 8), 6)
+    del flush
+    return rep
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def run_ours(args):
+    import torch.distributed as dist
+    from mobgt_b200 import _C, collator, model as M, synth
+    rank, world_size = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _C.require_cuda()
+    pk = peaks()
+    world = synth.make_world("c2", seed=1)
+    B = args.batch
+    items = make_workload(args.workload, world, B, rank)
+    torch.manual_seed(1)
+    model = M.Graphormer(dataset_name="toyotagraph", world=world, **HP).to(dev).train()
+    params = [p for p in model.parameters()]
+    # one flat fp32 gradient buffer: p.grad are views, so the data-parallel exchange is a single NCCL all-reduce
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    opt = torch.optim.AdamW(params, lr=HP["peak_lr"], weight_decay=HP["weight_decay"], fused=True)
+    from mobgt_b200.lr import PolynomialDecayLR
+    sched = PolynomialDecayLR(opt, HP["warmup_updates"], HP["tot_updates"], HP["peak_lr"], HP["end_lr"], 1.0)
+    latlon = torch.from_numpy(world.latlon).to(dev)
+
+    def collate():
+        return collator.collate_packed(items, world, latlon, 512, 20, 1024, device=dev)
+
+    def train_step(b):
+        flat.zero_()
+        loss = model.training_step(b)
+        loss.backward()
+        if world_size > 1:
+            dist.all_reduce(flat)
+            flat.div_(world_size)
+        opt.step()
+        sched.step()
+        return loss
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b_.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b_)], device=dev)
+        if world_size > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    batch = collate()
+    for _ in range(args.warmup):
+        train_step(batch)
+    n0 = _C.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms = timed(lambda: train_step(batch), args.steps)
+    launches = (_C.launch_count() - n0) / args.steps
+    # end to end: host items -> collate (H2D + K1) -> step -> loss on the host, every step
+    losses = []
+
+    def e2e_step():
+        b = collate()
+        losses.append(float(train_step(b).item()))
+        return b
+
+    for _ in range(max(1, args.warmup // 2)):
+        bb = e2e_step()
+    e2e_steps = max(2, args.steps // 2)
+    ms_e2e = timed(e2e_step, e2e_steps)
+    clocks = sampler.stop() if sampler else None
+    h2d = int(bb.h2d_bytes)
+    if rank == 0:
+        graphs = B * world_size
+        line = {"metric": "train_graphs_per_sec", "value": graphs * args.steps / (ms / 1e3), "unit": "graphs/s",
+                "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": args.workload, "world": "toyotagraph-shaped P=60000 C=300 U=995", "hidden": 128, "layers": 6,
+                           "heads": 8, "ffn": 1024, "multi_hop_max_dist": 20, "graphs_per_gpu": B,
+                           "tokens_per_gpu": int(batch.tok_pos.numel()), "parallelism": f"dp{world_size}",
+                           "l2": "per-step working set (activations + bias planes, > 1 GB) exceeds the 126 MB L2"},
+                "e2e": {"value": graphs * e2e_steps / (ms_e2e / 1e3), "unit": "graphs/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / e2e_steps},
+                "gpu_launches": launches, "clocks": clocks, "final_loss": losses[-1] if losses else None}
+        if world_size == 1 and not args.no_kernel_report:
+            rep = kernel_report(model, batch, pk)
+            top = max(rep, key=lambda k: rep[k]["ms"] * rep[k]["launches_per_step"])
+            r = rep[top]
+            line["roofline"] = {"kernel": top, "bound": "hbm", "achieved": r["gbs"], "peak": pk["hbm"], "unit": "GB/s",
+                                "frac": r["frac_hbm"], "traffic": None, "peak_source": pk["src"],
+                                "share_of_step": r["ms"] * r["launches_per_step"] / (ms / args.steps)}
+            line["kernels"] = {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in rep.items()}
+        if world_size == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_rate(args.workload, steps=4, warmup=1)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "graphs/s", "cores": r["cores"], "kind": "port",
+                                    "sample": f"{r['sample_graphs']} graphs/step of the same batch, 4 timed steps after 1 warm-up; "
+                                              f"compiled algos.pyx (oracle/_ref) when present + CPU restatement of "
+                                              f"collator/model_fqandtoyo (fwd+bwd+AdamW), {r['cores']} torch threads"}
+        print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2-dense128", choices=["c2-dense128", "c2-natural"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-report", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -87,12 +87,19 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+_cuda_ok = False
+
+
 def require_cuda():
+    global _cuda_ok
+    if _cuda_ok:
+        return
     import torch
     if not torch.cuda.is_available():
         raise MobgtError("the MobGT hot path runs on a B200 (sm_100a) only: no CUDA device is available "
                          "and there is no CPU fallback")
     call("mobgt_device_check")
+    _cuda_ok = True
 
 
 def launch_count():

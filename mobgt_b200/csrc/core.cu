@@ -26,12 +26,11 @@ extern "C" int32_t mobgt_last_error(char *buf, size_t buflen) {
 }
 
 extern "C" int32_t mobgt_device_check(void) {
-    int dev = 0;
+    int dev = 0, major = 0, minor = 0;
     MOBGT_CUDA_OK(cudaGetDevice(&dev));
-    cudaDeviceProp p;
-    MOBGT_CUDA_OK(cudaGetDeviceProperties(&p, dev));
-    MOBGT_REQUIRE(p.major == 10, MOBGT_ERR_CUDA, "libmobgt is built for sm_100a only; device is sm_%d%d", p.major,
-                  p.minor);
+    MOBGT_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    MOBGT_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    MOBGT_REQUIRE(major == 10, MOBGT_ERR_CUDA, "libmobgt is built for sm_100a only; device is sm_%d%d", major, minor);
     return MOBGT_OK;
 }
 

@@ -117,6 +117,37 @@ __global__ void __launch_bounds__(256) k2_bias_fwd_kernel(const K2Common c, cons
 }
 
 // ---- backward --------------------------------------------------------------------------------------
+// Histogram add with warp-level pre-aggregation: the keys of one stream (one hop slot, or rel_pos / poi_pos) are
+// heavily duplicated inside a warp (most walks carry the same edge feature), and same-address shared-memory atomics
+// serialise.  Up to two dominant key groups are peeled with a warp reduction (one atomic per head for the whole group);
+// whatever is left goes through individual atomics.  Must be called by all 32 lanes (key < 0 = nothing to add).
+__device__ __forceinline__ void warp_hist_add(float *hist, int key, const float (&w)[8]) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned act = __ballot_sync(full, key >= 0);
+#pragma unroll 1
+    for (int peel = 0; peel < 2 && act; ++peel) {
+        const int l = __ffs(act) - 1;
+        const int kk = __shfl_sync(full, key, l);
+        const unsigned grp = __ballot_sync(full, key == kk);
+        if (__popc(grp) < 3) break;
+        const bool in = key == kk;
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            float s = in ? w[h] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(full, s, o);
+            if (lane == l) atomicAdd(hist + kk * 8 + h, s);
+        }
+        if (in) key = -1;
+        act &= ~grp;
+    }
+    if (key >= 0) {
+#pragma unroll
+        for (int h = 0; h < 8; ++h) atomicAdd(hist + key * 8 + h, w[h]);
+    }
+}
+
 // persistent CTAs; shared-memory histograms dEW[hops][128][8], dR[512][8], dP[bins][8], dt[8]
 __global__ void __launch_bounds__(256) k2_bias_bwd_kernel(const K2Common c, const float *__restrict__ dB, int num_bins,
                                                           float *__restrict__ dEW, float *__restrict__ dR,
@@ -129,40 +160,45 @@ __global__ void __launch_bounds__(256) k2_bias_bwd_kernel(const K2Common c, cons
     __syncthreads();
     const int tiles = ceil_div(c.T * c.T, (int)blockDim.x);
     const size_t hs = (size_t)c.T * c.Tp;
+    const unsigned full = 0xffffffffu;
     for (int w = blockIdx.x; w < tiles * c.B; w += gridDim.x) {
         const int g = w / tiles, tile = w - g * tiles;
         const int n = c.n[g], Tg = n + 1;
         const int cell = tile * blockDim.x + threadIdx.x;
-        if (cell >= Tg * Tg) continue;
         const int a = cell / Tg, b = cell - a * Tg;
-        if (a == 0) continue;
-        const float *src = dB + ((size_t)g * kH * c.T + a) * c.Tp + b;
-        float d[8];
+        const bool in_graph = cell < Tg * Tg && a >= 1;
+        float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (in_graph) {
+            const float *src = dB + ((size_t)g * kH * c.T + a) * c.Tp + b;
 #pragma unroll
-        for (int h = 0; h < 8; ++h) d[h] = src[h * hs];
-        if (b == 0) {
-#pragma unroll
-            for (int h = 0; h < 8; ++h) atomicAdd(st + h, d[h]);
-            continue;
+            for (int h = 0; h < 8; ++h) d[h] = src[h * hs];
         }
-        const int64_t pc = c.sq_off[g] + (int64_t)(a - 1) * n + (b - 1);
-        const int rp = c.rel_pos[pc];
-        const int M = rp - 1;
-        if (M >= c.rel_pos_max) continue;
-        const int pp = c.poi_pos[pc];
-#pragma unroll
-        for (int h = 0; h < 8; ++h) {
-            atomicAdd(sR + rp * kH + h, d[h]);
-            atomicAdd(sP + pp * kH + h, d[h]);
+        // column 0 of rows >= 1: graph-token virtual distance
+        warp_hist_add(st, (in_graph && b == 0) ? 0 : -1, d);
+        bool pair = in_graph && b >= 1;
+        int rp = 0, pp = 0, M = 0;
+        int64_t pc = 0;
+        if (pair) {
+            pc = c.sq_off[g] + (int64_t)(a - 1) * n + (b - 1);
+            rp = c.rel_pos[pc];
+            M = rp - 1;
+            if (M >= c.rel_pos_max) pair = false;     // -inf entries carry no gradient
+            else pp = c.poi_pos[pc];
         }
+        warp_hist_add(sR, pair ? rp : -1, d);
+        warp_hist_add(sP, pair ? pp : -1, d);
         const float inv = 1.0f / (float)min(max(M, 1), c.hops);
+#pragma unroll
+        for (int h = 0; h < 8; ++h) d[h] *= inv;
         const uint8_t *ei = c.edge_in + pc * c.hops;
         for (int k = 0; k < c.hops; ++k) {
-            const int v = ei[k];
-            if (v == 0) break;
-            float *dst = sEW + ((size_t)k * kEdgeVocab + v) * kH;
-#pragma unroll
-            for (int h = 0; h < 8; ++h) atomicAdd(dst + h, d[h] * inv);
+            int v = 0;
+            if (pair) {
+                v = ei[k];
+                if (v == 0) pair = false;              // end of the walk
+            }
+            if (__ballot_sync(full, pair) == 0) break;
+            warp_hist_add(sEW, pair ? k * kEdgeVocab + v : -1, d);
         }
     }
     __syncthreads();
