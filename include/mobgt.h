@@ -158,6 +158,24 @@ int32_t mobgt_segment_sum(const void *src, int32_t src_dtype, int64_t src_stride
                           void *workspace, int64_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K5 — POI-logit head fused with per-row top-k and rank counting.  Replaces out_proj followed by get_acc / MRR_metric
+ * (model_fqandtoyo.py:1396-1428, :48-90, :122-131).  logits = z W^T + bias are produced tile by tile in TMEM and
+ * consumed in the epilogue; they are only written to HBM when logits_dump != NULL (tests).
+ *   z bf16 [M,K] ; W bf16 [V,K] = this rank's vocabulary shard (global index of row 0 = vocab_offset) ; bias f32 [V]|NULL
+ *   target i32 [M] global vocabulary index (<0: none) ; K multiple of 16, <= 320 ; k <= 32 ; nsplit <= 64
+ *   mode 0: st[row] = logit of the row's target, written by the shard that owns it (initialise st to -inf; across
+ *           shards: all-reduce MAX)
+ *   mode 1: per (row, split): sorted top-k (value, global index), count(s > st), count(s == st and idx < target)
+ * mobgt_topk_merge merges S sorted lists per row (ties -> lower index) and sums the counts into rank[M].
+ * ------------------------------------------------------------------------------------------ */
+int32_t mobgt_head_topk(const void *z, const void *W, const float *bias, const int32_t *target, int32_t M, int32_t V,
+                        int32_t K, int64_t vocab_offset, int32_t k, int32_t nsplit, int32_t mode, float *st,
+                        float *topk_val, int32_t *topk_idx, int32_t *cnt_gt, int32_t *cnt_eq, float *logits_dump,
+                        void *stream);
+int32_t mobgt_topk_merge(const float *val, const int32_t *idx, const int32_t *cnt_gt, const int32_t *cnt_eq, int32_t M,
+                         int32_t S, int32_t k, float *out_val, int32_t *out_idx, int32_t *rank, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Test hooks (tests/test_umma_selftest.py): exercise the tcgen05 / TMA building blocks in isolation.
  * out[128,N] (f32) = A * B, bf16 operands; a_mn / b_mn select MN-major operands
  * (A: a_mn ? [K,128] : [128,K];  B: b_mn ? [K,N] : [N,K], all row-major).

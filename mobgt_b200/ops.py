@@ -258,3 +258,97 @@ class EmbedSum(torch.autograd.Function):
         dDin[0].zero_()                 # padding_idx rows / graph-token rows carry key 0
         dDout[0].zero_()
         return None, d_nf, dDin, dDout, dpe, dgt
+
+
+# ----------------------------------------------------------------------------------------------- K5
+def head_split(M, V):
+    """vocabulary splits per 128-row tile of z so that the grid covers the 148 SMs about twice."""
+    mt = (M + 127) // 128
+    nt = (V + 127) // 128
+    return int(max(1, min(64, nt, (2 * 148 + mt - 1) // mt)))
+
+
+def head_topk_local(z, W, bias, target, k, vocab_offset=0, st=None, dump_logits=False):
+    """One vocabulary shard.  z bf16 [M,K], W bf16 [V,K], bias f32 [V]|None, target i32 [M] (global ids).
+    st=None -> runs mode 0 first (single-shard use).  Returns dict(val [M,k], idx [M,k], cnt [M] (partial rank), st)."""
+    M, K = z.shape
+    V = W.shape[0]
+    dev = z.device
+    ns = head_split(M, V)
+    s = _C.stream_ptr()
+    args = (_C.ptr(z), _C.ptr(W), _C.ptr(bias), _C.ptr(target), M, V, K, int(vocab_offset), k, ns)
+    if st is None:
+        st = torch.full((M,), float("-inf"), dtype=torch.float32, device=dev)
+        _C.call("mobgt_head_topk", *args, 0, _C.ptr(st), None, None, None, None, None, s)
+    tv = torch.empty(M, ns, k, dtype=torch.float32, device=dev)
+    ti = torch.empty(M, ns, k, dtype=torch.int32, device=dev)
+    cg = torch.empty(M, ns, dtype=torch.int32, device=dev)
+    ce = torch.empty(M, ns, dtype=torch.int32, device=dev)
+    logits = torch.empty(M, V, dtype=torch.float32, device=dev) if dump_logits else None
+    _C.call("mobgt_head_topk", *args, 1, _C.ptr(st), _C.ptr(tv), _C.ptr(ti), _C.ptr(cg), _C.ptr(ce), _C.ptr(logits), s)
+    val = torch.empty(M, k, dtype=torch.float32, device=dev)
+    idx = torch.empty(M, k, dtype=torch.int32, device=dev)
+    cnt = torch.empty(M, dtype=torch.int32, device=dev)
+    _C.call("mobgt_topk_merge", _C.ptr(tv), _C.ptr(ti), _C.ptr(cg), _C.ptr(ce), M, ns, k, _C.ptr(val), _C.ptr(idx), _C.ptr(cnt), s)
+    return dict(val=val, idx=idx, cnt=cnt, st=st, logits=logits)
+
+
+def head_target_logit(z, W, bias, target, vocab_offset=0):
+    """mode 0 only: st[row] = target logit if this shard owns the target, else -inf."""
+    M, K = z.shape
+    V = W.shape[0]
+    st = torch.full((M,), float("-inf"), dtype=torch.float32, device=z.device)
+    _C.call("mobgt_head_topk", _C.ptr(z), _C.ptr(W), _C.ptr(bias), _C.ptr(target), M, V, K, int(vocab_offset), 1,
+            head_split(M, V), 0, _C.ptr(st), None, None, None, None, None, _C.stream_ptr())
+    return st
+
+
+def topk_merge_lists(val, idx):
+    """val/idx [M, S, k] (each list sorted) -> merged [M, k]."""
+    M, S, k = val.shape
+    ov = torch.empty(M, k, dtype=torch.float32, device=val.device)
+    oi = torch.empty(M, k, dtype=torch.int32, device=val.device)
+    _C.call("mobgt_topk_merge", _C.ptr(val.contiguous()), _C.ptr(idx.contiguous()), None, None, M, S, k, _C.ptr(ov), _C.ptr(oi),
+            None, _C.stream_ptr())
+    return ov, oi
+
+
+def head_topk_sharded(z, W_shard, bias_shard, target, k, vocab_offset, group=None):
+    """Vocabulary-parallel evaluation head: every rank holds rows [vocab_offset, vocab_offset+V_r) of
+    out_proj and the full z.  s_t: owner shard computes it, all-reduce MAX.  Top-k: per-shard lists, all-gather over
+    NVLink (NCCL), k-way merge (ties -> lower index).  Rank of the target: all-reduce SUM of the partial counts."""
+    import torch.distributed as dist
+    st = head_target_logit(z, W_shard, bias_shard, target, vocab_offset)
+    ws = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if ws > 1:
+        dist.all_reduce(st, op=dist.ReduceOp.MAX, group=group)
+    loc = head_topk_local(z, W_shard, bias_shard, target, k, vocab_offset, st=st)
+    if ws == 1:
+        return dict(val=loc["val"], idx=loc["idx"], rank=loc["cnt"], st=st)
+    M = z.shape[0]
+    gv = torch.empty(ws, M, k, dtype=torch.float32, device=z.device)
+    gi = torch.empty(ws, M, k, dtype=torch.int32, device=z.device)
+    dist.all_gather_into_tensor(gv, loc["val"], group=group)
+    dist.all_gather_into_tensor(gi, loc["idx"], group=group)
+    cnt = loc["cnt"].clone()
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+    val, idx = topk_merge_lists(gv.permute(1, 0, 2), gi.permute(1, 0, 2))
+    return dict(val=val, idx=idx, rank=cnt, st=st)
+
+
+def metrics_from_rank(rank, target, ks=(1, 5, 10, 20)):
+    """Acc@k / NDCG@k / MRR sums from the 0-based rank of each target (== the reference's get_acc / MRR_metric sums,
+    model_fqandtoyo.py:48-90, 122-131, including `target > 0` and the break at the first target == 0)."""
+    r = rank.double()
+    t = target.view(-1)
+    zero = (t == 0).nonzero()
+    stop = int(zero[0]) if len(zero) else len(t)
+    live = torch.zeros_like(t, dtype=torch.bool)
+    live[:stop] = True
+    out = {}
+    for k in ks:
+        hit = live & (rank < k) & (t > 0)
+        out[f"acc{k}"] = float(hit.sum())
+        out[f"ndcg{k}"] = float((1.0 / torch.log2(r[hit] + 2)).sum())
+    out["mrr"] = float((1.0 / (r + 1)).sum())
+    return out
