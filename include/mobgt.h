@@ -104,18 +104,22 @@ int32_t mobgt_poi_pos(const int32_t *x, const int32_t *n, const int64_t *sq_off,
  *   padding columns are masked inside the attention kernel from the sequence lengths.
  *   tables: R [512,H] rel_pos_encoder, Ppos [bins,H] poi_pos_encoder, E [128,H] edge_encoder,
  *           W [>=hops*H*H] edge_dis_encoder (viewed [k,h',h]), tvd [H] graph_token_virtual_distance.
- *   workspace: hops*128*H floats (the E.W table; also the dEW scratch of the backward).
+ *   hops is the hop-slot count of edge_in (a multiple of 4, as written by K1) and the clamp of the mean.
+ *   forward workspace: hops*128*H floats (the E.W table); backward workspace: mobgt_bias_bwd_workspace_bytes().
  * Backward: dBias f32 [B,H,T,Tp] (sum over layers) -> dR [512,H], dPpos [bins,H], dE [128,H],
  * dW [hops*H*H], dtvd [H]  (all overwritten).
  * ------------------------------------------------------------------------------------------ */
 int32_t mobgt_bias_fwd(const int32_t *n, const int64_t *sq_off, const int16_t *rel_pos, const int16_t *poi_pos,
                        const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t H,
-                       int32_t rel_pos_max, const float *R, const float *Ppos, const float *E, const float *W,
-                       const float *tvd, void *workspace, void *out, int32_t out_dtype, void *stream);
+                       int32_t rel_pos_max, int32_t num_bins, const float *R, const float *Ppos, const float *E,
+                       const float *W, const float *tvd, void *workspace, void *out, int32_t out_dtype, void *stream);
+/* bytes of `workspace` mobgt_bias_bwd needs (per-CTA partial histograms + totals); < 0 on bad arguments */
+int64_t mobgt_bias_bwd_workspace_bytes(int32_t T, int32_t hops, int32_t num_bins);
 int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const int16_t *rel_pos, const int16_t *poi_pos,
                        const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t H,
                        int32_t rel_pos_max, int32_t num_bins, const float *dBias, const float *E, const float *W,
-                       void *workspace, float *dR, float *dPpos, float *dE, float *dW, float *dtvd, void *stream);
+                       void *workspace, int64_t workspace_bytes, float *dR, float *dPpos, float *dE, float *dW,
+                       float *dtvd, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3 — biased multi-head attention (tcgen05 / TMEM / TMA).  Replaces the core of

@@ -27,10 +27,11 @@ SIGNATURES = {
     "mobgt_gen_edge_input": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p],
     "mobgt_degrees": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_p, c_p, c_p],
     "mobgt_poi_pos": [c_p, c_p, c_p, c_p, c_p, c_f32, c_i32, c_i32, c_i32, c_p, c_p],
-    "mobgt_bias_fwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
-                       c_i32, c_p],
-    "mobgt_bias_bwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p,
-                       c_p, c_p, c_p, c_p, c_p],
+    "mobgt_bias_fwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p,
+                       c_p, c_i32, c_p],
+    "mobgt_bias_bwd_workspace_bytes": [c_i32, c_i32, c_i32],
+    "mobgt_bias_bwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_i64,
+                       c_p, c_p, c_p, c_p, c_p, c_p],
     "mobgt_attn_fwd": [c_p, c_p, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_p, c_p, c_p],
     "mobgt_attn_bwd": [c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_p, c_p,
                        c_p, c_i64, c_p, c_i32, c_p],
@@ -57,7 +58,7 @@ def lib():
         for name, argt in SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = argt
-            fn.restype = c_i32
+            fn.restype = c_i64 if name.endswith("_bytes") else c_i32
         _lib = L
     return _lib
 

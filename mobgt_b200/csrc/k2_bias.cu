@@ -56,156 +56,349 @@ __device__ __forceinline__ void add8(float (&a)[8], const float *__restrict__ p)
     a[4] += y.x; a[5] += y.y; a[6] += y.z; a[7] += y.w;
 }
 
-template <typename OutT>
-__device__ __forceinline__ void store_out(OutT *p, float v);
-template <>
-__device__ __forceinline__ void store_out<float>(float *p, float v) { *p = v; }
-template <>
-__device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 
-// persistent CTAs (the EW table is staged once per CTA); one thread per (a, b) token pair, 8 heads each.
 template <typename OutT>
-__global__ void __launch_bounds__(256) k2_bias_fwd_kernel(const K2Common c, const float *__restrict__ R,
-                                                          const float *__restrict__ Pp, const float *__restrict__ tvd,
-                                                          const float *__restrict__ EWg, OutT *__restrict__ out) {
-    extern __shared__ __align__(16) float EW[];  // [hops][128][8]
-    const int tabn = c.hops * kEdgeVocab * kH;
-    for (int i = threadIdx.x * 4; i < tabn; i += blockDim.x * 4)
+__device__ __forceinline__ void store2(OutT *p, float a, float b);
+template <>
+__device__ __forceinline__ void store2<float>(float *p, float a, float b) { *reinterpret_cast<float2 *>(p) = make_float2(a, b); }
+template <>
+__device__ __forceinline__ void store2<__nv_bfloat16>(__nv_bfloat16 *p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162 *>(p) = __floats2bfloat162_rn(a, b);
+}
+template <typename OutT>
+__device__ __forceinline__ void store1(OutT *p, float a);
+template <>
+__device__ __forceinline__ void store1<float>(float *p, float a) { *p = a; }
+template <>
+__device__ __forceinline__ void store1<__nv_bfloat16>(__nv_bfloat16 *p, float a) { *p = __float2bfloat16_rn(a); }
+
+// Forward.  Persistent CTAs: EW [hops][128][8], R [512][8] and Ppos [bins][8] are staged once per CTA in shared memory.
+// One thread per PAIR OF ADJACENT CELLS (a, b) (a, b+1), b even, of the Tp-pitched plane row, so every head plane is
+// written as 4-byte (bf16x2) / 8-byte (f32x2) words and a warp covers 64 consecutive columns.  All index bytes of a
+// thread's two cells (2 x (2 + 2 + hops) B) are fetched up front as independent 32-bit loads; the hop loop then
+// runs out of registers and shared memory only.
+template <typename OutT>
+__global__ void __launch_bounds__(512, 2) k2_bias_fwd_kernel(const K2Common c, const float *__restrict__ Rg,
+                                                             const float *__restrict__ Pg, int num_bins,
+                                                             const float *__restrict__ tvd,
+                                                             const float *__restrict__ EWg, OutT *__restrict__ out) {
+    extern __shared__ __align__(16) float sm[];
+    const int nEW = c.hops * kEdgeVocab * kH, nR = 512 * kH, nP = num_bins * kH;
+    float *EW = sm, *R = EW + nEW, *Pp = R + nR;
+    for (int i = threadIdx.x * 4; i < nEW; i += blockDim.x * 4)
         *reinterpret_cast<float4 *>(EW + i) = *reinterpret_cast<const float4 *>(EWg + i);
+    for (int i = threadIdx.x * 4; i < nR; i += blockDim.x * 4)
+        *reinterpret_cast<float4 *>(R + i) = *reinterpret_cast<const float4 *>(Rg + i);
+    for (int i = threadIdx.x * 4; i < nP; i += blockDim.x * 4)
+        *reinterpret_cast<float4 *>(Pp + i) = *reinterpret_cast<const float4 *>(Pg + i);
+    float tv[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) tv[h] = tvd[h];
     __syncthreads();
-    const int tiles = ceil_div(c.T * c.T, (int)blockDim.x);
+    const int hopw = c.hops >> 2;                 // hops is a multiple of 4
+    const int half = c.Tp >> 1;                   // cell pairs per plane row
+    const int per_graph = c.T * half;
+    const int tiles = ceil_div(per_graph, (int)blockDim.x);
     const size_t hs = (size_t)c.T * c.Tp;
     for (int w = blockIdx.x; w < tiles * c.B; w += gridDim.x) {
         const int g = w / tiles, tile = w - g * tiles;
         const int n = c.n[g];
         const int Tg = n + 1;
-        const int cell = tile * blockDim.x + threadIdx.x;
-        if (cell >= Tg * Tg) continue;
-        const int a = cell / Tg, b = cell - a * Tg;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (a >= 1 && b == 0) {
+        const int f = tile * blockDim.x + threadIdx.x;
+        const int a = f / half, b = (f - a * half) * 2;
+        if (a >= Tg || b >= Tg) continue;
+        const bool two = b + 1 < Tg;
+        float acc[2][8];
 #pragma unroll
-            for (int h = 0; h < 8; ++h) acc[h] = tvd[h];
-        } else if (a >= 1) {
-            const int64_t pc = c.sq_off[g] + (int64_t)(a - 1) * n + (b - 1);
-            const int rp = c.rel_pos[pc];
-            const int M = rp - 1;
-            if (M >= c.rel_pos_max) {
+        for (int s = 0; s < 2; ++s)
 #pragma unroll
-                for (int h = 0; h < 8; ++h) acc[h] = -INFINITY;
-            } else {
-                const uint8_t *ei = c.edge_in + pc * c.hops;
-                for (int k = 0; k < c.hops; ++k) {
-                    const int v = ei[k];
-                    if (v == 0) break;
-                    add8(acc, EW + ((size_t)k * kEdgeVocab + v) * kH);
+            for (int h = 0; h < 8; ++h) acc[s][h] = 0.f;
+        if (a >= 1) {
+            const int64_t rowp = c.sq_off[g] + (int64_t)(a - 1) * n;   // pair (a-1, j) lives at rowp + j
+            // cell s of this thread is the pair j = b - 1 + s  (b == 0, s == 0: the virtual-distance column)
+            int rp[2], pp[2];
+            uint32_t ew[2][8];
+            bool is_pair[2];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int j = b - 1 + s;
+                is_pair[s] = j >= 0 && j < n;
+                rp[s] = 0; pp[s] = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) ew[s][q] = 0u;
+                if (is_pair[s]) {
+                    const int64_t pc = rowp + j;
+                    rp[s] = c.rel_pos[pc];
+                    pp[s] = c.poi_pos[pc];
+                    const uint32_t *ei = reinterpret_cast<const uint32_t *>(c.edge_in + pc * c.hops);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) if (q < hopw) ew[s][q] = __ldg(ei + q);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (!is_pair[s]) {
+                    if (b == 0 && s == 0) {
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) acc[0][h] = tv[h];
+                    }
+                    continue;
+                }
+                const int M = rp[s] - 1;
+                if (M >= c.rel_pos_max) {
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) acc[s][h] = -INFINITY;
+                    continue;
+                }
+                bool live = true;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (q < hopw && live) {
+                        const uint32_t wd = ew[s][q];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int v = (wd >> (8 * e)) & 0xFF;
+                            if (v == 0) { live = false; break; }     // end of the walk (E[0] == 0: padding row)
+                            add8(acc[s], EW + ((size_t)(q * 4 + e) * kEdgeVocab + v) * kH);
+                        }
+                    }
                 }
                 const float inv = 1.0f / (float)min(max(M, 1), c.hops);
-                const int pp = c.poi_pos[pc];
-                const float4 r0 = *reinterpret_cast<const float4 *>(R + rp * kH), r1 = *reinterpret_cast<const float4 *>(R + rp * kH + 4);
-                const float4 p0 = *reinterpret_cast<const float4 *>(Pp + pp * kH), p1 = *reinterpret_cast<const float4 *>(Pp + pp * kH + 4);
+                const float *r = R + rp[s] * kH, *q_ = Pp + min(pp[s], num_bins - 1) * kH;
+                const float4 r0 = *reinterpret_cast<const float4 *>(r), r1 = *reinterpret_cast<const float4 *>(r + 4);
+                const float4 p0 = *reinterpret_cast<const float4 *>(q_), p1 = *reinterpret_cast<const float4 *>(q_ + 4);
                 const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
                 const float qq[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
 #pragma unroll
-                for (int h = 0; h < 8; ++h) acc[h] = (rr[h] + qq[h]) + acc[h] * inv;
+                for (int h = 0; h < 8; ++h) acc[s][h] = (rr[h] + qq[h]) + acc[s][h] * inv;
             }
         }
         OutT *o = out + ((size_t)g * kH * c.T + a) * c.Tp + b;
+        if (two) {
 #pragma unroll
-        for (int h = 0; h < 8; ++h) store_out<OutT>(o + h * hs, acc[h]);
+            for (int h = 0; h < 8; ++h) store2<OutT>(o + h * hs, acc[0][h], acc[1][h]);
+        } else {
+#pragma unroll
+            for (int h = 0; h < 8; ++h) store1<OutT>(o + h * hs, acc[0][h]);
+        }
     }
 }
 
 // ---- backward --------------------------------------------------------------------------------------
-// Histogram add with warp-level pre-aggregation: the keys of one stream (one hop slot, or rel_pos / poi_pos) are
-// heavily duplicated inside a warp (most walks carry the same edge feature), and same-address shared-memory atomics
-// serialise.  Up to two dominant key groups are peeled with a warp reduction (one atomic per head for the whole group);
-// whatever is left goes through individual atomics.  Must be called by all 32 lanes (key < 0 = nothing to add).
-__device__ __forceinline__ void warp_hist_add(float *hist, int key, const float (&w)[8]) {
+// dBias (fp32, summed over layers) -> table gradients.  Every cell contributes its 8-vector d[h] to
+//   dt (column 0), dR[rp], dPpos[pp] and dEW[k][ei[k]] * 1/sp for every hop k of its walk:
+// 22 keyed adds whose keys are heavily duplicated (one distance / one edge feature dominates), and shared-memory fp32
+// atomicAdd is a compare-and-swap loop (ATOMS.CAST.SPIN) that serialises on equal addresses.  So the main path uses
+// NO atomics:
+//   * lanes = (4 cells) x (8 heads): lane (p4, h) owns head h of cell p4 of the current group, so one keyed add is a
+//     plain LDS / FADD / STS of 8 consecutive floats per cell, into WARP-PRIVATE histograms;
+//   * the poi_pos and walk histograms are replicated per p4 (no two lanes ever share an address); the rel_pos histogram
+//     is updated in 4 lock-step turns (one p4 per turn);
+//   * the 20 hop adds of a walk collapse into ONE: the cell is added to A[L] (L = walk length) as if every hop carried
+//     the dominant edge feature (kDomEdge: "one transition", by far the most common); only the hops with another
+//     feature are visited: N[k] += d (warp-private) and dEW[k][v] += d (shared-memory atomic into the CTA's dEW
+//     histogram, low contention), and the finish resolves dEW[k][dom] += sum_{L > k} A[L] - N[k].
+// Per-CTA totals go to a partial buffer in the workspace and are reduced in a fixed order by the finish kernels
+// (reproducible except for the rare-path atomics).
+constexpr int kDomEdge = 4;    // edge count 1 -> attn_edge_type 3 (wrapper.py:49-53) -> +1 (collator.py:86-93)
+
+struct K2BwdPlan {
+    int Rrows;      // rel_pos histogram rows: keys 0..Rrows-2 direct, key 511 -> row Rrows-1
+    int nEW, nR, nP, nA, nN, stride;   // floats; partial row = [EW | R | P | A | N | t(8)]
+    int warps;
+};
+
+__host__ __device__ inline K2BwdPlan k2_bwd_plan(int T, int hops, int num_bins) {
+    K2BwdPlan p;
+    p.Rrows = min(T, 511) + 1;
+    p.nEW = hops * kEdgeVocab * kH;
+    p.nR = p.Rrows * kH;
+    p.nP = num_bins * kH;
+    p.nA = (hops + 1) * kH;
+    p.nN = hops * kH;
+    p.stride = p.nEW + p.nR + p.nP + p.nA + p.nN + kH;
+    const int per_warp = (p.nR + 4 * (p.nP + p.nA + p.nN) + kH) * 4;
+    int w = (int)((227 * 1024 - 1024 - p.nEW * 4) / per_warp);
+    p.warps = w > 8 ? 8 : w;
+    return p;
+}
+
+__global__ void __launch_bounds__(256, 1) k2_bias_bwd_kernel(const K2Common c, const float *__restrict__ dB, int num_bins,
+                                                             const K2BwdPlan pl, float *__restrict__ partial,
+                                                             float *__restrict__ dR_overflow) {
+    extern __shared__ __align__(16) float sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int p4 = lane >> 3, h = lane & 7;
+    float *sEW = sm;
+    const int per_warp = pl.nR + 4 * (pl.nP + pl.nA + pl.nN) + kH;
+    float *sR = sm + pl.nEW + warp * per_warp;
+    float *sP = sR + pl.nR + p4 * pl.nP;
+    float *sA = sR + pl.nR + 4 * pl.nP + p4 * pl.nA;
+    float *sN = sR + pl.nR + 4 * (pl.nP + pl.nA) + p4 * pl.nN;
+    float *sT = sR + pl.nR + 4 * (pl.nP + pl.nA + pl.nN);
+    for (int i = threadIdx.x; i < pl.nEW + nwarp * per_warp; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    unsigned act = __ballot_sync(full, key >= 0);
-#pragma unroll 1
-    for (int peel = 0; peel < 2 && act; ++peel) {
-        const int l = __ffs(act) - 1;
-        const int kk = __shfl_sync(full, key, l);
-        const unsigned grp = __ballot_sync(full, key == kk);
-        if (__popc(grp) < 3) break;
-        const bool in = key == kk;
+    const size_t hs = (size_t)c.T * c.Tp;
+    const int hopw = c.hops >> 2;
+    const int gbase = lane & ~7;
+    float tacc = 0.f;
+    for (int u = blockIdx.x * nwarp + warp; u < c.B * c.T; u += gridDim.x * nwarp) {
+        const int g = u / c.T, a = u - g * c.T;
+        const int n = c.n[g];
+        if (a == 0 || a > n) continue;                       // row 0 carries no parameter (model_fqandtoyo.py:1160-1165)
+        const int Tg = n + 1;
+        const float *row = dB + ((size_t)g * kH * c.T + a) * c.Tp + h * hs;
+        const int64_t rowp = c.sq_off[g] + (int64_t)(a - 1) * n - 1;     // pair of cell b lives at rowp + b
+        for (int b0 = 0; b0 < Tg; b0 += 16) {
+            const int bq = b0 + 4 * p4;
+            float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bq < Tg) dv = *reinterpret_cast<const float4 *>(row + bq);
+            const float dj[4] = {dv.x, dv.y, dv.z, dv.w};
+            // keys of the 4 cells of this lane's p4 group, spread over the 8 head lanes:
+            //   every lane h: word h of the walk bytes; lane 0 also rel_pos, lane 1 also poi_pos
+            uint32_t wj[4];
+            int kj[4];
 #pragma unroll
-        for (int h = 0; h < 8; ++h) {
-            float s = in ? w[h] : 0.f;
+            for (int j = 0; j < 4; ++j) {
+                const int b = bq + j;
+                wj[j] = 0u;
+                kj[j] = 0;
+                if (b >= 1 && b < Tg) {
+                    const int64_t pc = rowp + b;
+                    if (h < hopw) wj[j] = __ldg(reinterpret_cast<const uint32_t *>(c.edge_in + pc * c.hops) + h);
+                    if (h == 0) kj[j] = c.rel_pos[pc];
+                    if (h == 1) kj[j] = c.poi_pos[pc];
+                }
+            }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(full, s, o);
-            if (lane == l) atomicAdd(hist + kk * 8 + h, s);
+            for (int j = 0; j < 4; ++j) {
+                const int b = bq + j;
+                const bool valid = b < Tg;
+                float d = valid ? dj[j] : 0.f;
+                if (b == 0) tacc += d;
+                bool pair = valid && b >= 1;
+                const int rp = __shfl_sync(full, kj[j], gbase);
+                const int pp = __shfl_sync(full, kj[j], gbase + 1);
+                // walk length L and the mask of hops that carry another feature than the dominant one (bit k = hop k),
+                // reduced over the 8 word lanes of the cell
+                const uint32_t wd = wj[j];
+                int L = 0;
+                uint32_t hm = 0u;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t v = (wd >> (8 * e)) & 0xFFu;
+                    L += (v != 0u);
+                    hm |= (v != 0u && v != (uint32_t)kDomEdge) ? (1u << e) : 0u;
+                }
+                hm <<= 4 * h;
+                L += __shfl_xor_sync(full, L, 1);
+                hm |= __shfl_xor_sync(full, hm, 1);
+                L += __shfl_xor_sync(full, L, 2);
+                hm |= __shfl_xor_sync(full, hm, 2);
+                L += __shfl_xor_sync(full, L, 4);
+                hm |= __shfl_xor_sync(full, hm, 4);
+                const int M = rp - 1;
+                if (M >= c.rel_pos_max) pair = false;            // -inf entries carry no gradient
+                // rel_pos histogram: 4 lock-step turns (cells of one group may share a key)
+                int rk = -1;
+                if (pair) {
+                    rk = (rp == 511) ? pl.Rrows - 1 : (rp < pl.Rrows - 1 ? rp : -2);
+                    if (rk == -2) atomicAdd(dR_overflow + rp * kH + h, d);     // key outside the plan (never for K1 output)
+                }
+#pragma unroll
+                for (int turn = 0; turn < 4; ++turn) {
+                    if (p4 == turn && rk >= 0) sR[rk * kH + h] += d;
+                    __syncwarp();
+                }
+                if (pair) {
+                    sP[min(pp, num_bins - 1) * kH + h] += d;
+                    d *= 1.0f / (float)min(max(M, 1), c.hops);
+                    sA[L * kH + h] += d;                          // L == 0 (no walk): row 0 of A is ignored
+                } else {
+                    hm = 0u;
+                }
+                // hops with a non-dominant feature (few): N[k] += d (taken back from the dominant bin at the end) and
+                // dEW[k][v] += d in the CTA's shared histogram
+                while (__any_sync(full, hm != 0u)) {
+                    const int k = hm ? __ffs(hm) - 1 : 0;
+                    const uint32_t wv = __shfl_sync(full, wd, gbase + (k >> 2));
+                    if (hm) {
+                        const int v = (wv >> (8 * (k & 3))) & 0xFF;
+                        sN[k * kH + h] += d;
+                        atomicAdd(sEW + ((size_t)k * kEdgeVocab + v) * kH + h, d);
+                        hm &= hm - 1u;
+                    }
+                }
+            }
         }
-        if (in) key = -1;
-        act &= ~grp;
     }
-    if (key >= 0) {
-#pragma unroll
-        for (int h = 0; h < 8; ++h) atomicAdd(hist + key * 8 + h, w[h]);
+    // column-0 sums: lanes (p4 = 0, h) hold them
+    if (p4 == 0) sT[h] = tacc;
+    __syncthreads();
+    // CTA totals -> partial[blockIdx]
+    float *out = partial + (size_t)blockIdx.x * pl.stride;
+    for (int i = threadIdx.x; i < pl.nEW; i += blockDim.x) out[i] = sEW[i];
+    const float *wbase = sm + pl.nEW;
+    for (int i = threadIdx.x; i < pl.nR; i += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < nwarp; ++w) s += wbase[w * per_warp + i];
+        out[pl.nEW + i] = s;
+    }
+    for (int i = threadIdx.x; i < pl.nP; i += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < nwarp; ++w)
+            for (int r = 0; r < 4; ++r) s += wbase[w * per_warp + pl.nR + r * pl.nP + i];
+        out[pl.nEW + pl.nR + i] = s;
+    }
+    for (int i = threadIdx.x; i < pl.nA; i += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < nwarp; ++w)
+            for (int r = 0; r < 4; ++r) s += wbase[w * per_warp + pl.nR + 4 * pl.nP + r * pl.nA + i];
+        out[pl.nEW + pl.nR + pl.nP + i] = s;
+    }
+    for (int i = threadIdx.x; i < pl.nN; i += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < nwarp; ++w)
+            for (int r = 0; r < 4; ++r) s += wbase[w * per_warp + pl.nR + 4 * (pl.nP + pl.nA) + r * pl.nN + i];
+        out[pl.nEW + pl.nR + pl.nP + pl.nA + i] = s;
+    }
+    if (threadIdx.x < kH) {
+        float s = 0.f;
+        for (int w = 0; w < nwarp; ++w) s += wbase[w * per_warp + pl.nR + 4 * (pl.nP + pl.nA + pl.nN) + threadIdx.x];
+        out[pl.nEW + pl.nR + pl.nP + pl.nA + pl.nN + threadIdx.x] = s;
     }
 }
 
-// persistent CTAs; shared-memory histograms dEW[hops][128][8], dR[512][8], dP[bins][8], dt[8]
-__global__ void __launch_bounds__(256) k2_bias_bwd_kernel(const K2Common c, const float *__restrict__ dB, int num_bins,
-                                                          float *__restrict__ dEW, float *__restrict__ dR,
-                                                          float *__restrict__ dP, float *__restrict__ dt) {
-    extern __shared__ __align__(16) float sm[];
-    const int nEW = c.hops * kEdgeVocab * kH, nR = 512 * kH, nP = num_bins * kH;
-    float *sEW = sm, *sR = sEW + nEW, *sP = sR + nR, *st = sP + nP;
-    const int tot = nEW + nR + nP + kH;
-    for (int i = threadIdx.x; i < tot; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
-    const int tiles = ceil_div(c.T * c.T, (int)blockDim.x);
-    const size_t hs = (size_t)c.T * c.Tp;
-    const unsigned full = 0xffffffffu;
-    for (int w = blockIdx.x; w < tiles * c.B; w += gridDim.x) {
-        const int g = w / tiles, tile = w - g * tiles;
-        const int n = c.n[g], Tg = n + 1;
-        const int cell = tile * blockDim.x + threadIdx.x;
-        const int a = cell / Tg, b = cell - a * Tg;
-        const bool in_graph = cell < Tg * Tg && a >= 1;
-        float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (in_graph) {
-            const float *src = dB + ((size_t)g * kH * c.T + a) * c.Tp + b;
-#pragma unroll
-            for (int h = 0; h < 8; ++h) d[h] = src[h * hs];
-        }
-        // column 0 of rows >= 1: graph-token virtual distance
-        warp_hist_add(st, (in_graph && b == 0) ? 0 : -1, d);
-        bool pair = in_graph && b >= 1;
-        int rp = 0, pp = 0, M = 0;
-        int64_t pc = 0;
-        if (pair) {
-            pc = c.sq_off[g] + (int64_t)(a - 1) * n + (b - 1);
-            rp = c.rel_pos[pc];
-            M = rp - 1;
-            if (M >= c.rel_pos_max) pair = false;     // -inf entries carry no gradient
-            else pp = c.poi_pos[pc];
-        }
-        warp_hist_add(sR, pair ? rp : -1, d);
-        warp_hist_add(sP, pair ? pp : -1, d);
-        const float inv = 1.0f / (float)min(max(M, 1), c.hops);
-#pragma unroll
-        for (int h = 0; h < 8; ++h) d[h] *= inv;
-        const uint8_t *ei = c.edge_in + pc * c.hops;
-        for (int k = 0; k < c.hops; ++k) {
-            int v = 0;
-            if (pair) {
-                v = ei[k];
-                if (v == 0) pair = false;              // end of the walk
-            }
-            if (__ballot_sync(full, pair) == 0) break;
-            warp_hist_add(sEW, pair ? k * kEdgeVocab + v : -1, d);
-        }
+// tot[i] = sum over CTAs (fixed order) of partial[cta][i];  then the walk-length histogram is folded into dEW:
+// dEW[k][dom][h] += sum_{L > k} A[L][h] - N[k][h]   (second kernel, after the totals exist)
+__global__ void k2_bias_bwd_reduce_kernel(const float *__restrict__ partial, int nparts, int stride, float *__restrict__ tot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= stride) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * stride + i];
+    tot[i] = s;
+}
+
+__global__ void k2_bias_bwd_scatter_kernel(float *__restrict__ tot, const K2BwdPlan pl, int hops, int num_bins,
+                                           float *__restrict__ dR, float *__restrict__ dP, float *__restrict__ dt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float *tR = tot + pl.nEW, *tP = tR + pl.nR, *tA = tP + pl.nP, *tN = tA + pl.nA, *tT = tN + pl.nN;
+    if (i < 512 * kH) {
+        const int rp = i / kH, hh = i % kH;
+        const int row = (rp == 511) ? pl.Rrows - 1 : (rp < pl.Rrows - 1 ? rp : -1);
+        dR[i] += (row >= 0) ? tR[row * kH + hh] : 0.f;     // dR holds the (normally empty) overflow atomics
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nEW; i += blockDim.x) if (sEW[i] != 0.f) atomicAdd(dEW + i, sEW[i]);
-    for (int i = threadIdx.x; i < nR; i += blockDim.x) if (sR[i] != 0.f) atomicAdd(dR + i, sR[i]);
-    for (int i = threadIdx.x; i < nP; i += blockDim.x) if (sP[i] != 0.f) atomicAdd(dP + i, sP[i]);
-    if (threadIdx.x < kH && st[threadIdx.x] != 0.f) atomicAdd(dt + threadIdx.x, st[threadIdx.x]);
+    if (i < num_bins * kH) dP[i] = tP[i];
+    if (i < kH) dt[i] = tT[i];
+    if (i < hops * kH) {
+        const int k = i / kH, hh = i % kH;
+        float s = 0.f;
+        for (int L = k + 1; L <= hops; ++L) s += tA[L * kH + hh];
+        s -= tN[i];
+        tot[((size_t)k * kEdgeVocab + kDomEdge) * kH + hh] += s;
+    }
 }
 
 // dE[v][h'] = sum_k sum_h dEW[k][v][h] W[k][h'][h] ;  dW[k][h'][h] = sum_v E[v][h'] dEW[k][v][h]
@@ -236,12 +429,15 @@ using namespace mobgt;
 
 extern "C" int32_t mobgt_bias_fwd(const int32_t *n, const int64_t *sq_off, const int16_t *rel_pos, const int16_t *poi_pos,
                                   const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t H,
-                                  int32_t rel_pos_max, const float *R, const float *Ppos, const float *E, const float *W,
-                                  const float *tvd, void *workspace, void *out, int32_t out_dtype, void *stream) {
+                                  int32_t rel_pos_max, int32_t num_bins, const float *R, const float *Ppos, const float *E,
+                                  const float *W, const float *tvd, void *workspace, void *out, int32_t out_dtype,
+                                  void *stream) {
     MOBGT_REQUIRE(n && sq_off && rel_pos && poi_pos && edge_in && R && Ppos && E && W && tvd && workspace && out,
                   MOBGT_ERR_NULL, "mobgt_bias_fwd: null pointer");
     MOBGT_REQUIRE(H == kH, MOBGT_ERR_UNSUPPORTED, "mobgt_bias_fwd: num_heads=%d (only 8 is built)", H);
-    MOBGT_REQUIRE(hops >= 1 && hops <= MOBGT_MAX_HOPS, MOBGT_ERR_BAD_SHAPE, "mobgt_bias_fwd: hops=%d", hops);
+    MOBGT_REQUIRE(hops >= 4 && hops <= MOBGT_MAX_HOPS && hops % 4 == 0, MOBGT_ERR_BAD_SHAPE,
+                  "mobgt_bias_fwd: hops=%d must be a multiple of 4 in [4,%d]", hops, MOBGT_MAX_HOPS);
+    MOBGT_REQUIRE(num_bins >= 1 && num_bins <= 1024, MOBGT_ERR_BAD_SHAPE, "mobgt_bias_fwd: num_bins=%d", num_bins);
     MOBGT_REQUIRE(T >= 2 && Tp >= T && Tp % 8 == 0, MOBGT_ERR_BAD_SHAPE, "mobgt_bias_fwd: T=%d Tp=%d", T, Tp);
     MOBGT_REQUIRE(out_dtype == MOBGT_F32 || out_dtype == MOBGT_BF16, MOBGT_ERR_BAD_DTYPE, "mobgt_bias_fwd: dtype");
     if (B <= 0) return MOBGT_OK;
@@ -251,44 +447,60 @@ extern "C" int32_t mobgt_bias_fwd(const int32_t *n, const int64_t *sq_off, const
     k2_prep_kernel<<<ceil_div(tabn, 256), 256, 0, s>>>(E, W, hops, EW);
     MOBGT_LAUNCH_OK("k2_prep_kernel");
     K2Common c{n, sq_off, rel_pos, poi_pos, edge_in, B, T, Tp, hops, rel_pos_max};
-    const size_t smem = (size_t)tabn * sizeof(float);
-    const int tiles_total = ceil_div(T * T, 256) * B;
+    const size_t smem = (size_t)(tabn + 512 * kH + num_bins * kH) * sizeof(float);
+    const int tiles_total = ceil_div(T * (Tp / 2), 512) * B;
     dim3 grid((unsigned)min(2 * kNumSMs, tiles_total));
     if (out_dtype == MOBGT_F32) {
         MOBGT_CUDA_OK(cudaFuncSetAttribute(k2_bias_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k2_bias_fwd_kernel<float><<<grid, 256, smem, s>>>(c, R, Ppos, tvd, EW, static_cast<float *>(out));
+        k2_bias_fwd_kernel<float><<<grid, 512, smem, s>>>(c, R, Ppos, num_bins, tvd, EW, static_cast<float *>(out));
     } else {
         MOBGT_CUDA_OK(cudaFuncSetAttribute(k2_bias_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k2_bias_fwd_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(c, R, Ppos, tvd, EW, static_cast<__nv_bfloat16 *>(out));
+        k2_bias_fwd_kernel<__nv_bfloat16><<<grid, 512, smem, s>>>(c, R, Ppos, num_bins, tvd, EW, static_cast<__nv_bfloat16 *>(out));
     }
     MOBGT_LAUNCH_OK("k2_bias_fwd_kernel");
     return MOBGT_OK;
 }
 
+extern "C" int64_t mobgt_bias_bwd_workspace_bytes(int32_t T, int32_t hops, int32_t num_bins) {
+    if (T < 2 || hops < 4 || hops > MOBGT_MAX_HOPS || num_bins < 1 || num_bins > 1024) return -1;
+    const K2BwdPlan pl = k2_bwd_plan(T, hops, num_bins);
+    return (int64_t)(kNumSMs + 1) * pl.stride * (int64_t)sizeof(float);
+}
+
 extern "C" int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const int16_t *rel_pos, const int16_t *poi_pos,
                                   const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t H,
                                   int32_t rel_pos_max, int32_t num_bins, const float *dBias, const float *E, const float *W,
-                                  void *workspace, float *dR, float *dPpos, float *dE, float *dW, float *dtvd, void *stream) {
+                                  void *workspace, int64_t workspace_bytes, float *dR, float *dPpos, float *dE, float *dW,
+                                  float *dtvd, void *stream) {
     MOBGT_REQUIRE(n && sq_off && rel_pos && poi_pos && edge_in && dBias && E && W && workspace && dR && dPpos && dE && dW && dtvd,
                   MOBGT_ERR_NULL, "mobgt_bias_bwd: null pointer");
     MOBGT_REQUIRE(H == kH, MOBGT_ERR_UNSUPPORTED, "mobgt_bias_bwd: num_heads=%d (only 8 is built)", H);
-    MOBGT_REQUIRE(hops >= 1 && hops <= MOBGT_MAX_HOPS && num_bins >= 1 && num_bins <= 1024, MOBGT_ERR_BAD_SHAPE,
+    MOBGT_REQUIRE(hops >= 4 && hops <= MOBGT_MAX_HOPS && hops % 4 == 0 && num_bins >= 1 && num_bins <= 1024, MOBGT_ERR_BAD_SHAPE,
                   "mobgt_bias_bwd: hops=%d num_bins=%d", hops, num_bins);
+    MOBGT_REQUIRE(T >= 2 && Tp >= T && Tp % 8 == 0, MOBGT_ERR_BAD_SHAPE, "mobgt_bias_bwd: T=%d Tp=%d", T, Tp);
+    const K2BwdPlan pl = k2_bwd_plan(T, hops, num_bins);
+    MOBGT_REQUIRE(pl.warps >= 1, MOBGT_ERR_UNSUPPORTED, "mobgt_bias_bwd: no shared-memory plan for T=%d bins=%d", T, num_bins);
+    const int64_t need = (int64_t)(kNumSMs + 1) * pl.stride * (int64_t)sizeof(float);
+    MOBGT_REQUIRE(workspace_bytes >= need, MOBGT_ERR_WORKSPACE_TOO_SMALL, "mobgt_bias_bwd: workspace %lld < %lld bytes",
+                  (long long)workspace_bytes, (long long)need);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    float *dEW = static_cast<float *>(workspace);
-    const int nEW = hops * kEdgeVocab * kH;
-    MOBGT_CUDA_OK(cudaMemsetAsync(dEW, 0, (size_t)nEW * 4, s));
+    float *tot = static_cast<float *>(workspace);          // [stride] totals, then [kNumSMs][stride] per-CTA partials
+    float *partial = tot + pl.stride;
     MOBGT_CUDA_OK(cudaMemsetAsync(dR, 0, 512 * kH * 4, s));
-    MOBGT_CUDA_OK(cudaMemsetAsync(dPpos, 0, (size_t)num_bins * kH * 4, s));
-    MOBGT_CUDA_OK(cudaMemsetAsync(dtvd, 0, kH * 4, s));
+    const int nparts = B > 0 ? kNumSMs : 0;
     if (B > 0) {
         K2Common c{n, sq_off, rel_pos, poi_pos, edge_in, B, T, Tp, hops, rel_pos_max};
-        const size_t smem = (size_t)(nEW + 512 * kH + num_bins * kH + kH) * sizeof(float);
+        const int per_warp = pl.nR + 4 * (pl.nP + pl.nA + pl.nN) + kH;
+        const size_t smem = (size_t)(pl.nEW + pl.warps * per_warp) * sizeof(float);
         MOBGT_CUDA_OK(cudaFuncSetAttribute(k2_bias_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k2_bias_bwd_kernel<<<2 * kNumSMs, 256, smem, s>>>(c, dBias, num_bins, dEW, dR, dPpos, dtvd);
+        k2_bias_bwd_kernel<<<kNumSMs, pl.warps * 32, smem, s>>>(c, dBias, num_bins, pl, partial, dR);
         MOBGT_LAUNCH_OK("k2_bias_bwd_kernel");
     }
-    k2_bias_bwd_finish_kernel<<<ceil_div(kEdgeVocab * kH + hops * kH * kH, 256), 256, 0, s>>>(dEW, E, W, hops, dE, dW);
+    k2_bias_bwd_reduce_kernel<<<ceil_div(pl.stride, 256), 256, 0, s>>>(partial, nparts, pl.stride, tot);
+    MOBGT_LAUNCH_OK("k2_bias_bwd_reduce_kernel");
+    k2_bias_bwd_scatter_kernel<<<ceil_div(512 * kH, 256), 256, 0, s>>>(tot, pl, hops, num_bins, dR, dPpos, dtvd);
+    MOBGT_LAUNCH_OK("k2_bias_bwd_scatter_kernel");
+    k2_bias_bwd_finish_kernel<<<ceil_div(kEdgeVocab * kH + hops * kH * kH, 256), 256, 0, s>>>(tot, E, W, hops, dE, dW);
     MOBGT_LAUNCH_OK("k2_bias_bwd_finish_kernel");
     return MOBGT_OK;
 }

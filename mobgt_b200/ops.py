@@ -34,8 +34,8 @@ def bias_fwd_raw(batch, R, Ppos, E, W, tvd, out_dtype=torch.bfloat16, T=None, Tp
     out = torch.empty(B, H, T, Tp, dtype=out_dtype, device=dev)
     ws = torch.empty(batch.hops * 128 * H, dtype=torch.float32, device=dev)
     _C.call("mobgt_bias_fwd", _C.ptr(batch.n), _C.ptr(batch.sq_off), _C.ptr(batch.rel_pos16), _C.ptr(batch.poi_pos16),
-            _C.ptr(batch.edge_in8), B, T, Tp, batch.hops, H, batch.rel_pos_max, _C.ptr(R), _C.ptr(Ppos), _C.ptr(E), _C.ptr(W),
-            _C.ptr(tvd), _C.ptr(ws), _C.ptr(out), _dt(out), _C.stream_ptr())
+            _C.ptr(batch.edge_in8), B, T, Tp, batch.hops, H, batch.rel_pos_max, int(Ppos.shape[0]), _C.ptr(R), _C.ptr(Ppos),
+            _C.ptr(E), _C.ptr(W), _C.ptr(tvd), _C.ptr(ws), _C.ptr(out), _dt(out), _C.stream_ptr())
     return out
 
 
@@ -43,15 +43,18 @@ def bias_bwd_raw(batch, dbias, E, W, num_bins):
     B, H, T, Tp = dbias.shape
     dev = dbias.device
     hops = batch.hops
-    ws = torch.empty(hops * 128 * H, dtype=torch.float32, device=dev)
+    ws_bytes = int(_C.lib().mobgt_bias_bwd_workspace_bytes(T, hops, num_bins))
+    if ws_bytes < 0:
+        raise _C.MobgtError(f"mobgt_bias_bwd_workspace_bytes rejected T={T} hops={hops} num_bins={num_bins}")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     dR = torch.empty(512, H, dtype=torch.float32, device=dev)
     dP = torch.empty(num_bins, H, dtype=torch.float32, device=dev)
     dE = torch.empty(128, H, dtype=torch.float32, device=dev)
-    dW = torch.zeros(W.numel(), dtype=torch.float32, device=dev)
+    dW = torch.zeros(W.numel(), dtype=torch.float32, device=dev)   # rows >= hops*H*H of edge_dis_encoder get no gradient
     dt = torch.empty(H, dtype=torch.float32, device=dev)
     _C.call("mobgt_bias_bwd", _C.ptr(batch.n), _C.ptr(batch.sq_off), _C.ptr(batch.rel_pos16), _C.ptr(batch.poi_pos16),
             _C.ptr(batch.edge_in8), B, T, Tp, hops, H, batch.rel_pos_max, num_bins, _C.ptr(dbias), _C.ptr(E), _C.ptr(W),
-            _C.ptr(ws), _C.ptr(dR), _C.ptr(dP), _C.ptr(dE), _C.ptr(dW), _C.ptr(dt), _C.stream_ptr())
+            _C.ptr(ws), ws_bytes, _C.ptr(dR), _C.ptr(dP), _C.ptr(dE), _C.ptr(dW), _C.ptr(dt), _C.stream_ptr())
     return dR, dP, dE, dW.view_as(W), dt
 
 
