@@ -155,10 +155,10 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ kernel micro-timing
-def time_kernel(fn, flush, iters=8):
+def time_kernel(fn, flush, iters=8, warm=2):
     """CUDA-event time of fn() on the current stream, L2 flushed before every launch; returns mean ms."""
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-    for _ in range(2):
+    for _ in range(warm):
         fn()
     for a, b in ev:
         flush.zero_()
@@ -169,7 +169,7 @@ def time_kernel(fn, flush, iters=8):
     return float(np.mean([a.elapsed_time(b) for a, b in ev]))
 
 
-def kernel_report(model, batch, pk):
+def kernel_report(model, batch, pk, iters=8, head_c5=True):
     """Per-kernel device time at the workload's shapes + algorithmic bytes -> roofline."""
     from mobgt_b200 import ops
     from mobgt_b200.algos import apsp_edge_input_packed
@@ -189,6 +189,7 @@ def kernel_report(model, batch, pk):
     dout = torch.randn(ntok, 192, device=dev).to(torch.bfloat16)
     dbias = torch.zeros(bias.shape, dtype=torch.float32, device=dev)
     rep = {}
+    tk = lambda fn: time_kernel(fn, flush, iters=iters, warm=min(2, iters))
 
     def add(name, ms, nbytes, per_step, flops=None):
         rep[name] = dict(ms=ms, gbs=nbytes / ms / 1e6, frac_hbm=nbytes / ms / 1e6 / pk["hbm"], bytes=nbytes, launches_per_step=per_step)
@@ -196,29 +197,39 @@ def kernel_report(model, batch, pk):
             rep[name]["tflops"] = flops / ms / 1e9
             rep[name]["frac_tc"] = flops / ms / 1e9 / pk["tc"]
 
-    add("k1_apsp_edge_input", time_kernel(lambda: apsp_edge_input_packed(batch.feat8, batch.n, batch.sq_off, batch.n_host, hops, 1), flush),
+    add("k1_apsp_edge_input", tk(lambda: apsp_edge_input_packed(batch.feat8, batch.n, batch.sq_off, batch.n_host, hops, 1)),
         cells * (1 + 2 + hops), 0)
-    add("k2_bias_fwd", time_kernel(lambda: ops.bias_fwd_raw(batch, *tabs), flush), cells * (4 + hops) + H * pairs_t * 2, 1)
-    add("k2_bias_bwd", time_kernel(lambda: ops.bias_bwd_raw(batch, dbias, tabs[2], tabs[3], tabs[1].shape[0]), flush),
+    add("k2_bias_fwd", tk(lambda: ops.bias_fwd_raw(batch, *tabs)), cells * (4 + hops) + H * pairs_t * 2, 1)
+    add("k2_bias_bwd", tk(lambda: ops.bias_bwd_raw(batch, dbias, tabs[2], tabs[3], tabs[1].shape[0])),
         cells * (4 + hops) + H * pairs_t * 4, 1)
     fl = 4.0 * H * pairs_t * 24
-    add("k3_attn_fwd", time_kernel(lambda: ops.attn_fwd_raw(qkv, bias, batch), flush), 4 * ntok * 192 * 2 + H * pairs_t * 2, 6, fl)
-    add("k3_attn_bwd", time_kernel(lambda: ops.attn_bwd_raw(qkv, bias, out, dout, lse, batch, dbias, 1), flush),
+    add("k3_attn_fwd", tk(lambda: ops.attn_fwd_raw(qkv, bias, batch)), 4 * ntok * 192 * 2 + H * pairs_t * 2, 6, fl)
+    add("k3_attn_bwd", tk(lambda: ops.attn_bwd_raw(qkv, bias, out, dout, lse, batch, dbias, 1)),
         8 * ntok * 192 * 2 + H * pairs_t * 2 + H * pairs_t * 8, 6, 2.5 * fl)
     Gd, Gc = model.gcn_tables()
     Gd, Gc = Gd.detach(), Gc.detach()
     Tm = model.time_embed_model_48.weight.detach()
     nn_ = ntok - B
-    add("k4_embed_gather", time_kernel(lambda: ops.embed_gather_raw(batch, model.cat_of_poi, Gd, Tm, Gc), flush),
+    add("k4_embed_gather", tk(lambda: ops.embed_gather_raw(batch, model.cat_of_poi, Gd, Tm, Gc)),
         nn_ * (192 * 4 + 192 * 2 + 12), 1)
     nf = torch.randn(nn_, 192, device=dev).to(torch.bfloat16)
     pe, gt = model.pos_embed.pe.detach(), model.graph_token.weight.detach().view(-1)
     Din, Dout = model.in_degree_encoder.weight.detach(), model.out_degree_encoder.weight.detach()
-    add("k4_embed_sum", time_kernel(lambda: ops.embed_sum_raw(batch, nf, Din, Dout, pe, gt), flush),
+    add("k4_embed_sum", tk(lambda: ops.embed_sum_raw(batch, nf, Din, Dout, pe, gt)),
         nn_ * (192 * 2 + 3 * 192 * 4 + 16) + ntok * 192 * 2, 1)
     g = torch.randn(ntok, 192, device=dev).to(torch.bfloat16)
     plan = ops.sort_plan(batch.tok_pos)
-    add("k4_segment_sum", time_kernel(lambda: ops.segment_sum_raw(g, 0, 192, plan, 2000), flush), ntok * (192 * 2 + 8), 6)
+    add("k4_segment_sum", tk(lambda: ops.segment_sum_raw(g, 0, 192, plan, 2000)), ntok * (192 * 2 + 8), 6)
+    # K5 — the evaluation head (not part of the training step): c2 shape, and one GPU's shard of the c5 shape
+    for name, Mh, Vh in (("k5_head_c2", 256, 60001),) + ((("k5_head_c5_shard", 4096, 125000),) if head_c5 else ()):
+        g_ = torch.Generator(device=dev).manual_seed(5)
+        z = torch.randn(Mh, 320, device=dev, generator=g_).to(torch.bfloat16)
+        Wh = (torch.randn(Vh, 320, device=dev, generator=g_) * 0.02).to(torch.bfloat16)
+        tgt = torch.randint(0, Vh, (Mh,), device=dev, generator=g_).int()
+        st = ops.head_target_logit(z, Wh, None, tgt)
+        add(name, tk(lambda: ops.head_topk_local(z, Wh, None, tgt, 10, st=st)), Vh * 320 * 2 + Mh * 320 * 2 + Mh * 10 * 8, 0,
+            2.0 * Mh * 320 * Vh)
+        del z, Wh
     del flush
     return rep
 

@@ -201,16 +201,16 @@ def collate_packed(items, world=None, latlon_dev=None, max_node=512, multi_hop_m
     return b
 
 
-def collator_foursquare(items, max_node=512, multi_hop_max_dist=20, rel_pos_max=20, world=None, **kw):
+def collator_foursquare(items, max_node=512, multi_hop_max_dist=20, rel_pos_max=20, world=None, latlon_dev=None, **kw):
     """collator.py:310-458"""
-    return collate_packed(items, world, None, max_node, multi_hop_max_dist, rel_pos_max, **kw)
+    return collate_packed(items, world, latlon_dev, max_node, multi_hop_max_dist, rel_pos_max, **kw)
 
 
-def collator_gowalla(items, max_node=512, multi_hop_max_dist=20, rel_pos_max=20, world=None, **kw):
+def collator_gowalla(items, max_node=512, multi_hop_max_dist=20, rel_pos_max=20, world=None, latlon_dev=None, **kw):
     """collator.py:460-608"""
-    return collate_packed(items, world, None, max_node, multi_hop_max_dist, rel_pos_max, **kw)
+    return collate_packed(items, world, latlon_dev, max_node, multi_hop_max_dist, rel_pos_max, **kw)
 
 
-def collator_toyota(items, max_node=512, multi_hop_max_dist=20, rel_pos_max=20, world=None, **kw):
+def collator_toyota(items, max_node=512, multi_hop_max_dist=20, rel_pos_max=20, world=None, latlon_dev=None, **kw):
     """collator.py:610-748"""
-    return collate_packed(items, world, None, max_node, multi_hop_max_dist, rel_pos_max, **kw)
+    return collate_packed(items, world, latlon_dev, max_node, multi_hop_max_dist, rel_pos_max, **kw)

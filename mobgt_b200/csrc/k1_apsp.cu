@@ -46,7 +46,7 @@ struct K1Params {
 };
 
 constexpr uint32_t kInf = MOBGT_UNREACHABLE;
-constexpr uint16_t kNoWalk = 0xFFFFu;
+constexpr uint16_t kNoWalk = 0x8000u;   // flag bit on X[i][j]: no walk STARTS at (i,j); the low bits stay a valid next hop
 
 __device__ __forceinline__ uint32_t pick16(const uint4 &v, int e) {
     const int w = e >> 1;
@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(512) k1_apsp_kernel(const K1Params p, const in
             // pairs whose last improving intermediate is node 510 -- reproduced here (P is kept whenever n > 510)
             const bool skip510 = WITH_PATH && (pick16(p4, e) == kInf);
             if (unreach || i == j || skip510) {
-                xo[e >> 1] |= (e & 1) ? 0xFFFF0000u : 0x0000FFFFu;  // kNoWalk
+                // flag only: walks of OTHER pairs (i',j) that pass through i still need X[i][j] (a skip510 pair is reachable)
+                xo[e >> 1] |= (e & 1) ? ((uint32_t)kNoWalk << 16) : (uint32_t)kNoWalk;
             }
             if (j < n) {
                 const size_t o = (size_t)off + (size_t)i * n + j;
@@ -257,10 +258,10 @@ __global__ void __launch_bounds__(512) k1_apsp_kernel(const K1Params p, const in
             const int j = c0 + jl;
             uint32_t *stw = reinterpret_cast<uint32_t *>(st) + lane * hopw;
             for (int w = 0; w < hopw; ++w) stw[w] = none4;
-            if (jl < wc && Xsh[(size_t)i * W + jl] != kNoWalk) {
+            if (jl < wc && !(Xsh[(size_t)i * W + jl] & kNoWalk)) {
                 int cur = i;
                 for (int h = 0; h < hops; ++h) {
-                    const int nx = Xsh[(size_t)cur * W + jl];
+                    const int nx = Xsh[(size_t)cur * W + jl] & (kNoWalk - 1);
                     st[lane * hops + h] = (uint8_t)(__ldg(feat + (size_t)cur * n + nx) + p.shift);
                     cur = nx;
                     if (cur == j) break;

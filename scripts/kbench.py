@@ -14,6 +14,7 @@ from mobgt_b200 import collator, model as M, synth
 from mobgt_b200.algos import apsp_edge_input_packed, pack_graphs
 
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
+iters = int([a.split("=")[1] for a in sys.argv if a.startswith("--iters=")][0]) if any(a.startswith("--iters=") for a in sys.argv) else 8
 workload = args[0] if args else "c2-dense128"
 pk = bench.peaks()
 world = synth.make_world("c2", seed=1)
@@ -28,7 +29,7 @@ b = collator.collate_packed(items, world, None, 512, 20, 1024)
 torch.cuda.synchronize()
 t2 = time.perf_counter()
 print(f"collate wall: first {1e3 * (t1 - t0):.1f} ms, second {1e3 * (t2 - t1):.1f} ms")
-rep = bench.kernel_report(model, b, pk)
+rep = bench.kernel_report(model, b, pk, iters=iters)
 for k, v in rep.items():
     print(f"{k:22s} {v['ms'] * 1e3:9.1f} us  {v['gbs']:8.1f} GB/s  hbm {100 * v['frac_hbm']:5.1f}%"
           + (f"  {v['tflops']:7.1f} TF/s tc {100 * v['frac_tc']:4.1f}%" if "tflops" in v else ""))

@@ -101,6 +101,26 @@ def test_chain_512_sentinel(lib_built):
     assert (M == Mo).all() and (P == Po).all() and (e == eo).all()
 
 
+@pytest.mark.parametrize("n", [511, 512])
+def test_node_510_is_a_real_intermediate(lib_built, n):
+    """n > 510: node 510's index collides with the reference's 510 sentinel, so pairs whose LAST improving intermediate
+    is node 510 are skipped by gen_edge_input (algos.pyx:87-88) while walks of other pairs still pass through them.
+    Node 510 is made a hub so that many shortest paths use it."""
+    rng = np.random.default_rng(510 + n)
+    a = rng.random((n, n)) < 0.003
+    a[510, rng.random(n) < 0.3] = True
+    a[rng.random(n) < 0.3, 510] = True
+    s, d = np.nonzero(a)
+    g = (n, s, d, rng.integers(1, 100, size=len(s)))
+    res, nn, sq = run_gpu([g, g])           # twice: the second copy runs as another cluster of the same launch
+    Mo, Po, eo, md = run_algos(algos_oracle, *g, hop_cap=HOPS)
+    assert ((Po == 510) & (Mo < 510)).sum() > 100, "fixture must exercise the path == 510 collision"
+    for gi in range(2):
+        M, P, e = unpack(res, nn, sq, gi)
+        assert (M == Mo).all() and (P == Po).all() and (e == eo).all()
+        assert int(res["maxdist"][gi]) == md
+
+
 def test_shift_and_no_path_variant(lib_built):
     rng = np.random.default_rng(9)
     graphs = []

@@ -71,6 +71,30 @@ def test_oracle_vs_compiled_reference_random():
         assert e.shape == e2.shape and (e == e2).all()
 
 
+def test_oracle_vs_compiled_reference_node_510_collision():
+    """n = 512 with node 510 as a hub: reachable pairs whose last improving intermediate is node 510 carry path == 510 and
+    are skipped by the reference's gen_edge_input (algos.pyx:87-88).  The oracle must reproduce that."""
+    import build_ref
+    ref = build_ref.load()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    rng = np.random.default_rng(1022)
+    n = 512
+    adj = rng.random((n, n)) < 0.003
+    adj[510, rng.random(n) < 0.3] = True
+    adj[rng.random(n) < 0.3, 510] = True
+    ef = np.zeros((n, n, 1), np.int64)
+    ef[adj] = rng.integers(3, 50, size=(int(adj.sum()), 1))
+    M, p = ref.floyd_warshall(adj)
+    M2, p2 = algos_oracle.floyd_warshall(adj)
+    assert (M == M2).all() and (p == p2).all()
+    assert ((p == 510) & (M < 510)).sum() > 100
+    md = int(M[M < 510].max())              # hop axis just long enough for every walk (keeps the reference's temp small)
+    e = ref.gen_edge_input(md, p, ef)
+    e2 = algos_oracle.gen_edge_input(md, p2, ef)
+    assert e.shape == e2.shape and (e == e2).all()
+
+
 def test_fw_invariants_property():
     """SURVEY.md §4 property checks on the oracle."""
     rng = np.random.default_rng(11)
