@@ -44,6 +44,7 @@ struct AttnBwdParams {
     float scale;
     int max_boxes;
     int accumulate;            // 0: overwrite dbias, 1: dbias += dS
+    int bias_bufs;             // 1 or 2 bias tiles in shared memory
 };
 
 __device__ __forceinline__ float bwd_exp2(float x) {
@@ -52,34 +53,49 @@ __device__ __forceinline__ float bwd_exp2(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(128, 1)
+// d(bias) += v at 4 consecutive floats: one fire-and-forget vector reduction (REDG.E.ADD.F32x4) — no load round trip
+// in the tile loop.  Every dbias element is touched by exactly one thread per launch, launches are stream-ordered, so
+// the layer sum is still deterministic.
+__device__ __forceinline__ void red_add_f32x4(float *addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// 256 threads = two warpgroups.  Thread (wg, t128) owns query row t128 of the current tile (TMEM lane t128; warps w and
+// w+4 may both access lanes 32*(w%4)..+31) and the 16-column chunks c0 = 16*wg, 16*wg + 32, ... of the score tile.
+// Q / dO (and, when it fits, the bias tile) are double-buffered: the TMA loads of iteration t+1 are issued before the
+// S / dP MMAs of iteration t, so their latency hides behind the softmax-gradient math.
+__global__ void __launch_bounds__(256, 1)
 k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                    const __grid_constant__ CUtensorMap tmBias, const AttnBwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_qdo, bar_kv, bar_bias, bar_s, bar_mma;
+    __shared__ __align__(8) uint64_t bar_qdo[2], bar_bias[2], bar_kv, bar_s, bar_mma;
     __shared__ uint32_t tmem_slot;
     __shared__ float sLse[kMaxTiles * kTile], sDelta[kMaxTiles * kTile];
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, t128 = tid & 127;
     const int g = blockIdx.x / p.H, h = blockIdx.x - g * p.H;
     const int t0 = p.tok_off[g];
     const int Tg = p.tok_off[g + 1] - t0;
     const int NB = ceil_div(Tg, kTile);
+    const int NT = NB * NB;
     const int HD = p.H * kAttD;
+    const int nbias = p.bias_bufs;
 
-    uint8_t *sBias = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
-    uint8_t *sP = sBias + kBiasTileBytes;
+    uint8_t *sBias = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // nbias x 32 KB, 1024-aligned (swizzle atom)
+    uint8_t *sP = sBias + (size_t)nbias * kBiasTileBytes;
     uint8_t *sdS = sP + kPBytes;
-    uint8_t *sQ = sdS + kPBytes;
-    uint8_t *sdO = sQ + kBoxBytes;
-    uint8_t *sK = sdO + kBoxBytes;
+    uint8_t *sQ = sdS + kPBytes;            // 2 x 8 KB
+    uint8_t *sdO = sQ + 2 * kBoxBytes;      // 2 x 8 KB
+    uint8_t *sK = sdO + 2 * kBoxBytes;
     uint8_t *sV = sK + (size_t)p.max_boxes * kBoxBytes;
 
     if (tid == 0) {
-        mbar_init(&bar_qdo, 1);
+        mbar_init(&bar_qdo[0], 1);
+        mbar_init(&bar_qdo[1], 1);
+        mbar_init(&bar_bias[0], 1);
+        mbar_init(&bar_bias[1], 1);
         mbar_init(&bar_kv, 1);
-        mbar_init(&bar_bias, 1);
         mbar_init(&bar_s, 1);
         mbar_init(&bar_mma, 1);
         fence_barrier_init();
@@ -89,18 +105,18 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_prefetch_desc(&tmdO);
         tma_prefetch_desc(&tmBias);
     }
-    {
+    {   // zero the K-padding chunk (d = 24..31) of every operand box: 128 rows x 16 B each
         const uint4 z = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4 *>(sQ + 3 * kTile * 16 + tid * 16) = z;
-        *reinterpret_cast<uint4 *>(sdO + 3 * kTile * 16 + tid * 16) = z;
-        for (int b = 0; b < NB; ++b) {
-            *reinterpret_cast<uint4 *>(sK + (size_t)b * kBoxBytes + 3 * kTile * 16 + tid * 16) = z;
-            *reinterpret_cast<uint4 *>(sV + (size_t)b * kBoxBytes + 3 * kTile * 16 + tid * 16) = z;
-        }
+        uint8_t *qd = wg == 0 ? sQ : sdO;
+        *reinterpret_cast<uint4 *>(qd + 3 * kTile * 16 + t128 * 16) = z;
+        *reinterpret_cast<uint4 *>(qd + kBoxBytes + 3 * kTile * 16 + t128 * 16) = z;
+        uint8_t *kv = wg == 0 ? sK : sV;
+        for (int b = 0; b < NB; ++b) *reinterpret_cast<uint4 *>(kv + (size_t)b * kBoxBytes + 3 * kTile * 16 + t128 * 16) = z;
     }
-    // lse (log2 units) and D = rowsum(dO * O) of every query row of this (graph, head)
-    for (int r = tid; r < NB * kTile; r += 128) {
-        float lse2 = 0.f, dl = 0.f;
+    // lse (log2 units) and D = rowsum(dO * O) of every query row of this (graph, head).  Rows past the graph get
+    // lse = +inf, so that p = 2^(s - lse) = 0 and dS = 0 there without any per-element select.
+    for (int r = tid; r < NB * kTile; r += 256) {
+        float lse2 = INFINITY, dl = 0.f;
         if (r < Tg) {
             lse2 = p.lse[(size_t)(t0 + r) * p.H + h] * 1.4426950408889634f;
             const uint4 *po = reinterpret_cast<const uint4 *>(p.o + (size_t)(t0 + r) * HD + h * kAttD);
@@ -126,49 +142,63 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const uint32_t tS = tmem, tdP = tmem + 128, tdK = tmem + 256, tdV = tmem + 288, tdQ = tmem + 320;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const int plane = g * p.H + h;
 
+    // TMA loads of flattened iteration t = j * NB + i (thread 0 only)
+    auto load_qdo = [&](int t) {
+        const int i = t % NB, b = t & 1;
+        mbar_expect_tx(&bar_qdo[b], 2 * kBoxTxBytes);
+        tma_load_3d(sQ + b * kBoxBytes, &tmQ, &bar_qdo[b], 0, t0 + i * kTile, h * kAttChunks);
+        tma_load_3d(sdO + b * kBoxBytes, &tmdO, &bar_qdo[b], 0, t0 + i * kTile, h * kAttChunks);
+    };
+    auto load_bias = [&](int t) {
+        const int j = t / NB, i = t % NB, b = (nbias == 2) ? (t & 1) : 0;
+        uint8_t *dst = sBias + (size_t)b * kBiasTileBytes;
+        mbar_expect_tx(&bar_bias[b], kBiasTileBytes);
+        tma_load_3d(dst, &tmBias, &bar_bias[b], j * kTile, i * kTile, plane);
+        tma_load_3d(dst + kTile * 128, &tmBias, &bar_bias[b], j * kTile + 64, i * kTile, plane);
+    };
     if (tid == 0) {
         mbar_expect_tx(&bar_kv, (uint32_t)(2 * NB * kBoxTxBytes));
         for (int b = 0; b < NB; ++b) {
             tma_load_3d(sK + (size_t)b * kBoxBytes, &tmK, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
             tma_load_3d(sV + (size_t)b * kBoxBytes, &tmV, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
         }
+        load_qdo(0);
+        load_bias(0);
     }
     __syncwarp();
-    uint32_t ph_qdo = 0, ph_bias = 0, ph_s = 0, ph_mma = 0;
+    uint32_t ph_s = 0, ph_mma = 0;
     const float sl2 = p.scale * 1.4426950408889634f;
     constexpr float kL2e = 1.4426950408889634f;
-    const int plane = g * p.H + h;
-    bool first = true;
+    bool mma_pending = false;
 
     for (int j = 0; j < NB; ++j) {
         const int kv_valid = min(kTile, Tg - j * kTile);
         const int nb = round_up(kv_valid, 16);
         for (int i = 0; i < NB; ++i) {
+            const int t = j * NB + i, buf = t & 1;
             const int q_valid = min(kTile, Tg - i * kTile);
             const int qk = round_up(q_valid, 16);          // K extent (query rows) of the dV / dK MMAs
-            const int row = i * kTile + tid;
+            const int row = i * kTile + t128;
             const bool row_ok = row < Tg;
-            if (!first) {   // the previous iteration's dV/dK/dQ MMAs read sP, sdS, sQ, sdO
+            const bool warp_live = i * kTile + (warp & 3) * 32 < Tg;   // any valid query row in this warp's 32 lanes?
+            if (mma_pending) {   // the previous iteration's dV/dK/dQ MMAs read sP, sdS and the other Q / dO buffer
                 mbar_wait(&bar_mma, ph_mma);
                 ph_mma ^= 1;
                 tc_fence_after();
             }
-            first = false;
             if (tid == 0) {
-                mbar_expect_tx(&bar_qdo, 2 * kBoxTxBytes);
-                tma_load_3d(sQ, &tmQ, &bar_qdo, 0, t0 + i * kTile, h * kAttChunks);
-                tma_load_3d(sdO, &tmdO, &bar_qdo, 0, t0 + i * kTile, h * kAttChunks);
-                mbar_expect_tx(&bar_bias, kBiasTileBytes);
-                tma_load_3d(sBias, &tmBias, &bar_bias, j * kTile, i * kTile, plane);
-                tma_load_3d(sBias + kTile * 128, &tmBias, &bar_bias, j * kTile + 64, i * kTile, plane);
-                mbar_wait(&bar_qdo, ph_qdo);
-                ph_qdo ^= 1;
-                if (j == 0 && i == 0) mbar_wait(&bar_kv, 0);
+                if (t + 1 < NT) {
+                    load_qdo(t + 1);
+                    if (nbias == 2) load_bias(t + 1);
+                }
+                mbar_wait(&bar_qdo[buf], (t >> 1) & 1);
+                if (t == 0) mbar_wait(&bar_kv, 0);
                 tc_fence_after();
                 const uint32_t idesc = make_idesc_bf16(kTile, nb, 0, 0);
-                const uint32_t aq = smem_u32(sQ), ado = smem_u32(sdO);
+                const uint32_t aq = smem_u32(sQ + buf * kBoxBytes), ado = smem_u32(sdO + buf * kBoxBytes);
                 const uint32_t bk = smem_u32(sK + (size_t)j * kBoxBytes), bv = smem_u32(sV + (size_t)j * kBoxBytes);
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks)
@@ -183,60 +213,76 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             __syncwarp();
             mbar_wait(&bar_s, ph_s);
             ph_s ^= 1;
-            mbar_wait(&bar_bias, ph_bias);
-            ph_bias ^= 1;
+            const int bb = (nbias == 2) ? buf : 0;
+            mbar_wait(&bar_bias[bb], (nbias == 2) ? ((t >> 1) & 1) : (t & 1));
             tc_fence_after();
 
-            const float lse2 = sLse[row < NB * kTile ? row : 0];
-            const float delta = sDelta[row < NB * kTile ? row : 0];
-            float *db_row = p.dbias + ((size_t)plane * p.T + row) * p.Tp + j * kTile;
-            for (int c0 = 0; c0 < nb; c0 += 16) {
-                uint32_t sv[16], dpv[16];
-                tmem_ld16(tS + lane_off + c0, sv);
-                tmem_ld16(tdP + lane_off + c0, dpv);
-                tmem_ld_wait();
+            if (warp_live) {
+                const uint8_t *sB = sBias + (size_t)bb * kBiasTileBytes;
+                const float lse2 = sLse[row];
+                const float delta = sDelta[row];
+                float *db_row = p.dbias + ((size_t)plane * p.T + row) * p.Tp + j * kTile;
+                for (int c0 = wg * 16; c0 < nb; c0 += 32) {
+                    uint32_t sv[16], dpv[16];
+                    tmem_ld16(tS + lane_off + c0, sv);
+                    tmem_ld16(tdP + lane_off + c0, dpv);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int q8 = 0; q8 < 2; ++q8) {
-                    const int c8 = (c0 >> 3) + q8;
-                    const uint8_t *bp = sBias + (c8 >> 3) * (kTile * 128) + tid * 128 + (((c8 & 7) ^ (tid & 7)) << 4);
-                    const uint4 bvv = *reinterpret_cast<const uint4 *>(bp);
-                    const uint32_t bw[4] = {bvv.x, bvv.y, bvv.z, bvv.w};
-                    float pv[8], dsv[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int col = c8 * 8 + e;
-                        const float bias = __uint_as_float((e & 1) ? (bw[e >> 1] & 0xFFFF0000u) : (bw[e >> 1] << 16));
-                        const float s = __uint_as_float(sv[q8 * 8 + e]) * sl2 + bias * kL2e;
-                        const bool ok = row_ok && (col < kv_valid);
-                        const float pe = ok ? bwd_exp2(s - lse2) : 0.f;
-                        pv[e] = pe;
-                        dsv[e] = ok ? pe * (__uint_as_float(dpv[q8 * 8 + e]) - delta) : 0.f;
-                    }
-                    uint4 pk, dk;
-                    pk.x = pack_bf16(pv[0], pv[1]); pk.y = pack_bf16(pv[2], pv[3]);
-                    pk.z = pack_bf16(pv[4], pv[5]); pk.w = pack_bf16(pv[6], pv[7]);
-                    dk.x = pack_bf16(dsv[0], dsv[1]); dk.y = pack_bf16(dsv[2], dsv[3]);
-                    dk.z = pack_bf16(dsv[4], dsv[5]); dk.w = pack_bf16(dsv[6], dsv[7]);
-                    *reinterpret_cast<uint4 *>(sP + c8 * (kTile * 16) + tid * 16) = pk;
-                    *reinterpret_cast<uint4 *>(sdS + c8 * (kTile * 16) + tid * 16) = dk;
-                    if (row_ok) {   // d(bias) = dS, fp32, this thread's row
+                    for (int q8 = 0; q8 < 2; ++q8) {
+                        const int c8 = (c0 >> 3) + q8;
                         const int colb = c8 * 8;
-                        if (colb + 8 <= kv_valid) {
-                            float4 *d4 = reinterpret_cast<float4 *>(db_row + colb);
-                            float4 v0 = make_float4(dsv[0], dsv[1], dsv[2], dsv[3]);
-                            float4 v1 = make_float4(dsv[4], dsv[5], dsv[6], dsv[7]);
-                            if (p.accumulate) {
-                                const float4 o0 = d4[0], o1 = d4[1];
-                                v0.x += o0.x; v0.y += o0.y; v0.z += o0.z; v0.w += o0.w;
-                                v1.x += o1.x; v1.y += o1.y; v1.z += o1.z; v1.w += o1.w;
-                            }
-                            d4[0] = v0;
-                            d4[1] = v1;
-                        } else {
+                        const uint8_t *bp = sB + (c8 >> 3) * (kTile * 128) + t128 * 128 + (((c8 & 7) ^ (t128 & 7)) << 4);
+                        uint4 bvv = *reinterpret_cast<const uint4 *>(bp);
+                        if (!row_ok) bvv = make_uint4(0, 0, 0, 0);   // bias rows past the graph are never written: not numbers
+                        const uint32_t bw[4] = {bvv.x, bvv.y, bvv.z, bvv.w};
+                        float dsv[8];
+                        uint4 pk, dk;
+                        if (colb + 8 <= kv_valid) {   // all 8 key columns valid: no per-element masking
+                            float pv[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e)
-                                if (colb + e < kv_valid) db_row[colb + e] = p.accumulate ? db_row[colb + e] + dsv[e] : dsv[e];
+                            for (int e = 0; e < 8; ++e) {
+                                const float bias = __uint_as_float((e & 1) ? (bw[e >> 1] & 0xFFFF0000u) : (bw[e >> 1] << 16));
+                                const float s = fmaf(__uint_as_float(sv[q8 * 8 + e]), sl2, bias * kL2e);
+                                pv[e] = bwd_exp2(s - lse2);
+                                dsv[e] = pv[e] * (__uint_as_float(dpv[q8 * 8 + e]) - delta);
+                            }
+                            pk.x = pack_bf16(pv[0], pv[1]); pk.y = pack_bf16(pv[2], pv[3]);
+                            pk.z = pack_bf16(pv[4], pv[5]); pk.w = pack_bf16(pv[6], pv[7]);
+                            if (row_ok) {   // d(bias) = dS, fp32, this thread's row
+                                if (p.accumulate) {
+                                    red_add_f32x4(db_row + colb, dsv[0], dsv[1], dsv[2], dsv[3]);
+                                    red_add_f32x4(db_row + colb + 4, dsv[4], dsv[5], dsv[6], dsv[7]);
+                                } else {
+                                    float4 *d4 = reinterpret_cast<float4 *>(db_row + colb);
+                                    d4[0] = make_float4(dsv[0], dsv[1], dsv[2], dsv[3]);
+                                    d4[1] = make_float4(dsv[4], dsv[5], dsv[6], dsv[7]);
+                                }
+                            }
+                        } else {                      // ragged edge of the graph (bias padding columns are never read as numbers)
+                            float pv[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const bool ok = row_ok && (colb + e < kv_valid);
+                                const float bias = __uint_as_float((e & 1) ? (bw[e >> 1] & 0xFFFF0000u) : (bw[e >> 1] << 16));
+                                const float s = fmaf(__uint_as_float(sv[q8 * 8 + e]), sl2, bias * kL2e);
+                                pv[e] = ok ? bwd_exp2(s - lse2) : 0.f;
+                                dsv[e] = ok ? pv[e] * (__uint_as_float(dpv[q8 * 8 + e]) - delta) : 0.f;
+                            }
+                            pk.x = pack_bf16(pv[0], pv[1]); pk.y = pack_bf16(pv[2], pv[3]);
+                            pk.z = pack_bf16(pv[4], pv[5]); pk.w = pack_bf16(pv[6], pv[7]);
+                            if (row_ok) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e)
+                                    if (colb + e < kv_valid) {
+                                        if (p.accumulate) atomicAdd(db_row + colb + e, dsv[e]);
+                                        else db_row[colb + e] = dsv[e];
+                                    }
+                            }
                         }
+                        dk.x = pack_bf16(dsv[0], dsv[1]); dk.y = pack_bf16(dsv[2], dsv[3]);
+                        dk.z = pack_bf16(dsv[4], dsv[5]); dk.w = pack_bf16(dsv[6], dsv[7]);
+                        *reinterpret_cast<uint4 *>(sP + c8 * (kTile * 16) + t128 * 16) = pk;
+                        *reinterpret_cast<uint4 *>(sdS + c8 * (kTile * 16) + t128 * 16) = dk;
                     }
                 }
             }
@@ -245,7 +291,9 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             __syncthreads();
             if (tid == 0) {
                 tc_fence_after();
-                const uint32_t aP = smem_u32(sP), aS = smem_u32(sdS), bQ = smem_u32(sQ), bdO = smem_u32(sdO);
+                if (nbias == 1 && t + 1 < NT) load_bias(t + 1);   // single bias buffer: free only now
+                const uint32_t aP = smem_u32(sP), aS = smem_u32(sdS);
+                const uint32_t bQ = smem_u32(sQ + buf * kBoxBytes), bdO = smem_u32(sdO + buf * kBoxBytes);
                 const uint32_t bK = smem_u32(sK + (size_t)j * kBoxBytes);
                 const uint32_t id_t = make_idesc_bf16(kTile, 32, 1, 1);   // A = P^T / dS^T (MN-major), B MN-major
                 const uint32_t id_q = make_idesc_bf16(kTile, 32, 0, 1);   // A = dS (K-major),        B MN-major
@@ -261,47 +309,41 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 umma_commit(&bar_mma);
             }
             __syncwarp();
+            mma_pending = true;
         }
-        // ---- dK_j, dV_j complete: TMEM -> bf16 -> global (key row = j*128 + tid)
+        // ---- dK_j (warpgroup 0) and dV_j (warpgroup 1) complete: TMEM -> bf16 -> global (key row = j*128 + t128)
         mbar_wait(&bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
-        first = true;   // the wait above already covered the last iteration's MMAs
+        mma_pending = false;   // the wait above already covered the last iteration's MMAs
         {
-            uint32_t kvv[32];
-            const int krow = j * kTile + tid;
-            tmem_ld32(tdK + lane_off, kvv);
-            tmem_ld_wait();
-            if (krow < Tg) {
-                uint32_t w[12];
+            const int krow = j * kTile + t128;
+            if (j * kTile + (warp & 3) * 32 < Tg) {
+                uint32_t kvv[32];
+                tmem_ld32((wg == 0 ? tdK : tdV) + lane_off, kvv);
+                tmem_ld_wait();
+                if (krow < Tg) {
+                    const float sc = wg == 0 ? p.scale : 1.0f;
+                    uint32_t w[12];
 #pragma unroll
-                for (int e = 0; e < 12; ++e)
-                    w[e] = pack_bf16(__uint_as_float(kvv[2 * e]) * p.scale, __uint_as_float(kvv[2 * e + 1]) * p.scale);
-                uint4 *dst = reinterpret_cast<uint4 *>(p.dk + (size_t)(t0 + krow) * p.dqkv_stride + h * kAttD);
-                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
-            }
-            tmem_ld32(tdV + lane_off, kvv);
-            tmem_ld_wait();
-            if (krow < Tg) {
-                uint32_t w[12];
-#pragma unroll
-                for (int e = 0; e < 12; ++e) w[e] = pack_bf16(__uint_as_float(kvv[2 * e]), __uint_as_float(kvv[2 * e + 1]));
-                uint4 *dst = reinterpret_cast<uint4 *>(p.dv + (size_t)(t0 + krow) * p.dqkv_stride + h * kAttD);
-                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+                    for (int e = 0; e < 12; ++e)
+                        w[e] = pack_bf16(__uint_as_float(kvv[2 * e]) * sc, __uint_as_float(kvv[2 * e + 1]) * sc);
+                    uint4 *dst = reinterpret_cast<uint4 *>((wg == 0 ? p.dk : p.dv) + (size_t)(t0 + krow) * p.dqkv_stride + h * kAttD);
+                    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+                }
             }
         }
         tc_fence_before();
         __syncthreads();
     }
-    // ---- dQ_i for every query tile
+    // ---- dQ_i for every query tile (tiles alternate between the warpgroups)
     tc_fence_after();
-    for (int i = 0; i < NB; ++i) {
+    for (int i = wg; i < NB; i += 2) {
+        const int row = i * kTile + t128;
+        if (i * kTile + (warp & 3) * 32 >= Tg) continue;
         uint32_t qv[32];
-        const int row = i * kTile + tid;
         tmem_ld32(tdQ + 32 * i + lane_off, qv);
         tmem_ld_wait();
         if (row < Tg) {
@@ -356,7 +398,9 @@ extern "C" int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, i
         if (rc) return rc;
     }
     const int max_boxes = ceil_div(t_max_host, kTile);
-    const size_t smem = (size_t)kBiasTileBytes + 2 * kPBytes + 2 * kBoxBytes + (size_t)2 * max_boxes * kBoxBytes + 1024;
+    const size_t smem_base = 2 * kPBytes + 4 * kBoxBytes + (size_t)2 * max_boxes * kBoxBytes + 1024;
+    const int bias_bufs = (smem_base + 2 * kBiasTileBytes <= 220 * 1024) ? 2 : 1;
+    const size_t smem = smem_base + (size_t)bias_bufs * kBiasTileBytes;
     MOBGT_CUDA_OK(cudaFuncSetAttribute(k3_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AttnBwdParams p{tok_off,
                     static_cast<const __nv_bfloat16 *>(o),
@@ -372,8 +416,9 @@ extern "C" int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, i
                     Tp,
                     scale,
                     max_boxes,
-                    accumulate};
-    k3_attn_bwd_kernel<<<B * H, 128, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmdO, tmB, p);
+                    accumulate,
+                    bias_bufs};
+    k3_attn_bwd_kernel<<<B * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmdO, tmB, p);
     MOBGT_LAUNCH_OK("k3_attn_bwd_kernel");
     return MOBGT_OK;
 }

@@ -43,15 +43,22 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(128, 1)
+// 256 threads = two warpgroups.  Thread (wg, t128) owns query row t128 of the current tile (TMEM lane t128; warps w and
+// w+4 may both access lanes 32*(w%4)..+31) and the 16-column chunks c0 = 16*wg, 16*wg + 32, ... of the score tile, i.e. at
+// most 64 scores, which stay in registers between the max pass and the exp pass (one TMEM read, one bias decode).
+// The row max is exchanged between the warpgroups through shared memory; the row sums are combined once per query tile.
+// After the max pass nobody needs the bias tile any more, so the next tile's TMA load is issued there and overlaps the
+// exp pass and the P.V MMA.
+__global__ void __launch_bounds__(256, 2)
 k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBias,
                    const AttnFwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_q, bar_kv, bar_bias, bar_s, bar_o;
     __shared__ uint32_t tmem_slot;
+    __shared__ float sMax[2][kTile];
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, t128 = tid & 127;
     const int g = blockIdx.x / p.H, h = blockIdx.x - g * p.H;
     const int t0 = p.tok_off[g];
     const int Tg = p.tok_off[g + 1] - t0;
@@ -78,11 +85,9 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // zero the K-padding chunk (d = 24..31) of Q and of every K / V box: 128 rows x 16 B each
     {
         const uint4 z = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4 *>(sQ + 3 * kTile * 16 + tid * 16) = z;
-        for (int b = 0; b < NB; ++b) {
-            *reinterpret_cast<uint4 *>(sK + (size_t)b * kBoxBytes + 3 * kTile * 16 + tid * 16) = z;
-            *reinterpret_cast<uint4 *>(sV + (size_t)b * kBoxBytes + 3 * kTile * 16 + tid * 16) = z;
-        }
+        if (wg == 0) *reinterpret_cast<uint4 *>(sQ + 3 * kTile * 16 + t128 * 16) = z;
+        uint8_t *kv = wg == 0 ? sK : sV;
+        for (int b = 0; b < NB; ++b) *reinterpret_cast<uint4 *>(kv + (size_t)b * kBoxBytes + 3 * kTile * 16 + t128 * 16) = z;
     }
     if (warp == 0) tmem_alloc<256>(&tmem_slot);
     fence_proxy_async_smem();
@@ -91,39 +96,44 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const uint32_t tS = tmem, tO = tmem + 128;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const int plane = g * p.H + h;
 
+    auto load_bias = [&](int i, int j) {   // thread 0 only
+        mbar_expect_tx(&bar_bias, kBiasTileBytes);
+        tma_load_3d(sBias, &tmBias, &bar_bias, j * kTile, i * kTile, plane);
+        tma_load_3d(sBias + kTile * 128, &tmBias, &bar_bias, j * kTile + 64, i * kTile, plane);
+    };
+    auto load_q = [&](int i) {             // thread 0 only
+        mbar_expect_tx(&bar_q, kBoxTxBytes);
+        tma_load_3d(sQ, &tmQ, &bar_q, 0, t0 + i * kTile, h * kAttChunks);
+    };
     if (tid == 0) {
         mbar_expect_tx(&bar_kv, (uint32_t)(2 * NB * kBoxTxBytes));
         for (int b = 0; b < NB; ++b) {
             tma_load_3d(sK + (size_t)b * kBoxBytes, &tmK, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
             tma_load_3d(sV + (size_t)b * kBoxBytes, &tmV, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
         }
+        load_q(0);
+        load_bias(0, 0);
     }
     __syncwarp();
     uint32_t ph_q = 0, ph_bias = 0, ph_s = 0, ph_o = 0;
     const float sl2 = p.scale * 1.4426950408889634f;  // scale * log2(e)
     constexpr float kL2e = 1.4426950408889634f;
-    const int plane = g * p.H + h;
 
     for (int i = 0; i < NB; ++i) {
-        const int row = i * kTile + tid;       // query row inside the graph
+        const int row = i * kTile + t128;      // query row inside the graph
         const bool row_ok = row < Tg;
-        if (tid == 0) {
-            mbar_expect_tx(&bar_q, kBoxTxBytes);
-            tma_load_3d(sQ, &tmQ, &bar_q, 0, t0 + i * kTile, h * kAttChunks);
-            mbar_expect_tx(&bar_bias, kBiasTileBytes);
-            tma_load_3d(sBias, &tmBias, &bar_bias, 0, i * kTile, plane);
-            tma_load_3d(sBias + kTile * 128, &tmBias, &bar_bias, 64, i * kTile, plane);
-        }
-        __syncwarp();
-        float m_run = -INFINITY, l_run = 0.f;  // running max (in log2 units of the scaled score) and sum
+        const bool warp_live = i * kTile + (warp & 3) * 32 < Tg;   // any valid query row in this warp's 32 lanes?
+        float m_run = -INFINITY, l_run = 0.f;  // running max (log2 units of the scaled score); this warpgroup's share of the sum
         for (int j = 0; j < NB; ++j) {
             const int kv_valid = min(kTile, Tg - j * kTile);    // valid key columns in this block
             const int nb = round_up(kv_valid, 16);              // MMA N / K extent
             if (tid == 0) {
                 if (j == 0) {
                     mbar_wait(&bar_q, ph_q);
+                    ph_q ^= 1;
                     if (i == 0) mbar_wait(&bar_kv, 0);
                 }
                 tc_fence_after();
@@ -138,33 +148,51 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             __syncwarp();
             mbar_wait(&bar_s, ph_s);
             ph_s ^= 1;
+            if (tid == 0 && j + 1 == NB && i + 1 < NB) load_q(i + 1);   // the last S MMA of this tile has consumed Q
             mbar_wait(&bar_bias, ph_bias);
             ph_bias ^= 1;
             tc_fence_after();
 
-            // ---- pass 1: row max of (scale * S + bias) over the valid columns, in log2 units
+            // ---- pass 1: s = scale * S + bias (log2 units) for this thread's columns -> registers; row max
+            float sreg[64];
             float m_blk = -INFINITY;
-            for (int c0 = 0; c0 < nb; c0 += 16) {
-                uint32_t sv[16];
-                tmem_ld16(tS + lane_off + c0, sv);
-                tmem_ld_wait();
+            if (warp_live) {
 #pragma unroll
-                for (int q8 = 0; q8 < 2; ++q8) {
-                    const int c8 = (c0 >> 3) + q8;             // 8-column chunk index inside the 128-wide tile
-                    const uint8_t *bp = sBias + (c8 >> 3) * (kTile * 128) + tid * 128 + (((c8 & 7) ^ (tid & 7)) << 4);
-                    const uint4 bv = *reinterpret_cast<const uint4 *>(bp);
-                    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c0 = wg * 16 + cc * 32;
+                    if (c0 < nb) {
+                        uint32_t sv[16];
+                        tmem_ld16(tS + lane_off + c0, sv);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int col = c8 * 8 + e;
-                        const float bias = __uint_as_float((e & 1) ? (bw[e >> 1] & 0xFFFF0000u) : (bw[e >> 1] << 16));
-                        const float s = __uint_as_float(sv[q8 * 8 + e]) * sl2 + bias * kL2e;
-                        if (col < kv_valid) m_blk = fmaxf(m_blk, s);
+                        for (int q8 = 0; q8 < 2; ++q8) {
+                            const int c8 = (c0 >> 3) + q8;             // 8-column chunk index inside the 128-wide tile
+                            const uint8_t *bp = sBias + (c8 >> 3) * (kTile * 128) + t128 * 128 + (((c8 & 7) ^ (t128 & 7)) << 4);
+                            uint4 bv = *reinterpret_cast<const uint4 *>(bp);
+                            if (!row_ok) bv = make_uint4(0, 0, 0, 0);   // bias rows past the graph are never written
+                            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+                            const bool full = c8 * 8 + 8 <= kv_valid;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float bias = __uint_as_float((e & 1) ? (bw[e >> 1] & 0xFFFF0000u) : (bw[e >> 1] << 16));
+                                float s = fmaf(__uint_as_float(sv[q8 * 8 + e]), sl2, bias * kL2e);
+                                if (!full && c8 * 8 + e >= kv_valid) s = -INFINITY;   // padding key columns (collator.py:57-64)
+                                sreg[cc * 16 + q8 * 8 + e] = s;
+                                m_blk = fmaxf(m_blk, s);
+                            }
+                        }
                     }
                 }
             }
+            sMax[wg][t128] = m_blk;
+            __syncthreads();              // both halves of every row max are visible; nobody reads the bias tile any more
+            if (tid == 0) {
+                if (j + 1 < NB) load_bias(i, j + 1);
+                else if (i + 1 < NB) load_bias(i + 1, 0);
+            }
+            m_blk = fmaxf(m_blk, sMax[wg ^ 1][t128]);
             const float m_new = fmaxf(m_run, m_blk);
-            const float m_use = row_ok ? m_new : 0.f;           // garbage rows: keep the arithmetic finite
+            const float m_use = (m_new == -INFINITY) ? 0.f : m_new;   // rows past the graph: keep the arithmetic finite
             const float alpha = (j == 0) ? 0.f : fast_exp2(m_run - m_use);
             // ---- pass 2: p = 2^(s - m), row sum, bf16 P tile to shared memory ([chunk][row][8])
             if (j > 0) {   // the previous P.V must be complete before P / O are touched again
@@ -173,45 +201,39 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 tc_fence_after();
             }
             float l_blk = 0.f;
-            for (int c0 = 0; c0 < nb; c0 += 16) {
-                uint32_t sv[16];
-                tmem_ld16(tS + lane_off + c0, sv);
-                tmem_ld_wait();
+            if (warp_live) {
 #pragma unroll
-                for (int q8 = 0; q8 < 2; ++q8) {
-                    const int c8 = (c0 >> 3) + q8;
-                    const uint8_t *bp = sBias + (c8 >> 3) * (kTile * 128) + tid * 128 + (((c8 & 7) ^ (tid & 7)) << 4);
-                    const uint4 bv = *reinterpret_cast<const uint4 *>(bp);
-                    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-                    float pv[8];
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c0 = wg * 16 + cc * 32;
+                    if (c0 < nb) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int col = c8 * 8 + e;
-                        const float bias = __uint_as_float((e & 1) ? (bw[e >> 1] & 0xFFFF0000u) : (bw[e >> 1] << 16));
-                        const float s = __uint_as_float(sv[q8 * 8 + e]) * sl2 + bias * kL2e;
-                        float pe = (col < kv_valid && row_ok) ? fast_exp2(s - m_use) : 0.f;
-                        pv[e] = pe;
+                        for (int q8 = 0; q8 < 2; ++q8) {
+                            const int c8 = (c0 >> 3) + q8;
+                            float pv[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                pv[e] = fast_exp2(sreg[cc * 16 + q8 * 8 + e] - m_use);
+                                l_blk += pv[e];     // row sum in fp32 (P is rounded to bf16 only for the tensor-core operand)
+                            }
+                            uint4 pk;
+                            pk.x = pack_bf16(pv[0], pv[1]);
+                            pk.y = pack_bf16(pv[2], pv[3]);
+                            pk.z = pack_bf16(pv[4], pv[5]);
+                            pk.w = pack_bf16(pv[6], pv[7]);
+                            *reinterpret_cast<uint4 *>(sP + c8 * (kTile * 16) + t128 * 16) = pk;
+                        }
                     }
-                    uint4 pk;
-                    pk.x = pack_bf16(pv[0], pv[1]);
-                    pk.y = pack_bf16(pv[2], pv[3]);
-                    pk.z = pack_bf16(pv[4], pv[5]);
-                    pk.w = pack_bf16(pv[6], pv[7]);
-                    // row sum in fp32 (P itself is rounded to bf16 only for the tensor-core operand)
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) l_blk += pv[e];
-                    *reinterpret_cast<uint4 *>(sP + c8 * (kTile * 16) + tid * 16) = pk;
                 }
             }
             l_run = l_run * alpha + l_blk;
             m_run = m_new;
-            if (j > 0) {   // rescale the running O accumulator
-                uint32_t ov[32];
-                tmem_ld32(tO + lane_off, ov);
+            if (j > 0 && warp_live) {   // rescale the running O accumulator (16 of the 32 columns per warpgroup)
+                uint32_t ov[16];
+                tmem_ld16(tO + lane_off + wg * 16, ov);
                 tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
-                tmem_st32(tO + lane_off, ov);
+                for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+                tmem_st16(tO + lane_off + wg * 16, ov);
                 tmem_st_wait();
             }
             fence_proxy_async_smem();
@@ -225,39 +247,39 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     umma_bf16(tO, make_smem_desc(ap + ks * 2 * kTile * 16, kTile * 16, 128),
                               make_smem_desc(bv + ks * 256, 128, kTile * 16), idesc, (j > 0 || ks > 0));
                 umma_commit(&bar_o);
-                // the bias tile and (on the last block) Q are free again: prefetch the next tile
-                if (j + 1 < NB) {
-                    mbar_expect_tx(&bar_bias, kBiasTileBytes);
-                    tma_load_3d(sBias, &tmBias, &bar_bias, (j + 1) * kTile, i * kTile, plane);
-                    tma_load_3d(sBias + kTile * 128, &tmBias, &bar_bias, (j + 1) * kTile + 64, i * kTile, plane);
-                }
             }
             __syncwarp();
         }
-        if (tid == 0) ph_q ^= 1;
-        // ---- epilogue of the query tile: O / l -> bf16, lse
+        // ---- epilogue of the query tile: O / l -> bf16, lse.  The two warpgroups' shares of the row sum are exchanged
+        //      through sMax (free since the last barrier of the j loop); each warpgroup stores 16 of the 32 O columns.
+        sMax[wg][t128] = l_run;
         mbar_wait(&bar_o, ph_o);
         ph_o ^= 1;
         tc_fence_after();
-        {
-            uint32_t ov[32];
-            tmem_ld32(tO + lane_off, ov);
+        __syncthreads();
+        if (warp_live) {
+            uint32_t ov[16];
+            tmem_ld16(tO + lane_off + wg * 16, ov);
             tmem_ld_wait();
             if (row_ok) {
-                const float inv = 1.0f / l_run;
-                uint32_t w[12];
+                const float l_tot = sMax[0][t128] + sMax[1][t128];
+                const float inv = 1.0f / l_tot;
+                uint32_t w[8];
 #pragma unroll
-                for (int e = 0; e < 12; ++e)
+                for (int e = 0; e < 8; ++e)
                     w[e] = pack_bf16(__uint_as_float(ov[2 * e]) * inv, __uint_as_float(ov[2 * e + 1]) * inv);
                 uint4 *dst = reinterpret_cast<uint4 *>(p.out + (size_t)(t0 + row) * (p.H * kAttD) + h * kAttD);
-                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
-                p.lse[(size_t)(t0 + row) * p.H + h] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+                if (wg == 0) {
+                    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    p.lse[(size_t)(t0 + row) * p.H + h] = (m_run + log2f(l_tot)) * 0.6931471805599453f;
+                } else {
+                    dst[2] = make_uint4(w[0], w[1], w[2], w[3]);   // columns 16..23 (24..31 are the MMA padding)
+                }
             }
         }
         tc_fence_before();
-        __syncthreads();   // every thread is done with TMEM S/O and sQ/sBias before the next tile's loads
+        __syncthreads();   // every thread is done with TMEM S/O before the next tile's MMAs
     }
     tc_fence_before();
     __syncthreads();
@@ -301,7 +323,7 @@ extern "C" int32_t mobgt_attn_fwd(const void *q, const void *k, const void *v, i
     const size_t smem = (size_t)kBiasTileBytes + kPBytes + kBoxBytes + (size_t)2 * max_boxes * kBoxBytes + 1024;
     MOBGT_CUDA_OK(cudaFuncSetAttribute(k3_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AttnFwdParams p{tok_off, static_cast<__nv_bfloat16 *>(out), lse, H, scale, max_boxes};
-    k3_attn_fwd_kernel<<<B * H, 128, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmB, p);
+    k3_attn_fwd_kernel<<<B * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmB, p);
     MOBGT_LAUNCH_OK("k3_attn_fwd_kernel");
     return MOBGT_OK;
 }

@@ -318,25 +318,12 @@ def topk_merge_lists(val, idx):
 
 def head_topk_sharded(z, W_shard, bias_shard, target, k, vocab_offset, group=None):
     """Vocabulary-parallel evaluation head: every rank holds rows [vocab_offset, vocab_offset+V_r) of
-    out_proj and the full z.  s_t: owner shard computes it, all-reduce MAX.  Top-k: per-shard lists, all-gather over
-    NVLink (NCCL), k-way merge (ties -> lower index).  Rank of the target: all-reduce SUM of the partial counts."""
-    import torch.distributed as dist
-    st = head_target_logit(z, W_shard, bias_shard, target, vocab_offset)
-    ws = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-    if ws > 1:
-        dist.all_reduce(st, op=dist.ReduceOp.MAX, group=group)
-    loc = head_topk_local(z, W_shard, bias_shard, target, k, vocab_offset, st=st)
-    if ws == 1:
-        return dict(val=loc["val"], idx=loc["idx"], rank=loc["cnt"], st=st)
-    M = z.shape[0]
-    gv = torch.empty(ws, M, k, dtype=torch.float32, device=z.device)
-    gi = torch.empty(ws, M, k, dtype=torch.int32, device=z.device)
-    dist.all_gather_into_tensor(gv, loc["val"], group=group)
-    dist.all_gather_into_tensor(gi, loc["idx"], group=group)
-    cnt = loc["cnt"].clone()
-    dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
-    val, idx = topk_merge_lists(gv.permute(1, 0, 2), gi.permute(1, 0, 2))
-    return dict(val=val, idx=idx, rank=cnt, st=st)
+    out_proj and the full z.  The collective choreography (s_t all-reduce MAX -> local top-k / counts -> all-gather of the
+    lists over NVLink -> all-reduce SUM of the counts -> k-way merge, ties -> lower index) lives in parallel.py so that it
+    is also exercised over gloo on CPU; here it is bound to the libmobgt kernels."""
+    import sys
+    from . import parallel
+    return parallel.sharded_head_topk(sys.modules[__name__], z, W_shard, bias_shard, target, k, vocab_offset, group)
 
 
 def metrics_from_rank(rank, target, ks=(1, 5, 10, 20)):
