@@ -187,7 +187,8 @@ def kernel_report(model, batch, pk, iters=8, head_c5=True):
     qkv = torch.randn(ntok, 576, device=dev).to(torch.bfloat16)
     out, lse = ops.attn_fwd_raw(qkv, bias, batch)
     dout = torch.randn(ntok, 192, device=dev).to(torch.bfloat16)
-    dbias = torch.zeros(bias.shape, dtype=torch.float32, device=dev)
+    n_layers = len(model.layers)
+    planes = torch.zeros((n_layers,) + tuple(bias.shape), dtype=torch.bfloat16, device=dev)   # per-layer dS planes (bf16)
     rep = {}
     tk = lambda fn: time_kernel(fn, flush, iters=iters, warm=min(2, iters))
 
@@ -200,12 +201,12 @@ def kernel_report(model, batch, pk, iters=8, head_c5=True):
     add("k1_apsp_edge_input", tk(lambda: apsp_edge_input_packed(batch.feat8, batch.n, batch.sq_off, batch.n_host, hops, 1)),
         cells * (1 + 2 + hops), 0)
     add("k2_bias_fwd", tk(lambda: ops.bias_fwd_raw(batch, *tabs)), cells * (4 + hops) + H * pairs_t * 2, 1)
-    add("k2_bias_bwd", tk(lambda: ops.bias_bwd_raw(batch, dbias, tabs[2], tabs[3], tabs[1].shape[0])),
-        cells * (4 + hops) + H * pairs_t * 4, 1)
+    add("k2_bias_bwd", tk(lambda: ops.bias_bwd_raw(batch, planes, tabs[2], tabs[3], tabs[1].shape[0])),
+        cells * (4 + hops) + n_layers * H * pairs_t * 2, 1)
     fl = 4.0 * H * pairs_t * 24
     add("k3_attn_fwd", tk(lambda: ops.attn_fwd_raw(qkv, bias, batch)), 4 * ntok * 192 * 2 + H * pairs_t * 2, 6, fl)
-    add("k3_attn_bwd", tk(lambda: ops.attn_bwd_raw(qkv, bias, out, dout, lse, batch, dbias, 1)),
-        8 * ntok * 192 * 2 + H * pairs_t * 2 + H * pairs_t * 8, 6, 2.5 * fl)
+    add("k3_attn_bwd", tk(lambda: ops.attn_bwd_raw(qkv, bias, out, dout, lse, batch, planes[0], 2)),
+        8 * ntok * 192 * 2 + H * pairs_t * 2 + H * pairs_t * 2, 6, 2.5 * fl)
     Gd, Gc = model.gcn_tables()
     Gd, Gc = Gd.detach(), Gc.detach()
     Tm = model.time_embed_model_48.weight.detach()

@@ -106,8 +106,10 @@ int32_t mobgt_poi_pos(const int32_t *x, const int32_t *n, const int64_t *sq_off,
  *           W [>=hops*H*H] edge_dis_encoder (viewed [k,h',h]), tvd [H] graph_token_virtual_distance.
  *   hops is the hop-slot count of edge_in (a multiple of 4, as written by K1) and the clamp of the mean.
  *   forward workspace: hops*128*H floats (the E.W table); backward workspace: mobgt_bias_bwd_workspace_bytes().
- * Backward: dBias f32 [B,H,T,Tp] (sum over layers) -> dR [512,H], dPpos [bins,H], dE [128,H],
- * dW [hops*H*H], dtvd [H]  (all overwritten).
+ * Backward: dBias -> dR [512,H], dPpos [bins,H], dE [128,H], dW [hops*H*H], dtvd [H]  (all overwritten).
+ *   dbias_dtype MOBGT_F32:  one f32 [B,H,T,Tp] buffer holding the sum over layers (n_layers = 1);
+ *   dbias_dtype MOBGT_BF16: n_layers bf16 [B,H,T,Tp] planes, layer_stride elements apart (mobgt_attn_bwd mode 2),
+ *                           summed in fp32 inside the kernel.
  * ------------------------------------------------------------------------------------------ */
 int32_t mobgt_bias_fwd(const int32_t *n, const int64_t *sq_off, const int16_t *rel_pos, const int16_t *poi_pos,
                        const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t H,
@@ -117,9 +119,9 @@ int32_t mobgt_bias_fwd(const int32_t *n, const int64_t *sq_off, const int16_t *r
 int64_t mobgt_bias_bwd_workspace_bytes(int32_t T, int32_t hops, int32_t num_bins);
 int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const int16_t *rel_pos, const int16_t *poi_pos,
                        const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t H,
-                       int32_t rel_pos_max, int32_t num_bins, const float *dBias, const float *E, const float *W,
-                       void *workspace, int64_t workspace_bytes, float *dR, float *dPpos, float *dE, float *dW,
-                       float *dtvd, void *stream);
+                       int32_t rel_pos_max, int32_t num_bins, const void *dBias, int32_t dbias_dtype, int32_t n_layers,
+                       int64_t layer_stride, const float *E, const float *W, void *workspace, int64_t workspace_bytes,
+                       float *dR, float *dPpos, float *dE, float *dW, float *dtvd, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3 — biased multi-head attention (tcgen05 / TMEM / TMA).  Replaces the core of
@@ -134,13 +136,16 @@ int32_t mobgt_attn_fwd(const void *q, const void *k, const void *v, int64_t qkv_
 
 /* Backward of mobgt_attn_fwd.  o, dout: bf16 [ntok, H*24] contiguous; lse from the forward.
  * dq, dk, dv: bf16 with a common row stride (usually slices of one [ntok, 3*H*24] buffer).
- * dbias f32 [B,H,T,Tp] receives dS = d(scores) = d(bias): overwritten (accumulate = 0) or added to
- * (accumulate = 1; the bias is shared by all encoder layers).  Scores / probabilities are recomputed
- * in-tile and never stored in HBM. */
+ * dbias receives dS = d(scores) = d(bias) [B,H,T,Tp]:
+ *   mode 0: f32, overwritten ;  mode 1: f32, added to (the bias is shared by all encoder layers) ;
+ *   mode 2: bf16, overwritten by ONE TMA store per tile from the MMA operand image — each layer writes its own plane and
+ *           mobgt_bias_bwd sums the planes in fp32 (no read-modify-write traffic; rows / columns past a graph's
+ *           tokens receive unspecified values and are never read).
+ * Scores / probabilities are recomputed in-tile and never stored in HBM. */
 int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, int64_t qkv_row_stride, const void *bias,
                        const void *o, const void *dout, const float *lse, const int32_t *tok_off, int32_t B,
                        int32_t H, int32_t ntok, int32_t T, int32_t Tp, int32_t t_max_host, float scale, void *dq,
-                       void *dk, void *dv, int64_t dqkv_row_stride, float *dbias, int32_t accumulate, void *stream);
+                       void *dk, void *dv, int64_t dqkv_row_stride, void *dbias, int32_t mode, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4 — node-embedding gather / sum and the deterministic segmented scatter-add backward.
@@ -186,6 +191,10 @@ int32_t mobgt_topk_merge(const float *val, const int32_t *idx, const int32_t *cn
  * ------------------------------------------------------------------------------------------ */
 int32_t mobgt_selftest_umma(const void *A, const void *B, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
                             float *out, void *stream);
+
+/* Debug hook: register (NULL: clear) a device buffer of 256 int64; thread 0 of one CTA of mobgt_attn_fwd / mobgt_attn_bwd then
+ * stamps clock64() at its pipeline stages (scripts/timeline.py). */
+int32_t mobgt_debug_set_timeline(void *dev_buf256);
 
 #ifdef __cplusplus
 }

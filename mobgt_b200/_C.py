@@ -30,8 +30,8 @@ SIGNATURES = {
     "mobgt_bias_fwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p,
                        c_p, c_i32, c_p],
     "mobgt_bias_bwd_workspace_bytes": [c_i32, c_i32, c_i32],
-    "mobgt_bias_bwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_i64,
-                       c_p, c_p, c_p, c_p, c_p, c_p],
+    "mobgt_bias_bwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_i32, c_i64, c_p,
+                       c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p],
     "mobgt_attn_fwd": [c_p, c_p, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_p, c_p, c_p],
     "mobgt_attn_bwd": [c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_p, c_p,
                        c_p, c_i64, c_p, c_i32, c_p],
@@ -40,6 +40,7 @@ SIGNATURES = {
     "mobgt_segment_sum": [c_p, c_i32, c_i64, c_i32, c_i32, c_p, c_p, c_i32, c_p, c_i32, c_p, c_i64, c_p],
     "mobgt_head_topk": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "mobgt_topk_merge": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p],
+    "mobgt_debug_set_timeline": [c_p],
     "mobgt_selftest_umma": [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p],
 }
 

@@ -41,6 +41,14 @@ inline int32_t cuda_fail(cudaError_t e, const char *what) {
 
 constexpr int kNumSMs = 148;
 
+// Debug timeline (mobgt_debug_set_timeline): when a device buffer of 256 int64 is registered, thread 0 of ONE CTA of the
+// attention kernels stamps clock64() at its pipeline stages (scripts/timeline.py prints the deltas).  NULL = off.
+extern long long *g_timeline_dev;
+#define MOBGT_STAMP(tl, slot)                                                                              \
+    do {                                                                                                   \
+        if ((tl) != nullptr && threadIdx.x == 0 && blockIdx.x == gridDim.x / 2 && (slot) < 256) (tl)[(slot)] = clock64(); \
+    } while (0)
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 

@@ -6,6 +6,7 @@
 namespace mobgt {
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
+long long *g_timeline_dev = nullptr;
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...) {
@@ -38,5 +39,11 @@ extern "C" int32_t mobgt_device_check(void) {
 extern "C" int32_t mobgt_launch_count(int64_t *out) {
     if (!out) return MOBGT_ERR_NULL;
     *out = mobgt::g_launches.load(std::memory_order_relaxed);
+    return MOBGT_OK;
+}
+
+// Debug hook: register (or clear, with NULL) a device buffer of 256 int64 for the attention kernels' clock64() timeline.
+extern "C" int32_t mobgt_debug_set_timeline(void *dev_buf256) {
+    mobgt::g_timeline_dev = static_cast<long long *>(dev_buf256);
     return MOBGT_OK;
 }

@@ -224,7 +224,11 @@ __host__ __device__ inline K2BwdPlan k2_bwd_plan(int T, int hops, int num_bins) 
     return p;
 }
 
-__global__ void __launch_bounds__(256, 1) k2_bias_bwd_kernel(const K2Common c, const float *__restrict__ dB, int num_bins,
+// DT = float: one fp32 dBias buffer (nlayers == 1).  DT = bf16: nlayers per-layer dS planes (layer_stride elements apart,
+// written by mobgt_attn_bwd mode 2), summed here in fp32.
+template <typename DT>
+__global__ void __launch_bounds__(256, 1) k2_bias_bwd_kernel(const K2Common c, const DT *__restrict__ dB, int nlayers,
+                                                             int64_t layer_stride, int num_bins,
                                                              const K2BwdPlan pl, float *__restrict__ partial,
                                                              float *__restrict__ dR_overflow) {
     extern __shared__ __align__(16) float sm[];
@@ -249,13 +253,23 @@ __global__ void __launch_bounds__(256, 1) k2_bias_bwd_kernel(const K2Common c, c
         const int n = c.n[g];
         if (a == 0 || a > n) continue;                       // row 0 carries no parameter (model_fqandtoyo.py:1160-1165)
         const int Tg = n + 1;
-        const float *row = dB + ((size_t)g * kH * c.T + a) * c.Tp + h * hs;
+        const DT *row = dB + ((size_t)g * kH * c.T + a) * c.Tp + h * hs;
         const int64_t rowp = c.sq_off[g] + (int64_t)(a - 1) * n - 1;     // pair of cell b lives at rowp + b
         for (int b0 = 0; b0 < Tg; b0 += 16) {
             const int bq = b0 + 4 * p4;
-            float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (bq < Tg) dv = *reinterpret_cast<const float4 *>(row + bq);
-            const float dj[4] = {dv.x, dv.y, dv.z, dv.w};
+            float dj[4] = {0.f, 0.f, 0.f, 0.f};
+            if (bq < Tg) {
+                if constexpr (sizeof(DT) == 4) {
+                    const float4 dv = *reinterpret_cast<const float4 *>(row + bq);
+                    dj[0] = dv.x; dj[1] = dv.y; dj[2] = dv.z; dj[3] = dv.w;
+                } else {
+                    for (int l = 0; l < nlayers; ++l) {
+                        const uint2 dv = *reinterpret_cast<const uint2 *>(row + (size_t)l * layer_stride + bq);
+                        dj[0] += bf16lo(dv.x); dj[1] += __uint_as_float(dv.x & 0xFFFF0000u);
+                        dj[2] += bf16lo(dv.y); dj[3] += __uint_as_float(dv.y & 0xFFFF0000u);
+                    }
+                }
+            }
             // keys of the 4 cells of this lane's p4 group, spread over the 8 head lanes:
             //   every lane h: word h of the walk bytes; lane 0 also rel_pos, lane 1 also poi_pos
             uint32_t wj[4];
@@ -469,7 +483,8 @@ extern "C" int64_t mobgt_bias_bwd_workspace_bytes(int32_t T, int32_t hops, int32
 
 extern "C" int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const int16_t *rel_pos, const int16_t *poi_pos,
                                   const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t H,
-                                  int32_t rel_pos_max, int32_t num_bins, const float *dBias, const float *E, const float *W,
+                                  int32_t rel_pos_max, int32_t num_bins, const void *dBias, int32_t dbias_dtype,
+                                  int32_t n_layers, int64_t layer_stride, const float *E, const float *W,
                                   void *workspace, int64_t workspace_bytes, float *dR, float *dPpos, float *dE, float *dW,
                                   float *dtvd, void *stream) {
     MOBGT_REQUIRE(n && sq_off && rel_pos && poi_pos && edge_in && dBias && E && W && workspace && dR && dPpos && dE && dW && dtvd,
@@ -478,6 +493,8 @@ extern "C" int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const
     MOBGT_REQUIRE(hops >= 4 && hops <= MOBGT_MAX_HOPS && hops % 4 == 0 && num_bins >= 1 && num_bins <= 1024, MOBGT_ERR_BAD_SHAPE,
                   "mobgt_bias_bwd: hops=%d num_bins=%d", hops, num_bins);
     MOBGT_REQUIRE(T >= 2 && Tp >= T && Tp % 8 == 0, MOBGT_ERR_BAD_SHAPE, "mobgt_bias_bwd: T=%d Tp=%d", T, Tp);
+    MOBGT_REQUIRE((dbias_dtype == MOBGT_F32 && n_layers == 1) || (dbias_dtype == MOBGT_BF16 && n_layers >= 1 && n_layers <= 64),
+                  MOBGT_ERR_BAD_DTYPE, "mobgt_bias_bwd: dbias dtype %d with %d layer planes", dbias_dtype, n_layers);
     const K2BwdPlan pl = k2_bwd_plan(T, hops, num_bins);
     MOBGT_REQUIRE(pl.warps >= 1, MOBGT_ERR_UNSUPPORTED, "mobgt_bias_bwd: no shared-memory plan for T=%d bins=%d", T, num_bins);
     const int64_t need = (int64_t)(kNumSMs + 1) * pl.stride * (int64_t)sizeof(float);
@@ -492,8 +509,16 @@ extern "C" int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const
         K2Common c{n, sq_off, rel_pos, poi_pos, edge_in, B, T, Tp, hops, rel_pos_max};
         const int per_warp = pl.nR + 4 * (pl.nP + pl.nA + pl.nN) + kH;
         const size_t smem = (size_t)(pl.nEW + pl.warps * per_warp) * sizeof(float);
-        MOBGT_CUDA_OK(cudaFuncSetAttribute(k2_bias_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k2_bias_bwd_kernel<<<kNumSMs, pl.warps * 32, smem, s>>>(c, dBias, num_bins, pl, partial, dR);
+        if (dbias_dtype == MOBGT_F32) {
+            MOBGT_CUDA_OK(cudaFuncSetAttribute(k2_bias_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k2_bias_bwd_kernel<float><<<kNumSMs, pl.warps * 32, smem, s>>>(c, static_cast<const float *>(dBias), 1, 0, num_bins, pl,
+                                                                          partial, dR);
+        } else {
+            MOBGT_CUDA_OK(cudaFuncSetAttribute(k2_bias_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smem));
+            k2_bias_bwd_kernel<__nv_bfloat16><<<kNumSMs, pl.warps * 32, smem, s>>>(
+                c, static_cast<const __nv_bfloat16 *>(dBias), n_layers, layer_stride, num_bins, pl, partial, dR);
+        }
         MOBGT_LAUNCH_OK("k2_bias_bwd_kernel");
     }
     k2_bias_bwd_reduce_kernel<<<ceil_div(pl.stride, 256), 256, 0, s>>>(partial, nparts, pl.stride, tot);

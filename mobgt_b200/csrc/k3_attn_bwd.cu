@@ -39,12 +39,13 @@ struct AttnBwdParams {
     const float *lse;          // [ntok, H]
     __nv_bfloat16 *dq, *dk, *dv;  // [ntok, *] with row stride dqkv_stride (elements)
     int64_t dqkv_stride;
-    float *dbias;              // [B,H,T,Tp] f32
+    float *dbias;              // [B,H,T,Tp] f32 (modes 0, 1); mode 2 writes bf16 through the tmDS tensor map
     int H, T, Tp;
     float scale;
     int max_boxes;
-    int accumulate;            // 0: overwrite dbias, 1: dbias += dS
+    int accumulate;            // 0: f32 overwrite, 1: f32 dbias += dS, 2: bf16 overwrite (per-layer plane, TMA store)
     int bias_bufs;             // 1 or 2 bias tiles in shared memory
+    long long *timeline;       // debug (mobgt_debug_set_timeline) or NULL
 };
 
 __device__ __forceinline__ float bwd_exp2(float x) {
@@ -67,13 +68,16 @@ __device__ __forceinline__ void red_add_f32x4(float *addr, float a, float b, flo
 __global__ void __launch_bounds__(256, 1)
 k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                   const __grid_constant__ CUtensorMap tmBias, const AttnBwdParams p) {
+                   const __grid_constant__ CUtensorMap tmBias, const __grid_constant__ CUtensorMap tmDS,
+                   const AttnBwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_qdo[2], bar_bias[2], bar_kv, bar_s, bar_mma;
     __shared__ uint32_t tmem_slot;
     __shared__ float sLse[kMaxTiles * kTile], sDelta[kMaxTiles * kTile];
 
+    MOBGT_STAMP(p.timeline, 0);
     const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, t128 = tid & 127;
+    const bool warp0 = warp_index_uniform() == 0;   // the issuing warp (one elected lane issues TMA / MMA)
     const int g = blockIdx.x / p.H, h = blockIdx.x - g * p.H;
     const int t0 = p.tok_off[g];
     const int Tg = p.tok_off[g + 1] - t0;
@@ -104,6 +108,20 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_prefetch_desc(&tmV);
         tma_prefetch_desc(&tmdO);
         tma_prefetch_desc(&tmBias);
+        if (p.accumulate == 2) tma_prefetch_desc(&tmDS);
+        // first loads right away (this thread initialised the barriers): they fly during the lse / delta prologue below
+        const int plane0 = g * p.H + h;
+        mbar_expect_tx(&bar_kv, (uint32_t)(2 * NB * kBoxTxBytes));
+        for (int b = 0; b < NB; ++b) {
+            tma_load_3d(sK + (size_t)b * kBoxBytes, &tmK, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
+            tma_load_3d(sV + (size_t)b * kBoxBytes, &tmV, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
+        }
+        mbar_expect_tx(&bar_qdo[0], 2 * kBoxTxBytes);
+        tma_load_3d(sQ, &tmQ, &bar_qdo[0], 0, t0, h * kAttChunks);
+        tma_load_3d(sdO, &tmdO, &bar_qdo[0], 0, t0, h * kAttChunks);
+        mbar_expect_tx(&bar_bias[0], kBiasTileBytes);
+        tma_load_3d(sBias, &tmBias, &bar_bias[0], 0, 0, plane0);
+        tma_load_3d(sBias + kTile * 128, &tmBias, &bar_bias[0], 64, 0, plane0);
     }
     {   // zero the K-padding chunk (d = 24..31) of every operand box: 128 rows x 16 B each
         const uint4 z = make_uint4(0, 0, 0, 0);
@@ -140,6 +158,7 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    MOBGT_STAMP(p.timeline, 1);
     const uint32_t tmem = tmem_slot;
     const uint32_t tS = tmem, tdP = tmem + 128, tdK = tmem + 256, tdV = tmem + 288, tdQ = tmem + 320;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
@@ -159,14 +178,30 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_load_3d(dst, &tmBias, &bar_bias[b], j * kTile, i * kTile, plane);
         tma_load_3d(dst + kTile * 128, &tmBias, &bar_bias[b], j * kTile + 64, i * kTile, plane);
     };
-    if (tid == 0) {
-        mbar_expect_tx(&bar_kv, (uint32_t)(2 * NB * kBoxTxBytes));
-        for (int b = 0; b < NB; ++b) {
-            tma_load_3d(sK + (size_t)b * kBoxBytes, &tmK, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
-            tma_load_3d(sV + (size_t)b * kBoxBytes, &tmV, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
-        }
-        load_qdo(0);
-        load_bias(0);
+    // S = Q_i K_j^T and dP = dO_i V_j^T of flattened iteration t into TMEM (thread 0 only)
+    auto issue_sdp = [&](int t) {
+        const int j = t / NB, b = t & 1;
+        mbar_wait(&bar_qdo[b], (t >> 1) & 1);
+        tc_fence_after();
+        const int nbj = round_up(min(kTile, Tg - j * kTile), 16);
+        const uint32_t idesc = make_idesc_bf16(kTile, nbj, 0, 0);
+        const uint32_t aq = smem_u32(sQ + b * kBoxBytes), ado = smem_u32(sdO + b * kBoxBytes);
+        const uint32_t bk = smem_u32(sK + (size_t)j * kBoxBytes), bv = smem_u32(sV + (size_t)j * kBoxBytes);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+            umma_bf16(tS, make_smem_desc(aq + ks * 2 * kTile * 16, kTile * 16, 128),
+                      make_smem_desc(bk + ks * 2 * kTile * 16, kTile * 16, 128), idesc, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+            umma_bf16(tdP, make_smem_desc(ado + ks * 2 * kTile * 16, kTile * 16, 128),
+                      make_smem_desc(bv + ks * 2 * kTile * 16, kTile * 16, 128), idesc, ks > 0);
+        umma_commit(&bar_s);
+    };
+    if (warp0 && elect_one()) {
+        mbar_wait(&bar_kv, 0);
+        MOBGT_STAMP(p.timeline, 2);
+        issue_sdp(0);
+        MOBGT_STAMP(p.timeline, 3);
     }
     __syncwarp();
     uint32_t ph_s = 0, ph_mma = 0;
@@ -189,44 +224,41 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 ph_mma ^= 1;
                 tc_fence_after();
             }
-            if (tid == 0) {
+            MOBGT_STAMP(p.timeline, 8 + 8 * t + 0);   // after bar_mma wait
+            if (warp0 && elect_one()) {
                 if (t + 1 < NT) {
                     load_qdo(t + 1);
                     if (nbias == 2) load_bias(t + 1);
                 }
-                mbar_wait(&bar_qdo[buf], (t >> 1) & 1);
-                if (t == 0) mbar_wait(&bar_kv, 0);
-                tc_fence_after();
-                const uint32_t idesc = make_idesc_bf16(kTile, nb, 0, 0);
-                const uint32_t aq = smem_u32(sQ + buf * kBoxBytes), ado = smem_u32(sdO + buf * kBoxBytes);
-                const uint32_t bk = smem_u32(sK + (size_t)j * kBoxBytes), bv = smem_u32(sV + (size_t)j * kBoxBytes);
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks)
-                    umma_bf16(tS, make_smem_desc(aq + ks * 2 * kTile * 16, kTile * 16, 128),
-                              make_smem_desc(bk + ks * 2 * kTile * 16, kTile * 16, 128), idesc, ks > 0);
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks)
-                    umma_bf16(tdP, make_smem_desc(ado + ks * 2 * kTile * 16, kTile * 16, 128),
-                              make_smem_desc(bv + ks * 2 * kTile * 16, kTile * 16, 128), idesc, ks > 0);
-                umma_commit(&bar_s);
             }
             __syncwarp();
             mbar_wait(&bar_s, ph_s);
             ph_s ^= 1;
+            MOBGT_STAMP(p.timeline, 8 + 8 * t + 1);   // S / dP ready
             const int bb = (nbias == 2) ? buf : 0;
             mbar_wait(&bar_bias[bb], (nbias == 2) ? ((t >> 1) & 1) : (t & 1));
             tc_fence_after();
+            MOBGT_STAMP(p.timeline, 8 + 8 * t + 2);   // bias tile ready
 
             if (warp_live) {
                 const uint8_t *sB = sBias + (size_t)bb * kBiasTileBytes;
                 const float lse2 = sLse[row];
                 const float delta = sDelta[row];
                 float *db_row = p.dbias + ((size_t)plane * p.T + row) * p.Tp + j * kTile;
-                for (int c0 = wg * 16; c0 < nb; c0 += 32) {
-                    uint32_t sv[16], dpv[16];
-                    tmem_ld16(tS + lane_off + c0, sv);
-                    tmem_ld16(tdP + lane_off + c0, dpv);
-                    tmem_ld_wait();
+                uint32_t svv[4][16], dpvv[4][16];
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc)     // every TMEM load of this thread's columns in flight before the one wait
+                    if (wg * 16 + cc * 32 < nb) {
+                        tmem_ld16(tS + lane_off + wg * 16 + cc * 32, svv[cc]);
+                        tmem_ld16(tdP + lane_off + wg * 16 + cc * 32, dpvv[cc]);
+                    }
+                tmem_ld_wait();
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c0 = wg * 16 + cc * 32;
+                    if (c0 >= nb) continue;
+                    const uint32_t (&sv)[16] = svv[cc];
+                    const uint32_t (&dpv)[16] = dpvv[cc];
 #pragma unroll
                     for (int q8 = 0; q8 < 2; ++q8) {
                         const int c8 = (c0 >> 3) + q8;
@@ -248,7 +280,7 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                             }
                             pk.x = pack_bf16(pv[0], pv[1]); pk.y = pack_bf16(pv[2], pv[3]);
                             pk.z = pack_bf16(pv[4], pv[5]); pk.w = pack_bf16(pv[6], pv[7]);
-                            if (row_ok) {   // d(bias) = dS, fp32, this thread's row
+                            if (row_ok && p.accumulate != 2) {   // d(bias) = dS, fp32, this thread's row
                                 if (p.accumulate) {
                                     red_add_f32x4(db_row + colb, dsv[0], dsv[1], dsv[2], dsv[3]);
                                     red_add_f32x4(db_row + colb + 4, dsv[4], dsv[5], dsv[6], dsv[7]);
@@ -270,7 +302,7 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                             }
                             pk.x = pack_bf16(pv[0], pv[1]); pk.y = pack_bf16(pv[2], pv[3]);
                             pk.z = pack_bf16(pv[4], pv[5]); pk.w = pack_bf16(pv[6], pv[7]);
-                            if (row_ok) {
+                            if (row_ok && p.accumulate != 2) {
 #pragma unroll
                                 for (int e = 0; e < 8; ++e)
                                     if (colb + e < kv_valid) {
@@ -286,12 +318,18 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     }
                 }
             }
+            MOBGT_STAMP(p.timeline, 8 + 8 * t + 3);   // math done (thread 0)
             fence_proxy_async_smem();
             tc_fence_before();
             __syncthreads();
-            if (tid == 0) {
+            MOBGT_STAMP(p.timeline, 8 + 8 * t + 4);   // barrier passed
+            if (warp0 && elect_one()) {
                 tc_fence_after();
                 if (nbias == 1 && t + 1 < NT) load_bias(t + 1);   // single bias buffer: free only now
+                if (p.accumulate == 2) {   // this layer's dS plane (bf16): one TMA store straight from the MMA operand image
+                    tma_store_4d(&tmDS, sdS, 0, i * kTile, j * (kTile / 8), plane);
+                    tma_store_commit();
+                }
                 const uint32_t aP = smem_u32(sP), aS = smem_u32(sdS);
                 const uint32_t bQ = smem_u32(sQ + buf * kBoxBytes), bdO = smem_u32(sdO + buf * kBoxBytes);
                 const uint32_t bK = smem_u32(sK + (size_t)j * kBoxBytes);
@@ -307,6 +345,10 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     umma_bf16(tdQ + 32 * i, make_smem_desc(aS + ks * 2 * kTile * 16, kTile * 16, 128),
                               make_smem_desc(bK + ks * 256, 128, kTile * 16), id_q, (j > 0 || ks > 0));
                 umma_commit(&bar_mma);
+                // S / dP of the next iteration right behind: every thread has finished reading this one's from TMEM
+                MOBGT_STAMP(p.timeline, 8 + 8 * t + 5);   // dV/dK/dQ issued
+                if (t + 1 < NT) issue_sdp(t + 1);
+                MOBGT_STAMP(p.timeline, 8 + 8 * t + 6);   // next S/dP issued (includes the Q/dO TMA wait)
             }
             __syncwarp();
             mma_pending = true;
@@ -316,6 +358,7 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         ph_mma ^= 1;
         tc_fence_after();
         mma_pending = false;   // the wait above already covered the last iteration's MMAs
+        MOBGT_STAMP(p.timeline, 8 + 8 * (j * NB + NB - 1) + 7);   // block's dK/dV complete
         {
             const int krow = j * kTile + t128;
             if (j * kTile + (warp & 3) * 32 < Tg) {
@@ -357,9 +400,11 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
         }
     }
+    if (warp0 && p.accumulate == 2) tma_store_wait_all();   // whichever lane of warp 0 was the elected issuer
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem);
+    MOBGT_STAMP(p.timeline, 4);
 }
 
 }  // namespace mobgt
@@ -372,7 +417,7 @@ using namespace mobgt;
 extern "C" int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, int64_t qkv_row_stride, const void *bias,
                                   const void *o, const void *dout, const float *lse, const int32_t *tok_off, int32_t B,
                                   int32_t H, int32_t ntok, int32_t T, int32_t Tp, int32_t t_max_host, float scale, void *dq,
-                                  void *dk, void *dv, int64_t dqkv_row_stride, float *dbias, int32_t accumulate, void *stream) {
+                                  void *dk, void *dv, int64_t dqkv_row_stride, void *dbias, int32_t accumulate, void *stream) {
     MOBGT_REQUIRE(q && k && v && bias && o && dout && lse && tok_off && dq && dk && dv && dbias, MOBGT_ERR_NULL,
                   "mobgt_attn_bwd: null pointer");
     MOBGT_REQUIRE(qkv_row_stride % 8 == 0 && dqkv_row_stride % 8 == 0 && Tp % 8 == 0 && Tp >= T, MOBGT_ERR_BAD_SHAPE,
@@ -397,6 +442,14 @@ extern "C" int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, i
         int32_t rc = encode_tmap_bf16(&tmB, bias, 3, dims, str, box, 1);
         if (rc) return rc;
     }
+    CUtensorMap tmDS = tmB;   // only used in mode 2
+    if (accumulate == 2) {    // dbias is a bf16 [B,H,T,Tp] plane of this layer, written in the [chunk][row][8] box order
+        uint64_t dims[4] = {8, (uint64_t)T, (uint64_t)Tp / 8, (uint64_t)B * H};
+        uint64_t str[3] = {(uint64_t)Tp * 2, 16, (uint64_t)T * Tp * 2};
+        uint32_t box[4] = {8, kTile, kTile / 8, 1};
+        int32_t rc = encode_tmap_bf16(&tmDS, dbias, 4, dims, str, box, 0);
+        if (rc) return rc;
+    }
     const int max_boxes = ceil_div(t_max_host, kTile);
     const size_t smem_base = 2 * kPBytes + 4 * kBoxBytes + (size_t)2 * max_boxes * kBoxBytes + 1024;
     const int bias_bufs = (smem_base + 2 * kBiasTileBytes <= 220 * 1024) ? 2 : 1;
@@ -410,15 +463,16 @@ extern "C" int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, i
                     static_cast<__nv_bfloat16 *>(dk),
                     static_cast<__nv_bfloat16 *>(dv),
                     dqkv_row_stride,
-                    dbias,
+                    static_cast<float *>(dbias),
                     H,
                     T,
                     Tp,
                     scale,
                     max_boxes,
                     accumulate,
-                    bias_bufs};
-    k3_attn_bwd_kernel<<<B * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmdO, tmB, p);
+                    bias_bufs,
+                    g_timeline_dev};
+    k3_attn_bwd_kernel<<<B * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmdO, tmB, tmDS, p);
     MOBGT_LAUNCH_OK("k3_attn_bwd_kernel");
     return MOBGT_OK;
 }

@@ -35,6 +35,7 @@ struct AttnFwdParams {
     int H;
     float scale;
     int max_boxes;           // ceil(Tmax / 128): K/V boxes provisioned in shared memory
+    long long *timeline;     // debug (mobgt_debug_set_timeline) or NULL
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -58,7 +59,9 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __shared__ uint32_t tmem_slot;
     __shared__ float sMax[2][kTile];
 
+    MOBGT_STAMP(p.timeline, 0);
     const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, t128 = tid & 127;
+    const bool warp0 = warp_index_uniform() == 0;   // the issuing warp (one elected lane issues TMA / MMA)
     const int g = blockIdx.x / p.H, h = blockIdx.x - g * p.H;
     const int t0 = p.tok_off[g];
     const int Tg = p.tok_off[g + 1] - t0;
@@ -81,6 +84,17 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_prefetch_desc(&tmK);
         tma_prefetch_desc(&tmV);
         tma_prefetch_desc(&tmBias);
+        // first loads right away (this thread initialised the barriers)
+        mbar_expect_tx(&bar_kv, (uint32_t)(2 * NB * kBoxTxBytes));
+        for (int b = 0; b < NB; ++b) {
+            tma_load_3d(sK + (size_t)b * kBoxBytes, &tmK, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
+            tma_load_3d(sV + (size_t)b * kBoxBytes, &tmV, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
+        }
+        mbar_expect_tx(&bar_q, kBoxTxBytes);
+        tma_load_3d(sQ, &tmQ, &bar_q, 0, t0, h * kAttChunks);
+        mbar_expect_tx(&bar_bias, kBiasTileBytes);
+        tma_load_3d(sBias, &tmBias, &bar_bias, 0, 0, g * p.H + h);
+        tma_load_3d(sBias + kTile * 128, &tmBias, &bar_bias, 64, 0, g * p.H + h);
     }
     // zero the K-padding chunk (d = 24..31) of Q and of every K / V box: 128 rows x 16 B each
     {
@@ -94,6 +108,7 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    MOBGT_STAMP(p.timeline, 1);
     const uint32_t tmem = tmem_slot;
     const uint32_t tS = tmem, tO = tmem + 128;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
@@ -108,17 +123,27 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_expect_tx(&bar_q, kBoxTxBytes);
         tma_load_3d(sQ, &tmQ, &bar_q, 0, t0 + i * kTile, h * kAttChunks);
     };
-    if (tid == 0) {
-        mbar_expect_tx(&bar_kv, (uint32_t)(2 * NB * kBoxTxBytes));
-        for (int b = 0; b < NB; ++b) {
-            tma_load_3d(sK + (size_t)b * kBoxBytes, &tmK, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
-            tma_load_3d(sV + (size_t)b * kBoxBytes, &tmV, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
-        }
-        load_q(0);
-        load_bias(0, 0);
+    uint32_t ph_bias = 0, ph_s = 0, ph_o = 0;
+    // S = Q_i K_j^T into TMEM (thread 0 only); new_q: first block of a query tile -> wait for its Q box
+    auto issue_s = [&](int j, int new_q_tile) {   // new_q_tile >= 0: first block of that query tile -> wait for its Q box
+        if (new_q_tile >= 0) mbar_wait(&bar_q, new_q_tile & 1);
+        const int nbj = round_up(min(kTile, Tg - j * kTile), 16);
+        const uint32_t idesc = make_idesc_bf16(kTile, nbj, 0, 0);
+        const uint32_t aq = smem_u32(sQ), bk = smem_u32(sK + (size_t)j * kBoxBytes);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+            umma_bf16(tS, make_smem_desc(aq + ks * 2 * kTile * 16, kTile * 16, 128),
+                      make_smem_desc(bk + ks * 2 * kTile * 16, kTile * 16, 128), idesc, ks > 0);
+        umma_commit(&bar_s);
+    };
+    if (warp0 && elect_one()) {
+        mbar_wait(&bar_kv, 0);
+        tc_fence_after();
+        MOBGT_STAMP(p.timeline, 2);
+        issue_s(0, 0);
+        MOBGT_STAMP(p.timeline, 3);
     }
     __syncwarp();
-    uint32_t ph_q = 0, ph_bias = 0, ph_s = 0, ph_o = 0;
     const float sl2 = p.scale * 1.4426950408889634f;  // scale * log2(e)
     constexpr float kL2e = 1.4426950408889634f;
 
@@ -130,40 +155,28 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int j = 0; j < NB; ++j) {
             const int kv_valid = min(kTile, Tg - j * kTile);    // valid key columns in this block
             const int nb = round_up(kv_valid, 16);              // MMA N / K extent
-            if (tid == 0) {
-                if (j == 0) {
-                    mbar_wait(&bar_q, ph_q);
-                    ph_q ^= 1;
-                    if (i == 0) mbar_wait(&bar_kv, 0);
-                }
-                tc_fence_after();
-                const uint32_t idesc = make_idesc_bf16(kTile, nb, 0, 0);
-                const uint32_t aq = smem_u32(sQ), bk = smem_u32(sK + (size_t)j * kBoxBytes);
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks)
-                    umma_bf16(tS, make_smem_desc(aq + ks * 2 * kTile * 16, kTile * 16, 128),
-                              make_smem_desc(bk + ks * 2 * kTile * 16, kTile * 16, 128), idesc, ks > 0);
-                umma_commit(&bar_s);
-            }
             __syncwarp();
             mbar_wait(&bar_s, ph_s);
             ph_s ^= 1;
-            if (tid == 0 && j + 1 == NB && i + 1 < NB) load_q(i + 1);   // the last S MMA of this tile has consumed Q
+            MOBGT_STAMP(p.timeline, 8 + 8 * (i * NB + j) + 0);   // S ready
+            if (j + 1 == NB && i + 1 < NB && warp0 && elect_one()) load_q(i + 1);   // the last S MMA of this tile has consumed Q
             mbar_wait(&bar_bias, ph_bias);
             ph_bias ^= 1;
             tc_fence_after();
+            MOBGT_STAMP(p.timeline, 8 + 8 * (i * NB + j) + 1);   // bias tile ready
 
             // ---- pass 1: s = scale * S + bias (log2 units) for this thread's columns -> registers; row max
-            float sreg[64];
+            uint32_t sv[4][16];           // raw S, then (in place) the biased scores: the only per-tile register array
             float m_blk = -INFINITY;
             if (warp_live) {
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc)
+                    if (wg * 16 + cc * 32 < nb) tmem_ld16(tS + lane_off + wg * 16 + cc * 32, sv[cc]);   // all loads in flight
+                tmem_ld_wait();
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) {
                     const int c0 = wg * 16 + cc * 32;
                     if (c0 < nb) {
-                        uint32_t sv[16];
-                        tmem_ld16(tS + lane_off + c0, sv);
-                        tmem_ld_wait();
 #pragma unroll
                         for (int q8 = 0; q8 < 2; ++q8) {
                             const int c8 = (c0 >> 3) + q8;             // 8-column chunk index inside the 128-wide tile
@@ -175,21 +188,30 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
                                 const float bias = __uint_as_float((e & 1) ? (bw[e >> 1] & 0xFFFF0000u) : (bw[e >> 1] << 16));
-                                float s = fmaf(__uint_as_float(sv[q8 * 8 + e]), sl2, bias * kL2e);
+                                float s = fmaf(__uint_as_float(sv[cc][q8 * 8 + e]), sl2, bias * kL2e);
                                 if (!full && c8 * 8 + e >= kv_valid) s = -INFINITY;   // padding key columns (collator.py:57-64)
-                                sreg[cc * 16 + q8 * 8 + e] = s;
+                                sv[cc][q8 * 8 + e] = __float_as_uint(s);
                                 m_blk = fmaxf(m_blk, s);
                             }
                         }
                     }
                 }
             }
+            MOBGT_STAMP(p.timeline, 8 + 8 * (i * NB + j) + 2);   // pass 1 done (thread 0)
             sMax[wg][t128] = m_blk;
+            tc_fence_before();            // this thread's tcgen05.ld of S precede the next S MMA issued after the barrier
             __syncthreads();              // both halves of every row max are visible; nobody reads the bias tile any more
-            if (tid == 0) {
-                if (j + 1 < NB) load_bias(i, j + 1);
-                else if (i + 1 < NB) load_bias(i + 1, 0);
+            if (warp0 && elect_one()) {   // every thread holds its scores in registers: TMEM S and the bias tile are free again
+                tc_fence_after();
+                if (j + 1 < NB) {
+                    load_bias(i, j + 1);
+                    issue_s(j + 1, -1);
+                } else if (i + 1 < NB) {
+                    load_bias(i + 1, 0);
+                    issue_s(0, i + 1);
+                }
             }
+            MOBGT_STAMP(p.timeline, 8 + 8 * (i * NB + j) + 3);   // barrier A passed, next loads / S MMA issued
             m_blk = fmaxf(m_blk, sMax[wg ^ 1][t128]);
             const float m_new = fmaxf(m_run, m_blk);
             const float m_use = (m_new == -INFINITY) ? 0.f : m_new;   // rows past the graph: keep the arithmetic finite
@@ -212,7 +234,7 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                             float pv[8];
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
-                                pv[e] = fast_exp2(sreg[cc * 16 + q8 * 8 + e] - m_use);
+                                pv[e] = fast_exp2(__uint_as_float(sv[cc][q8 * 8 + e]) - m_use);
                                 l_blk += pv[e];     // row sum in fp32 (P is rounded to bf16 only for the tensor-core operand)
                             }
                             uint4 pk;
@@ -236,10 +258,12 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 tmem_st16(tO + lane_off + wg * 16, ov);
                 tmem_st_wait();
             }
+            MOBGT_STAMP(p.timeline, 8 + 8 * (i * NB + j) + 4);   // pass 2 done (thread 0)
             fence_proxy_async_smem();
             tc_fence_before();
             __syncthreads();
-            if (tid == 0) {
+            MOBGT_STAMP(p.timeline, 8 + 8 * (i * NB + j) + 5);   // barrier B passed
+            if (warp0 && elect_one()) {
                 tc_fence_after();
                 const uint32_t idesc = make_idesc_bf16(kTile, 32, 0, 1);
                 const uint32_t ap = smem_u32(sP), bv = smem_u32(sV + (size_t)j * kBoxBytes);
@@ -278,12 +302,14 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 }
             }
         }
+        MOBGT_STAMP(p.timeline, 8 + 8 * (i * NB + NB - 1) + 7);   // tile epilogue done
         tc_fence_before();
         __syncthreads();   // every thread is done with TMEM S/O before the next tile's MMAs
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<256>(tmem);
+    MOBGT_STAMP(p.timeline, 4);
 }
 
 }  // namespace mobgt
@@ -322,7 +348,7 @@ extern "C" int32_t mobgt_attn_fwd(const void *q, const void *k, const void *v, i
     const int max_boxes = ceil_div(t_max_host, kTile);
     const size_t smem = (size_t)kBiasTileBytes + kPBytes + kBoxBytes + (size_t)2 * max_boxes * kBoxBytes + 1024;
     MOBGT_CUDA_OK(cudaFuncSetAttribute(k3_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AttnFwdParams p{tok_off, static_cast<__nv_bfloat16 *>(out), lse, H, scale, max_boxes};
+    AttnFwdParams p{tok_off, static_cast<__nv_bfloat16 *>(out), lse, H, scale, max_boxes, g_timeline_dev};
     k3_attn_fwd_kernel<<<B * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmB, p);
     MOBGT_LAUNCH_OK("k3_attn_fwd_kernel");
     return MOBGT_OK;

@@ -138,11 +138,11 @@ class MultiHeadAttention(nn.Module):
         self.attention_dropout_rate = attention_dropout_rate
         self.output_layer = nn.Linear(num_heads * self.att_size, hidden_size)
 
-    def forward(self, x, bias_slot):
+    def forward(self, x, bias_slot, layer=0):
         w = torch.cat([self.linear_q.weight, self.linear_k.weight, self.linear_v.weight], 0)
         b = torch.cat([self.linear_q.bias, self.linear_k.bias, self.linear_v.bias], 0)
         qkv = F.linear(x.to(torch.bfloat16), w.to(torch.bfloat16), b.to(torch.bfloat16))
-        a = ops.BiasedAttention.apply(qkv, bias_slot)
+        a = ops.BiasedAttention.apply(qkv, bias_slot, layer)
         return F.linear(a, self.output_layer.weight.to(torch.bfloat16), self.output_layer.bias.to(torch.bfloat16))
 
 
@@ -159,9 +159,9 @@ class EncoderLayer(nn.Module):
         self.ffn = FeedForwardNetwork(hidden_size, ffn_size, dropout_rate)
         self.ffn_dropout = nn.Dropout(dropout_rate)
 
-    def forward(self, x, bias_slot):
+    def forward(self, x, bias_slot, layer=0):
         # residual stream and LayerNorms in fp32, GEMMs / attention in bf16 (the reference's --precision 16 AMP split)
-        y = self.self_attention(x, bias_slot)
+        y = self.self_attention(x, bias_slot, layer)
         x = x + self.self_attention_dropout(y).float()
         y = self.ffn_norm1(x)
         f = self.ffn
@@ -282,10 +282,10 @@ class Graphormer(nn.Module):
                             "mobgt_b200.collator.collator_* or Batch1-from-dense")
         bias = self.attn_bias(b)
         tok = self.node_tokens(b)
-        slot = ops.BiasSlot(bias, b)
+        slot = ops.BiasSlot(bias, b, len(self.layers))
         x = ops.BiasGradSink.apply(self.input_dropout(tok).float(), bias, slot)                          # :1347
-        for layer in self.layers:                                                                        # :1348-1352
-            x = layer(x, slot)
+        for li, layer in enumerate(self.layers):                                                         # :1348-1352
+            x = layer(x, slot, li)
         z0 = x.index_select(0, b.tok_off[:-1].long()).float()                                            # output[:, 0, :]
         user_embedding = self.user_embed_model(b.user.view(-1) - 1)                                      # :1239
         z = self.embed_fuse_model3(z0, user_embedding)                                                   # :1356 (token 0 only)

@@ -40,7 +40,13 @@ def bias_fwd_raw(batch, R, Ppos, E, W, tvd, out_dtype=torch.bfloat16, T=None, Tp
 
 
 def bias_bwd_raw(batch, dbias, E, W, num_bins):
-    B, H, T, Tp = dbias.shape
+    """dbias: f32 [B,H,T,Tp] (sum over layers) or bf16 [L,B,H,T,Tp] (per-layer dS planes, summed in the kernel)."""
+    if dbias.dtype == torch.bfloat16:
+        L, B, H, T, Tp = dbias.shape
+        dt, stride = BF16, dbias.stride(0)
+    else:
+        B, H, T, Tp = dbias.shape
+        L, dt, stride = 1, F32, 0
     dev = dbias.device
     hops = batch.hops
     ws_bytes = int(_C.lib().mobgt_bias_bwd_workspace_bytes(T, hops, num_bins))
@@ -51,16 +57,17 @@ def bias_bwd_raw(batch, dbias, E, W, num_bins):
     dP = torch.empty(num_bins, H, dtype=torch.float32, device=dev)
     dE = torch.empty(128, H, dtype=torch.float32, device=dev)
     dW = torch.zeros(W.numel(), dtype=torch.float32, device=dev)   # rows >= hops*H*H of edge_dis_encoder get no gradient
-    dt = torch.empty(H, dtype=torch.float32, device=dev)
+    dtv = torch.empty(H, dtype=torch.float32, device=dev)
     _C.call("mobgt_bias_bwd", _C.ptr(batch.n), _C.ptr(batch.sq_off), _C.ptr(batch.rel_pos16), _C.ptr(batch.poi_pos16),
-            _C.ptr(batch.edge_in8), B, T, Tp, hops, H, batch.rel_pos_max, num_bins, _C.ptr(dbias), _C.ptr(E), _C.ptr(W),
-            _C.ptr(ws), ws_bytes, _C.ptr(dR), _C.ptr(dP), _C.ptr(dE), _C.ptr(dW), _C.ptr(dt), _C.stream_ptr())
-    return dR, dP, dE, dW.view_as(W), dt
+            _C.ptr(batch.edge_in8), B, T, Tp, hops, H, batch.rel_pos_max, num_bins, _C.ptr(dbias), dt, L, stride, _C.ptr(E),
+            _C.ptr(W), _C.ptr(ws), ws_bytes, _C.ptr(dR), _C.ptr(dP), _C.ptr(dE), _C.ptr(dW), _C.ptr(dtv), _C.stream_ptr())
+    return dR, dP, dE, dW.view_as(W), dtv
 
 
 class AttnBias(torch.autograd.Function):
     """graph_attn_bias = f(rel_pos, poi_pos, edge_input; 5 tables)   (model_fqandtoyo.py:1143-1216).
-    The gradient arriving here is the fp32 dBias buffer the attention backward of all layers accumulated into."""
+    In training the gradient is the stack of per-layer bf16 dS planes written by the attention backward kernels
+    (handed over by BiasGradSink through the batch object); a plain f32 gradient tensor works too."""
 
     @staticmethod
     def forward(ctx, batch, R, Ppos, E, W, tvd, out_dtype):
@@ -72,7 +79,9 @@ class AttnBias(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dbias):
         E, W = ctx.saved_tensors
-        dR, dP, dE, dW, dt = bias_bwd_raw(ctx.batch, dbias.float().contiguous(), E, W.view(-1), ctx.num_bins)
+        planes = ctx.batch.__dict__.pop("_ds_planes", None)     # bf16 [L,B,H,T,Tp] left by BiasGradSink (training path)
+        db = planes if planes is not None else dbias.float().contiguous()
+        dR, dP, dE, dW, dt = bias_bwd_raw(ctx.batch, db, E, W.view(-1), ctx.num_bins)
         dR[0].zero_()          # padding_idx rows (never indexed by a packed pair anyway)
         dP[0].zero_()
         return None, dR, dP, dE, dW.view(-1, 1), dt.view(1, -1), None
@@ -95,11 +104,13 @@ def attn_fwd_raw(qkv, bias, batch, scale=None):
 
 
 def attn_bwd_raw(qkv, bias, out, dout, lse, batch, dbias, accumulate, scale=None):
-    """-> dqkv bf16 [ntok, 3*H*24]; dbias (f32 [B,H,T,Tp]) is written / accumulated in place."""
+    """-> dqkv bf16 [ntok, 3*H*24]; dbias [B,H,T,Tp] is written in place: f32 overwritten (accumulate=0) / added to
+    (accumulate=1), or bf16 overwritten (accumulate=2: this layer's own dS plane, TMA-stored)."""
     ntok = qkv.shape[0]
     B, H, T, Tp = bias.shape
     D = H * HEAD_DIM
-    assert dout.is_contiguous() and out.is_contiguous() and dbias.dtype == torch.float32 and dbias.shape == bias.shape
+    assert dout.is_contiguous() and out.is_contiguous() and dbias.shape == bias.shape and dbias.is_contiguous()
+    assert dbias.dtype == (torch.bfloat16 if accumulate == 2 else torch.float32)
     dqkv = torch.empty_like(qkv)
     scale = float(HEAD_DIM ** -0.5) if scale is None else float(scale)
     base, dbase = qkv.data_ptr(), dqkv.data_ptr()
@@ -112,33 +123,32 @@ def attn_bwd_raw(qkv, bias, out, dout, lse, batch, dbias, accumulate, scale=None
 class BiasedAttention(torch.autograd.Function):
     """softmax(scale * q k^T + bias) v per packed graph and head (model_fqandtoyo.py:1693-1706).
 
-    `bias_slot` carries the bias tensor and the shared fp32 dBias accumulation buffer: the bias is one tensor
-    used by every encoder layer, so each layer's backward adds its dS into bias_slot.dbias in place (first
-    writer overwrites) and the gradient w.r.t. `bias` is delivered once, by BiasGradSink below."""
+    The bias is ONE tensor used by every encoder layer.  Each layer's backward stores its own dS = d(bias) plane
+    (bf16, written by a TMA store from the tile the dK / dQ MMAs consume) into bias_slot.planes[layer]; the gradient
+    w.r.t. `bias` is delivered once, by BiasGradSink below, and the planes are summed in fp32 by mobgt_bias_bwd."""
 
     @staticmethod
-    def forward(ctx, qkv, bias_slot):
+    def forward(ctx, qkv, bias_slot, layer):
         out, lse = attn_fwd_raw(qkv, bias_slot.bias, bias_slot.batch)
         ctx.save_for_backward(qkv, out, lse)
-        ctx.slot = bias_slot
+        ctx.slot, ctx.layer = bias_slot, layer
         return out
 
     @staticmethod
     def backward(ctx, dout):
         qkv, out, lse = ctx.saved_tensors
         slot = ctx.slot
-        if slot.dbias is None:
-            slot.dbias = torch.empty(slot.bias.shape, dtype=torch.float32, device=qkv.device)
-            acc = 0
-        else:
-            acc = 1
-        dqkv = attn_bwd_raw(qkv, slot.bias, out, dout.contiguous(), lse, slot.batch, slot.dbias, acc)
-        return dqkv, None
+        if slot.planes is None:
+            slot.planes = torch.empty((slot.n_layers,) + tuple(slot.bias.shape), dtype=torch.bfloat16, device=qkv.device)
+            slot.written = set()
+        dqkv = attn_bwd_raw(qkv, slot.bias, out, dout.contiguous(), lse, slot.batch, slot.planes[ctx.layer], 2)
+        slot.written.add(ctx.layer)
+        return dqkv, None, None
 
 
 class BiasSlot:
-    def __init__(self, bias, batch):
-        self.bias, self.batch, self.dbias = bias, batch, None
+    def __init__(self, bias, batch, n_layers):
+        self.bias, self.batch, self.n_layers, self.planes, self.written = bias, batch, n_layers, None, set()
 
 
 class BiasGradSink(torch.autograd.Function):
@@ -153,8 +163,14 @@ class BiasGradSink(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dtok):
         slot = ctx.slot
-        db, slot.dbias = slot.dbias, None
-        return dtok, db, None
+        planes, slot.planes = slot.planes, None
+        if planes is None:
+            return dtok, None, None
+        for l in range(slot.n_layers):          # a layer whose backward never ran contributes nothing
+            if l not in slot.written:
+                planes[l].zero_()
+        slot.batch.__dict__["_ds_planes"] = planes
+        return dtok, planes[0], None            # a correctly shaped stand-in; AttnBias.backward picks up the whole stack
 
 
 # ----------------------------------------------------------------------------------------------- K4

@@ -111,6 +111,12 @@ def test_bias_bwd_matches_autograd_of_oracle(lib_built):
     close(dE, m.edge_encoder.weight.grad, "dE")
     close(dW.view(-1, 1), m.edge_dis_encoder.weight.grad, "dW")
     close(dt.view(1, -1), m.graph_token_virtual_distance.weight.grad, "dtvd")
+    # per-layer bf16 planes (mobgt_attn_bwd mode 2) summed inside the kernel == the f32 path on the summed planes
+    planes = torch.stack([(dB * c).to(torch.bfloat16) for c in (0.5, 0.25, 1.0)]).cuda()
+    ref5 = ops.bias_bwd_raw(b, planes.float().sum(0).contiguous(), E.cuda().contiguous(), W.view(-1).cuda().contiguous(), Pp.shape[0])
+    got5 = ops.bias_bwd_raw(b, planes, E.cuda().contiguous(), W.view(-1).cuda().contiguous(), Pp.shape[0])
+    for a5, b5 in zip(got5, ref5):
+        assert torch.allclose(a5, b5, rtol=1e-5, atol=1e-5 * (b5.abs().max().item() + 1e-6))
 
 
 def torch_attention(qkv, bias, tok_off, H=8, d=24):
@@ -207,6 +213,8 @@ def test_attention_bwd_matches_torch_autograd(lib_built, cfg, B, cap, nfix):
     dqkv = ops.attn_bwd_raw(qkv.cuda(), bias, out, dout.cuda(), lse, b, dbias, 0)
     dbias2 = dbias.clone()
     ops.attn_bwd_raw(qkv.cuda(), bias, out, dout.cuda(), lse, b, dbias2, 1)      # accumulate: 2x
+    plane = torch.full(bias.shape, float("nan"), dtype=torch.bfloat16, device="cuda")
+    dqkv3 = ops.attn_bwd_raw(qkv.cuda(), bias, out, dout.cuda(), lse, b, plane, 2)
     torch.cuda.synchronize()
     # fp32 autograd reference on the same bf16-rounded inputs
     tok_off = b.tok_off.cpu().numpy()
@@ -225,6 +233,10 @@ def test_attention_bwd_matches_torch_autograd(lib_built, cfg, B, cap, nfix):
         assert torch.isfinite(got).all()
         assert (got - gb).abs().max().item() <= 2e-2 * max(1.0, gb.abs().max().item())
         assert torch.allclose(dbias2[g, :, :Tg, :Tg].cpu(), 2 * got, rtol=1e-6, atol=1e-7)
+        # mode 2 (training path): the same dS, rounded once to bf16, TMA-stored from the MMA operand tile
+        got16 = plane[g, :, :Tg, :Tg].float().cpu()
+        assert torch.equal(got16, got.to(torch.bfloat16).float())
+    assert torch.equal(dqkv3.cpu(), dqkv.cpu())
 
 
 def torch_attention_diff(qkv, bias, tok_off, H=8, d=24):
