@@ -333,8 +333,10 @@ def run_ours(args):
             rep = kernel_report(model, batch, pk)
             top = max(rep, key=lambda k: rep[k]["ms"] * rep[k]["launches_per_step"])
             r = rep[top]
+            tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")      # dram bytes / launch from the committed ncu capture
+            traffic = json.load(open(tp)).get(top) if (os.path.exists(tp) and args.workload == "c2-dense128") else None
             line["roofline"] = {"kernel": top, "bound": "hbm", "achieved": r["gbs"], "peak": pk["hbm"], "unit": "GB/s",
-                                "frac": r["frac_hbm"], "traffic": None, "peak_source": pk["src"],
+                                "frac": r["frac_hbm"], "traffic": traffic, "peak_source": pk["src"],
                                 "share_of_step": r["ms"] * r["launches_per_step"] / (ms / args.steps)}
             line["kernels"] = {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in rep.items()}
         if world_size == 1 and not args.no_cpu_baseline:
