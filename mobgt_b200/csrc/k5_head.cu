@@ -2,13 +2,27 @@
 //
 // Replaces out_proj + the evaluation metrics path, model_fqandtoyo.py:1396/1408/1421 (logits = z W^T + b) followed by
 // get_acc (:48-90: topk(20) on the device, then a numpy loop) and MRR_metric (:122-131: a full descending argsort of every
-// row on the CPU).  Here the [M, V] logits never reach HBM: each CTA keeps a 128-row tile of z resident, streams 128-row
-// tiles of its vocabulary slice through tcgen05.mma (accumulator in TMEM), and the epilogue threads (one per row) keep
-//   * a running sorted top-k list of (value, global index)            -> Acc@k / NDCG@k
-//   * count(s > s_t) and count(s == s_t and idx < t)  (rank of target) -> MRR (ties towards the lower index)
-// Two modes: mode 0 extracts s_t (the target's own logit, from the same MMA arithmetic, only on tiles that contain a target),
-// mode 1 counts and selects.  Vocabulary sharding across GPUs = `vocab_offset` + merging the per-shard lists
-// (mobgt_topk_merge) after an NCCL all-gather; counts are summed.
+// row on the CPU).  The [M, V] logits never reach HBM.
+//
+// mode 1 (k5_head_kernel) — warp-specialised, one CTA per (128-row tile of z, vocabulary split):
+//   warp 0      TMA producer: z tile once (resident, K/64 blocks of [128 rows][128 B]); W tiles stream through a ring of
+//               16 KB stages, one stage = 128 vocabulary rows x 64 K-columns, 2-D boxes with the 128-byte swizzle
+//   warp 1      MMA issuer: tcgen05.mma M=128 N=128 K=16, K/16 steps per tile, accumulators double-buffered in TMEM
+//               (2 x 128 columns); a stage is released by tcgen05.commit, a finished accumulator is published the same way
+//   warp 2      TMEM allocation;  warp 3 idle
+//   warps 4-11  two epilogue warpgroups, one per accumulator buffer (tile t goes to group t & 1).  Thread = row.  Per element:
+//               + bias, one compare for the rank count, a 4-wide max against the running k-th value.  The rank
+//                   rank = #(s > s_t) + #(s == s_t and idx < t)       (ties towards the lower index)
+//               needs ONE compare per element: columns before the target are compared against prev_float(s_t) (>= s_t),
+//               columns after it against s_t; only the tile that holds the target takes a per-element path.
+//               Top-k candidates (rare after the first tiles) are appended to a small per-row buffer and inserted into
+//               the row's sorted list (64-bit keys: order-preserving value bits | ~index) in a lane-aligned drain loop, so
+//               the warp does not serialise 32 rows' insertions one after the other.
+//   Each (row, split, group) emits a sorted top-k list + its partial rank count; mobgt_topk_merge merges them.
+// mode 0 (k5_target_logit_kernel) — s_t, the target's own logit, from the SAME MMA arithmetic: per 128-row tile the W rows
+//   of the rows' targets are gathered into the swizzled B tile, one 128x128 MMA group runs, and s_t is the diagonal.
+// Vocabulary sharding across GPUs = `vocab_offset` + all-reduce MAX of s_t + merging the per-shard lists after an
+// all-gather (parallel.sharded_head_topk); counts are summed.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -20,6 +34,11 @@ using namespace sm100;
 constexpr int kHeadTile = 128;
 constexpr int kHeadMaxK = 320;     // 2*hidden + 64 (model_fqandtoyo.py:1059-1068)
 constexpr int kHeadMaxTop = 32;
+constexpr int kKB = 64;                          // K columns per stage = one 128-byte swizzle row
+constexpr int kBlkBytes = kHeadTile * 128;       // 16 KB: [128 rows][128 B]
+constexpr int kMaxRing = 8;
+constexpr int kCandCap = 8;
+constexpr int kHeadThreads = 384;                // 4 service warps + 2 epilogue warpgroups
 
 struct HeadParams {
     const float *bias;       // [V] or null
@@ -30,142 +49,337 @@ struct HeadParams {
     int32_t *cnt_gt, *cnt_eq;  // [M, nsplit]
     float *logits;           // optional [M, V]
     int M, V, K, k, nsplit, mode;
+    int ring;                // W stages in shared memory
     int64_t vocab_offset;
 };
 
-__global__ void __launch_bounds__(128, 1)
-k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW, const HeadParams p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_a, bar_b, bar_mma;
-    __shared__ uint32_t tmem_slot;
-    __shared__ float sbias[kHeadTile];
-    __shared__ int any_target;
+__device__ __forceinline__ uint32_t f2ord(float v) {
+    const uint32_t u = __float_as_uint(v);
+    return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
+}
+// largest float strictly below x (x finite or +inf); -inf stays -inf:  v >= x  <=>  v > prev_float(x)
+__device__ __forceinline__ float prev_float(float x) {
+    const uint32_t u = __float_as_uint(x);
+    if ((u << 1) == 0u) return __uint_as_float(0x80000001u);   // +-0 -> -denorm_min
+    if (u == 0xFF800000u) return x;
+    return __uint_as_float((u & 0x80000000u) ? u + 1u : u - 1u);
+}
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+__device__ __forceinline__ unsigned long long lds64(uint32_t a) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) {
+    asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+}
+constexpr uint32_t kEnt = kHeadTile * 8;   // byte distance between consecutive entries of one row's list / buffer
+
+struct RowState {
+    uint32_t lk;              // shared-memory address of this row's sorted list (entries kEnt apart)
+    uint32_t cd;              // ... of this row's candidate buffer
+    float thr;                // value of the k-th entry (-inf while the list is not full)
+    int ncand, cnt, k;
+};
+
+// Insert the buffered candidates into the sorted list (everything passed by value: the row state stays in registers).
+// Returns the new threshold.  Lanes that arrive here together run the loop together (lane-aligned insertion).
+__device__ __noinline__ float drain_list(uint32_t lk, uint32_t cd, int ncand, int k) {
+    const uint32_t last = lk + (uint32_t)(k - 1) * kEnt;
+    while (ncand > 0) {
+        --ncand;
+        const unsigned long long key = lds64(cd + (uint32_t)ncand * kEnt);
+        if (key > lds64(last)) {
+            uint32_t pos = last;
+            while (pos > lk) {
+                const unsigned long long up = lds64(pos - kEnt);
+                if (up >= key) break;
+                sts64(pos, up);
+                pos -= kEnt;
+            }
+            sts64(pos, key);
+        }
+    }
+    const unsigned long long kth = lds64(last);
+    return kth ? ord2f((uint32_t)(kth >> 32)) : -INFINITY;
+}
+__device__ __forceinline__ void drain(RowState &s) {
+    s.thr = drain_list(s.lk, s.cd, s.ncand, s.k);
+    s.ncand = 0;
+}
+__device__ __forceinline__ void candidate(RowState &s, float v, long long gi) {
+    if (s.ncand == kCandCap) drain(s);
+    if (v > s.thr) {
+        sts64(s.cd + (uint32_t)s.ncand * kEnt, ((unsigned long long)f2ord(v) << 32) | (uint32_t)(~(uint32_t)gi));
+        ++s.ncand;
+    }
+}
+
+__global__ void __launch_bounds__(kHeadThreads, 1)
+k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW, const HeadParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_a, bar_full[kMaxRing], bar_empty[kMaxRing], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x;
+    const int warp = warp_index_uniform();
+    const int lane = tid & 31;
     const int mt = blockIdx.x, sp = blockIdx.y;
-    const int chunks = p.K / 8;
-    const int tile_bytes = chunks * kHeadTile * 16;
+    const int kblocks = ceil_div(p.K, kKB);
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
-    uint8_t *sB = sA + tile_bytes;
-    float *lval = reinterpret_cast<float *>(sB + tile_bytes);            // [k][128]
-    int32_t *lidx = reinterpret_cast<int32_t *>(lval + p.k * kHeadTile);  // [k][128]
+    uint8_t *sB = sA + (size_t)kblocks * kBlkBytes;
+    unsigned long long *lkey = reinterpret_cast<unsigned long long *>(sB + (size_t)p.ring * kBlkBytes);   // [2][k][128]
+    unsigned long long *cand = lkey + (size_t)2 * p.k * kHeadTile;                                        // [2][cap][128]
 
     const int ntiles = ceil_div(p.V, kHeadTile);
-    const int tps = ceil_div(ntiles, p.nsplit);
+    const int gs = gridDim.y;
+    const int tps = ceil_div(ntiles, gs);
     const int n_begin = sp * tps, n_end = min(ntiles, n_begin + tps);
+    const int T = max(0, n_end - n_begin);
 
     if (tid == 0) {
         mbar_init(&bar_a, 1);
-        mbar_init(&bar_b, 1);
-        mbar_init(&bar_mma, 1);
+        for (int s = 0; s < kMaxRing; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 4);
+        }
         fence_barrier_init();
         tma_prefetch_desc(&tmZ);
         tma_prefetch_desc(&tmW);
     }
-    if (warp == 0) tmem_alloc<128>(&tmem_slot);
-    for (int j = 0; j < p.k; ++j) {
-        lval[j * kHeadTile + tid] = -INFINITY;
-        lidx[j * kHeadTile + tid] = -1;
-    }
+    if (warp == 2) tmem_alloc<256>(&tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
 
-    const int row = mt * kHeadTile + tid;
-    const bool row_ok = row < p.M;
-    const long long tgt = row_ok ? (long long)p.target[row] : -1;       // global index
-    const float st = (p.mode == 1 && row_ok) ? p.st[row] : 0.f;
-    const long long tloc = tgt - p.vocab_offset;                         // index inside this shard
-    int cgt = 0, ceq = 0, filled = 0;
-    float thr = -INFINITY;
-
-    if (tid == 0) {
-        mbar_expect_tx(&bar_a, (uint32_t)tile_bytes);
-        tma_load_3d(sA, &tmZ, &bar_a, 0, mt * kHeadTile, 0);
-    }
-    __syncwarp();
-    uint32_t ph_b = 0, ph_mma = 0;
-    bool a_ready = false;
-
-    for (int n = n_begin; n < n_end; ++n) {
-        if (p.mode == 0) {   // only tiles that hold some row's target matter
-            if (tid == 0) any_target = 0;
-            __syncthreads();
-            if (row_ok && tloc >= (long long)n * kHeadTile && tloc < (long long)(n + 1) * kHeadTile) any_target = 1;
-            __syncthreads();
-            if (!any_target) continue;
-        }
-        if (tid == 0) {
-            mbar_expect_tx(&bar_b, (uint32_t)tile_bytes);
-            tma_load_3d(sB, &tmW, &bar_b, 0, n * kHeadTile, 0);
-            if (!a_ready) mbar_wait(&bar_a, 0);
-            mbar_wait(&bar_b, ph_b);
-            tc_fence_after();
-            const uint32_t idesc = make_idesc_bf16(kHeadTile, kHeadTile, 0, 0);
-            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-            for (int ks = 0; ks < p.K / 16; ++ks)
-                umma_bf16(tmem, make_smem_desc(a0 + ks * 2 * kHeadTile * 16, kHeadTile * 16, 128),
-                          make_smem_desc(b0 + ks * 2 * kHeadTile * 16, kHeadTile * 16, 128), idesc, ks > 0);
-            umma_commit(&bar_mma);
-        }
-        a_ready = true;
-        ph_b ^= 1;
-        {
-            const int col = n * kHeadTile + tid;
-            sbias[tid] = (p.bias != nullptr && col < p.V) ? p.bias[col] : 0.f;
-        }
-        __syncthreads();
-        mbar_wait(&bar_mma, ph_mma);
-        ph_mma ^= 1;
-        tc_fence_after();
-        for (int c0 = 0; c0 < kHeadTile; c0 += 16) {
-            uint32_t acc[16];
-            tmem_ld16(tmem + lane_off + c0, acc);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const int col = n * kHeadTile + c0 + e;
-                if (col >= p.V || !row_ok) break;
-                const float v = __uint_as_float(acc[e]) + sbias[c0 + e];
-                const long long gi = p.vocab_offset + col;
-                if (p.logits) p.logits[(size_t)row * p.V + col] = v;
-                if (p.mode == 0) {
-                    if (gi == tgt) p.st[row] = v;
-                } else {
-                    if (gi != tgt) {
-                        cgt += v > st;
-                        ceq += (v == st) && (gi < tgt);
-                    }
-                    if (filled < p.k || v > thr) {      // ascending index scan: an equal value never displaces an earlier one
-                        int pos = filled < p.k ? filled : p.k - 1;
-                        while (pos > 0 && lval[(pos - 1) * kHeadTile + tid] < v) {
-                            lval[pos * kHeadTile + tid] = lval[(pos - 1) * kHeadTile + tid];
-                            lidx[pos * kHeadTile + tid] = lidx[(pos - 1) * kHeadTile + tid];
-                            --pos;
-                        }
-                        lval[pos * kHeadTile + tid] = v;
-                        lidx[pos * kHeadTile + tid] = (int32_t)gi;
-                        if (filled < p.k) ++filled;
-                        if (filled == p.k) thr = lval[(p.k - 1) * kHeadTile + tid];
-                    }
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            mbar_expect_tx(&bar_a, (uint32_t)(kblocks * kBlkBytes));
+            for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(sA + (size_t)kb * kBlkBytes, &tmZ, &bar_a, kb * kKB, mt * kHeadTile);
+            int it = 0;
+            for (int t = 0; t < T; ++t) {
+                const int n = n_begin + t;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const int s = it % p.ring;
+                    const uint32_t ph = (uint32_t)(it / p.ring) & 1u;
+                    mbar_wait(&bar_empty[s], ph ^ 1u);
+                    mbar_expect_tx(&bar_full[s], (uint32_t)kBlkBytes);
+                    tma_load_2d(sB + (size_t)s * kBlkBytes, &tmW, &bar_full[s], kb * kKB, n * kHeadTile);
                 }
             }
-            __syncwarp();     // tcgen05.ld is warp-collective: reconverge before the next chunk
         }
-        tc_fence_before();
-        __syncthreads();      // TMEM accumulator and sB are free for the next tile
-    }
-    if (p.mode == 1 && row_ok) {
-        const size_t o = ((size_t)row * p.nsplit + sp);
-        for (int j = 0; j < p.k; ++j) {
-            p.topk_val[o * p.k + j] = lval[j * kHeadTile + tid];
-            p.topk_idx[o * p.k + j] = lidx[j * kHeadTile + tid];
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(kHeadTile, kHeadTile, 0, 0);
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+            mbar_wait(&bar_a, 0);
+            int it = 0;
+            for (int t = 0; t < T; ++t) {
+                const int a = t & 1;
+                mbar_wait(&acc_empty[a], ((uint32_t)(t >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const int s = it % p.ring;
+                    mbar_wait(&bar_full[s], (uint32_t)(it / p.ring) & 1u);
+                    tc_fence_after();
+                    const int ksteps = min(kKB, p.K - kb * kKB) / 16;
+                    for (int j = 0; j < ksteps; ++j)
+                        umma_bf16(tmem + (uint32_t)(a * kHeadTile), make_smem_desc_sw128(a0 + kb * kBlkBytes + j * 32),
+                                  make_smem_desc_sw128(b0 + s * kBlkBytes + j * 32), idesc, (kb | j) != 0);
+                    umma_commit(&bar_empty[s]);
+                }
+                umma_commit(&acc_full[a]);
+            }
         }
-        p.cnt_gt[o] = cgt;
-        p.cnt_eq[o] = ceq;
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue warpgroups
+        const int e = (warp - 4) >> 2;                      // accumulator buffer / tile parity
+        const int r = ((warp & 3) << 5) | lane;             // row inside the tile == TMEM lane
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        const int row = mt * kHeadTile + r;
+        const bool row_ok = row < p.M;
+        const long long tgt = row_ok ? (long long)p.target[row] : -1;
+        const long long tloc = tgt - p.vocab_offset;
+        const float st = row_ok ? p.st[row] : 0.f;
+        const float st_prev = prev_float(st);
+        RowState s;
+        s.lk = smem_u32(lkey + (size_t)e * p.k * kHeadTile + r);
+        s.cd = smem_u32(cand + (size_t)e * kCandCap * kHeadTile + r);
+        s.k = p.k;
+        s.thr = -INFINITY;
+        s.ncand = 0;
+        s.cnt = 0;
+        for (int j = 0; j < p.k; ++j) sts64(s.lk + (uint32_t)j * kEnt, 0ull);
+
+        for (int t = e; t < T; t += 2) {
+            const int n = n_begin + t;
+            const int col_base = n * kHeadTile;
+            mbar_wait(&acc_full[e], (uint32_t)(t >> 1) & 1u);
+            tc_fence_after();
+            const bool partial = col_base + kHeadTile > p.V;
+            const bool has_tgt = tloc >= col_base && tloc < col_base + kHeadTile;
+            const float cmp = (tloc >= col_base + kHeadTile) ? st_prev : st;   // whole tile before / after the target
+#pragma unroll 1
+            for (int c0 = 0; c0 < kHeadTile; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld32(tmem + lane_off + (uint32_t)(e * kHeadTile + c0), acc);
+                tmem_ld_wait();
+                if (c0 == kHeadTile - 32) {   // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[e]);
+                }
+                const int cb = col_base + c0;
+                if (partial || has_tgt || p.logits != nullptr) {
+                    // exact per-element path: vocabulary tail, the tile that holds this row's target, logits dump (tests)
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const int col = cb + q;
+                        if (col < p.V) {
+                            const float v = __uint_as_float(acc[q]) + (p.bias ? __ldg(p.bias + col) : 0.f);
+                            if (p.logits && row_ok) p.logits[(size_t)row * p.V + col] = v;
+                            if (col != tloc) s.cnt += (col < tloc) ? (v >= st) : (v > st);
+                            if (v > s.thr) candidate(s, v, p.vocab_offset + col);
+                        }
+                    }
+                } else {
+                    float b[32];
+                    if (p.bias) {
+                        const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + cb);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 x = __ldg(b4 + q);
+                            b[4 * q] = x.x; b[4 * q + 1] = x.y; b[4 * q + 2] = x.z; b[4 * q + 3] = x.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) b[q] = 0.f;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 32; q += 4) {
+                        const float v0 = __uint_as_float(acc[q]) + b[q], v1 = __uint_as_float(acc[q + 1]) + b[q + 1];
+                        const float v2 = __uint_as_float(acc[q + 2]) + b[q + 2], v3 = __uint_as_float(acc[q + 3]) + b[q + 3];
+                        s.cnt += (int)(v0 > cmp) + (int)(v1 > cmp) + (int)(v2 > cmp) + (int)(v3 > cmp);
+                        const float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+                        if (m > s.thr) {
+                            const long long g0 = p.vocab_offset + cb + q;
+                            if (v0 > s.thr) candidate(s, v0, g0);
+                            if (v1 > s.thr) candidate(s, v1, g0 + 1);
+                            if (v2 > s.thr) candidate(s, v2, g0 + 2);
+                            if (v3 > s.thr) candidate(s, v3, g0 + 3);
+                        }
+                    }
+                }
+                __syncwarp();     // tcgen05.ld is warp-collective: reconverge before the next chunk
+            }
+            drain(s);             // all lanes together: lane-aligned insertion, fresh threshold for the next tile
+            __syncwarp();
+        }
+        if (row_ok) {
+            const size_t o = (size_t)row * p.nsplit + (size_t)sp * 2 + e;
+            for (int j = 0; j < p.k; ++j) {
+                const unsigned long long key = lds64(s.lk + (uint32_t)j * kEnt);
+                p.topk_val[o * p.k + j] = key ? ord2f((uint32_t)(key >> 32)) : -INFINITY;
+                p.topk_idx[o * p.k + j] = key ? (int32_t)(~(uint32_t)key) : -1;
+            }
+            p.cnt_gt[o] = s.cnt;
+            p.cnt_eq[o] = 0;
+        }
     }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<256>(tmem);
+}
+
+// mode 0: st[row] = z[row] . W[target[row]] + bias[target[row]] through the same tcgen05 arithmetic as mode 1
+// (same operand layout, same K-step sequence), for the rows whose target lies in this shard.
+struct TargetParams {
+    const __nv_bfloat16 *W;
+    const float *bias;
+    const int32_t *target;
+    float *st;
+    int M, V, K;
+    int64_t vocab_offset;
+};
+
+__global__ void __launch_bounds__(128, 1)
+k5_target_logit_kernel(const __grid_constant__ CUtensorMap tmZ, const TargetParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_a, bar_mma;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = warp_index_uniform(), lane = tid & 31;
+    const int mt = blockIdx.x;
+    const int kblocks = ceil_div(p.K, kKB);
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = sA + (size_t)kblocks * kBlkBytes;
+
+    if (tid == 0) {
+        mbar_init(&bar_a, 1);
+        mbar_init(&bar_mma, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmZ);
+    }
+    if (warp == 0) tmem_alloc<128>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (warp == 0 && elect_one()) {
+        mbar_expect_tx(&bar_a, (uint32_t)(kblocks * kBlkBytes));
+        for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(sA + (size_t)kb * kBlkBytes, &tmZ, &bar_a, kb * kKB, mt * kHeadTile);
+    }
+    __syncwarp();
+    // gather: row r of the B tile = W[target[row] - vocab_offset], written in the 128-byte-swizzle layout
+    const int row = mt * kHeadTile + tid;
+    const long long tloc = row < p.M ? (long long)p.target[row] - p.vocab_offset : -1;
+    const bool own = tloc >= 0 && tloc < p.V;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.W + (size_t)(own ? tloc : 0) * p.K);
+        const int nchunk = p.K / 8;
+        for (int c = 0; c < kblocks * 8; ++c) {
+            const uint4 v = (own && c < nchunk) ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4 *>(sB + (size_t)(c >> 3) * kBlkBytes + tid * 128 + (((c & 7) ^ (tid & 7)) << 4)) = v;
+        }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (warp == 0 && elect_one()) {
+        const uint32_t idesc = make_idesc_bf16(kHeadTile, kHeadTile, 0, 0);
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+        mbar_wait(&bar_a, 0);
+        tc_fence_after();
+        for (int kb = 0; kb < kblocks; ++kb) {
+            const int ksteps = min(kKB, p.K - kb * kKB) / 16;
+            for (int j = 0; j < ksteps; ++j)
+                umma_bf16(tmem, make_smem_desc_sw128(a0 + kb * kBlkBytes + j * 32), make_smem_desc_sw128(b0 + kb * kBlkBytes + j * 32),
+                          idesc, (kb | j) != 0);
+        }
+        umma_commit(&bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    uint32_t acc[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(warp * 32), acc);    // the diagonal 32x32 block of this warp
+    tmem_ld_wait();
+    float d = 0.f;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) d = (q == lane) ? __uint_as_float(acc[q]) : d;
+    if (own) p.st[row] = d + (p.bias ? p.bias[tloc] : 0.f);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<128>(tmem);
@@ -202,6 +416,13 @@ __global__ void k5_topk_merge_kernel(const float *__restrict__ val, const int32_
     }
 }
 
+static int32_t encode_rows_sw128(CUtensorMap *tm, const void *base, int rows, int K) {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
+    uint64_t str[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {kKB, kHeadTile};
+    return encode_tmap_bf16(tm, base, 2, dims, str, box, 1);
+}
+
 }  // namespace mobgt
 
 using namespace mobgt;
@@ -213,29 +434,36 @@ extern "C" int32_t mobgt_head_topk(const void *z, const void *W, const float *bi
     MOBGT_REQUIRE(z && W && target && st, MOBGT_ERR_NULL, "mobgt_head_topk: null pointer");
     MOBGT_REQUIRE(mode == 0 || (topk_val && topk_idx && cnt_gt && cnt_eq), MOBGT_ERR_NULL, "mobgt_head_topk: null output");
     MOBGT_REQUIRE(K % 16 == 0 && K >= 16 && K <= kHeadMaxK, MOBGT_ERR_BAD_SHAPE, "mobgt_head_topk: K=%d", K);
-    MOBGT_REQUIRE(k >= 1 && k <= kHeadMaxTop && nsplit >= 1 && nsplit <= 64, MOBGT_ERR_BAD_SHAPE, "mobgt_head_topk: k=%d nsplit=%d",
-                  k, nsplit);
+    MOBGT_REQUIRE(k >= 1 && k <= kHeadMaxTop, MOBGT_ERR_BAD_SHAPE, "mobgt_head_topk: k=%d", k);
+    MOBGT_REQUIRE(mode == 0 || (nsplit >= 2 && nsplit <= 64 && nsplit % 2 == 0), MOBGT_ERR_BAD_SHAPE,
+                  "mobgt_head_topk: nsplit=%d must be even, in [2,64] (two epilogue groups per vocabulary split)", nsplit);
+    MOBGT_REQUIRE(((uintptr_t)z & 15) == 0 && ((uintptr_t)W & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0), MOBGT_ERR_BAD_SHAPE,
+                  "mobgt_head_topk: z, W and bias must be 16-byte aligned");
     if (M <= 0 || V <= 0) return MOBGT_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
     CUtensorMap tmZ, tmW;
-    {
-        uint64_t dims[3] = {8, (uint64_t)M, (uint64_t)K / 8};
-        uint64_t str[2] = {(uint64_t)K * 2, 16};
-        uint32_t box[3] = {8, kHeadTile, (uint32_t)K / 8};
-        int32_t rc = encode_tmap_bf16(&tmZ, z, 3, dims, str, box, 0);
-        if (rc) return rc;
+    int32_t rc = encode_rows_sw128(&tmZ, z, M, K);
+    if (rc) return rc;
+    const int kblocks = ceil_div(K, kKB);
+    if (mode == 0) {
+        const size_t smem = (size_t)2 * kblocks * kBlkBytes + 1024;
+        MOBGT_CUDA_OK(cudaFuncSetAttribute(k5_target_logit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TargetParams tp{static_cast<const __nv_bfloat16 *>(W), bias, target, st, M, V, K, vocab_offset};
+        k5_target_logit_kernel<<<ceil_div(M, kHeadTile), 128, smem, s>>>(tmZ, tp);
+        MOBGT_LAUNCH_OK("k5_target_logit_kernel");
+        return MOBGT_OK;
     }
-    {
-        uint64_t dims[3] = {8, (uint64_t)V, (uint64_t)K / 8};
-        uint64_t str[2] = {(uint64_t)K * 2, 16};
-        uint32_t box[3] = {8, kHeadTile, (uint32_t)K / 8};
-        int32_t rc = encode_tmap_bf16(&tmW, W, 3, dims, str, box, 0);
-        if (rc) return rc;
-    }
-    const size_t smem = (size_t)2 * (K / 8) * kHeadTile * 16 + (size_t)2 * k * kHeadTile * 4 + 1024;
+    rc = encode_rows_sw128(&tmW, W, V, K);
+    if (rc) return rc;
+    const size_t fixed = (size_t)kblocks * kBlkBytes + (size_t)2 * (k + kCandCap) * kHeadTile * 8 + 1024;
+    int ring = (int)((227 * 1024 - 512 - (long long)fixed) / kBlkBytes);
+    ring = ring > kMaxRing ? kMaxRing : ring;
+    MOBGT_REQUIRE(ring >= 2, MOBGT_ERR_UNSUPPORTED, "mobgt_head_topk: no shared-memory plan for K=%d k=%d", K, k);
+    const size_t smem = fixed + (size_t)ring * kBlkBytes;
     MOBGT_CUDA_OK(cudaFuncSetAttribute(k5_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HeadParams p{bias, target, st, topk_val, topk_idx, cnt_gt, cnt_eq, logits_dump, M, V, K, k, nsplit, mode, vocab_offset};
-    dim3 grid((unsigned)ceil_div(M, kHeadTile), (unsigned)nsplit);
-    k5_head_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(tmZ, tmW, p);
+    HeadParams p{bias, target, st, topk_val, topk_idx, cnt_gt, cnt_eq, logits_dump, M, V, K, k, nsplit, mode, ring, vocab_offset};
+    dim3 grid((unsigned)ceil_div(M, kHeadTile), (unsigned)(nsplit / 2));
+    k5_head_kernel<<<grid, kHeadThreads, smem, s>>>(tmZ, tmW, p);
     MOBGT_LAUNCH_OK("k5_head_kernel");
     return MOBGT_OK;
 }

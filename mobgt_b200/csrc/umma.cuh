@@ -125,6 +125,19 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     d |= (uint64_t)1 << 46;
     return d;
 }
+// K-major operand in the 128-byte-swizzle layout written by a 2-D TMA box {64 bf16, rows} with CU_TENSOR_MAP_SWIZZLE_128B:
+// smem[row][128 B], 16-byte chunk c of row r stored at chunk position c ^ (r & 7); 8-row groups are 1024 B apart (SBO),
+// LBO is ignored for swizzled K-major operands.  The tile base must be 1024-byte aligned; a K step of 16 bf16 inside the
+// 64-wide block advances the start address by 32 B.   [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // Instruction descriptor for kind::f16, bf16 x bf16 -> f32:
 //   [4,6) c_format=1 (f32) | [7,10) a_format=1 (bf16) | [10,13) b_format=1 | bit15 a_major (1 = MN) |
 //   bit16 b_major | [17,23) N>>3 | [24,29) M>>4

@@ -281,10 +281,17 @@ class EmbedSum(torch.autograd.Function):
 
 # ----------------------------------------------------------------------------------------------- K5
 def head_split(M, V):
-    """vocabulary splits per 128-row tile of z so that the grid covers the 148 SMs about twice."""
+    """Number of per-row output lists = 2 x (vocabulary splits per 128-row tile of z): every CTA of mobgt_head_topk runs two
+    epilogue groups.  The split count minimises waves x (tiles per CTA + a fixed per-CTA cost) over the 148 SMs."""
     mt = (M + 127) // 128
     nt = (V + 127) // 128
-    return int(max(1, min(64, nt, (2 * 148 + mt - 1) // mt)))
+    best, best_cost = 1, None
+    for gs in range(1, min(32, nt) + 1):
+        waves = (mt * gs + 147) // 148
+        cost = waves * ((nt + gs - 1) // gs + 8)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = gs, cost
+    return 2 * best
 
 
 def head_topk_local(z, W, bias, target, k, vocab_offset=0, st=None, dump_logits=False):
@@ -318,7 +325,7 @@ def head_target_logit(z, W, bias, target, vocab_offset=0):
     V = W.shape[0]
     st = torch.full((M,), float("-inf"), dtype=torch.float32, device=z.device)
     _C.call("mobgt_head_topk", _C.ptr(z), _C.ptr(W), _C.ptr(bias), _C.ptr(target), M, V, K, int(vocab_offset), 1,
-            head_split(M, V), 0, _C.ptr(st), None, None, None, None, None, _C.stream_ptr())
+            2, 0, _C.ptr(st), None, None, None, None, None, _C.stream_ptr())
     return st
 
 

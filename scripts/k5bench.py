@@ -1,0 +1,23 @@
+"""K5 alone: device time of the fused head (mode 1 + merge, and mode 0) at the c2 / c5-shard shapes: python scripts/k5bench.py"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import bench
+from mobgt_b200 import ops
+
+pk = bench.peaks()
+dev = torch.device("cuda")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+for name, M, V, k in (("c2", 256, 60001, 10), ("c5_shard", 4096, 125000, 10), ("c5_shard_k20", 4096, 125000, 20), ("mid", 1024, 125000, 10)):
+    g = torch.Generator(device=dev).manual_seed(5)
+    z = torch.randn(M, 320, device=dev, generator=g).to(torch.bfloat16)
+    W = (torch.randn(V, 320, device=dev, generator=g) * 0.02).to(torch.bfloat16)
+    b = torch.randn(V, device=dev, generator=g) * 0.1
+    tgt = torch.randint(0, V, (M,), device=dev, generator=g).int()
+    st = ops.head_target_logit(z, W, b, tgt)
+    t1 = bench.time_kernel(lambda: ops.head_topk_local(z, W, b, tgt, k, st=st), flush, iters=6)
+    t0 = bench.time_kernel(lambda: ops.head_target_logit(z, W, b, tgt), flush, iters=6)
+    fl = 2.0 * M * 320 * V
+    print(f"{name:14s} M={M} V={V} k={k} nsplit={ops.head_split(M, V)}: mode1+merge {t1*1e3:8.1f} us = {fl/t1/1e9:7.1f} TF/s "
+          f"({100*fl/t1/1e9/pk['tc']:.1f}% of bf16 peak) ; mode0 {t0*1e3:7.1f} us")
