@@ -105,12 +105,15 @@ int32_t mobgt_poi_pos(const int32_t *x, const int32_t *n, const int64_t *sq_off,
  *   tables: R [512,H] rel_pos_encoder, Ppos [bins,H] poi_pos_encoder, E [128,H] edge_encoder,
  *           W [>=hops*H*H] edge_dis_encoder (viewed [k,h',h]), tvd [H] graph_token_virtual_distance.
  *   hops is the hop-slot count of edge_in (a multiple of 4, as written by K1) and the clamp of the mean.
- *   forward workspace: hops*128*H floats (the E.W table); backward workspace: mobgt_bias_bwd_workspace_bytes().
+ *   forward workspace: mobgt_bias_fwd_workspace_bytes() (the E.W table [hops,128,H] and the rel_pos-keyed table RL [512,H]);
+ *   backward workspace: mobgt_bias_bwd_workspace_bytes().
  * Backward: dBias -> dR [512,H], dPpos [bins,H], dE [128,H], dW [hops*H*H], dtvd [H]  (all overwritten).
  *   dbias_dtype MOBGT_F32:  one f32 [B,H,T,Tp] buffer holding the sum over layers (n_layers = 1);
  *   dbias_dtype MOBGT_BF16: n_layers bf16 [B,H,T,Tp] planes, layer_stride elements apart (mobgt_attn_bwd mode 2),
  *                           summed in fp32 inside the kernel.
  * ------------------------------------------------------------------------------------------ */
+/* bytes of `workspace` mobgt_bias_fwd needs; < 0 on bad arguments */
+int64_t mobgt_bias_fwd_workspace_bytes(int32_t hops, int32_t H);
 int32_t mobgt_bias_fwd(const int32_t *n, const int64_t *sq_off, const int16_t *rel_pos, const int16_t *poi_pos,
                        const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t H,
                        int32_t rel_pos_max, int32_t num_bins, const float *R, const float *Ppos, const float *E,

@@ -29,6 +29,7 @@ SIGNATURES = {
     "mobgt_poi_pos": [c_p, c_p, c_p, c_p, c_p, c_f32, c_i32, c_i32, c_i32, c_p, c_p],
     "mobgt_bias_fwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p,
                        c_p, c_i32, c_p],
+    "mobgt_bias_fwd_workspace_bytes": [c_i32, c_i32],
     "mobgt_bias_bwd_workspace_bytes": [c_i32, c_i32, c_i32],
     "mobgt_bias_bwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_i32, c_i64, c_p,
                        c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p],

@@ -38,15 +38,45 @@ struct K2Common {
     int B, T, Tp, hops, rel_pos_max;
 };
 
-// EW[k][v][h] = sum_h' E[v][h'] * W[k][h'][h]
-__global__ void k2_prep_kernel(const float *__restrict__ E, const float *__restrict__ W, int hops, float *__restrict__ EW) {
+constexpr int kDomEdge = 4;    // edge count 1 -> attn_edge_type 3 (wrapper.py:49-53) -> +1 (collator.py:86-93): "one transition"
+constexpr int kRelRows = 512;  // rel_pos_encoder rows (model_fqandtoyo.py:786): keys 0..511
+
+// walk length the distance key rp = M + 1 predicts: min(M, hops) for a reachable off-diagonal pair, else 0
+__host__ __device__ __forceinline__ int expected_walk(int rp, int hops) {
+    const int M = rp - 1;
+    return (M < 510) ? min(max(M, 0), hops) : 0;
+}
+
+// Prologue tables (workspace):
+//   EW[k][v][h] = sum_h' E[v][h'] * W[k][h'][h]                                            [hops][128][8]
+//   RL[rp][h]   = R[rp][h] + ( sum_{k < L(rp)} EW[k][dom][h] ) / clamp(rp-1, 1, hops)       [512][8]
+// RL is the whole rel_pos-keyed part of the bias of a pair whose walk is the EXPECTED one: L(rp) hops that all carry the
+// dominant edge feature (a single transition).  -inf where rp-1 >= rel_pos_max (collator.py:354-358).
+__global__ void k2_prep_kernel(const float *__restrict__ E, const float *__restrict__ W, const float *__restrict__ R, int hops,
+                               int rel_pos_max, float *__restrict__ EW, float *__restrict__ RL) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= hops * kEdgeVocab * kH) return;
-    const int h = idx % kH, v = (idx / kH) % kEdgeVocab, k = idx / (kH * kEdgeVocab);
-    float acc = 0.f;
+    const int nEW = hops * kEdgeVocab * kH;
+    if (idx < nEW) {
+        const int h = idx % kH, v = (idx / kH) % kEdgeVocab, k = idx / (kH * kEdgeVocab);
+        float acc = 0.f;
 #pragma unroll
-    for (int hp = 0; hp < kH; ++hp) acc += E[v * kH + hp] * W[(k * kH + hp) * kH + h];
-    EW[idx] = acc;
+        for (int hp = 0; hp < kH; ++hp) acc += E[v * kH + hp] * W[(k * kH + hp) * kH + h];
+        EW[idx] = acc;
+    } else if (idx < nEW + kRelRows * kH) {
+        const int j = idx - nEW;
+        const int h = j % kH, rp = j / kH;
+        const int L = expected_walk(rp, hops);
+        float ps = 0.f;
+        for (int k = 0; k < L; ++k) {
+            float acc = 0.f;
+#pragma unroll
+            for (int hp = 0; hp < kH; ++hp) acc += E[kDomEdge * kH + hp] * W[(k * kH + hp) * kH + h];
+            ps += acc;
+        }
+        const int M = rp - 1;
+        const float inv = 1.0f / (float)min(max(M, 1), hops);
+        RL[j] = (M >= rel_pos_max) ? -INFINITY : R[j] + ps * inv;
+    }
 }
 
 __device__ __forceinline__ void add8(float (&a)[8], const float *__restrict__ p) {
@@ -54,6 +84,12 @@ __device__ __forceinline__ void add8(float (&a)[8], const float *__restrict__ p)
     const float4 y = *reinterpret_cast<const float4 *>(p + 4);
     a[0] += x.x; a[1] += x.y; a[2] += x.z; a[3] += x.w;
     a[4] += y.x; a[5] += y.y; a[6] += y.z; a[7] += y.w;
+}
+__device__ __forceinline__ void sub8(float (&a)[8], const float *__restrict__ p) {
+    const float4 x = *reinterpret_cast<const float4 *>(p);
+    const float4 y = *reinterpret_cast<const float4 *>(p + 4);
+    a[0] -= x.x; a[1] -= x.y; a[2] -= x.z; a[3] -= x.w;
+    a[4] -= y.x; a[5] -= y.y; a[6] -= y.z; a[7] -= y.w;
 }
 
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
@@ -73,30 +109,42 @@ __device__ __forceinline__ void store1<float>(float *p, float a) { *p = a; }
 template <>
 __device__ __forceinline__ void store1<__nv_bfloat16>(__nv_bfloat16 *p, float a) { *p = __float2bfloat16_rn(a); }
 
-// Forward.  Persistent CTAs: EW [hops][128][8], R [512][8] and Ppos [bins][8] are staged once per CTA in shared memory.
-// One thread per PAIR OF ADJACENT CELLS (a, b) (a, b+1), b even, of the Tp-pitched plane row, so every head plane is
-// written as 4-byte (bf16x2) / 8-byte (f32x2) words and a warp covers 64 consecutive columns.  All index bytes of a
-// thread's two cells (2 x (2 + 2 + hops) B) are fetched up front as independent 32-bit loads; the hop loop then
-// runs out of registers and shared memory only.
-template <typename OutT>
-__global__ void __launch_bounds__(512, 2) k2_bias_fwd_kernel(const K2Common c, const float *__restrict__ Rg,
+// expected walk bytes of a pair with walk length L: word q = dominant feature in bytes [4q, 4q+4) ∩ [0, L)
+__device__ __forceinline__ uint32_t expected_word(int L, int q) {
+    const int r = min(max(L - 4 * q, 0), 4);
+    const uint32_t mask = r >= 4 ? 0xFFFFFFFFu : ((1u << (8 * r)) - 1u);
+    return (0x01010101u * (uint32_t)kDomEdge) & mask;
+}
+
+// Forward.  Persistent CTAs; RL [512][8], Ppos [bins][8] and the expected-walk words XW [hops+1][8] are staged once per
+// CTA in shared memory.  One thread per PAIR OF ADJACENT CELLS (a, b) (a, b+1), b even, of the Tp-pitched plane row, so
+// every head plane is written as 4-byte (bf16x2) / 8-byte (f32x2) words and a warp covers 64 consecutive columns.  All
+// index bytes of a thread's two cells (2 x (2 + 2 + hops) B) are fetched up front as independent loads.
+//
+// Per cell the work is TWO table gathers: bias = RL[rp] + Ppos[pp].  The walk bytes are only compared (XOR) against the
+// walk the distance predicts; the bytes that differ — another edge feature (0.7 % of the hops of trajectory graphs) or a
+// walk cut short by the reference's node-0 quirk (algos.pyx:57-62) — are corrected one by one from the EW table in
+// global memory (L1-resident):   Edge = sum_k EW[k][e_k]  =  PS[L] + sum_{k : e_k != x_k} ( EW[k][e_k] - EW[k][x_k] ).
+// The identity holds for ANY byte pattern (EW[k][0] = 0: edge_encoder row 0 is the padding row, model_fqandtoyo.py:784).
+template <typename OutT, int HOPW>
+__global__ void __launch_bounds__(512, 2) k2_bias_fwd_kernel(const K2Common c, const float *__restrict__ RLg,
                                                              const float *__restrict__ Pg, int num_bins,
                                                              const float *__restrict__ tvd,
                                                              const float *__restrict__ EWg, OutT *__restrict__ out) {
     extern __shared__ __align__(16) float sm[];
-    const int nEW = c.hops * kEdgeVocab * kH, nR = 512 * kH, nP = num_bins * kH;
-    float *EW = sm, *R = EW + nEW, *Pp = R + nR;
-    for (int i = threadIdx.x * 4; i < nEW; i += blockDim.x * 4)
-        *reinterpret_cast<float4 *>(EW + i) = *reinterpret_cast<const float4 *>(EWg + i);
+    const int nR = kRelRows * kH, nP = num_bins * kH;
+    float *RL = sm, *Pp = RL + nR;
+    uint32_t *XW = reinterpret_cast<uint32_t *>(Pp + nP);          // [hops + 1][8]
     for (int i = threadIdx.x * 4; i < nR; i += blockDim.x * 4)
-        *reinterpret_cast<float4 *>(R + i) = *reinterpret_cast<const float4 *>(Rg + i);
+        *reinterpret_cast<float4 *>(RL + i) = *reinterpret_cast<const float4 *>(RLg + i);
     for (int i = threadIdx.x * 4; i < nP; i += blockDim.x * 4)
         *reinterpret_cast<float4 *>(Pp + i) = *reinterpret_cast<const float4 *>(Pg + i);
+    constexpr int hopw = HOPW;                    // hops = 4 * HOPW
+    for (int i = threadIdx.x; i < (c.hops + 1) * 8; i += blockDim.x) XW[i] = (i & 7) < hopw ? expected_word(i >> 3, i & 7) : 0u;
     float tv[8];
 #pragma unroll
     for (int h = 0; h < 8; ++h) tv[h] = tvd[h];
     __syncthreads();
-    const int hopw = c.hops >> 2;                 // hops is a multiple of 4
     const int half = c.Tp >> 1;                   // cell pairs per plane row
     const int per_graph = c.T * half;
     const int tiles = ceil_div(per_graph, (int)blockDim.x);
@@ -118,7 +166,7 @@ __global__ void __launch_bounds__(512, 2) k2_bias_fwd_kernel(const K2Common c, c
             const int64_t rowp = c.sq_off[g] + (int64_t)(a - 1) * n;   // pair (a-1, j) lives at rowp + j
             // cell s of this thread is the pair j = b - 1 + s  (b == 0, s == 0: the virtual-distance column)
             int rp[2], pp[2];
-            uint32_t ew[2][8];
+            uint32_t ew[2][HOPW];
             bool is_pair[2];
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
@@ -126,14 +174,14 @@ __global__ void __launch_bounds__(512, 2) k2_bias_fwd_kernel(const K2Common c, c
                 is_pair[s] = j >= 0 && j < n;
                 rp[s] = 0; pp[s] = 0;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) ew[s][q] = 0u;
+                for (int q = 0; q < HOPW; ++q) ew[s][q] = 0u;
                 if (is_pair[s]) {
                     const int64_t pc = rowp + j;
                     rp[s] = c.rel_pos[pc];
                     pp[s] = c.poi_pos[pc];
                     const uint32_t *ei = reinterpret_cast<const uint32_t *>(c.edge_in + pc * c.hops);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) if (q < hopw) ew[s][q] = __ldg(ei + q);
+                    for (int q = 0; q < HOPW; ++q) ew[s][q] = __ldg(ei + q);
                 }
             }
 #pragma unroll
@@ -145,33 +193,38 @@ __global__ void __launch_bounds__(512, 2) k2_bias_fwd_kernel(const K2Common c, c
                     }
                     continue;
                 }
-                const int M = rp[s] - 1;
-                if (M >= c.rel_pos_max) {
+                const int rk = min(max(rp[s], 0), kRelRows - 1);
+                const int L = expected_walk(rk, c.hops);
+                const uint4 x0 = *reinterpret_cast<const uint4 *>(XW + L * 8), x1 = *reinterpret_cast<const uint4 *>(XW + L * 8 + 4);
+                const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                uint32_t any = 0u;
 #pragma unroll
-                    for (int h = 0; h < 8; ++h) acc[s][h] = -INFINITY;
-                    continue;
-                }
-                bool live = true;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    if (q < hopw && live) {
-                        const uint32_t wd = ew[s][q];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int v = (wd >> (8 * e)) & 0xFF;
-                            if (v == 0) { live = false; break; }     // end of the walk (E[0] == 0: padding row)
-                            add8(acc[s], EW + ((size_t)(q * 4 + e) * kEdgeVocab + v) * kH);
-                        }
-                    }
-                }
-                const float inv = 1.0f / (float)min(max(M, 1), c.hops);
-                const float *r = R + rp[s] * kH, *q_ = Pp + min(pp[s], num_bins - 1) * kH;
+                for (int q = 0; q < HOPW; ++q) any |= ew[s][q] ^ xw[q];
+                const float *r = RL + rk * kH, *q_ = Pp + min(max(pp[s], 0), num_bins - 1) * kH;
                 const float4 r0 = *reinterpret_cast<const float4 *>(r), r1 = *reinterpret_cast<const float4 *>(r + 4);
                 const float4 p0 = *reinterpret_cast<const float4 *>(q_), p1 = *reinterpret_cast<const float4 *>(q_ + 4);
-                const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-                const float qq[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+                acc[s][0] = r0.x + p0.x; acc[s][1] = r0.y + p0.y; acc[s][2] = r0.z + p0.z; acc[s][3] = r0.w + p0.w;
+                acc[s][4] = r1.x + p1.x; acc[s][5] = r1.y + p1.y; acc[s][6] = r1.z + p1.z; acc[s][7] = r1.w + p1.w;
+                if (any != 0u) {
+                    float corr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int h = 0; h < 8; ++h) acc[s][h] = (rr[h] + qq[h]) + acc[s][h] * inv;
+                    for (int q = 0; q < HOPW; ++q) {
+                        {
+                            uint32_t d = ew[s][q] ^ xw[q];
+                            while (d != 0u) {
+                                const int e = (__ffs(d) - 1) >> 3;
+                                const int v = (ew[s][q] >> (8 * e)) & 0xFF, x = (xw[q] >> (8 * e)) & 0xFF;
+                                const float *row = EWg + (size_t)(q * 4 + e) * kEdgeVocab * kH;
+                                add8(corr, row + min(v, kEdgeVocab - 1) * kH);
+                                sub8(corr, row + x * kH);
+                                d &= ~(0xFFu << (8 * e));
+                            }
+                        }
+                    }
+                    const float inv = 1.0f / (float)min(max(rk - 1, 1), c.hops);
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) acc[s][h] += corr[h] * inv;
+                }
             }
         }
         OutT *o = out + ((size_t)g * kH * c.T + a) * c.Tp + b;
@@ -201,7 +254,6 @@ __global__ void __launch_bounds__(512, 2) k2_bias_fwd_kernel(const K2Common c, c
 //     histogram, low contention), and the finish resolves dEW[k][dom] += sum_{L > k} A[L] - N[k].
 // Per-CTA totals go to a partial buffer in the workspace and are reduced in a fixed order by the finish kernels
 // (reproducible except for the rare-path atomics).
-constexpr int kDomEdge = 4;    // edge count 1 -> attn_edge_type 3 (wrapper.py:49-53) -> +1 (collator.py:86-93)
 
 struct K2BwdPlan {
     int Rrows;      // rel_pos histogram rows: keys 0..Rrows-2 direct, key 511 -> row Rrows-1
@@ -441,6 +493,11 @@ __global__ void k2_bias_bwd_finish_kernel(const float *__restrict__ dEW, const f
 
 using namespace mobgt;
 
+extern "C" int64_t mobgt_bias_fwd_workspace_bytes(int32_t hops, int32_t H) {
+    if (H != kH || hops < 4 || hops > MOBGT_MAX_HOPS || hops % 4 != 0) return -1;
+    return (int64_t)(hops * kEdgeVocab + kRelRows) * kH * (int64_t)sizeof(float);
+}
+
 extern "C" int32_t mobgt_bias_fwd(const int32_t *n, const int64_t *sq_off, const int16_t *rel_pos, const int16_t *poi_pos,
                                   const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t H,
                                   int32_t rel_pos_max, int32_t num_bins, const float *R, const float *Ppos, const float *E,
@@ -456,21 +513,33 @@ extern "C" int32_t mobgt_bias_fwd(const int32_t *n, const int64_t *sq_off, const
     MOBGT_REQUIRE(out_dtype == MOBGT_F32 || out_dtype == MOBGT_BF16, MOBGT_ERR_BAD_DTYPE, "mobgt_bias_fwd: dtype");
     if (B <= 0) return MOBGT_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    float *EW = static_cast<float *>(workspace);
+    float *EW = static_cast<float *>(workspace);                 // [hops][128][8] then RL [512][8]
     const int tabn = hops * kEdgeVocab * kH;
-    k2_prep_kernel<<<ceil_div(tabn, 256), 256, 0, s>>>(E, W, hops, EW);
+    float *RL = EW + tabn;
+    k2_prep_kernel<<<ceil_div(tabn + kRelRows * kH, 256), 256, 0, s>>>(E, W, R, hops, rel_pos_max, EW, RL);
     MOBGT_LAUNCH_OK("k2_prep_kernel");
     K2Common c{n, sq_off, rel_pos, poi_pos, edge_in, B, T, Tp, hops, rel_pos_max};
-    const size_t smem = (size_t)(tabn + 512 * kH + num_bins * kH) * sizeof(float);
+    const size_t smem = (size_t)(kRelRows * kH + num_bins * kH + (hops + 1) * 8) * sizeof(float);
     const int tiles_total = ceil_div(T * (Tp / 2), 512) * B;
     dim3 grid((unsigned)min(2 * kNumSMs, tiles_total));
-    if (out_dtype == MOBGT_F32) {
-        MOBGT_CUDA_OK(cudaFuncSetAttribute(k2_bias_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k2_bias_fwd_kernel<float><<<grid, 512, smem, s>>>(c, R, Ppos, num_bins, tvd, EW, static_cast<float *>(out));
-    } else {
-        MOBGT_CUDA_OK(cudaFuncSetAttribute(k2_bias_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k2_bias_fwd_kernel<__nv_bfloat16><<<grid, 512, smem, s>>>(c, R, Ppos, num_bins, tvd, EW, static_cast<__nv_bfloat16 *>(out));
+    auto launch = [&](auto kern, auto *o) -> int32_t {
+        MOBGT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 512, smem, s>>>(c, RL, Ppos, num_bins, tvd, EW, o);
+        return MOBGT_OK;
+    };
+    int32_t rc = MOBGT_OK;
+#define MOBGT_K2_CASE(HW)                                                                                             \
+    case HW:                                                                                                          \
+        rc = (out_dtype == MOBGT_F32) ? launch(k2_bias_fwd_kernel<float, HW>, static_cast<float *>(out))              \
+                                      : launch(k2_bias_fwd_kernel<__nv_bfloat16, HW>, static_cast<__nv_bfloat16 *>(out)); \
+        break;
+    switch (hops / 4) {
+        MOBGT_K2_CASE(1) MOBGT_K2_CASE(2) MOBGT_K2_CASE(3) MOBGT_K2_CASE(4) MOBGT_K2_CASE(5) MOBGT_K2_CASE(6) MOBGT_K2_CASE(7)
+        MOBGT_K2_CASE(8)
+        default: MOBGT_REQUIRE(false, MOBGT_ERR_BAD_SHAPE, "mobgt_bias_fwd: hops=%d", hops);
     }
+#undef MOBGT_K2_CASE
+    if (rc) return rc;
     MOBGT_LAUNCH_OK("k2_bias_fwd_kernel");
     return MOBGT_OK;
 }

@@ -78,46 +78,36 @@ __device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) {
 }
 constexpr uint32_t kEnt = kHeadTile * 8;   // byte distance between consecutive entries of one row's list / buffer
 
-struct RowState {
-    uint32_t lk;              // shared-memory address of this row's sorted list (entries kEnt apart)
-    uint32_t cd;              // ... of this row's candidate buffer
-    float thr;                // value of the k-th entry (-inf while the list is not full)
-    int ncand, cnt, k;
-};
-
-// Insert the buffered candidates into the sorted list (everything passed by value: the row state stays in registers).
-// Returns the new threshold.  Lanes that arrive here together run the loop together (lane-aligned insertion).
-__device__ __noinline__ float drain_list(uint32_t lk, uint32_t cd, int ncand, int k) {
-    const uint32_t last = lk + (uint32_t)(k - 1) * kEnt;
+// ---- per-row selection state ---------------------------------------------------------------------------------------
+// The sorted top-k list of a row lives in the REGISTERS of the row's thread (LK 64-bit keys: order-preserving value bits in
+// the high word, ~global index in the low word, so a larger key is a better entry and ties go to the lower index).  An
+// insertion is a fully unrolled compare-exchange chain from the bottom of the list — ALU only, no dependent shared-memory
+// round trips.  Candidates (rare after the first tiles) are appended to a small per-row buffer in shared memory and
+// inserted at the end of the tile, when all 32 lanes of the warp drain together; a buffer that fills up inside a tile is
+// drained at ONE place (the re-run loop of harvest()) so the unrolled insertion exists twice in the kernel, not per group.
+template <int LK>
+__device__ __forceinline__ void list_insert(unsigned long long (&list)[LK], unsigned long long key) {
+    list[LK - 1] = key;      // precondition: key > list[LK-1]
+#pragma unroll
+    for (int j = LK - 1; j > 0; --j) {
+        const unsigned long long a = list[j - 1], b = list[j];
+        const bool sw = b > a;
+        list[j - 1] = sw ? b : a;
+        list[j] = sw ? a : b;
+    }
+}
+template <int LK>
+__device__ __forceinline__ float list_drain(unsigned long long (&list)[LK], uint32_t cd, int &ncand) {
     while (ncand > 0) {
         --ncand;
         const unsigned long long key = lds64(cd + (uint32_t)ncand * kEnt);
-        if (key > lds64(last)) {
-            uint32_t pos = last;
-            while (pos > lk) {
-                const unsigned long long up = lds64(pos - kEnt);
-                if (up >= key) break;
-                sts64(pos, up);
-                pos -= kEnt;
-            }
-            sts64(pos, key);
-        }
+        if (key > list[LK - 1]) list_insert<LK>(list, key);
     }
-    const unsigned long long kth = lds64(last);
+    const unsigned long long kth = list[LK - 1];
     return kth ? ord2f((uint32_t)(kth >> 32)) : -INFINITY;
 }
-__device__ __forceinline__ void drain(RowState &s) {
-    s.thr = drain_list(s.lk, s.cd, s.ncand, s.k);
-    s.ncand = 0;
-}
-__device__ __forceinline__ void candidate(RowState &s, float v, long long gi) {
-    if (s.ncand == kCandCap) drain(s);
-    if (v > s.thr) {
-        sts64(s.cd + (uint32_t)s.ncand * kEnt, ((unsigned long long)f2ord(v) << 32) | (uint32_t)(~(uint32_t)gi));
-        ++s.ncand;
-    }
-}
 
+template <int LK>
 __global__ void __launch_bounds__(kHeadThreads, 1)
 k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW, const HeadParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -132,8 +122,7 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
     uint8_t *sB = sA + (size_t)kblocks * kBlkBytes;
-    unsigned long long *lkey = reinterpret_cast<unsigned long long *>(sB + (size_t)p.ring * kBlkBytes);   // [2][k][128]
-    unsigned long long *cand = lkey + (size_t)2 * p.k * kHeadTile;                                        // [2][cap][128]
+    unsigned long long *cand = reinterpret_cast<unsigned long long *>(sB + (size_t)p.ring * kBlkBytes);   // [2][cap][128]
 
     const int ntiles = ceil_div(p.V, kHeadTile);
     const int gs = gridDim.y;
@@ -215,14 +204,12 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
         const long long tloc = tgt - p.vocab_offset;
         const float st = row_ok ? p.st[row] : 0.f;
         const float st_prev = prev_float(st);
-        RowState s;
-        s.lk = smem_u32(lkey + (size_t)e * p.k * kHeadTile + r);
-        s.cd = smem_u32(cand + (size_t)e * kCandCap * kHeadTile + r);
-        s.k = p.k;
-        s.thr = -INFINITY;
-        s.ncand = 0;
-        s.cnt = 0;
-        for (int j = 0; j < p.k; ++j) sts64(s.lk + (uint32_t)j * kEnt, 0ull);
+        const uint32_t cd = smem_u32(cand + (size_t)e * kCandCap * kHeadTile + r);
+        unsigned long long list[LK];
+#pragma unroll
+        for (int j = 0; j < LK; ++j) list[j] = 0ull;
+        float thr = -INFINITY;
+        int ncand = 0, cnt = 0;
 
         for (int t = e; t < T; t += 2) {
             const int n = n_begin + t;
@@ -230,72 +217,102 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
             mbar_wait(&acc_full[e], (uint32_t)(t >> 1) & 1u);
             tc_fence_after();
             const bool partial = col_base + kHeadTile > p.V;
-            const bool has_tgt = tloc >= col_base && tloc < col_base + kHeadTile;
-            const float cmp = (tloc >= col_base + kHeadTile) ? st_prev : st;   // whole tile before / after the target
 #pragma unroll 1
             for (int c0 = 0; c0 < kHeadTile; c0 += 32) {
                 uint32_t acc[32];
+                float v[32];
+                const int cb = col_base + c0;
                 tmem_ld32(tmem + lane_off + (uint32_t)(e * kHeadTile + c0), acc);
+                // the bias words of this chunk (same address in every lane: one broadcast transaction each), in flight
+                // together with the TMEM read
+                if (p.bias && !partial) {
+                    const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + cb);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 x = __ldg(b4 + q);
+                        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) v[q] = (p.bias && cb + q < p.V) ? __ldg(p.bias + cb + q) : 0.f;
+                }
                 tmem_ld_wait();
                 if (c0 == kHeadTile - 32) {   // accumulator fully read: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[e]);
                 }
-                const int cb = col_base + c0;
-                if (partial || has_tgt || p.logits != nullptr) {
-                    // exact per-element path: vocabulary tail, the tile that holds this row's target, logits dump (tests)
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] += __uint_as_float(acc[q]);
+                if (partial) {                // vocabulary tail: columns >= V neither count nor qualify
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) v[q] = (cb + q < p.V) ? v[q] : -INFINITY;
+                }
+                if (p.logits != nullptr && row_ok) {     // logits dump (tests)
+#pragma unroll
+                    for (int q = 0; q < 32; ++q)
+                        if (cb + q < p.V) p.logits[(size_t)row * p.V + cb + q] = v[q];
+                }
+                // rank count: ONE compare per element.  Chunks entirely before the target compare against prev_float(s_t)
+                // (v >= s_t), the others against s_t; the chunk that holds the target fixes up its own leading columns.
+                const float cmp = (tloc >= cb + 32) ? st_prev : st;
+                if (tloc >= cb && tloc < cb + 32) {
 #pragma unroll
                     for (int q = 0; q < 32; ++q) {
-                        const int col = cb + q;
-                        if (col < p.V) {
-                            const float v = __uint_as_float(acc[q]) + (p.bias ? __ldg(p.bias + col) : 0.f);
-                            if (p.logits && row_ok) p.logits[(size_t)row * p.V + col] = v;
-                            if (col != tloc) s.cnt += (col < tloc) ? (v >= st) : (v > st);
-                            if (v > s.thr) candidate(s, v, p.vocab_offset + col);
+                        if (cb + q < tloc) cnt += (int)(v[q] == st);
+                        if (cb + q == tloc) cnt -= (int)(v[q] > st);      // the target itself never counts
+                    }
+                }
+                float m4[8];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const float v0 = v[4 * g], v1 = v[4 * g + 1], v2 = v[4 * g + 2], v3 = v[4 * g + 3];
+                    cnt += (int)(v0 > cmp) + (int)(v1 > cmp) + (int)(v2 > cmp) + (int)(v3 > cmp);
+                    m4[g] = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+                }
+                // harvest the top-k candidates of the chunk, group by group; a full buffer ends the pass, is drained (the
+                // single in-tile insertion site) and the pass resumes at the group it stopped at
+                int gdone = 0;
+                for (;;) {
+                    bool ovf = false;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        if (g >= gdone && !ovf && m4[g] > thr) {
+                            if (ncand > kCandCap - 4) {
+                                ovf = true;
+                                gdone = g;
+                            } else {
+                                const uint32_t gi = (uint32_t)(p.vocab_offset + cb + 4 * g);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    if (v[4 * g + i] > thr) {
+                                        sts64(cd + (uint32_t)ncand * kEnt,
+                                              ((unsigned long long)f2ord(v[4 * g + i]) << 32) | (uint32_t)(~(gi + (uint32_t)i)));
+                                        ++ncand;
+                                    }
+                                }
+                            }
                         }
                     }
-                } else {
-                    float b[32];
-                    if (p.bias) {
-                        const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + cb);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 x = __ldg(b4 + q);
-                            b[4 * q] = x.x; b[4 * q + 1] = x.y; b[4 * q + 2] = x.z; b[4 * q + 3] = x.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) b[q] = 0.f;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 32; q += 4) {
-                        const float v0 = __uint_as_float(acc[q]) + b[q], v1 = __uint_as_float(acc[q + 1]) + b[q + 1];
-                        const float v2 = __uint_as_float(acc[q + 2]) + b[q + 2], v3 = __uint_as_float(acc[q + 3]) + b[q + 3];
-                        s.cnt += (int)(v0 > cmp) + (int)(v1 > cmp) + (int)(v2 > cmp) + (int)(v3 > cmp);
-                        const float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
-                        if (m > s.thr) {
-                            const long long g0 = p.vocab_offset + cb + q;
-                            if (v0 > s.thr) candidate(s, v0, g0);
-                            if (v1 > s.thr) candidate(s, v1, g0 + 1);
-                            if (v2 > s.thr) candidate(s, v2, g0 + 2);
-                            if (v3 > s.thr) candidate(s, v3, g0 + 3);
-                        }
-                    }
+                    if (!ovf) break;
+                    thr = list_drain<LK>(list, cd, ncand);
                 }
                 __syncwarp();     // tcgen05.ld is warp-collective: reconverge before the next chunk
             }
-            drain(s);             // all lanes together: lane-aligned insertion, fresh threshold for the next tile
+            thr = list_drain<LK>(list, cd, ncand);   // all lanes together; fresh threshold for the next tile
             __syncwarp();
         }
         if (row_ok) {
             const size_t o = (size_t)row * p.nsplit + (size_t)sp * 2 + e;
-            for (int j = 0; j < p.k; ++j) {
-                const unsigned long long key = lds64(s.lk + (uint32_t)j * kEnt);
-                p.topk_val[o * p.k + j] = key ? ord2f((uint32_t)(key >> 32)) : -INFINITY;
-                p.topk_idx[o * p.k + j] = key ? (int32_t)(~(uint32_t)key) : -1;
+#pragma unroll
+            for (int j = 0; j < LK; ++j) {
+                if (j < p.k) {
+                    const unsigned long long key = list[j];
+                    p.topk_val[o * p.k + j] = key ? ord2f((uint32_t)(key >> 32)) : -INFINITY;
+                    p.topk_idx[o * p.k + j] = key ? (int32_t)(~(uint32_t)key) : -1;
+                }
             }
-            p.cnt_gt[o] = s.cnt;
+            p.cnt_gt[o] = cnt;
             p.cnt_eq[o] = 0;
         }
     }
@@ -385,34 +402,52 @@ k5_target_logit_kernel(const __grid_constant__ CUtensorMap tmZ, const TargetPara
     if (warp == 0) tmem_dealloc<128>(tmem);
 }
 
-// Merge S sorted (descending, ties -> lower index first) candidate lists per row and add the rank counts.
-__global__ void k5_topk_merge_kernel(const float *__restrict__ val, const int32_t *__restrict__ idx,
-                                     const int32_t *__restrict__ cgt, const int32_t *__restrict__ ceq, int M, int S, int k,
-                                     float *__restrict__ oval, int32_t *__restrict__ oidx, int32_t *__restrict__ rank) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+// Merge S sorted candidate lists per row (descending, ties -> lower index first) and add the rank counts.
+// One WARP per row: the S*k candidates are packed into 64-bit keys (order-preserving value bits | ~index) in shared memory;
+// k rounds of "every lane scans its strided share for its best key, warp arg-max, the winner's slot is cleared".
+constexpr int kMergeWarps = 4;
+__global__ void __launch_bounds__(kMergeWarps * 32)
+k5_topk_merge_kernel(const float *__restrict__ val, const int32_t *__restrict__ idx, const int32_t *__restrict__ cgt,
+                     const int32_t *__restrict__ ceq, int M, int S, int k, float *__restrict__ oval,
+                     int32_t *__restrict__ oidx, int32_t *__restrict__ rank) {
+    extern __shared__ __align__(8) unsigned long long mkeys[];      // [kMergeWarps][S*k]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * kMergeWarps + warp;
     if (r >= M) return;
-    int head[64];
-    for (int s = 0; s < S; ++s) head[s] = 0;
+    const int n = S * k;
+    unsigned long long *keys = mkeys + (size_t)warp * n;
+    for (int i = lane; i < n; i += 32) {
+        const size_t o = (size_t)r * n + i;
+        const int id = idx[o];
+        keys[i] = id < 0 ? 0ull : (((unsigned long long)f2ord(val[o]) << 32) | (uint32_t)(~(uint32_t)id));
+    }
+    __syncwarp();
     for (int j = 0; j < k; ++j) {
-        int best = -1;
-        float bv = -INFINITY;
-        int bi = 0x7fffffff;
-        for (int s = 0; s < S; ++s) {
-            if (head[s] >= k) continue;
-            const size_t o = ((size_t)r * S + s) * k + head[s];
-            const float v = val[o];
-            const int i = idx[o];
-            if (i < 0) continue;
-            if (best < 0 || v > bv || (v == bv && i < bi)) { best = s; bv = v; bi = i; }
+        unsigned long long best = 0ull;
+        int bi = -1;
+        for (int i = lane; i < n; i += 32) {
+            const unsigned long long x = keys[i];
+            if (x > best) { best = x; bi = i; }
         }
-        oval[(size_t)r * k + j] = best >= 0 ? bv : -INFINITY;
-        oidx[(size_t)r * k + j] = best >= 0 ? bi : -1;
-        if (best >= 0) ++head[best];
+        unsigned long long wb = best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long y = __shfl_xor_sync(0xffffffffu, wb, o);
+            wb = y > wb ? y : wb;
+        }
+        if (wb != 0ull && best == wb) keys[bi] = 0ull;       // keys are unique (distinct vocabulary indices)
+        if (lane == 0) {
+            oval[(size_t)r * k + j] = wb ? ord2f((uint32_t)(wb >> 32)) : -INFINITY;
+            oidx[(size_t)r * k + j] = wb ? (int32_t)(~(uint32_t)wb) : -1;
+        }
+        __syncwarp();
     }
     if (rank) {
         int rk = 0;
-        for (int s = 0; s < S; ++s) rk += cgt[(size_t)r * S + s] + ceq[(size_t)r * S + s];
-        rank[r] = rk;
+        for (int s = lane; s < S; s += 32) rk += cgt[(size_t)r * S + s] + ceq[(size_t)r * S + s];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rk += __shfl_xor_sync(0xffffffffu, rk, o);
+        if (lane == 0) rank[r] = rk;
     }
 }
 
@@ -455,15 +490,23 @@ extern "C" int32_t mobgt_head_topk(const void *z, const void *W, const float *bi
     }
     rc = encode_rows_sw128(&tmW, W, V, K);
     if (rc) return rc;
-    const size_t fixed = (size_t)kblocks * kBlkBytes + (size_t)2 * (k + kCandCap) * kHeadTile * 8 + 1024;
+    const size_t fixed = (size_t)kblocks * kBlkBytes + (size_t)2 * kCandCap * kHeadTile * 8 + 1024;
     int ring = (int)((227 * 1024 - 512 - (long long)fixed) / kBlkBytes);
     ring = ring > kMaxRing ? kMaxRing : ring;
     MOBGT_REQUIRE(ring >= 2, MOBGT_ERR_UNSUPPORTED, "mobgt_head_topk: no shared-memory plan for K=%d k=%d", K, k);
     const size_t smem = fixed + (size_t)ring * kBlkBytes;
-    MOBGT_CUDA_OK(cudaFuncSetAttribute(k5_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     HeadParams p{bias, target, st, topk_val, topk_idx, cnt_gt, cnt_eq, logits_dump, M, V, K, k, nsplit, mode, ring, vocab_offset};
     dim3 grid((unsigned)ceil_div(M, kHeadTile), (unsigned)(nsplit / 2));
-    k5_head_kernel<<<grid, kHeadThreads, smem, s>>>(tmZ, tmW, p);
+    // the list length is a compile-time constant (register-resident list): the smallest built size >= k
+    auto launch = [&](auto kern) -> int32_t {
+        MOBGT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kHeadThreads, smem, s>>>(tmZ, tmW, p);
+        return MOBGT_OK;
+    };
+    if (k <= 10) rc = launch(k5_head_kernel<10>);
+    else if (k <= 20) rc = launch(k5_head_kernel<20>);
+    else rc = launch(k5_head_kernel<32>);
+    if (rc) return rc;
     MOBGT_LAUNCH_OK("k5_head_kernel");
     return MOBGT_OK;
 }
@@ -475,8 +518,10 @@ extern "C" int32_t mobgt_topk_merge(const float *val, const int32_t *idx, const 
     MOBGT_REQUIRE(!rank || (cnt_gt && cnt_eq), MOBGT_ERR_NULL, "mobgt_topk_merge: rank needs the counts");
     MOBGT_REQUIRE(S >= 1 && S <= 64 && k >= 1 && k <= kHeadMaxTop, MOBGT_ERR_BAD_SHAPE, "mobgt_topk_merge: S=%d k=%d", S, k);
     if (M <= 0) return MOBGT_OK;
-    k5_topk_merge_kernel<<<ceil_div(M, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(val, idx, cnt_gt, cnt_eq, M, S, k, out_val,
-                                                                                         out_idx, rank);
+    const size_t smem = (size_t)kMergeWarps * S * k * sizeof(unsigned long long);
+    MOBGT_CUDA_OK(cudaFuncSetAttribute(k5_topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k5_topk_merge_kernel<<<ceil_div(M, kMergeWarps), kMergeWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+        val, idx, cnt_gt, cnt_eq, M, S, k, out_val, out_idx, rank);
     MOBGT_LAUNCH_OK("k5_topk_merge_kernel");
     return MOBGT_OK;
 }

@@ -32,7 +32,10 @@ def bias_fwd_raw(batch, R, Ppos, E, W, tvd, out_dtype=torch.bfloat16, T=None, Tp
     Tp = Tp or bias_pitch(T)
     dev = R.device
     out = torch.empty(B, H, T, Tp, dtype=out_dtype, device=dev)
-    ws = torch.empty(batch.hops * 128 * H, dtype=torch.float32, device=dev)
+    ws_bytes = int(_C.lib().mobgt_bias_fwd_workspace_bytes(batch.hops, H))
+    if ws_bytes < 0:
+        raise _C.MobgtError(f"mobgt_bias_fwd_workspace_bytes rejected hops={batch.hops} H={H}")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     _C.call("mobgt_bias_fwd", _C.ptr(batch.n), _C.ptr(batch.sq_off), _C.ptr(batch.rel_pos16), _C.ptr(batch.poi_pos16),
             _C.ptr(batch.edge_in8), B, T, Tp, batch.hops, H, batch.rel_pos_max, int(Ppos.shape[0]), _C.ptr(R), _C.ptr(Ppos),
             _C.ptr(E), _C.ptr(W), _C.ptr(tvd), _C.ptr(ws), _C.ptr(out), _dt(out), _C.stream_ptr())

@@ -18,6 +18,18 @@ for name, M, V, k in (("c2", 256, 60001, 10), ("c5_shard", 4096, 125000, 10), ("
     st = ops.head_target_logit(z, W, b, tgt)
     t1 = bench.time_kernel(lambda: ops.head_topk_local(z, W, b, tgt, k, st=st), flush, iters=6)
     t0 = bench.time_kernel(lambda: ops.head_target_logit(z, W, b, tgt), flush, iters=6)
+    # the two launches of mode 1 apart, on preallocated buffers (no allocator / host time between the events)
+    from mobgt_b200 import _C
+    ns = ops.head_split(M, V)
+    tv = torch.empty(M, ns, k, dtype=torch.float32, device=dev); ti = torch.empty(M, ns, k, dtype=torch.int32, device=dev)
+    cg = torch.empty(M, ns, dtype=torch.int32, device=dev); ce = torch.empty(M, ns, dtype=torch.int32, device=dev)
+    ov = torch.empty(M, k, dtype=torch.float32, device=dev); oi = torch.empty(M, k, dtype=torch.int32, device=dev)
+    rk = torch.empty(M, dtype=torch.int32, device=dev)
+    sp = _C.stream_ptr()
+    th = bench.time_kernel(lambda: _C.call("mobgt_head_topk", _C.ptr(z), _C.ptr(W), _C.ptr(b), _C.ptr(tgt), M, V, 320, 0, k, ns, 1,
+                                           _C.ptr(st), _C.ptr(tv), _C.ptr(ti), _C.ptr(cg), _C.ptr(ce), None, sp), flush, iters=6)
+    tm = bench.time_kernel(lambda: _C.call("mobgt_topk_merge", _C.ptr(tv), _C.ptr(ti), _C.ptr(cg), _C.ptr(ce), M, ns, k,
+                                           _C.ptr(ov), _C.ptr(oi), _C.ptr(rk), sp), flush, iters=6)
     fl = 2.0 * M * 320 * V
     print(f"{name:14s} M={M} V={V} k={k} nsplit={ops.head_split(M, V)}: mode1+merge {t1*1e3:8.1f} us = {fl/t1/1e9:7.1f} TF/s "
-          f"({100*fl/t1/1e9/pk['tc']:.1f}% of bf16 peak) ; mode0 {t0*1e3:7.1f} us")
+          f"({100*fl/t1/1e9/pk['tc']:.1f}% of bf16 peak) ; mode0 {t0*1e3:7.1f} us ; head kernel alone {th*1e3:8.1f} us = {fl/th/1e9:7.1f} TF/s ({100*fl/th/1e9/pk['tc']:.1f}%) ; merge alone {tm*1e3:6.1f} us")
