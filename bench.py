@@ -306,9 +306,20 @@ def run_ours(args):
     # end to end: host items -> collate (H2D + K1) -> step -> loss on the host, every step
     losses = []
 
+    def endless():
+        while True:
+            yield items
+
+    # one-batch-ahead loader (the reference's DataLoader-worker role): the host packing + H2D + K1 of batch i+1 are issued
+    # right after the kernels of step i have been enqueued, so they overlap its GPU time; every timed step still contains
+    # exactly one collate (pack + pinned H2D + K1 + poi_pos), one training step and one D2H read of the loss
+    loader = collator.PackedLoader(endless(), lambda it: collator.collate_packed(it, world, latlon, 512, 20, 1024, device=dev))
+
     def e2e_step():
-        b = collate()
-        losses.append(float(train_step(b).item()))
+        b = loader.current()
+        loss = train_step(b)
+        loader.advance()
+        losses.append(float(loss.item()))
         return b
 
     for _ in range(max(1, args.warmup // 2)):

@@ -24,6 +24,85 @@ def _to_np(a, dtype=None):
     return a.astype(dtype) if dtype is not None else a
 
 
+class _Staging:
+    """Two pinned host buffers used in turn: a buffer is reused only after the copy that read it has completed."""
+
+    def __init__(self):
+        self.slots = [None, None]
+        self.events = [None, None]
+        self.turn = 0
+
+    def get(self, nbytes):
+        i = self.turn
+        self.turn ^= 1
+        if self.events[i] is not None:
+            self.events[i].synchronize()
+        if self.slots[i] is None or self.slots[i].numel() < nbytes:
+            self.slots[i] = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8).pin_memory()
+        return i, self.slots[i]
+
+    def mark(self, i):
+        self.events[i] = torch.cuda.Event()
+        self.events[i].record()
+
+
+_staging = {}
+
+
+def _upload(host, dev):
+    """host: name -> numpy array.  One pinned buffer, one async H2D copy; returns name -> device tensor views."""
+    offs, total = {}, 0
+    for k, a in host.items():
+        a = np.ascontiguousarray(a)
+        host[k] = a
+        offs[k] = total
+        total += (a.nbytes + 15) // 16 * 16
+    st = _staging.setdefault(str(dev), _Staging())
+    slot, pinned = st.get(total)
+    pn = pinned.numpy()
+    for k, a in host.items():
+        pn[offs[k]:offs[k] + a.nbytes] = a.reshape(-1).view(np.uint8)
+    dbuf = torch.empty(max(total, 16), dtype=torch.uint8, device=dev)
+    dbuf[:total].copy_(pinned[:total], non_blocking=True)
+    st.mark(slot)
+    out = {}
+    for k, a in host.items():
+        t = dbuf[offs[k]:offs[k] + a.nbytes].view(torch.from_numpy(a[:0].reshape(-1)).dtype)
+        out[k] = t.view(a.shape)
+    return out
+
+
+class PackedLoader:
+    """One-batch-ahead collation (the role of the reference's DataLoader workers, data.py:255-267): `next()` hands out the
+    batch whose host packing, H2D copy and K1 / poi_pos kernels were issued during the PREVIOUS call, then collates the
+    following one — while the GPU is still busy with the caller's training step.  `batches` is an iterator of item lists."""
+
+    def __init__(self, batches, collate_fn):
+        self._it = iter(batches)
+        self._collate = collate_fn
+        self._next = self._pull()
+
+    def _pull(self):
+        try:
+            return self._collate(next(self._it))
+        except StopIteration:
+            return None
+
+    def current(self):
+        return self._next
+
+    def advance(self):
+        """Collate the following batch (call it right after the step's kernels have been enqueued)."""
+        self._next = self._pull()
+
+    def __iter__(self):
+        while self._next is not None:
+            b = self._next
+            yield b
+            if self._next is b:       # the consumer did not call advance() itself
+                self.advance()
+
+
 class Batch1:
     """Same public surface as collator.py:149-215 (attributes, .to(device), len()); packed storage inside."""
 
@@ -176,17 +255,16 @@ def collate_packed(items, world=None, latlon_dev=None, max_node=512, multi_hop_m
     tok_graph[tok_off[:-1]] = np.arange(B)
 
     dev = torch.device(device)
-
-    def up(a):
-        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().to(dev, non_blocking=True)
-
-    b = Batch1(
-        B=B, N=int(ns.max()) if B else 0, hops=int(multi_hop_max_dist), rel_pos_max=int(rel_pos_max), n_host=ns,
-        n=up(ns), sq_off=up(sq), node_off=up(no), tok_off=up(tok_off), tok_graph=up(tok_graph), tok_pos=up(tok_pos),
-        feat8=up(feat), x_nodes=up(x_nodes), slot=up(slot), time_nodes=up(time_nodes), time_normal_nodes=up(tn),
-        cat_nodes=up(cat_nodes), in_deg=up(indeg + 1), out_deg=up(outdeg + 1),       # pad_1d_unsqueeze "+1" (collator.py:12)
-        user=up(user), y=up(y), idx=up(idx), h2d_bytes=0)
-    b.h2d_bytes = int(sum(v.numel() * v.element_size() for v in b.__dict__.values() if isinstance(v, torch.Tensor)))
+    # ONE pinned staging buffer and ONE host->device copy for all host-packed arrays (17 small pin_memory() allocations and
+    # copies cost more than the transfer itself); the device tensors below are typed views into the single device buffer
+    host = dict(n=ns, sq_off=sq, node_off=no, tok_off=tok_off, tok_graph=tok_graph, tok_pos=tok_pos, feat8=feat,
+                x_nodes=x_nodes, slot=slot, time_nodes=time_nodes, time_normal_nodes=tn, cat_nodes=cat_nodes,
+                in_deg=indeg + 1, out_deg=outdeg + 1,                          # pad_1d_unsqueeze "+1" (collator.py:12)
+                user=user, y=y, idx=idx)
+    views = _upload(host, dev)
+    b = Batch1(B=B, N=int(ns.max()) if B else 0, hops=int(multi_hop_max_dist), rel_pos_max=int(rel_pos_max), n_host=ns,
+               h2d_bytes=0, **views)
+    b.h2d_bytes = int(sum(v.numel() * v.element_size() for v in views.values()))
     k1 = apsp_edge_input_packed(b.feat8, b.n, b.sq_off, ns, hops=int(multi_hop_max_dist), shift=1, want_path=want_path)
     b.rel_pos16, b.edge_in8, b.maxdist, b.path16 = k1["dist"], k1["edge_in"], k1["maxdist"], k1["path"]
     b.poi_pos16 = torch.empty(cells, dtype=torch.int16, device=dev)

@@ -117,21 +117,26 @@ __device__ __forceinline__ uint32_t expected_word(int L, int q) {
 }
 
 // Forward.  Persistent CTAs; RL [512][8], Ppos [bins][8] and the expected-walk words XW [hops+1][8] are staged once per
-// CTA in shared memory.  One thread per PAIR OF ADJACENT CELLS (a, b) (a, b+1), b even, of the Tp-pitched plane row, so
+// CTA in shared memory.  A tile is 512 threads x 2 adjacent cells (a, b) (a, b+1), b even, of the Tp-pitched plane row, so
 // every head plane is written as 4-byte (bf16x2) / 8-byte (f32x2) words and a warp covers 64 consecutive columns.  All
 // index bytes of a thread's two cells (2 x (2 + 2 + hops) B) are fetched up front as independent loads.
 //
-// Per cell the work is TWO table gathers: bias = RL[rp] + Ppos[pp].  The walk bytes are only compared (XOR) against the
-// walk the distance predicts; the bytes that differ — another edge feature (0.7 % of the hops of trajectory graphs) or a
-// walk cut short by the reference's node-0 quirk (algos.pyx:57-62) — are corrected one by one from the EW table in
-// global memory (L1-resident):   Edge = sum_k EW[k][e_k]  =  PS[L] + sum_{k : e_k != x_k} ( EW[k][e_k] - EW[k][x_k] ).
-// The identity holds for ANY byte pattern (EW[k][0] = 0: edge_encoder row 0 is the padding row, model_fqandtoyo.py:784).
+// Phase A (thread = 2 cells, 8 heads): bias = RL[rp] + Ppos[pp] — TWO table gathers per cell.  The walk bytes are only
+// compared (XOR) against the walk the distance predicts; a cell whose bytes differ — another edge feature (0.7 % of the
+// hops of trajectory graphs) or a walk cut short by the reference's node-0 quirk (algos.pyx:57-62) — is appended to a
+// shared-memory list (6 % of the cells).
+// Phase B (8 lanes = 8 heads per listed cell, 64 cells at a time): the differing bytes are corrected from the EW table
+//   Edge = sum_k EW[k][e_k]  =  PS[L] + sum_{k : e_k != x_k} ( EW[k][e_k] - EW[k][x_k] )
+// and the cell's 8 outputs are rewritten.  The identity holds for ANY byte pattern (EW[k][0] = 0: edge_encoder row 0 is
+// the padding row, model_fqandtoyo.py:784).  Keeping the corrections out of phase A keeps its warps convergent.
 template <typename OutT, int HOPW>
 __global__ void __launch_bounds__(512, 2) k2_bias_fwd_kernel(const K2Common c, const float *__restrict__ RLg,
                                                              const float *__restrict__ Pg, int num_bins,
                                                              const float *__restrict__ tvd,
                                                              const float *__restrict__ EWg, OutT *__restrict__ out) {
     extern __shared__ __align__(16) float sm[];
+    __shared__ int dcount[3];
+    __shared__ uint16_t dlist[3][1024];
     const int nR = kRelRows * kH, nP = num_bins * kH;
     float *RL = sm, *Pp = RL + nR;
     uint32_t *XW = reinterpret_cast<uint32_t *>(Pp + nP);          // [hops + 1][8]
@@ -141,304 +146,410 @@ __global__ void __launch_bounds__(512, 2) k2_bias_fwd_kernel(const K2Common c, c
         *reinterpret_cast<float4 *>(Pp + i) = *reinterpret_cast<const float4 *>(Pg + i);
     constexpr int hopw = HOPW;                    // hops = 4 * HOPW
     for (int i = threadIdx.x; i < (c.hops + 1) * 8; i += blockDim.x) XW[i] = (i & 7) < hopw ? expected_word(i >> 3, i & 7) : 0u;
-    float tv[8];
-#pragma unroll
-    for (int h = 0; h < 8; ++h) tv[h] = tvd[h];
+    if (threadIdx.x < 3) dcount[threadIdx.x] = 0;
     __syncthreads();
     const int half = c.Tp >> 1;                   // cell pairs per plane row
     const int per_graph = c.T * half;
     const int tiles = ceil_div(per_graph, (int)blockDim.x);
+    const uint64_t half_magic = ((1ull << 40) + half - 1) / half;     // f / half == (f * magic) >> 40 for f < 2^18
     const size_t hs = (size_t)c.T * c.Tp;
-    for (int w = blockIdx.x; w < tiles * c.B; w += gridDim.x) {
+    int it = 0;
+    for (int w = blockIdx.x; w < tiles * c.B; w += gridDim.x, ++it) {
+        const int buf = it % 3;
         const int g = w / tiles, tile = w - g * tiles;
         const int n = c.n[g];
         const int Tg = n + 1;
-        const int f = tile * blockDim.x + threadIdx.x;
-        const int a = f / half, b = (f - a * half) * 2;
-        if (a >= Tg || b >= Tg) continue;
-        const bool two = b + 1 < Tg;
-        float acc[2][8];
+        const int64_t sq = c.sq_off[g];
+        if (threadIdx.x == 0) dcount[(it + 1) % 3] = 0;      // the list of the next tile (last read two tiles ago)
+        {
+            const int f = tile * blockDim.x + threadIdx.x;
+            const int a = (int)(((uint64_t)f * half_magic) >> 40), b = (f - a * half) * 2;
+            if (a < Tg && b < Tg) {
+                const bool two = b + 1 < Tg;
+                float acc[2][8];
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
+                for (int s = 0; s < 2; ++s)
 #pragma unroll
-            for (int h = 0; h < 8; ++h) acc[s][h] = 0.f;
-        if (a >= 1) {
-            const int64_t rowp = c.sq_off[g] + (int64_t)(a - 1) * n;   // pair (a-1, j) lives at rowp + j
-            // cell s of this thread is the pair j = b - 1 + s  (b == 0, s == 0: the virtual-distance column)
-            int rp[2], pp[2];
-            uint32_t ew[2][HOPW];
-            bool is_pair[2];
+                    for (int h = 0; h < 8; ++h) acc[s][h] = 0.f;
+                if (a >= 1) {
+                    const int64_t rowp = sq + (int64_t)(a - 1) * n;   // pair (a-1, j) lives at rowp + j
+                    // cell s of this thread is the pair j = b - 1 + s  (b == 0, s == 0: the virtual-distance column)
+                    int rp[2], pp[2];
+                    uint32_t ew[2][HOPW];
+                    bool is_pair[2];
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int j = b - 1 + s;
-                is_pair[s] = j >= 0 && j < n;
-                rp[s] = 0; pp[s] = 0;
+                    for (int s = 0; s < 2; ++s) {
+                        const int j = b - 1 + s;
+                        is_pair[s] = j >= 0 && j < n;
+                        rp[s] = 0; pp[s] = 0;
 #pragma unroll
-                for (int q = 0; q < HOPW; ++q) ew[s][q] = 0u;
-                if (is_pair[s]) {
-                    const int64_t pc = rowp + j;
-                    rp[s] = c.rel_pos[pc];
-                    pp[s] = c.poi_pos[pc];
-                    const uint32_t *ei = reinterpret_cast<const uint32_t *>(c.edge_in + pc * c.hops);
+                        for (int q = 0; q < HOPW; ++q) ew[s][q] = 0u;
+                        if (is_pair[s]) {
+                            const int64_t pc = rowp + j;
+                            rp[s] = c.rel_pos[pc];
+                            pp[s] = c.poi_pos[pc];
+                            const uint32_t *ei = reinterpret_cast<const uint32_t *>(c.edge_in + pc * c.hops);
 #pragma unroll
-                    for (int q = 0; q < HOPW; ++q) ew[s][q] = __ldg(ei + q);
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                if (!is_pair[s]) {
-                    if (b == 0 && s == 0) {
-#pragma unroll
-                        for (int h = 0; h < 8; ++h) acc[0][h] = tv[h];
-                    }
-                    continue;
-                }
-                const int rk = min(max(rp[s], 0), kRelRows - 1);
-                const int L = expected_walk(rk, c.hops);
-                const uint4 x0 = *reinterpret_cast<const uint4 *>(XW + L * 8), x1 = *reinterpret_cast<const uint4 *>(XW + L * 8 + 4);
-                const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-                uint32_t any = 0u;
-#pragma unroll
-                for (int q = 0; q < HOPW; ++q) any |= ew[s][q] ^ xw[q];
-                const float *r = RL + rk * kH, *q_ = Pp + min(max(pp[s], 0), num_bins - 1) * kH;
-                const float4 r0 = *reinterpret_cast<const float4 *>(r), r1 = *reinterpret_cast<const float4 *>(r + 4);
-                const float4 p0 = *reinterpret_cast<const float4 *>(q_), p1 = *reinterpret_cast<const float4 *>(q_ + 4);
-                acc[s][0] = r0.x + p0.x; acc[s][1] = r0.y + p0.y; acc[s][2] = r0.z + p0.z; acc[s][3] = r0.w + p0.w;
-                acc[s][4] = r1.x + p1.x; acc[s][5] = r1.y + p1.y; acc[s][6] = r1.z + p1.z; acc[s][7] = r1.w + p1.w;
-                if (any != 0u) {
-                    float corr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int q = 0; q < HOPW; ++q) {
-                        {
-                            uint32_t d = ew[s][q] ^ xw[q];
-                            while (d != 0u) {
-                                const int e = (__ffs(d) - 1) >> 3;
-                                const int v = (ew[s][q] >> (8 * e)) & 0xFF, x = (xw[q] >> (8 * e)) & 0xFF;
-                                const float *row = EWg + (size_t)(q * 4 + e) * kEdgeVocab * kH;
-                                add8(corr, row + min(v, kEdgeVocab - 1) * kH);
-                                sub8(corr, row + x * kH);
-                                d &= ~(0xFFu << (8 * e));
-                            }
+                            for (int q = 0; q < HOPW; ++q) ew[s][q] = __ldg(ei + q);
                         }
                     }
-                    const float inv = 1.0f / (float)min(max(rk - 1, 1), c.hops);
 #pragma unroll
-                    for (int h = 0; h < 8; ++h) acc[s][h] += corr[h] * inv;
+                    for (int s = 0; s < 2; ++s) {
+                        if (!is_pair[s]) {
+                            if (b == 0 && s == 0) {
+#pragma unroll
+                                for (int h = 0; h < 8; ++h) acc[0][h] = __ldg(tvd + h);
+                            }
+                            continue;
+                        }
+                        const int rk = min(max(rp[s], 0), kRelRows - 1);
+                        const int L = expected_walk(rk, c.hops);
+                        const uint4 x0 = *reinterpret_cast<const uint4 *>(XW + L * 8), x1 = *reinterpret_cast<const uint4 *>(XW + L * 8 + 4);
+                        const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                        uint32_t any = 0u;
+#pragma unroll
+                        for (int q = 0; q < HOPW; ++q) any |= ew[s][q] ^ xw[q];
+                        const float *r = RL + rk * kH, *q_ = Pp + min(max(pp[s], 0), num_bins - 1) * kH;
+                        const float4 r0 = *reinterpret_cast<const float4 *>(r), r1 = *reinterpret_cast<const float4 *>(r + 4);
+                        const float4 p0 = *reinterpret_cast<const float4 *>(q_), p1 = *reinterpret_cast<const float4 *>(q_ + 4);
+                        acc[s][0] = r0.x + p0.x; acc[s][1] = r0.y + p0.y; acc[s][2] = r0.z + p0.z; acc[s][3] = r0.w + p0.w;
+                        acc[s][4] = r1.x + p1.x; acc[s][5] = r1.y + p1.y; acc[s][6] = r1.z + p1.z; acc[s][7] = r1.w + p1.w;
+                        if (any != 0u) dlist[buf][atomicAdd(&dcount[buf], 1)] = (uint16_t)(threadIdx.x * 2 + s);
+                    }
+                }
+                OutT *o = out + ((size_t)g * kH * c.T + a) * c.Tp + b;
+                if (two) {
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) store2<OutT>(o + h * hs, acc[0][h], acc[1][h]);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) store1<OutT>(o + h * hs, acc[0][h]);
                 }
             }
         }
-        OutT *o = out + ((size_t)g * kH * c.T + a) * c.Tp + b;
-        if (two) {
+        __syncthreads();
+        // ---- phase B: the listed cells, 8 lanes (heads) each
+        const int cnt = dcount[buf];
+        const int h = threadIdx.x & 7;
+        for (int e = threadIdx.x >> 3; e < cnt; e += (int)blockDim.x >> 3) {
+            const int code = dlist[buf][e];
+            const int f = tile * blockDim.x + (code >> 1), s = code & 1;
+            const int a = (int)(((uint64_t)f * half_magic) >> 40), b = (f - a * half) * 2;
+            const int j = b - 1 + s;
+            const int64_t pc = sq + (int64_t)(a - 1) * n + j;
+            const int rk = min(max((int)c.rel_pos[pc], 0), kRelRows - 1);
+            const int pk = min(max((int)c.poi_pos[pc], 0), num_bins - 1);
+            const int L = expected_walk(rk, c.hops);
+            const uint32_t *ei = reinterpret_cast<const uint32_t *>(c.edge_in + pc * c.hops);
+            float corr = 0.f;
 #pragma unroll
-            for (int h = 0; h < 8; ++h) store2<OutT>(o + h * hs, acc[0][h], acc[1][h]);
-        } else {
-#pragma unroll
-            for (int h = 0; h < 8; ++h) store1<OutT>(o + h * hs, acc[0][h]);
+            for (int q = 0; q < HOPW; ++q) {
+                const uint32_t ewq = __ldg(ei + q), xwq = XW[L * 8 + q];
+                uint32_t d = ewq ^ xwq;
+                while (d != 0u) {
+                    const int eb = (__ffs(d) - 1) >> 3;
+                    const int v = (ewq >> (8 * eb)) & 0xFF, x = (xwq >> (8 * eb)) & 0xFF;
+                    const float *row = EWg + (size_t)(q * 4 + eb) * kEdgeVocab * kH + h;
+                    corr += __ldg(row + min(v, kEdgeVocab - 1) * kH) - __ldg(row + x * kH);
+                    d &= ~(0xFFu << (8 * eb));
+                }
+            }
+            const float inv = 1.0f / (float)min(max(rk - 1, 1), c.hops);
+            const float val = (RL[rk * kH + h] + Pp[pk * kH + h]) + corr * inv;
+            store1<OutT>(out + ((size_t)(g * kH + h) * c.T + a) * c.Tp + b + s, val);
         }
     }
 }
 
 // ---- backward --------------------------------------------------------------------------------------
-// dBias (fp32, summed over layers) -> table gradients.  Every cell contributes its 8-vector d[h] to
-//   dt (column 0), dR[rp], dPpos[pp] and dEW[k][ei[k]] * 1/sp for every hop k of its walk:
-// 22 keyed adds whose keys are heavily duplicated (one distance / one edge feature dominates), and shared-memory fp32
-// atomicAdd is a compare-and-swap loop (ATOMS.CAST.SPIN) that serialises on equal addresses.  So the main path uses
-// NO atomics:
-//   * lanes = (4 cells) x (8 heads): lane (p4, h) owns head h of cell p4 of the current group, so one keyed add is a
-//     plain LDS / FADD / STS of 8 consecutive floats per cell, into WARP-PRIVATE histograms;
-//   * the poi_pos and walk histograms are replicated per p4 (no two lanes ever share an address); the rel_pos histogram
-//     is updated in 4 lock-step turns (one p4 per turn);
-//   * the 20 hop adds of a walk collapse into ONE: the cell is added to A[L] (L = walk length) as if every hop carried
-//     the dominant edge feature (kDomEdge: "one transition", by far the most common); only the hops with another
-//     feature are visited: N[k] += d (warp-private) and dEW[k][v] += d (shared-memory atomic into the CTA's dEW
-//     histogram, low contention), and the finish resolves dEW[k][dom] += sum_{L > k} A[L] - N[k].
-// Per-CTA totals go to a partial buffer in the workspace and are reduced in a fixed order by the finish kernels
-// (reproducible except for the rare-path atomics).
+// dBias (per-layer bf16 dS planes, or one fp32 buffer) -> table gradients.  With the forward's decomposition
+//   bias(cell) = RL[rp] + Ppos[pp] + ( sum over the bytes that deviate from the expected walk ) / sp
+// every cell contributes its 8-vector d[h] to exactly TWO keyed sums, dRL[rp] and dPpos[pp] (plus dt for column 0); only
+// the deviating bytes (0.09 per cell on trajectory graphs) touch dEW directly.  The finish kernels unfold dRL:
+//   dR[rp] = dRL[rp] ;   dEW[k][dom] += sum_{rp : L(rp) > k} dRL[rp] / sp(rp).
+// One WARP per plane row (g, a), 1 persistent CTA per SM, three phases per row:
+//   1. sum phase   — the row of every (layer, head) plane is read with 16-byte loads (lane = 8-cell chunk of one head, all
+//                    layers in flight together), summed in fp32 and parked in the warp's shared-memory strip dsum[h][b];
+//   2. index phase — lane = cell: rel_pos, poi_pos and the walk words are read once and packed into cinfo[b] (histogram
+//                    rows + flags) and cdev[b] (up to two deviating bytes, so the histogram phase never touches global
+//                    memory);
+//   3. histogram   — lanes = (table: R | P) x (2 cells) x (8 heads): ONE read-modify-write per lane and step into
+//                    warp-private histograms laid out [key][cell slot][head] — no atomics, no cross-lane hazards; two
+//                    steps are in flight per lane (equal keys are merged in registers).
+//   Deviating bytes: shared-memory atomics into the CTA's small dEW table (features < 16), global atomics otherwise.
+// Per-CTA totals go to a partial buffer and are reduced in a fixed order (reproducible except for the rare-path atomics).
+constexpr int kSmallVocab = 16;   // edge features kept in the CTA's shared dEW table
 
 struct K2BwdPlan {
     int Rrows;      // rel_pos histogram rows: keys 0..Rrows-2 direct, key 511 -> row Rrows-1
-    int nEW, nR, nP, nA, nN, stride;   // floats; partial row = [EW | R | P | A | N | t(8)]
+    int nEWs, nR, nP, stride;   // floats; partial row = [EWsmall | R | P | t(8)]
+    int pitch;      // floats per head in the dsum strip: >= Tp, == 4 (mod 32)
+    int per_warp;   // floats of warp-private shared memory
+    int cta_words;  // floats of CTA-wide shared memory in front of the warp strips
     int warps;
 };
 
-__host__ __device__ inline K2BwdPlan k2_bwd_plan(int T, int hops, int num_bins) {
+__host__ __device__ inline K2BwdPlan k2_bwd_plan(int T, int Tp, int hops, int num_bins) {
     K2BwdPlan p;
     p.Rrows = min(T, 511) + 1;
-    p.nEW = hops * kEdgeVocab * kH;
+    p.nEWs = hops * kSmallVocab * kH;
     p.nR = p.Rrows * kH;
     p.nP = num_bins * kH;
-    p.nA = (hops + 1) * kH;
-    p.nN = hops * kH;
-    p.stride = p.nEW + p.nR + p.nP + p.nA + p.nN + kH;
-    const int per_warp = (p.nR + 4 * (p.nP + p.nA + p.nN) + kH) * 4;
-    int w = (int)((227 * 1024 - 1024 - p.nEW * 4) / per_warp);
-    p.warps = w > 8 ? 8 : w;
+    p.stride = p.nEWs + p.nR + p.nP + kH;
+    p.pitch = ((Tp + 27) / 32) * 32 + 4;
+    p.per_warp = 2 * (p.nR + p.nP) + kH * p.pitch + 2 * p.pitch + kH;      // hR | hP | dsum | cinfo | cdev | t
+    p.cta_words = p.nEWs + (hops + 1) * 8 + 40;                            // sEW | XW | 1/sp table
+    int w = (int)((227 * 1024 - 2048 - p.cta_words * 4) / (p.per_warp * 4));
+    p.warps = w > 16 ? 16 : w;
     return p;
 }
 
-// DT = float: one fp32 dBias buffer (nlayers == 1).  DT = bf16: nlayers per-layer dS planes (layer_stride elements apart,
-// written by mobgt_attn_bwd mode 2), summed here in fp32.
+constexpr uint32_t kInfoPair = 1u << 21, kInfoDev = 1u << 20, kInfoCol0 = 1u << 22, kInfoOvf = 1u << 23, kInfoUnreach = 1u << 24;
+
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_f32x4(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
 template <typename DT>
-__global__ void __launch_bounds__(256, 1) k2_bias_bwd_kernel(const K2Common c, const DT *__restrict__ dB, int nlayers,
+__global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, const DT *__restrict__ dB, int nlayers,
                                                              int64_t layer_stride, int num_bins,
                                                              const K2BwdPlan pl, float *__restrict__ partial,
-                                                             float *__restrict__ dR_overflow) {
+                                                             float *__restrict__ dEWfull, float *__restrict__ dR_overflow) {
     extern __shared__ __align__(16) float sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int p4 = lane >> 3, h = lane & 7;
-    float *sEW = sm;
-    const int per_warp = pl.nR + 4 * (pl.nP + pl.nA + pl.nN) + kH;
-    float *sR = sm + pl.nEW + warp * per_warp;
-    float *sP = sR + pl.nR + p4 * pl.nP;
-    float *sA = sR + pl.nR + 4 * pl.nP + p4 * pl.nA;
-    float *sN = sR + pl.nR + 4 * (pl.nP + pl.nA) + p4 * pl.nN;
-    float *sT = sR + pl.nR + 4 * (pl.nP + pl.nA + pl.nN);
-    for (int i = threadIdx.x; i < pl.nEW + nwarp * per_warp; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
-    const unsigned full = 0xffffffffu;
-    const size_t hs = (size_t)c.T * c.Tp;
+    const int ty = lane >> 4, c2 = (lane >> 3) & 1, h = lane & 7;      // table (0 = R, 1 = P), cell slot, head
+    float *sEW = sm;                                              // [hops][16][8]
+    uint32_t *XW = reinterpret_cast<uint32_t *>(sm + pl.nEWs);    // [hops + 1][8]
+    float *invT = sm + pl.nEWs + (c.hops + 1) * 8;                // [40]: 1 / sp
+    float *wbase = sm + pl.cta_words;
+    const uint32_t s_warp = (uint32_t)__cvta_generic_to_shared(wbase + (size_t)warp * pl.per_warp);
+    const uint32_t s_hR = s_warp;                                 // [Rrows][2][8]
+    const uint32_t s_hP = s_hR + 2u * pl.nR * 4u;                 // [bins][2][8]
+    const uint32_t s_dsum = s_hP + 2u * pl.nP * 4u;               // [8][pitch]
+    const uint32_t s_cinfo = s_dsum + (uint32_t)(kH * pl.pitch) * 4u;   // [pitch]
+    const uint32_t s_cdev = s_cinfo + (uint32_t)pl.pitch * 4u;    // [pitch]
+    const uint32_t s_T = s_cdev + (uint32_t)pl.pitch * 4u;        // [8]
+    const uint32_t s_hist = (ty ? s_hP : s_hR) + (uint32_t)(c2 * kH + h) * 4u;      // + key * 64 B
+    const uint32_t key_shift = ty ? 10u : 0u;
     const int hopw = c.hops >> 2;
-    const int gbase = lane & ~7;
+    for (int i = threadIdx.x; i < pl.nEWs; i += blockDim.x) sEW[i] = 0.f;
+    for (int i = threadIdx.x; i < (c.hops + 1) * 8; i += blockDim.x) XW[i] = (i & 7) < hopw ? expected_word(i >> 3, i & 7) : 0u;
+    for (int i = threadIdx.x; i < 40; i += blockDim.x) invT[i] = 1.0f / (float)max(i, 1);
+    for (int i = threadIdx.x; i < nwarp * pl.per_warp; i += blockDim.x) wbase[i] = 0.f;
+    __syncthreads();
+    const size_t hs = (size_t)c.T * c.Tp;
+    const uint32_t pitch4 = (uint32_t)pl.pitch * 4u;
     float tacc = 0.f;
     for (int u = blockIdx.x * nwarp + warp; u < c.B * c.T; u += gridDim.x * nwarp) {
         const int g = u / c.T, a = u - g * c.T;
         const int n = c.n[g];
         if (a == 0 || a > n) continue;                       // row 0 carries no parameter (model_fqandtoyo.py:1160-1165)
         const int Tg = n + 1;
-        const DT *row = dB + ((size_t)g * kH * c.T + a) * c.Tp + h * hs;
         const int64_t rowp = c.sq_off[g] + (int64_t)(a - 1) * n - 1;     // pair of cell b lives at rowp + b
-        for (int b0 = 0; b0 < Tg; b0 += 16) {
-            const int bq = b0 + 4 * p4;
-            float dj[4] = {0.f, 0.f, 0.f, 0.f};
-            if (bq < Tg) {
-                if constexpr (sizeof(DT) == 4) {
-                    const float4 dv = *reinterpret_cast<const float4 *>(row + bq);
-                    dj[0] = dv.x; dj[1] = dv.y; dj[2] = dv.z; dj[3] = dv.w;
+        // ---- 1. sum phase: dsum[h][b] = sum over layers of plane[l][g][h][a][b]
+        const DT *rowbase = dB + ((size_t)g * kH * c.T + a) * c.Tp;
+        constexpr int kPer = 16 / (int)sizeof(DT);           // cells per 16-byte load
+        const int nitems = ceil_div(Tg, kPer) * kH;
+        for (int i0 = 0; i0 < nitems; i0 += 64) {
+            float accv[2][8];
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) accv[s][q] = 0.f;
+            const DT *src[2];
+            bool ok[2];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int i = i0 + 32 * s + lane;
+                ok[s] = i < nitems;
+                src[s] = rowbase + (size_t)(i & 7) * hs + (i >> 3) * kPer;
+            }
+            for (int l0 = 0; l0 < nlayers; l0 += 6) {
+                uint4 v[2][6];
+                if (l0 + 6 <= nlayers) {
+#pragma unroll
+                    for (int s = 0; s < 2; ++s)
+#pragma unroll
+                        for (int j = 0; j < 6; ++j)
+                            v[s][j] = ok[s] ? __ldg(reinterpret_cast<const uint4 *>(src[s] + (size_t)(l0 + j) * layer_stride))
+                                            : make_uint4(0u, 0u, 0u, 0u);
                 } else {
-                    for (int l = 0; l < nlayers; ++l) {
-                        const uint2 dv = *reinterpret_cast<const uint2 *>(row + (size_t)l * layer_stride + bq);
-                        dj[0] += bf16lo(dv.x); dj[1] += __uint_as_float(dv.x & 0xFFFF0000u);
-                        dj[2] += bf16lo(dv.y); dj[3] += __uint_as_float(dv.y & 0xFFFF0000u);
+#pragma unroll
+                    for (int s = 0; s < 2; ++s)
+#pragma unroll
+                        for (int j = 0; j < 6; ++j)
+                            v[s][j] = (ok[s] && l0 + j < nlayers)
+                                          ? __ldg(reinterpret_cast<const uint4 *>(src[s] + (size_t)(l0 + j) * layer_stride))
+                                          : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        const uint32_t w4[4] = {v[s][j].x, v[s][j].y, v[s][j].z, v[s][j].w};
+                        if constexpr (sizeof(DT) == 4) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) accv[s][q] += __uint_as_float(w4[q]);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                accv[s][2 * q] += bf16lo(w4[q]);
+                                accv[s][2 * q + 1] += __uint_as_float(w4[q] & 0xFFFF0000u);
+                            }
+                        }
+                    }
+            }
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int i = i0 + 32 * s + lane;
+                if (ok[s]) {
+                    const uint32_t dst = s_dsum + (uint32_t)(i & 7) * pitch4 + (uint32_t)((i >> 3) * kPer) * 4u;
+                    sts_f32x4(dst, accv[s][0], accv[s][1], accv[s][2], accv[s][3]);
+                    if constexpr (sizeof(DT) == 2) sts_f32x4(dst + 16u, accv[s][4], accv[s][5], accv[s][6], accv[s][7]);
+                }
+            }
+        }
+        // ---- 2. index phase: cinfo[b] = R row | P row << 10 | flags ;  cdev[b] = up to two deviating bytes
+        for (int b = lane; b < Tg; b += 32) {
+            uint32_t info = kInfoCol0, dev = 0u;
+            if (b >= 1) {
+                const int64_t pc = rowp + b;
+                const int rp = c.rel_pos[pc], pp = c.poi_pos[pc];
+                const uint32_t *ei = reinterpret_cast<const uint32_t *>(c.edge_in + pc * c.hops);
+                uint32_t ew[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) ew[q] = q < hopw ? __ldg(ei + q) : 0u;
+                const int rk = min(max(rp, 0), kRelRows - 1);
+                const int L = expected_walk(rk, c.hops);
+                const int row = (rk == 511) ? pl.Rrows - 1 : (rk < pl.Rrows - 1 ? rk : -1);
+                info = (uint32_t)(row < 0 ? 0 : row) | ((uint32_t)min(max(pp, 0), num_bins - 1) << 10);
+                if (rk - 1 < c.rel_pos_max) info |= kInfoPair;        // -inf entries carry no gradient
+                if (row < 0) info |= kInfoOvf;                       // key outside the plan (never for K1 output)
+                if (rk - 1 >= 510) info |= kInfoUnreach;
+                int ndev = 0;
+                dev = (uint32_t)L << 2;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    uint32_t df = ew[q] ^ XW[L * 8 + q];
+                    while (df != 0u) {
+                        const int e = (__ffs(df) - 1) >> 3;
+                        if (ndev < 2) dev |= (((uint32_t)(q * 4 + e) << 7) | ((ew[q] >> (8 * e)) & 0x7Fu)) << (8 + 12 * ndev);
+                        ++ndev;
+                        df &= ~(0xFFu << (8 * e));
                     }
                 }
+                if (ndev) info |= kInfoDev;
+                dev |= (uint32_t)min(ndev, 3);
             }
-            // keys of the 4 cells of this lane's p4 group, spread over the 8 head lanes:
-            //   every lane h: word h of the walk bytes; lane 0 also rel_pos, lane 1 also poi_pos
-            uint32_t wj[4];
-            int kj[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int b = bq + j;
-                wj[j] = 0u;
-                kj[j] = 0;
-                if (b >= 1 && b < Tg) {
-                    const int64_t pc = rowp + b;
-                    if (h < hopw) wj[j] = __ldg(reinterpret_cast<const uint32_t *>(c.edge_in + pc * c.hops) + h);
-                    if (h == 0) kj[j] = c.rel_pos[pc];
-                    if (h == 1) kj[j] = c.poi_pos[pc];
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int b = bq + j;
-                const bool valid = b < Tg;
-                float d = valid ? dj[j] : 0.f;
-                if (b == 0) tacc += d;
-                bool pair = valid && b >= 1;
-                const int rp = __shfl_sync(full, kj[j], gbase);
-                const int pp = __shfl_sync(full, kj[j], gbase + 1);
-                // walk length L and the mask of hops that carry another feature than the dominant one (bit k = hop k),
-                // reduced over the 8 word lanes of the cell
-                const uint32_t wd = wj[j];
-                int L = 0;
-                uint32_t hm = 0u;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const uint32_t v = (wd >> (8 * e)) & 0xFFu;
-                    L += (v != 0u);
-                    hm |= (v != 0u && v != (uint32_t)kDomEdge) ? (1u << e) : 0u;
-                }
-                hm <<= 4 * h;
-                L += __shfl_xor_sync(full, L, 1);
-                hm |= __shfl_xor_sync(full, hm, 1);
-                L += __shfl_xor_sync(full, L, 2);
-                hm |= __shfl_xor_sync(full, hm, 2);
-                L += __shfl_xor_sync(full, L, 4);
-                hm |= __shfl_xor_sync(full, hm, 4);
-                const int M = rp - 1;
-                if (M >= c.rel_pos_max) pair = false;            // -inf entries carry no gradient
-                // rel_pos histogram: 4 lock-step turns (cells of one group may share a key)
-                int rk = -1;
-                if (pair) {
-                    rk = (rp == 511) ? pl.Rrows - 1 : (rp < pl.Rrows - 1 ? rp : -2);
-                    if (rk == -2) atomicAdd(dR_overflow + rp * kH + h, d);     // key outside the plan (never for K1 output)
-                }
-#pragma unroll
-                for (int turn = 0; turn < 4; ++turn) {
-                    if (p4 == turn && rk >= 0) sR[rk * kH + h] += d;
-                    __syncwarp();
-                }
-                if (pair) {
-                    sP[min(pp, num_bins - 1) * kH + h] += d;
-                    d *= 1.0f / (float)min(max(M, 1), c.hops);
-                    sA[L * kH + h] += d;                          // L == 0 (no walk): row 0 of A is ignored
-                } else {
-                    hm = 0u;
-                }
-                // hops with a non-dominant feature (few): N[k] += d (taken back from the dominant bin at the end) and
-                // dEW[k][v] += d in the CTA's shared histogram
-                while (__any_sync(full, hm != 0u)) {
-                    const int k = hm ? __ffs(hm) - 1 : 0;
-                    const uint32_t wv = __shfl_sync(full, wd, gbase + (k >> 2));
-                    if (hm) {
-                        const int v = (wv >> (8 * (k & 3))) & 0xFF;
-                        sN[k * kH + h] += d;
-                        atomicAdd(sEW + ((size_t)k * kEdgeVocab + v) * kH + h, d);
-                        hm &= hm - 1u;
+            sts_u32(s_cinfo + (uint32_t)b * 4u, info);
+            sts_u32(s_cdev + (uint32_t)b * 4u, dev);
+        }
+        __syncwarp();
+        // ---- 3. histogram phase: lane = (table, cell slot c2, head h); cells b0 + c2 and b0 + 2 + c2 per iteration
+        for (int b0 = 0; b0 < Tg; b0 += 4) {
+            const int bA = b0 + c2, bB = b0 + 2 + c2;
+            const uint32_t iA = bA < Tg ? lds_u32(s_cinfo + (uint32_t)bA * 4u) : 0u;
+            const uint32_t iB = bB < Tg ? lds_u32(s_cinfo + (uint32_t)bB * 4u) : 0u;
+            const float dA = bA < Tg ? lds_f32(s_dsum + (uint32_t)h * pitch4 + (uint32_t)bA * 4u) : 0.f;
+            const float dB_ = bB < Tg ? lds_f32(s_dsum + (uint32_t)h * pitch4 + (uint32_t)bB * 4u) : 0.f;
+            if (ty == 0) tacc += ((iA & kInfoCol0) ? dA : 0.f) + ((iB & kInfoCol0) ? dB_ : 0.f);
+            const bool okA = (iA & kInfoPair) && !(ty == 0 && (iA & kInfoOvf));
+            const bool okB = (iB & kInfoPair) && !(ty == 0 && (iB & kInfoOvf));
+            const uint32_t aA = s_hist + ((iA >> key_shift) & 1023u) * 64u;
+            const uint32_t aB = s_hist + ((iB >> key_shift) & 1023u) * 64u;
+            // two read-modify-writes in flight; equal addresses are chained in registers, the second store wins
+            const float vA = lds_f32(aA), vB = lds_f32(aB);
+            const float nA = vA + (okA ? dA : 0.f);
+            const float nB = ((aA == aB) ? nA : vB) + (okB ? dB_ : 0.f);
+            sts_f32(aA, nA);
+            sts_f32(aB, nB);
+            if ((iA | iB) & (kInfoDev | kInfoOvf)) {
+                // rare: walk bytes that differ from the expected walk (R lanes: 8 heads of the cell), keys outside the plan
+#pragma unroll 1
+                for (int s = 0; s < 2; ++s) {
+                    const uint32_t info = s ? iB : iA;
+                    const int b = s ? bB : bA;
+                    const float d = s ? dB_ : dA;
+                    if (ty != 0 || !(info & kInfoPair)) continue;
+                    if (info & kInfoOvf) atomicAdd(dR_overflow + min(max((int)c.rel_pos[rowp + b], 0), kRelRows - 1) * kH + h, d);
+                    if (!(info & kInfoDev)) continue;
+                    const uint32_t cd = lds_u32(s_cdev + (uint32_t)b * 4u);
+                    const int L = (cd >> 2) & 63, nd = cd & 3;
+                    const float dinv = d * invT[(info & kInfoUnreach) ? c.hops : max(L, 1)];
+                    if (nd <= 2) {
+                        for (int j = 0; j < nd; ++j) {
+                            const uint32_t e = (cd >> (8 + 12 * j)) & 4095u;
+                            const int k = e >> 7, v = e & 127, x = k < L ? kDomEdge : 0;
+                            if (v != 0) {
+                                if (v < kSmallVocab) atomicAdd(sEW + (k * kSmallVocab + v) * kH + h, dinv);
+                                else atomicAdd(dEWfull + ((size_t)k * kEdgeVocab + v) * kH + h, dinv);
+                            }
+                            if (x != 0) atomicAdd(sEW + (k * kSmallVocab + x) * kH + h, -dinv);
+                        }
+                    } else {
+                        const uint32_t *ei = reinterpret_cast<const uint32_t *>(c.edge_in + (rowp + b) * c.hops);
+                        for (int q = 0; q < hopw; ++q) {
+                            const uint32_t ew = __ldg(ei + q), xw = XW[L * 8 + q];
+                            uint32_t df = ew ^ xw;
+                            while (df != 0u) {
+                                const int e = (__ffs(df) - 1) >> 3;
+                                const int v = (ew >> (8 * e)) & 0xFF, x = (xw >> (8 * e)) & 0xFF;
+                                const int k = q * 4 + e;
+                                if (v != 0) {
+                                    if (v < kSmallVocab) atomicAdd(sEW + (k * kSmallVocab + v) * kH + h, dinv);
+                                    else atomicAdd(dEWfull + ((size_t)k * kEdgeVocab + min(v, kEdgeVocab - 1)) * kH + h, dinv);
+                                }
+                                if (x != 0) atomicAdd(sEW + (k * kSmallVocab + x) * kH + h, -dinv);
+                                df &= ~(0xFFu << (8 * e));
+                            }
+                        }
                     }
                 }
             }
         }
+        __syncwarp();
     }
-    // column-0 sums: lanes (p4 = 0, h) hold them
-    if (p4 == 0) sT[h] = tacc;
+    // column-0 sums: R lanes (ty == 0) hold a partial per (c2, h); fold the cell slots
+    tacc += __shfl_xor_sync(0xffffffffu, tacc, 8);
+    if (lane < 8) sts_f32(s_T + (uint32_t)h * 4u, tacc);
     __syncthreads();
     // CTA totals -> partial[blockIdx]
     float *out = partial + (size_t)blockIdx.x * pl.stride;
-    for (int i = threadIdx.x; i < pl.nEW; i += blockDim.x) out[i] = sEW[i];
-    const float *wbase = sm + pl.nEW;
+    for (int i = threadIdx.x; i < pl.nEWs; i += blockDim.x) out[i] = sEW[i];
     for (int i = threadIdx.x; i < pl.nR; i += blockDim.x) {
+        const int key = i / kH, hh = i % kH;
         float s = 0.f;
-        for (int w = 0; w < nwarp; ++w) s += wbase[w * per_warp + i];
-        out[pl.nEW + i] = s;
+        for (int w = 0; w < nwarp; ++w)
+            for (int r = 0; r < 2; ++r) s += wbase[(size_t)w * pl.per_warp + (key * 2 + r) * kH + hh];
+        out[pl.nEWs + i] = s;
     }
     for (int i = threadIdx.x; i < pl.nP; i += blockDim.x) {
+        const int key = i / kH, hh = i % kH;
         float s = 0.f;
         for (int w = 0; w < nwarp; ++w)
-            for (int r = 0; r < 4; ++r) s += wbase[w * per_warp + pl.nR + r * pl.nP + i];
-        out[pl.nEW + pl.nR + i] = s;
-    }
-    for (int i = threadIdx.x; i < pl.nA; i += blockDim.x) {
-        float s = 0.f;
-        for (int w = 0; w < nwarp; ++w)
-            for (int r = 0; r < 4; ++r) s += wbase[w * per_warp + pl.nR + 4 * pl.nP + r * pl.nA + i];
-        out[pl.nEW + pl.nR + pl.nP + i] = s;
-    }
-    for (int i = threadIdx.x; i < pl.nN; i += blockDim.x) {
-        float s = 0.f;
-        for (int w = 0; w < nwarp; ++w)
-            for (int r = 0; r < 4; ++r) s += wbase[w * per_warp + pl.nR + 4 * (pl.nP + pl.nA) + r * pl.nN + i];
-        out[pl.nEW + pl.nR + pl.nP + pl.nA + i] = s;
+            for (int r = 0; r < 2; ++r) s += wbase[(size_t)w * pl.per_warp + 2 * pl.nR + (key * 2 + r) * kH + hh];
+        out[pl.nEWs + pl.nR + i] = s;
     }
     if (threadIdx.x < kH) {
         float s = 0.f;
-        for (int w = 0; w < nwarp; ++w) s += wbase[w * per_warp + pl.nR + 4 * (pl.nP + pl.nA + pl.nN) + threadIdx.x];
-        out[pl.nEW + pl.nR + pl.nP + pl.nA + pl.nN + threadIdx.x] = s;
+        for (int w = 0; w < nwarp; ++w) s += wbase[(size_t)w * pl.per_warp + pl.per_warp - kH + threadIdx.x];
+        out[pl.nEWs + pl.nR + pl.nP + threadIdx.x] = s;
     }
 }
 
-// tot[i] = sum over CTAs (fixed order) of partial[cta][i];  then the walk-length histogram is folded into dEW:
-// dEW[k][dom][h] += sum_{L > k} A[L][h] - N[k][h]   (second kernel, after the totals exist)
+// tot[i] = sum over CTAs (fixed order) of partial[cta][i]
 __global__ void k2_bias_bwd_reduce_kernel(const float *__restrict__ partial, int nparts, int stride, float *__restrict__ tot) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= stride) return;
@@ -447,23 +558,36 @@ __global__ void k2_bias_bwd_reduce_kernel(const float *__restrict__ partial, int
     tot[i] = s;
 }
 
-__global__ void k2_bias_bwd_scatter_kernel(float *__restrict__ tot, const K2BwdPlan pl, int hops, int num_bins,
-                                           float *__restrict__ dR, float *__restrict__ dP, float *__restrict__ dt) {
+// totals -> dR, dPpos, dt, and the full dEW[k][v][h] (which already holds the global rare-path atomics):
+//   dEW[k][v] += EWsmall[k][v] (v < 16) ;  dEW[k][dom] += sum_{rp : L(rp) > k} dRL[rp] / sp(rp)   (one warp per (k, h))
+__global__ void k2_bias_bwd_scatter_kernel(const float *__restrict__ tot, const K2BwdPlan pl, int hops, int num_bins,
+                                           float *__restrict__ dEWfull, float *__restrict__ dR, float *__restrict__ dP,
+                                           float *__restrict__ dt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const float *tR = tot + pl.nEW, *tP = tR + pl.nR, *tA = tP + pl.nP, *tN = tA + pl.nA, *tT = tN + pl.nN;
-    if (i < 512 * kH) {
+    const float *tE = tot, *tR = tot + pl.nEWs, *tP = tR + pl.nR, *tT = tP + pl.nP;
+    if (i < kRelRows * kH) {
         const int rp = i / kH, hh = i % kH;
         const int row = (rp == 511) ? pl.Rrows - 1 : (rp < pl.Rrows - 1 ? rp : -1);
         dR[i] += (row >= 0) ? tR[row * kH + hh] : 0.f;     // dR holds the (normally empty) overflow atomics
     }
     if (i < num_bins * kH) dP[i] = tP[i];
     if (i < kH) dt[i] = tT[i];
-    if (i < hops * kH) {
-        const int k = i / kH, hh = i % kH;
+    if (i < hops * kSmallVocab * kH) {
+        const int hh = i % kH, v = (i / kH) % kSmallVocab, k = i / (kH * kSmallVocab);
+        if (v != kDomEdge) dEWfull[((size_t)k * kEdgeVocab + v) * kH + hh] += tE[i];
+    }
+    const int wid = i >> 5, lane = i & 31;
+    if (wid < hops * kH) {                                  // warp-uniform
+        const int k = wid / kH, hh = wid % kH;
         float s = 0.f;
-        for (int L = k + 1; L <= hops; ++L) s += tA[L * kH + hh];
-        s -= tN[i];
-        tot[((size_t)k * kEdgeVocab + kDomEdge) * kH + hh] += s;
+        for (int row = lane; row < pl.Rrows; row += 32) {
+            const int rp = (row == pl.Rrows - 1) ? 511 : row;
+            if (expected_walk(rp, hops) > k) s += tR[row * kH + hh] / (float)min(max(rp - 1, 1), hops);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0)
+            dEWfull[((size_t)k * kEdgeVocab + kDomEdge) * kH + hh] += s + tE[(k * kSmallVocab + kDomEdge) * kH + hh];
     }
 }
 
@@ -546,8 +670,8 @@ extern "C" int32_t mobgt_bias_fwd(const int32_t *n, const int64_t *sq_off, const
 
 extern "C" int64_t mobgt_bias_bwd_workspace_bytes(int32_t T, int32_t hops, int32_t num_bins) {
     if (T < 2 || hops < 4 || hops > MOBGT_MAX_HOPS || num_bins < 1 || num_bins > 1024) return -1;
-    const K2BwdPlan pl = k2_bwd_plan(T, hops, num_bins);
-    return (int64_t)(kNumSMs + 1) * pl.stride * (int64_t)sizeof(float);
+    const K2BwdPlan pl = k2_bwd_plan(T, round_up(T, 8), hops, num_bins);
+    return ((int64_t)hops * kEdgeVocab * kH + (int64_t)(kNumSMs + 1) * pl.stride) * (int64_t)sizeof(float);
 }
 
 extern "C" int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const int16_t *rel_pos, const int16_t *poi_pos,
@@ -564,37 +688,41 @@ extern "C" int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const
     MOBGT_REQUIRE(T >= 2 && Tp >= T && Tp % 8 == 0, MOBGT_ERR_BAD_SHAPE, "mobgt_bias_bwd: T=%d Tp=%d", T, Tp);
     MOBGT_REQUIRE((dbias_dtype == MOBGT_F32 && n_layers == 1) || (dbias_dtype == MOBGT_BF16 && n_layers >= 1 && n_layers <= 64),
                   MOBGT_ERR_BAD_DTYPE, "mobgt_bias_bwd: dbias dtype %d with %d layer planes", dbias_dtype, n_layers);
-    const K2BwdPlan pl = k2_bwd_plan(T, hops, num_bins);
+    MOBGT_REQUIRE(((uintptr_t)dBias & 15) == 0 && (dbias_dtype == MOBGT_F32 || layer_stride % 8 == 0), MOBGT_ERR_BAD_SHAPE,
+                  "mobgt_bias_bwd: dBias planes must be 16-byte aligned");
+    const K2BwdPlan pl = k2_bwd_plan(T, Tp, hops, num_bins);
     MOBGT_REQUIRE(pl.warps >= 1, MOBGT_ERR_UNSUPPORTED, "mobgt_bias_bwd: no shared-memory plan for T=%d bins=%d", T, num_bins);
-    const int64_t need = (int64_t)(kNumSMs + 1) * pl.stride * (int64_t)sizeof(float);
+    const int64_t nEW = (int64_t)hops * kEdgeVocab * kH;
+    const int64_t need = (nEW + (int64_t)(kNumSMs + 1) * pl.stride) * (int64_t)sizeof(float);
     MOBGT_REQUIRE(workspace_bytes >= need, MOBGT_ERR_WORKSPACE_TOO_SMALL, "mobgt_bias_bwd: workspace %lld < %lld bytes",
                   (long long)workspace_bytes, (long long)need);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    float *tot = static_cast<float *>(workspace);          // [stride] totals, then [kNumSMs][stride] per-CTA partials
+    float *dEWfull = static_cast<float *>(workspace);      // [hops][128][8], then [stride] totals, then [kNumSMs][stride] partials
+    float *tot = dEWfull + nEW;
     float *partial = tot + pl.stride;
-    MOBGT_CUDA_OK(cudaMemsetAsync(dR, 0, 512 * kH * 4, s));
+    MOBGT_CUDA_OK(cudaMemsetAsync(dR, 0, kRelRows * kH * 4, s));
+    MOBGT_CUDA_OK(cudaMemsetAsync(dEWfull, 0, (size_t)nEW * 4, s));
     const int nparts = B > 0 ? kNumSMs : 0;
     if (B > 0) {
         K2Common c{n, sq_off, rel_pos, poi_pos, edge_in, B, T, Tp, hops, rel_pos_max};
-        const int per_warp = pl.nR + 4 * (pl.nP + pl.nA + pl.nN) + kH;
-        const size_t smem = (size_t)(pl.nEW + pl.warps * per_warp) * sizeof(float);
+        const size_t smem = (size_t)(pl.cta_words + pl.warps * pl.per_warp) * sizeof(float);
         if (dbias_dtype == MOBGT_F32) {
             MOBGT_CUDA_OK(cudaFuncSetAttribute(k2_bias_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k2_bias_bwd_kernel<float><<<kNumSMs, pl.warps * 32, smem, s>>>(c, static_cast<const float *>(dBias), 1, 0, num_bins, pl,
-                                                                          partial, dR);
+                                                                          partial, dEWfull, dR);
         } else {
             MOBGT_CUDA_OK(cudaFuncSetAttribute(k2_bias_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)smem));
             k2_bias_bwd_kernel<__nv_bfloat16><<<kNumSMs, pl.warps * 32, smem, s>>>(
-                c, static_cast<const __nv_bfloat16 *>(dBias), n_layers, layer_stride, num_bins, pl, partial, dR);
+                c, static_cast<const __nv_bfloat16 *>(dBias), n_layers, layer_stride, num_bins, pl, partial, dEWfull, dR);
         }
         MOBGT_LAUNCH_OK("k2_bias_bwd_kernel");
     }
     k2_bias_bwd_reduce_kernel<<<ceil_div(pl.stride, 256), 256, 0, s>>>(partial, nparts, pl.stride, tot);
     MOBGT_LAUNCH_OK("k2_bias_bwd_reduce_kernel");
-    k2_bias_bwd_scatter_kernel<<<ceil_div(512 * kH, 256), 256, 0, s>>>(tot, pl, hops, num_bins, dR, dPpos, dtvd);
+    k2_bias_bwd_scatter_kernel<<<ceil_div(max(max(kRelRows, num_bins) * kH, hops * kH * 32), 256), 256, 0, s>>>(tot, pl, hops, num_bins, dEWfull, dR, dPpos, dtvd);
     MOBGT_LAUNCH_OK("k2_bias_bwd_scatter_kernel");
-    k2_bias_bwd_finish_kernel<<<ceil_div(kEdgeVocab * kH + hops * kH * kH, 256), 256, 0, s>>>(tot, E, W, hops, dE, dW);
+    k2_bias_bwd_finish_kernel<<<ceil_div(kEdgeVocab * kH + hops * kH * kH, 256), 256, 0, s>>>(dEWfull, E, W, hops, dE, dW);
     MOBGT_LAUNCH_OK("k2_bias_bwd_finish_kernel");
     return MOBGT_OK;
 }

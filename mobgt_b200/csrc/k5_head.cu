@@ -96,15 +96,26 @@ __device__ __forceinline__ void list_insert(unsigned long long (&list)[LK], unsi
         list[j] = sw ? a : b;
     }
 }
+// buffer entries are RAW (high word = float bits, low word = column inside this shard); the order-preserving key is built
+// here, off the hot path
 template <int LK>
-__device__ __forceinline__ float list_drain(unsigned long long (&list)[LK], uint32_t cd, int &ncand) {
+__device__ __forceinline__ float list_drain(unsigned long long (&list)[LK], uint32_t cd, int &ncand, long long vocab_offset) {
     while (ncand > 0) {
         --ncand;
-        const unsigned long long key = lds64(cd + (uint32_t)ncand * kEnt);
+        const unsigned long long raw = lds64(cd + (uint32_t)ncand * kEnt);
+        const uint32_t gi = (uint32_t)(vocab_offset + (long long)(uint32_t)raw);
+        const unsigned long long key = ((unsigned long long)f2ord(__uint_as_float((uint32_t)(raw >> 32))) << 32) | (uint32_t)(~gi);
         if (key > list[LK - 1]) list_insert<LK>(list, key);
     }
     const unsigned long long kth = list[LK - 1];
     return kth ? ord2f((uint32_t)(kth >> 32)) : -INFINITY;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// spin with back-off: the TMA / MMA warps share their schedulers with epilogue warps and must not eat their issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(24);
 }
 
 template <int LK>
@@ -161,7 +172,7 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % p.ring;
                     const uint32_t ph = (uint32_t)(it / p.ring) & 1u;
-                    mbar_wait(&bar_empty[s], ph ^ 1u);
+                    mbar_wait_relaxed(&bar_empty[s], ph ^ 1u);
                     mbar_expect_tx(&bar_full[s], (uint32_t)kBlkBytes);
                     tma_load_2d(sB + (size_t)s * kBlkBytes, &tmW, &bar_full[s], kb * kKB, n * kHeadTile);
                 }
@@ -177,11 +188,11 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
             int it = 0;
             for (int t = 0; t < T; ++t) {
                 const int a = t & 1;
-                mbar_wait(&acc_empty[a], ((uint32_t)(t >> 1) & 1u) ^ 1u);
+                mbar_wait_relaxed(&acc_empty[a], ((uint32_t)(t >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % p.ring;
-                    mbar_wait(&bar_full[s], (uint32_t)(it / p.ring) & 1u);
+                    mbar_wait_relaxed(&bar_full[s], (uint32_t)(it / p.ring) & 1u);
                     tc_fence_after();
                     const int ksteps = min(kKB, p.K - kb * kKB) / 16;
                     for (int j = 0; j < ksteps; ++j)
@@ -201,40 +212,46 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
         const int row = mt * kHeadTile + r;
         const bool row_ok = row < p.M;
         const long long tgt = row_ok ? (long long)p.target[row] : -1;
-        const long long tloc = tgt - p.vocab_offset;
+        const long long tloc64 = tgt - p.vocab_offset;      // column of the target inside this shard (any sign / size)
+        const int tloc = tloc64 < 0 ? -1 : (tloc64 > 0x7fffff00ll ? 0x7fffff00 : (int)tloc64);
         const float st = row_ok ? p.st[row] : 0.f;
         const float st_prev = prev_float(st);
         const uint32_t cd = smem_u32(cand + (size_t)e * kCandCap * kHeadTile + r);
+        const uint32_t sbias = smem_u32(cand + (size_t)2 * kCandCap * kHeadTile) + (uint32_t)e * 2 * kHeadTile * 4;   // [2][128] f32
         unsigned long long list[LK];
 #pragma unroll
         for (int j = 0; j < LK; ++j) list[j] = 0ull;
         float thr = -INFINITY;
         int ncand = 0, cnt = 0;
+        // bias of column col_base + r of the tile (one element per thread, coalesced): -inf past the vocabulary, so the
+        // zero accumulators of the TMA-zero-filled tail rows neither count nor qualify
+        auto tile_bias = [&](int t) -> float {
+            const int col = (n_begin + t) * kHeadTile + r;
+            return col < p.V ? (p.bias ? __ldg(p.bias + col) : 0.f) : -INFINITY;
+        };
+        float bnext = e < T ? tile_bias(e) : 0.f;
 
-        for (int t = e; t < T; t += 2) {
+        int it = 0;
+        for (int t = e; t < T; t += 2, ++it) {
             const int n = n_begin + t;
             const int col_base = n * kHeadTile;
+            const uint32_t sb = sbias + (uint32_t)(it & 1) * kHeadTile * 4;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb + (uint32_t)r * 4), "f"(bnext) : "memory");
+            if (t + 2 < T) bnext = tile_bias(t + 2);
+            named_bar_sync(1 + e, kHeadTile);
             mbar_wait(&acc_full[e], (uint32_t)(t >> 1) & 1u);
             tc_fence_after();
-            const bool partial = col_base + kHeadTile > p.V;
 #pragma unroll 1
             for (int c0 = 0; c0 < kHeadTile; c0 += 32) {
                 uint32_t acc[32];
                 float v[32];
                 const int cb = col_base + c0;
                 tmem_ld32(tmem + lane_off + (uint32_t)(e * kHeadTile + c0), acc);
-                // the bias words of this chunk (same address in every lane: one broadcast transaction each), in flight
-                // together with the TMEM read
-                if (p.bias && !partial) {
-                    const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + cb);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 x = __ldg(b4 + q);
-                        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) v[q] = (p.bias && cb + q < p.V) ? __ldg(p.bias + cb + q) : 0.f;
+                for (int q = 0; q < 8; ++q) {          // same address in every lane: broadcast reads
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(v[4 * q]), "=f"(v[4 * q + 1]), "=f"(v[4 * q + 2]), "=f"(v[4 * q + 3])
+                                 : "r"(sb + (uint32_t)(c0 + 4 * q) * 4));
                 }
                 tmem_ld_wait();
                 if (c0 == kHeadTile - 32) {   // accumulator fully read: hand it back to the MMA warp
@@ -244,17 +261,14 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
                 }
 #pragma unroll
                 for (int q = 0; q < 32; ++q) v[q] += __uint_as_float(acc[q]);
-                if (partial) {                // vocabulary tail: columns >= V neither count nor qualify
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) v[q] = (cb + q < p.V) ? v[q] : -INFINITY;
-                }
                 if (p.logits != nullptr && row_ok) {     // logits dump (tests)
 #pragma unroll
                     for (int q = 0; q < 32; ++q)
                         if (cb + q < p.V) p.logits[(size_t)row * p.V + cb + q] = v[q];
                 }
-                // rank count: ONE compare per element.  Chunks entirely before the target compare against prev_float(s_t)
-                // (v >= s_t), the others against s_t; the chunk that holds the target fixes up its own leading columns.
+                // rank count: ONE subtract + one shifted add per element (sign bit of cmp - v  <=>  v > cmp).  Chunks entirely
+                // before the target compare against prev_float(s_t) (v >= s_t), the others against s_t; the chunk that holds
+                // the target fixes up its own leading columns.
                 const float cmp = (tloc >= cb + 32) ? st_prev : st;
                 if (tloc >= cb && tloc < cb + 32) {
 #pragma unroll
@@ -267,39 +281,41 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                     const float v0 = v[4 * g], v1 = v[4 * g + 1], v2 = v[4 * g + 2], v3 = v[4 * g + 3];
-                    cnt += (int)(v0 > cmp) + (int)(v1 > cmp) + (int)(v2 > cmp) + (int)(v3 > cmp);
+                    cnt += (int)(__float_as_uint(cmp - v0) >> 31) + (int)(__float_as_uint(cmp - v1) >> 31) +
+                           (int)(__float_as_uint(cmp - v2) >> 31) + (int)(__float_as_uint(cmp - v3) >> 31);
                     m4[g] = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
                 }
-                // harvest the top-k candidates of the chunk, group by group; a full buffer ends the pass, is drained (the
+                // harvest the top-k candidates of the chunk, group by group; a full buffer leaves the pass, is drained (the
                 // single in-tile insertion site) and the pass resumes at the group it stopped at
-                int gdone = 0;
+                int g0 = 0;
                 for (;;) {
-                    bool ovf = false;
+                    bool full_buf = false;
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
-                        if (g >= gdone && !ovf && m4[g] > thr) {
+                        if (!full_buf && g >= g0 && m4[g] > thr) {
                             if (ncand > kCandCap - 4) {
-                                ovf = true;
-                                gdone = g;
+                                full_buf = true;
+                                g0 = g;
                             } else {
-                                const uint32_t gi = (uint32_t)(p.vocab_offset + cb + 4 * g);
+                                uint32_t colg;           // opaque: keeps the column arithmetic inside this rare block
+                                asm volatile("add.u32 %0, %1, %2;" : "=r"(colg) : "r"((uint32_t)cb), "r"(4u * g));
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
                                     if (v[4 * g + i] > thr) {
                                         sts64(cd + (uint32_t)ncand * kEnt,
-                                              ((unsigned long long)f2ord(v[4 * g + i]) << 32) | (uint32_t)(~(gi + (uint32_t)i)));
+                                              ((unsigned long long)__float_as_uint(v[4 * g + i]) << 32) | (colg + (uint32_t)i));
                                         ++ncand;
                                     }
                                 }
                             }
                         }
                     }
-                    if (!ovf) break;
-                    thr = list_drain<LK>(list, cd, ncand);
+                    if (!full_buf) break;
+                    thr = list_drain<LK>(list, cd, ncand, p.vocab_offset);
                 }
                 __syncwarp();     // tcgen05.ld is warp-collective: reconverge before the next chunk
             }
-            thr = list_drain<LK>(list, cd, ncand);   // all lanes together; fresh threshold for the next tile
+            thr = list_drain<LK>(list, cd, ncand, p.vocab_offset);   // all lanes together; fresh threshold for the next tile
             __syncwarp();
         }
         if (row_ok) {
@@ -490,7 +506,7 @@ extern "C" int32_t mobgt_head_topk(const void *z, const void *W, const float *bi
     }
     rc = encode_rows_sw128(&tmW, W, V, K);
     if (rc) return rc;
-    const size_t fixed = (size_t)kblocks * kBlkBytes + (size_t)2 * kCandCap * kHeadTile * 8 + 1024;
+    const size_t fixed = (size_t)kblocks * kBlkBytes + (size_t)2 * kCandCap * kHeadTile * 8 + (size_t)4 * kHeadTile * 4 + 1024;
     int ring = (int)((227 * 1024 - 512 - (long long)fixed) / kBlkBytes);
     ring = ring > kMaxRing ? kMaxRing : ring;
     MOBGT_REQUIRE(ring >= 2, MOBGT_ERR_UNSUPPORTED, "mobgt_head_topk: no shared-memory plan for K=%d k=%d", K, k);
