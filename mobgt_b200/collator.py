@@ -117,6 +117,24 @@ class Batch1:
     def __len__(self):
         return int(self.B)
 
+    def build_plans(self):
+        """Fixed summation orders of the deterministic segmented scatter-adds (K4 backward): a stable sort of every key
+        stream of the batch.  They depend on the batch indices only, so they are part of collation (device sorts, no
+        host synchronisation); the category plan needs the model's cat_of_poi table and is added on first use."""
+        from .ops import sort_plan
+        plans = self.__dict__.setdefault("_plans", {})
+        plans["node_rows"] = self.node_rows
+        plans["poi"] = sort_plan(self.x_nodes.long() - 1)
+        plans["slot"] = sort_plan(self.slot)
+        plans["pos"] = sort_plan(self.tok_pos)
+        ind = torch.zeros_like(self.tok_pos)
+        ind[self.node_rows] = self.in_deg
+        outd = torch.zeros_like(self.tok_pos)
+        outd[self.node_rows] = self.out_deg
+        plans["ind"] = sort_plan(ind)
+        plans["outd"] = sort_plan(outd)
+        return plans
+
     def to(self, device):
         dev = torch.device(device)
         for k, v in list(self.__dict__.items()):
@@ -225,23 +243,27 @@ def collate_packed(items, world=None, latlon_dev=None, max_node=512, multi_hop_m
     no = np.zeros(B + 1, np.int64)
     np.cumsum(ns.astype(np.int64), out=no[1:])
     Nn, cells = int(no[-1]), int(sq[-1])
+    # all edge lists of the batch in one shot (one scatter / two bincounts instead of a Python loop over the items)
+    eis = [_to_np(it.edge_index) for it in items]
+    ecnt = np.array([e.shape[1] for e in eis], np.int64)
+    ei = np.concatenate(eis, axis=1).astype(np.int64) if B else np.zeros((2, 0), np.int64)
+    ea = np.concatenate([_to_np(it.edge_attr).reshape(-1) for it in items]).astype(np.int64) if B else np.zeros(0, np.int64)
+    eg = np.repeat(np.arange(B), ecnt)                    # graph of every edge
     feat = np.zeros(cells, np.uint8)
-    indeg = np.zeros(Nn, np.int32)
-    outdeg = np.zeros(Nn, np.int32)
-    for g, it in enumerate(items):
-        ei = _to_np(it.edge_index, np.int64)
-        ea = _to_np(it.edge_attr, np.int64).reshape(-1)
-        n = int(ns[g])
-        feat[sq[g] + ei[0] * n + ei[1]] = ea + 2          # wrapper.py:49-53: convert_to_single_emb(+1) then +1
-        indeg[no[g]:no[g + 1]] = np.bincount(ei[0], minlength=n)    # wrapper.py:97: adj.sum(dim=1)
-        outdeg[no[g]:no[g + 1]] = np.bincount(ei[1], minlength=n)   # wrapper.py:98: adj.sum(dim=0)
-    x_nodes = np.concatenate([_to_np(it.x, np.int64).reshape(-1) for it in items]).astype(np.int32)
-    tn = np.concatenate([_to_np(it.time_normal, np.float32).reshape(-1) for it in items])
-    time_nodes = np.concatenate([_to_np(it.time, np.int64).reshape(-1) for it in items]).astype(np.int32)
-    cat_nodes = np.concatenate([_to_np(it.cat, np.int64).reshape(-1) for it in items]).astype(np.int32)
+    feat[sq[:-1][eg] + ei[0] * ns.astype(np.int64)[eg] + ei[1]] = ea + 2     # wrapper.py:49-53: convert_to_single_emb(+1) then +1
+    indeg = np.bincount(no[:-1][eg] + ei[0], minlength=Nn).astype(np.int32)   # wrapper.py:97: adj.sum(dim=1)
+    outdeg = np.bincount(no[:-1][eg] + ei[1], minlength=Nn).astype(np.int32)  # wrapper.py:98: adj.sum(dim=0)
+
+    def cat_field(name, dtype):
+        return np.concatenate([_to_np(getattr(it, name)).reshape(-1) for it in items]).astype(dtype, copy=False)
+
+    x_nodes = cat_field("x", np.int32)
+    tn = cat_field("time_normal", np.float32)
+    time_nodes = cat_field("time", np.int32)
+    cat_nodes = cat_field("cat", np.int32)
     slot = (tn * np.float32(48)).astype(np.int64).astype(np.int32)          # model_fqandtoyo.py:1262
-    user = np.array([int(_to_np(it.user).reshape(-1)[0]) + 1 for it in items], np.int64).reshape(B, 1)   # wrapper.py:39
-    y = np.array([int(_to_np(it.y).reshape(-1)[0]) for it in items], np.int64)                           # collator.py:367
+    user = (np.array([_to_np(it.user).reshape(-1)[0] for it in items]).astype(np.int64) + 1).reshape(B, 1)   # wrapper.py:39
+    y = np.array([_to_np(it.y).reshape(-1)[0] for it in items]).astype(np.int64)                             # collator.py:367
     idx = np.array([int(getattr(it, "idx", i)) for i, it in enumerate(items)], np.int64)
     tok_off = (no + np.arange(B + 1)).astype(np.int32)
     g_of_node = np.repeat(np.arange(B, dtype=np.int32), ns)
@@ -260,11 +282,12 @@ def collate_packed(items, world=None, latlon_dev=None, max_node=512, multi_hop_m
     host = dict(n=ns, sq_off=sq, node_off=no, tok_off=tok_off, tok_graph=tok_graph, tok_pos=tok_pos, feat8=feat,
                 x_nodes=x_nodes, slot=slot, time_nodes=time_nodes, time_normal_nodes=tn, cat_nodes=cat_nodes,
                 in_deg=indeg + 1, out_deg=outdeg + 1,                          # pad_1d_unsqueeze "+1" (collator.py:12)
-                user=user, y=y, idx=idx)
+                user=user, y=y, idx=idx, node_rows=rows.astype(np.int64))
     views = _upload(host, dev)
     b = Batch1(B=B, N=int(ns.max()) if B else 0, hops=int(multi_hop_max_dist), rel_pos_max=int(rel_pos_max), n_host=ns,
                h2d_bytes=0, **views)
     b.h2d_bytes = int(sum(v.numel() * v.element_size() for v in views.values()))
+    b.build_plans()
     k1 = apsp_edge_input_packed(b.feat8, b.n, b.sq_off, ns, hops=int(multi_hop_max_dist), shift=1, want_path=want_path)
     b.rel_pos16, b.edge_in8, b.maxdist, b.path16 = k1["dist"], k1["edge_in"], k1["maxdist"], k1["path"]
     b.poi_pos16 = torch.empty(cells, dtype=torch.int16, device=dev)

@@ -117,26 +117,21 @@ __device__ __forceinline__ uint32_t expected_word(int L, int q) {
 }
 
 // Forward.  Persistent CTAs; RL [512][8], Ppos [bins][8] and the expected-walk words XW [hops+1][8] are staged once per
-// CTA in shared memory.  A tile is 512 threads x 2 adjacent cells (a, b) (a, b+1), b even, of the Tp-pitched plane row, so
+// CTA in shared memory.  One thread per PAIR OF ADJACENT CELLS (a, b) (a, b+1), b even, of the Tp-pitched plane row, so
 // every head plane is written as 4-byte (bf16x2) / 8-byte (f32x2) words and a warp covers 64 consecutive columns.  All
 // index bytes of a thread's two cells (2 x (2 + 2 + hops) B) are fetched up front as independent loads.
 //
-// Phase A (thread = 2 cells, 8 heads): bias = RL[rp] + Ppos[pp] — TWO table gathers per cell.  The walk bytes are only
-// compared (XOR) against the walk the distance predicts; a cell whose bytes differ — another edge feature (0.7 % of the
-// hops of trajectory graphs) or a walk cut short by the reference's node-0 quirk (algos.pyx:57-62) — is appended to a
-// shared-memory list (6 % of the cells).
-// Phase B (8 lanes = 8 heads per listed cell, 64 cells at a time): the differing bytes are corrected from the EW table
-//   Edge = sum_k EW[k][e_k]  =  PS[L] + sum_{k : e_k != x_k} ( EW[k][e_k] - EW[k][x_k] )
-// and the cell's 8 outputs are rewritten.  The identity holds for ANY byte pattern (EW[k][0] = 0: edge_encoder row 0 is
-// the padding row, model_fqandtoyo.py:784).  Keeping the corrections out of phase A keeps its warps convergent.
+// Per cell the work is TWO table gathers: bias = RL[rp] + Ppos[pp].  The walk bytes are only compared (XOR) against the
+// walk the distance predicts; the bytes that differ — another edge feature (0.7 % of the hops of trajectory graphs) or a
+// walk cut short by the reference's node-0 quirk (algos.pyx:57-62) — are corrected one by one from the EW table in
+// global memory (L1-resident):   Edge = sum_k EW[k][e_k]  =  PS[L] + sum_{k : e_k != x_k} ( EW[k][e_k] - EW[k][x_k] ).
+// The identity holds for ANY byte pattern (EW[k][0] = 0: edge_encoder row 0 is the padding row, model_fqandtoyo.py:784).
 template <typename OutT, int HOPW>
 __global__ void __launch_bounds__(512, 2) k2_bias_fwd_kernel(const K2Common c, const float *__restrict__ RLg,
                                                              const float *__restrict__ Pg, int num_bins,
                                                              const float *__restrict__ tvd,
                                                              const float *__restrict__ EWg, OutT *__restrict__ out) {
     extern __shared__ __align__(16) float sm[];
-    __shared__ int dcount[3];
-    __shared__ uint16_t dlist[3][1024];
     const int nR = kRelRows * kH, nP = num_bins * kH;
     float *RL = sm, *Pp = RL + nR;
     uint32_t *XW = reinterpret_cast<uint32_t *>(Pp + nP);          // [hops + 1][8]
@@ -146,117 +141,97 @@ __global__ void __launch_bounds__(512, 2) k2_bias_fwd_kernel(const K2Common c, c
         *reinterpret_cast<float4 *>(Pp + i) = *reinterpret_cast<const float4 *>(Pg + i);
     constexpr int hopw = HOPW;                    // hops = 4 * HOPW
     for (int i = threadIdx.x; i < (c.hops + 1) * 8; i += blockDim.x) XW[i] = (i & 7) < hopw ? expected_word(i >> 3, i & 7) : 0u;
-    if (threadIdx.x < 3) dcount[threadIdx.x] = 0;
     __syncthreads();
     const int half = c.Tp >> 1;                   // cell pairs per plane row
     const int per_graph = c.T * half;
     const int tiles = ceil_div(per_graph, (int)blockDim.x);
     const uint64_t half_magic = ((1ull << 40) + half - 1) / half;     // f / half == (f * magic) >> 40 for f < 2^18
     const size_t hs = (size_t)c.T * c.Tp;
-    int it = 0;
-    for (int w = blockIdx.x; w < tiles * c.B; w += gridDim.x, ++it) {
-        const int buf = it % 3;
+    for (int w = blockIdx.x; w < tiles * c.B; w += gridDim.x) {
         const int g = w / tiles, tile = w - g * tiles;
         const int n = c.n[g];
         const int Tg = n + 1;
-        const int64_t sq = c.sq_off[g];
-        if (threadIdx.x == 0) dcount[(it + 1) % 3] = 0;      // the list of the next tile (last read two tiles ago)
-        {
-            const int f = tile * blockDim.x + threadIdx.x;
-            const int a = (int)(((uint64_t)f * half_magic) >> 40), b = (f - a * half) * 2;
-            if (a < Tg && b < Tg) {
-                const bool two = b + 1 < Tg;
-                float acc[2][8];
+        const int f = tile * blockDim.x + threadIdx.x;
+        const int a = (int)(((uint64_t)f * half_magic) >> 40), b = (f - a * half) * 2;
+        if (a >= Tg || b >= Tg) continue;
+        const bool two = b + 1 < Tg;
+        float acc[2][8];
 #pragma unroll
-                for (int s = 0; s < 2; ++s)
+        for (int s = 0; s < 2; ++s)
 #pragma unroll
-                    for (int h = 0; h < 8; ++h) acc[s][h] = 0.f;
-                if (a >= 1) {
-                    const int64_t rowp = sq + (int64_t)(a - 1) * n;   // pair (a-1, j) lives at rowp + j
-                    // cell s of this thread is the pair j = b - 1 + s  (b == 0, s == 0: the virtual-distance column)
-                    int rp[2], pp[2];
-                    uint32_t ew[2][HOPW];
-                    bool is_pair[2];
+            for (int h = 0; h < 8; ++h) acc[s][h] = 0.f;
+        if (a >= 1) {
+            const int64_t rowp = c.sq_off[g] + (int64_t)(a - 1) * n;   // pair (a-1, j) lives at rowp + j
+            // cell s of this thread is the pair j = b - 1 + s  (b == 0, s == 0: the virtual-distance column)
+            int rp[2], pp[2];
+            uint32_t ew[2][HOPW];
+            bool is_pair[2];
 #pragma unroll
-                    for (int s = 0; s < 2; ++s) {
-                        const int j = b - 1 + s;
-                        is_pair[s] = j >= 0 && j < n;
-                        rp[s] = 0; pp[s] = 0;
+            for (int s = 0; s < 2; ++s) {
+                const int j = b - 1 + s;
+                is_pair[s] = j >= 0 && j < n;
+                rp[s] = 0; pp[s] = 0;
 #pragma unroll
-                        for (int q = 0; q < HOPW; ++q) ew[s][q] = 0u;
-                        if (is_pair[s]) {
-                            const int64_t pc = rowp + j;
-                            rp[s] = c.rel_pos[pc];
-                            pp[s] = c.poi_pos[pc];
-                            const uint32_t *ei = reinterpret_cast<const uint32_t *>(c.edge_in + pc * c.hops);
+                for (int q = 0; q < HOPW; ++q) ew[s][q] = 0u;
+                if (is_pair[s]) {
+                    const int64_t pc = rowp + j;
+                    rp[s] = c.rel_pos[pc];
+                    pp[s] = c.poi_pos[pc];
+                    const uint32_t *ei = reinterpret_cast<const uint32_t *>(c.edge_in + pc * c.hops);
 #pragma unroll
-                            for (int q = 0; q < HOPW; ++q) ew[s][q] = __ldg(ei + q);
-                        }
-                    }
-#pragma unroll
-                    for (int s = 0; s < 2; ++s) {
-                        if (!is_pair[s]) {
-                            if (b == 0 && s == 0) {
-#pragma unroll
-                                for (int h = 0; h < 8; ++h) acc[0][h] = __ldg(tvd + h);
-                            }
-                            continue;
-                        }
-                        const int rk = min(max(rp[s], 0), kRelRows - 1);
-                        const int L = expected_walk(rk, c.hops);
-                        const uint4 x0 = *reinterpret_cast<const uint4 *>(XW + L * 8), x1 = *reinterpret_cast<const uint4 *>(XW + L * 8 + 4);
-                        const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-                        uint32_t any = 0u;
-#pragma unroll
-                        for (int q = 0; q < HOPW; ++q) any |= ew[s][q] ^ xw[q];
-                        const float *r = RL + rk * kH, *q_ = Pp + min(max(pp[s], 0), num_bins - 1) * kH;
-                        const float4 r0 = *reinterpret_cast<const float4 *>(r), r1 = *reinterpret_cast<const float4 *>(r + 4);
-                        const float4 p0 = *reinterpret_cast<const float4 *>(q_), p1 = *reinterpret_cast<const float4 *>(q_ + 4);
-                        acc[s][0] = r0.x + p0.x; acc[s][1] = r0.y + p0.y; acc[s][2] = r0.z + p0.z; acc[s][3] = r0.w + p0.w;
-                        acc[s][4] = r1.x + p1.x; acc[s][5] = r1.y + p1.y; acc[s][6] = r1.z + p1.z; acc[s][7] = r1.w + p1.w;
-                        if (any != 0u) dlist[buf][atomicAdd(&dcount[buf], 1)] = (uint16_t)(threadIdx.x * 2 + s);
-                    }
+                    for (int q = 0; q < HOPW; ++q) ew[s][q] = __ldg(ei + q);
                 }
-                OutT *o = out + ((size_t)g * kH * c.T + a) * c.Tp + b;
-                if (two) {
+            }
 #pragma unroll
-                    for (int h = 0; h < 8; ++h) store2<OutT>(o + h * hs, acc[0][h], acc[1][h]);
-                } else {
+            for (int s = 0; s < 2; ++s) {
+                if (!is_pair[s]) {
+                    if (b == 0 && s == 0) {
 #pragma unroll
-                    for (int h = 0; h < 8; ++h) store1<OutT>(o + h * hs, acc[0][h]);
+                        for (int h = 0; h < 8; ++h) acc[0][h] = __ldg(tvd + h);
+                    }
+                    continue;
+                }
+                const int rk = min(max(rp[s], 0), kRelRows - 1);
+                const int L = expected_walk(rk, c.hops);
+                const uint4 x0 = *reinterpret_cast<const uint4 *>(XW + L * 8), x1 = *reinterpret_cast<const uint4 *>(XW + L * 8 + 4);
+                const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                uint32_t any = 0u;
+#pragma unroll
+                for (int q = 0; q < HOPW; ++q) any |= ew[s][q] ^ xw[q];
+                const float *r = RL + rk * kH, *q_ = Pp + min(max(pp[s], 0), num_bins - 1) * kH;
+                const float4 r0 = *reinterpret_cast<const float4 *>(r), r1 = *reinterpret_cast<const float4 *>(r + 4);
+                const float4 p0 = *reinterpret_cast<const float4 *>(q_), p1 = *reinterpret_cast<const float4 *>(q_ + 4);
+                acc[s][0] = r0.x + p0.x; acc[s][1] = r0.y + p0.y; acc[s][2] = r0.z + p0.z; acc[s][3] = r0.w + p0.w;
+                acc[s][4] = r1.x + p1.x; acc[s][5] = r1.y + p1.y; acc[s][6] = r1.z + p1.z; acc[s][7] = r1.w + p1.w;
+                if (any != 0u) {
+                    float corr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int q = 0; q < HOPW; ++q) {
+                        {
+                            uint32_t d = ew[s][q] ^ xw[q];
+                            while (d != 0u) {
+                                const int e = (__ffs(d) - 1) >> 3;
+                                const int v = (ew[s][q] >> (8 * e)) & 0xFF, x = (xw[q] >> (8 * e)) & 0xFF;
+                                const float *row = EWg + (size_t)(q * 4 + e) * kEdgeVocab * kH;
+                                add8(corr, row + min(v, kEdgeVocab - 1) * kH);
+                                sub8(corr, row + x * kH);
+                                d &= ~(0xFFu << (8 * e));
+                            }
+                        }
+                    }
+                    const float inv = 1.0f / (float)min(max(rk - 1, 1), c.hops);
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) acc[s][h] += corr[h] * inv;
                 }
             }
         }
-        __syncthreads();
-        // ---- phase B: the listed cells, 8 lanes (heads) each
-        const int cnt = dcount[buf];
-        const int h = threadIdx.x & 7;
-        for (int e = threadIdx.x >> 3; e < cnt; e += (int)blockDim.x >> 3) {
-            const int code = dlist[buf][e];
-            const int f = tile * blockDim.x + (code >> 1), s = code & 1;
-            const int a = (int)(((uint64_t)f * half_magic) >> 40), b = (f - a * half) * 2;
-            const int j = b - 1 + s;
-            const int64_t pc = sq + (int64_t)(a - 1) * n + j;
-            const int rk = min(max((int)c.rel_pos[pc], 0), kRelRows - 1);
-            const int pk = min(max((int)c.poi_pos[pc], 0), num_bins - 1);
-            const int L = expected_walk(rk, c.hops);
-            const uint32_t *ei = reinterpret_cast<const uint32_t *>(c.edge_in + pc * c.hops);
-            float corr = 0.f;
+        OutT *o = out + ((size_t)g * kH * c.T + a) * c.Tp + b;
+        if (two) {
 #pragma unroll
-            for (int q = 0; q < HOPW; ++q) {
-                const uint32_t ewq = __ldg(ei + q), xwq = XW[L * 8 + q];
-                uint32_t d = ewq ^ xwq;
-                while (d != 0u) {
-                    const int eb = (__ffs(d) - 1) >> 3;
-                    const int v = (ewq >> (8 * eb)) & 0xFF, x = (xwq >> (8 * eb)) & 0xFF;
-                    const float *row = EWg + (size_t)(q * 4 + eb) * kEdgeVocab * kH + h;
-                    corr += __ldg(row + min(v, kEdgeVocab - 1) * kH) - __ldg(row + x * kH);
-                    d &= ~(0xFFu << (8 * eb));
-                }
-            }
-            const float inv = 1.0f / (float)min(max(rk - 1, 1), c.hops);
-            const float val = (RL[rk * kH + h] + Pp[pk * kH + h]) + corr * inv;
-            store1<OutT>(out + ((size_t)(g * kH + h) * c.T + a) * c.Tp + b + s, val);
+            for (int h = 0; h < 8; ++h) store2<OutT>(o + h * hs, acc[0][h], acc[1][h]);
+        } else {
+#pragma unroll
+            for (int h = 0; h < 8; ++h) store1<OutT>(o + h * hs, acc[0][h]);
         }
     }
 }
@@ -297,7 +272,7 @@ __host__ __device__ inline K2BwdPlan k2_bwd_plan(int T, int Tp, int hops, int nu
     p.nP = num_bins * kH;
     p.stride = p.nEWs + p.nR + p.nP + kH;
     p.pitch = ((Tp + 27) / 32) * 32 + 4;
-    p.per_warp = 2 * (p.nR + p.nP) + kH * p.pitch + 2 * p.pitch + kH;      // hR | hP | dsum | cinfo | cdev | t
+    p.per_warp = 2 * (p.nR + kH) + 2 * (p.nP + kH) + kH * p.pitch + 3 * p.pitch + kH;   // hR+trash | hP+trash | dsum | cinfo | cdev | dlist | t
     p.cta_words = p.nEWs + (hops + 1) * 8 + 40;                            // sEW | XW | 1/sp table
     int w = (int)((227 * 1024 - 2048 - p.cta_words * 4) / (p.per_warp * 4));
     p.warps = w > 16 ? 16 : w;
@@ -335,14 +310,16 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
     float *invT = sm + pl.nEWs + (c.hops + 1) * 8;                // [40]: 1 / sp
     float *wbase = sm + pl.cta_words;
     const uint32_t s_warp = (uint32_t)__cvta_generic_to_shared(wbase + (size_t)warp * pl.per_warp);
-    const uint32_t s_hR = s_warp;                                 // [Rrows][2][8]
-    const uint32_t s_hP = s_hR + 2u * pl.nR * 4u;                 // [bins][2][8]
-    const uint32_t s_dsum = s_hP + 2u * pl.nP * 4u;               // [8][pitch]
-    const uint32_t s_cinfo = s_dsum + (uint32_t)(kH * pl.pitch) * 4u;   // [pitch]
+    const uint32_t s_hR = s_warp;                                 // [Rrows + 1][2][8]   (last row: trash)
+    const uint32_t s_hP = s_hR + 2u * (pl.nR + kH) * 4u;          // [bins + 1][2][8]    (last row: trash)
+    const uint32_t s_dsum = s_hP + 2u * (pl.nP + kH) * 4u;        // [8][pitch]
+    const uint32_t s_cinfo = s_dsum + (uint32_t)(kH * pl.pitch) * 4u;   // [pitch]: R row | P row << 16
     const uint32_t s_cdev = s_cinfo + (uint32_t)pl.pitch * 4u;    // [pitch]
-    const uint32_t s_T = s_cdev + (uint32_t)pl.pitch * 4u;        // [8]
+    const uint32_t s_dlist = s_cdev + (uint32_t)pl.pitch * 4u;    // [pitch]: cells that need the slow path
+    const uint32_t s_T = s_dlist + (uint32_t)pl.pitch * 4u;       // [8]
     const uint32_t s_hist = (ty ? s_hP : s_hR) + (uint32_t)(c2 * kH + h) * 4u;      // + key * 64 B
-    const uint32_t key_shift = ty ? 10u : 0u;
+    const uint32_t key_shift = ty ? 16u : 0u;
+    const uint32_t trashR = (uint32_t)pl.Rrows, trashP = (uint32_t)num_bins;
     const int hopw = c.hops >> 2;
     for (int i = threadIdx.x; i < pl.nEWs; i += blockDim.x) sEW[i] = 0.f;
     for (int i = threadIdx.x; i < (c.hops + 1) * 8; i += blockDim.x) XW[i] = (i & 7) < hopw ? expected_word(i >> 3, i & 7) : 0u;
@@ -421,10 +398,14 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
                 }
             }
         }
-        // ---- 2. index phase: cinfo[b] = R row | P row << 10 | flags ;  cdev[b] = up to two deviating bytes
-        for (int b = lane; b < Tg; b += 32) {
-            uint32_t info = kInfoCol0, dev = 0u;
-            if (b >= 1) {
+        // ---- 2. index phase: cinfo[b] = R row | P row << 16 (the trash rows for cells that carry no gradient) ;
+        //         cdev[b] = up to two deviating bytes ;  dlist = the cells that need the slow path
+        int ndl = 0;
+        const int Tg4 = (Tg + 3) & ~3;
+        for (int b0 = 0; b0 < Tg4; b0 += 32) {
+            const int b = b0 + lane;
+            uint32_t info = trashR | (trashP << 16), dev = 0u, slow = 0u;
+            if (b >= 1 && b < Tg) {
                 const int64_t pc = rowp + b;
                 const int rp = c.rel_pos[pc], pp = c.poi_pos[pc];
                 const uint32_t *ei = reinterpret_cast<const uint32_t *>(c.edge_in + pc * c.hops);
@@ -434,95 +415,99 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
                 const int rk = min(max(rp, 0), kRelRows - 1);
                 const int L = expected_walk(rk, c.hops);
                 const int row = (rk == 511) ? pl.Rrows - 1 : (rk < pl.Rrows - 1 ? rk : -1);
-                info = (uint32_t)(row < 0 ? 0 : row) | ((uint32_t)min(max(pp, 0), num_bins - 1) << 10);
-                if (rk - 1 < c.rel_pos_max) info |= kInfoPair;        // -inf entries carry no gradient
-                if (row < 0) info |= kInfoOvf;                       // key outside the plan (never for K1 output)
-                if (rk - 1 >= 510) info |= kInfoUnreach;
-                int ndev = 0;
-                dev = (uint32_t)L << 2;
+                if (rk - 1 < c.rel_pos_max) {                        // -inf entries carry no gradient
+                    info = (row < 0 ? trashR : (uint32_t)row) | ((uint32_t)min(max(pp, 0), num_bins - 1) << 16);
+                    int ndev = 0;
+                    dev = (uint32_t)L << 2;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    uint32_t df = ew[q] ^ XW[L * 8 + q];
-                    while (df != 0u) {
-                        const int e = (__ffs(df) - 1) >> 3;
-                        if (ndev < 2) dev |= (((uint32_t)(q * 4 + e) << 7) | ((ew[q] >> (8 * e)) & 0x7Fu)) << (8 + 12 * ndev);
-                        ++ndev;
-                        df &= ~(0xFFu << (8 * e));
+                    for (int q = 0; q < 8; ++q) {
+                        uint32_t df = ew[q] ^ XW[L * 8 + q];
+                        while (df != 0u) {
+                            const int e = (__ffs(df) - 1) >> 3;
+                            if (ndev < 2) dev |= (((uint32_t)(q * 4 + e) << 7) | ((ew[q] >> (8 * e)) & 0x7Fu)) << (8 + 12 * ndev);
+                            ++ndev;
+                            df &= ~(0xFFu << (8 * e));
+                        }
                     }
+                    dev |= (uint32_t)min(ndev, 3);
+                    if (ndev || row < 0)
+                        slow = (uint32_t)b | (row < 0 ? 1u << 12 : 0u) | (rk - 1 >= 510 ? 1u << 13 : 0u) | (ndev ? 1u << 14 : 0u) | (1u << 31);
                 }
-                if (ndev) info |= kInfoDev;
-                dev |= (uint32_t)min(ndev, 3);
             }
-            sts_u32(s_cinfo + (uint32_t)b * 4u, info);
-            sts_u32(s_cdev + (uint32_t)b * 4u, dev);
+            if (b < Tg4) {
+                sts_u32(s_cinfo + (uint32_t)b * 4u, info);
+                sts_u32(s_cdev + (uint32_t)b * 4u, dev);
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, slow != 0u);
+            if (slow) sts_u32(s_dlist + (uint32_t)(ndl + __popc(bal & ((1u << lane) - 1u))) * 4u, slow);
+            ndl += __popc(bal);
         }
         __syncwarp();
-        // ---- 3. histogram phase: lane = (table, cell slot c2, head h); cells b0 + c2 and b0 + 2 + c2 per iteration
-        for (int b0 = 0; b0 < Tg; b0 += 4) {
-            const int bA = b0 + c2, bB = b0 + 2 + c2;
-            const uint32_t iA = bA < Tg ? lds_u32(s_cinfo + (uint32_t)bA * 4u) : 0u;
-            const uint32_t iB = bB < Tg ? lds_u32(s_cinfo + (uint32_t)bB * 4u) : 0u;
-            const float dA = bA < Tg ? lds_f32(s_dsum + (uint32_t)h * pitch4 + (uint32_t)bA * 4u) : 0.f;
-            const float dB_ = bB < Tg ? lds_f32(s_dsum + (uint32_t)h * pitch4 + (uint32_t)bB * 4u) : 0.f;
-            if (ty == 0) tacc += ((iA & kInfoCol0) ? dA : 0.f) + ((iB & kInfoCol0) ? dB_ : 0.f);
-            const bool okA = (iA & kInfoPair) && !(ty == 0 && (iA & kInfoOvf));
-            const bool okB = (iB & kInfoPair) && !(ty == 0 && (iB & kInfoOvf));
-            const uint32_t aA = s_hist + ((iA >> key_shift) & 1023u) * 64u;
-            const uint32_t aB = s_hist + ((iB >> key_shift) & 1023u) * 64u;
-            // two read-modify-writes in flight; equal addresses are chained in registers, the second store wins
-            const float vA = lds_f32(aA), vB = lds_f32(aB);
-            const float nA = vA + (okA ? dA : 0.f);
-            const float nB = ((aA == aB) ? nA : vB) + (okB ? dB_ : 0.f);
-            sts_f32(aA, nA);
-            sts_f32(aB, nB);
-            if ((iA | iB) & (kInfoDev | kInfoOvf)) {
-                // rare: walk bytes that differ from the expected walk (R lanes: 8 heads of the cell), keys outside the plan
-#pragma unroll 1
-                for (int s = 0; s < 2; ++s) {
-                    const uint32_t info = s ? iB : iA;
-                    const int b = s ? bB : bA;
-                    const float d = s ? dB_ : dA;
-                    if (ty != 0 || !(info & kInfoPair)) continue;
-                    if (info & kInfoOvf) atomicAdd(dR_overflow + min(max((int)c.rel_pos[rowp + b], 0), kRelRows - 1) * kH + h, d);
-                    if (!(info & kInfoDev)) continue;
-                    const uint32_t cd = lds_u32(s_cdev + (uint32_t)b * 4u);
-                    const int L = (cd >> 2) & 63, nd = cd & 3;
-                    const float dinv = d * invT[(info & kInfoUnreach) ? c.hops : max(L, 1)];
-                    if (nd <= 2) {
-                        for (int j = 0; j < nd; ++j) {
-                            const uint32_t e = (cd >> (8 + 12 * j)) & 4095u;
-                            const int k = e >> 7, v = e & 127, x = k < L ? kDomEdge : 0;
-                            if (v != 0) {
-                                if (v < kSmallVocab) atomicAdd(sEW + (k * kSmallVocab + v) * kH + h, dinv);
-                                else atomicAdd(dEWfull + ((size_t)k * kEdgeVocab + v) * kH + h, dinv);
-                            }
-                            if (x != 0) atomicAdd(sEW + (k * kSmallVocab + x) * kH + h, -dinv);
+        // ---- 3. histogram phase: lane = (table, cell slot c2, head h); adjacent cells b0 + 2 c2, b0 + 2 c2 + 1 per step.
+        //         Cells without a gradient point at the trash rows, so the loop carries no predicates.
+        if (lane < 8) tacc += lds_f32(s_dsum + (uint32_t)h * pitch4);          // column 0: graph-token virtual distance
+        {
+            uint32_t pi = s_cinfo + (uint32_t)c2 * 8u, pd = s_dsum + (uint32_t)h * pitch4 + (uint32_t)c2 * 8u;
+            for (int b0 = 0; b0 < Tg4; b0 += 4, pi += 16u, pd += 16u) {
+                uint32_t iA, iB;
+                float dA, dB_;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(iA), "=r"(iB) : "r"(pi) : "memory");
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(dA), "=f"(dB_) : "r"(pd) : "memory");
+                const uint32_t aA = s_hist + ((iA >> key_shift) & 0xFFFFu) * 64u;
+                const uint32_t aB = s_hist + ((iB >> key_shift) & 0xFFFFu) * 64u;
+                // two read-modify-writes in flight; equal addresses are chained in registers, the second store wins
+                const float vA = lds_f32(aA), vB = lds_f32(aB);
+                const float nA = vA + dA;
+                const float nB = ((aA == aB) ? nA : vB) + dB_;
+                sts_f32(aA, nA);
+                sts_f32(aB, nB);
+            }
+        }
+        // ---- slow path (rare): walk bytes that differ from the expected walk, keys outside the plan; 8 lanes = 8 heads per
+        //      listed cell, 4 cells at a time
+        for (int e0 = 0; e0 < ndl; e0 += 4) {
+            const int e = e0 + (lane >> 3);
+            if (e >= ndl) continue;
+            const uint32_t ent = lds_u32(s_dlist + (uint32_t)e * 4u);
+            const int b = ent & 0xFFF;
+            const float d = lds_f32(s_dsum + (uint32_t)h * pitch4 + (uint32_t)b * 4u);
+            if (ent & (1u << 12)) atomicAdd(dR_overflow + min(max((int)c.rel_pos[rowp + b], 0), kRelRows - 1) * kH + h, d);
+            if (!(ent & (1u << 14))) continue;
+            const uint32_t cd = lds_u32(s_cdev + (uint32_t)b * 4u);
+            const int L = (cd >> 2) & 63, nd = cd & 3;
+            const float dinv = d * invT[(ent & (1u << 13)) ? c.hops : max(L, 1)];
+            if (nd <= 2) {
+                for (int j = 0; j < nd; ++j) {
+                    const uint32_t en = (cd >> (8 + 12 * j)) & 4095u;
+                    const int k = en >> 7, v = en & 127, x = k < L ? kDomEdge : 0;
+                    if (v != 0) {
+                        if (v < kSmallVocab) atomicAdd(sEW + (k * kSmallVocab + v) * kH + h, dinv);
+                        else atomicAdd(dEWfull + ((size_t)k * kEdgeVocab + v) * kH + h, dinv);
+                    }
+                    if (x != 0) atomicAdd(sEW + (k * kSmallVocab + x) * kH + h, -dinv);
+                }
+            } else {
+                const uint32_t *ei = reinterpret_cast<const uint32_t *>(c.edge_in + (rowp + b) * c.hops);
+                for (int q = 0; q < hopw; ++q) {
+                    const uint32_t ew = __ldg(ei + q), xw = XW[L * 8 + q];
+                    uint32_t df = ew ^ xw;
+                    while (df != 0u) {
+                        const int eb = (__ffs(df) - 1) >> 3;
+                        const int v = (ew >> (8 * eb)) & 0xFF, x = (xw >> (8 * eb)) & 0xFF;
+                        const int k = q * 4 + eb;
+                        if (v != 0) {
+                            if (v < kSmallVocab) atomicAdd(sEW + (k * kSmallVocab + v) * kH + h, dinv);
+                            else atomicAdd(dEWfull + ((size_t)k * kEdgeVocab + min(v, kEdgeVocab - 1)) * kH + h, dinv);
                         }
-                    } else {
-                        const uint32_t *ei = reinterpret_cast<const uint32_t *>(c.edge_in + (rowp + b) * c.hops);
-                        for (int q = 0; q < hopw; ++q) {
-                            const uint32_t ew = __ldg(ei + q), xw = XW[L * 8 + q];
-                            uint32_t df = ew ^ xw;
-                            while (df != 0u) {
-                                const int e = (__ffs(df) - 1) >> 3;
-                                const int v = (ew >> (8 * e)) & 0xFF, x = (xw >> (8 * e)) & 0xFF;
-                                const int k = q * 4 + e;
-                                if (v != 0) {
-                                    if (v < kSmallVocab) atomicAdd(sEW + (k * kSmallVocab + v) * kH + h, dinv);
-                                    else atomicAdd(dEWfull + ((size_t)k * kEdgeVocab + min(v, kEdgeVocab - 1)) * kH + h, dinv);
-                                }
-                                if (x != 0) atomicAdd(sEW + (k * kSmallVocab + x) * kH + h, -dinv);
-                                df &= ~(0xFFu << (8 * e));
-                            }
-                        }
+                        if (x != 0) atomicAdd(sEW + (k * kSmallVocab + x) * kH + h, -dinv);
+                        df &= ~(0xFFu << (8 * eb));
                     }
                 }
             }
         }
         __syncwarp();
     }
-    // column-0 sums: R lanes (ty == 0) hold a partial per (c2, h); fold the cell slots
-    tacc += __shfl_xor_sync(0xffffffffu, tacc, 8);
+    // column-0 sums: lanes 0..7 hold them
     if (lane < 8) sts_f32(s_T + (uint32_t)h * 4u, tacc);
     __syncthreads();
     // CTA totals -> partial[blockIdx]
@@ -539,7 +524,7 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
         const int key = i / kH, hh = i % kH;
         float s = 0.f;
         for (int w = 0; w < nwarp; ++w)
-            for (int r = 0; r < 2; ++r) s += wbase[(size_t)w * pl.per_warp + 2 * pl.nR + (key * 2 + r) * kH + hh];
+            for (int r = 0; r < 2; ++r) s += wbase[(size_t)w * pl.per_warp + 2 * (pl.nR + kH) + (key * 2 + r) * kH + hh];
         out[pl.nEWs + pl.nR + i] = s;
     }
     if (threadIdx.x < kH) {

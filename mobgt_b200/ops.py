@@ -234,10 +234,9 @@ class EmbedGather(torch.autograd.Function):
         dout = dout.contiguous()
         plans = b.__dict__.setdefault("_plans", {})
         if "poi" not in plans:
-            poi = b.x_nodes.long() - 1
-            plans["poi"] = sort_plan(poi)
-            plans["slot"] = sort_plan(b.slot)
-            plans["cat"] = sort_plan(ctx.cat_of_poi[poi].long() - 1)
+            b.build_plans()
+        if "cat" not in plans:
+            plans["cat"] = sort_plan(ctx.cat_of_poi[b.x_nodes.long() - 1].long() - 1)
         dGd = segment_sum_raw(dout, 0, Dp, plans["poi"], P)
         dTm = segment_sum_raw(dout, Dp, Dt, plans["slot"], Tr)
         dGc = segment_sum_raw(dout, Dp + Dt, Dc, plans["cat"], C)
@@ -262,15 +261,7 @@ class EmbedSum(torch.autograd.Function):
         D = dtok.shape[1]
         plans = b.__dict__.setdefault("_plans", {})
         if "pos" not in plans:
-            node_rows = (b.tok_pos > 0).nonzero().view(-1)
-            plans["node_rows"] = node_rows
-            plans["pos"] = sort_plan(b.tok_pos)
-            ind = torch.zeros_like(b.tok_pos)
-            ind[node_rows] = b.in_deg
-            outd = torch.zeros_like(b.tok_pos)
-            outd[node_rows] = b.out_deg
-            plans["ind"] = sort_plan(ind)
-            plans["outd"] = sort_plan(outd)
+            b.build_plans()
         (ri, _), (ro, _), (rp, _) = ctx.shapes
         d_nf = dtok.index_select(0, plans["node_rows"])
         dDin = segment_sum_raw(dtok, 0, D, plans["ind"], ri)
