@@ -178,12 +178,16 @@ int32_t mobgt_segment_sum(const void *src, int32_t src_dtype, int64_t src_stride
  *   mode 0: st[row] = logit of the row's target, written by the shard that owns it (initialise st to -inf; across
  *           shards: all-reduce MAX)
  *   mode 1: per (row, split): sorted top-k (value, global index), count(s > st), count(s == st and idx < target)
+ *   thr_share: u32 [M] zero-initialised scratch or NULL.  Every list of a row publishes its k-th value there (atomic max of
+ *           order-preserving bits); since the k-th value of ANY subset bounds the row's final k-th value from below, all
+ *           lists of the row (all splits, and — over NVLink peer memory or after an all-reduce MAX — all shards) prune
+ *           with it.  The merged top-k is unchanged; lists may come back shorter than k (index -1 = empty slot).
  * mobgt_topk_merge merges S sorted lists per row (ties -> lower index) and sums the counts into rank[M].
  * ------------------------------------------------------------------------------------------ */
 int32_t mobgt_head_topk(const void *z, const void *W, const float *bias, const int32_t *target, int32_t M, int32_t V,
                         int32_t K, int64_t vocab_offset, int32_t k, int32_t nsplit, int32_t mode, float *st,
                         float *topk_val, int32_t *topk_idx, int32_t *cnt_gt, int32_t *cnt_eq, float *logits_dump,
-                        void *stream);
+                        void *thr_share, void *stream);
 int32_t mobgt_topk_merge(const float *val, const int32_t *idx, const int32_t *cnt_gt, const int32_t *cnt_eq, int32_t M,
                          int32_t S, int32_t k, float *out_val, int32_t *out_idx, int32_t *rank, void *stream);
 

@@ -39,7 +39,7 @@ SIGNATURES = {
     "mobgt_embed_gather_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],
     "mobgt_embed_sum_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p],
     "mobgt_segment_sum": [c_p, c_i32, c_i64, c_i32, c_i32, c_p, c_p, c_i32, c_p, c_i32, c_p, c_i64, c_p],
-    "mobgt_head_topk": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+    "mobgt_head_topk": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "mobgt_topk_merge": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p],
     "mobgt_debug_set_timeline": [c_p],
     "mobgt_selftest_umma": [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p],

@@ -50,6 +50,8 @@ struct HeadParams {
     float *logits;           // optional [M, V]
     int M, V, K, k, nsplit, mode;
     int ring;                // W stages in shared memory
+    long long *timeline;     // debug (mobgt_debug_set_timeline) or NULL
+    uint32_t *thr_share;     // [M] best k-th value seen by ANY list of the row (order-preserving bits; 0 = none) or NULL
     int64_t vocab_offset;
 };
 
@@ -100,6 +102,7 @@ __device__ __forceinline__ void list_insert(unsigned long long (&list)[LK], unsi
 // here, off the hot path
 template <int LK>
 __device__ __forceinline__ float list_drain(unsigned long long (&list)[LK], uint32_t cd, int &ncand, long long vocab_offset) {
+#pragma unroll 1
     while (ncand > 0) {
         --ncand;
         const unsigned long long raw = lds64(cd + (uint32_t)ncand * kEnt);
@@ -110,12 +113,37 @@ __device__ __forceinline__ float list_drain(unsigned long long (&list)[LK], uint
     const unsigned long long kth = list[LK - 1];
     return kth ? ord2f((uint32_t)(kth >> 32)) : -INFINITY;
 }
+// append one raw candidate entry {column, value bits}; Q = column offset inside the 32-column chunk (immediate)
+template <int Q>
+__device__ __forceinline__ void cand_append(uint32_t addr, uint32_t cb, float v) {
+    asm volatile(
+        "{\n\t.reg .u32 c;\n\t"
+        "add.u32 c, %1, %2;\n\t"
+        "st.shared.v2.u32 [%0], {c, %3};\n\t}"
+        ::"r"(addr), "r"(cb), "n"(Q), "r"(__float_as_uint(v))
+        : "memory");
+}
+template <int LK, int G>
+__device__ __forceinline__ void harvest_groups(const float (&v)[32], const float (&m4)[8], unsigned long long (&list)[LK],
+                                               float &thr, int &ncand, uint32_t cd, uint32_t cb, long long vocab_offset) {
+    if constexpr (G < 8) {
+        if (m4[G] > thr) {
+            if (ncand > kCandCap - 4) thr = fmaxf(thr, list_drain<LK>(list, cd, ncand, vocab_offset));
+            if (v[4 * G] > thr) { cand_append<4 * G>(cd + (uint32_t)ncand * kEnt, cb, v[4 * G]); ++ncand; }
+            if (v[4 * G + 1] > thr) { cand_append<4 * G + 1>(cd + (uint32_t)ncand * kEnt, cb, v[4 * G + 1]); ++ncand; }
+            if (v[4 * G + 2] > thr) { cand_append<4 * G + 2>(cd + (uint32_t)ncand * kEnt, cb, v[4 * G + 2]); ++ncand; }
+            if (v[4 * G + 3] > thr) { cand_append<4 * G + 3>(cd + (uint32_t)ncand * kEnt, cb, v[4 * G + 3]); ++ncand; }
+        }
+        harvest_groups<LK, G + 1>(v, m4, list, thr, ncand, cd, cb, vocab_offset);
+    }
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 // spin with back-off: the TMA / MMA warps share their schedulers with epilogue warps and must not eat their issue slots
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(24);
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity, unsigned ns = 24) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
 }
 
 template <int LK>
@@ -130,6 +158,9 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
     const int lane = tid & 31;
     const int mt = blockIdx.x, sp = blockIdx.y;
     const int kblocks = ceil_div(p.K, kKB);
+    // timing experiments only (scripts/k5bench.py --dbg): mode bits 8.. = skip harvest (1) / skip count + harvest (2); bits 12.. = spin back-off / 8 ns
+    const int dbg = (p.mode >> 8) & 15;
+    const unsigned spin_ns = ((p.mode >> 12) & 15) ? 8u * ((p.mode >> 12) & 15) : 24u;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
     uint8_t *sB = sA + (size_t)kblocks * kBlkBytes;
@@ -172,7 +203,7 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % p.ring;
                     const uint32_t ph = (uint32_t)(it / p.ring) & 1u;
-                    mbar_wait_relaxed(&bar_empty[s], ph ^ 1u);
+                    mbar_wait_relaxed(&bar_empty[s], ph ^ 1u, spin_ns);
                     mbar_expect_tx(&bar_full[s], (uint32_t)kBlkBytes);
                     tma_load_2d(sB + (size_t)s * kBlkBytes, &tmW, &bar_full[s], kb * kKB, n * kHeadTile);
                 }
@@ -188,17 +219,21 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
             int it = 0;
             for (int t = 0; t < T; ++t) {
                 const int a = t & 1;
-                mbar_wait_relaxed(&acc_empty[a], ((uint32_t)(t >> 1) & 1u) ^ 1u);
+                const bool stamp = p.timeline != nullptr && blockIdx.x == 1 && blockIdx.y == 1 && t < 14;
+                if (stamp) p.timeline[16 + 4 * t] = clock64();
+                mbar_wait_relaxed(&acc_empty[a], ((uint32_t)(t >> 1) & 1u) ^ 1u, spin_ns);
                 tc_fence_after();
+                if (stamp) p.timeline[16 + 4 * t + 1] = clock64();
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % p.ring;
-                    mbar_wait_relaxed(&bar_full[s], (uint32_t)(it / p.ring) & 1u);
+                    mbar_wait_relaxed(&bar_full[s], (uint32_t)(it / p.ring) & 1u, spin_ns);
                     tc_fence_after();
                     const int ksteps = min(kKB, p.K - kb * kKB) / 16;
                     for (int j = 0; j < ksteps; ++j)
                         umma_bf16(tmem + (uint32_t)(a * kHeadTile), make_smem_desc_sw128(a0 + kb * kBlkBytes + j * 32),
                                   make_smem_desc_sw128(b0 + s * kBlkBytes + j * 32), idesc, (kb | j) != 0);
                     umma_commit(&bar_empty[s]);
+                    if (stamp && kb == kblocks - 1) p.timeline[16 + 4 * t + 2] = clock64();
                 }
                 umma_commit(&acc_full[a]);
             }
@@ -223,6 +258,7 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
         for (int j = 0; j < LK; ++j) list[j] = 0ull;
         float thr = -INFINITY;
         int ncand = 0, cnt = 0;
+        uint32_t last_pub = 0u;
         // bias of column col_base + r of the tile (one element per thread, coalesced): -inf past the vocabulary, so the
         // zero accumulators of the TMA-zero-filled tail rows neither count nor qualify
         auto tile_bias = [&](int t) -> float {
@@ -235,12 +271,18 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
         for (int t = e; t < T; t += 2, ++it) {
             const int n = n_begin + t;
             const int col_base = n * kHeadTile;
+            // the best k-th value any list of this row has published so far: a lower bound of the row's final k-th value, so
+            // every list may use it as its threshold (>= : ties must survive, hence prev_float)
+            const uint32_t gshare = (p.thr_share != nullptr && row_ok) ? __ldcg(p.thr_share + row) : 0u;
             const uint32_t sb = sbias + (uint32_t)(it & 1) * kHeadTile * 4;
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb + (uint32_t)r * 4), "f"(bnext) : "memory");
             if (t + 2 < T) bnext = tile_bias(t + 2);
             named_bar_sync(1 + e, kHeadTile);
             mbar_wait(&acc_full[e], (uint32_t)(t >> 1) & 1u);
             tc_fence_after();
+            if (gshare != 0u) thr = fmaxf(thr, prev_float(ord2f(gshare)));
+            const bool estamp = p.timeline != nullptr && blockIdx.x == 1 && blockIdx.y == 1 && t < 14 && r == 0;
+            if (estamp) p.timeline[80 + 4 * t] = clock64();
 #pragma unroll 1
             for (int c0 = 0; c0 < kHeadTile; c0 += 32) {
                 uint32_t acc[32];
@@ -258,6 +300,7 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[e]);
+                    if (estamp) p.timeline[80 + 4 * t + 1] = clock64();
                 }
 #pragma unroll
                 for (int q = 0; q < 32; ++q) v[q] += __uint_as_float(acc[q]);
@@ -278,6 +321,11 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
                     }
                 }
                 float m4[8];
+                if (dbg & 2) {
+                    cnt += (int)(__float_as_uint(v[0] + v[31]) >> 31);
+                    __syncwarp();
+                    continue;
+                }
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                     const float v0 = v[4 * g], v1 = v[4 * g + 1], v2 = v[4 * g + 2], v3 = v[4 * g + 3];
@@ -285,38 +333,23 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
                            (int)(__float_as_uint(cmp - v2) >> 31) + (int)(__float_as_uint(cmp - v3) >> 31);
                     m4[g] = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
                 }
-                // harvest the top-k candidates of the chunk, group by group; a full buffer leaves the pass, is drained (the
-                // single in-tile insertion site) and the pass resumes at the group it stopped at
-                int g0 = 0;
-                for (;;) {
-                    bool full_buf = false;
-#pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        if (!full_buf && g >= g0 && m4[g] > thr) {
-                            if (ncand > kCandCap - 4) {
-                                full_buf = true;
-                                g0 = g;
-                            } else {
-                                uint32_t colg;           // opaque: keeps the column arithmetic inside this rare block
-                                asm volatile("add.u32 %0, %1, %2;" : "=r"(colg) : "r"((uint32_t)cb), "r"(4u * g));
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    if (v[4 * g + i] > thr) {
-                                        sts64(cd + (uint32_t)ncand * kEnt,
-                                              ((unsigned long long)__float_as_uint(v[4 * g + i]) << 32) | (colg + (uint32_t)i));
-                                        ++ncand;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    if (!full_buf) break;
-                    thr = list_drain<LK>(list, cd, ncand, p.vocab_offset);
-                }
+                // harvest the top-k candidates of the chunk, group by group (rare after the first tiles).  The column and the
+                // 64-bit entry are formed INSIDE the store's asm block, so nothing of the rare path is hoisted into the
+                // common one; a buffer without room for 4 more entries is drained on the spot.
+                if (!(dbg & 1)) harvest_groups<LK, 0>(v, m4, list, thr, ncand, cd, (uint32_t)cb, p.vocab_offset);
                 __syncwarp();     // tcgen05.ld is warp-collective: reconverge before the next chunk
             }
-            thr = list_drain<LK>(list, cd, ncand, p.vocab_offset);   // all lanes together; fresh threshold for the next tile
+            {   // all lanes together; fresh threshold for the next tile (never below a bound taken from thr_share)
+                const float own = list_drain<LK>(list, cd, ncand, p.vocab_offset);
+                thr = fmaxf(thr, own);
+                const uint32_t kth = (uint32_t)(list[LK - 1] >> 32);
+                if (p.thr_share != nullptr && row_ok && kth > last_pub && kth > gshare) {
+                    atomicMax(p.thr_share + row, kth);
+                    last_pub = kth;
+                }
+            }
             __syncwarp();
+            if (estamp) p.timeline[80 + 4 * t + 2] = clock64();
         }
         if (row_ok) {
             const size_t o = (size_t)row * p.nsplit + (size_t)sp * 2 + e;
@@ -481,7 +514,7 @@ using namespace mobgt;
 extern "C" int32_t mobgt_head_topk(const void *z, const void *W, const float *bias, const int32_t *target, int32_t M,
                                    int32_t V, int32_t K, int64_t vocab_offset, int32_t k, int32_t nsplit, int32_t mode,
                                    float *st, float *topk_val, int32_t *topk_idx, int32_t *cnt_gt, int32_t *cnt_eq,
-                                   float *logits_dump, void *stream) {
+                                   float *logits_dump, void *thr_share, void *stream) {
     MOBGT_REQUIRE(z && W && target && st, MOBGT_ERR_NULL, "mobgt_head_topk: null pointer");
     MOBGT_REQUIRE(mode == 0 || (topk_val && topk_idx && cnt_gt && cnt_eq), MOBGT_ERR_NULL, "mobgt_head_topk: null output");
     MOBGT_REQUIRE(K % 16 == 0 && K >= 16 && K <= kHeadMaxK, MOBGT_ERR_BAD_SHAPE, "mobgt_head_topk: K=%d", K);
@@ -511,7 +544,7 @@ extern "C" int32_t mobgt_head_topk(const void *z, const void *W, const float *bi
     ring = ring > kMaxRing ? kMaxRing : ring;
     MOBGT_REQUIRE(ring >= 2, MOBGT_ERR_UNSUPPORTED, "mobgt_head_topk: no shared-memory plan for K=%d k=%d", K, k);
     const size_t smem = fixed + (size_t)ring * kBlkBytes;
-    HeadParams p{bias, target, st, topk_val, topk_idx, cnt_gt, cnt_eq, logits_dump, M, V, K, k, nsplit, mode, ring, vocab_offset};
+    HeadParams p{bias, target, st, topk_val, topk_idx, cnt_gt, cnt_eq, logits_dump, M, V, K, k, nsplit, mode, ring, g_timeline_dev, static_cast<uint32_t *>(thr_share), vocab_offset};
     dim3 grid((unsigned)ceil_div(M, kHeadTile), (unsigned)(nsplit / 2));
     // the list length is a compile-time constant (register-resident list): the smallest built size >= k
     auto launch = [&](auto kern) -> int32_t {

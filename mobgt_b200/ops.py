@@ -276,13 +276,15 @@ class EmbedSum(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------- K5
 def head_split(M, V):
     """Number of per-row output lists = 2 x (vocabulary splits per 128-row tile of z): every CTA of mobgt_head_topk runs two
-    epilogue groups.  The split count minimises waves x (tiles per CTA + a fixed per-CTA cost) over the 148 SMs."""
+    epilogue groups.  The split count minimises waves x (tiles per CTA + a fixed per-CTA cost) over the 148 SMs.  The fixed
+    cost is the warm-up of a fresh top-k list (every early element is a candidate): measured on B200 with the kernel's
+    clock64 timeline (scripts/k5bench.py --timeline), ~120k cycles per CTA = 33 streamed tiles at the TMA-bound tile time."""
     mt = (M + 127) // 128
     nt = (V + 127) // 128
     best, best_cost = 1, None
     for gs in range(1, min(32, nt) + 1):
         waves = (mt * gs + 147) // 148
-        cost = waves * ((nt + gs - 1) // gs + 8)
+        cost = waves * ((nt + gs - 1) // gs + 33)
         if best_cost is None or cost < best_cost:
             best, best_cost = gs, cost
     return 2 * best
@@ -299,13 +301,14 @@ def head_topk_local(z, W, bias, target, k, vocab_offset=0, st=None, dump_logits=
     args = (_C.ptr(z), _C.ptr(W), _C.ptr(bias), _C.ptr(target), M, V, K, int(vocab_offset), k, ns)
     if st is None:
         st = torch.full((M,), float("-inf"), dtype=torch.float32, device=dev)
-        _C.call("mobgt_head_topk", *args, 0, _C.ptr(st), None, None, None, None, None, s)
+        _C.call("mobgt_head_topk", *args, 0, _C.ptr(st), None, None, None, None, None, None, s)
     tv = torch.empty(M, ns, k, dtype=torch.float32, device=dev)
     ti = torch.empty(M, ns, k, dtype=torch.int32, device=dev)
     cg = torch.empty(M, ns, dtype=torch.int32, device=dev)
     ce = torch.empty(M, ns, dtype=torch.int32, device=dev)
     logits = torch.empty(M, V, dtype=torch.float32, device=dev) if dump_logits else None
-    _C.call("mobgt_head_topk", *args, 1, _C.ptr(st), _C.ptr(tv), _C.ptr(ti), _C.ptr(cg), _C.ptr(ce), _C.ptr(logits), s)
+    share = torch.zeros(M, dtype=torch.int32, device=dev)       # per-row pruning bound shared by all lists of the row
+    _C.call("mobgt_head_topk", *args, 1, _C.ptr(st), _C.ptr(tv), _C.ptr(ti), _C.ptr(cg), _C.ptr(ce), _C.ptr(logits), _C.ptr(share), s)
     val = torch.empty(M, k, dtype=torch.float32, device=dev)
     idx = torch.empty(M, k, dtype=torch.int32, device=dev)
     cnt = torch.empty(M, dtype=torch.int32, device=dev)
@@ -319,7 +322,7 @@ def head_target_logit(z, W, bias, target, vocab_offset=0):
     V = W.shape[0]
     st = torch.full((M,), float("-inf"), dtype=torch.float32, device=z.device)
     _C.call("mobgt_head_topk", _C.ptr(z), _C.ptr(W), _C.ptr(bias), _C.ptr(target), M, V, K, int(vocab_offset), 1,
-            2, 0, _C.ptr(st), None, None, None, None, None, _C.stream_ptr())
+            2, 0, _C.ptr(st), None, None, None, None, None, None, _C.stream_ptr())
     return st
 
 
