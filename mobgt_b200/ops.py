@@ -276,15 +276,15 @@ class EmbedSum(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------- K5
 def head_split(M, V):
     """Number of per-row output lists = 2 x (vocabulary splits per 128-row tile of z): every CTA of mobgt_head_topk runs two
-    epilogue groups.  The split count minimises waves x (tiles per CTA + a fixed per-CTA cost) over the 148 SMs.  The fixed
-    cost is the warm-up of a fresh top-k list (every early element is a candidate): measured on B200 with the kernel's
-    clock64 timeline (scripts/k5bench.py --timeline), ~120k cycles per CTA = 33 streamed tiles at the TMA-bound tile time."""
+    epilogue groups.  The split count minimises waves x (tiles per CTA + a fixed per-CTA cost) over the 148 SMs.  (Measured on
+    B200, c5 shard: 9 splits x 32 row tiles in two waves (573 us) beat 4 splits in one 86 %-full wave (638 us): the warm-up
+    of a fresh top-k list costs ~8 tiles once the lists of a row share their pruning bound.)"""
     mt = (M + 127) // 128
     nt = (V + 127) // 128
     best, best_cost = 1, None
     for gs in range(1, min(32, nt) + 1):
         waves = (mt * gs + 147) // 148
-        cost = waves * ((nt + gs - 1) // gs + 33)
+        cost = waves * ((nt + gs - 1) // gs + 8)
         if best_cost is None or cost < best_cost:
             best, best_cost = gs, cost
     return 2 * best

@@ -17,6 +17,8 @@ if [[ $ST == *b* ]]; then
 fi
 if [[ $ST == *k* ]]; then
   timeout 900 python scripts/kbench.py c2-dense128 --k1 > $O/kbench.log 2>&1; echo "kbench rc=$?"; cat $O/kbench.log
+  timeout 300 python scripts/k5bench.py --dbg --timeline > $O/k5bench.log 2>&1; echo "k5bench rc=$?"; grep -v Warning $O/k5bench.log | head -12
+  timeout 300 python scripts/e2e_breakdown.py > $O/e2e_breakdown.log 2>&1; echo "e2e_breakdown rc=$?"
   timeout 600 python scripts/profile_step.py > $O/profile_step.log 2>&1; echo "profile_step rc=$?"
 fi
 if [[ $ST == *l* ]]; then
@@ -25,7 +27,7 @@ if [[ $ST == *l* ]]; then
 fi
 if [[ $ST == *n* ]]; then
   for spec in "k2_bias_fwd_kernel:k2_fwd" "k2_bias_bwd_kernel:k2_bwd" "k3_attn_fwd:k3_fwd" "k3_attn_bwd:k3_bwd" "k1_apsp_kernel:k1" \
-              "k4_:k4" "k5_head:k5"; do
+              "k4_:k4" "k5_head_kernel:k5"; do
     k=${spec%%:*}; n=${spec##*:}
     timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$k" -c 4 -o $O/$n -f \
         python scripts/kbench.py c2-dense128 --iters=1 > $O/$n.log 2>&1; echo "ncu $n rc=$?"
