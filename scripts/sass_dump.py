@@ -11,7 +11,7 @@ for p in parts[1:]:
     name = subprocess.run(["c++filt", mangled], capture_output=True, text=True).stdout.strip()
     short = re.sub(r"\(.*", "", name).replace("void ", "").replace("mobgt::", "")
     short = re.sub(r"[^\w]+", "_", short).strip("_")
-    body = [l for l in p.splitlines() if re.search(r"/\*[0-9a-f]{4}\*/", l)]
+    body = [l for l in p.splitlines() if re.search(r"/\*[0-9a-f]{4,}\*/", l)]
     ins = [re.sub(r"^\s*/\*[0-9a-f]+\*/\s*", "", l) for l in body]
     ins = [re.sub(r"\s*/\*.*", "", l).strip() for l in ins]
     ins = [l for l in ins if l]
