@@ -221,6 +221,19 @@ def kernel_report(model, batch, pk, iters=8, head_c5=True):
     g = torch.randn(ntok, 192, device=dev).to(torch.bfloat16)
     plan = ops.sort_plan(batch.tok_pos)
     add("k4_segment_sum", tk(lambda: ops.segment_sum_raw(g, 0, 192, plan, 2000)), ntok * (192 * 2 + 8), 6)
+    # K6 — encoder row ops (first slice): LayerNorm fwd / bwd at [ntok, 192], bias-gradient column sums
+    ln = model.layers[0].ffn_norm2
+    xs = torch.randn(ntok, 192, device=dev)
+    dy32, dy16 = torch.randn(ntok, 192, device=dev), torch.randn(ntok, 192, device=dev).to(torch.bfloat16)
+    add("k6_layernorm_fwd", tk(lambda: ops.layer_norm(xs, ln, "both")), ntok * 192 * (4 + 4 + 2), 12)
+    xg = xs.clone().requires_grad_(True)
+    o32, o16 = ops.layer_norm(xg, ln, "both")
+    add("k6_layernorm_bwd", tk(lambda: torch.autograd.grad([o32, o16], [xg], [dy32, dy16], retain_graph=True)),
+        ntok * 192 * (4 + 2 + 4 + 4), 12)
+    wide = torch.randn(ntok, 1024, device=dev).to(torch.bfloat16)
+    add("k6_colsum_1024", tk(lambda: ops.colsum(wide)), ntok * 1024 * 2, 6)
+    add("k6_colsum_192", tk(lambda: ops.colsum(dy16)), ntok * 192 * 2, 12)
+    del wide
     # K5 — the evaluation head (not part of the training step): c2 shape, and one GPU's shard of the c5 shape
     for name, Mh, Vh in (("k5_head_c2", 256, 60001),) + ((("k5_head_c5_shard", 4096, 125000),) if head_c5 else ()):
         g_ = torch.Generator(device=dev).manual_seed(5)

@@ -170,6 +170,26 @@ int32_t mobgt_segment_sum(const void *src, int32_t src_dtype, int64_t src_stride
                           void *workspace, int64_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K6 — encoder row ops next to the attention path (first slice).  Replace nn.LayerNorm forward / backward
+ * (EncoderLayer ffn_norm1 / ffn_norm2 and final_ln, model_fqandtoyo.py:1731-1743, :1360-1364; biased variance, eps inside the
+ * sqrt) and the bias gradient dy.sum(0) of every nn.Linear on the path.
+ *   layernorm_fwd: x f32 [N,D] -> out f32 [N,D] (+ optional bf16 copy for the next GEMM), mean / rstd f32 [N] for backward.
+ *   layernorm_bwd: dy f32 and/or dy_bf16 [N,D] (summed when both are given) -> dx f32 [N,D], dgamma / dbeta f32 [D]
+ *                  (deterministic two-stage reduction; workspace: mobgt_layernorm_bwd_workspace_bytes(D)).
+ *   colsum:        out[c] = sum_r src[r, c]  (src bf16 or f32, row stride in elements; fp32 accumulation, fixed order).
+ *   D multiple of 32 with D/32 in {2,4,6,8,10,12,16}.
+ * ------------------------------------------------------------------------------------------ */
+int32_t mobgt_layernorm_fwd(const float *x, const float *gamma, const float *beta, float eps, int32_t N, int32_t D, float *out,
+                            void *out_bf16, float *mean, float *rstd, void *stream);
+int64_t mobgt_layernorm_bwd_workspace_bytes(int32_t D);
+int32_t mobgt_layernorm_bwd(const float *dy, const void *dy_bf16, const float *x, const float *gamma, const float *mean,
+                            const float *rstd, int32_t N, int32_t D, float *dx, float *dgamma, float *dbeta, void *workspace,
+                            int64_t workspace_bytes, void *stream);
+int64_t mobgt_colsum_workspace_bytes(int32_t N, int32_t C);
+int32_t mobgt_colsum(const void *src, int32_t src_dtype, int64_t src_stride, int32_t N, int32_t C, float *out, void *workspace,
+                     int64_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * K5 — POI-logit head fused with per-row top-k and rank counting.  Replaces out_proj followed by get_acc / MRR_metric
  * (model_fqandtoyo.py:1396-1428, :48-90, :122-131).  logits = z W^T + bias are produced tile by tile in TMEM and
  * consumed in the epilogue; they are only written to HBM when logits_dump != NULL (tests).

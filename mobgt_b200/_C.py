@@ -41,6 +41,11 @@ SIGNATURES = {
     "mobgt_segment_sum": [c_p, c_i32, c_i64, c_i32, c_i32, c_p, c_p, c_i32, c_p, c_i32, c_p, c_i64, c_p],
     "mobgt_head_topk": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "mobgt_topk_merge": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p],
+    "mobgt_layernorm_fwd": [c_p, c_p, c_p, c_f32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p],
+    "mobgt_layernorm_bwd_workspace_bytes": [c_i32],
+    "mobgt_layernorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_p, c_p, c_p, c_p, c_i64, c_p],
+    "mobgt_colsum_workspace_bytes": [c_i32, c_i32],
+    "mobgt_colsum": [c_p, c_i32, c_i64, c_i32, c_i32, c_p, c_p, c_i64, c_p],
     "mobgt_debug_set_timeline": [c_p],
     "mobgt_selftest_umma": [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p],
 }

@@ -1,0 +1,255 @@
+// K6 — encoder row ops next to the attention path (first slice): LayerNorm forward / backward and the
+// column sum that produces the bias gradient of every Linear (sm_100a, HBM-bound streaming kernels).
+//
+// Replace, inside EncoderLayer.forward (model_fqandtoyo.py:1731-1743) and the final LN (:1360-1364):
+//   * nn.LayerNorm forward  — torch: vectorized_layer_norm_kernel (53 us at [33 024, 192])
+//   * its backward          — torch: GammaBetaBackwardCUDAKernelTemplate + layer_norm_grad_input_kernel (252 + 27 us; 18.5 % of
+//                             the training step's kernel time, profiles/r01z_launches_summary.txt)
+//   * grad_bias = dy.sum(0) — torch: reduce_kernel<bf16> (66 us per Linear; 9.5 % of the step)
+// One warp per row, the row lives in registers (D / 32 values per lane), statistics by warp shuffles; dgamma / dbeta and the
+// column sums are accumulated per lane across all rows a warp owns, folded per CTA in shared memory and reduced over the CTAs
+// in a fixed order by a second tiny kernel (deterministic, no atomics).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace mobgt {
+
+constexpr int kNormWarps = 8;        // warps (rows in flight) per CTA
+constexpr int kNormCtas = 2 * kNumSMs;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int PER>
+__global__ void __launch_bounds__(kNormWarps * 32) k6_layernorm_fwd_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
+                                                                          const float *__restrict__ beta, float eps, int N,
+                                                                          float *__restrict__ out, __nv_bfloat16 *__restrict__ out16,
+                                                                          float *__restrict__ mean, float *__restrict__ rstd) {
+    constexpr int D = PER * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float g[PER], b[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        g[i] = gamma[i * 32 + lane];
+        b[i] = beta[i * 32 + lane];
+    }
+    for (int row = blockIdx.x * kNormWarps + warp; row < N; row += gridDim.x * kNormWarps) {
+        const float *xr = x + (size_t)row * D;
+        float v[PER];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            v[i] = xr[i * 32 + lane];
+            s += v[i];
+        }
+        const float mu = warp_sum(s) * (1.0f / D);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const float d = v[i] - mu;
+            q += d * d;
+        }
+        const float rs = rsqrtf(warp_sum(q) * (1.0f / D) + eps);      // biased variance, as torch.nn.LayerNorm
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const float y = (v[i] - mu) * rs * g[i] + b[i];
+            out[(size_t)row * D + i * 32 + lane] = y;
+            if (out16 != nullptr) out16[(size_t)row * D + i * 32 + lane] = __float2bfloat16_rn(y);
+        }
+        if (lane == 0) {
+            mean[row] = mu;
+            rstd[row] = rs;
+        }
+    }
+}
+
+// dx = rstd * ( g dy - mean(g dy) - xhat mean(g dy xhat) ) ;  dgamma = sum_rows dy xhat ;  dbeta = sum_rows dy
+template <int PER>
+__global__ void __launch_bounds__(kNormWarps * 32) k6_layernorm_bwd_kernel(const float *__restrict__ dy, const __nv_bfloat16 *__restrict__ dy16,
+                                                                          const float *__restrict__ x,
+                                                                          const float *__restrict__ gamma, const float *__restrict__ mean,
+                                                                          const float *__restrict__ rstd, int N, float *__restrict__ dx,
+                                                                          float *__restrict__ partial) {
+    constexpr int D = PER * 32;
+    __shared__ float sred[kNormWarps][2 * D];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float g[PER], dg[PER], db[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        g[i] = gamma[i * 32 + lane];
+        dg[i] = 0.f;
+        db[i] = 0.f;
+    }
+    for (int row = blockIdx.x * kNormWarps + warp; row < N; row += gridDim.x * kNormWarps) {
+        const float mu = mean[row], rs = rstd[row];
+        float xh[PER], gy[PER];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            // the fp32 consumer (residual stream) and the bf16 consumer (next GEMM) of the output both send a gradient
+            float d = dy != nullptr ? dy[(size_t)row * D + i * 32 + lane] : 0.f;
+            if (dy16 != nullptr) d += __bfloat162float(dy16[(size_t)row * D + i * 32 + lane]);
+            xh[i] = (x[(size_t)row * D + i * 32 + lane] - mu) * rs;
+            gy[i] = d * g[i];
+            s1 += gy[i];
+            s2 += gy[i] * xh[i];
+            dg[i] += d * xh[i];
+            db[i] += d;
+        }
+        const float m1 = warp_sum(s1) * (1.0f / D), m2 = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+        for (int i = 0; i < PER; ++i) dx[(size_t)row * D + i * 32 + lane] = rs * (gy[i] - m1 - xh[i] * m2);
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        sred[warp][i * 32 + lane] = dg[i];
+        sred[warp][D + i * 32 + lane] = db[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kNormWarps; ++w) s += sred[w][c];
+        partial[(size_t)blockIdx.x * 2 * D + c] = s;
+    }
+}
+
+// out[c] = sum over parts (fixed order) of partial[part][c]
+__global__ void k6_reduce_parts_kernel(const float *__restrict__ partial, int nparts, int C, float *__restrict__ out0, int C0,
+                                       float *__restrict__ out1) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * C + c];
+    if (c < C0) out0[c] = s;
+    else out1[c - C0] = s;
+}
+
+// column sums of a row-major [N, C] matrix (bf16 or f32, row stride in elements): thread = 8 (bf16) / 4 (f32) adjacent columns
+// (one 16-byte load per row), CTA = (column group, row strip); per-CTA strip sums -> partial[strip][C]
+template <typename T>
+__global__ void __launch_bounds__(256) k6_colsum_kernel(const T *__restrict__ src, int64_t stride, int N, int C, int rows_per_strip,
+                                                        float *__restrict__ partial) {
+    constexpr int V = 16 / (int)sizeof(T);
+    __shared__ float sacc[8][32 * V];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = (blockIdx.x * 32 + lane) * V;
+    const int r0 = blockIdx.y * rows_per_strip, r1 = min(N, r0 + rows_per_strip);
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    if (col < C) {
+        for (int r = r0 + warp; r < r1; r += 8) {
+            const uint4 w = *reinterpret_cast<const uint4 *>(src + (size_t)r * stride + col);
+            const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+            if constexpr (sizeof(T) == 4) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] += __uint_as_float(u[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc[2 * i] += __uint_as_float(u[i] << 16);
+                    acc[2 * i + 1] += __uint_as_float(u[i] & 0xFFFF0000u);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) sacc[warp][lane * V + i] = acc[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < 32 * V; c += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += sacc[w][c];
+        const int gc = blockIdx.x * 32 * V + c;
+        if (gc < C) partial[(size_t)blockIdx.y * C + gc] = s;
+    }
+}
+
+}  // namespace mobgt
+
+using namespace mobgt;
+
+#define MOBGT_NORM_DISPATCH(PERV, CALL)     \
+    switch (PERV) {                         \
+        case 2: { constexpr int P_ = 2; CALL; } break;   \
+        case 4: { constexpr int P_ = 4; CALL; } break;   \
+        case 6: { constexpr int P_ = 6; CALL; } break;   \
+        case 8: { constexpr int P_ = 8; CALL; } break;   \
+        case 10: { constexpr int P_ = 10; CALL; } break; \
+        case 12: { constexpr int P_ = 12; CALL; } break; \
+        case 16: { constexpr int P_ = 16; CALL; } break; \
+        default: MOBGT_REQUIRE(false, MOBGT_ERR_UNSUPPORTED, "layernorm: D=%d is not built (D/32 in {2,4,6,8,10,12,16})", D); \
+    }
+
+extern "C" int64_t mobgt_layernorm_bwd_workspace_bytes(int32_t D) {
+    if (D <= 0 || D % 32 != 0 || D > 512) return -1;
+    return (int64_t)kNormCtas * 2 * D * (int64_t)sizeof(float);
+}
+
+extern "C" int32_t mobgt_layernorm_fwd(const float *x, const float *gamma, const float *beta, float eps, int32_t N, int32_t D,
+                                       float *out, void *out_bf16, float *mean, float *rstd, void *stream) {
+    MOBGT_REQUIRE(x && gamma && beta && out && mean && rstd, MOBGT_ERR_NULL, "mobgt_layernorm_fwd: null pointer");
+    MOBGT_REQUIRE(D > 0 && D % 32 == 0 && D <= 512, MOBGT_ERR_BAD_SHAPE, "mobgt_layernorm_fwd: D=%d", D);
+    if (N <= 0) return MOBGT_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = min(kNormCtas, ceil_div(N, kNormWarps));
+    MOBGT_NORM_DISPATCH(D / 32, (k6_layernorm_fwd_kernel<P_><<<grid, kNormWarps * 32, 0, s>>>(
+                                    x, gamma, beta, eps, N, out, static_cast<__nv_bfloat16 *>(out_bf16), mean, rstd)));
+    MOBGT_LAUNCH_OK("k6_layernorm_fwd_kernel");
+    return MOBGT_OK;
+}
+
+extern "C" int32_t mobgt_layernorm_bwd(const float *dy, const void *dy_bf16, const float *x, const float *gamma, const float *mean, const float *rstd,
+                                       int32_t N, int32_t D, float *dx, float *dgamma, float *dbeta, void *workspace,
+                                       int64_t workspace_bytes, void *stream) {
+    MOBGT_REQUIRE((dy || dy_bf16) && x && gamma && mean && rstd && dx && dgamma && dbeta && workspace, MOBGT_ERR_NULL,
+                  "mobgt_layernorm_bwd: null pointer");
+    MOBGT_REQUIRE(D > 0 && D % 32 == 0 && D <= 512, MOBGT_ERR_BAD_SHAPE, "mobgt_layernorm_bwd: D=%d", D);
+    MOBGT_REQUIRE(workspace_bytes >= (int64_t)kNormCtas * 2 * D * 4, MOBGT_ERR_WORKSPACE_TOO_SMALL, "mobgt_layernorm_bwd: workspace");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = N > 0 ? min(kNormCtas, ceil_div(N, kNormWarps)) : 0;
+    float *partial = static_cast<float *>(workspace);
+    if (grid > 0) {
+        MOBGT_NORM_DISPATCH(D / 32, (k6_layernorm_bwd_kernel<P_><<<grid, kNormWarps * 32, 0, s>>>(
+                                        dy, static_cast<const __nv_bfloat16 *>(dy_bf16), x, gamma, mean, rstd, N, dx, partial)));
+        MOBGT_LAUNCH_OK("k6_layernorm_bwd_kernel");
+    }
+    k6_reduce_parts_kernel<<<ceil_div(2 * D, 128), 128, 0, s>>>(partial, grid, 2 * D, dgamma, D, dbeta);
+    MOBGT_LAUNCH_OK("k6_reduce_parts_kernel");
+    return MOBGT_OK;
+}
+
+extern "C" int64_t mobgt_colsum_workspace_bytes(int32_t N, int32_t C) {
+    if (N < 0 || C <= 0) return -1;
+    const int strips = max(1, min(64, ceil_div(N, 256)));
+    return (int64_t)strips * C * (int64_t)sizeof(float);
+}
+
+extern "C" int32_t mobgt_colsum(const void *src, int32_t src_dtype, int64_t src_stride, int32_t N, int32_t C, float *out,
+                                void *workspace, int64_t workspace_bytes, void *stream) {
+    MOBGT_REQUIRE(src && out && workspace, MOBGT_ERR_NULL, "mobgt_colsum: null pointer");
+    MOBGT_REQUIRE(src_dtype == MOBGT_F32 || src_dtype == MOBGT_BF16, MOBGT_ERR_BAD_DTYPE, "mobgt_colsum: dtype");
+    const int V = src_dtype == MOBGT_F32 ? 4 : 8;
+    MOBGT_REQUIRE(C > 0 && C % V == 0 && src_stride % V == 0 && ((uintptr_t)src & 15) == 0, MOBGT_ERR_BAD_SHAPE,
+                  "mobgt_colsum: C=%d and the row stride must be multiples of %d elements, src 16-byte aligned", C, V);
+    const int strips = max(1, min(64, ceil_div(N, 256)));
+    MOBGT_REQUIRE(workspace_bytes >= (int64_t)strips * C * 4, MOBGT_ERR_WORKSPACE_TOO_SMALL, "mobgt_colsum: workspace");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float *partial = static_cast<float *>(workspace);
+    const int rows_per_strip = max(1, ceil_div(max(N, 1), strips));
+    dim3 grid((unsigned)ceil_div(C, 32 * V), (unsigned)strips);
+    if (src_dtype == MOBGT_F32)
+        k6_colsum_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float *>(src), src_stride, N, C, rows_per_strip, partial);
+    else
+        k6_colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(src), src_stride, N, C, rows_per_strip,
+                                                             partial);
+    MOBGT_LAUNCH_OK("k6_colsum_kernel");
+    k6_reduce_parts_kernel<<<ceil_div(C, 128), 128, 0, s>>>(partial, strips, C, out, C, out);
+    MOBGT_LAUNCH_OK("k6_reduce_parts_kernel");
+    return MOBGT_OK;
+}

@@ -138,12 +138,13 @@ class MultiHeadAttention(nn.Module):
         self.attention_dropout_rate = attention_dropout_rate
         self.output_layer = nn.Linear(num_heads * self.att_size, hidden_size)
 
-    def forward(self, x, bias_slot, layer=0):
+    def forward(self, x16, bias_slot, layer=0):
+        """x16: bf16 [ntok, hidden] (the LayerNorm kernel of the previous layer emits this copy)."""
         w = torch.cat([self.linear_q.weight, self.linear_k.weight, self.linear_v.weight], 0)
         b = torch.cat([self.linear_q.bias, self.linear_k.bias, self.linear_v.bias], 0)
-        qkv = F.linear(x.to(torch.bfloat16), w.to(torch.bfloat16), b.to(torch.bfloat16))
+        qkv = ops.LinearBiasFn.apply(x16, w.to(torch.bfloat16), b.to(torch.bfloat16))
         a = ops.BiasedAttention.apply(qkv, bias_slot, layer)
-        return F.linear(a, self.output_layer.weight.to(torch.bfloat16), self.output_layer.bias.to(torch.bfloat16))
+        return ops.linear_bf16(a, self.output_layer)
 
 
 class EncoderLayer(nn.Module):
@@ -159,16 +160,16 @@ class EncoderLayer(nn.Module):
         self.ffn = FeedForwardNetwork(hidden_size, ffn_size, dropout_rate)
         self.ffn_dropout = nn.Dropout(dropout_rate)
 
-    def forward(self, x, bias_slot, layer=0):
-        # residual stream and LayerNorms in fp32, GEMMs / attention in bf16 (the reference's --precision 16 AMP split)
-        y = self.self_attention(x, bias_slot, layer)
+    def forward(self, x, x16, bias_slot, layer=0):
+        """x: fp32 residual stream [ntok, hidden]; x16: its bf16 copy.  Residual stream and LayerNorms in fp32, GEMMs /
+        attention in bf16 (the reference's --precision 16 AMP split).  LayerNorms and the Linear bias gradients are K6."""
+        y = self.self_attention(x16, bias_slot, layer)
         x = x + self.self_attention_dropout(y).float()
-        y = self.ffn_norm1(x)
+        y16 = ops.layer_norm(x, self.ffn_norm1, "bf16")
         f = self.ffn
-        y = F.linear(F.gelu(F.linear(y.to(torch.bfloat16), f.layer1.weight.to(torch.bfloat16), f.layer1.bias.to(torch.bfloat16))),
-                     f.layer2.weight.to(torch.bfloat16), f.layer2.bias.to(torch.bfloat16))
+        y = ops.linear_bf16(F.gelu(ops.linear_bf16(y16, f.layer1)), f.layer2)
         x = x + self.ffn_dropout(y).float()
-        return self.ffn_norm2(x)
+        return ops.layer_norm(x, self.ffn_norm2, "both")
 
 
 def gradient_tail_loss(inputs, targets, alpha=0.25, beta=1, k=1):
@@ -284,12 +285,13 @@ class Graphormer(nn.Module):
         tok = self.node_tokens(b)
         slot = ops.BiasSlot(bias, b, len(self.layers))
         x = ops.BiasGradSink.apply(self.input_dropout(tok).float(), bias, slot)                          # :1347
+        x16 = x.to(torch.bfloat16)
         for li, layer in enumerate(self.layers):                                                         # :1348-1352
-            x = layer(x, slot, li)
+            x, x16 = layer(x, x16, slot, li)
         z0 = x.index_select(0, b.tok_off[:-1].long()).float()                                            # output[:, 0, :]
         user_embedding = self.user_embed_model(b.user.view(-1) - 1)                                      # :1239
         z = self.embed_fuse_model3(z0, user_embedding)                                                   # :1356 (token 0 only)
-        z = self.output_dropout(self.ELU(self.final_ln(z)))                                              # :1360-1364
+        z = self.output_dropout(self.ELU(ops.layer_norm(z.float(), self.final_ln)))                      # :1360-1364
         cat_output = self.cat_decoder(z)
         output = self.out_proj(z)
         if self.traits["log_softmax"]:

@@ -273,6 +273,95 @@ class EmbedSum(torch.autograd.Function):
         return None, d_nf, dDin, dDout, dpe, dgt
 
 
+
+# ----------------------------------------------------------------------------------------------- K6
+def colsum(src):
+    """out[c] = sum_r src[r, c] in fp32 (src bf16 / f32 [N, C], last dim contiguous): the bias gradient of a Linear."""
+    assert src.dim() == 2 and src.stride(1) == 1
+    N, C = src.shape
+    ws_bytes = int(_C.lib().mobgt_colsum_workspace_bytes(N, C))
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=src.device)
+    out = torch.empty(C, dtype=torch.float32, device=src.device)
+    _C.call("mobgt_colsum", src.data_ptr(), _dt(src), src.stride(0), N, C, _C.ptr(out), _C.ptr(ws), ws_bytes, _C.stream_ptr())
+    return out
+
+
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the last dim of a 2-D fp32 tensor (model_fqandtoyo.py:1731-1743, :1360-1364).  `want` selects the
+    outputs: "f32", "bf16" (only the copy the next GEMM consumes) or "both" (residual stream + GEMM input); in backward the
+    gradients of the two outputs are summed inside the kernel."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, want):
+        x = x.contiguous()
+        N, D = x.shape
+        dev = x.device
+        out = torch.empty(N, D, dtype=torch.float32, device=dev)
+        out16 = torch.empty(N, D, dtype=torch.bfloat16, device=dev) if want != "f32" else None
+        mean = torch.empty(N, dtype=torch.float32, device=dev)
+        rstd = torch.empty(N, dtype=torch.float32, device=dev)
+        g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        _C.call("mobgt_layernorm_fwd", _C.ptr(x), _C.ptr(g), _C.ptr(b), float(eps), N, D, _C.ptr(out), _C.ptr(out16), _C.ptr(mean),
+                _C.ptr(rstd), _C.stream_ptr())
+        ctx.save_for_backward(x, g, mean, rstd)
+        ctx.want = want
+        if want == "f32":
+            return out
+        if want == "bf16":
+            return out16
+        return out, out16
+
+    @staticmethod
+    def backward(ctx, *grads):
+        x, g, mean, rstd = ctx.saved_tensors
+        N, D = x.shape
+        if ctx.want == "f32":
+            dy32, dy16 = grads[0], None
+        elif ctx.want == "bf16":
+            dy32, dy16 = None, grads[0]
+        else:
+            dy32, dy16 = grads
+        dy32 = dy32.contiguous() if dy32 is not None else None
+        dy16 = dy16.contiguous() if dy16 is not None else None
+        dx = torch.empty_like(x)
+        dgamma = torch.empty(D, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(D, dtype=torch.float32, device=x.device)
+        ws_bytes = int(_C.lib().mobgt_layernorm_bwd_workspace_bytes(D))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        _C.call("mobgt_layernorm_bwd", _C.ptr(dy32), _C.ptr(dy16), _C.ptr(x), _C.ptr(g), _C.ptr(mean), _C.ptr(rstd), N, D, _C.ptr(dx),
+                _C.ptr(dgamma), _C.ptr(dbeta), _C.ptr(ws), ws_bytes, _C.stream_ptr())
+        return dx, dgamma, dbeta, None, None
+
+
+def layer_norm(x, ln, want="f32"):
+    """x f32 [N, D]; ln: an nn.LayerNorm (weight, bias, eps)."""
+    return LayerNormFn.apply(x, ln.weight, ln.bias, ln.eps, want)
+
+
+class LinearBiasFn(torch.autograd.Function):
+    """y = x W^T + b with bf16 operands (library GEMMs); the bias gradient dy.sum(0) is the K6 column-sum kernel (fp32
+    accumulation, fixed order) instead of torch's generic reduce."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return torch.nn.functional.linear(x, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dy @ w
+        dw = dy.t() @ x
+        db = colsum(dy).to(dy.dtype)
+        return dx, dw, db
+
+
+def linear_bf16(x, lin):
+    """nn.Linear `lin` (fp32 master weights) applied to a bf16 [N, in] tensor."""
+    return LinearBiasFn.apply(x, lin.weight.to(torch.bfloat16), lin.bias.to(torch.bfloat16))
+
+
 # ----------------------------------------------------------------------------------------------- K5
 def head_split(M, V):
     """Number of per-row output lists = 2 x (vocabulary splits per 128-row tile of z): every CTA of mobgt_head_topk runs two

@@ -251,3 +251,50 @@ def torch_attention_diff(qkv, bias, tok_off, H=8, d=24):
         s = (q * d ** -0.5) @ k.transpose(1, 2) + bias[g, :, :T, :T]
         outs.append((torch.softmax(s, -1) @ v).transpose(0, 1).reshape(T, D))
     return torch.cat(outs), None
+
+
+# ---------------------------------------------------------------------------------------------------- K6
+@pytest.mark.parametrize("N,D", [(1000, 192), (257, 320), (33, 64)])
+def test_layernorm_fwd_bwd_vs_torch(lib_built, N, D):
+    """K6 LayerNorm == torch.nn.functional.layer_norm (fp32), forward and autograd backward, incl. the two-output form."""
+    from mobgt_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    x = (torch.randn(N, D, generator=g) * 2 + 0.5).cuda()
+    ln = torch.nn.LayerNorm(D).cuda()
+    with torch.no_grad():
+        ln.weight.copy_(torch.randn(D, generator=g).cuda() * 0.5 + 1)
+        ln.bias.copy_(torch.randn(D, generator=g).cuda() * 0.1)
+    dy32 = torch.randn(N, D, generator=g).cuda()
+    dy16 = torch.randn(N, D, generator=g).cuda().to(torch.bfloat16)
+    xr = x.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (D,), ln.weight, ln.bias, ln.eps)
+    (ref * (dy32 + dy16.float())).sum().backward()
+    ref_dx, ref_dg, ref_db = xr.grad.clone(), ln.weight.grad.clone(), ln.bias.grad.clone()
+    ln.zero_grad()
+    xo = x.clone().requires_grad_(True)
+    out, out16 = ops.layer_norm(xo, ln, "both")
+    assert torch.allclose(out, ref.detach(), rtol=1e-5, atol=1e-5)
+    assert torch.equal(out16, out.to(torch.bfloat16))
+    ((out * dy32).sum() + (out16.float() * dy16.float()).sum()).backward()
+    scale = ref_dx.abs().max().item()
+    assert (xo.grad - ref_dx).abs().max().item() <= 2e-5 * scale + 1e-5
+    assert (ln.weight.grad - ref_dg).abs().max().item() <= 2e-5 * ref_dg.abs().max().item() + 1e-4
+    assert (ln.bias.grad - ref_db).abs().max().item() <= 2e-5 * ref_db.abs().max().item() + 1e-4
+    # single-output forms
+    o32 = ops.layer_norm(x, ln, "f32")
+    o16 = ops.layer_norm(x, ln, "bf16")
+    assert torch.equal(o32, out.detach()) and torch.equal(o16, out16.detach())
+
+
+@pytest.mark.parametrize("N,C,dt", [(33024, 192, torch.bfloat16), (5000, 1024, torch.bfloat16), (77, 576, torch.bfloat16), (300, 64, torch.float32)])
+def test_colsum_vs_torch(lib_built, N, C, dt):
+    from mobgt_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    src = torch.randn(N, C, generator=g).cuda().to(dt)
+    ref = src.double().sum(0)
+    got = ops.colsum(src)
+    assert (got.double() - ref).abs().max().item() <= 1e-5 * N ** 0.5 * max(1.0, ref.abs().max().item())
+    # strided view (a slice of a wider matrix)
+    wide = torch.randn(N, 2 * C, generator=g).cuda().to(dt)
+    got2 = ops.colsum(wide[:, C:])
+    assert (got2.double() - wide[:, C:].double().sum(0)).abs().max().item() <= 1e-5 * N ** 0.5 * max(1.0, ref.abs().max().item())
