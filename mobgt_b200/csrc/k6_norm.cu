@@ -24,10 +24,25 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// counter-based dropout mask: element `idx` of call `seed` is kept iff hash >= p * 2^32 (lowbias32 mix); the backward
+// regenerates the mask from (seed, idx) instead of storing it
+__device__ __forceinline__ bool drop_keep(uint32_t idx, uint32_t seed_lo, uint32_t seed_hi, uint32_t thresh) {
+    uint32_t z = idx + seed_lo;
+    z ^= z >> 16; z *= 0x7feb352du;
+    z ^= z >> 15; z *= 0x846ca68bu;
+    z ^= z >> 16; z ^= seed_hi;
+    z *= 0x9E3779B1u; z ^= z >> 15;
+    return z >= thresh;
+}
+
+// out = LayerNorm(s),  s = x + dropout(y)   (y == NULL: s = x).  s is written when s_out != NULL (the new residual stream).
 template <int PER>
-__global__ void __launch_bounds__(kNormWarps * 32) k6_layernorm_fwd_kernel(const float *__restrict__ x, const float *__restrict__ gamma,
+__global__ void __launch_bounds__(kNormWarps * 32) k6_layernorm_fwd_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ y,
+                                                                          uint32_t drop_thresh, float drop_scale, uint32_t seed_lo,
+                                                                          uint32_t seed_hi, const float *__restrict__ gamma,
                                                                           const float *__restrict__ beta, float eps, int N,
-                                                                          float *__restrict__ out, __nv_bfloat16 *__restrict__ out16,
+                                                                          float *__restrict__ s_out, float *__restrict__ out,
+                                                                          __nv_bfloat16 *__restrict__ out16,
                                                                           float *__restrict__ mean, float *__restrict__ rstd) {
     constexpr int D = PER * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -38,13 +53,23 @@ __global__ void __launch_bounds__(kNormWarps * 32) k6_layernorm_fwd_kernel(const
         b[i] = beta[i * 32 + lane];
     }
     for (int row = blockIdx.x * kNormWarps + warp; row < N; row += gridDim.x * kNormWarps) {
-        const float *xr = x + (size_t)row * D;
+        const size_t base = (size_t)row * D;
         float v[PER];
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
-            v[i] = xr[i * 32 + lane];
+            v[i] = x[base + i * 32 + lane];
+            if (y != nullptr) {
+                const float yv = __bfloat162float(y[base + i * 32 + lane]);
+                if (drop_thresh == 0u) v[i] += yv;
+                else if (drop_keep((uint32_t)(base + i * 32 + lane), seed_lo, seed_hi, drop_thresh))
+                    v[i] += __bfloat162float(__float2bfloat16_rn(yv * drop_scale));      // bf16 dropout output, as nn.Dropout on a bf16 tensor
+            }
             s += v[i];
+        }
+        if (s_out != nullptr) {
+#pragma unroll
+            for (int i = 0; i < PER; ++i) s_out[base + i * 32 + lane] = v[i];
         }
         const float mu = warp_sum(s) * (1.0f / D);
         float q = 0.f;
@@ -56,9 +81,9 @@ __global__ void __launch_bounds__(kNormWarps * 32) k6_layernorm_fwd_kernel(const
         const float rs = rsqrtf(warp_sum(q) * (1.0f / D) + eps);      // biased variance, as torch.nn.LayerNorm
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
-            const float y = (v[i] - mu) * rs * g[i] + b[i];
-            out[(size_t)row * D + i * 32 + lane] = y;
-            if (out16 != nullptr) out16[(size_t)row * D + i * 32 + lane] = __float2bfloat16_rn(y);
+            const float o = (v[i] - mu) * rs * g[i] + b[i];
+            if (out != nullptr) out[base + i * 32 + lane] = o;
+            if (out16 != nullptr) out16[base + i * 32 + lane] = __float2bfloat16_rn(o);
         }
         if (lane == 0) {
             mean[row] = mu;
@@ -67,12 +92,16 @@ __global__ void __launch_bounds__(kNormWarps * 32) k6_layernorm_fwd_kernel(const
     }
 }
 
-// dx = rstd * ( g dy - mean(g dy) - xhat mean(g dy xhat) ) ;  dgamma = sum_rows dy xhat ;  dbeta = sum_rows dy
+// ds = rstd * ( g dy - mean(g dy) - xhat mean(g dy xhat) ) + ds_ext ;  dgamma = sum_rows dy xhat ;  dbeta = sum_rows dy
+// (x = the LayerNorm input s).  dx = ds (residual branch) and, when dyb_out != NULL, dyb_out = bf16(ds * mask * scale) is the
+// gradient of the sub-layer output that went through the dropout.
 template <int PER>
 __global__ void __launch_bounds__(kNormWarps * 32) k6_layernorm_bwd_kernel(const float *__restrict__ dy, const __nv_bfloat16 *__restrict__ dy16,
-                                                                          const float *__restrict__ x,
+                                                                          const float *__restrict__ ds_ext, const float *__restrict__ x,
                                                                           const float *__restrict__ gamma, const float *__restrict__ mean,
-                                                                          const float *__restrict__ rstd, int N, float *__restrict__ dx,
+                                                                          const float *__restrict__ rstd, int N, uint32_t drop_thresh,
+                                                                          float drop_scale, uint32_t seed_lo, uint32_t seed_hi,
+                                                                          float *__restrict__ dx, __nv_bfloat16 *__restrict__ dyb_out,
                                                                           float *__restrict__ partial) {
     constexpr int D = PER * 32;
     __shared__ float sred[kNormWarps][2 * D];
@@ -85,15 +114,16 @@ __global__ void __launch_bounds__(kNormWarps * 32) k6_layernorm_bwd_kernel(const
         db[i] = 0.f;
     }
     for (int row = blockIdx.x * kNormWarps + warp; row < N; row += gridDim.x * kNormWarps) {
+        const size_t base = (size_t)row * D;
         const float mu = mean[row], rs = rstd[row];
         float xh[PER], gy[PER];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
             // the fp32 consumer (residual stream) and the bf16 consumer (next GEMM) of the output both send a gradient
-            float d = dy != nullptr ? dy[(size_t)row * D + i * 32 + lane] : 0.f;
-            if (dy16 != nullptr) d += __bfloat162float(dy16[(size_t)row * D + i * 32 + lane]);
-            xh[i] = (x[(size_t)row * D + i * 32 + lane] - mu) * rs;
+            float d = dy != nullptr ? dy[base + i * 32 + lane] : 0.f;
+            if (dy16 != nullptr) d += __bfloat162float(dy16[base + i * 32 + lane]);
+            xh[i] = (x[base + i * 32 + lane] - mu) * rs;
             gy[i] = d * g[i];
             s1 += gy[i];
             s2 += gy[i] * xh[i];
@@ -102,7 +132,15 @@ __global__ void __launch_bounds__(kNormWarps * 32) k6_layernorm_bwd_kernel(const
         }
         const float m1 = warp_sum(s1) * (1.0f / D), m2 = warp_sum(s2) * (1.0f / D);
 #pragma unroll
-        for (int i = 0; i < PER; ++i) dx[(size_t)row * D + i * 32 + lane] = rs * (gy[i] - m1 - xh[i] * m2);
+        for (int i = 0; i < PER; ++i) {
+            float ds = rs * (gy[i] - m1 - xh[i] * m2);
+            if (ds_ext != nullptr) ds += ds_ext[base + i * 32 + lane];
+            dx[base + i * 32 + lane] = ds;
+            if (dyb_out != nullptr) {
+                const bool keep = drop_thresh == 0u || drop_keep((uint32_t)(base + i * 32 + lane), seed_lo, seed_hi, drop_thresh);
+                dyb_out[base + i * 32 + lane] = __float2bfloat16_rn(keep ? ds * (drop_thresh == 0u ? 1.0f : drop_scale) : 0.f);
+            }
+        }
     }
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
@@ -191,37 +229,65 @@ extern "C" int64_t mobgt_layernorm_bwd_workspace_bytes(int32_t D) {
     return (int64_t)kNormCtas * 2 * D * (int64_t)sizeof(float);
 }
 
-extern "C" int32_t mobgt_layernorm_fwd(const float *x, const float *gamma, const float *beta, float eps, int32_t N, int32_t D,
-                                       float *out, void *out_bf16, float *mean, float *rstd, void *stream) {
-    MOBGT_REQUIRE(x && gamma && beta && out && mean && rstd, MOBGT_ERR_NULL, "mobgt_layernorm_fwd: null pointer");
-    MOBGT_REQUIRE(D > 0 && D % 32 == 0 && D <= 512, MOBGT_ERR_BAD_SHAPE, "mobgt_layernorm_fwd: D=%d", D);
+static uint32_t drop_threshold(float p) {
+    if (!(p > 0.f)) return 0u;
+    const double t = (double)p * 4294967296.0;
+    return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+}
+
+extern "C" int32_t mobgt_add_dropout_layernorm_fwd(const float *x, const void *y_bf16, float drop_p, uint64_t seed, const float *gamma,
+                                                   const float *beta, float eps, int32_t N, int32_t D, float *s_out, float *out,
+                                                   void *out_bf16, float *mean, float *rstd, void *stream) {
+    MOBGT_REQUIRE(x && gamma && beta && (out || out_bf16) && mean && rstd, MOBGT_ERR_NULL, "mobgt_add_dropout_layernorm_fwd: null pointer");
+    MOBGT_REQUIRE(D > 0 && D % 32 == 0 && D <= 512, MOBGT_ERR_BAD_SHAPE, "mobgt_add_dropout_layernorm_fwd: D=%d", D);
+    MOBGT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, MOBGT_ERR_BAD_SHAPE, "mobgt_add_dropout_layernorm_fwd: p=%f", (double)drop_p);
+    MOBGT_REQUIRE((int64_t)N * D < (1ll << 32), MOBGT_ERR_BAD_SHAPE, "mobgt_add_dropout_layernorm_fwd: N*D must be < 2^32");
     if (N <= 0) return MOBGT_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int grid = min(kNormCtas, ceil_div(N, kNormWarps));
+    const uint32_t th = y_bf16 ? drop_threshold(drop_p) : 0u;
+    const float sc = 1.0f / (1.0f - drop_p);
     MOBGT_NORM_DISPATCH(D / 32, (k6_layernorm_fwd_kernel<P_><<<grid, kNormWarps * 32, 0, s>>>(
-                                    x, gamma, beta, eps, N, out, static_cast<__nv_bfloat16 *>(out_bf16), mean, rstd)));
+                                    x, static_cast<const __nv_bfloat16 *>(y_bf16), th, sc, (uint32_t)seed, (uint32_t)(seed >> 32), gamma,
+                                    beta, eps, N, s_out, out, static_cast<__nv_bfloat16 *>(out_bf16), mean, rstd)));
     MOBGT_LAUNCH_OK("k6_layernorm_fwd_kernel");
     return MOBGT_OK;
 }
 
-extern "C" int32_t mobgt_layernorm_bwd(const float *dy, const void *dy_bf16, const float *x, const float *gamma, const float *mean, const float *rstd,
-                                       int32_t N, int32_t D, float *dx, float *dgamma, float *dbeta, void *workspace,
-                                       int64_t workspace_bytes, void *stream) {
-    MOBGT_REQUIRE((dy || dy_bf16) && x && gamma && mean && rstd && dx && dgamma && dbeta && workspace, MOBGT_ERR_NULL,
-                  "mobgt_layernorm_bwd: null pointer");
-    MOBGT_REQUIRE(D > 0 && D % 32 == 0 && D <= 512, MOBGT_ERR_BAD_SHAPE, "mobgt_layernorm_bwd: D=%d", D);
-    MOBGT_REQUIRE(workspace_bytes >= (int64_t)kNormCtas * 2 * D * 4, MOBGT_ERR_WORKSPACE_TOO_SMALL, "mobgt_layernorm_bwd: workspace");
+extern "C" int32_t mobgt_layernorm_fwd(const float *x, const float *gamma, const float *beta, float eps, int32_t N, int32_t D,
+                                       float *out, void *out_bf16, float *mean, float *rstd, void *stream) {
+    return mobgt_add_dropout_layernorm_fwd(x, nullptr, 0.f, 0ull, gamma, beta, eps, N, D, nullptr, out, out_bf16, mean, rstd, stream);
+}
+
+extern "C" int32_t mobgt_add_dropout_layernorm_bwd(const float *dy, const void *dy_bf16, const float *ds_ext, const float *s_saved,
+                                                   const float *gamma, const float *mean, const float *rstd, int32_t N, int32_t D,
+                                                   float drop_p, uint64_t seed, float *dx, void *dyb_out, float *dgamma, float *dbeta,
+                                                   void *workspace, int64_t workspace_bytes, void *stream) {
+    MOBGT_REQUIRE((dy || dy_bf16) && s_saved && gamma && mean && rstd && dx && dgamma && dbeta && workspace, MOBGT_ERR_NULL,
+                  "mobgt_add_dropout_layernorm_bwd: null pointer");
+    MOBGT_REQUIRE(D > 0 && D % 32 == 0 && D <= 512, MOBGT_ERR_BAD_SHAPE, "mobgt_add_dropout_layernorm_bwd: D=%d", D);
+    MOBGT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, MOBGT_ERR_BAD_SHAPE, "mobgt_add_dropout_layernorm_bwd: p=%f", (double)drop_p);
+    MOBGT_REQUIRE(workspace_bytes >= (int64_t)kNormCtas * 2 * D * 4, MOBGT_ERR_WORKSPACE_TOO_SMALL, "mobgt_add_dropout_layernorm_bwd: workspace");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int grid = N > 0 ? min(kNormCtas, ceil_div(N, kNormWarps)) : 0;
     float *partial = static_cast<float *>(workspace);
     if (grid > 0) {
         MOBGT_NORM_DISPATCH(D / 32, (k6_layernorm_bwd_kernel<P_><<<grid, kNormWarps * 32, 0, s>>>(
-                                        dy, static_cast<const __nv_bfloat16 *>(dy_bf16), x, gamma, mean, rstd, N, dx, partial)));
+                                        dy, static_cast<const __nv_bfloat16 *>(dy_bf16), ds_ext, s_saved, gamma, mean, rstd, N,
+                                        drop_threshold(drop_p), 1.0f / (1.0f - drop_p), (uint32_t)seed, (uint32_t)(seed >> 32), dx,
+                                        static_cast<__nv_bfloat16 *>(dyb_out), partial)));
         MOBGT_LAUNCH_OK("k6_layernorm_bwd_kernel");
     }
     k6_reduce_parts_kernel<<<ceil_div(2 * D, 128), 128, 0, s>>>(partial, grid, 2 * D, dgamma, D, dbeta);
     MOBGT_LAUNCH_OK("k6_reduce_parts_kernel");
     return MOBGT_OK;
+}
+
+extern "C" int32_t mobgt_layernorm_bwd(const float *dy, const void *dy_bf16, const float *x, const float *gamma, const float *mean,
+                                       const float *rstd, int32_t N, int32_t D, float *dx, float *dgamma, float *dbeta, void *workspace,
+                                       int64_t workspace_bytes, void *stream) {
+    return mobgt_add_dropout_layernorm_bwd(dy, dy_bf16, nullptr, x, gamma, mean, rstd, N, D, 0.f, 0ull, dx, nullptr, dgamma, dbeta,
+                                           workspace, workspace_bytes, stream);
 }
 
 extern "C" int64_t mobgt_colsum_workspace_bytes(int32_t N, int32_t C) {

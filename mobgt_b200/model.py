@@ -138,13 +138,19 @@ class MultiHeadAttention(nn.Module):
         self.attention_dropout_rate = attention_dropout_rate
         self.output_layer = nn.Linear(num_heads * self.att_size, hidden_size)
 
-    def forward(self, x16, bias_slot, layer=0):
-        """x16: bf16 [ntok, hidden] (the LayerNorm kernel of the previous layer emits this copy)."""
-        w = torch.cat([self.linear_q.weight, self.linear_k.weight, self.linear_v.weight], 0)
-        b = torch.cat([self.linear_q.bias, self.linear_k.bias, self.linear_v.bias], 0)
-        qkv = ops.LinearBiasFn.apply(x16, w.to(torch.bfloat16), b.to(torch.bfloat16))
+    def forward(self, x16, bias_slot, layer=0, w16=None):
+        """x16: bf16 [ntok, hidden] (the LayerNorm kernel of the previous layer emits this copy); w16: Bf16Weights or None."""
+        q, k, v = self.linear_q, self.linear_k, self.linear_v
+        if w16 is not None:
+            wq, bq = w16.get((layer, "qkv"))
+            wo, bo = w16.get((layer, "o"))
+        else:
+            wq = torch.cat([q.weight, k.weight, v.weight], 0).detach().to(torch.bfloat16)
+            bq = torch.cat([q.bias, k.bias, v.bias], 0).detach().to(torch.bfloat16)
+            wo = bo = None
+        qkv = ops.LinearBiasFn.apply(x16, wq, bq, q.weight, k.weight, v.weight, q.bias, k.bias, v.bias)
         a = ops.BiasedAttention.apply(qkv, bias_slot, layer)
-        return ops.linear_bf16(a, self.output_layer)
+        return ops.linear_bf16(a, self.output_layer, wo, bo)
 
 
 class EncoderLayer(nn.Module):
@@ -160,16 +166,17 @@ class EncoderLayer(nn.Module):
         self.ffn = FeedForwardNetwork(hidden_size, ffn_size, dropout_rate)
         self.ffn_dropout = nn.Dropout(dropout_rate)
 
-    def forward(self, x, x16, bias_slot, layer=0):
+    def forward(self, x, x16, bias_slot, layer=0, w16=None):
         """x: fp32 residual stream [ntok, hidden]; x16: its bf16 copy.  Residual stream and LayerNorms in fp32, GEMMs /
-        attention in bf16 (the reference's --precision 16 AMP split).  LayerNorms and the Linear bias gradients are K6."""
-        y = self.self_attention(x16, bias_slot, layer)
-        x = x + self.self_attention_dropout(y).float()
-        y16 = ops.layer_norm(x, self.ffn_norm1, "bf16")
+        attention in bf16 (the reference's --precision 16 AMP split).  Each residual add + dropout + LayerNorm is one K6 kernel
+        per direction; the Linear bias gradients are the K6 column sum."""
+        y = self.self_attention(x16, bias_slot, layer, w16)
+        x1, y16 = ops.add_dropout_layer_norm(x, y, self.ffn_norm1, self.self_attention_dropout.p, self.training, "bf16", need_s=True)
         f = self.ffn
-        y = ops.linear_bf16(F.gelu(ops.linear_bf16(y16, f.layer1)), f.layer2)
-        x = x + self.ffn_dropout(y).float()
-        return ops.layer_norm(x, self.ffn_norm2, "both")
+        w1, b1 = w16.get((layer, "f1")) if w16 is not None else (None, None)
+        w2, b2 = w16.get((layer, "f2")) if w16 is not None else (None, None)
+        y = ops.linear_bf16(F.gelu(ops.linear_bf16(y16, f.layer1, w1, b1)), f.layer2, w2, b2)
+        return ops.add_dropout_layer_norm(x1, y, self.ffn_norm2, self.ffn_dropout.p, self.training, "both")
 
 
 def gradient_tail_loss(inputs, targets, alpha=0.25, beta=1, k=1):
@@ -221,6 +228,13 @@ class Graphormer(nn.Module):
         self.input_dropout = nn.Dropout(intput_dropout_rate)
         self.output_dropout = nn.Dropout(intput_dropout_rate)
         self.layers = nn.ModuleList([EncoderLayer(D, ffn_dim, dropout_rate, attention_dropout_rate, H) for _ in range(n_layers)])
+        self._w16 = ops.Bf16Weights()          # bf16 working copies of the encoder's Linear parameters
+        for li, layer in enumerate(self.layers):
+            a = layer.self_attention
+            self._w16.register((li, "qkv"), [a.linear_q, a.linear_k, a.linear_v])
+            self._w16.register((li, "o"), [a.output_layer])
+            self._w16.register((li, "f1"), [layer.ffn.layer1])
+            self._w16.register((li, "f2"), [layer.ffn.layer2])
         self.final_ln = nn.LayerNorm(2 * hidden_dim + 64)
         self.out_proj = nn.Linear(2 * hidden_dim + 64, P + tr["poi_extra"])
         self.ELU = nn.ELU()
@@ -286,8 +300,9 @@ class Graphormer(nn.Module):
         slot = ops.BiasSlot(bias, b, len(self.layers))
         x = ops.BiasGradSink.apply(self.input_dropout(tok).float(), bias, slot)                          # :1347
         x16 = x.to(torch.bfloat16)
+        self._w16.refresh()
         for li, layer in enumerate(self.layers):                                                         # :1348-1352
-            x, x16 = layer(x, x16, slot, li)
+            x, x16 = layer(x, x16, slot, li, self._w16)
         z0 = x.index_select(0, b.tok_off[:-1].long()).float()                                            # output[:, 0, :]
         user_embedding = self.user_embed_model(b.user.view(-1) - 1)                                      # :1239
         z = self.embed_fuse_model3(z0, user_embedding)                                                   # :1356 (token 0 only)

@@ -338,28 +338,147 @@ def layer_norm(x, ln, want="f32"):
     return LayerNormFn.apply(x, ln.weight, ln.bias, ln.eps, want)
 
 
-class LinearBiasFn(torch.autograd.Function):
-    """y = x W^T + b with bf16 operands (library GEMMs); the bias gradient dy.sum(0) is the K6 column-sum kernel (fp32
-    accumulation, fixed order) instead of torch's generic reduce."""
+_drop_calls = 0
+
+
+def _next_drop_seed():
+    """A fresh 64-bit seed per dropout call, derived from torch's seed (torch.manual_seed makes runs reproducible)."""
+    global _drop_calls
+    _drop_calls += 1
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + _drop_calls * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+
+
+class AddDropoutLayerNormFn(torch.autograd.Function):
+    """The post-LN residual block of EncoderLayer.forward (model_fqandtoyo.py:1731-1743) in one kernel each way:
+        s = x + dropout(y) ;  out = LayerNorm(s)
+    x f32 [N, D] residual stream, y bf16 [N, D] sub-layer output.  Returns (s, outputs...) with outputs per `want` as in
+    LayerNormFn; s is returned only when `need_s` (it feeds the next residual add)."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
-        ctx.save_for_backward(x, w)
-        return torch.nn.functional.linear(x, w, b)
+    def forward(ctx, x, y, gamma, beta, eps, p, want, need_s):
+        x, y = x.contiguous(), y.contiguous()
+        N, D = x.shape
+        dev = x.device
+        s = torch.empty(N, D, dtype=torch.float32, device=dev)
+        out = torch.empty(N, D, dtype=torch.float32, device=dev) if want != "bf16" else None
+        out16 = torch.empty(N, D, dtype=torch.bfloat16, device=dev) if want != "f32" else None
+        mean = torch.empty(N, dtype=torch.float32, device=dev)
+        rstd = torch.empty(N, dtype=torch.float32, device=dev)
+        g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        seed = _next_drop_seed() if p > 0 else 0
+        _C.call("mobgt_add_dropout_layernorm_fwd", _C.ptr(x), _C.ptr(y), float(p), seed, _C.ptr(g), _C.ptr(b), float(eps), N, D,
+                _C.ptr(s), _C.ptr(out), _C.ptr(out16), _C.ptr(mean), _C.ptr(rstd), _C.stream_ptr())
+        ctx.save_for_backward(s, g, mean, rstd)
+        ctx.cfg = (float(p), seed, want, need_s)
+        outs = {"f32": (out,), "bf16": (out16,), "both": (out, out16)}[want]
+        return ((s,) + outs) if need_s else outs if len(outs) > 1 else outs[0]
+
+    @staticmethod
+    def backward(ctx, *grads):
+        s, g, mean, rstd = ctx.saved_tensors
+        p, seed, want, need_s = ctx.cfg
+        N, D = s.shape
+        grads = list(grads)
+        ds_ext = grads.pop(0) if need_s else None
+        if want == "f32":
+            dy32, dy16 = grads[0], None
+        elif want == "bf16":
+            dy32, dy16 = None, grads[0]
+        else:
+            dy32, dy16 = grads
+        if dy32 is None and dy16 is None:          # only the residual branch carries a gradient
+            dy32 = torch.zeros_like(s)
+        c = lambda t: t.contiguous() if t is not None else None
+        dy32, dy16, ds_ext = c(dy32), c(dy16), c(ds_ext)
+        dx = torch.empty_like(s)
+        dyb = torch.empty(N, D, dtype=torch.bfloat16, device=s.device)
+        dgamma = torch.empty(D, dtype=torch.float32, device=s.device)
+        dbeta = torch.empty(D, dtype=torch.float32, device=s.device)
+        ws_bytes = int(_C.lib().mobgt_layernorm_bwd_workspace_bytes(D))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=s.device)
+        _C.call("mobgt_add_dropout_layernorm_bwd", _C.ptr(dy32), _C.ptr(dy16), _C.ptr(ds_ext), _C.ptr(s), _C.ptr(g), _C.ptr(mean),
+                _C.ptr(rstd), N, D, p, seed, _C.ptr(dx), _C.ptr(dyb), _C.ptr(dgamma), _C.ptr(dbeta), _C.ptr(ws), ws_bytes,
+                _C.stream_ptr())
+        return dx, dyb, dgamma, dbeta, None, None, None, None
+
+
+def add_dropout_layer_norm(x, y, ln, p, training, want="f32", need_s=False):
+    return AddDropoutLayerNormFn.apply(x, y, ln.weight, ln.bias, ln.eps, float(p) if training else 0.0, want, need_s)
+
+
+
+class LinearBiasFn(torch.autograd.Function):
+    """y = x W^T + b with bf16 operands (library GEMMs).  w16 / b16 are the bf16 working copies of the fp32 master parameters
+    `masters` = (w_0, ..., w_{m-1}, b_0, ..., b_{m-1}) — m > 1 when several nn.Linear are fused into one GEMM (q, k, v), their
+    rows stacked in w16.  The gradients go straight to the masters in fp32; the bias gradient dy.sum(0) is the K6 column-sum
+    kernel (fp32 accumulation, fixed order) instead of torch's generic reduce."""
+
+    @staticmethod
+    def forward(ctx, x, w16, b16, *masters):
+        ctx.save_for_backward(x, w16)
+        ctx.rows = [w.shape[0] for w in masters[:len(masters) // 2]]
+        return torch.nn.functional.linear(x, w16, b16)
 
     @staticmethod
     def backward(ctx, dy):
-        x, w = ctx.saved_tensors
+        x, w16 = ctx.saved_tensors
         dy = dy.contiguous()
-        dx = dy @ w
-        dw = dy.t() @ x
-        db = colsum(dy).to(dy.dtype)
-        return dx, dw, db
+        dx = dy @ w16
+        dw = (dy.t() @ x).float()
+        db = colsum(dy)
+        if len(ctx.rows) == 1:
+            return dx, None, None, dw, db
+        return (dx, None, None) + tuple(dw.split(ctx.rows, 0)) + tuple(db.split(ctx.rows, 0))
 
 
-def linear_bf16(x, lin):
-    """nn.Linear `lin` (fp32 master weights) applied to a bf16 [N, in] tensor."""
-    return LinearBiasFn.apply(x, lin.weight.to(torch.bfloat16), lin.bias.to(torch.bfloat16))
+class Bf16Weights:
+    """bf16 working copies of a set of fp32 nn.Linear parameters, refreshed with ONE multi-tensor copy when an optimizer step
+    has changed the masters (tensor version counters) — instead of a cast kernel + autograd node per parameter per step."""
+
+    def __init__(self):
+        self.groups = []          # (key, [linears])
+        self.bufs = {}
+        self.stamp = None
+
+    def register(self, key, linears):
+        self.groups.append((key, list(linears)))
+
+    def _alloc(self, dev):
+        for key, lins in self.groups:
+            rows = sum(l.weight.shape[0] for l in lins)
+            w = torch.empty(rows, lins[0].weight.shape[1], dtype=torch.bfloat16, device=dev)
+            b = torch.empty(rows, dtype=torch.bfloat16, device=dev)
+            self.bufs[key] = (w, b)
+        self.dst, self.src = [], []
+        for key, lins in self.groups:
+            w, b = self.bufs[key]
+            r = 0
+            for l in lins:
+                n = l.weight.shape[0]
+                self.dst += [w[r:r + n], b[r:r + n]]
+                self.src += [l.weight, l.bias]
+                r += n
+
+    def get(self, key):
+        return self.bufs[key]
+
+    def refresh(self):
+        dev = self.groups[0][1][0].weight.device
+        if not self.bufs or next(iter(self.bufs.values()))[0].device != dev:
+            self._alloc(dev)
+            self.stamp = None
+        stamp = sum(p._version for p in self.src)
+        if stamp != self.stamp:
+            with torch.no_grad():
+                torch._foreach_copy_(self.dst, [p.detach() for p in self.src])
+            self.stamp = sum(p._version for p in self.src)
+
+
+def linear_bf16(x, lin, w16=None, b16=None):
+    """nn.Linear `lin` (fp32 master weights) applied to a bf16 [N, in] tensor; w16 / b16: its bf16 working copies."""
+    if w16 is None:
+        w16, b16 = lin.weight.detach().to(torch.bfloat16), lin.bias.detach().to(torch.bfloat16)
+    return LinearBiasFn.apply(x, w16, b16, lin.weight, lin.bias)
 
 
 # ----------------------------------------------------------------------------------------------- K5

@@ -298,3 +298,42 @@ def test_colsum_vs_torch(lib_built, N, C, dt):
     wide = torch.randn(N, 2 * C, generator=g).cuda().to(dt)
     got2 = ops.colsum(wide[:, C:])
     assert (got2.double() - wide[:, C:].double().sum(0)).abs().max().item() <= 1e-5 * N ** 0.5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_add_dropout_layernorm_vs_torch(lib_built, p):
+    """s = x + dropout(y); out = LN(s): against torch with the SAME mask (recovered from the kernel's own s output)."""
+    from mobgt_b200 import ops
+    N, D = 777, 192
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(N, D, generator=g).cuda()
+    y = torch.randn(N, D, generator=g).cuda().to(torch.bfloat16)
+    ln = torch.nn.LayerNorm(D).cuda()
+    with torch.no_grad():
+        ln.weight.copy_(torch.randn(D, generator=g).cuda() * 0.5 + 1)
+        ln.bias.copy_(torch.randn(D, generator=g).cuda() * 0.1)
+    xo, yo = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    s, out, out16 = ops.add_dropout_layer_norm(xo, yo, ln, p, True, "both", need_s=True)
+    keep = (s.detach() != x) | (y.float() == 0)                       # the mask the kernel drew
+    if p == 0.0:
+        assert keep.all()
+    else:
+        assert 0.85 < keep.float().mean().item() < 0.95
+    scale = 1.0 / (1.0 - p)
+    xr, yr = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    dropped = (yr * scale * keep).to(torch.bfloat16) if p > 0 else yr
+    sr = xr + dropped.float()
+    ref = torch.nn.functional.layer_norm(sr, (D,), ln.weight, ln.bias, ln.eps)
+    assert torch.allclose(s, sr.detach(), rtol=0, atol=1e-6)
+    assert torch.allclose(out, ref.detach(), rtol=1e-5, atol=1e-5)
+    dy32, dy16, dse = (torch.randn(N, D, generator=g).cuda() for _ in range(3))
+    dy16 = dy16.to(torch.bfloat16)
+    ln.zero_grad()
+    (ref * (dy32 + dy16.float())).sum().backward(retain_graph=True)
+    (sr * dse).sum().backward()
+    ref_g = (xr.grad.clone(), yr.grad.float().clone(), ln.weight.grad.clone(), ln.bias.grad.clone())
+    ln.zero_grad()
+    ((out * dy32).sum() + (out16.float() * dy16.float()).sum() + (s * dse).sum()).backward()
+    got = (xo.grad, yo.grad.float(), ln.weight.grad, ln.bias.grad)
+    for a, b, tol in zip(got, ref_g, (2e-5, 1e-2, 2e-5, 2e-5)):
+        assert (a - b).abs().max().item() <= tol * b.abs().max().item() + 1e-4
