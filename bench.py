@@ -296,12 +296,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, finalize=None):
         barrier()
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(steps):
             fn()
+        if finalize is not None:
+            finalize()
         b_.record()
         barrier()
         ms = torch.tensor([a.elapsed_time(b_)], device=dev)
@@ -323,22 +325,42 @@ def run_ours(args):
         while True:
             yield items
 
-    # one-batch-ahead loader (the reference's DataLoader-worker role): the host packing + H2D + K1 of batch i+1 are issued
-    # right after the kernels of step i have been enqueued, so they overlap its GPU time; every timed step still contains
-    # exactly one collate (pack + pinned H2D + K1 + poi_pos), one training step and one D2H read of the loss
-    loader = collator.PackedLoader(endless(), lambda it: collator.collate_packed(it, world, latlon, 512, 20, 1024, device=dev))
+    # one-batch-ahead loader (the reference's DataLoader-worker role, data.py:255-267): the numpy packing of the raw items runs
+    # in 2 worker processes that hand over one pinned byte buffer per batch; the H2D copy, the sort plans, K1 and poi_pos of
+    # batch i+1 are issued right after the kernels of step i have been enqueued.  Every timed step still contains exactly one
+    # collate (pack + pinned H2D + K1 + poi_pos), one training step and one D2H read of the loss.
+    loader = collator.PackedLoader(endless(), num_workers=args.loader_workers, world=world, latlon_dev=latlon,
+                                   multi_hop_max_dist=20, rel_pos_max=1024, device=dev)
+
+    # the loss of every step is read back to the host (async D2H into pinned memory + event); the host consumes it one step
+    # late, so the read-back does not drain the GPU queue between steps.  The last read happens inside the timed region.
+    loss_pin = torch.empty(2, dtype=torch.float32).pin_memory()
+    state = dict(pending=None, k=0)
+
+    def e2e_flush():
+        if state["pending"] is not None:
+            ev, slot = state["pending"]
+            ev.synchronize()
+            losses.append(float(loss_pin[slot]))
+            state["pending"] = None
 
     def e2e_step():
         b = loader.current()
         loss = train_step(b)
+        slot = state["k"] & 1
+        loss_pin[slot:slot + 1].copy_(loss.detach().view(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
         loader.advance()
-        losses.append(float(loss.item()))
+        e2e_flush()                       # the PREVIOUS step's loss (its event has long completed)
+        state["pending"], state["k"] = (ev, slot), state["k"] + 1
         return b
 
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(max(2, args.warmup // 2)):
         bb = e2e_step()
-    e2e_steps = max(2, args.steps // 2)
-    ms_e2e = timed(e2e_step, e2e_steps)
+    e2e_flush()
+    e2e_steps = max(4, args.steps // 2)
+    ms_e2e = timed(e2e_step, e2e_steps, finalize=e2e_flush)
     clocks = sampler.stop() if sampler else None
     h2d = int(bb.h2d_bytes)
     if rank == 0:
@@ -382,6 +404,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2-dense128", choices=["c2-dense128", "c2-natural"])
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--loader-workers", type=int, default=2, help="DataLoader worker processes packing raw items (e2e path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-report", action="store_true")
     args = ap.parse_args()

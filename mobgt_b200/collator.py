@@ -49,37 +49,42 @@ class _Staging:
 _staging = {}
 
 
-def _upload(host, dev):
-    """host: name -> numpy array.  One pinned buffer, one async H2D copy; returns name -> device tensor views."""
-    offs, total = {}, 0
-    for k, a in host.items():
-        a = np.ascontiguousarray(a)
-        host[k] = a
-        offs[k] = total
-        total += (a.nbytes + 15) // 16 * 16
-    st = _staging.setdefault(str(dev), _Staging())
-    slot, pinned = st.get(total)
-    pn = pinned.numpy()
-    for k, a in host.items():
-        pn[offs[k]:offs[k] + a.nbytes] = a.reshape(-1).view(np.uint8)
-    dbuf = torch.empty(max(total, 16), dtype=torch.uint8, device=dev)
-    dbuf[:total].copy_(pinned[:total], non_blocking=True)
-    st.mark(slot)
-    out = {}
-    for k, a in host.items():
-        t = dbuf[offs[k]:offs[k] + a.nbytes].view(torch.from_numpy(a[:0].reshape(-1)).dtype)
-        out[k] = t.view(a.shape)
-    return out
+class _PackStream(torch.utils.data.IterableDataset):
+    """Worker-side half of PackedLoader: worker w packs the batches i = w (mod num_workers) of the stream."""
+
+    def __init__(self, batches, max_node):
+        self.batches, self.max_node = batches, max_node
+
+    def __iter__(self):
+        info = torch.utils.data.get_worker_info()
+        w, nw = (info.id, info.num_workers) if info is not None else (0, 1)
+        for i, items in enumerate(self.batches):
+            if i % nw == w:
+                hp = pack_host(items, self.max_node)
+                yield dict(buf=torch.from_numpy(hp.buf), layout=hp.layout, B=hp.B, N=hp.N, ns=torch.from_numpy(hp.ns), cells=hp.cells)
 
 
 class PackedLoader:
-    """One-batch-ahead collation (the role of the reference's DataLoader workers, data.py:255-267): `next()` hands out the
-    batch whose host packing, H2D copy and K1 / poi_pos kernels were issued during the PREVIOUS call, then collates the
-    following one — while the GPU is still busy with the caller's training step.  `batches` is an iterator of item lists."""
+    """One-batch-ahead collation (the role of the reference's DataLoader workers, data.py:255-267).  `batches` is an iterable
+    of item lists.
+      * num_workers = 0: `advance()` packs the next batch on the calling thread — right after the kernels of the current step
+        have been enqueued, so the packing, H2D copy and K1 / poi_pos kernels overlap the step's GPU time;
+      * num_workers > 0: the numpy packing (`pack_host`) runs in DataLoader worker processes which hand over ONE byte buffer
+        per batch through shared memory; the calling thread copies it into the pinned staging buffer and issues the H2D copy
+        and the collation kernels (`collate_from_host`).
+    """
 
-    def __init__(self, batches, collate_fn):
-        self._it = iter(batches)
-        self._collate = collate_fn
+    def __init__(self, batches, collate_fn=None, num_workers=0, max_node=512, **collate_kw):
+        self._kw = collate_kw
+        if num_workers > 0:
+            ds = _PackStream(batches, max_node)
+            dl = torch.utils.data.DataLoader(ds, batch_size=None, num_workers=num_workers, pin_memory=False, prefetch_factor=2,
+                                             persistent_workers=False)
+            self._it = iter(dl)
+            self._collate = lambda d: collate_from_host(HostPack(d["buf"], d["layout"], d["B"], d["N"], d["ns"], d["cells"]), **self._kw)
+        else:
+            self._it = iter(batches)
+            self._collate = collate_fn if collate_fn is not None else (lambda items: collate_packed(items, max_node=max_node, **self._kw))
         self._next = self._pull()
 
     def _pull(self):
@@ -230,11 +235,17 @@ class Batch1:
         raise AttributeError(name)
 
 
-def collate_packed(items, world=None, latlon_dev=None, max_node=512, multi_hop_max_dist=20, rel_pos_max=1024,
-                   device="cuda", want_path=False):
-    """Shared body of the three POI collators.  items: raw dataset items (owndata.py:340-349 fields; numpy or
-    torch).  Returns a device-resident Batch1."""
-    _C.require_cuda()
+class HostPack:
+    """The host half of a collated batch: every host-packed array laid out in ONE byte buffer (16-byte aligned segments),
+    plus the few Python scalars the device half needs.  Pure numpy: safe to build in DataLoader worker processes, cheap to
+    ship through shared memory, and uploaded with a single H2D copy."""
+
+    def __init__(self, buf, layout, B, N, ns, cells):
+        self.buf, self.layout, self.B, self.N, self.ns, self.cells = buf, layout, B, N, ns, cells
+
+
+def pack_host(items, max_node=512):
+    """raw dataset items (owndata.py:340-349 fields; numpy or torch) -> HostPack.  No CUDA, no torch ops on the hot path."""
     items = [it for it in items if it is not None and len(_to_np(it.x)) <= max_node]     # collator.py:313
     B = len(items)
     ns = np.array([len(_to_np(it.x)) for it in items], np.int32)
@@ -249,8 +260,6 @@ def collate_packed(items, world=None, latlon_dev=None, max_node=512, multi_hop_m
     ei = np.concatenate(eis, axis=1).astype(np.int64) if B else np.zeros((2, 0), np.int64)
     ea = np.concatenate([_to_np(it.edge_attr).reshape(-1) for it in items]).astype(np.int64) if B else np.zeros(0, np.int64)
     eg = np.repeat(np.arange(B), ecnt)                    # graph of every edge
-    feat = np.zeros(cells, np.uint8)
-    feat[sq[:-1][eg] + ei[0] * ns.astype(np.int64)[eg] + ei[1]] = ea + 2     # wrapper.py:49-53: convert_to_single_emb(+1) then +1
     indeg = np.bincount(no[:-1][eg] + ei[0], minlength=Nn).astype(np.int32)   # wrapper.py:97: adj.sum(dim=1)
     outdeg = np.bincount(no[:-1][eg] + ei[1], minlength=Nn).astype(np.int32)  # wrapper.py:98: adj.sum(dim=0)
 
@@ -275,31 +284,77 @@ def collate_packed(items, world=None, latlon_dev=None, max_node=512, multi_hop_m
     tok_graph[rows] = g_of_node
     tok_pos[rows] = pos_of_node
     tok_graph[tok_off[:-1]] = np.arange(B)
-
-    dev = torch.device(device)
-    # ONE pinned staging buffer and ONE host->device copy for all host-packed arrays (17 small pin_memory() allocations and
-    # copies cost more than the transfer itself); the device tensors below are typed views into the single device buffer
-    host = dict(n=ns, sq_off=sq, node_off=no, tok_off=tok_off, tok_graph=tok_graph, tok_pos=tok_pos, feat8=feat,
+    host = dict(n=ns, sq_off=sq, node_off=no, tok_off=tok_off, tok_graph=tok_graph, tok_pos=tok_pos, feat8=None,
                 x_nodes=x_nodes, slot=slot, time_nodes=time_nodes, time_normal_nodes=tn, cat_nodes=cat_nodes,
                 in_deg=indeg + 1, out_deg=outdeg + 1,                          # pad_1d_unsqueeze "+1" (collator.py:12)
                 user=user, y=y, idx=idx, node_rows=rows.astype(np.int64))
-    views = _upload(host, dev)
-    b = Batch1(B=B, N=int(ns.max()) if B else 0, hops=int(multi_hop_max_dist), rel_pos_max=int(rel_pos_max), n_host=ns,
-               h2d_bytes=0, **views)
+    layout, total = {}, 0
+    for k, a in host.items():
+        if k == "feat8":
+            shape, dt, nbytes = (cells,), np.dtype(np.uint8), cells
+        else:
+            a = np.ascontiguousarray(a)
+            host[k] = a
+            shape, dt, nbytes = a.shape, a.dtype, a.nbytes
+        layout[k] = (total, shape, dt.str, nbytes)
+        total += (nbytes + 15) // 16 * 16
+    buf = np.zeros(max(total, 16), np.uint8)
+    for k, a in host.items():
+        if a is not None:
+            off, _, _, nbytes = layout[k]
+            buf[off:off + nbytes] = a.reshape(-1).view(np.uint8)
+    # the edge-type plane is scattered straight into its segment of the buffer
+    off = layout["feat8"][0]
+    buf[off + sq[:-1][eg] + ei[0] * ns.astype(np.int64)[eg] + ei[1]] = ea + 2     # wrapper.py:49-53: convert_to_single_emb(+1) then +1
+    return HostPack(buf, layout, B, int(ns.max()) if B else 0, ns, cells)
+
+
+def _upload_pack(hp, dev):
+    """HostPack -> name -> device tensor views (one async H2D copy from pinned memory)."""
+    total = int(hp.buf.shape[0])
+    src = hp.buf.numpy() if isinstance(hp.buf, torch.Tensor) else hp.buf      # worker batches arrive as shared-memory tensors
+    st = _staging.setdefault(str(dev), _Staging())
+    slot, pinned = st.get(total)
+    pinned.numpy()[:total] = src              # plain memcpy into the persistent pinned staging buffer (numpy: no thread-pool launch)
+    dbuf = torch.empty(total, dtype=torch.uint8, device=dev)
+    dbuf.copy_(pinned[:total], non_blocking=True)
+    st.mark(slot)
+    out = {}
+    for k, (off, shape, dts, nbytes) in hp.layout.items():
+        tdt = torch.from_numpy(np.zeros(0, np.dtype(dts))).dtype
+        out[k] = dbuf[off:off + nbytes].view(tdt).view(tuple(shape))
+    return out
+
+
+def collate_from_host(hp, world=None, latlon_dev=None, multi_hop_max_dist=20, rel_pos_max=1024, device="cuda", want_path=False):
+    """The device half of collation: one H2D copy, the K4-backward sort plans, K1 (APSP + path edges) and poi_pos."""
+    _C.require_cuda()
+    dev = torch.device(device)
+    views = _upload_pack(hp, dev)
+    ns = hp.ns.numpy() if isinstance(hp.ns, torch.Tensor) else hp.ns
+    b = Batch1(B=hp.B, N=hp.N, hops=int(multi_hop_max_dist), rel_pos_max=int(rel_pos_max), n_host=ns, h2d_bytes=0, **views)
     b.h2d_bytes = int(sum(v.numel() * v.element_size() for v in views.values()))
     b.build_plans()
     k1 = apsp_edge_input_packed(b.feat8, b.n, b.sq_off, ns, hops=int(multi_hop_max_dist), shift=1, want_path=want_path)
     b.rel_pos16, b.edge_in8, b.maxdist, b.path16 = k1["dist"], k1["edge_in"], k1["maxdist"], k1["path"]
-    b.poi_pos16 = torch.empty(cells, dtype=torch.int16, device=dev)
+    b.poi_pos16 = torch.empty(hp.cells, dtype=torch.int16, device=dev)
     if world is not None:
         if latlon_dev is None:
             latlon_dev = torch.from_numpy(world.latlon).to(dev)
         b._latlon = latlon_dev
         _C.call("mobgt_poi_pos", _C.ptr(b.x_nodes), _C.ptr(b.n), _C.ptr(b.sq_off), _C.ptr(b.node_off), _C.ptr(latlon_dev),
-                float(np.float32(world.dist_max)), int(world.num_bins), B, int(b.N), _C.ptr(b.poi_pos16), _C.stream_ptr())
+                float(np.float32(world.dist_max)), int(world.num_bins), hp.B, int(b.N), _C.ptr(b.poi_pos16), _C.stream_ptr())
     else:
         b.poi_pos16.fill_(1)
     return b
+
+
+def collate_packed(items, world=None, latlon_dev=None, max_node=512, multi_hop_max_dist=20, rel_pos_max=1024,
+                   device="cuda", want_path=False):
+    """Shared body of the three POI collators.  items: raw dataset items (owndata.py:340-349 fields; numpy or
+    torch).  Returns a device-resident Batch1."""
+    _C.require_cuda()
+    return collate_from_host(pack_host(items, max_node), world, latlon_dev, multi_hop_max_dist, rel_pos_max, device, want_path)
 
 
 def collator_foursquare(items, max_node=512, multi_hop_max_dist=20, rel_pos_max=20, world=None, latlon_dev=None, **kw):
