@@ -130,23 +130,58 @@ __global__ void k4_segsum_a_kernel(const T *__restrict__ src, int64_t src_stride
     }
 }
 
+// Pass B: a run that leaves chunk c through its tail continues through the heads of the following chunks.  The end of the
+// run is found by a ballot scan of the chunk flags; the head partials are then summed by kSegRows thread rows over strided
+// chunks and folded in a fixed order (deterministic).  Long runs (low-cardinality keys such as degrees: hundreds of chunks)
+// no longer walk the chain one chunk at a time.
+constexpr int kSegRows = 8;
 __global__ void k4_segsum_b_kernel(const float *__restrict__ part, const int32_t *__restrict__ flags,
                                    const int32_t *__restrict__ tail_key, int nchunks, int D, float *__restrict__ table,
                                    int nkeys) {
+    extern __shared__ __align__(16) float sfold[];      // [kSegRows][D]
+    __shared__ int s_end;
     const int c = blockIdx.x;
     if (!(flags[c] & kHasTail)) return;
-    const int e0 = threadIdx.x * 4;
-    if (e0 >= D) return;
-    float4 acc = *reinterpret_cast<const float4 *>(part + ((size_t)c * 2 + 1) * D + e0);
-    for (int cc = c + 1; cc < nchunks; ++cc) {
-        const int f = flags[cc];
-        if (!(f & kHasHead)) break;
-        const float4 h = *reinterpret_cast<const float4 *>(part + ((size_t)cc * 2 + 0) * D + e0);
-        acc.x += h.x; acc.y += h.y; acc.z += h.z; acc.w += h.w;
-        if (!(f & kHeadContinues)) break;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    if (ty == 0 && tx < 32) {
+        int end = nchunks;                               // exclusive end of the chunks whose head belongs to this run
+        for (int base = c + 1; base < nchunks; base += 32) {
+            const int cc = base + tx;
+            const int f = cc < nchunks ? flags[cc] : 0;
+            const bool excl = !(f & kHasHead);                              // the run ended before chunk cc
+            const bool incl = (f & kHasHead) && !(f & kHeadContinues);      // the run ends inside chunk cc
+            const unsigned m = __ballot_sync(0xffffffffu, excl || incl);
+            if (m != 0u) {
+                const int L = __ffs(m) - 1;
+                const bool incl_first = __shfl_sync(0xffffffffu, (int)incl, L) != 0;
+                end = base + L + (incl_first ? 1 : 0);
+                break;
+            }
+        }
+        if (tx == 0) s_end = end;
     }
-    const int key = tail_key[c];
-    if (key >= 0 && key < nkeys) *reinterpret_cast<float4 *>(table + (size_t)key * D + e0) = acc;
+    __syncthreads();
+    const int end = s_end;
+    const int e0 = tx * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e0 < D) {
+        if (ty == 0) acc = *reinterpret_cast<const float4 *>(part + ((size_t)c * 2 + 1) * D + e0);
+        for (int cc = c + 1 + ty; cc < end; cc += (int)blockDim.y) {
+            const float4 h = *reinterpret_cast<const float4 *>(part + ((size_t)cc * 2 + 0) * D + e0);
+            acc.x += h.x; acc.y += h.y; acc.z += h.z; acc.w += h.w;
+        }
+        *reinterpret_cast<float4 *>(sfold + (size_t)ty * D + e0) = acc;
+    }
+    __syncthreads();
+    if (ty == 0 && e0 < D) {
+        float4 t = *reinterpret_cast<const float4 *>(sfold + e0);
+        for (int r = 1; r < (int)blockDim.y; ++r) {
+            const float4 h = *reinterpret_cast<const float4 *>(sfold + (size_t)r * D + e0);
+            t.x += h.x; t.y += h.y; t.z += h.z; t.w += h.w;
+        }
+        const int key = tail_key[c];
+        if (key >= 0 && key < nkeys) *reinterpret_cast<float4 *>(table + (size_t)key * D + e0) = t;
+    }
 }
 
 template <typename T>
@@ -222,7 +257,9 @@ extern "C" int32_t mobgt_segment_sum(const void *src, int32_t src_dtype, int64_t
                                                                       D, perm, keys_sorted, nrows, table, nkeys, part, flags,
                                                                       tail_key);
     MOBGT_LAUNCH_OK("k4_segsum_a_kernel");
-    k4_segsum_b_kernel<<<nchunks, threads, 0, s>>>(part, flags, tail_key, nchunks, D, table, nkeys);
+    const int seg_rows = min(kSegRows, 1024 / threads);
+    k4_segsum_b_kernel<<<nchunks, dim3(threads, seg_rows), (size_t)seg_rows * D * sizeof(float), s>>>(part, flags, tail_key, nchunks, D,
+                                                                                                 table, nkeys);
     MOBGT_LAUNCH_OK("k4_segsum_b_kernel");
     return MOBGT_OK;
 }
