@@ -16,7 +16,8 @@
 namespace mobgt {
 
 constexpr int kNormWarps = 8;        // warps (rows in flight) per CTA
-constexpr int kNormCtas = 2 * kNumSMs;
+constexpr int kNormCtas = 6 * kNumSMs;      // forward: 6 CTAs x 8 warps resident per SM (40 registers / thread)
+constexpr int kNormCtasBwd = 4 * kNumSMs;   // backward: 4 CTAs per SM (64 registers / thread)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -156,15 +157,25 @@ __global__ void __launch_bounds__(kNormWarps * 32) k6_layernorm_bwd_kernel(const
     }
 }
 
-// out[c] = sum over parts (fixed order) of partial[part][c]
-__global__ void k6_reduce_parts_kernel(const float *__restrict__ partial, int nparts, int C, float *__restrict__ out0, int C0,
-                                       float *__restrict__ out1) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// out[c] = sum over parts of partial[part][c]: block = 32 columns x 8 rows, row r sums the parts p = r (mod 8) in order, the
+// 8 row sums are folded in order (fixed summation tree: deterministic)
+__global__ void __launch_bounds__(256) k6_reduce_parts_kernel(const float *__restrict__ partial, int nparts, int C,
+                                                              float *__restrict__ out0, int C0, float *__restrict__ out1) {
+    __shared__ float sfold[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * C + c];
-    if (c < C0) out0[c] = s;
-    else out1[c - C0] = s;
+    if (c < C)
+        for (int p = ty; p < nparts; p += 8) s += partial[(size_t)p * C + c];
+    sfold[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float t = sfold[0][tx];
+#pragma unroll
+        for (int r = 1; r < 8; ++r) t += sfold[r][tx];
+        if (c < C0) out0[c] = t;
+        else out1[c - C0] = t;
+    }
 }
 
 // column sums of a row-major [N, C] matrix (bf16 or f32, row stride in elements): thread = 8 (bf16) / 4 (f32) adjacent columns
@@ -181,17 +192,25 @@ __global__ void __launch_bounds__(256) k6_colsum_kernel(const T *__restrict__ sr
 #pragma unroll
     for (int i = 0; i < V; ++i) acc[i] = 0.f;
     if (col < C) {
-        for (int r = r0 + warp; r < r1; r += 8) {
-            const uint4 w = *reinterpret_cast<const uint4 *>(src + (size_t)r * stride + col);
-            const uint32_t u[4] = {w.x, w.y, w.z, w.w};
-            if constexpr (sizeof(T) == 4) {
+        // 4 rows (8 warps apart) in flight per iteration: the loads are independent, the adds keep a fixed order
+        for (int r = r0 + warp; r < r1; r += 32) {
+            uint4 w[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i] += __uint_as_float(u[i]);
-            } else {
+            for (int j = 0; j < 4; ++j)
+                w[j] = (r + 8 * j < r1) ? __ldg(reinterpret_cast<const uint4 *>(src + (size_t)(r + 8 * j) * stride + col))
+                                        : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    acc[2 * i] += __uint_as_float(u[i] << 16);
-                    acc[2 * i + 1] += __uint_as_float(u[i] & 0xFFFF0000u);
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t u[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
+                if constexpr (sizeof(T) == 4) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[i] += __uint_as_float(u[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[2 * i] += __uint_as_float(u[i] << 16);
+                        acc[2 * i + 1] += __uint_as_float(u[i] & 0xFFFF0000u);
+                    }
                 }
             }
         }
@@ -269,7 +288,7 @@ extern "C" int32_t mobgt_add_dropout_layernorm_bwd(const float *dy, const void *
     MOBGT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, MOBGT_ERR_BAD_SHAPE, "mobgt_add_dropout_layernorm_bwd: p=%f", (double)drop_p);
     MOBGT_REQUIRE(workspace_bytes >= (int64_t)kNormCtas * 2 * D * 4, MOBGT_ERR_WORKSPACE_TOO_SMALL, "mobgt_add_dropout_layernorm_bwd: workspace");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int grid = N > 0 ? min(kNormCtas, ceil_div(N, kNormWarps)) : 0;
+    const int grid = N > 0 ? min(kNormCtasBwd, ceil_div(N, kNormWarps)) : 0;
     float *partial = static_cast<float *>(workspace);
     if (grid > 0) {
         MOBGT_NORM_DISPATCH(D / 32, (k6_layernorm_bwd_kernel<P_><<<grid, kNormWarps * 32, 0, s>>>(
@@ -278,7 +297,7 @@ extern "C" int32_t mobgt_add_dropout_layernorm_bwd(const float *dy, const void *
                                         static_cast<__nv_bfloat16 *>(dyb_out), partial)));
         MOBGT_LAUNCH_OK("k6_layernorm_bwd_kernel");
     }
-    k6_reduce_parts_kernel<<<ceil_div(2 * D, 128), 128, 0, s>>>(partial, grid, 2 * D, dgamma, D, dbeta);
+    k6_reduce_parts_kernel<<<ceil_div(2 * D, 32), 256, 0, s>>>(partial, grid, 2 * D, dgamma, D, dbeta);
     MOBGT_LAUNCH_OK("k6_reduce_parts_kernel");
     return MOBGT_OK;
 }
@@ -292,7 +311,7 @@ extern "C" int32_t mobgt_layernorm_bwd(const float *dy, const void *dy_bf16, con
 
 extern "C" int64_t mobgt_colsum_workspace_bytes(int32_t N, int32_t C) {
     if (N < 0 || C <= 0) return -1;
-    const int strips = max(1, min(64, ceil_div(N, 256)));
+    const int strips = max(1, min(256, ceil_div(N, 128)));
     return (int64_t)strips * C * (int64_t)sizeof(float);
 }
 
@@ -303,7 +322,7 @@ extern "C" int32_t mobgt_colsum(const void *src, int32_t src_dtype, int64_t src_
     const int V = src_dtype == MOBGT_F32 ? 4 : 8;
     MOBGT_REQUIRE(C > 0 && C % V == 0 && src_stride % V == 0 && ((uintptr_t)src & 15) == 0, MOBGT_ERR_BAD_SHAPE,
                   "mobgt_colsum: C=%d and the row stride must be multiples of %d elements, src 16-byte aligned", C, V);
-    const int strips = max(1, min(64, ceil_div(N, 256)));
+    const int strips = max(1, min(256, ceil_div(N, 128)));
     MOBGT_REQUIRE(workspace_bytes >= (int64_t)strips * C * 4, MOBGT_ERR_WORKSPACE_TOO_SMALL, "mobgt_colsum: workspace");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     float *partial = static_cast<float *>(workspace);
@@ -315,7 +334,7 @@ extern "C" int32_t mobgt_colsum(const void *src, int32_t src_dtype, int64_t src_
         k6_colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(src), src_stride, N, C, rows_per_strip,
                                                              partial);
     MOBGT_LAUNCH_OK("k6_colsum_kernel");
-    k6_reduce_parts_kernel<<<ceil_div(C, 128), 128, 0, s>>>(partial, strips, C, out, C, out);
+    k6_reduce_parts_kernel<<<ceil_div(C, 32), 256, 0, s>>>(partial, strips, C, out, C, out);
     MOBGT_LAUNCH_OK("k6_reduce_parts_kernel");
     return MOBGT_OK;
 }
