@@ -251,7 +251,7 @@ def kernel_report(model, batch, pk, iters=8, head_c5=True):
 # ------------------------------------------------------------------------------------------------ ours
 def run_ours(args):
     import torch.distributed as dist
-    from mobgt_b200 import _C, collator, model as M, synth
+    from mobgt_b200 import _C, collator, graphs, model as M, synth
     rank, world_size = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -280,10 +280,21 @@ def run_ours(args):
     def collate():
         return collator.collate_packed(items, world, latlon, 512, 20, 1024, device=dev)
 
+    graphed = {"g": None}
+
     def train_step(b):
-        flat.zero_()
-        loss = model.training_step(b)
-        loss.backward()
+        g = graphed["g"]
+        loss = None
+        if g is not None:
+            try:
+                g.load(b)
+                loss = g.run()
+            except graphs.ShapeMismatch:
+                loss = None
+        if loss is None:
+            flat.zero_()
+            loss = model.training_step(b)
+            loss.backward()
         if world_size > 1:
             dist.all_reduce(flat)
             flat.div_(world_size)
@@ -314,6 +325,18 @@ def run_ours(args):
     batch = collate()
     for _ in range(args.warmup):
         train_step(batch)
+    # fixed-shape workloads: capture forward + backward in a CUDA graph (mobgt_b200/graphs.py); anything not capturable, and every
+    # batch whose shapes differ from the captured ones, runs eagerly
+    graph_note = "off"
+    if args.cuda_graph and args.workload == "c2-dense128":
+        try:
+            graphed["g"] = graphs.GraphedTrainStep(model, flat, batch)
+            graph_note = "fwd+bwd captured"
+            for _ in range(2):
+                train_step(batch)
+        except graphs.GraphCaptureError as e:
+            graph_note = f"eager ({str(e)[:160]})"
+            print(f"[bench] {graph_note}", file=sys.stderr)
     n0 = _C.launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     ms = timed(lambda: train_step(batch), args.steps)
@@ -370,7 +393,7 @@ def run_ours(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": args.workload, "world": "toyotagraph-shaped P=60000 C=300 U=995", "hidden": 128, "layers": 6,
                            "heads": 8, "ffn": 1024, "multi_hop_max_dist": 20, "graphs_per_gpu": B,
-                           "tokens_per_gpu": int(batch.tok_pos.numel()), "parallelism": f"dp{world_size}",
+                           "tokens_per_gpu": int(batch.tok_pos.numel()), "parallelism": f"dp{world_size}", "cuda_graph": graph_note,
                            "l2": "per-step working set (activations + bias planes, > 1 GB) exceeds the 126 MB L2"},
                 "e2e": {"value": graphs * e2e_steps / (ms_e2e / 1e3), "unit": "graphs/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / e2e_steps},
@@ -405,6 +428,7 @@ def main():
     ap.add_argument("--workload", default="c2-dense128", choices=["c2-dense128", "c2-natural"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--loader-workers", type=int, default=2, help="DataLoader worker processes packing raw items (e2e path)")
+    ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false", help="run every step eagerly")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-report", action="store_true")
     args = ap.parse_args()

@@ -178,7 +178,9 @@ int32_t mobgt_segment_sum(const void *src, int32_t src_dtype, int64_t src_stride
  *                  (deterministic two-stage reduction; workspace: mobgt_layernorm_bwd_workspace_bytes(D)).
  *   add_dropout_layernorm_fwd / _bwd: the post-LN residual block  s = x + dropout(y) ; out = LayerNorm(s)  in one pass
  *                  (x f32 residual stream, y bf16 sub-layer output; s_out f32 = the new residual stream, optional).  The mask
- *                  is a counter-based hash of (seed, element index), regenerated in backward: nothing is stored.  Backward:
+ *                  is a counter-based hash of (seed, element index), regenerated in backward: nothing is stored.  seed_dev
+ *                  (u64 in device memory, optional) is folded into the seed at run time, so a CUDA graph that replays the
+ *                  kernels with baked-in arguments draws a fresh mask per replay (increment it inside the graph).  Backward:
  *                  ds = LayerNorm-backward(dy [+ dy_bf16]) + ds_ext (gradient reaching s from its later uses, optional);
  *                  dx = ds ; dyb_out (bf16, optional) = ds * mask / (1 - p).
  *   colsum:        out[c] = sum_r src[r, c]  (src bf16 or f32, row stride in elements; fp32 accumulation, fixed order).
@@ -192,11 +194,11 @@ int32_t mobgt_layernorm_bwd(const float *dy, const void *dy_bf16, const float *x
                             int64_t workspace_bytes, void *stream);
 int32_t mobgt_add_dropout_layernorm_fwd(const float *x, const void *y_bf16, float drop_p, uint64_t seed, const float *gamma,
                                         const float *beta, float eps, int32_t N, int32_t D, float *s_out, float *out, void *out_bf16,
-                                        float *mean, float *rstd, void *stream);
+                                        float *mean, float *rstd, const void *seed_dev, void *stream);
 int32_t mobgt_add_dropout_layernorm_bwd(const float *dy, const void *dy_bf16, const float *ds_ext, const float *s_saved,
                                         const float *gamma, const float *mean, const float *rstd, int32_t N, int32_t D, float drop_p,
                                         uint64_t seed, float *dx, void *dyb_out, float *dgamma, float *dbeta, void *workspace,
-                                        int64_t workspace_bytes, void *stream);
+                                        int64_t workspace_bytes, const void *seed_dev, void *stream);
 int64_t mobgt_colsum_workspace_bytes(int32_t N, int32_t C);
 int32_t mobgt_colsum(const void *src, int32_t src_dtype, int64_t src_stride, int32_t N, int32_t C, float *out, void *workspace,
                      int64_t workspace_bytes, void *stream);

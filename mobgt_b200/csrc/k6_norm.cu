@@ -36,17 +36,29 @@ __device__ __forceinline__ bool drop_keep(uint32_t idx, uint32_t seed_lo, uint32
     return z >= thresh;
 }
 
+// A step counter kept in device memory (optional) is folded into the host seed, so that a CUDA graph that replays these
+// kernels with baked-in arguments still draws a fresh mask every replay (the counter is incremented inside the graph).
+__device__ __forceinline__ void mix_device_seed(const unsigned long long *seed_dev, uint32_t &lo, uint32_t &hi) {
+    if (seed_dev != nullptr) {
+        const unsigned long long sd = *seed_dev;
+        lo ^= (uint32_t)sd * 0x9E3779B1u;
+        hi += (uint32_t)(sd >> 32) ^ ((uint32_t)sd * 0x85EBCA6Bu);
+    }
+}
+
 // out = LayerNorm(s),  s = x + dropout(y)   (y == NULL: s = x).  s is written when s_out != NULL (the new residual stream).
 template <int PER>
 __global__ void __launch_bounds__(kNormWarps * 32) k6_layernorm_fwd_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ y,
                                                                           uint32_t drop_thresh, float drop_scale, uint32_t seed_lo,
-                                                                          uint32_t seed_hi, const float *__restrict__ gamma,
+                                                                          uint32_t seed_hi, const unsigned long long *__restrict__ seed_dev,
+                                                                          const float *__restrict__ gamma,
                                                                           const float *__restrict__ beta, float eps, int N,
                                                                           float *__restrict__ s_out, float *__restrict__ out,
                                                                           __nv_bfloat16 *__restrict__ out16,
                                                                           float *__restrict__ mean, float *__restrict__ rstd) {
     constexpr int D = PER * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    mix_device_seed(seed_dev, seed_lo, seed_hi);
     float g[PER], b[PER];
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
@@ -102,11 +114,13 @@ __global__ void __launch_bounds__(kNormWarps * 32) k6_layernorm_bwd_kernel(const
                                                                           const float *__restrict__ gamma, const float *__restrict__ mean,
                                                                           const float *__restrict__ rstd, int N, uint32_t drop_thresh,
                                                                           float drop_scale, uint32_t seed_lo, uint32_t seed_hi,
+                                                                          const unsigned long long *__restrict__ seed_dev,
                                                                           float *__restrict__ dx, __nv_bfloat16 *__restrict__ dyb_out,
                                                                           float *__restrict__ partial) {
     constexpr int D = PER * 32;
     __shared__ float sred[kNormWarps][2 * D];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    mix_device_seed(seed_dev, seed_lo, seed_hi);
     float g[PER], dg[PER], db[PER];
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
@@ -256,7 +270,7 @@ static uint32_t drop_threshold(float p) {
 
 extern "C" int32_t mobgt_add_dropout_layernorm_fwd(const float *x, const void *y_bf16, float drop_p, uint64_t seed, const float *gamma,
                                                    const float *beta, float eps, int32_t N, int32_t D, float *s_out, float *out,
-                                                   void *out_bf16, float *mean, float *rstd, void *stream) {
+                                                   void *out_bf16, float *mean, float *rstd, const void *seed_dev, void *stream) {
     MOBGT_REQUIRE(x && gamma && beta && (out || out_bf16) && mean && rstd, MOBGT_ERR_NULL, "mobgt_add_dropout_layernorm_fwd: null pointer");
     MOBGT_REQUIRE(D > 0 && D % 32 == 0 && D <= 512, MOBGT_ERR_BAD_SHAPE, "mobgt_add_dropout_layernorm_fwd: D=%d", D);
     MOBGT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, MOBGT_ERR_BAD_SHAPE, "mobgt_add_dropout_layernorm_fwd: p=%f", (double)drop_p);
@@ -267,21 +281,23 @@ extern "C" int32_t mobgt_add_dropout_layernorm_fwd(const float *x, const void *y
     const uint32_t th = y_bf16 ? drop_threshold(drop_p) : 0u;
     const float sc = 1.0f / (1.0f - drop_p);
     MOBGT_NORM_DISPATCH(D / 32, (k6_layernorm_fwd_kernel<P_><<<grid, kNormWarps * 32, 0, s>>>(
-                                    x, static_cast<const __nv_bfloat16 *>(y_bf16), th, sc, (uint32_t)seed, (uint32_t)(seed >> 32), gamma,
-                                    beta, eps, N, s_out, out, static_cast<__nv_bfloat16 *>(out_bf16), mean, rstd)));
+                                    x, static_cast<const __nv_bfloat16 *>(y_bf16), th, sc, (uint32_t)seed, (uint32_t)(seed >> 32),
+                                    static_cast<const unsigned long long *>(seed_dev), gamma, beta, eps, N, s_out, out,
+                                    static_cast<__nv_bfloat16 *>(out_bf16), mean, rstd)));
     MOBGT_LAUNCH_OK("k6_layernorm_fwd_kernel");
     return MOBGT_OK;
 }
 
 extern "C" int32_t mobgt_layernorm_fwd(const float *x, const float *gamma, const float *beta, float eps, int32_t N, int32_t D,
                                        float *out, void *out_bf16, float *mean, float *rstd, void *stream) {
-    return mobgt_add_dropout_layernorm_fwd(x, nullptr, 0.f, 0ull, gamma, beta, eps, N, D, nullptr, out, out_bf16, mean, rstd, stream);
+    return mobgt_add_dropout_layernorm_fwd(x, nullptr, 0.f, 0ull, gamma, beta, eps, N, D, nullptr, out, out_bf16, mean, rstd, nullptr,
+                                           stream);
 }
 
 extern "C" int32_t mobgt_add_dropout_layernorm_bwd(const float *dy, const void *dy_bf16, const float *ds_ext, const float *s_saved,
                                                    const float *gamma, const float *mean, const float *rstd, int32_t N, int32_t D,
                                                    float drop_p, uint64_t seed, float *dx, void *dyb_out, float *dgamma, float *dbeta,
-                                                   void *workspace, int64_t workspace_bytes, void *stream) {
+                                                   void *workspace, int64_t workspace_bytes, const void *seed_dev, void *stream) {
     MOBGT_REQUIRE((dy || dy_bf16) && s_saved && gamma && mean && rstd && dx && dgamma && dbeta && workspace, MOBGT_ERR_NULL,
                   "mobgt_add_dropout_layernorm_bwd: null pointer");
     MOBGT_REQUIRE(D > 0 && D % 32 == 0 && D <= 512, MOBGT_ERR_BAD_SHAPE, "mobgt_add_dropout_layernorm_bwd: D=%d", D);
@@ -293,8 +309,9 @@ extern "C" int32_t mobgt_add_dropout_layernorm_bwd(const float *dy, const void *
     if (grid > 0) {
         MOBGT_NORM_DISPATCH(D / 32, (k6_layernorm_bwd_kernel<P_><<<grid, kNormWarps * 32, 0, s>>>(
                                         dy, static_cast<const __nv_bfloat16 *>(dy_bf16), ds_ext, s_saved, gamma, mean, rstd, N,
-                                        drop_threshold(drop_p), 1.0f / (1.0f - drop_p), (uint32_t)seed, (uint32_t)(seed >> 32), dx,
-                                        static_cast<__nv_bfloat16 *>(dyb_out), partial)));
+                                        drop_threshold(drop_p), 1.0f / (1.0f - drop_p), (uint32_t)seed, (uint32_t)(seed >> 32),
+                                        static_cast<const unsigned long long *>(seed_dev), dx, static_cast<__nv_bfloat16 *>(dyb_out),
+                                        partial)));
         MOBGT_LAUNCH_OK("k6_layernorm_bwd_kernel");
     }
     k6_reduce_parts_kernel<<<ceil_div(2 * D, 32), 256, 0, s>>>(partial, grid, 2 * D, dgamma, D, dbeta);
@@ -306,7 +323,7 @@ extern "C" int32_t mobgt_layernorm_bwd(const float *dy, const void *dy_bf16, con
                                        const float *rstd, int32_t N, int32_t D, float *dx, float *dgamma, float *dbeta, void *workspace,
                                        int64_t workspace_bytes, void *stream) {
     return mobgt_add_dropout_layernorm_bwd(dy, dy_bf16, nullptr, x, gamma, mean, rstd, N, D, 0.f, 0ull, dx, nullptr, dgamma, dbeta,
-                                           workspace, workspace_bytes, stream);
+                                           workspace, workspace_bytes, nullptr, stream);
 }
 
 extern "C" int64_t mobgt_colsum_workspace_bytes(int32_t N, int32_t C) {

@@ -339,6 +339,12 @@ def layer_norm(x, ln, want="f32"):
 
 
 _drop_calls = 0
+_seed_dev = None          # optional u64 device tensor folded into every dropout seed (CUDA-graph replays: graphs.GraphedTrainStep)
+
+
+def set_device_seed(t):
+    global _seed_dev
+    _seed_dev = t
 
 
 def _next_drop_seed():
@@ -367,9 +373,10 @@ class AddDropoutLayerNormFn(torch.autograd.Function):
         g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
         seed = _next_drop_seed() if p > 0 else 0
         _C.call("mobgt_add_dropout_layernorm_fwd", _C.ptr(x), _C.ptr(y), float(p), seed, _C.ptr(g), _C.ptr(b), float(eps), N, D,
-                _C.ptr(s), _C.ptr(out), _C.ptr(out16), _C.ptr(mean), _C.ptr(rstd), _C.stream_ptr())
+                _C.ptr(s), _C.ptr(out), _C.ptr(out16), _C.ptr(mean), _C.ptr(rstd), _C.ptr(_seed_dev), _C.stream_ptr())
         ctx.save_for_backward(s, g, mean, rstd)
         ctx.cfg = (float(p), seed, want, need_s)
+        ctx.seed_dev = _seed_dev
         outs = {"f32": (out,), "bf16": (out16,), "both": (out, out16)}[want]
         return ((s,) + outs) if need_s else outs if len(outs) > 1 else outs[0]
 
@@ -398,7 +405,7 @@ class AddDropoutLayerNormFn(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=s.device)
         _C.call("mobgt_add_dropout_layernorm_bwd", _C.ptr(dy32), _C.ptr(dy16), _C.ptr(ds_ext), _C.ptr(s), _C.ptr(g), _C.ptr(mean),
                 _C.ptr(rstd), N, D, p, seed, _C.ptr(dx), _C.ptr(dyb), _C.ptr(dgamma), _C.ptr(dbeta), _C.ptr(ws), ws_bytes,
-                _C.stream_ptr())
+                _C.ptr(ctx.seed_dev), _C.stream_ptr())
         return dx, dyb, dgamma, dbeta, None, None, None, None
 
 

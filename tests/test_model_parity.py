@@ -100,3 +100,42 @@ def test_metrics_match_reference_semantics(lib_built):
     assert np.allclose(acc, racc) and np.allclose(ndcg, rndcg)
     t2 = torch.randint(0, 500, (64,), generator=g)
     assert abs(metrics.MRR_metric(t2.cuda(), scores.cuda()) - mo.mrr_metric(t2, scores)) < 1e-9
+
+
+@pytest.mark.gpu
+def test_cuda_graph_step_matches_eager(lib_built):
+    """graphs.GraphedTrainStep: replaying the captured forward + backward on a freshly loaded batch gives the same loss and
+    the same gradients as the eager step (eval mode: no dropout, so the comparison is exact up to atomics-free determinism)."""
+    import torch
+    from mobgt_b200 import collator, graphs, model as M, synth
+    world = synth.make_world("tiny", seed=1)
+    dev = torch.device("cuda")
+    torch.manual_seed(3)
+    model = M.Graphormer(dataset_name="toyotagraph", world=world, n_layers=2, num_heads=8, hidden_dim=128, dropout_rate=0.1,
+                         intput_dropout_rate=0.1, weight_decay=0.01, ffn_dim=256, warmup_updates=10, tot_updates=100, peak_lr=2e-4,
+                         end_lr=1e-9, edge_type="multi_hop", multi_hop_max_dist=20, attention_dropout_rate=0.1).to(dev).eval()
+    params = list(model.parameters())
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    latlon = torch.from_numpy(world.latlon).to(dev)
+    mk = lambda seed: collator.collate_packed(synth.make_items(world, 6, 12, seed=seed, cfg_id=2, n_fixed=12), world, latlon, 512, 20, 1024)
+    b0, b1 = mk(1), mk(2)
+    try:
+        g = graphs.GraphedTrainStep(model, flat, b0)
+    except graphs.GraphCaptureError as e:
+        pytest.skip(f"not capturable here: {e}")
+    for b in (b1, mk(1)):
+        g.load(b)
+        loss_g = float(g.run())
+        grad_g = flat.clone()
+        flat.zero_()
+        loss_e = model.training_step(b)
+        loss_e.backward()
+        assert abs(loss_g - float(loss_e)) <= 1e-5 * max(1.0, abs(float(loss_e)))
+        scale = flat.abs().max().item()
+        assert (grad_g - flat).abs().max().item() <= 1e-4 * scale + 1e-7
+    with pytest.raises(graphs.ShapeMismatch):
+        g.load(collator.collate_packed(synth.make_items(world, 6, 12, seed=5, cfg_id=2, n_fixed=9), world, latlon, 512, 20, 1024))
