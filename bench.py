@@ -36,6 +36,15 @@ HP = dict(n_layers=6, num_heads=8, hidden_dim=128, dropout_rate=0.1, intput_drop
           attention_dropout_rate=0.1)      # README.md:62 canonical flags
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -151,7 +160,7 @@ def run_reference(args):
                        "heads": 8, "ffn": 1024, "multi_hop_max_dist": 20, "graphs_per_step": r["sample_graphs"]},
             "cpu_baseline": {"value": r["value"], "unit": "graphs/s", "cores": r["cores"], "kind": "port", "sample": sample},
             "e2e": {"value": r["value"], "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ kernel micro-timing
@@ -340,7 +349,9 @@ def run_ours(args):
     n0 = _C.launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     ms = timed(lambda: train_step(batch), args.steps)
-    launches = (_C.launch_count() - n0) / args.steps
+    launches = (_C.launch_count() - n0) / args.steps        # libmobgt launches issued from the host in the timed region ...
+    if graphed["g"] is not None:
+        launches += graphed["g"].launches                    # ... plus the libmobgt kernel nodes of the graph replayed every step
     # end to end: host items -> collate (H2D + K1) -> step -> loss on the host, every step
     losses = []
 
@@ -414,7 +425,7 @@ def run_ours(args):
                                     "sample": f"{r['sample_graphs']} graphs/step of the same batch, 4 timed steps after 1 warm-up; "
                                               f"compiled algos.pyx (oracle/_ref) when present + CPU restatement of "
                                               f"collator/model_fqandtoyo (fwd+bwd+AdamW), {r['cores']} torch threads"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world_size > 1:
         dist.destroy_process_group()
 
@@ -433,6 +444,12 @@ def main():
     ap.add_argument("--no-kernel-report", action="store_true")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
+    # stdout carries exactly ONE JSON line: everything libraries print to fd 1 meanwhile (the NCCL version banner, ...) goes to
+    # stderr; the line is written to the saved descriptor at the end
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

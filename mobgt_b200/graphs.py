@@ -17,7 +17,7 @@ capturable this way and run eagerly.
 """
 import torch
 
-from . import ops
+from . import _C, ops
 
 
 class GraphCaptureError(RuntimeError):
@@ -57,8 +57,10 @@ class GraphedTrainStep:
             torch.cuda.synchronize()
             if hasattr(model, "_w16"):
                 model._w16.stamp = None          # the bf16 re-cast of the weights must be part of the captured work
+            n0 = _C.launch_count()
             with torch.cuda.graph(self.graph):
                 self.loss = self._body()
+            self.launches = _C.launch_count() - n0       # libmobgt kernel nodes in the graph = launches per replay
             torch.cuda.synchronize()
         except Exception as e:                   # noqa: BLE001 — anything that is illegal during capture: report, let the caller fall back
             ops.set_device_seed(None)

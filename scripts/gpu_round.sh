@@ -23,7 +23,7 @@ if [[ $ST == *k* ]]; then
 fi
 if [[ $ST == *l* ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $O/launches.csv \
-      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-kernel-report > $O/launches.log 2>&1; echo "ncu launches rc=$?"
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-kernel-report --no-cuda-graph --loader-workers 0 > $O/launches.log 2>&1; echo "ncu launches rc=$?"
 fi
 if [[ $ST == *n* ]]; then
   for spec in "k2_bias_fwd_kernel:k2_fwd" "k2_bias_bwd_kernel:k2_bwd" "k3_attn_fwd:k3_fwd" "k3_attn_bwd:k3_bwd" "k1_apsp_kernel:k1" \
