@@ -113,7 +113,9 @@ def cpu_reference_rate(workload, steps, warmup, sample=None, verbose=False):
     sample = sample or 4
     items = make_workload(workload, world, sample, 0)
     torch.manual_seed(1)
-    model = mo.Graphormer(world, n_layers=HP["n_layers"], ffn_dim=HP["ffn_dim"]).train()
+    model = mo.Graphormer(world, n_layers=HP["n_layers"], ffn_dim=HP["ffn_dim"], dropout_rate=HP["dropout_rate"],
+                          intput_dropout_rate=HP["intput_dropout_rate"], attention_dropout_rate=HP["attention_dropout_rate"],
+                          pos_dropout=0.1).train()
     opt = torch.optim.AdamW(model.parameters(), lr=HP["peak_lr"], weight_decay=HP["weight_decay"])
 
     def preprocess(it):
@@ -194,7 +196,8 @@ def kernel_report(model, batch, pk, iters=8, head_c5=True):
                                                        model.graph_token_virtual_distance.weight.view(-1))]
     bias = ops.bias_fwd_raw(batch, *tabs)
     qkv = torch.randn(ntok, 576, device=dev).to(torch.bfloat16)
-    out, lse = ops.attn_fwd_raw(qkv, bias, batch)
+    dp, ds = HP["attention_dropout_rate"], 0x5DEECE66D1234567      # K3 is timed as the training step runs it: dropout on
+    out, lse = ops.attn_fwd_raw(qkv, bias, batch, drop_p=dp, seed=ds)
     dout = torch.randn(ntok, 192, device=dev).to(torch.bfloat16)
     n_layers = len(model.layers)
     planes = torch.zeros((n_layers,) + tuple(bias.shape), dtype=torch.bfloat16, device=dev)   # per-layer dS planes (bf16)
@@ -213,8 +216,8 @@ def kernel_report(model, batch, pk, iters=8, head_c5=True):
     add("k2_bias_bwd", tk(lambda: ops.bias_bwd_raw(batch, planes, tabs[2], tabs[3], tabs[1].shape[0])),
         cells * (4 + hops) + n_layers * H * pairs_t * 2, 1)
     fl = 4.0 * H * pairs_t * 24
-    add("k3_attn_fwd", tk(lambda: ops.attn_fwd_raw(qkv, bias, batch)), 4 * ntok * 192 * 2 + H * pairs_t * 2, 6, fl)
-    add("k3_attn_bwd", tk(lambda: ops.attn_bwd_raw(qkv, bias, out, dout, lse, batch, planes[0], 2)),
+    add("k3_attn_fwd", tk(lambda: ops.attn_fwd_raw(qkv, bias, batch, drop_p=dp, seed=ds)), 4 * ntok * 192 * 2 + H * pairs_t * 2, 6, fl)
+    add("k3_attn_bwd", tk(lambda: ops.attn_bwd_raw(qkv, bias, out, dout, lse, batch, planes[0], 2, drop_p=dp, seed=ds)),
         8 * ntok * 192 * 2 + H * pairs_t * 2 + H * pairs_t * 2, 6, 2.5 * fl)
     Gd, Gc = model.gcn_tables()
     Gd, Gc = Gd.detach(), Gc.detach()

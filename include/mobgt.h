@@ -132,10 +132,15 @@ int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const int16_t *r
  * graph g owns token rows tok_off[g]..tok_off[g+1] (row 0 = graph token).  head dim is 24.
  *   q,k,v  bf16 [ntok, H*24] with a common row stride (elements) — usually slices of one fused projection
  *   bias   bf16 [B,H,T,Tp] from mobgt_bias_fwd ;  out bf16 [ntok, H*24] ;  lse f32 [ntok, H]
+ *   drop_p, seed, seed_dev: the attention dropout of model_fqandtoyo.py:1704 (`x = self.att_dropout(x)` on the softmax
+ *          probabilities; training only — pass drop_p = 0 in eval).  The keep mask is a counter-based hash of
+ *          (seed, plane, row, column), regenerated by the backward from the SAME seed: nothing is stored.  seed_dev (u64 in
+ *          device memory, optional) is folded into the seed at run time (CUDA-graph replays draw fresh masks).
  * ------------------------------------------------------------------------------------------ */
 int32_t mobgt_attn_fwd(const void *q, const void *k, const void *v, int64_t qkv_row_stride, const void *bias,
                        const int32_t *tok_off, int32_t B, int32_t H, int32_t ntok, int32_t T, int32_t Tp,
-                       int32_t t_max_host, float scale, void *out, float *lse, void *stream);
+                       int32_t t_max_host, float scale, float drop_p, uint64_t seed, const void *seed_dev, void *out,
+                       float *lse, void *stream);
 
 /* Backward of mobgt_attn_fwd.  o, dout: bf16 [ntok, H*24] contiguous; lse from the forward.
  * dq, dk, dv: bf16 with a common row stride (usually slices of one [ntok, 3*H*24] buffer).
@@ -148,7 +153,8 @@ int32_t mobgt_attn_fwd(const void *q, const void *k, const void *v, int64_t qkv_
 int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, int64_t qkv_row_stride, const void *bias,
                        const void *o, const void *dout, const float *lse, const int32_t *tok_off, int32_t B,
                        int32_t H, int32_t ntok, int32_t T, int32_t Tp, int32_t t_max_host, float scale, void *dq,
-                       void *dk, void *dv, int64_t dqkv_row_stride, void *dbias, int32_t mode, void *stream);
+                       void *dk, void *dv, int64_t dqkv_row_stride, void *dbias, int32_t mode, float drop_p, uint64_t seed,
+                       const void *seed_dev, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4 — node-embedding gather / sum and the deterministic segmented scatter-add backward.

@@ -72,10 +72,14 @@ class PackedLoader:
       * num_workers > 0: the numpy packing (`pack_host`) runs in DataLoader worker processes which hand over ONE byte buffer
         per batch through shared memory; the calling thread copies it into the pinned staging buffer and issues the H2D copy
         and the collation kernels (`collate_from_host`).
+    side_stream=True (default): the H2D copy and the collation kernels (K1, poi_pos, the K4 sort plans) of batch i+1 are issued
+    on a second CUDA stream, so they run concurrently with the kernels of training step i instead of queueing behind them;
+    `current()` makes the consumer's stream wait for the batch (event) and registers the batch's memory with that stream.
     """
 
-    def __init__(self, batches, collate_fn=None, num_workers=0, max_node=512, **collate_kw):
+    def __init__(self, batches, collate_fn=None, num_workers=0, max_node=512, side_stream=True, **collate_kw):
         self._kw = collate_kw
+        self._stream = torch.cuda.Stream() if (side_stream and torch.cuda.is_available()) else None
         if num_workers > 0:
             ds = _PackStream(batches, max_node)
             dl = torch.utils.data.DataLoader(ds, batch_size=None, num_workers=num_workers, pin_memory=False, prefetch_factor=2,
@@ -89,12 +93,27 @@ class PackedLoader:
 
     def _pull(self):
         try:
-            return self._collate(next(self._it))
+            nxt = next(self._it)
         except StopIteration:
             return None
+        if self._stream is None:
+            return self._collate(nxt)
+        with torch.cuda.stream(self._stream):
+            b = self._collate(nxt)
+            ev = torch.cuda.Event()
+            ev.record(self._stream)
+        b.__dict__["_ready"] = ev
+        return b
 
     def current(self):
-        return self._next
+        b = self._next
+        ev = b.__dict__.pop("_ready", None) if b is not None else None
+        if ev is not None:
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            for t in _batch_tensors(b):          # allocated on the side stream, consumed on this one
+                t.record_stream(cur)
+        return b
 
     def advance(self):
         """Collate the following batch (call it right after the step's kernels have been enqueued)."""
@@ -106,6 +125,23 @@ class PackedLoader:
             yield b
             if self._next is b:       # the consumer did not call advance() itself
                 self.advance()
+
+
+def _batch_tensors(b):
+    """Every device tensor a Batch1 owns (fields and K4 sort plans)."""
+    def walk(v):
+        if isinstance(v, torch.Tensor):
+            if v.is_cuda:
+                yield v
+        elif isinstance(v, (tuple, list)):
+            for x in v:
+                yield from walk(x)
+        elif isinstance(v, dict):
+            for x in v.values():
+                yield from walk(x)
+    for k, v in b.__dict__.items():
+        if k != "_dense":
+            yield from walk(v)
 
 
 class Batch1:

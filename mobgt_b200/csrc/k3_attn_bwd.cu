@@ -46,6 +46,7 @@ struct AttnBwdParams {
     int accumulate;            // 0: f32 overwrite, 1: f32 dbias += dS, 2: bf16 overwrite (per-layer plane, TMA store)
     int bias_bufs;             // 1 or 2 bias tiles in shared memory
     long long *timeline;       // debug (mobgt_debug_set_timeline) or NULL
+    AttnDrop drop;             // the forward's attention dropout (same seed): th16 == 0 when it was off
 };
 
 __device__ __forceinline__ float bwd_exp2(float x) {
@@ -65,6 +66,9 @@ __device__ __forceinline__ void red_add_f32x4(float *addr, float a, float b, flo
 // w+4 may both access lanes 32*(w%4)..+31) and the 16-column chunks c0 = 16*wg, 16*wg + 32, ... of the score tile.
 // Q / dO (and, when it fits, the bias tile) are double-buffered: the TMA loads of iteration t+1 are issued before the
 // S / dP MMAs of iteration t, so their latency hides behind the softmax-gradient math.
+// kDrop (training-mode attention dropout, forward: O = (M o P / (1-p)) V with keep mask M regenerated here):
+//   dV = (M o P / (1-p))^T dO ;  dP = M o (dO V^T) / (1-p) ;  dS = P o (dP - D) ;  D = rowsum(dO o O) still holds.
+template <bool kDrop>
 __global__ void __launch_bounds__(256, 1)
 k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -208,6 +212,8 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float sl2 = p.scale * 1.4426950408889634f;
     constexpr float kL2e = 1.4426950408889634f;
     bool mma_pending = false;
+    uint32_t seed_lo = 0, seed_hi = 0;
+    if (kDrop) attn_drop_fold_seed(p.drop, seed_lo, seed_hi);
 
     for (int j = 0; j < NB; ++j) {
         const int kv_valid = min(kTile, Tg - j * kTile);
@@ -244,6 +250,8 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 const uint8_t *sB = sBias + (size_t)bb * kBiasTileBytes;
                 const float lse2 = sLse[row];
                 const float delta = sDelta[row];
+                const uint32_t rowkey = kDrop ? attn_drop_rowkey((uint32_t)plane, (uint32_t)row, seed_lo, seed_hi) : 0u;
+                const float ik = p.drop.inv_keep;
                 float *db_row = p.dbias + ((size_t)plane * p.T + row) * p.Tp + j * kTile;
                 uint32_t svv[4][16], dpvv[4][16];
 #pragma unroll
@@ -269,6 +277,7 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         const uint32_t bw[4] = {bvv.x, bvv.y, bvv.z, bvv.w};
                         float dsv[8];
                         uint4 pk, dk;
+                        const uint32_t keep = kDrop ? attn_drop_keep8(rowkey, (uint32_t)(j * (kTile / 8) + c8), p.drop.th16) : 0xFFu;
                         if (colb + 8 <= kv_valid) {   // all 8 key columns valid: no per-element masking
                             float pv[8];
 #pragma unroll
@@ -276,7 +285,13 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                                 const float bias = __uint_as_float((e & 1) ? (bw[e >> 1] & 0xFFFF0000u) : (bw[e >> 1] << 16));
                                 const float s = fmaf(__uint_as_float(sv[q8 * 8 + e]), sl2, bias * kL2e);
                                 pv[e] = bwd_exp2(s - lse2);
-                                dsv[e] = pv[e] * (__uint_as_float(dpv[q8 * 8 + e]) - delta);
+                                if (kDrop) {
+                                    const bool kp = (keep >> e) & 1u;
+                                    dsv[e] = pv[e] * ((kp ? __uint_as_float(dpv[q8 * 8 + e]) * ik : 0.f) - delta);
+                                    pv[e] = kp ? pv[e] * ik : 0.f;      // the dV operand is the dropped-out P
+                                } else {
+                                    dsv[e] = pv[e] * (__uint_as_float(dpv[q8 * 8 + e]) - delta);
+                                }
                             }
                             pk.x = pack_bf16(pv[0], pv[1]); pk.y = pack_bf16(pv[2], pv[3]);
                             pk.z = pack_bf16(pv[4], pv[5]); pk.w = pack_bf16(pv[6], pv[7]);
@@ -298,7 +313,13 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                                 const float bias = __uint_as_float((e & 1) ? (bw[e >> 1] & 0xFFFF0000u) : (bw[e >> 1] << 16));
                                 const float s = fmaf(__uint_as_float(sv[q8 * 8 + e]), sl2, bias * kL2e);
                                 pv[e] = ok ? bwd_exp2(s - lse2) : 0.f;
-                                dsv[e] = ok ? pv[e] * (__uint_as_float(dpv[q8 * 8 + e]) - delta) : 0.f;
+                                if (kDrop) {
+                                    const bool kp = (keep >> e) & 1u;
+                                    dsv[e] = ok ? pv[e] * ((kp ? __uint_as_float(dpv[q8 * 8 + e]) * ik : 0.f) - delta) : 0.f;
+                                    pv[e] = kp ? pv[e] * ik : 0.f;
+                                } else {
+                                    dsv[e] = ok ? pv[e] * (__uint_as_float(dpv[q8 * 8 + e]) - delta) : 0.f;
+                                }
                             }
                             pk.x = pack_bf16(pv[0], pv[1]); pk.y = pack_bf16(pv[2], pv[3]);
                             pk.z = pack_bf16(pv[4], pv[5]); pk.w = pack_bf16(pv[6], pv[7]);
@@ -417,7 +438,8 @@ using namespace mobgt;
 extern "C" int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, int64_t qkv_row_stride, const void *bias,
                                   const void *o, const void *dout, const float *lse, const int32_t *tok_off, int32_t B,
                                   int32_t H, int32_t ntok, int32_t T, int32_t Tp, int32_t t_max_host, float scale, void *dq,
-                                  void *dk, void *dv, int64_t dqkv_row_stride, void *dbias, int32_t accumulate, void *stream) {
+                                  void *dk, void *dv, int64_t dqkv_row_stride, void *dbias, int32_t accumulate, float drop_p,
+                                  uint64_t seed, const void *seed_dev, void *stream) {
     MOBGT_REQUIRE(q && k && v && bias && o && dout && lse && tok_off && dq && dk && dv && dbias, MOBGT_ERR_NULL,
                   "mobgt_attn_bwd: null pointer");
     MOBGT_REQUIRE(qkv_row_stride % 8 == 0 && dqkv_row_stride % 8 == 0 && Tp % 8 == 0 && Tp >= T, MOBGT_ERR_BAD_SHAPE,
@@ -454,7 +476,10 @@ extern "C" int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, i
     const size_t smem_base = 2 * kPBytes + 4 * kBoxBytes + (size_t)2 * max_boxes * kBoxBytes + 1024;
     const int bias_bufs = (smem_base + 2 * kBiasTileBytes <= 220 * 1024) ? 2 : 1;
     const size_t smem = smem_base + (size_t)bias_bufs * kBiasTileBytes;
-    MOBGT_CUDA_OK(cudaFuncSetAttribute(k3_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MOBGT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, MOBGT_ERR_BAD_SHAPE, "mobgt_attn_bwd: drop_p=%f must be in [0, 1)", drop_p);
+    const AttnDrop drop = make_attn_drop(drop_p, seed, seed_dev);
+    auto kern = drop.th16 ? k3_attn_bwd_kernel<true> : k3_attn_bwd_kernel<false>;
+    MOBGT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AttnBwdParams p{tok_off,
                     static_cast<const __nv_bfloat16 *>(o),
                     static_cast<const __nv_bfloat16 *>(dout),
@@ -471,8 +496,9 @@ extern "C" int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, i
                     max_boxes,
                     accumulate,
                     bias_bufs,
-                    g_timeline_dev};
-    k3_attn_bwd_kernel<<<B * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmdO, tmB, tmDS, p);
+                    g_timeline_dev,
+                    drop};
+    kern<<<B * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmdO, tmB, tmDS, p);
     MOBGT_LAUNCH_OK("k3_attn_bwd_kernel");
     return MOBGT_OK;
 }

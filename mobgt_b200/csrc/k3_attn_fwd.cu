@@ -36,6 +36,7 @@ struct AttnFwdParams {
     float scale;
     int max_boxes;           // ceil(Tmax / 128): K/V boxes provisioned in shared memory
     long long *timeline;     // debug (mobgt_debug_set_timeline) or NULL
+    AttnDrop drop;           // attention dropout on P (model_fqandtoyo.py:1704); th16 == 0 in eval
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -50,6 +51,9 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // The row max is exchanged between the warpgroups through shared memory; the row sums are combined once per query tile.
 // After the max pass nobody needs the bias tile any more, so the next tile's TMA load is issued there and overlaps the
 // exp pass and the P.V MMA.
+// kDrop: training-mode attention dropout — the row sum (softmax denominator) is taken BEFORE the mask, the bf16 P tile that
+// feeds the P.V MMA holds only the kept probabilities, and 1 / (1 - p) is folded into the final 1 / l normalisation.
+template <bool kDrop>
 __global__ void __launch_bounds__(256, 2)
 k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmBias,
@@ -146,9 +150,12 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncwarp();
     const float sl2 = p.scale * 1.4426950408889634f;  // scale * log2(e)
     constexpr float kL2e = 1.4426950408889634f;
+    uint32_t seed_lo = 0, seed_hi = 0;
+    if (kDrop) attn_drop_fold_seed(p.drop, seed_lo, seed_hi);
 
     for (int i = 0; i < NB; ++i) {
         const int row = i * kTile + t128;      // query row inside the graph
+        const uint32_t rowkey = kDrop ? attn_drop_rowkey((uint32_t)plane, (uint32_t)row, seed_lo, seed_hi) : 0u;
         const bool row_ok = row < Tg;
         const bool warp_live = i * kTile + (warp & 3) * 32 < Tg;   // any valid query row in this warp's 32 lanes?
         float m_run = -INFINITY, l_run = 0.f;  // running max (log2 units of the scaled score); this warpgroup's share of the sum
@@ -237,6 +244,11 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                                 pv[e] = fast_exp2(__uint_as_float(sv[cc][q8 * 8 + e]) - m_use);
                                 l_blk += pv[e];     // row sum in fp32 (P is rounded to bf16 only for the tensor-core operand)
                             }
+                            if (kDrop) {
+                                const uint32_t keep = attn_drop_keep8(rowkey, (uint32_t)(j * (kTile / 8) + c8), p.drop.th16);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) pv[e] = ((keep >> e) & 1u) ? pv[e] : 0.f;
+                            }
                             uint4 pk;
                             pk.x = pack_bf16(pv[0], pv[1]);
                             pk.y = pack_bf16(pv[2], pv[3]);
@@ -287,7 +299,7 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             tmem_ld_wait();
             if (row_ok) {
                 const float l_tot = sMax[0][t128] + sMax[1][t128];
-                const float inv = 1.0f / l_tot;
+                const float inv = (kDrop ? p.drop.inv_keep : 1.0f) / l_tot;
                 uint32_t w[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e)
@@ -320,13 +332,15 @@ using namespace mobgt;
 // [ntok, 3*H*24] projection.  bias: bf16 [B, H, T, Tp].  out: bf16 [ntok, H*24] (contiguous).  lse: f32 [ntok, H].
 extern "C" int32_t mobgt_attn_fwd(const void *q, const void *k, const void *v, int64_t qkv_row_stride, const void *bias,
                                   const int32_t *tok_off, int32_t B, int32_t H, int32_t ntok, int32_t T, int32_t Tp,
-                                  int32_t t_max_host, float scale, void *out, float *lse, void *stream) {
+                                  int32_t t_max_host, float scale, float drop_p, uint64_t seed, const void *seed_dev,
+                                  void *out, float *lse, void *stream) {
     MOBGT_REQUIRE(q && k && v && bias && tok_off && out && lse, MOBGT_ERR_NULL, "mobgt_attn_fwd: null pointer");
     MOBGT_REQUIRE(H >= 1 && B >= 0 && ntok >= 0, MOBGT_ERR_BAD_SHAPE, "mobgt_attn_fwd: B=%d H=%d ntok=%d", B, H, ntok);
     MOBGT_REQUIRE(qkv_row_stride % 8 == 0 && Tp % 8 == 0 && Tp >= T, MOBGT_ERR_BAD_SHAPE,
                   "mobgt_attn_fwd: row stride %lld and Tp=%d must be multiples of 8", (long long)qkv_row_stride, Tp);
     MOBGT_REQUIRE(t_max_host >= 1 && t_max_host <= T && T <= MOBGT_MAX_NODES + 1, MOBGT_ERR_BAD_SHAPE,
                   "mobgt_attn_fwd: t_max=%d T=%d", t_max_host, T);
+    MOBGT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, MOBGT_ERR_BAD_SHAPE, "mobgt_attn_fwd: drop_p=%f must be in [0, 1)", drop_p);
     if (B == 0 || ntok == 0) return MOBGT_OK;
     CUtensorMap tmQ, tmK, tmV, tmB;
     const void *ptrs[3] = {q, k, v};
@@ -347,9 +361,11 @@ extern "C" int32_t mobgt_attn_fwd(const void *q, const void *k, const void *v, i
     }
     const int max_boxes = ceil_div(t_max_host, kTile);
     const size_t smem = (size_t)kBiasTileBytes + kPBytes + kBoxBytes + (size_t)2 * max_boxes * kBoxBytes + 1024;
-    MOBGT_CUDA_OK(cudaFuncSetAttribute(k3_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AttnFwdParams p{tok_off, static_cast<__nv_bfloat16 *>(out), lse, H, scale, max_boxes, g_timeline_dev};
-    k3_attn_fwd_kernel<<<B * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmB, p);
+    AttnFwdParams p{tok_off, static_cast<__nv_bfloat16 *>(out), lse, H, scale, max_boxes, g_timeline_dev,
+                    make_attn_drop(drop_p, seed, seed_dev)};
+    auto kern = p.drop.th16 ? k3_attn_fwd_kernel<true> : k3_attn_fwd_kernel<false>;
+    MOBGT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmB, p);
     MOBGT_LAUNCH_OK("k3_attn_fwd_kernel");
     return MOBGT_OK;
 }

@@ -149,7 +149,7 @@ class MultiHeadAttention(nn.Module):
             bq = torch.cat([q.bias, k.bias, v.bias], 0).detach().to(torch.bfloat16)
             wo = bo = None
         qkv = ops.LinearBiasFn.apply(x16, wq, bq, q.weight, k.weight, v.weight, q.bias, k.bias, v.bias)
-        a = ops.BiasedAttention.apply(qkv, bias_slot, layer)
+        a = ops.BiasedAttention.apply(qkv, bias_slot, layer, self.attention_dropout_rate if self.training else 0.0)   # :1704
         return ops.linear_bf16(a, self.output_layer, wo, bo)
 
 
@@ -191,8 +191,13 @@ def gradient_tail_loss(inputs, targets, alpha=0.25, beta=1, k=1):
 class Graphormer(nn.Module):
     def __init__(self, n_layers, num_heads, hidden_dim, dropout_rate, intput_dropout_rate, weight_decay, ffn_dim,
                  dataset_name, warmup_updates, tot_updates, peak_lr, end_lr, edge_type, multi_hop_max_dist,
-                 attention_dropout_rate, flag=False, flag_m=3, flag_step_size=1e-3, flag_mag=1e-3, lr_step=2, world=None):
+                 attention_dropout_rate, flag=False, flag_m=3, flag_step_size=1e-3, flag_mag=1e-3, lr_step=2, world=None,
+                 tf32=True):
+        """tf32: run the GEMMs that stay in fp32 storage (GCN dense parts modelGNN.py:39, user fuse, cat_decoder, out_proj) on
+        the TF32 tensor cores instead of SIMT FFMA.  The reference runs them in fp16 under `--precision 16` autocast
+        (README.md:62), so TF32 (10-bit mantissa, fp32 range and accumulate) is at least as precise; tf32=False keeps IEEE fp32."""
         super().__init__()
+        self.tf32 = bool(tf32)
         if world is None:
             raise ValueError("Graphormer needs a PoiWorld (the dataset tables the reference reads from ../dataset/<name>/raw, "
                              "model_fqandtoyo.py:791-832)")
@@ -292,6 +297,8 @@ class Graphormer(nn.Module):
 
     def forward(self, batched_data, perturb=None):
         b = batched_data
+        if self.tf32 and not torch.backends.cuda.matmul.allow_tf32:
+            torch.backends.cuda.matmul.allow_tf32 = True       # process-wide cuBLAS switch (also seen by the autograd threads)
         if not hasattr(b, "rel_pos16"):
             raise TypeError("Graphormer.forward expects a mobgt_b200.collator.Batch1 (packed); build it with "
                             "mobgt_b200.collator.collator_* or Batch1-from-dense")

@@ -91,8 +91,9 @@ class AttnBias(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------- K3
-def attn_fwd_raw(qkv, bias, batch, scale=None):
-    """qkv bf16 [ntok, 3*H*24] (fused projection) ; bias bf16 [B,H,T,Tp] -> (out bf16 [ntok, H*24], lse f32 [ntok,H])"""
+def attn_fwd_raw(qkv, bias, batch, scale=None, drop_p=0.0, seed=0):
+    """qkv bf16 [ntok, 3*H*24] (fused projection) ; bias bf16 [B,H,T,Tp] -> (out bf16 [ntok, H*24], lse f32 [ntok,H]).
+    drop_p > 0: attention dropout on the probabilities (model_fqandtoyo.py:1704), mask = hash(seed, plane, row, col)."""
     ntok = qkv.shape[0]
     B, H, T, Tp = bias.shape
     D = H * HEAD_DIM
@@ -102,11 +103,12 @@ def attn_fwd_raw(qkv, bias, batch, scale=None):
     scale = float(HEAD_DIM ** -0.5) if scale is None else float(scale)
     base = qkv.data_ptr()
     _C.call("mobgt_attn_fwd", base, base + 2 * D, base + 4 * D, 3 * D, _C.ptr(bias), _C.ptr(batch.tok_off), B, H, ntok, T, Tp,
-            int(batch.N) + 1, scale, _C.ptr(out), _C.ptr(lse), _C.stream_ptr())
+            int(batch.N) + 1, scale, float(drop_p), int(seed), _C.ptr(_seed_dev) if drop_p > 0 else None, _C.ptr(out), _C.ptr(lse),
+            _C.stream_ptr())
     return out, lse
 
 
-def attn_bwd_raw(qkv, bias, out, dout, lse, batch, dbias, accumulate, scale=None):
+def attn_bwd_raw(qkv, bias, out, dout, lse, batch, dbias, accumulate, scale=None, drop_p=0.0, seed=0):
     """-> dqkv bf16 [ntok, 3*H*24]; dbias [B,H,T,Tp] is written in place: f32 overwritten (accumulate=0) / added to
     (accumulate=1), or bf16 overwritten (accumulate=2: this layer's own dS plane, TMA-stored)."""
     ntok = qkv.shape[0]
@@ -119,7 +121,7 @@ def attn_bwd_raw(qkv, bias, out, dout, lse, batch, dbias, accumulate, scale=None
     base, dbase = qkv.data_ptr(), dqkv.data_ptr()
     _C.call("mobgt_attn_bwd", base, base + 2 * D, base + 4 * D, 3 * D, _C.ptr(bias), _C.ptr(out), _C.ptr(dout), _C.ptr(lse),
             _C.ptr(batch.tok_off), B, H, ntok, T, Tp, int(batch.N) + 1, scale, dbase, dbase + 2 * D, dbase + 4 * D, 3 * D,
-            _C.ptr(dbias), int(accumulate), _C.stream_ptr())
+            _C.ptr(dbias), int(accumulate), float(drop_p), int(seed), _C.ptr(_seed_dev) if drop_p > 0 else None, _C.stream_ptr())
     return dqkv
 
 
@@ -131,10 +133,12 @@ class BiasedAttention(torch.autograd.Function):
     w.r.t. `bias` is delivered once, by BiasGradSink below, and the planes are summed in fp32 by mobgt_bias_bwd."""
 
     @staticmethod
-    def forward(ctx, qkv, bias_slot, layer):
-        out, lse = attn_fwd_raw(qkv, bias_slot.bias, bias_slot.batch)
+    def forward(ctx, qkv, bias_slot, layer, drop_p=0.0):
+        """drop_p: the attention dropout rate when training (`att_dropout`, model_fqandtoyo.py:1674, 1704), else 0."""
+        seed = _next_drop_seed() if drop_p > 0 else 0
+        out, lse = attn_fwd_raw(qkv, bias_slot.bias, bias_slot.batch, drop_p=drop_p, seed=seed)
         ctx.save_for_backward(qkv, out, lse)
-        ctx.slot, ctx.layer = bias_slot, layer
+        ctx.slot, ctx.layer, ctx.drop = bias_slot, layer, (drop_p, seed)
         return out
 
     @staticmethod
@@ -144,9 +148,10 @@ class BiasedAttention(torch.autograd.Function):
         if slot.planes is None:
             slot.planes = torch.empty((slot.n_layers,) + tuple(slot.bias.shape), dtype=torch.bfloat16, device=qkv.device)
             slot.written = set()
-        dqkv = attn_bwd_raw(qkv, slot.bias, out, dout.contiguous(), lse, slot.batch, slot.planes[ctx.layer], 2)
+        dqkv = attn_bwd_raw(qkv, slot.bias, out, dout.contiguous(), lse, slot.batch, slot.planes[ctx.layer], 2,
+                            drop_p=ctx.drop[0], seed=ctx.drop[1])
         slot.written.add(ctx.layer)
-        return dqkv, None, None
+        return dqkv, None, None, None
 
 
 class BiasSlot:

@@ -221,7 +221,7 @@ class UserEmbeddings(nn.Module):
 
 
 class LearnablePositionalEncoding(nn.Module):
-    """:330-358 (dropout omitted: parity is defined with dropout off)"""
+    """:330-358 (its Dropout(0.1), :358, is applied by Graphormer.forward below when `pos_dropout` > 0)"""
 
     def __init__(self, d_model, max_len):
         super().__init__()
@@ -244,8 +244,9 @@ class FeedForwardNetwork(nn.Module):
 class MultiHeadAttention(nn.Module):
     """:1659-1711"""
 
-    def __init__(self, hidden, heads):
+    def __init__(self, hidden, heads, attention_dropout_rate=0.0):
         super().__init__()
+        self.att_dropout = nn.Dropout(attention_dropout_rate)                                 # :1674
         self.num_heads = heads
         self.att_size = hidden // heads
         self.scale = self.att_size ** -0.5
@@ -260,7 +261,7 @@ class MultiHeadAttention(nn.Module):
         k = self.linear_k(k).view(b, -1, self.num_heads, d).transpose(1, 2).transpose(2, 3)
         v = self.linear_v(v).view(b, -1, self.num_heads, d).transpose(1, 2)
         x = torch.matmul(q * self.scale, k) + attn_bias
-        x = torch.softmax(x, dim=3).matmul(v)
+        x = self.att_dropout(torch.softmax(x, dim=3)).matmul(v)                               # :1703-1705
         x = x.transpose(1, 2).contiguous().view(b, -1, self.num_heads * d)
         return self.output_layer(x)
 
@@ -268,17 +269,19 @@ class MultiHeadAttention(nn.Module):
 class EncoderLayer(nn.Module):
     """:1714-1743 — post-LN variant of the live model (self_attention_norm exists but is unused)"""
 
-    def __init__(self, hidden, ffn, heads):
+    def __init__(self, hidden, ffn, heads, dropout_rate=0.0, attention_dropout_rate=0.0):
         super().__init__()
         self.self_attention_norm = nn.LayerNorm(hidden)
-        self.self_attention = MultiHeadAttention(hidden, heads)
+        self.self_attention = MultiHeadAttention(hidden, heads, attention_dropout_rate)
+        self.self_attention_dropout = nn.Dropout(dropout_rate)                                # :1724
+        self.ffn_dropout = nn.Dropout(dropout_rate)                                           # :1729
         self.ffn_norm1 = nn.LayerNorm(hidden)
         self.ffn_norm2 = nn.LayerNorm(hidden)
         self.ffn = FeedForwardNetwork(hidden, ffn)
 
     def forward(self, x, attn_bias):
-        x = x + self.self_attention(x, x, x, attn_bias)
-        x = x + self.ffn(self.ffn_norm1(x))
+        x = x + self.self_attention_dropout(self.self_attention(x, x, x, attn_bias))          # :1731-1735
+        x = x + self.ffn_dropout(self.ffn(self.ffn_norm1(x)))                                 # :1737-1741
         return self.ffn_norm2(x)
 
 
@@ -306,8 +309,13 @@ class Graphormer(nn.Module):
     """model_fqandtoyo.py:580-1121 (__init__) and :1123-1432 (forward), POI dataset branches."""
 
     def __init__(self, world, n_layers=6, num_heads=8, hidden_dim=128, ffn_dim=1024, multi_hop_max_dist=20,
-                 dataset_name=None):
+                 dataset_name=None, dropout_rate=0.0, intput_dropout_rate=0.0, attention_dropout_rate=0.0, pos_dropout=0.0):
+        """All dropout rates default to 0: parity is defined with dropout off.  The timed CPU arm (bench.py) passes the
+        canonical rates (README.md:62 flags; LearnablePositionalEncoding's own Dropout(0.1), :334) so it does the same work."""
         super().__init__()
+        self.input_dropout = nn.Dropout(intput_dropout_rate)                                  # :1041
+        self.output_dropout = nn.Dropout(intput_dropout_rate)                                 # :770, :892, :1021 (same rate)
+        self.pos_dropout = nn.Dropout(pos_dropout)                                            # :334, applied :358
         self.dataset_name = dataset_name or world.dataset_name
         tr = DATASET_TRAITS[self.dataset_name]
         self.traits = tr
@@ -331,7 +339,7 @@ class Graphormer(nn.Module):
         self.out_degree_encoder = nn.Embedding(128, D, padding_idx=0)
         self.fre_embed_model = nn.Embedding(int(world.check_freq.max()) + 1, D, padding_idx=0)
         self.poi_pos_encoder = nn.Embedding(world.num_bins, H, padding_idx=0)
-        self.layers = nn.ModuleList([EncoderLayer(D, ffn_dim, H) for _ in range(n_layers)])
+        self.layers = nn.ModuleList([EncoderLayer(D, ffn_dim, H, dropout_rate, attention_dropout_rate) for _ in range(n_layers)])
         self.final_ln = nn.LayerNorm(2 * hidden_dim + 64)
         self.out_proj = nn.Linear(2 * hidden_dim + 64, P + tr["poi_extra"])
         self.graph_token = nn.Embedding(1, D)
@@ -417,6 +425,7 @@ class Graphormer(nn.Module):
         h, cat_target = self.node_features(b, looped)
         self.cat_target = cat_target
         h0 = h
+        h = self.input_dropout(self.pos_dropout(h))                                           # :358, :1347
         for layer in self.layers:                                                             # :1348-1352
             h = layer(h, bias)
         user_embedding = self.user_embed_model(b.user - 1).squeeze(1)                         # :1239-1240
@@ -429,7 +438,7 @@ class Graphormer(nn.Module):
             z = tmp[:, 0, :]
         else:   # only token 0 is consumed downstream (:1394-1396) -- equal to the looped form on [:,0,:]
             z = self.embed_fuse_model3(h[:, 0, :], user_embedding)
-        z = F.elu(self.final_ln(z))                                                           # :1360-1362
+        z = self.output_dropout(F.elu(self.final_ln(z)))                                      # :1360-1364
         cat_logits = self.cat_decoder(z)
         poi_logits = self.out_proj(z)
         if self.traits["log_softmax"]:

@@ -1,8 +1,8 @@
 #!/bin/bash
 # One GPU-box pass: parity tests, bench (both arms), per-kernel times, ncu launch list + one `--set full` capture per kernel.
-# usage (from the repo root, on the box): bash scripts/gpu_round.sh [tag] [stages]   stages = subset of "tbkln" (default all)
+# usage (from the repo root, on the box): bash scripts/gpu_round.sh [tag] [stages]   stages = subset of "tbkcln" (default all)
 TAG=${1:-r01}
-ST=${2:-tbkln}
+ST=${2:-tbkcln}
 O=gpurun_out/$TAG
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/smi.txt 2>&1
@@ -20,6 +20,9 @@ if [[ $ST == *k* ]]; then
   timeout 300 python scripts/k5bench.py --dbg --timeline > $O/k5bench.log 2>&1; echo "k5bench rc=$?"; grep -v Warning $O/k5bench.log | head -12
   timeout 300 python scripts/e2e_breakdown.py > $O/e2e_breakdown.log 2>&1; echo "e2e_breakdown rc=$?"
   timeout 600 python scripts/profile_step.py > $O/profile_step.log 2>&1; echo "profile_step rc=$?"
+fi
+if [[ $ST == *c* ]]; then
+  timeout 600 python scripts/c3_preprocess.py > $O/c3_preprocess.json 2> $O/c3_preprocess.err; echo "c3 rc=$?"; cat $O/c3_preprocess.json
 fi
 if [[ $ST == *l* ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $O/launches.csv \

@@ -43,3 +43,33 @@ def digest(M, path, e20):
     h.update(np.ascontiguousarray(path).tobytes())
     h.update(np.ascontiguousarray(e20).tobytes())
     return np.frombuffer(h.digest()[:16], np.uint8)
+
+
+# ---- numpy restatement of libmobgt's attention-dropout keep mask (mobgt_b200/csrc/common.cuh: attn_drop_*)
+def _lowbias32(z):
+    z = z.astype(np.uint32)
+    z ^= z >> np.uint32(16)
+    z = (z * np.uint32(0x7FEB352D)).astype(np.uint32)
+    z ^= z >> np.uint32(15)
+    z = (z * np.uint32(0x846CA68B)).astype(np.uint32)
+    z ^= z >> np.uint32(16)
+    return z
+
+
+def attn_drop_keep(plane, T, p, seed):
+    """keep mask bool [T, T] of attention plane `plane` (= graph * H + head) for dropout rate p and the 64-bit call seed."""
+    th16 = min(int(p * 65536.0 + 0.5), 65535) if p > 0 else 0
+    lo, hi = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
+    with np.errstate(over="ignore"):
+        rows = np.arange(T, dtype=np.uint32)
+        rowkey = _lowbias32(np.uint32(plane) * np.uint32(1024) + rows + lo) ^ hi                   # [T]
+        nch = (T + 7) // 8
+        chunk = np.arange(nch, dtype=np.uint32)
+        w0 = _lowbias32(rowkey[:, None] + chunk[None, :] * np.uint32(0x9E3779B1))                   # [T, nch]
+        words = [w0]
+        for c in (0xC2B2AE35, 0x27D4EB2F, 0x165667B1):
+            w = (w0 * np.uint32(c)).astype(np.uint32)
+            words.append(w ^ (w >> np.uint32(15)))
+        fields = np.stack([f for w in words for f in (w & np.uint32(0xFFFF), w >> np.uint32(16))], axis=-1)   # [T, nch, 8]
+    keep = (fields >= th16).reshape(T, nch * 8)[:, :T]
+    return keep, 65536.0 / (65536 - th16)

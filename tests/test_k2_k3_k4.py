@@ -5,6 +5,7 @@ import pytest
 import torch
 
 import model_oracle as mo
+from helpers import attn_drop_keep
 
 pytestmark = pytest.mark.gpu
 
@@ -239,7 +240,8 @@ def test_attention_bwd_matches_torch_autograd(lib_built, cfg, B, cap, nfix):
     assert torch.equal(dqkv3.cpu(), dqkv.cpu())
 
 
-def torch_attention_diff(qkv, bias, tok_off, H=8, d=24):
+def torch_attention_diff(qkv, bias, tok_off, H=8, d=24, drop=None):
+    """drop = (p, seed): apply libmobgt's counter-based keep mask (tests/helpers.attn_drop_keep) like nn.Dropout would."""
     D = H * d
     outs = []
     for g in range(len(tok_off) - 1):
@@ -249,8 +251,54 @@ def torch_attention_diff(qkv, bias, tok_off, H=8, d=24):
         k = qkv[a:e, D:2 * D].view(T, H, d).transpose(0, 1)
         v = qkv[a:e, 2 * D:].view(T, H, d).transpose(0, 1)
         s = (q * d ** -0.5) @ k.transpose(1, 2) + bias[g, :, :T, :T]
-        outs.append((torch.softmax(s, -1) @ v).transpose(0, 1).reshape(T, D))
+        pr = torch.softmax(s, -1)
+        if drop is not None:
+            masks = [attn_drop_keep(g * H + h, T, drop[0], drop[1]) for h in range(H)]
+            keep = torch.from_numpy(np.stack([m[0] for m in masks]))
+            pr = pr * keep.to(pr.dtype) * masks[0][1]                     # model_fqandtoyo.py:1704
+        outs.append((pr @ v).transpose(0, 1).reshape(T, D))
     return torch.cat(outs), None
+
+
+@pytest.mark.parametrize("cfg,B,cap,nfix", [("tiny", 6, 12, None), ("c1", 5, 128, 128), ("c1", 2, 300, 300)])
+def test_attention_dropout_fwd_bwd_matches_torch_with_same_mask(lib_built, cfg, B, cap, nfix):
+    """Training-mode attention dropout (model_fqandtoyo.py:1674, 1704): forward and backward regenerate the same counter-based
+    mask; against torch autograd with that mask restated in numpy."""
+    from mobgt_b200 import ops
+    w, items, ob, b = make_case(cfg, B, cap, n_fixed=nfix)
+    R, Pp, E, W, t = tables(seed=9)
+    cu = [x.cuda().contiguous() for x in (R, Pp, E, W.view(-1), t.view(-1))]
+    bias = ops.bias_fwd_raw(b, *cu, out_dtype=torch.bfloat16)
+    ntok = int(b.tok_pos.numel())
+    gen = torch.Generator().manual_seed(31)
+    qkv = (torch.randn(ntok, 3 * 192, generator=gen) * 1.2).to(torch.bfloat16)
+    dout = (torch.randn(ntok, 192, generator=gen)).to(torch.bfloat16)
+    p, seed = 0.1, 0x9E3779B97F4A7C15
+    out, lse = ops.attn_fwd_raw(qkv.cuda(), bias, b, drop_p=p, seed=seed)
+    out0, lse0 = ops.attn_fwd_raw(qkv.cuda(), bias, b)
+    out_b, _ = ops.attn_fwd_raw(qkv.cuda(), bias, b, drop_p=p, seed=seed + 1)
+    dbias = torch.full(bias.shape, float("nan"), dtype=torch.float32, device="cuda")
+    dqkv = ops.attn_bwd_raw(qkv.cuda(), bias, out, dout.cuda(), lse, b, dbias, 0, drop_p=p, seed=seed)
+    torch.cuda.synchronize()
+    assert torch.equal(lse, lse0)                              # the softmax denominator is taken before the mask
+    assert not torch.equal(out, out0) and not torch.equal(out, out_b)
+    tok_off = b.tok_off.cpu().numpy()
+    q32 = qkv.float().requires_grad_(True)
+    b32 = bias.float().cpu().requires_grad_(True)
+    ref, _ = torch_attention_diff(q32, b32, tok_off, drop=(p, seed))
+    err = (out.float().cpu() - ref.detach()).abs().max().item()
+    assert err <= 2e-2 * max(1.0, ref.abs().max().item()), f"attention out max err {err}"
+    (ref * dout.float()).sum().backward()
+    gq = q32.grad
+    scale = gq.abs().max().item()
+    err = (dqkv.float().cpu() - gq).abs().max().item()
+    assert err <= 2e-2 * max(1.0, scale), f"dqkv max err {err} (scale {scale})"
+    for g in range(B):
+        Tg = int(tok_off[g + 1] - tok_off[g])
+        gb = b32.grad[g, :, :Tg, :Tg]
+        got = dbias[g, :, :Tg, :Tg].cpu()
+        assert torch.isfinite(got).all()
+        assert (got - gb).abs().max().item() <= 2e-2 * max(1.0, gb.abs().max().item())
 
 
 # ---------------------------------------------------------------------------------------------------- K6
