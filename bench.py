@@ -396,7 +396,7 @@ def run_ours(args):
     for _ in range(max(2, args.warmup // 2)):
         bb = e2e_step()
     e2e_flush()
-    e2e_steps = max(4, args.steps // 2)
+    e2e_steps = max(4, args.steps)
     ms_e2e = timed(e2e_step, e2e_steps, finalize=e2e_flush)
     clocks = sampler.stop() if sampler else None
     h2d = int(bb.h2d_bytes)

@@ -47,7 +47,21 @@ struct AttnBwdParams {
     int bias_bufs;             // 1 or 2 bias tiles in shared memory
     long long *timeline;       // debug (mobgt_debug_set_timeline) or NULL
     AttnDrop drop;             // the forward's attention dropout (same seed): th16 == 0 when it was off
+    const __nv_bfloat16 *q, *k, *v;   // raw views of the operands (row stride qkv_stride) for the single-token tail
+    int64_t qkv_stride;
+    const __nv_bfloat16 *bias;        // [B,H,T,Tp]
 };
+
+// 24 bf16 (three 16-byte words) -> fp32
+__device__ __forceinline__ void unpack24(const uint4 &a, const uint4 &b, const uint4 &c, float (&f)[24]) {
+    const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int e = 0; e < 12; ++e) {
+        f[2 * e] = __uint_as_float(w[e] << 16);
+        f[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
+    }
+}
+__device__ __forceinline__ float bf16_at(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
 
 __device__ __forceinline__ float bwd_exp2(float x) {
     float y;
@@ -68,6 +82,13 @@ __device__ __forceinline__ void red_add_f32x4(float *addr, float a, float b, flo
 // S / dP MMAs of iteration t, so their latency hides behind the softmax-gradient math.
 // kDrop (training-mode attention dropout, forward: O = (M o P / (1-p)) V with keep mask M regenerated here):
 //   dV = (M o P / (1-p))^T dO ;  dP = M o (dO V^T) / (1-p) ;  dS = P o (dP - D) ;  D = rowsum(dO o O) still holds.
+//
+// Single-token tail ("fold"): a graph whose token count is 128 m + 1 (every graph at a node cap of 128 m: n nodes + the graph
+// token) would spill ONE query row and ONE key column into a second tile in each dimension, i.e. three extra near-empty
+// tile iterations per (j, i) border that cost as much latency as full ones.  For such graphs the MMA loop runs over the m x m
+// full tiles only and the last token sp = 128 m is handled by plain SIMT math (lse is known, so every element is independent):
+//   row sp against all keys, all rows against key sp -> dS / P scalars in shared memory, their rank-1 contributions are added
+//   to the dK / dV / dQ accumulators in the epilogues, and dQ[sp], dK[sp], dV[sp] are three small mat-vec reductions.
 template <bool kDrop>
 __global__ void __launch_bounds__(256, 1)
 k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -78,6 +99,10 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __shared__ __align__(8) uint64_t bar_qdo[2], bar_bias[2], bar_kv, bar_s, bar_mma;
     __shared__ uint32_t tmem_slot;
     __shared__ float sLse[kMaxTiles * kTile], sDelta[kMaxTiles * kTile];
+    __shared__ float sA_ds[kMaxTiles * kTile], sA_pd[kMaxTiles * kTile];   // tail: dS / dropped P of (row sp, key c)
+    __shared__ float sB_ds[kMaxTiles * kTile], sB_pd[kMaxTiles * kTile];   // tail: dS / dropped P of (row r, key sp)
+    __shared__ float sSp[4][kAttD];                                        // q, k, v, dO of token sp
+    __shared__ float sRed[3][10][kAttD];
 
     MOBGT_STAMP(p.timeline, 0);
     const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, t128 = tid & 127;
@@ -85,11 +110,38 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int g = blockIdx.x / p.H, h = blockIdx.x - g * p.H;
     const int t0 = p.tok_off[g];
     const int Tg = p.tok_off[g + 1] - t0;
-    const int NB = ceil_div(Tg, kTile);
+    const bool fold = Tg > kTile && (Tg % kTile) == 1;     // single-token tail handled by SIMT (see above)
+    const int NB = fold ? Tg / kTile : ceil_div(Tg, kTile);
+    const int sp = Tg - 1;                                 // the tail token (fold only)
     const int NT = NB * NB;
     const int HD = p.H * kAttD;
     const int nbias = p.bias_bufs;
 
+    // Global loads issued at the very top, consumed after the barrier / TMA set-up (their latency hides behind it):
+    //   this thread's first row of the lse / delta prologue, and (fold) the bias row / column of the tail token.
+    const int rows_pro = NB * kTile + (fold ? 1 : 0);
+    float lse_pre = 0.f;
+    uint4 o_pre[3], d_pre[3];
+    if (tid < Tg && tid < rows_pro) {
+        lse_pre = p.lse[(size_t)(t0 + tid) * p.H + h];
+        const uint4 *po = reinterpret_cast<const uint4 *>(p.o + (size_t)(t0 + tid) * HD + h * kAttD);
+        const uint4 *pd = reinterpret_cast<const uint4 *>(p.dout + (size_t)(t0 + tid) * HD + h * kAttD);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            o_pre[q] = po[q];
+            d_pre[q] = pd[q];
+        }
+    }
+    float b_row[3] = {0.f, 0.f, 0.f}, b_col[2] = {0.f, 0.f};
+    if (fold) {
+        const __nv_bfloat16 *bias_pl0 = p.bias + (size_t)(g * p.H + h) * p.T * p.Tp;
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+            if (tid + u * 256 < Tg) b_row[u] = bf16_at(bias_pl0 + (size_t)sp * p.Tp + tid + u * 256);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (tid + u * 256 < sp) b_col[u] = bf16_at(bias_pl0 + (size_t)(tid + u * 256) * p.Tp + sp);
+    }
     uint8_t *sBias = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // nbias x 32 KB, 1024-aligned (swizzle atom)
     uint8_t *sP = sBias + (size_t)nbias * kBiasTileBytes;
     uint8_t *sdS = sP + kPBytes;
@@ -137,15 +189,23 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     // lse (log2 units) and D = rowsum(dO * O) of every query row of this (graph, head).  Rows past the graph get
     // lse = +inf, so that p = 2^(s - lse) = 0 and dS = 0 there without any per-element select.
-    for (int r = tid; r < NB * kTile; r += 256) {
+    float sp_val = 0.f;
+    if (fold && tid < 4 * kAttD) {   // q, k, v, dO of the tail token as fp32 (load issued here, stored after the loop below)
+        const int which = tid / kAttD, e = tid - which * kAttD;
+        const __nv_bfloat16 *src = which == 0 ? p.q : which == 1 ? p.k : which == 2 ? p.v : p.dout;
+        const int64_t stride = which == 3 ? (int64_t)HD : p.qkv_stride;
+        sp_val = bf16_at(src + (size_t)(t0 + sp) * stride + h * kAttD + e);
+    }
+    for (int r = tid; r < rows_pro; r += 256) {
         float lse2 = INFINITY, dl = 0.f;
         if (r < Tg) {
-            lse2 = p.lse[(size_t)(t0 + r) * p.H + h] * 1.4426950408889634f;
+            const bool pre = r == tid;      // first row: loaded at the top of the kernel
+            lse2 = (pre ? lse_pre : p.lse[(size_t)(t0 + r) * p.H + h]) * 1.4426950408889634f;
             const uint4 *po = reinterpret_cast<const uint4 *>(p.o + (size_t)(t0 + r) * HD + h * kAttD);
             const uint4 *pd = reinterpret_cast<const uint4 *>(p.dout + (size_t)(t0 + r) * HD + h * kAttD);
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
-                const uint4 a = po[q], b = pd[q];
+                const uint4 a = pre ? o_pre[q] : po[q], b = pre ? d_pre[q] : pd[q];
                 const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -157,6 +217,7 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         sLse[r] = lse2;
         sDelta[r] = dl;
     }
+    if (fold && tid < 4 * kAttD) sSp[tid / kAttD][tid % kAttD] = sp_val;
     if (warp == 0) tmem_alloc<512>(&tmem_slot);
     fence_proxy_async_smem();
     tc_fence_before();
@@ -214,6 +275,139 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     bool mma_pending = false;
     uint32_t seed_lo = 0, seed_hi = 0;
     if (kDrop) attn_drop_fold_seed(p.drop, seed_lo, seed_hi);
+    const uint32_t th_hi = p.drop.th16 << 16;
+
+    if (fold) {   // ---- the single-token tail, SIMT (overlaps the first S / dP MMAs)
+        const float ik = p.drop.inv_keep;
+        const __nv_bfloat16 *bias_pl = p.bias + (size_t)plane * p.T * p.Tp;
+        __nv_bfloat16 *ds16 = reinterpret_cast<__nv_bfloat16 *>(p.dbias) + (size_t)plane * p.T * p.Tp;   // mode 2
+        float *ds32 = p.dbias + (size_t)plane * p.T * p.Tp;                                              // modes 0 / 1
+        auto emit_ds = [&](int r, int c, float v) {
+            const size_t o = (size_t)r * p.Tp + c;
+            if (p.accumulate == 2) ds16[o] = __float2bfloat16_rn(v);
+            else if (p.accumulate == 1) atomicAdd(ds32 + o, v);
+            else ds32[o] = v;
+        };
+        // 24 bf16 of row `row` of a [chunk][row][8] operand box
+        auto box_row = [&](const uint8_t *box, int row, float (&f)[24]) {
+            const uint8_t *b0 = box + row * 16;
+            unpack24(*reinterpret_cast<const uint4 *>(b0), *reinterpret_cast<const uint4 *>(b0 + kTile * 16),
+                     *reinterpret_cast<const uint4 *>(b0 + 2 * kTile * 16), f);
+        };
+        mbar_wait(&bar_kv, 0);                      // K / V boxes and the first Q / dO tile have landed
+        mbar_wait(&bar_qdo[0], 0);                  // (every thread observes the phases; tile 0 stays put until iteration 1)
+        {   // part A: query row sp against every key c (itself included)
+            const float lse_s = sLse[sp], delta_s = sDelta[sp];
+            const uint32_t rk = kDrop ? attn_drop_rowkey((uint32_t)plane, (uint32_t)sp, seed_lo, seed_hi) : 0u;
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const int c = tid + u * 256;
+                if (c >= Tg) break;
+                float dot = 0.f, dp = 0.f;
+                if (c < sp) {
+                    float kf[24], vf[24];
+                    box_row(sK + (size_t)(c >> 7) * kBoxBytes, c & 127, kf);
+                    box_row(sV + (size_t)(c >> 7) * kBoxBytes, c & 127, vf);
+#pragma unroll
+                    for (int e = 0; e < kAttD; ++e) {
+                        dot = fmaf(sSp[0][e], kf[e], dot);
+                        dp = fmaf(sSp[3][e], vf[e], dp);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < kAttD; ++e) {
+                        dot = fmaf(sSp[0][e], sSp[1][e], dot);
+                        dp = fmaf(sSp[3][e], sSp[2][e], dp);
+                    }
+                }
+                const float pr = bwd_exp2(fmaf(dot, sl2, b_row[u] * kL2e) - lse_s);
+                bool kp = true;
+                if (kDrop) kp = (attn_drop_keep8(rk, (uint32_t)(c >> 3), p.drop.th16) >> (c & 7)) & 1u;
+                const float ds = pr * ((kDrop ? (kp ? dp * ik : 0.f) : dp) - delta_s);
+                sA_ds[c] = ds;
+                sA_pd[c] = kDrop ? (kp ? pr * ik : 0.f) : pr;
+                emit_ds(sp, c, ds);
+            }
+        }
+        {   // part B: every full-tile query row r against key sp (rows of tile 0 from shared memory, the others from global)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int r = tid + u * 256;
+                if (r >= sp) break;
+                float qf[24], df[24];
+                if (r < kTile) {
+                    box_row(sQ, r, qf);
+                    box_row(sdO, r, df);
+                } else {
+                    const uint4 *qg = reinterpret_cast<const uint4 *>(p.q + (size_t)(t0 + r) * p.qkv_stride + h * kAttD);
+                    const uint4 *dg = reinterpret_cast<const uint4 *>(p.dout + (size_t)(t0 + r) * HD + h * kAttD);
+                    unpack24(qg[0], qg[1], qg[2], qf);
+                    unpack24(dg[0], dg[1], dg[2], df);
+                }
+                float dot = 0.f, dp = 0.f;
+#pragma unroll
+                for (int e = 0; e < kAttD; ++e) {
+                    dot = fmaf(qf[e], sSp[1][e], dot);
+                    dp = fmaf(df[e], sSp[2][e], dp);
+                }
+                const float pr = bwd_exp2(fmaf(dot, sl2, b_col[u] * kL2e) - sLse[r]);
+                bool kp = true;
+                if (kDrop) {
+                    const uint32_t rk = attn_drop_rowkey((uint32_t)plane, (uint32_t)r, seed_lo, seed_hi);
+                    kp = (attn_drop_keep8(rk, (uint32_t)(sp >> 3), p.drop.th16) >> (sp & 7)) & 1u;
+                }
+                const float ds = pr * ((kDrop ? (kp ? dp * ik : 0.f) : dp) - sDelta[r]);
+                sB_ds[r] = ds;
+                sB_pd[r] = kDrop ? (kp ? pr * ik : 0.f) : pr;
+                emit_ds(r, sp, ds);
+            }
+        }
+        __syncthreads();
+        if (tid < 240) {   // dQ[sp] = sum_c dS[sp][c] k_c ; dK[sp] = sum_r dS[r][sp] q_r ; dV[sp] = sum_r P[r][sp] dO_r : thread = (e, seg)
+            const int seg = tid / kAttD, e = tid - seg * kAttD;
+            const int eo = (e >> 3) * (kTile * 16) + (e & 7) * 2;      // byte offset of element e inside a box row
+            float aq = 0.f, ak = 0.f, av = 0.f;
+            for (int c = seg; c < sp; c += 10)                         // keys: every box is resident
+                aq = fmaf(sA_ds[c], bf16_at(reinterpret_cast<const __nv_bfloat16 *>(
+                                        sK + (size_t)(c >> 7) * kBoxBytes + (c & 127) * 16 + eo)), aq);
+            for (int r = seg; r < kTile; r += 10) {                    // query rows of tile 0: shared memory
+                ak = fmaf(sB_ds[r], bf16_at(reinterpret_cast<const __nv_bfloat16 *>(sQ + r * 16 + eo)), ak);
+                av = fmaf(sB_pd[r], bf16_at(reinterpret_cast<const __nv_bfloat16 *>(sdO + r * 16 + eo)), av);
+            }
+            for (int r0 = kTile + seg; r0 < sp; r0 += 80) {            // further tiles: global, 8 rows in flight
+                float qv8[8], dv8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int r = r0 + 10 * u;
+                    qv8[u] = r < sp ? bf16_at(p.q + (size_t)(t0 + r) * p.qkv_stride + h * kAttD + e) : 0.f;
+                    dv8[u] = r < sp ? bf16_at(p.dout + (size_t)(t0 + r) * HD + h * kAttD + e) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int r = r0 + 10 * u;
+                    if (r < sp) {
+                        ak = fmaf(sB_ds[r], qv8[u], ak);
+                        av = fmaf(sB_pd[r], dv8[u], av);
+                    }
+                }
+            }
+            sRed[0][seg][e] = aq;
+            sRed[1][seg][e] = ak;
+            sRed[2][seg][e] = av;
+        }
+        __syncthreads();
+        if (tid < 3 * kAttD) {
+            const int which = tid / kAttD, e = tid - which * kAttD;
+            float a = 0.f;
+#pragma unroll
+            for (int sg = 0; sg < 10; ++sg) a += sRed[which][sg][e];
+            // the (sp, sp) element: dQ += dS k_sp ; dK += dS q_sp ; dV += P dO_sp
+            a += which == 0 ? sA_ds[sp] * sSp[1][e] : which == 1 ? sA_ds[sp] * sSp[0][e] : sA_pd[sp] * sSp[3][e];
+            if (which < 2) a *= p.scale;
+            __nv_bfloat16 *dst = (which == 0 ? p.dq : which == 1 ? p.dk : p.dv) + (size_t)(t0 + sp) * p.dqkv_stride + h * kAttD + e;
+            *dst = __float2bfloat16_rn(a);
+        }
+    }
 
     for (int j = 0; j < NB; ++j) {
         const int kv_valid = min(kTile, Tg - j * kTile);
@@ -277,7 +471,8 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         const uint32_t bw[4] = {bvv.x, bvv.y, bvv.z, bvv.w};
                         float dsv[8];
                         uint4 pk, dk;
-                        const uint32_t keep = kDrop ? attn_drop_keep8(rowkey, (uint32_t)(j * (kTile / 8) + c8), p.drop.th16) : 0xFFu;
+                        AttnDropWords dw;
+                        if (kDrop) dw = attn_drop_words(rowkey, (uint32_t)(j * (kTile / 8) + c8));
                         if (colb + 8 <= kv_valid) {   // all 8 key columns valid: no per-element masking
                             float pv[8];
 #pragma unroll
@@ -286,7 +481,7 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                                 const float s = fmaf(__uint_as_float(sv[q8 * 8 + e]), sl2, bias * kL2e);
                                 pv[e] = bwd_exp2(s - lse2);
                                 if (kDrop) {
-                                    const bool kp = (keep >> e) & 1u;
+                                    const bool kp = attn_drop_keep(dw, e, th_hi);
                                     dsv[e] = pv[e] * ((kp ? __uint_as_float(dpv[q8 * 8 + e]) * ik : 0.f) - delta);
                                     pv[e] = kp ? pv[e] * ik : 0.f;      // the dV operand is the dropped-out P
                                 } else {
@@ -314,7 +509,7 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                                 const float s = fmaf(__uint_as_float(sv[q8 * 8 + e]), sl2, bias * kL2e);
                                 pv[e] = ok ? bwd_exp2(s - lse2) : 0.f;
                                 if (kDrop) {
-                                    const bool kp = (keep >> e) & 1u;
+                                    const bool kp = attn_drop_keep(dw, e, th_hi);
                                     dsv[e] = ok ? pv[e] * ((kp ? __uint_as_float(dpv[q8 * 8 + e]) * ik : 0.f) - delta) : 0.f;
                                     pv[e] = kp ? pv[e] * ik : 0.f;
                                 } else {
@@ -388,6 +583,12 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 tmem_ld_wait();
                 if (krow < Tg) {
                     const float sc = wg == 0 ? p.scale : 1.0f;
+                    if (fold) {   // + dS[sp][krow] q_sp (dK) / P[sp][krow] dO_sp (dV)
+                        const float a = wg == 0 ? sA_ds[krow] : sA_pd[krow];
+                        const float *vec = wg == 0 ? sSp[0] : sSp[3];
+#pragma unroll
+                        for (int e = 0; e < kAttD; ++e) kvv[e] = __float_as_uint(fmaf(a, vec[e], __uint_as_float(kvv[e])));
+                    }
                     uint32_t w[12];
 #pragma unroll
                     for (int e = 0; e < 12; ++e)
@@ -411,6 +612,11 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld32(tdQ + 32 * i + lane_off, qv);
         tmem_ld_wait();
         if (row < Tg) {
+            if (fold) {   // + dS[row][sp] k_sp
+                const float a = sB_ds[row];
+#pragma unroll
+                for (int e = 0; e < kAttD; ++e) qv[e] = __float_as_uint(fmaf(a, sSp[1][e], __uint_as_float(qv[e])));
+            }
             uint32_t w[12];
 #pragma unroll
             for (int e = 0; e < 12; ++e)
@@ -472,9 +678,10 @@ extern "C" int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, i
         int32_t rc = encode_tmap_bf16(&tmDS, dbias, 4, dims, str, box, 0);
         if (rc) return rc;
     }
-    const int max_boxes = ceil_div(t_max_host, kTile);
+    // a graph of 128 m + 1 tokens keeps only its m full boxes in shared memory (single-token tail), and T <= 513
+    const int max_boxes = t_max_host > kTile && t_max_host % kTile == 1 ? t_max_host / kTile : ceil_div(t_max_host, kTile);
     const size_t smem_base = 2 * kPBytes + 4 * kBoxBytes + (size_t)2 * max_boxes * kBoxBytes + 1024;
-    const int bias_bufs = (smem_base + 2 * kBiasTileBytes <= 220 * 1024) ? 2 : 1;
+    const int bias_bufs = (smem_base + 2 * kBiasTileBytes <= 204 * 1024) ? 2 : 1;    // + 20 KB of static shared memory
     const size_t smem = smem_base + (size_t)bias_bufs * kBiasTileBytes;
     MOBGT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, MOBGT_ERR_BAD_SHAPE, "mobgt_attn_bwd: drop_p=%f must be in [0, 1)", drop_p);
     const AttnDrop drop = make_attn_drop(drop_p, seed, seed_dev);
@@ -497,7 +704,12 @@ extern "C" int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, i
                     accumulate,
                     bias_bufs,
                     g_timeline_dev,
-                    drop};
+                    drop,
+                    static_cast<const __nv_bfloat16 *>(q),
+                    static_cast<const __nv_bfloat16 *>(k),
+                    static_cast<const __nv_bfloat16 *>(v),
+                    qkv_row_stride,
+                    static_cast<const __nv_bfloat16 *>(bias)};
     kern<<<B * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmdO, tmB, tmDS, p);
     MOBGT_LAUNCH_OK("k3_attn_bwd_kernel");
     return MOBGT_OK;

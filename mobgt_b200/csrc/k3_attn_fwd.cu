@@ -37,7 +37,20 @@ struct AttnFwdParams {
     int max_boxes;           // ceil(Tmax / 128): K/V boxes provisioned in shared memory
     long long *timeline;     // debug (mobgt_debug_set_timeline) or NULL
     AttnDrop drop;           // attention dropout on P (model_fqandtoyo.py:1704); th16 == 0 in eval
+    const __nv_bfloat16 *q, *k, *v;   // raw views of the operands (row stride qkv_stride) for the single-token tail
+    int64_t qkv_stride;
+    const __nv_bfloat16 *bias;        // [B,H,T,Tp]
+    int T, Tp;
 };
+
+__device__ __forceinline__ void fwd_unpack24(const uint4 &a, const uint4 &b, const uint4 &c, float (&f)[24]) {
+    const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int e = 0; e < 12; ++e) {
+        f[2 * e] = __uint_as_float(w[e] << 16);
+        f[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
+    }
+}
 
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
@@ -53,6 +66,10 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // exp pass and the P.V MMA.
 // kDrop: training-mode attention dropout — the row sum (softmax denominator) is taken BEFORE the mask, the bf16 P tile that
 // feeds the P.V MMA holds only the kept probabilities, and 1 / (1 - p) is folded into the final 1 / l normalisation.
+//
+// Single-token tail ("fold"): a graph of 128 m + 1 tokens (n = 128 m nodes + the graph token) runs the MMA loop over its
+// m x m full tiles only; the last token sp = 128 m is handled by SIMT: its key column enters every row's online softmax as
+// one more (register) block in the tile epilogue, and its own query row is one block-wide softmax + a small mat-vec.
 template <bool kDrop>
 __global__ void __launch_bounds__(256, 2)
 k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -62,6 +79,11 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __shared__ __align__(8) uint64_t bar_q, bar_kv, bar_bias, bar_s, bar_o;
     __shared__ uint32_t tmem_slot;
     __shared__ float sMax[2][kTile];
+    __shared__ float sTail[4 * kTile];          // fold: score (log2 units) of (row r, key sp)
+    __shared__ float sTp[4 * kTile + 4];        // fold: kept probabilities of (row sp, key c)
+    __shared__ float sSp[3][kAttD];             // fold: q, k, v of token sp
+    __shared__ float sRed[10][kAttD];
+    __shared__ float sScal[16];
 
     MOBGT_STAMP(p.timeline, 0);
     const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, t128 = tid & 127;
@@ -69,8 +91,28 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int g = blockIdx.x / p.H, h = blockIdx.x - g * p.H;
     const int t0 = p.tok_off[g];
     const int Tg = p.tok_off[g + 1] - t0;
-    const int NB = ceil_div(Tg, kTile);
+    const bool fold = Tg > kTile && (Tg % kTile) == 1;     // single-token tail handled by SIMT (see above)
+    const int NB = fold ? Tg / kTile : ceil_div(Tg, kTile);
+    const int sp = Tg - 1;                                 // the tail token (fold only)
 
+    // fold: the bias row / column of the tail token and its q, k, v — global loads issued at the very top, consumed after the
+    // prologue (their latency hides behind the barrier / TMEM / TMA set-up)
+    float b_row[3] = {0.f, 0.f, 0.f}, b_col[2] = {0.f, 0.f};
+    if (fold) {
+        const __nv_bfloat16 *bias_pl0 = p.bias + (size_t)(g * p.H + h) * p.T * p.Tp;
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+            if (tid + u * 256 < Tg) b_row[u] = __bfloat162float(bias_pl0[(size_t)sp * p.Tp + tid + u * 256]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (tid + u * 256 < sp) b_col[u] = __bfloat162float(bias_pl0[(size_t)(tid + u * 256) * p.Tp + sp]);
+    }
+    float sp_val = 0.f;
+    if (fold && tid < 3 * kAttD) {   // q, k, v of the tail token as fp32 (load issued here, stored before the first barrier)
+        const int which = tid / kAttD, e = tid - which * kAttD;
+        const __nv_bfloat16 *src = which == 0 ? p.q : which == 1 ? p.k : p.v;
+        sp_val = __bfloat162float(src[(size_t)(t0 + sp) * p.qkv_stride + h * kAttD + e]);
+    }
     uint8_t *sBias = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // 32 KB, 1024-aligned (swizzle atom)
     uint8_t *sP = sBias + kBiasTileBytes;                    // 32 KB
     uint8_t *sQ = sP + kPBytes;                              // 8 KB
@@ -108,6 +150,7 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int b = 0; b < NB; ++b) *reinterpret_cast<uint4 *>(kv + (size_t)b * kBoxBytes + 3 * kTile * 16 + t128 * 16) = z;
     }
     if (warp == 0) tmem_alloc<256>(&tmem_slot);
+    if (fold && tid < 3 * kAttD) sSp[tid / kAttD][tid % kAttD] = sp_val;
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -152,6 +195,100 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     constexpr float kL2e = 1.4426950408889634f;
     uint32_t seed_lo = 0, seed_hi = 0;
     if (kDrop) attn_drop_fold_seed(p.drop, seed_lo, seed_hi);
+    const uint32_t th_hi = p.drop.th16 << 16;
+
+    if (fold) {   // ---- the single-token tail, SIMT (overlaps the first S MMA)
+        const __nv_bfloat16 *bias_pl = p.bias + (size_t)plane * p.T * p.Tp;
+        mbar_wait(&bar_kv, 0);                      // K / V boxes and the first Q tile have landed
+        mbar_wait(&bar_q, 0);                       // (every thread observes the phases; tile 0 stays put until the loop)
+        // (1) every full-tile row r against key sp: the score joins the row's online softmax in the tile epilogue
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int r = tid + u * 256;
+            if (r >= sp) break;
+            float qf[24];
+            if (r < kTile) {      // tile 0: from shared memory
+                const uint8_t *qb = sQ + r * 16;
+                fwd_unpack24(*reinterpret_cast<const uint4 *>(qb), *reinterpret_cast<const uint4 *>(qb + kTile * 16),
+                             *reinterpret_cast<const uint4 *>(qb + 2 * kTile * 16), qf);
+            } else {
+                const uint4 *qg = reinterpret_cast<const uint4 *>(p.q + (size_t)(t0 + r) * p.qkv_stride + h * kAttD);
+                fwd_unpack24(qg[0], qg[1], qg[2], qf);
+            }
+            float dot = 0.f;
+#pragma unroll
+            for (int e = 0; e < kAttD; ++e) dot = fmaf(qf[e], sSp[1][e], dot);
+            sTail[r] = fmaf(dot, sl2, b_col[u] * kL2e);
+        }
+        // (2) query row sp against every key: block-wide softmax
+        float sc[3], mx = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int c = tid + u * 256;
+            sc[u] = -INFINITY;
+            if (c < Tg) {
+                float dot = 0.f;
+                if (c < sp) {
+                    const uint8_t *kb = sK + (size_t)(c >> 7) * kBoxBytes + (c & 127) * 16;
+                    float kf[24];
+                    fwd_unpack24(*reinterpret_cast<const uint4 *>(kb), *reinterpret_cast<const uint4 *>(kb + kTile * 16),
+                                 *reinterpret_cast<const uint4 *>(kb + 2 * kTile * 16), kf);
+#pragma unroll
+                    for (int e = 0; e < kAttD; ++e) dot = fmaf(sSp[0][e], kf[e], dot);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < kAttD; ++e) dot = fmaf(sSp[0][e], sSp[1][e], dot);
+                }
+                sc[u] = fmaf(dot, sl2, b_row[u] * kL2e);
+                mx = fmaxf(mx, sc[u]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((tid & 31) == 0) sScal[warp] = mx;
+        __syncthreads();
+        mx = sScal[0];
+#pragma unroll
+        for (int w8 = 1; w8 < 8; ++w8) mx = fmaxf(mx, sScal[w8]);
+        const uint32_t rk = kDrop ? attn_drop_rowkey((uint32_t)plane, (uint32_t)sp, seed_lo, seed_hi) : 0u;
+        float ls = 0.f;
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int c = tid + u * 256;
+            if (c < Tg) {
+                const float pe = fast_exp2(sc[u] - mx);
+                ls += pe;                                   // the denominator is taken before the dropout mask
+                bool kp = true;
+                if (kDrop) kp = (attn_drop_keep8(rk, (uint32_t)(c >> 3), p.drop.th16) >> (c & 7)) & 1u;
+                sTp[c] = kp ? pe : 0.f;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
+        if ((tid & 31) == 0) sScal[8 + warp] = ls;
+        __syncthreads();
+        ls = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) ls += sScal[8 + w8];
+        if (tid < 240) {   // O[sp] = sum_c P[c] v_c : thread = (e, seg)
+            const int seg = tid / kAttD, e = tid - seg * kAttD;
+            float a = 0.f;
+            for (int c = seg; c < sp; c += 10) {
+                const __nv_bfloat16 *vb = reinterpret_cast<const __nv_bfloat16 *>(
+                    sV + (size_t)(c >> 7) * kBoxBytes + (e >> 3) * (kTile * 16) + (c & 127) * 16) + (e & 7);
+                a = fmaf(sTp[c], __bfloat162float(*vb), a);
+            }
+            sRed[seg][e] = a;
+        }
+        __syncthreads();
+        if (tid < kAttD) {
+            float a = sTp[sp] * sSp[2][tid];
+#pragma unroll
+            for (int sg = 0; sg < 10; ++sg) a += sRed[sg][tid];
+            p.out[(size_t)(t0 + sp) * (p.H * kAttD) + h * kAttD + tid] = __float2bfloat16_rn(a * (kDrop ? p.drop.inv_keep : 1.0f) / ls);
+            if (tid == 0) p.lse[(size_t)(t0 + sp) * p.H + h] = (mx + log2f(ls)) * 0.6931471805599453f;
+        }
+    }
 
     for (int i = 0; i < NB; ++i) {
         const int row = i * kTile + t128;      // query row inside the graph
@@ -245,9 +382,9 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                                 l_blk += pv[e];     // row sum in fp32 (P is rounded to bf16 only for the tensor-core operand)
                             }
                             if (kDrop) {
-                                const uint32_t keep = attn_drop_keep8(rowkey, (uint32_t)(j * (kTile / 8) + c8), p.drop.th16);
+                                const AttnDropWords dw = attn_drop_words(rowkey, (uint32_t)(j * (kTile / 8) + c8));
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) pv[e] = ((keep >> e) & 1u) ? pv[e] : 0.f;
+                                for (int e = 0; e < 8; ++e) pv[e] = attn_drop_keep(dw, e, th_hi) ? pv[e] : 0.f;
                             }
                             uint4 pk;
                             pk.x = pack_bf16(pv[0], pv[1]);
@@ -298,7 +435,21 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             tmem_ld16(tO + lane_off + wg * 16, ov);
             tmem_ld_wait();
             if (row_ok) {
-                const float l_tot = sMax[0][t128] + sMax[1][t128];
+                float l_tot = sMax[0][t128] + sMax[1][t128];
+                if (fold) {   // one more online-softmax block: the tail key's column
+                    const float st = sTail[row];
+                    const float m_new = fmaxf(m_run, st);
+                    const float al = fast_exp2(m_run - m_new), pe = fast_exp2(st - m_new);
+                    l_tot = fmaf(l_tot, al, pe);
+                    bool kp = true;
+                    if (kDrop) kp = (attn_drop_keep8(rowkey, (uint32_t)(sp >> 3), p.drop.th16) >> (sp & 7)) & 1u;
+                    const float pd = kp ? pe : 0.f;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (wg == 0 || e < 8)
+                            ov[e] = __float_as_uint(fmaf(__uint_as_float(ov[e]), al, pd * sSp[2][wg * 16 + e]));
+                    m_run = m_new;
+                }
                 const float inv = (kDrop ? p.drop.inv_keep : 1.0f) / l_tot;
                 uint32_t w[8];
 #pragma unroll
@@ -359,10 +510,13 @@ extern "C" int32_t mobgt_attn_fwd(const void *q, const void *k, const void *v, i
         int32_t rc = encode_tmap_bf16(&tmB, bias, 3, dims, str, box, 1);
         if (rc) return rc;
     }
-    const int max_boxes = ceil_div(t_max_host, kTile);
+    // a graph of 128 m + 1 tokens keeps only its m full boxes in shared memory (single-token tail), and T <= 513
+    const int max_boxes = t_max_host > kTile && t_max_host % kTile == 1 ? t_max_host / kTile : ceil_div(t_max_host, kTile);
     const size_t smem = (size_t)kBiasTileBytes + kPBytes + kBoxBytes + (size_t)2 * max_boxes * kBoxBytes + 1024;
     AttnFwdParams p{tok_off, static_cast<__nv_bfloat16 *>(out), lse, H, scale, max_boxes, g_timeline_dev,
-                    make_attn_drop(drop_p, seed, seed_dev)};
+                    make_attn_drop(drop_p, seed, seed_dev),
+                    static_cast<const __nv_bfloat16 *>(q), static_cast<const __nv_bfloat16 *>(k),
+                    static_cast<const __nv_bfloat16 *>(v), qkv_row_stride, static_cast<const __nv_bfloat16 *>(bias), T, Tp};
     auto kern = p.drop.th16 ? k3_attn_fwd_kernel<true> : k3_attn_fwd_kernel<false>;
     MOBGT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<B * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmB, p);

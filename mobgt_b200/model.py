@@ -240,6 +240,8 @@ class Graphormer(nn.Module):
             self._w16.register((li, "o"), [a.output_layer])
             self._w16.register((li, "f1"), [layer.ffn.layer1])
             self._w16.register((li, "f2"), [layer.ffn.layer2])
+        self._w16.register(("emb", "fuse2"), [self.embed_fuse_model2.fuse_embed])
+        self._w16.register(("emb", "fuse4"), [self.embed_fuse_model4.fuse_embed])
         self.final_ln = nn.LayerNorm(2 * hidden_dim + 64)
         self.out_proj = nn.Linear(2 * hidden_dim + 64, P + tr["poi_extra"])
         self.ELU = nn.ELU()
@@ -289,8 +291,13 @@ class Graphormer(nn.Module):
         e = ops.EmbedGather.apply(b, self.cat_of_poi, Gd, self.time_embed_model_48.weight, Gc, dtype)
         hp = self.hidden_dim + self.time_embed_dim
         f2, f4 = self.embed_fuse_model2.fuse_embed, self.embed_fuse_model4.fuse_embed
-        x = F.leaky_relu(F.linear(e[:, :hp], f2.weight.to(dtype), f2.bias.to(dtype)), 0.2)              # :1268
-        x = F.leaky_relu(F.linear(torch.cat([x, e[:, hp:]], 1), f4.weight.to(dtype), f4.bias.to(dtype)), 0.2)   # :1269
+        if dtype == torch.bfloat16:     # bf16 working copies of the weights, bias gradients through the K6 column sum
+            self._w16.refresh()
+            x = F.leaky_relu(ops.linear_bf16(e[:, :hp], f2, *self._w16.get(("emb", "fuse2"))), 0.2)      # :1268
+            x = F.leaky_relu(ops.linear_bf16(torch.cat([x, e[:, hp:]], 1), f4, *self._w16.get(("emb", "fuse4"))), 0.2)   # :1269
+        else:
+            x = F.leaky_relu(F.linear(e[:, :hp], f2.weight.to(dtype), f2.bias.to(dtype)), 0.2)          # :1268
+            x = F.leaky_relu(F.linear(torch.cat([x, e[:, hp:]], 1), f4.weight.to(dtype), f4.bias.to(dtype)), 0.2)   # :1269
         tok = ops.EmbedSum.apply(b, x, self.in_degree_encoder.weight, self.out_degree_encoder.weight, self.pos_embed.pe,
                                  self.graph_token.weight)
         return F.dropout(tok, self.pos_embed.p, self.training)                                           # :358

@@ -18,7 +18,9 @@ out, lse = ops.attn_fwd_raw(qkv, bias, b)
 dout = torch.randn(ntok, 192, device="cuda").to(torch.bfloat16)
 dbias = torch.zeros(bias.shape, dtype=torch.bfloat16, device="cuda")
 tl = torch.zeros(256, dtype=torch.int64, device="cuda")
-for name, fn in (("bwd", lambda: ops.attn_bwd_raw(qkv, bias, out, dout, lse, b, dbias, 2)), ("fwd", lambda: ops.attn_fwd_raw(qkv, bias, b))):
+dp = float(os.environ.get("DROP", "0.1"))
+for name, fn in (("bwd", lambda: ops.attn_bwd_raw(qkv, bias, out, dout, lse, b, dbias, 2, drop_p=dp, seed=77)),
+                 ("fwd", lambda: ops.attn_fwd_raw(qkv, bias, b, drop_p=dp, seed=77))):
     fn()
     torch.cuda.synchronize()
     tl.zero_()
