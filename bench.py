@@ -238,12 +238,25 @@ def kernel_report(model, batch, pk, iters=8, head_c5=True):
     xs = torch.randn(ntok, 192, device=dev)
     dy32, dy16 = torch.randn(ntok, 192, device=dev), torch.randn(ntok, 192, device=dev).to(torch.bfloat16)
     add("k6_layernorm_fwd", tk(lambda: ops.layer_norm(xs, ln, "both")), ntok * 192 * (4 + 4 + 2), 12)
-    xg = xs.clone().requires_grad_(True)
-    o32, o16 = ops.layer_norm(xg, ln, "both")
-    add("k6_layernorm_bwd", tk(lambda: torch.autograd.grad([o32, o16], [xg], [dy32, dy16], retain_graph=True)),
+    # backward through the C-ABI directly (an autograd.grad call would time Python / autograd dispatch, not the kernel)
+    from mobgt_b200 import _C as C_
+    mean_, rstd_ = torch.empty(ntok, device=dev), torch.empty(ntok, device=dev)
+    o32_, o16_ = torch.empty(ntok, 192, device=dev), torch.empty(ntok, 192, device=dev, dtype=torch.bfloat16)
+    gam, bet = ln.weight.detach().float().contiguous(), ln.bias.detach().float().contiguous()
+    C_.call("mobgt_layernorm_fwd", C_.ptr(xs), C_.ptr(gam), C_.ptr(bet), float(ln.eps), ntok, 192, C_.ptr(o32_), C_.ptr(o16_),
+            C_.ptr(mean_), C_.ptr(rstd_), C_.stream_ptr())
+    dx_, dg_, db_ = torch.empty_like(xs), torch.empty(192, device=dev), torch.empty(192, device=dev)
+    wsb = int(C_.lib().mobgt_layernorm_bwd_workspace_bytes(192))
+    ws_ = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    add("k6_layernorm_bwd", tk(lambda: C_.call("mobgt_layernorm_bwd", C_.ptr(dy32), C_.ptr(dy16), C_.ptr(xs), C_.ptr(gam), C_.ptr(mean_),
+                                               C_.ptr(rstd_), ntok, 192, C_.ptr(dx_), C_.ptr(dg_), C_.ptr(db_), C_.ptr(ws_), wsb,
+                                               C_.stream_ptr())),
         ntok * 192 * (4 + 2 + 4 + 4), 12)
     wide = torch.randn(ntok, 1024, device=dev).to(torch.bfloat16)
-    add("k6_colsum_1024", tk(lambda: ops.colsum(wide)), ntok * 1024 * 2, 6)
+    wide2 = torch.randn(ntok, 1024, device=dev).to(torch.bfloat16)
+    add("k6_gelu_bwd_colsum", tk(lambda: ops.gelu_bwd_colsum_raw(wide2, wide)), ntok * 1024 * (2 + 2 + 2), 6)
+    del wide2
+    add("k6_colsum_1024", tk(lambda: ops.colsum(wide)), ntok * 1024 * 2, 0)
     add("k6_colsum_192", tk(lambda: ops.colsum(dy16)), ntok * 192 * 2, 12)
     del wide
     # K5 — the evaluation head (not part of the training step): c2 shape, and one GPU's shard of the c5 shape
@@ -304,6 +317,7 @@ def run_ours(args):
             except graphs.ShapeMismatch:
                 loss = None
         if loss is None:
+            graphed["eager_steps"] = graphed.get("eager_steps", 0) + 1
             flat.zero_()
             loss = model.training_step(b)
             loss.backward()
@@ -366,7 +380,8 @@ def run_ours(args):
     # in 2 worker processes that hand over one pinned byte buffer per batch; the H2D copy, the sort plans, K1 and poi_pos of
     # batch i+1 are issued right after the kernels of step i have been enqueued.  Every timed step still contains exactly one
     # collate (pack + pinned H2D + K1 + poi_pos), one training step and one D2H read of the loss.
-    loader = collator.PackedLoader(endless(), num_workers=args.loader_workers, world=world, latlon_dev=latlon,
+    loader = collator.PackedLoader(endless(), num_workers=args.loader_workers, side_stream=not args.no_side_stream, world=world,
+                                   latlon_dev=latlon,
                                    multi_hop_max_dist=20, rel_pos_max=1024, device=dev)
 
     # the loss of every step is read back to the host (async D2H into pinned memory + event); the host consumes it one step
@@ -381,7 +396,11 @@ def run_ours(args):
             losses.append(float(loss_pin[slot]))
             state["pending"] = None
 
+    trace = [] if os.environ.get("MOBGT_E2E_TRACE") else None
+
     def e2e_step():
+        if trace is not None:
+            trace.append(time.perf_counter())
         b = loader.current()
         loss = train_step(b)
         slot = state["k"] & 1
@@ -393,12 +412,18 @@ def run_ours(args):
         state["pending"], state["k"] = (ev, slot), state["k"] + 1
         return b
 
-    for _ in range(max(2, args.warmup // 2)):
+    # warm-up: the caching allocator's pool of collation buffers (two batches in flight + blocks waiting for the consumer
+    # stream) and the loader workers reach their steady state
+    for _ in range(max(6, args.warmup)):
         bb = e2e_step()
     e2e_flush()
     e2e_steps = max(4, args.steps)
     ms_e2e = timed(e2e_step, e2e_steps, finalize=e2e_flush)
     clocks = sampler.stop() if sampler else None
+    if trace is not None and rank == 0:
+        dt = np.diff(np.array(trace[-e2e_steps:])) * 1e3
+        print("[bench] e2e host step intervals (ms): " + " ".join(f"{x:.1f}" for x in dt), file=sys.stderr)
+        print(f"[bench] eager (non-graph) steps so far: {graphed.get('eager_steps', 0)}", file=sys.stderr)
     h2d = int(bb.h2d_bytes)
     if rank == 0:
         graphs = B * world_size
@@ -442,6 +467,7 @@ def main():
     ap.add_argument("--workload", default="c2-dense128", choices=["c2-dense128", "c2-natural"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--loader-workers", type=int, default=2, help="DataLoader worker processes packing raw items (e2e path)")
+    ap.add_argument("--no-side-stream", action="store_true", help="e2e: collate on the training stream (no overlap)")
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false", help="run every step eagerly")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-report", action="store_true")

@@ -239,6 +239,12 @@ int32_t mobgt_topk_merge(const float *val, const int32_t *idx, const int32_t *cn
 int32_t mobgt_selftest_umma(const void *A, const void *B, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
                             float *out, void *stream);
 
+/* Backward of the FFN's GELU (nn.GELU(), exact erf form; model_fqandtoyo.py:1650, applied :1654) on bf16 activations, fp32 math.
+ *   gelu_bwd_colsum: dh = da * gelu'(h) (bf16 [N, C]) and dbias[c] = sum_r dh[r, c] (fp32, fixed order) — the input gradient of
+ *                    the activation fused with the bias gradient of the Linear that produced h.  Workspace as mobgt_colsum. */
+int32_t mobgt_gelu_bwd_colsum(const void *da_bf16, const void *h_bf16, int32_t N, int32_t C, void *dh_bf16, float *dbias,
+                              void *workspace, int64_t workspace_bytes, void *stream);
+
 /* Debug hook: register (NULL: clear) a device buffer of 256 int64; thread 0 of one CTA of mobgt_attn_fwd / mobgt_attn_bwd then
  * stamps clock64() at its pipeline stages (scripts/timeline.py). */
 int32_t mobgt_debug_set_timeline(void *dev_buf256);

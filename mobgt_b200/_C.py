@@ -50,6 +50,7 @@ SIGNATURES = {
                                         c_p, c_i64, c_p, c_p],
     "mobgt_colsum_workspace_bytes": [c_i32, c_i32],
     "mobgt_colsum": [c_p, c_i32, c_i64, c_i32, c_i32, c_p, c_p, c_i64, c_p],
+    "mobgt_gelu_bwd_colsum": [c_p, c_p, c_i32, c_i32, c_p, c_p, c_p, c_i64, c_p],
     "mobgt_debug_set_timeline": [c_p],
     "mobgt_selftest_umma": [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p],
 }

@@ -175,7 +175,7 @@ class EncoderLayer(nn.Module):
         f = self.ffn
         w1, b1 = w16.get((layer, "f1")) if w16 is not None else (None, None)
         w2, b2 = w16.get((layer, "f2")) if w16 is not None else (None, None)
-        y = ops.linear_bf16(F.gelu(ops.linear_bf16(y16, f.layer1, w1, b1)), f.layer2, w2, b2)
+        y = ops.linear_bf16(ops.linear_gelu_bf16(y16, f.layer1, w1, b1), f.layer2, w2, b2)
         return ops.add_dropout_layer_norm(x1, y, self.ffn_norm2, self.ffn_dropout.p, self.training, "both")
 
 

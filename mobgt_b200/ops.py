@@ -493,6 +493,43 @@ def linear_bf16(x, lin, w16=None, b16=None):
     return LinearBiasFn.apply(x, w16, b16, lin.weight, lin.bias)
 
 
+def gelu_bwd_colsum_raw(da, h):
+    """-> (dh bf16 [N, C] = da * gelu'(h), dbias f32 [C] = dh.sum(0)) in one pass."""
+    assert da.dtype == torch.bfloat16 and h.dtype == torch.bfloat16 and da.is_contiguous() and h.is_contiguous() and da.shape == h.shape
+    N, C = h.shape
+    dh = torch.empty_like(h)
+    db = torch.empty(C, dtype=torch.float32, device=h.device)
+    ws_bytes = int(_C.lib().mobgt_colsum_workspace_bytes(N, C))
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=h.device)
+    _C.call("mobgt_gelu_bwd_colsum", _C.ptr(da), _C.ptr(h), N, C, _C.ptr(dh), _C.ptr(db), _C.ptr(ws), ws_bytes, _C.stream_ptr())
+    return dh, db
+
+
+class LinearGeluFn(torch.autograd.Function):
+    """a = gelu(x W^T + b): FeedForwardNetwork.layer1 + nn.GELU (model_fqandtoyo.py:1646-1655) with bf16 operands.  The GEMM is
+    the library's, and so is the forward GELU; in backward the activation gradient and the bias gradient (its column sum) come
+    out of ONE pass over dA and h.  Gradients go straight to the fp32 master parameters."""
+
+    @staticmethod
+    def forward(ctx, x, w16, b16, w_master, b_master):
+        h = torch.nn.functional.linear(x, w16, b16)
+        ctx.save_for_backward(x, w16, h)
+        return torch.nn.functional.gelu(h)
+
+    @staticmethod
+    def backward(ctx, da):
+        x, w16, h = ctx.saved_tensors
+        dh, db = gelu_bwd_colsum_raw(da.contiguous(), h)
+        return dh @ w16, None, None, (dh.t() @ x).float(), db
+
+
+def linear_gelu_bf16(x, lin, w16=None, b16=None):
+    """gelu(nn.Linear `lin`(x)) for a bf16 [N, in] tensor whose out_features is a multiple of 8."""
+    if w16 is None:
+        w16, b16 = lin.weight.detach().to(torch.bfloat16), lin.bias.detach().to(torch.bfloat16)
+    return LinearGeluFn.apply(x, w16, b16, lin.weight, lin.bias)
+
+
 # ----------------------------------------------------------------------------------------------- K5
 def head_split(M, V):
     """Number of per-row output lists = 2 x (vocabulary splits per 128-row tile of z): every CTA of mobgt_head_topk runs two

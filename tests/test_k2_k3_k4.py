@@ -385,3 +385,41 @@ def test_add_dropout_layernorm_vs_torch(lib_built, p):
     got = (xo.grad, yo.grad.float(), ln.weight.grad, ln.bias.grad)
     for a, b, tol in zip(got, ref_g, (2e-5, 1e-2, 2e-5, 2e-5)):
         assert (a - b).abs().max().item() <= tol * b.abs().max().item() + 1e-4
+
+
+@pytest.mark.parametrize("N,C", [(33024, 1024), (777, 256), (5, 8)])
+def test_gelu_bwd_colsum_vs_torch(lib_built, N, C):
+    """K6: backward of nn.GELU() (exact erf form, model_fqandtoyo.py:1650) fused with the bias-gradient column sum, against torch
+    autograd on the same bf16 inputs."""
+    from mobgt_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    h = (torch.randn(N, C, generator=g) * 2.0).to(torch.bfloat16).cuda()
+    da = torch.randn(N, C, generator=g).to(torch.bfloat16).cuda()
+    hr = h.float().requires_grad_(True)
+    ref = torch.nn.functional.gelu(hr)
+    dh, db = ops.gelu_bwd_colsum_raw(da, h)
+    (ref * da.float()).sum().backward()
+    assert (dh.float() - hr.grad).abs().max().item() <= 1e-2 * max(1.0, hr.grad.abs().max().item())
+    # the fused column sum is the fp32 sum of the bf16 values that were stored
+    want = dh.double().sum(0)
+    assert (db.double() - want).abs().max().item() <= 1e-5 * N ** 0.5 * max(1.0, want.abs().max().item())
+
+
+def test_linear_gelu_fn_matches_unfused(lib_built):
+    from mobgt_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    lin = torch.nn.Linear(192, 1024).cuda()
+    x = torch.randn(1000, 192, generator=g).to(torch.bfloat16).cuda()
+    dy = torch.randn(1000, 1024, generator=g).to(torch.bfloat16).cuda()
+    xa = x.clone().requires_grad_(True)
+    ya = ops.linear_gelu_bf16(xa, lin)
+    (ya.float() * dy.float()).sum().backward()
+    ga = (xa.grad.float().clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+    lin.zero_grad()
+    xb = x.clone().requires_grad_(True)
+    yb = torch.nn.functional.gelu(ops.linear_bf16(xb, lin))
+    (yb.float() * dy.float()).sum().backward()
+    gb = (xb.grad.float(), lin.weight.grad, lin.bias.grad)
+    assert (ya.float() - yb.float()).abs().max().item() <= 2e-2 * max(1.0, yb.float().abs().max().item())
+    for a_, b_ in zip(ga, gb):
+        assert (a_ - b_).abs().max().item() <= 2e-2 * max(1.0, b_.abs().max().item())
