@@ -380,7 +380,11 @@ def run_ours(args):
     # in 2 worker processes that hand over one pinned byte buffer per batch; the H2D copy, the sort plans, K1 and poi_pos of
     # batch i+1 are issued right after the kernels of step i have been enqueued.  Every timed step still contains exactly one
     # collate (pack + pinned H2D + K1 + poi_pos), one training step and one D2H read of the loss.
-    loader = collator.PackedLoader(endless(), num_workers=args.loader_workers, side_stream=not args.no_side_stream, world=world,
+    # side-stream collation overlaps K1 / the sort plans with the training step on ONE GPU (e2e 9.6 -> 8.6 ms); with the NCCL
+    # gradient all-reduce in the step it measured slower at N = 2 (11.0 vs 9.8 ms, profiles/r04z_bench_n2*.json), so the
+    # data-parallel runs collate on the training stream
+    side = (not args.no_side_stream) and world_size == 1
+    loader = collator.PackedLoader(endless(), num_workers=args.loader_workers, side_stream=side, world=world,
                                    latlon_dev=latlon,
                                    multi_hop_max_dist=20, rel_pos_max=1024, device=dev)
 
@@ -433,6 +437,7 @@ def run_ours(args):
                 "config": {"workload": args.workload, "world": "toyotagraph-shaped P=60000 C=300 U=995", "hidden": 128, "layers": 6,
                            "heads": 8, "ffn": 1024, "multi_hop_max_dist": 20, "graphs_per_gpu": B,
                            "tokens_per_gpu": int(batch.tok_pos.numel()), "parallelism": f"dp{world_size}", "cuda_graph": graph_note,
+                           "e2e_collate_stream": "side" if side else "training",
                            "l2": "per-step working set (activations + bias planes, > 1 GB) exceeds the 126 MB L2"},
                 "e2e": {"value": graphs * e2e_steps / (ms_e2e / 1e3), "unit": "graphs/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / e2e_steps},
