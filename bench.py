@@ -380,10 +380,11 @@ def run_ours(args):
     # in 2 worker processes that hand over one pinned byte buffer per batch; the H2D copy, the sort plans, K1 and poi_pos of
     # batch i+1 are issued right after the kernels of step i have been enqueued.  Every timed step still contains exactly one
     # collate (pack + pinned H2D + K1 + poi_pos), one training step and one D2H read of the loss.
-    # side-stream collation overlaps K1 / the sort plans with the training step on ONE GPU (e2e 9.6 -> 8.6 ms); with the NCCL
-    # gradient all-reduce in the step it measured slower at N = 2 (11.0 vs 9.8 ms, profiles/r04z_bench_n2*.json), so the
-    # data-parallel runs collate on the training stream
-    side = (not args.no_side_stream) and world_size == 1
+    # side-stream collation: K1 / poi_pos / the sort plans of batch i+1 run next to the head of training step i.  The loader
+    # gates them behind the previous step (PackedLoader.current records the gate), so they never run next to the NCCL
+    # all-reduce: N = 2 e2e 8.96 ms with the gate, 11.0 ms without it, 9.76 ms on the training stream
+    # (profiles/r04z_bench_n2*.json)
+    side = not args.no_side_stream
     loader = collator.PackedLoader(endless(), num_workers=args.loader_workers, side_stream=side, world=world,
                                    latlon_dev=latlon,
                                    multi_hop_max_dist=20, rel_pos_max=1024, device=dev)

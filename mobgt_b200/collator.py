@@ -80,6 +80,7 @@ class PackedLoader:
     def __init__(self, batches, collate_fn=None, num_workers=0, max_node=512, side_stream=True, **collate_kw):
         self._kw = collate_kw
         self._stream = torch.cuda.Stream() if (side_stream and torch.cuda.is_available()) else None
+        self._gate = None
         if num_workers > 0:
             ds = _PackStream(batches, max_node)
             dl = torch.utils.data.DataLoader(ds, batch_size=None, num_workers=num_workers, pin_memory=False, prefetch_factor=2,
@@ -98,6 +99,10 @@ class PackedLoader:
             return None
         if self._stream is None:
             return self._collate(nxt)
+        if self._gate is not None:
+            # start only after everything the consumer had enqueued when it fetched the current batch (the previous step incl.
+            # its gradient all-reduce and optimizer): the collation then overlaps the head of the running step, not NCCL
+            self._stream.wait_event(self._gate)
         with torch.cuda.stream(self._stream):
             b = self._collate(nxt)
             ev = torch.cuda.Event()
@@ -107,6 +112,9 @@ class PackedLoader:
 
     def current(self):
         b = self._next
+        if self._stream is not None:
+            self._gate = torch.cuda.Event()
+            self._gate.record(torch.cuda.current_stream())
         ev = b.__dict__.pop("_ready", None) if b is not None else None
         if ev is not None:
             cur = torch.cuda.current_stream()
