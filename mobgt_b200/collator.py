@@ -115,7 +115,7 @@ class PackedLoader:
         if self._stream is not None:
             self._gate = torch.cuda.Event()
             self._gate.record(torch.cuda.current_stream())
-        ev = b.__dict__.pop("_ready", None) if b is not None else None
+        ev = b.__dict__.pop("_ready", None) if (b is not None and self._stream is not None) else None
         if ev is not None:
             cur = torch.cuda.current_stream()
             cur.wait_event(ev)

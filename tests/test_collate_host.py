@@ -50,3 +50,19 @@ def test_worker_stream_shards_batches_in_order():
     for d, hp in zip(got, ref):
         assert np.array_equal(d["buf"].numpy(), hp.buf) and d["B"] == hp.B and d["cells"] == hp.cells
         assert {k: tuple(v) if not isinstance(v, tuple) else v for k, v in d["layout"].items()}.keys() == hp.layout.keys()
+
+
+def test_packed_loader_protocol_without_cuda():
+    """PackedLoader's one-batch-ahead protocol (current / advance / iteration, end of stream) with a host-only collate_fn:
+    the side stream is only created when CUDA is available, so this runs on the CPU."""
+    from mobgt_b200 import collator
+    batches = [[i, i + 1] for i in range(5)]
+    seen = []
+    loader = collator.PackedLoader(iter(batches), collate_fn=lambda items: {"items": list(items)}, num_workers=0)
+    assert loader.current()["items"] == [0, 1]
+    loader.advance()
+    assert loader.current()["items"] == [1, 2]
+    for b in loader:                      # iteration continues from the current batch and advances by itself
+        seen.append(b["items"][0])
+    assert seen == [1, 2, 3, 4]
+    assert loader.current() is None       # end of stream
