@@ -51,3 +51,17 @@ def test_bad_arguments_return_status_not_crash(lib_built):
     rc = L.mobgt_apsp_edge_input(None, None, None, None, 1, 4, 20, 0, None, None, None, None, None)
     assert rc == -6                                       # MOBGT_ERR_NULL
     assert "null" in _C.last_error()
+
+
+def test_binding_arity_matches_header(lib_built):
+    """Every ctypes signature in mobgt_b200/_C.py has as many arguments as the declaration in include/mobgt.h (a drifted
+    binding would pass garbage in the trailing arguments instead of failing loudly)."""
+    from mobgt_b200 import _C
+    src = open(os.path.join(ROOT, "include", "mobgt.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decls = dict(re.findall(r"\b(mobgt_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src))
+    assert sorted(decls) == sorted(_C.SIGNATURES)
+    for name, params in decls.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_C.SIGNATURES[name]), (name, n, len(_C.SIGNATURES[name]))
