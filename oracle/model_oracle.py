@@ -1,13 +1,15 @@
 """ORACLE (test infrastructure, not product code): CPU PyTorch restatement of the reference's
 device hot path, /root/reference/graphormer/{wrapper,collator,model_fqandtoyo,modelGNN,lr}.py.
 
-The reference itself cannot be imported here (pytorch_lightning / torch_geometric / ogb are not
-installed, `.cuda()` is hard-coded, the poi_data blob is missing — SURVEY.md §0.5), so every function
-below restates the cited lines with plain torch on CPU.  PARITY PIN: the integer preprocessing
-(preprocess_item) is pinned to the compiled reference through oracle/algos_oracle.c + tests/golden;
-the floating-point model arithmetic is PyTorch's own (nn.Linear / Embedding / LayerNorm / softmax),
-for which the reference holds no golden vectors -> "parity unpinned" beyond the restatement
-(SURVEY.md §8c).  Two bias modes: 'fp32' (= model.py:157-190 arithmetic + the live model's poi_pos
+The reference needs pytorch_lightning / torch_geometric / ogb (not installed) and its dataset files, so every function below
+restates the cited lines with plain torch on CPU.  PARITY PIN: the integer preprocessing (preprocess_item) is pinned to the
+compiled reference through oracle/algos_oracle.c + tests/golden/algos_golden.npz; the collator fields, the forward pass, the
+losses and the metrics are pinned to the UNMODIFIED reference modules (wrapper.py, collator.py, model_fqandtoyo.py, modelGNN.py),
+which tests/golden/make_model_golden.py executes on the CPU in the build container behind import stubs for the three missing
+packages, for the toyotagraph / gowalla_nevda / foursquaregraph branches: tests/golden/model_golden_*.npz, metrics_golden.npz,
+checked by tests/test_oracle_model_golden.py (fields bit for bit, logits / loss within 1e-5).  Not pinned: `poi_pos` binning
+(the reference bins a distance pickle that is not shipped; PoiWorld.poi_pos_bins is a stand-in), the dropout masks (stochastic)
+and the reference's fp16 AMP rounding (the oracle is fp32; tolerances are the north_star's).  Two bias modes: 'fp32' (= model.py:157-190 arithmetic + the live model's poi_pos
 term; the 1e-5 target) and 'ref_half' (the live model's .half() round trips,
 model_fqandtoyo.py:1178-1198; compared at the bf16 tolerance).
 

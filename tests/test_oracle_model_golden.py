@@ -1,0 +1,82 @@
+"""CPU: oracle/model_oracle.py (the restatement every GPU parity test is measured against) reproduces the outputs of the REAL
+reference — `wrapper.preprocess_item`, `collator.collator_toyota` and `model_fqandtoyo.Graphormer.forward` + losses, executed
+unmodified in the build container by tests/golden/make_model_golden.py (import stubs for pytorch_lightning / torch_geometric /
+ogb only) and frozen in tests/golden/model_golden_<dataset>.npz for the three constructor / forward / loss branches of the live
+model (toyotagraph, gowalla_nevda, foursquaregraph).  This pins the model half of the oracle to the reference itself."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import model_oracle as mo
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _gen():
+    spec = importlib.util.spec_from_file_location("make_model_golden", os.path.join(HERE, "golden", "make_model_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+DATASETS = ("toyotagraph", "gowalla_nevda", "foursquaregraph")
+
+
+def _setup(dataset_name):
+    g = _gen()
+    gold = np.load(os.path.join(HERE, "golden", f"model_golden_{dataset_name}.npz"))
+    world, items = g.make_world_and_items(dataset_name)
+    ob = mo.collate([mo.preprocess_item(it, hop_cap=20) for it in items], world, multi_hop_max_dist=20, rel_pos_max=1024)
+    return g, gold, world, ob
+
+
+@pytest.mark.parametrize("dataset_name", DATASETS)
+def test_oracle_collator_fields_equal_reference_collator(dataset_name):
+    """wrapper.py:25-102 + collator.py:310-458 / 460-608 / 610-748 executed by the reference == the oracle's preprocess_item + collate, field by
+    field, bit for bit (poi_pos excepted: the reference bins a distance pickle that is not shipped)."""
+    g, gold, world, ob = _setup(dataset_name)
+    for name in ("x", "rel_pos", "edge_input", "in_degree", "out_degree", "y", "user"):
+        ref = torch.from_numpy(gold["f_" + name])
+        got = getattr(ob, name)
+        assert tuple(got.shape) == tuple(ref.shape), (name, got.shape, ref.shape)
+        assert torch.equal(got.long(), ref.long()), name
+    assert torch.equal(ob.attn_bias, torch.from_numpy(gold["f_attn_bias"]))          # 0 / -inf pattern
+    assert torch.equal(ob.time_normal.float(), torch.from_numpy(gold["f_time_normal"]).float())
+
+
+@pytest.mark.parametrize("dataset_name", DATASETS)
+def test_oracle_forward_and_loss_equal_reference_model(dataset_name):
+    """model_fqandtoyo.py:1123-1432 (eval mode) and the losses :545-550 / :1446-1471 of each dataset branch: the oracle with the
+    same parameters (filled per name from the shared seeded generator) gives the reference's outputs within 1e-5 relative."""
+    g, gold, world, ob = _setup(dataset_name)
+    om = mo.Graphormer(world, n_layers=g.HP["n_layers"], ffn_dim=g.HP["ffn_dim"], dataset_name=dataset_name).eval()
+    with torch.no_grad():
+        for name, p in om.named_parameters():
+            p.copy_(g.golden_weights(name, tuple(p.shape)))
+        poi, cat = om(ob)
+        loss = om.training_loss(ob)
+    rp, rc = torch.from_numpy(gold["poi_logits"]), torch.from_numpy(gold["cat_logits"])
+    assert tuple(poi.shape) == tuple(rp.shape) and tuple(cat.shape) == tuple(rc.shape)
+    assert (poi - rp).abs().max().item() <= 1e-5 * max(1.0, rp.abs().max().item()), (poi - rp).abs().max().item()
+    assert (cat - rc).abs().max().item() <= 1e-5 * max(1.0, rc.abs().max().item()), (cat - rc).abs().max().item()
+    assert torch.equal(om.cat_target.view(-1).long(), torch.from_numpy(gold["cat_target"]).long())
+    assert abs(float(loss) - float(gold["loss"][0])) <= 1e-5 * abs(float(gold["loss"][0]))
+    assert torch.equal(poi.argsort(dim=1, descending=True)[:, :10], rp.argsort(dim=1, descending=True)[:, :10])
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_metrics_equal_reference(tag):
+    """get_acc / MRR_metric (model_fqandtoyo.py:48-90, 122-131) run by the reference on seeded logits == the oracle's restatement
+    and the product's device-side mirror (mobgt_b200.metrics), including the `break` at the first zero target (case b)."""
+    from mobgt_b200 import metrics as pm
+    gold = np.load(os.path.join(HERE, "golden", "metrics_golden.npz"))
+    scores, y = torch.from_numpy(gold["scores"]), torch.from_numpy(gold["y_" + tag])
+    for impl in (mo, pm):
+        acc, ndcg = impl.get_acc(y, scores)
+        assert np.array_equal(np.asarray(acc), gold["acc_" + tag]), impl.__name__
+        assert np.allclose(np.asarray(ndcg), gold["ndcg_" + tag], rtol=1e-12, atol=0), impl.__name__
+        mrr = getattr(impl, "MRR_metric", None) or impl.mrr_metric
+        assert abs(float(mrr(y, scores)) - float(gold["mrr_" + tag][0])) <= 1e-9 * float(gold["mrr_" + tag][0])
