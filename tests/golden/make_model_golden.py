@@ -44,6 +44,9 @@ B, CAP, SEED = 5, 12, 11
 DATASETS = {"toyotagraph": (995, "toyota_distance.pkl", "collator_toyota"),
             "gowalla_nevda": (1080, "gowalla_distance.pkl", "collator_gowalla"),
             "foursquaregraph": (1080, "tky_distance.pkl", "collator_foursquare")}
+# parameters whose full gradient is stored (the outputs of K2 / K4 backward and one encoder weight); all others: the norm
+GRAD_FULL = ("rel_pos_encoder.weight", "edge_encoder.weight", "edge_dis_encoder.weight", "graph_token_virtual_distance.weight",
+             "poi_pos_encoder.weight", "graph_token.weight", "layers.0.self_attention.linear_q.weight", "final_ln.weight")
 PAD0 = ("edge_encoder.weight", "rel_pos_encoder.weight", "in_degree_encoder.weight", "out_degree_encoder.weight",
         "fre_embed_model.weight", "poi_pos_encoder.weight")          # nn.Embedding(padding_idx=0) tables: row 0 stays zero
 
@@ -197,11 +200,22 @@ def run_dataset(dataset_name, tmp, ref_model, ref_collator, ref_wrapper, mo):
         loss = gtl(cat, cat_target, 0.1) + torch.nn.NLLLoss(ignore_index=0)(poi, rb.y)
     else:                                 # :1446-1460
         loss = gtl(poi, rb.y - 1, 0.2)
+    # ---- reference backward: autograd through the reference's own forward graph (the loss formula above, differentiable)
+    rm.zero_grad()
+    out_g = rm(copy.deepcopy(rb))
+    ct = rm.cat_target.clone().view(-1).long()
+    loss_g = (gtl(out_g[1], ct, 0.1) + torch.nn.NLLLoss(ignore_index=0)(out_g[0], rb.y)) if dataset_name == "toyotagraph" \
+        else gtl(out_g[0], rb.y - 1, 0.2)
+    loss_g.backward()
+    gnames = sorted(n for n, p_ in rm.named_parameters() if p_.grad is not None and float(p_.grad.abs().sum()) > 0)
+    gnorm = np.array([float(dict(rm.named_parameters())[n].grad.double().norm()) for n in gnames], np.float64)
+    full = {n: dict(rm.named_parameters())[n].grad.numpy().copy() for n in GRAD_FULL}
     fields = dict(x=rb.x, rel_pos=rb.rel_pos, edge_input=rb.edge_input, attn_bias=rb.attn_bias, in_degree=rb.in_degree,
                   out_degree=rb.out_degree, y=rb.y, user=rb.user, time_normal=rb.time_normal)
     path = os.path.join(HERE, f"model_golden_{dataset_name}.npz")
     np.savez_compressed(path, poi_logits=poi.numpy(), cat_logits=cat.numpy(), cat_target=cat_target.numpy(),
-                        loss=np.array([float(loss)], np.float64), **{"f_" + k: v.numpy() for k, v in fields.items()})
+                        loss=np.array([float(loss)], np.float64), grad_names=np.array(gnames), grad_norms=gnorm,
+                        **{"g_" + k: v for k, v in full.items()}, **{"f_" + k: v.numpy() for k, v in fields.items()})
     print("wrote", path, "poi", tuple(poi.shape), "cat", tuple(cat.shape), "loss", float(loss))
 
 
@@ -231,6 +245,17 @@ def main():
         acc, ndcg = ref_model.get_acc(y, scores)
         out.update({f"y_{tag}": y.numpy(), f"acc_{tag}": acc, f"ndcg_{tag}": ndcg,
                     f"mrr_{tag}": np.array([ref_model.MRR_metric(y, scores)], np.float64)})
+    # ---- learning-rate schedule: lr.py:18-32 `get_lr`, the reference's own method, evaluated for _step_count = 1..40 on a
+    #      plain attribute holder (the class itself cannot be constructed under torch 2.11: it passes `verbose` to
+    #      _LRScheduler.__init__, lr.py:15, which no longer exists)
+    import lr as ref_lr
+    holder = types.SimpleNamespace(warmup_updates=10, tot_updates=25, lr=2e-4, end_lr=1e-9, power=1.0,
+                                   optimizer=types.SimpleNamespace(param_groups=[{}]), _step_count=0)
+    lrs = []
+    for c in range(1, 41):
+        holder._step_count = c
+        lrs.append(ref_lr.PolynomialDecayLR.get_lr(holder)[0])
+    out["lr_by_step_count"] = np.array(lrs, np.float64)
     np.savez_compressed(os.path.join(HERE, "metrics_golden.npz"), scores=scores.numpy(), **out)
     print("wrote metrics_golden.npz", {k: np.asarray(v).reshape(-1)[:4] for k, v in out.items() if not k.startswith("y_")})
 
