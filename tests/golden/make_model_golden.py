@@ -68,10 +68,17 @@ def fill(model):
             p.copy_(golden_weights(name, tuple(p.shape)))
 
 
-def make_world_and_items(dataset_name="toyotagraph"):
+# golden cases: name -> (dataset branch, graphs, node cap, item seed).  `toyotagraph_n40`: longer trajectories (up to 40 nodes:
+# walks longer than multi_hop_max_dist, the clamp of model_fqandtoyo.py:1168-1176, more unreachable pairs)
+CASES = {"toyotagraph": ("toyotagraph", B, CAP, SEED), "gowalla_nevda": ("gowalla_nevda", B, CAP, SEED),
+         "foursquaregraph": ("foursquaregraph", B, CAP, SEED), "toyotagraph_n40": ("toyotagraph", 4, 40, 12)}
+
+
+def make_world_and_items(case="toyotagraph"):
     from mobgt_b200 import synth
+    dataset_name, nb, cap, seed = CASES[case]
     world = synth.make_world("tiny", seed=1, U=DATASETS[dataset_name][0], dataset_name=dataset_name)   # hard-coded user counts
-    items = synth.make_items(world, B, CAP, seed=SEED)
+    items = synth.make_items(world, nb, cap, seed=seed)
     return world, items
 
 
@@ -168,10 +175,12 @@ def to_ref_item(it):
                    user=t(it.user, torch.long), cat=t(it.cat, torch.long))
 
 
-def run_dataset(dataset_name, tmp, ref_model, ref_collator, ref_wrapper, mo):
+def run_dataset(case, tmp, ref_model, ref_collator, ref_wrapper, mo):
     import copy
-    world, items = make_world_and_items(dataset_name)
-    write_dataset(world, tmp, dataset_name)
+    dataset_name = CASES[case][0]
+    world, items = make_world_and_items(case)
+    if not os.path.exists(os.path.join(tmp, "dataset", dataset_name)):
+        write_dataset(world, tmp, dataset_name)
     torch.manual_seed(0)
     rm = ref_model.Graphormer(dataset_name=dataset_name, **HP).eval()
     # the shipped pickle is missing; the table only has to cover the bins the stand-in produces
@@ -212,7 +221,7 @@ def run_dataset(dataset_name, tmp, ref_model, ref_collator, ref_wrapper, mo):
     full = {n: dict(rm.named_parameters())[n].grad.numpy().copy() for n in GRAD_FULL}
     fields = dict(x=rb.x, rel_pos=rb.rel_pos, edge_input=rb.edge_input, attn_bias=rb.attn_bias, in_degree=rb.in_degree,
                   out_degree=rb.out_degree, y=rb.y, user=rb.user, time_normal=rb.time_normal)
-    path = os.path.join(HERE, f"model_golden_{dataset_name}.npz")
+    path = os.path.join(HERE, f"model_golden_{case}.npz")
     np.savez_compressed(path, poi_logits=poi.numpy(), cat_logits=cat.numpy(), cat_target=cat_target.numpy(),
                         loss=np.array([float(loss)], np.float64), grad_names=np.array(gnames), grad_norms=gnorm,
                         **{"g_" + k: v for k, v in full.items()}, **{"f_" + k: v.numpy() for k, v in fields.items()})
@@ -229,8 +238,8 @@ def main():
     import collator as ref_collator
     import wrapper as ref_wrapper
     import model_oracle as mo
-    for name in DATASETS:
-        run_dataset(name, tmp, ref_model, ref_collator, ref_wrapper, mo)
+    for case in CASES:
+        run_dataset(case, tmp, ref_model, ref_collator, ref_wrapper, mo)
     # ---- metrics (model_fqandtoyo.py:48-90 get_acc, :122-131 MRR_metric) on seeded logits; two cases: no zero target, and a
     #      zero target in the middle of the batch (the reference's loop BREAKS there, :88-89)
     g = torch.Generator().manual_seed(3)

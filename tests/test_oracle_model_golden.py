@@ -22,7 +22,7 @@ def _gen():
     return m
 
 
-DATASETS = ("toyotagraph", "gowalla_nevda", "foursquaregraph")
+DATASETS = ("toyotagraph", "gowalla_nevda", "foursquaregraph", "toyotagraph_n40")      # golden cases
 
 
 def _setup(dataset_name):
@@ -52,7 +52,7 @@ def test_oracle_forward_and_loss_equal_reference_model(dataset_name):
     """model_fqandtoyo.py:1123-1432 (eval mode) and the losses :545-550 / :1446-1471 of each dataset branch: the oracle with the
     same parameters (filled per name from the shared seeded generator) gives the reference's outputs within 1e-5 relative."""
     g, gold, world, ob = _setup(dataset_name)
-    om = mo.Graphormer(world, n_layers=g.HP["n_layers"], ffn_dim=g.HP["ffn_dim"], dataset_name=dataset_name).eval()
+    om = mo.Graphormer(world, n_layers=g.HP["n_layers"], ffn_dim=g.HP["ffn_dim"], dataset_name=g.CASES[dataset_name][0]).eval()
     with torch.no_grad():
         for name, p in om.named_parameters():
             p.copy_(g.golden_weights(name, tuple(p.shape)))
@@ -73,7 +73,7 @@ def test_oracle_gradients_equal_reference_backward(dataset_name):
     and the full gradients of the tables K2 / K4 backward produce (rel_pos / edge / edge_dis / poi_pos encoders, virtual
     distance, graph token) plus one encoder weight."""
     g, gold, world, ob = _setup(dataset_name)
-    om = mo.Graphormer(world, n_layers=g.HP["n_layers"], ffn_dim=g.HP["ffn_dim"], dataset_name=dataset_name).eval()
+    om = mo.Graphormer(world, n_layers=g.HP["n_layers"], ffn_dim=g.HP["ffn_dim"], dataset_name=g.CASES[dataset_name][0]).eval()
     with torch.no_grad():
         for name, p in om.named_parameters():
             p.copy_(g.golden_weights(name, tuple(p.shape)))

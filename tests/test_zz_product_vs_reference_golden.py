@@ -13,7 +13,7 @@ import model_oracle as mo
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
-DATASETS = ("toyotagraph", "gowalla_nevda", "foursquaregraph")
+DATASETS = ("toyotagraph", "gowalla_nevda", "foursquaregraph", "toyotagraph_n40")      # golden cases
 
 
 def _gen():
@@ -30,11 +30,11 @@ def test_product_matches_reference_golden(lib_built, dataset_name):
     gold = np.load(os.path.join(HERE, "golden", f"model_golden_{dataset_name}.npz"))
     world, items = g.make_world_and_items(dataset_name)
     # weights: the oracle module is only the carrier of the per-name seeded values (its state_dict keys are the reference's)
-    om = mo.Graphormer(world, n_layers=g.HP["n_layers"], ffn_dim=g.HP["ffn_dim"], dataset_name=dataset_name).eval()
+    om = mo.Graphormer(world, n_layers=g.HP["n_layers"], ffn_dim=g.HP["ffn_dim"], dataset_name=g.CASES[dataset_name][0]).eval()
     with torch.no_grad():
         for name, p in om.named_parameters():
             p.copy_(g.golden_weights(name, tuple(p.shape)))
-    pm = model.Graphormer(dataset_name=dataset_name, world=world, **g.HP).cuda().eval()
+    pm = model.Graphormer(dataset_name=g.CASES[dataset_name][0], world=world, **g.HP).cuda().eval()
     missing, _ = pm.load_state_dict(om.state_dict(), strict=False)
     assert not missing, missing
     pb = collator.collator_toyota(items, max_node=512, multi_hop_max_dist=20, rel_pos_max=1024, world=world)
