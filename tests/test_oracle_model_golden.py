@@ -124,3 +124,43 @@ def test_lr_schedule_equals_reference_get_lr():
         got.append(opt.param_groups[0]["lr"])
     assert np.allclose(np.array(got), gold, rtol=1e-12, atol=0)
 
+
+
+@pytest.mark.parametrize("dataset_name", DATASETS)
+def test_product_host_packing_equals_reference_collator(dataset_name):
+    """The PRODUCT's host half of collation (mobgt_b200.collator.pack_host, numpy, runs in the DataLoader workers) against the
+    fields the reference's wrapper.preprocess_item + collator_* produced: node ids, degrees (+1 shift), users, targets, time."""
+    from mobgt_b200 import collator
+    g = _gen()
+    gold = np.load(os.path.join(HERE, "golden", f"model_golden_{dataset_name}.npz"))
+    world, items = g.make_world_and_items(dataset_name)
+    hp = collator.pack_host(items)
+
+    def field(name):
+        off, shape, dts, nbytes = hp.layout[name]
+        return hp.buf[off:off + nbytes].view(np.dtype(dts)).reshape(shape)
+
+    ns, no = field("n"), field("node_off")
+    B, N = len(ns), int(ns.max())
+    assert gold["f_x"].shape[:2] == (B, N)
+
+    def padded(flat, dtype):
+        out = np.zeros((B, N), dtype)
+        for gi in range(B):
+            out[gi, :ns[gi]] = flat[no[gi]:no[gi + 1]]
+        return out
+
+    assert np.array_equal(padded(field("x_nodes"), np.int64), gold["f_x"][:, :, 0])            # 0 = pad (collator.py:29-37)
+    assert np.array_equal(padded(field("in_deg"), np.int64), gold["f_in_degree"])              # degree + 1, 0 = pad
+    assert np.array_equal(padded(field("out_deg"), np.int64), gold["f_out_degree"])
+    assert np.array_equal(field("user").reshape(-1), gold["f_user"].reshape(-1))               # uid + 1 (wrapper.py:39)
+    assert np.array_equal(field("y").reshape(-1), gold["f_y"].reshape(-1))
+    assert np.array_equal(padded(field("time_normal_nodes"), np.float32), gold["f_time_normal"][:, :, 0].astype(np.float32))
+    # the u8 edge-type plane K1 consumes == attn_edge_type of wrapper.py:49-53 (count + 2 on edges), checked through rel_pos:
+    # an edge (distance 1 -> rel_pos 2 after the collator's +1) exists exactly where the plane is non-zero, off the diagonal
+    sq, feat = field("sq_off"), field("feat8")
+    for gi in range(B):
+        n = int(ns[gi])
+        plane = feat[sq[gi]:sq[gi + 1]].reshape(n, n)
+        edge = (plane != 0) & ~np.eye(n, dtype=bool)
+        assert np.array_equal(edge, (gold["f_rel_pos"][gi, :n, :n] == 2) & ~np.eye(n, dtype=bool))
