@@ -265,6 +265,13 @@ def main():
         holder._step_count = c
         lrs.append(ref_lr.PolynomialDecayLR.get_lr(holder)[0])
     out["lr_by_step_count"] = np.array(lrs, np.float64)
+    # ---- the model's command-line flags (model_fqandtoyo.py:1618-1641): name -> (default, type)
+    import argparse
+    import json
+    ap = ref_model.Graphormer.add_model_specific_args(argparse.ArgumentParser())
+    flags = {a.dest: [a.default, type(a.default).__name__, a.type.__name__ if a.type else None]
+             for a in ap._actions if a.dest != "help"}
+    out["model_flags_json"] = np.array(json.dumps(flags, sort_keys=True))
     np.savez_compressed(os.path.join(HERE, "metrics_golden.npz"), scores=scores.numpy(), **out)
     print("wrote metrics_golden.npz", {k: np.asarray(v).reshape(-1)[:4] for k, v in out.items() if not k.startswith("y_")})
 

@@ -164,3 +164,16 @@ def test_product_host_packing_equals_reference_collator(dataset_name):
         plane = feat[sq[gi]:sq[gi + 1]].reshape(n, n)
         edge = (plane != 0) & ~np.eye(n, dtype=bool)
         assert np.array_equal(edge, (gold["f_rel_pos"][gi, :n, :n] == 2) & ~np.eye(n, dtype=bool))
+
+
+def test_model_flags_equal_reference():
+    """Graphormer.add_model_specific_args (model_fqandtoyo.py:1618-1641): same flag names, defaults and types as the reference's
+    own static method produced in the build container."""
+    import argparse
+    import json
+    from mobgt_b200.model import Graphormer
+    gold = json.loads(str(np.load(os.path.join(HERE, "golden", "metrics_golden.npz"))["model_flags_json"]))
+    ap = Graphormer.add_model_specific_args(argparse.ArgumentParser())
+    mine = {a.dest: [a.default, type(a.default).__name__, a.type.__name__ if a.type else None]
+            for a in ap._actions if a.dest != "help"}
+    assert json.loads(json.dumps(mine, sort_keys=True)) == gold
