@@ -224,6 +224,8 @@ def run_dataset(case, tmp, ref_model, ref_collator, ref_wrapper, mo):
     path = os.path.join(HERE, f"model_golden_{case}.npz")
     np.savez_compressed(path, poi_logits=poi.numpy(), cat_logits=cat.numpy(), cat_target=cat_target.numpy(),
                         loss=np.array([float(loss)], np.float64), grad_names=np.array(gnames), grad_norms=gnorm,
+                        state_shapes_json=np.array(__import__("json").dumps({k: list(v.shape) for k, v in rm.state_dict().items()},
+                                                                            sort_keys=True)),
                         **{"g_" + k: v for k, v in full.items()}, **{"f_" + k: v.numpy() for k, v in fields.items()})
     print("wrote", path, "poi", tuple(poi.shape), "cat", tuple(cat.shape), "loss", float(loss))
 

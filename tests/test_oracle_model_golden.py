@@ -177,3 +177,21 @@ def test_model_flags_equal_reference():
     mine = {a.dest: [a.default, type(a.default).__name__, a.type.__name__ if a.type else None]
             for a in ap._actions if a.dest != "help"}
     assert json.loads(json.dumps(mine, sort_keys=True)) == gold
+
+
+@pytest.mark.parametrize("dataset_name", DATASETS[:3])
+def test_product_state_dict_keys_load_from_reference(dataset_name):
+    """Every parameter of the PRODUCT model exists in the reference model's state_dict under the same name with the same shape
+    (so a reference checkpoint loads into it; the reference has more entries — modules its live forward never calls)."""
+    import json
+    from mobgt_b200 import model
+    g = _gen()
+    gold = np.load(os.path.join(HERE, "golden", f"model_golden_{dataset_name}.npz"))
+    ref_shapes = json.loads(str(gold["state_shapes_json"]))
+    world, _ = g.make_world_and_items(dataset_name)
+    pm = model.Graphormer(dataset_name=g.CASES[dataset_name][0], world=world, **g.HP)        # CPU construction: no kernels involved
+    mine = {k: list(v.shape) for k, v in pm.named_parameters()}
+    assert len(mine) > 60
+    for k, shp in mine.items():
+        assert k in ref_shapes, k
+        assert ref_shapes[k] == shp, (k, ref_shapes[k], shp)
