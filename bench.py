@@ -151,7 +151,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warm = max(1, min(args.steps, 12)), max(1, min(args.warmup, 2))
+    # exactly K timed steps after W warm-up steps, each a bounded 4-graph sample (~1 s on 16 cores): K = 20, W = 5 is ~25 s
+    steps, warm = max(1, args.steps), max(1, args.warmup)
     r = cpu_reference_rate(args.workload, steps, warm)
     sample = (f"{r['sample_graphs']} graphs/step of the {args.workload} batch, {steps} timed steps after {warm} warm-up; "
               f"compiled algos.pyx (oracle/_ref) + CPU restatement of collator/model_fqandtoyo, fwd+bwd+AdamW")
