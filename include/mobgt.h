@@ -67,12 +67,14 @@ int32_t mobgt_device_check(void);
  *   maxdist   i32 [G]             max(M) per graph (wrapper.py:58)              (out)
  * shift = 0 gives the raw algos.pyx values, shift = 1 the collated ones
  * (pad_rel_pos_unsqueeze / pad_3d_unsqueeze "+1", collator.py:76-93).
+ * hops = bytes per edge_in row (a multiple of 4, <= 32); dk = multi_hop_max_dist, the hop slots actually
+ * walked (1 <= dk <= hops; the reference's default is 5, entry.py / data.py:204): slots [dk, hops) stay "no hop".
  * gids (i32 [G_launch], may be NULL = identity) selects which graphs this launch covers;
  * n_max_host is the largest n among them (chooses the cluster size / shared-memory plan).
  * ------------------------------------------------------------------------------------------ */
 int32_t mobgt_apsp_edge_input(const uint8_t *feat, const int32_t *n, const int64_t *sq_off,
                               const int32_t *gids, int32_t G_launch, int32_t n_max_host,
-                              int32_t hops, int32_t shift,
+                              int32_t hops, int32_t dk, int32_t shift,
                               int16_t *dist, int16_t *path, uint8_t *edge_in, int32_t *maxdist,
                               void *stream);
 
@@ -104,7 +106,8 @@ int32_t mobgt_poi_pos(const int32_t *x, const int32_t *n, const int64_t *sq_off,
  *   padding columns are masked inside the attention kernel from the sequence lengths.
  *   tables: R [512,H] rel_pos_encoder, Ppos [bins,H] poi_pos_encoder, E [128,H] edge_encoder,
  *           W [>=hops*H*H] edge_dis_encoder (viewed [k,h',h]), tvd [H] graph_token_virtual_distance.
- *   hops is the hop-slot count of edge_in (a multiple of 4, as written by K1) and the clamp of the mean.
+ *   hops is the byte stride of an edge_in row (a multiple of 4, as written by K1); dk = multi_hop_max_dist is the number of
+ *   live hop slots and the clamp of the mean (sp = clamp(M, 1, dk), model_fqandtoyo.py:1168-1174); 1 <= dk <= hops.
  *   forward workspace: mobgt_bias_fwd_workspace_bytes() (the E.W table [hops,128,H] and the rel_pos-keyed table RL [512,H]);
  *   backward workspace: mobgt_bias_bwd_workspace_bytes().
  * Backward: dBias -> dR [512,H], dPpos [bins,H], dE [128,H], dW [hops*H*H], dtvd [H]  (all overwritten).
@@ -115,13 +118,13 @@ int32_t mobgt_poi_pos(const int32_t *x, const int32_t *n, const int64_t *sq_off,
 /* bytes of `workspace` mobgt_bias_fwd needs; < 0 on bad arguments */
 int64_t mobgt_bias_fwd_workspace_bytes(int32_t hops, int32_t H);
 int32_t mobgt_bias_fwd(const int32_t *n, const int64_t *sq_off, const int16_t *rel_pos, const int16_t *poi_pos,
-                       const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t H,
+                       const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t dk, int32_t H,
                        int32_t rel_pos_max, int32_t num_bins, const float *R, const float *Ppos, const float *E,
                        const float *W, const float *tvd, void *workspace, void *out, int32_t out_dtype, void *stream);
 /* bytes of `workspace` mobgt_bias_bwd needs (per-CTA partial histograms + totals); < 0 on bad arguments */
 int64_t mobgt_bias_bwd_workspace_bytes(int32_t T, int32_t hops, int32_t num_bins);
 int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const int16_t *rel_pos, const int16_t *poi_pos,
-                       const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t H,
+                       const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t dk, int32_t H,
                        int32_t rel_pos_max, int32_t num_bins, const void *dBias, int32_t dbias_dtype, int32_t n_layers,
                        int64_t layer_stride, const float *E, const float *W, void *workspace, int64_t workspace_bytes,
                        float *dR, float *dPpos, float *dE, float *dW, float *dtvd, void *stream);
@@ -244,6 +247,30 @@ int32_t mobgt_selftest_umma(const void *A, const void *B, int32_t N, int32_t K, 
  *                    the activation fused with the bias gradient of the Linear that produced h.  Workspace as mobgt_colsum. */
 int32_t mobgt_gelu_bwd_colsum(const void *da_bf16, const void *h_bf16, int32_t N, int32_t C, void *dh_bf16, float *dbias,
                               void *workspace, int64_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K7 — training losses over the logits.  logits: f32 or bf16 [B, V] with row_stride elements between
+ * rows; target: i64 [B] class ids.  Forward: ONE read of the logits; backward: one read + one write; `grad_out` is the
+ * upstream gradient of the scalar loss in DEVICE memory (f32 [1]) so the call is CUDA-graph capturable.  Partials are merged
+ * in a fixed order (bitwise reproducible).  workspace: mobgt_loss_workspace_bytes(B, V).
+ *   lsm_nll: mean over the rows with target != ignore_index of -log_softmax(logits)[target]
+ *            = log_softmax (model_fqandtoyo.py:1425) + NLLLoss(ignore_index=0) (data.py:165; model_fqandtoyo.py:1470-1471).
+ *            lse f32 [B] (saved for backward), loss f32 [2] = {loss, number of live rows}.
+ *   gtl:     GradientTailLoss(alpha, beta = 1, k = 1), model_fqandtoyo.py:545-550: mean over [B, V] of
+ *            -alpha (1-p) log p on the target class and -p log(1-p) elsewhere, p = sigmoid(logit).  loss f32 [1].
+ * dlogits has the dtype of logits.
+ * ------------------------------------------------------------------------------------------ */
+int64_t mobgt_loss_workspace_bytes(int32_t B, int32_t V);
+int32_t mobgt_lsm_nll_fwd(const void *logits, int32_t dtype, int64_t row_stride, const int64_t *target,
+                          int64_t ignore_index, int32_t B, int32_t V, void *workspace, int64_t workspace_bytes,
+                          float *lse, float *loss, void *stream);
+int32_t mobgt_lsm_nll_bwd(const void *logits, int32_t dtype, int64_t row_stride, const int64_t *target,
+                          int64_t ignore_index, int32_t B, int32_t V, const float *lse, const float *loss,
+                          const float *grad_out, void *dlogits, int64_t d_row_stride, void *stream);
+int32_t mobgt_gtl_fwd(const void *logits, int32_t dtype, int64_t row_stride, const int64_t *target, float alpha,
+                      int32_t B, int32_t V, void *workspace, int64_t workspace_bytes, float *loss, void *stream);
+int32_t mobgt_gtl_bwd(const void *logits, int32_t dtype, int64_t row_stride, const int64_t *target, float alpha,
+                      int32_t B, int32_t V, const float *grad_out, void *dlogits, int64_t d_row_stride, void *stream);
 
 /* Debug hook: register (NULL: clear) a device buffer of 256 int64; thread 0 of one CTA of mobgt_attn_fwd / mobgt_attn_bwd then
  * stamps clock64() at its pipeline stages (scripts/timeline.py). */

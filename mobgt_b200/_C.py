@@ -23,15 +23,15 @@ SIGNATURES = {
     "mobgt_last_error": [ctypes.c_char_p, ctypes.c_size_t],
     "mobgt_device_check": [],
     "mobgt_launch_count": [c_p],
-    "mobgt_apsp_edge_input": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p],
+    "mobgt_apsp_edge_input": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p],
     "mobgt_gen_edge_input": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p],
     "mobgt_degrees": [c_p, c_p, c_p, c_p, c_i32, c_i32, c_p, c_p, c_p],
     "mobgt_poi_pos": [c_p, c_p, c_p, c_p, c_p, c_f32, c_i32, c_i32, c_i32, c_p, c_p],
-    "mobgt_bias_fwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p,
+    "mobgt_bias_fwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p,
                        c_p, c_i32, c_p],
     "mobgt_bias_fwd_workspace_bytes": [c_i32, c_i32],
     "mobgt_bias_bwd_workspace_bytes": [c_i32, c_i32, c_i32],
-    "mobgt_bias_bwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_i32, c_i64, c_p,
+    "mobgt_bias_bwd": [c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_i32, c_i64, c_p,
                        c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p],
     "mobgt_attn_fwd": [c_p, c_p, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, ctypes.c_uint64, c_p,
                        c_p, c_p, c_p],
@@ -51,6 +51,11 @@ SIGNATURES = {
     "mobgt_colsum_workspace_bytes": [c_i32, c_i32],
     "mobgt_colsum": [c_p, c_i32, c_i64, c_i32, c_i32, c_p, c_p, c_i64, c_p],
     "mobgt_gelu_bwd_colsum": [c_p, c_p, c_i32, c_i32, c_p, c_p, c_p, c_i64, c_p],
+    "mobgt_loss_workspace_bytes": [c_i32, c_i32],
+    "mobgt_lsm_nll_fwd": [c_p, c_i32, c_i64, c_p, c_i64, c_i32, c_i32, c_p, c_i64, c_p, c_p, c_p],
+    "mobgt_lsm_nll_bwd": [c_p, c_i32, c_i64, c_p, c_i64, c_i32, c_i32, c_p, c_p, c_p, c_p, c_i64, c_p],
+    "mobgt_gtl_fwd": [c_p, c_i32, c_i64, c_p, c_f32, c_i32, c_i32, c_p, c_i64, c_p, c_p],
+    "mobgt_gtl_bwd": [c_p, c_i32, c_i64, c_p, c_f32, c_i32, c_i32, c_p, c_p, c_i64, c_p],
     "mobgt_debug_set_timeline": [c_p],
     "mobgt_selftest_umma": [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p],
 }

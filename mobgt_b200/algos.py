@@ -29,11 +29,22 @@ def pack_graphs(n_host):
     return n, sq, no
 
 
-def apsp_edge_input_packed(feat, n_dev, sq_off_dev, n_host, hops, shift=0, want_path=False, want_edges=True):
+def hop_stride(multi_hop_max_dist):
+    """Bytes per packed edge_in row for a given multi_hop_max_dist (1..32): the next multiple of 4 (the kernels move walk
+    bytes as 32-bit words); the slots past multi_hop_max_dist are never walked and stay "no hop"."""
+    dk = int(multi_hop_max_dist)
+    if not 1 <= dk <= 32:
+        raise ValueError(f"multi_hop_max_dist={dk}: libmobgt supports 1..32 hop slots")
+    return (dk + 3) // 4 * 4
+
+
+def apsp_edge_input_packed(feat, n_dev, sq_off_dev, n_host, hops, shift=0, want_path=False, want_edges=True, dk=None):
     """Batched K1 on device-resident packed graphs.
 
     feat u8 [sum n^2] (0 = no edge) ; n_dev i32 [G] ; sq_off_dev i64 [G(+1)] ; n_host: numpy copy of n
+    hops: bytes per edge_in row (multiple of 4); dk: hop slots walked (multi_hop_max_dist, default = hops).
     Returns dict(dist i16, path i16|None, edge_in u8 [sum n^2, hops]|None, maxdist i32 [G])."""
+    dk = int(hops if dk is None else dk)
     _C.require_cuda()
     dev = feat.device
     G = int(n_dev.numel())
@@ -59,7 +70,7 @@ def apsp_edge_input_packed(feat, n_dev, sq_off_dev, n_host, hops, shift=0, want_
         else:
             gids = torch.from_numpy(sel.astype(np.int32)).to(dev, non_blocking=True)
         _C.call("mobgt_apsp_edge_input", _C.ptr(feat), _C.ptr(n_dev), _C.ptr(sq_off_dev), _C.ptr(gids),
-                int(len(sel)), int(n_host[sel].max()), int(hops), int(shift),
+                int(len(sel)), int(n_host[sel].max()), int(hops), dk, int(shift),
                 _C.ptr(dist), _C.ptr(path), _C.ptr(edge_in), _C.ptr(maxdist), s)
     return dict(dist=dist, path=path, edge_in=edge_in, maxdist=maxdist)
 

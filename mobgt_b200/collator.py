@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _C
-from .algos import apsp_edge_input_packed
+from .algos import apsp_edge_input_packed, hop_stride
 
 
 def _to_np(a, dtype=None):
@@ -128,8 +128,10 @@ class PackedLoader:
         self._next = self._pull()
 
     def __iter__(self):
-        while self._next is not None:
-            b = self._next
+        while True:
+            b = self.current()        # waits for the side stream's event: the batch is safe to use on the caller's stream
+            if b is None:
+                return
             yield b
             if self._next is b:       # the consumer did not call advance() itself
                 self.advance()
@@ -165,6 +167,64 @@ class Batch1:
 
     def __len__(self):
         return int(self.B)
+
+    @classmethod
+    def from_dense(cls, ref, multi_hop_max_dist=20, rel_pos_max=1024, device=None):
+        """A reference-collated dense batch (collator.py:149-215: padded int64 / fp32 tensors) -> the packed Batch1 the
+        kernels consume.  Real nodes are the leading `x != 0` positions of every graph (pad_2d_squeeze, collator.py:29-37);
+        everything is sliced to the real n_g x n_g block, so the padding the reference wrote is dropped, not copied.  Used
+        when a caller hands `Graphormer.forward` the output of the reference's own collator."""
+        from .algos import hop_stride
+        dev = torch.device(device) if device is not None else ref.x.device
+        t = lambda a: a.to(dev)
+        x = t(ref.x)
+        B, N = int(x.shape[0]), int(x.shape[1])
+        nm = x.reshape(B, N, -1)[:, :, 0] != 0                                   # [B,N] real-node mask
+        n = nm.sum(1).to(torch.int32)
+        if bool(((torch.arange(N, device=dev).view(1, N) < n.view(B, 1)) != nm).any()):
+            raise ValueError("Batch1.from_dense: real nodes must occupy the leading positions of every graph")
+        pm = nm.unsqueeze(2) & nm.unsqueeze(1)                                   # [B,N,N] real-pair mask
+        dk = int(multi_hop_max_dist)
+        hops = hop_stride(dk)
+        nl = n.long()
+        zero = torch.zeros(1, dtype=torch.long, device=dev)
+        sq_off = torch.cat([zero, torch.cumsum(nl * nl, 0)])
+        node_off = torch.cat([zero, torch.cumsum(nl, 0)])
+        tok_off = (node_off + torch.arange(B + 1, device=dev)).to(torch.int32)
+        cells, Nn = int(sq_off[-1]), int(node_off[-1])
+        rel = t(ref.rel_pos)[pm]
+        ei = t(ref.edge_input)                                                   # [B,N,N,Dmax,1]
+        Dm = min(int(ei.shape[3]), dk)
+        edge_in8 = torch.zeros(cells, hops, dtype=torch.uint8, device=dev)
+        edge_in8[:, :Dm] = ei[..., 0][pm][:, :Dm].to(torch.uint8)
+        aet = t(ref.attn_edge_type)
+        feat8 = aet.reshape(B, aet.shape[1], aet.shape[2], -1)[:, :N, :N, 0][pm].to(torch.uint8)
+        g_of_node = torch.repeat_interleave(torch.arange(B, device=dev), nl)
+        pos = torch.arange(Nn, device=dev) - node_off[:-1][g_of_node] + 1
+        rows = torch.arange(Nn, device=dev) + g_of_node + 1
+        Ntok = Nn + B
+        tok_graph = torch.zeros(Ntok, dtype=torch.int32, device=dev)
+        tok_pos = torch.zeros(Ntok, dtype=torch.int32, device=dev)
+        tok_graph[rows] = g_of_node.int()
+        tok_pos[rows] = pos.int()
+        tok_graph[tok_off[:-1].long()] = torch.arange(B, device=dev, dtype=torch.int32)
+        tn = t(ref.time_normal).reshape(B, N)[nm].float()
+        maxdist = torch.zeros(B, dtype=torch.int32, device=dev)
+        if cells:
+            gcell = torch.repeat_interleave(torch.arange(B, device=dev), nl * nl)
+            maxdist = torch.zeros(B, dtype=torch.long, device=dev).scatter_reduce(0, gcell, rel - 1, "amax").int()
+        opt = lambda name: (t(getattr(ref, name)).reshape(B, N)[nm].int() if getattr(ref, name, None) is not None
+                            else torch.zeros(Nn, dtype=torch.int32, device=dev))
+        idx = getattr(ref, "idx", None)
+        b = cls(B=B, N=int(n.max()) if B else 0, hops=hops, dk=dk, rel_pos_max=int(rel_pos_max), n_host=n.cpu().numpy(),
+                h2d_bytes=0, n=n, sq_off=sq_off, node_off=node_off, tok_off=tok_off, tok_graph=tok_graph, tok_pos=tok_pos,
+                feat8=feat8, x_nodes=x.reshape(B, N, -1)[:, :, 0][nm].int(), slot=(tn * 48).long().int(), time_nodes=opt("time"),
+                time_normal_nodes=tn, cat_nodes=opt("cat"), in_deg=t(ref.in_degree)[nm].int(), out_deg=t(ref.out_degree)[nm].int(),
+                user=t(ref.user).long().view(B, 1), y=t(ref.y).long().view(B),
+                idx=t(torch.as_tensor(idx)).long() if idx is not None else torch.arange(B, device=dev),
+                node_rows=rows, rel_pos16=rel.to(torch.int16), poi_pos16=t(ref.poi_pos)[pm].to(torch.int16), edge_in8=edge_in8,
+                maxdist=maxdist, path16=None)
+        return b
 
     def build_plans(self):
         """Fixed summation orders of the deterministic segmented scatter-adds (K4 backward): a stable sort of every key
@@ -229,7 +289,7 @@ class Batch1:
             return out
         if name == "edge_input":
             # hop axis = min(multi_hop_max_dist, max_g max(M_g))  (collator.py:323,366)
-            dmax = int(min(self.hops, int(self.maxdist.max()))) if B else 0
+            dmax = int(min(getattr(self, "dk", self.hops), int(self.maxdist.max()))) if B else 0
             out = torch.zeros(B, N, N, dmax, 1, dtype=torch.long, device=dev)
             g, i, j = self._sq_index()
             out[g, i, j] = self.edge_in8[:, :dmax].long().unsqueeze(-1)
@@ -306,6 +366,13 @@ def pack_host(items, max_node=512):
     eg = np.repeat(np.arange(B), ecnt)                    # graph of every edge
     indeg = np.bincount(no[:-1][eg] + ei[0], minlength=Nn).astype(np.int32)   # wrapper.py:97: adj.sum(dim=1)
     outdeg = np.bincount(no[:-1][eg] + ei[1], minlength=Nn).astype(np.int32)  # wrapper.py:98: adj.sum(dim=0)
+    # the reference indexes nn.Embedding(128, ...) tables with these (edge_encoder :784, in/out_degree_encoder :861-862) and
+    # raises IndexError past row 127; fail the same way here instead of wrapping in uint8 / reading out of bounds on the device
+    if len(ea) and (ea.min() < 0 or ea.max() + 3 >= 128):
+        raise IndexError(f"edge_attr {int(ea.max())}: edge_input index edge_attr+3 must stay below the 128 rows of edge_encoder")
+    if Nn and max(int(indeg.max()), int(outdeg.max())) + 1 >= 128:
+        raise IndexError(f"node degree {max(int(indeg.max()), int(outdeg.max()))}: degree+1 must stay below the 128 rows of "
+                         "in_degree_encoder / out_degree_encoder")
 
     def cat_field(name, dtype):
         return np.concatenate([_to_np(getattr(it, name)).reshape(-1) for it in items]).astype(dtype, copy=False)
@@ -376,10 +443,12 @@ def collate_from_host(hp, world=None, latlon_dev=None, multi_hop_max_dist=20, re
     dev = torch.device(device)
     views = _upload_pack(hp, dev)
     ns = hp.ns.numpy() if isinstance(hp.ns, torch.Tensor) else hp.ns
-    b = Batch1(B=hp.B, N=hp.N, hops=int(multi_hop_max_dist), rel_pos_max=int(rel_pos_max), n_host=ns, h2d_bytes=0, **views)
+    dk = int(multi_hop_max_dist)
+    hops = hop_stride(dk)                  # bytes per edge_in8 row; slots [dk, hops) are padding
+    b = Batch1(B=hp.B, N=hp.N, hops=hops, dk=dk, rel_pos_max=int(rel_pos_max), n_host=ns, h2d_bytes=0, **views)
     b.h2d_bytes = int(sum(v.numel() * v.element_size() for v in views.values()))
     b.build_plans()
-    k1 = apsp_edge_input_packed(b.feat8, b.n, b.sq_off, ns, hops=int(multi_hop_max_dist), shift=1, want_path=want_path)
+    k1 = apsp_edge_input_packed(b.feat8, b.n, b.sq_off, ns, hops=hops, shift=1, want_path=want_path, dk=dk)
     b.rel_pos16, b.edge_in8, b.maxdist, b.path16 = k1["dist"], k1["edge_in"], k1["maxdist"], k1["path"]
     b.poi_pos16 = torch.empty(hp.cells, dtype=torch.int16, device=dev)
     if world is not None:

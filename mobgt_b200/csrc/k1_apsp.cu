@@ -37,7 +37,8 @@ struct K1Params {
     const int32_t *n;
     const int64_t *sq_off;
     const int32_t *gids;
-    int hops;
+    int hops;   // byte stride of one edge_in row (multiple of 4)
+    int dk;     // hop slots actually walked: multi_hop_max_dist (collator.py:323); slots [dk, hops) stay "no hop"
     int shift;
     int16_t *dist;
     int16_t *path;
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(512) k1_apsp_kernel(const K1Params p, const in
             for (int w = 0; w < hopw; ++w) stw[w] = none4;
             if (jl < wc && !(Xsh[(size_t)i * W + jl] & kNoWalk)) {
                 int cur = i;
-                for (int h = 0; h < hops; ++h) {
+                for (int h = 0; h < p.dk; ++h) {
                     const int nx = Xsh[(size_t)cur * W + jl] & (kNoWalk - 1);
                     st[lane * hops + h] = (uint8_t)(__ldg(feat + (size_t)cur * n + nx) + p.shift);
                     cur = nx;
@@ -351,7 +352,7 @@ using namespace mobgt;
 
 extern "C" int32_t mobgt_apsp_edge_input(const uint8_t *feat, const int32_t *n, const int64_t *sq_off,
                                          const int32_t *gids, int32_t G_launch, int32_t n_max_host, int32_t hops,
-                                         int32_t shift, int16_t *dist, int16_t *path, uint8_t *edge_in,
+                                         int32_t dk, int32_t shift, int16_t *dist, int16_t *path, uint8_t *edge_in,
                                          int32_t *maxdist, void *stream) {
     MOBGT_REQUIRE(feat && n && sq_off && dist && maxdist, MOBGT_ERR_NULL, "mobgt_apsp_edge_input: null pointer");
     MOBGT_REQUIRE(G_launch >= 0, MOBGT_ERR_BAD_SHAPE, "mobgt_apsp_edge_input: G_launch=%d", G_launch);
@@ -361,8 +362,9 @@ extern "C" int32_t mobgt_apsp_edge_input(const uint8_t *feat, const int32_t *n, 
     if (edge_in) {
         MOBGT_REQUIRE(hops >= 4 && hops <= MOBGT_MAX_HOPS && hops % 4 == 0, MOBGT_ERR_UNSUPPORTED,
                       "mobgt_apsp_edge_input: hops=%d must be a multiple of 4 in [4,%d]", hops, MOBGT_MAX_HOPS);
+        MOBGT_REQUIRE(dk >= 1 && dk <= hops, MOBGT_ERR_BAD_SHAPE, "mobgt_apsp_edge_input: dk=%d outside [1, hops=%d]", dk, hops);
     } else {
-        hops = 4;
+        hops = dk = 4;
     }
     if (G_launch == 0) return MOBGT_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -372,7 +374,7 @@ extern "C" int32_t mobgt_apsp_edge_input(const uint8_t *feat, const int32_t *n, 
     const int C = pick_cluster(n_max_host, with_path, hops, &nt, &smem);
     MOBGT_REQUIRE(C > 0, MOBGT_ERR_UNSUPPORTED, "mobgt_apsp_edge_input: no shared-memory plan for n=%d", n_max_host);
 
-    K1Params p{feat, n, sq_off, gids, hops, shift, dist, path, edge_in, maxdist};
+    K1Params p{feat, n, sq_off, gids, hops, dk, shift, dist, path, edge_in, maxdist};
     auto kern = with_path ? k1_apsp_kernel<true> : k1_apsp_kernel<false>;
     MOBGT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};

@@ -36,6 +36,7 @@ struct K2Common {
     const int16_t *poi_pos;  // packed [sum n^2]
     const uint8_t *edge_in;  // packed [sum n^2, hops]  (e+1)
     int B, T, Tp, hops, rel_pos_max;
+    int dk;                  // multi_hop_max_dist: walk bytes [dk, hops) are padding (0); sp = clamp(M, 1, dk)
 };
 
 constexpr int kDomEdge = 4;    // edge count 1 -> attn_edge_type 3 (wrapper.py:49-53) -> +1 (collator.py:86-93): "one transition"
@@ -53,7 +54,7 @@ __host__ __device__ __forceinline__ int expected_walk(int rp, int hops) {
 // RL is the whole rel_pos-keyed part of the bias of a pair whose walk is the EXPECTED one: L(rp) hops that all carry the
 // dominant edge feature (a single transition).  -inf where rp-1 >= rel_pos_max (collator.py:354-358).
 __global__ void k2_prep_kernel(const float *__restrict__ E, const float *__restrict__ W, const float *__restrict__ R, int hops,
-                               int rel_pos_max, float *__restrict__ EW, float *__restrict__ RL) {
+                               int dk, int rel_pos_max, float *__restrict__ EW, float *__restrict__ RL) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int nEW = hops * kEdgeVocab * kH;
     if (idx < nEW) {
@@ -65,7 +66,7 @@ __global__ void k2_prep_kernel(const float *__restrict__ E, const float *__restr
     } else if (idx < nEW + kRelRows * kH) {
         const int j = idx - nEW;
         const int h = j % kH, rp = j / kH;
-        const int L = expected_walk(rp, hops);
+        const int L = expected_walk(rp, dk);
         float ps = 0.f;
         for (int k = 0; k < L; ++k) {
             float acc = 0.f;
@@ -74,7 +75,7 @@ __global__ void k2_prep_kernel(const float *__restrict__ E, const float *__restr
             ps += acc;
         }
         const int M = rp - 1;
-        const float inv = 1.0f / (float)min(max(M, 1), hops);
+        const float inv = 1.0f / (float)min(max(M, 1), dk);
         RL[j] = (M >= rel_pos_max) ? -INFINITY : R[j] + ps * inv;
     }
 }
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(512, 2) k2_bias_fwd_kernel(const K2Common c, c
                     continue;
                 }
                 const int rk = min(max(rp[s], 0), kRelRows - 1);
-                const int L = expected_walk(rk, c.hops);
+                const int L = expected_walk(rk, c.dk);
                 const uint4 x0 = *reinterpret_cast<const uint4 *>(XW + L * 8), x1 = *reinterpret_cast<const uint4 *>(XW + L * 8 + 4);
                 const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                 uint32_t any = 0u;
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(512, 2) k2_bias_fwd_kernel(const K2Common c, c
                             }
                         }
                     }
-                    const float inv = 1.0f / (float)min(max(rk - 1, 1), c.hops);
+                    const float inv = 1.0f / (float)min(max(rk - 1, 1), c.dk);
 #pragma unroll
                     for (int h = 0; h < 8; ++h) acc[s][h] += corr[h] * inv;
                 }
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
 #pragma unroll
                 for (int q = 0; q < 8; ++q) ew[q] = q < hopw ? __ldg(ei + q) : 0u;
                 const int rk = min(max(rp, 0), kRelRows - 1);
-                const int L = expected_walk(rk, c.hops);
+                const int L = expected_walk(rk, c.dk);
                 const int row = (rk == 511) ? pl.Rrows - 1 : (rk < pl.Rrows - 1 ? rk : -1);
                 if (rk - 1 < c.rel_pos_max) {                        // -inf entries carry no gradient
                     info = (row < 0 ? trashR : (uint32_t)row) | ((uint32_t)min(max(pp, 0), num_bins - 1) << 16);
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
             if (!(ent & (1u << 14))) continue;
             const uint32_t cd = lds_u32(s_cdev + (uint32_t)b * 4u);
             const int L = (cd >> 2) & 63, nd = cd & 3;
-            const float dinv = d * invT[(ent & (1u << 13)) ? c.hops : max(L, 1)];
+            const float dinv = d * invT[(ent & (1u << 13)) ? c.dk : max(L, 1)];
             if (nd <= 2) {
                 for (int j = 0; j < nd; ++j) {
                     const uint32_t en = (cd >> (8 + 12 * j)) & 4095u;
@@ -545,7 +546,7 @@ __global__ void k2_bias_bwd_reduce_kernel(const float *__restrict__ partial, int
 
 // totals -> dR, dPpos, dt, and the full dEW[k][v][h] (which already holds the global rare-path atomics):
 //   dEW[k][v] += EWsmall[k][v] (v < 16) ;  dEW[k][dom] += sum_{rp : L(rp) > k} dRL[rp] / sp(rp)   (one warp per (k, h))
-__global__ void k2_bias_bwd_scatter_kernel(const float *__restrict__ tot, const K2BwdPlan pl, int hops, int num_bins,
+__global__ void k2_bias_bwd_scatter_kernel(const float *__restrict__ tot, const K2BwdPlan pl, int hops, int dk, int num_bins,
                                            float *__restrict__ dEWfull, float *__restrict__ dR, float *__restrict__ dP,
                                            float *__restrict__ dt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -567,7 +568,7 @@ __global__ void k2_bias_bwd_scatter_kernel(const float *__restrict__ tot, const 
         float s = 0.f;
         for (int row = lane; row < pl.Rrows; row += 32) {
             const int rp = (row == pl.Rrows - 1) ? 511 : row;
-            if (expected_walk(rp, hops) > k) s += tR[row * kH + hh] / (float)min(max(rp - 1, 1), hops);
+            if (expected_walk(rp, dk) > k) s += tR[row * kH + hh] / (float)min(max(rp - 1, 1), dk);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -608,7 +609,7 @@ extern "C" int64_t mobgt_bias_fwd_workspace_bytes(int32_t hops, int32_t H) {
 }
 
 extern "C" int32_t mobgt_bias_fwd(const int32_t *n, const int64_t *sq_off, const int16_t *rel_pos, const int16_t *poi_pos,
-                                  const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t H,
+                                  const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t dk, int32_t H,
                                   int32_t rel_pos_max, int32_t num_bins, const float *R, const float *Ppos, const float *E,
                                   const float *W, const float *tvd, void *workspace, void *out, int32_t out_dtype,
                                   void *stream) {
@@ -617,6 +618,7 @@ extern "C" int32_t mobgt_bias_fwd(const int32_t *n, const int64_t *sq_off, const
     MOBGT_REQUIRE(H == kH, MOBGT_ERR_UNSUPPORTED, "mobgt_bias_fwd: num_heads=%d (only 8 is built)", H);
     MOBGT_REQUIRE(hops >= 4 && hops <= MOBGT_MAX_HOPS && hops % 4 == 0, MOBGT_ERR_BAD_SHAPE,
                   "mobgt_bias_fwd: hops=%d must be a multiple of 4 in [4,%d]", hops, MOBGT_MAX_HOPS);
+    MOBGT_REQUIRE(dk >= 1 && dk <= hops, MOBGT_ERR_BAD_SHAPE, "mobgt_bias_fwd: dk=%d outside [1, hops=%d]", dk, hops);
     MOBGT_REQUIRE(num_bins >= 1 && num_bins <= 1024, MOBGT_ERR_BAD_SHAPE, "mobgt_bias_fwd: num_bins=%d", num_bins);
     MOBGT_REQUIRE(T >= 2 && Tp >= T && Tp % 8 == 0, MOBGT_ERR_BAD_SHAPE, "mobgt_bias_fwd: T=%d Tp=%d", T, Tp);
     MOBGT_REQUIRE(out_dtype == MOBGT_F32 || out_dtype == MOBGT_BF16, MOBGT_ERR_BAD_DTYPE, "mobgt_bias_fwd: dtype");
@@ -625,9 +627,9 @@ extern "C" int32_t mobgt_bias_fwd(const int32_t *n, const int64_t *sq_off, const
     float *EW = static_cast<float *>(workspace);                 // [hops][128][8] then RL [512][8]
     const int tabn = hops * kEdgeVocab * kH;
     float *RL = EW + tabn;
-    k2_prep_kernel<<<ceil_div(tabn + kRelRows * kH, 256), 256, 0, s>>>(E, W, R, hops, rel_pos_max, EW, RL);
+    k2_prep_kernel<<<ceil_div(tabn + kRelRows * kH, 256), 256, 0, s>>>(E, W, R, hops, dk, rel_pos_max, EW, RL);
     MOBGT_LAUNCH_OK("k2_prep_kernel");
-    K2Common c{n, sq_off, rel_pos, poi_pos, edge_in, B, T, Tp, hops, rel_pos_max};
+    K2Common c{n, sq_off, rel_pos, poi_pos, edge_in, B, T, Tp, hops, rel_pos_max, dk};
     const size_t smem = (size_t)(kRelRows * kH + num_bins * kH + (hops + 1) * 8) * sizeof(float);
     const int tiles_total = ceil_div(T * (Tp / 2), 512) * B;
     dim3 grid((unsigned)min(2 * kNumSMs, tiles_total));
@@ -660,7 +662,7 @@ extern "C" int64_t mobgt_bias_bwd_workspace_bytes(int32_t T, int32_t hops, int32
 }
 
 extern "C" int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const int16_t *rel_pos, const int16_t *poi_pos,
-                                  const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t H,
+                                  const uint8_t *edge_in, int32_t B, int32_t T, int32_t Tp, int32_t hops, int32_t dk, int32_t H,
                                   int32_t rel_pos_max, int32_t num_bins, const void *dBias, int32_t dbias_dtype,
                                   int32_t n_layers, int64_t layer_stride, const float *E, const float *W,
                                   void *workspace, int64_t workspace_bytes, float *dR, float *dPpos, float *dE, float *dW,
@@ -670,6 +672,7 @@ extern "C" int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const
     MOBGT_REQUIRE(H == kH, MOBGT_ERR_UNSUPPORTED, "mobgt_bias_bwd: num_heads=%d (only 8 is built)", H);
     MOBGT_REQUIRE(hops >= 4 && hops <= MOBGT_MAX_HOPS && hops % 4 == 0 && num_bins >= 1 && num_bins <= 1024, MOBGT_ERR_BAD_SHAPE,
                   "mobgt_bias_bwd: hops=%d num_bins=%d", hops, num_bins);
+    MOBGT_REQUIRE(dk >= 1 && dk <= hops, MOBGT_ERR_BAD_SHAPE, "mobgt_bias_bwd: dk=%d outside [1, hops=%d]", dk, hops);
     MOBGT_REQUIRE(T >= 2 && Tp >= T && Tp % 8 == 0, MOBGT_ERR_BAD_SHAPE, "mobgt_bias_bwd: T=%d Tp=%d", T, Tp);
     MOBGT_REQUIRE((dbias_dtype == MOBGT_F32 && n_layers == 1) || (dbias_dtype == MOBGT_BF16 && n_layers >= 1 && n_layers <= 64),
                   MOBGT_ERR_BAD_DTYPE, "mobgt_bias_bwd: dbias dtype %d with %d layer planes", dbias_dtype, n_layers);
@@ -689,7 +692,7 @@ extern "C" int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const
     MOBGT_CUDA_OK(cudaMemsetAsync(dEWfull, 0, (size_t)nEW * 4, s));
     const int nparts = B > 0 ? kNumSMs : 0;
     if (B > 0) {
-        K2Common c{n, sq_off, rel_pos, poi_pos, edge_in, B, T, Tp, hops, rel_pos_max};
+        K2Common c{n, sq_off, rel_pos, poi_pos, edge_in, B, T, Tp, hops, rel_pos_max, dk};
         const size_t smem = (size_t)(pl.cta_words + pl.warps * pl.per_warp) * sizeof(float);
         if (dbias_dtype == MOBGT_F32) {
             MOBGT_CUDA_OK(cudaFuncSetAttribute(k2_bias_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -705,7 +708,7 @@ extern "C" int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const
     }
     k2_bias_bwd_reduce_kernel<<<ceil_div(pl.stride, 256), 256, 0, s>>>(partial, nparts, pl.stride, tot);
     MOBGT_LAUNCH_OK("k2_bias_bwd_reduce_kernel");
-    k2_bias_bwd_scatter_kernel<<<ceil_div(max(max(kRelRows, num_bins) * kH, hops * kH * 32), 256), 256, 0, s>>>(tot, pl, hops, num_bins, dEWfull, dR, dPpos, dtvd);
+    k2_bias_bwd_scatter_kernel<<<ceil_div(max(max(kRelRows, num_bins) * kH, hops * kH * 32), 256), 256, 0, s>>>(tot, pl, hops, dk, num_bins, dEWfull, dR, dPpos, dtvd);
     MOBGT_LAUNCH_OK("k2_bias_bwd_scatter_kernel");
     k2_bias_bwd_finish_kernel<<<ceil_div(kEdgeVocab * kH + hops * kH * kH, 256), 256, 0, s>>>(dEWfull, E, W, hops, dE, dW);
     MOBGT_LAUNCH_OK("k2_bias_bwd_finish_kernel");

@@ -10,9 +10,12 @@ Flag groups (names and defaults as in the reference):
   * datamodule: --dataset_name --num_workers --batch_size --seed --multi_hop_max_dist --rel_pos_max   (data.py:197-207)
   * trainer:    the pytorch_lightning.Trainer flags the README uses      (README.md:62): --gpus --accelerator --precision
                 --max_epochs --max_steps --check_val_every_n_epoch --default_root_dir --resume_from_checkpoint
-The Lightning runtime itself is out of scope: a minimal torch loop replaces it — data-parallel over
-trajectory graphs with one NCCL all-reduce of a flat fp32 gradient buffer per step, `last.ckpt` auto-resume
-(entry.py:135-137) and the reference's three metric lines at test time (model_fqandtoyo.py:1593-1595).
+The Lightning runtime itself is out of scope: `mobgt_b200.trainer.Trainer` replaces it — the SAME class
+`bench.py` times: data-parallel over trajectory graphs (every rank gets the same number of graphs, like DistributedSampler),
+one-batch-ahead collation (`collator.PackedLoader`, `--num_workers` packing processes), CUDA-graph replay of fixed-shape
+steps, one all-reduce of the flat fp32 gradient buffer per step (its out_proj bucket overlapped with the backward),
+`last.ckpt` auto-resume (entry.py:135-137), and at test time the fused K5 head + the reference's three metric lines
+(model_fqandtoyo.py:1593-1595) over the metric sums of ALL ranks.
 
 The reference reads ../dataset/<name>/raw/*; those blobs are not shipped, so the data here is the
 seeded synthetic world of mobgt_b200.synth (`--synthetic` picks the BASELINE.json shape, `--train_graphs` the split size).
@@ -50,10 +53,15 @@ def build_parser():
     d.add_argument("--seed", type=int, default=1)
     d.add_argument("--multi_hop_max_dist", type=int, default=5)
     d.add_argument("--rel_pos_max", type=int, default=1024)
-    s = parser.add_argument_group("synthetic data (stand-in for ../dataset/<name>)")
+    s = parser.add_argument_group("synthetic data (stand-in for ../dataset/<name>) and run options of this implementation")
     s.add_argument("--synthetic", type=str, default=None, help="c1|c2|c4|tiny (default: by dataset_name)")
     s.add_argument("--train_graphs", type=int, default=2048)
     s.add_argument("--test_graphs", type=int, default=512)
+    s.add_argument("--n_fixed", type=int, default=None, help="every synthetic graph gets exactly this many nodes")
+    s.add_argument("--limit_train_steps", type=int, default=None, help="stop after this many optimizer steps (smoke runs)")
+    s.add_argument("--no_cuda_graph", action="store_true", help="never capture the step in a CUDA graph")
+    s.add_argument("--eval_vocab_parallel", action="store_true",
+                   help="evaluation head with out_proj sharded by vocabulary rows across the ranks (SURVEY.md §8e)")
     return parser
 
 
@@ -68,17 +76,21 @@ def _ckpt_dir(args):
 
 
 def cli_main(argv=None):
+    """-> dict(loss=last training loss | None, metrics=last evaluation | None, steps=optimizer steps run)"""
     import torch.distributed as dist
-    from . import _C, collator, synth
+    from . import _C, collator, parallel, synth
     from .model import Graphormer
+    from .trainer import Trainer
     args = parse_args(argv)
     rank, world_size = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     _C.require_cuda()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world_size > 1:
+    own_pg = False
+    if world_size > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
+        own_pg = True
     if rank == 0 and not args.test and not args.validate:
         print(args)
     torch.manual_seed(args.seed)                                        # pl.seed_everything (entry.py:60)
@@ -87,20 +99,23 @@ def cli_main(argv=None):
     shape = args.synthetic or DATASET_DEFAULT_SHAPE.get(args.dataset_name, "c2")
     world = synth.make_world(shape, seed=args.seed, dataset_name=args.dataset_name)
     cap = synth.CONFIGS[shape]["cap"]
-    train = synth.make_items(world, args.train_graphs, cap, seed=args.seed, cfg_id=11)
-    test = synth.make_items(world, args.test_graphs, cap, seed=args.seed, cfg_id=12)
-    collate = getattr(collator, COLLATORS[args.dataset_name])
+    train = synth.make_items(world, args.train_graphs, cap, seed=args.seed, cfg_id=11, n_fixed=args.n_fixed)
+    test = synth.make_items(world, args.test_graphs, cap, seed=args.seed, cfg_id=12, n_fixed=args.n_fixed)
     latlon = torch.from_numpy(world.latlon).to(dev)
+    ckw = dict(world=world, latlon_dev=latlon, multi_hop_max_dist=args.multi_hop_max_dist, rel_pos_max=args.rel_pos_max, device=dev)
 
-    def batches(items, shuffle, epoch):
+    def item_batches(items, shuffle, epoch, pad):
+        """This rank's share of the epoch as lists of raw items (DistributedSampler semantics, parallel.shard_graphs)."""
         order = np.arange(len(items))
         if shuffle:
             np.random.default_rng([args.seed, epoch]).shuffle(order)
-        order = order[rank::world_size]                                 # DistributedSampler: graphs g = r (mod world)
-        for i in range(0, len(order), args.batch_size):
-            sel = [items[j] for j in order[i:i + args.batch_size]]
-            yield collate(sel, max_node=512, multi_hop_max_dist=args.multi_hop_max_dist, rel_pos_max=args.rel_pos_max,
-                          world=world, latlon_dev=latlon, device=dev)
+        mine = parallel.shard_graphs(len(items), rank, world_size, order=order.tolist(), pad=pad)
+        for i in range(0, len(mine), args.batch_size):
+            yield [items[j] for j in mine[i:i + args.batch_size]]
+
+    def loader(items, shuffle, epoch, pad):
+        # one batch ahead: host packing in --num_workers processes, H2D + K1 + poi_pos + sort plans on a side stream
+        return collator.PackedLoader(item_batches(items, shuffle, epoch, pad), num_workers=args.num_workers, max_node=512, **ckw)
 
     model = Graphormer(
         n_layers=args.n_layers, num_heads=args.num_heads, hidden_dim=args.hidden_dim,
@@ -115,70 +130,59 @@ def cli_main(argv=None):
     if rank == 0:
         print("total params:", sum(p.numel() for p in model.parameters()))
 
-    (opt,), (sched_cfg,) = model.configure_optimizers()
-    sched = sched_cfg["scheduler"]
-    params = list(model.parameters())
-    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
-    off = 0
-    for p in params:
-        p.grad = flat[off:off + p.numel()].view_as(p)
-        off += p.numel()
-
+    tr = Trainer(model, dev, world_size, cuda_graph=not args.no_cuda_graph)
     ckdir = _ckpt_dir(args)
     last = os.path.join(ckdir, "last.ckpt")
-    step, epoch0 = 0, 0
+    epoch0 = 0
     resume = args.resume_from_checkpoint
     if not args.test and not args.validate and os.path.exists(last):    # entry.py:135-137
         resume = last
     if resume:
         ck = torch.load(resume, map_location=dev)
-        model.load_state_dict(ck["state_dict"], strict=False)
-        if "optimizer" in ck and not (args.test or args.validate):
-            opt.load_state_dict(ck["optimizer"])
-            sched.load_state_dict(ck["lr_scheduler"])
-            step, epoch0 = ck.get("global_step", 0), ck.get("epoch", 0)
+        tr.load_state_dict(ck, with_optimizer=not (args.test or args.validate))
+        epoch0 = 0 if (args.test or args.validate) else int(ck.get("epoch", 0))
         if rank == 0:
             print("args.resume_from_checkpoint", resume)
 
-    def evaluate(items, tag):
-        model.eval()
-        outs = []
-        with torch.no_grad():
-            for b in batches(items, False, 0):
-                outs.append(model.test_step(b))
-        res = model.test_epoch_end(outs) if rank == 0 or world_size == 1 else None
-        model.train()
-        return res
+    def evaluate(items):
+        return tr.evaluate(loader(items, False, 0, pad=False), vocab_parallel=args.eval_vocab_parallel)
 
+    result = dict(loss=None, metrics=None, steps=0)
     if args.test or args.validate:
-        print(evaluate(test, "test"))
+        result["metrics"] = evaluate(test)                              # entry.py:146-154
+        if rank == 0:
+            print(result["metrics"])
     else:
         model.train()
         t0 = time.time()
+        limit = args.max_steps if args.limit_train_steps is None else min(args.max_steps, tr.step_count + args.limit_train_steps)
+        loss = None
         for epoch in range(epoch0, args.max_epochs):
-            for b in batches(train, True, epoch):
-                if step >= args.max_steps:
-                    break
-                flat.zero_()
-                loss = model.training_step(b)
-                loss.backward()
-                if world_size > 1:
-                    dist.all_reduce(flat)
-                    flat.div_(world_size)
-                opt.step()
-                sched.step()
-                step += 1
-                if rank == 0 and step % max(1, args.progress_bar_refresh_rate) == 0:
-                    print(f"epoch {epoch} step {step} train_loss {loss.item():.5f} lr {sched.get_last_lr()[0]:.3e} "
+            ld = loader(train, True, epoch, pad=True)
+            b = ld.current()
+            while b is not None and tr.step_count < limit:
+                loss = tr.train_step(b)
+                ld.advance()                                            # collate the next batch under this step's kernels
+                b = ld.current()
+                if rank == 0 and tr.step_count % max(1, args.progress_bar_refresh_rate) == 0:
+                    print(f"epoch {epoch} step {tr.step_count} train_loss {loss.item():.5f} lr {tr.sched.get_last_lr()[0]:.3e} "
                           f"({time.time() - t0:.1f}s)")
             if (epoch + 1) % args.check_val_every_n_epoch == 0:
-                evaluate(test, "valid")
+                result["metrics"] = evaluate(test)
             if rank == 0:
                 os.makedirs(ckdir, exist_ok=True)
-                torch.save({"state_dict": model.state_dict(), "optimizer": opt.state_dict(), "lr_scheduler": sched.state_dict(),
-                            "global_step": step, "epoch": epoch + 1, "hyper_parameters": vars(args)}, last)
-    if world_size > 1:
+                ck = tr.state_dict()
+                ck.update(epoch=epoch + 1, hyper_parameters=vars(args))
+                torch.save(ck, last)
+            if tr.step_count >= limit:
+                break
+        result["loss"] = float(loss) if loss is not None else None
+        result["steps"] = tr.step_count
+        if rank == 0:
+            print(f"trained {tr.step_count} steps: {tr.graph_steps} CUDA-graph replays, {tr.eager_steps} eager ({tr.graph_note})")
+    if own_pg:
         dist.destroy_process_group()
+    return result
 
 
 if __name__ == "__main__":

@@ -36,8 +36,11 @@ def _tensor_fields(batch):
 
 
 class GraphedTrainStep:
-    def __init__(self, model, flat_grads, example_batch, warmup=3):
+    def __init__(self, model, flat_grads, example_batch, warmup=3, after_backward=None):
+        """after_backward: optional callable run right after loss.backward() inside the captured region (the trainer joins
+        the side stream of its early gradient all-reduce there, so the collective is part of the graph)."""
         self.model, self.flat = model, flat_grads
+        self._after_backward = after_backward
         self.static = example_batch
         self.dev = flat_grads.device
         if "_plans" not in example_batch.__dict__:
@@ -74,6 +77,8 @@ class GraphedTrainStep:
         self.flat.zero_()
         loss = self.model.training_step(self.static)
         loss.backward()
+        if self._after_backward is not None:
+            self._after_backward()
         return loss
 
     def load(self, batch):

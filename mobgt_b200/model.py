@@ -180,12 +180,10 @@ class EncoderLayer(nn.Module):
 
 
 def gradient_tail_loss(inputs, targets, alpha=0.25, beta=1, k=1):
-    """model_fqandtoyo.py:545-550 (`.to("cuda")` dropped: tensors already live on the device)."""
-    one_hot = torch.zeros_like(inputs)
-    one_hot.scatter_(1, targets[:len(inputs)].view(-1, 1), 1)
-    prob = torch.sigmoid(inputs)
-    loss = -alpha * (1 - prob) ** k * one_hot * torch.log(prob) - (1 - one_hot) * beta * prob ** k * torch.log(1 - prob)
-    return loss.mean()
+    """model_fqandtoyo.py:545-550 — the K7 kernel (csrc/k7_loss.cu); only the reference's own beta = k = 1 is built."""
+    if beta != 1 or k != 1:
+        raise NotImplementedError("GradientTailLoss: libmobgt implements beta = 1, k = 1 (the only values the reference uses)")
+    return ops.gradient_tail_loss(inputs, targets, alpha)
 
 
 class Graphormer(nn.Module):
@@ -198,6 +196,8 @@ class Graphormer(nn.Module):
         (README.md:62), so TF32 (10-bit mantissa, fp32 range and accumulate) is at least as precise; tf32=False keeps IEEE fp32."""
         super().__init__()
         self.tf32 = bool(tf32)
+        if self.tf32:
+            ops.enable_tf32()
         if world is None:
             raise ValueError("Graphormer needs a PoiWorld (the dataset tables the reference reads from ../dataset/<name>/raw, "
                              "model_fqandtoyo.py:791-832)")
@@ -288,7 +288,7 @@ class Graphormer(nn.Module):
     def node_tokens(self, b, dtype=torch.bfloat16):
         """K4 (model_fqandtoyo.py:1222-1344) -> packed tokens [ntok, 192]"""
         Gd, Gc = self.gcn_tables()
-        e = ops.EmbedGather.apply(b, self.cat_of_poi, Gd, self.time_embed_model_48.weight, Gc, dtype)
+        e = ops.EmbedGather.apply(b, self.cat_of_poi, Gd, self.time_embed_model_48.weight, Gc, dtype, self.traits["time_pad"])
         hp = self.hidden_dim + self.time_embed_dim
         f2, f4 = self.embed_fuse_model2.fuse_embed, self.embed_fuse_model4.fuse_embed
         if dtype == torch.bfloat16:     # bf16 working copies of the weights, bias gradients through the K6 column sum
@@ -302,17 +302,22 @@ class Graphormer(nn.Module):
                                  self.graph_token.weight)
         return F.dropout(tok, self.pos_embed.p, self.training)                                           # :358
 
-    def forward(self, batched_data, perturb=None):
-        b = batched_data
-        if self.tf32 and not torch.backends.cuda.matmul.allow_tf32:
-            torch.backends.cuda.matmul.allow_tf32 = True       # process-wide cuBLAS switch (also seen by the autograd threads)
-        if not hasattr(b, "rel_pos16"):
-            raise TypeError("Graphormer.forward expects a mobgt_b200.collator.Batch1 (packed); build it with "
-                            "mobgt_b200.collator.collator_* or Batch1-from-dense")
-        bias = self.attn_bias(b)
+    def _packed(self, batched_data):
+        """The packed Batch1 the kernels consume; a reference-collated dense batch (collator.py:149-215) is converted."""
+        if hasattr(batched_data, "rel_pos16"):
+            return batched_data
+        from .collator import Batch1
+        return Batch1.from_dense(batched_data, multi_hop_max_dist=self.multi_hop_max_dist, device=self.X.device)
+
+    def features(self, batched_data):
+        """model_fqandtoyo.py:1143-1364 up to the input of the two heads: z [B, 2*hidden+64] fp32 (user fuse of token 0,
+        final LayerNorm, ELU, output dropout) — the operand of `out_proj` / `cat_decoder` and of the fused K5 head."""
+        b = self._packed(batched_data)
         tok = self.node_tokens(b)
-        slot = ops.BiasSlot(bias, b, len(self.layers))
-        x = ops.BiasGradSink.apply(self.input_dropout(tok).float(), bias, slot)                          # :1347
+        slot = ops.BiasSlot(b, len(self.layers))
+        x = ops.BiasLink.apply(self.input_dropout(tok).float(), slot, self.rel_pos_encoder.weight, self.poi_pos_encoder.weight,
+                               self.edge_encoder.weight, self.edge_dis_encoder.weight,
+                               self.graph_token_virtual_distance.weight)                                 # K2 (:1143-1216), :1347
         x16 = x.to(torch.bfloat16)
         self._w16.refresh()
         for li, layer in enumerate(self.layers):                                                         # :1348-1352
@@ -321,46 +326,94 @@ class Graphormer(nn.Module):
         user_embedding = self.user_embed_model(b.user.view(-1) - 1)                                      # :1239
         z = self.embed_fuse_model3(z0, user_embedding)                                                   # :1356 (token 0 only)
         z = self.output_dropout(self.ELU(ops.layer_norm(z.float(), self.final_ln)))                      # :1360-1364
+        self.cat_target = self.cat_of_poi[b.y - 1].long() - 1                                            # :1265
+        return z, b
+
+    def forward(self, batched_data, perturb=None):
+        z, b = self.features(batched_data)
         cat_output = self.cat_decoder(z)
         output = self.out_proj(z)
         if self.traits["log_softmax"]:
             output = F.log_softmax(output, dim=1)                                                        # :1425
-        self.cat_target = self.cat_of_poi[b.y - 1].long() - 1                                            # :1265
         return [output, cat_output]
 
     # ------------------------------------------------------------------------------------------ steps
     def training_step(self, batched_data, batch_idx=0):
-        """model_fqandtoyo.py:1434-1478"""
-        y_out = self(batched_data)
+        """model_fqandtoyo.py:1434-1478.  The losses are the K7 kernels (csrc/k7_loss.cu): one pass over the logits gives the
+        loss, and the same pass of the backward gives d(logits)."""
+        z, b = self.features(batched_data)
+        cat_logits = self.cat_decoder(z)
+        poi_logits = self.out_proj(z)
         if self.dataset_name == "toyotagraph":
-            loss1 = gradient_tail_loss(y_out[1], self.cat_target, 0.1)
-            loss2 = F.nll_loss(y_out[0], batched_data.y, ignore_index=0)          # data.py:165 NLLLoss(ignore_index=0)
+            loss1 = ops.gradient_tail_loss(cat_logits, self.cat_target, 0.1)                            # :1464-1469
+            loss2 = ops.log_softmax_nll_loss(poi_logits, b.y, ignore_index=0)     # :1425 + data.py:165 NLLLoss(ignore_index=0)
             return loss1 + loss2
-        return gradient_tail_loss(y_out[0], batched_data.y - 1, 0.2)
+        return ops.gradient_tail_loss(poi_logits, b.y - 1, 0.2)                                         # :1447-1460
 
-    def validation_step(self, batched_data, batch_idx=0):
-        return {"y_pred": self(batched_data), "y_true": batched_data.y - 1}
+    def eval_targets(self, batched_data):
+        """y_true of validation_step / test_step (model_fqandtoyo.py:1485-1493, 1531-1539): `y - 1` for the datasets in the
+        reference's list, plain `y` for toyotagraph (its out_proj has P+1 classes and it trains on y, :1471)."""
+        y = batched_data.y
+        return y if self.dataset_name == "toyotagraph" else y - 1
 
-    def test_step(self, batched_data, batch_idx=0):
-        return {"y_pred": self(batched_data), "y_true": batched_data.y - 1, "idx": batched_data.idx}
+    def head_topk(self, z, y_true, k=20, vocab_parallel=None):
+        """K5: POI logits + per-row top-k + rank of the target, fused (the logits never reach HBM).  -> dict(idx [B,k] i32,
+        val [B,k], rank [B] i32).  log_softmax (toyotagraph, :1425) is monotone per row, so indices and ranks are those of
+        the reference's y_pred[0].  vocab_parallel: a process group -> out_proj rows sharded across its ranks, z rows of all
+        ranks gathered; returns the rows of THIS rank."""
+        W = self.out_proj.weight.detach().to(torch.bfloat16)
+        bias = self.out_proj.bias.detach().float()
+        z16 = z.detach().to(torch.bfloat16).contiguous()
+        t32 = y_true.to(torch.int32).contiguous()
+        if vocab_parallel is None:
+            r = ops.head_topk_local(z16, W.contiguous(), bias.contiguous(), t32, k)
+            return dict(idx=r["idx"], val=r["val"], rank=r["cnt"])
+        from . import parallel
+        return parallel.vocab_parallel_eval_head(ops, z16, W, bias, t32, k, vocab_parallel)
 
-    def test_epoch_end(self, outputs):
-        """model_fqandtoyo.py:1546-1597: Acc@{1,5,10,20}, NDCG@k, MRR over all batches; prints the reference's three lines."""
-        from .metrics import get_acc, MRR_metric
-        import numpy as np
-        tot = np.zeros(8)
-        mrr, n = 0.0, 0
+    def _eval_step(self, batched_data, full_logits, vocab_parallel):
+        z, b = self.features(batched_data)
+        y_true = self.eval_targets(b)
+        out = {"y_true": y_true, "idx": b.idx}
+        out.update(self.head_topk(z, y_true, 20, vocab_parallel))
+        if full_logits:                    # the reference's return value (a [B, P] tensor per batch); off on the fast path
+            output = self.out_proj(z)
+            out["y_pred"] = [F.log_softmax(output, dim=1) if self.traits["log_softmax"] else output, self.cat_decoder(z)]
+        return out
+
+    def validation_step(self, batched_data, batch_idx=0, full_logits=False, vocab_parallel=None):
+        """model_fqandtoyo.py:1484-1496, through the fused head: returns y_true plus top-20 indices and the target's rank."""
+        out = self._eval_step(batched_data, full_logits, vocab_parallel)
+        out.pop("idx")
+        return out
+
+    def test_step(self, batched_data, batch_idx=0, full_logits=False, vocab_parallel=None):
+        """model_fqandtoyo.py:1530-1544"""
+        return self._eval_step(batched_data, full_logits, vocab_parallel)
+
+    def test_epoch_end(self, outputs, group=None, quiet=False):
+        """model_fqandtoyo.py:1546-1597: Acc@{1,5,10,20}, NDCG@k, MRR over all batches (of all ranks: the per-batch SUMS are
+        all-reduced, the reference's `sync_dist=True`); prints the reference's three lines on rank 0."""
+        from . import parallel
+        tot, n = {}, 0
         for o in outputs:
-            acc, ndcg = get_acc(o["y_true"], o["y_pred"][0])
-            mrr += MRR_metric(o["y_true"], o["y_pred"][0])
-            tot += np.array([acc[2, 0], acc[1, 0], acc[0, 0], ndcg[2, 0], ndcg[1, 0], ndcg[0, 0], acc[3, 0], ndcg[3, 0]])
+            m = ops.metrics_from_rank(o["rank"], o["y_true"])      # per batch: keeps get_acc's break at the first target == 0
+            for k_, v in m.items():
+                tot[k_] = tot.get(k_, 0.0) + v
             n += len(o["y_true"])
-        avg = tot / max(n, 1)
-        print(f"ACC @1: {round(avg[0], 4)}, @5: {round(avg[1], 4)}, @10: {round(avg[2], 4)}")
-        print(f"NDCG @1: {round(avg[3], 4)}, @5: {round(avg[4], 4)}, @10: {round(avg[5], 4)}")
-        print(f"MRR: {round(mrr / max(n, 1), 4)}")
-        return dict(acc1=avg[0], acc5=avg[1], acc10=avg[2], ndcg1=avg[3], ndcg5=avg[4], ndcg10=avg[5], acc20=avg[6],
-                    ndcg20=avg[7], mrr=mrr / max(n, 1))
+        if not tot:
+            tot = {f"{a}{k_}": 0.0 for a in ("acc", "ndcg") for k_ in (1, 5, 10, 20)}
+            tot["mrr"] = 0.0
+        tot, n = parallel.reduce_metric_sums(tot, n, group=group, device=self.X.device)
+        avg = {k_: v / max(n, 1) for k_, v in tot.items()}
+        if not quiet and parallel.is_rank0(group):
+            print(f"ACC @1: {round(avg['acc1'], 4)}, @5: {round(avg['acc5'], 4)}, @10: {round(avg['acc10'], 4)}")
+            print(f"NDCG @1: {round(avg['ndcg1'], 4)}, @5: {round(avg['ndcg5'], 4)}, @10: {round(avg['ndcg10'], 4)}")
+            print(f"MRR: {round(avg['mrr'], 4)}")
+        avg["n"] = n
+        return avg
+
+    validation_epoch_end = test_epoch_end
 
     def configure_optimizers(self):
         """model_fqandtoyo.py:1599-1616"""

@@ -26,6 +26,11 @@ def bias_pitch(T):
 
 
 # ----------------------------------------------------------------------------------------------- K2
+def _dk(batch):
+    """multi_hop_max_dist of a batch (hop slots that are live); batch.hops is the byte stride of its edge_in8 rows."""
+    return int(getattr(batch, "dk", batch.hops))
+
+
 def bias_fwd_raw(batch, R, Ppos, E, W, tvd, out_dtype=torch.bfloat16, T=None, Tp=None):
     B, H = batch.B, R.shape[1]
     T = T or batch.N + 1
@@ -37,7 +42,7 @@ def bias_fwd_raw(batch, R, Ppos, E, W, tvd, out_dtype=torch.bfloat16, T=None, Tp
         raise _C.MobgtError(f"mobgt_bias_fwd_workspace_bytes rejected hops={batch.hops} H={H}")
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     _C.call("mobgt_bias_fwd", _C.ptr(batch.n), _C.ptr(batch.sq_off), _C.ptr(batch.rel_pos16), _C.ptr(batch.poi_pos16),
-            _C.ptr(batch.edge_in8), B, T, Tp, batch.hops, H, batch.rel_pos_max, int(Ppos.shape[0]), _C.ptr(R), _C.ptr(Ppos),
+            _C.ptr(batch.edge_in8), B, T, Tp, batch.hops, _dk(batch), H, batch.rel_pos_max, int(Ppos.shape[0]), _C.ptr(R), _C.ptr(Ppos),
             _C.ptr(E), _C.ptr(W), _C.ptr(tvd), _C.ptr(ws), _C.ptr(out), _dt(out), _C.stream_ptr())
     return out
 
@@ -62,15 +67,15 @@ def bias_bwd_raw(batch, dbias, E, W, num_bins):
     dW = torch.zeros(W.numel(), dtype=torch.float32, device=dev)   # rows >= hops*H*H of edge_dis_encoder get no gradient
     dtv = torch.empty(H, dtype=torch.float32, device=dev)
     _C.call("mobgt_bias_bwd", _C.ptr(batch.n), _C.ptr(batch.sq_off), _C.ptr(batch.rel_pos16), _C.ptr(batch.poi_pos16),
-            _C.ptr(batch.edge_in8), B, T, Tp, hops, H, batch.rel_pos_max, num_bins, _C.ptr(dbias), dt, L, stride, _C.ptr(E),
+            _C.ptr(batch.edge_in8), B, T, Tp, hops, _dk(batch), H, batch.rel_pos_max, num_bins, _C.ptr(dbias), dt, L, stride, _C.ptr(E),
             _C.ptr(W), _C.ptr(ws), ws_bytes, _C.ptr(dR), _C.ptr(dP), _C.ptr(dE), _C.ptr(dW), _C.ptr(dtv), _C.stream_ptr())
     return dR, dP, dE, dW.view_as(W), dtv
 
 
 class AttnBias(torch.autograd.Function):
-    """graph_attn_bias = f(rel_pos, poi_pos, edge_input; 5 tables)   (model_fqandtoyo.py:1143-1216).
-    In training the gradient is the stack of per-layer bf16 dS planes written by the attention backward kernels
-    (handed over by BiasGradSink through the batch object); a plain f32 gradient tensor works too."""
+    """graph_attn_bias = f(rel_pos, poi_pos, edge_input; 5 tables)   (model_fqandtoyo.py:1143-1216) as a stand-alone
+    differentiable op (gradient: a plain [B,H,T,Tp] tensor).  The model's forward uses BiasLink below, whose backward
+    consumes the per-layer bf16 dS planes of the attention kernels instead."""
 
     @staticmethod
     def forward(ctx, batch, R, Ppos, E, W, tvd, out_dtype):
@@ -82,9 +87,7 @@ class AttnBias(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dbias):
         E, W = ctx.saved_tensors
-        planes = ctx.batch.__dict__.pop("_ds_planes", None)     # bf16 [L,B,H,T,Tp] left by BiasGradSink (training path)
-        db = planes if planes is not None else dbias.float().contiguous()
-        dR, dP, dE, dW, dt = bias_bwd_raw(ctx.batch, db, E, W.view(-1), ctx.num_bins)
+        dR, dP, dE, dW, dt = bias_bwd_raw(ctx.batch, dbias.float().contiguous(), E, W.view(-1), ctx.num_bins)
         dR[0].zero_()          # padding_idx rows (never indexed by a packed pair anyway)
         dP[0].zero_()
         return None, dR, dP, dE, dW.view(-1, 1), dt.view(1, -1), None
@@ -130,7 +133,7 @@ class BiasedAttention(torch.autograd.Function):
 
     The bias is ONE tensor used by every encoder layer.  Each layer's backward stores its own dS = d(bias) plane
     (bf16, written by a TMA store from the tile the dK / dQ MMAs consume) into bias_slot.planes[layer]; the gradient
-    w.r.t. `bias` is delivered once, by BiasGradSink below, and the planes are summed in fp32 by mobgt_bias_bwd."""
+    w.r.t. the bias tables is produced once, by BiasLink below, where mobgt_bias_bwd sums the planes in fp32."""
 
     @staticmethod
     def forward(ctx, qkv, bias_slot, layer, drop_p=0.0):
@@ -155,30 +158,42 @@ class BiasedAttention(torch.autograd.Function):
 
 
 class BiasSlot:
-    def __init__(self, bias, batch, n_layers):
+    """What the six encoder layers of one forward share: the batch, the bias tensor (written once by K2) and, in backward,
+    the stack of per-layer bf16 dS planes."""
+
+    def __init__(self, batch, n_layers, bias=None):
         self.bias, self.batch, self.n_layers, self.planes, self.written = bias, batch, n_layers, None, set()
 
 
-class BiasGradSink(torch.autograd.Function):
-    """Identity on a token tensor in forward; in backward (which autograd runs after every encoder layer's backward,
-    because it sits before layer 0) it hands the accumulated dBias to the bias tensor's autograd edge."""
+class BiasLink(torch.autograd.Function):
+    """The attention bias of a training forward as ONE autograd node on the token stream, in front of encoder layer 0.
+    forward : K2 builds the bias from the five tables (model_fqandtoyo.py:1143-1216) into slot.bias — a plain tensor every
+              layer's attention reads; the token tensor passes through unchanged (the input dropout site, :1347).
+    backward: autograd reaches this node after EVERY layer's attention backward has stored its dS plane in slot.planes, so
+              the table gradients are one K2-backward over the stack; d(tokens) passes through."""
 
     @staticmethod
-    def forward(ctx, tok, bias, slot):
-        ctx.slot = slot
+    def forward(ctx, tok, slot, R, Ppos, E, W, tvd):
+        Rc, Pc, Ec, Wc, tc = (t.detach().float().contiguous() for t in (R, Ppos, E, W, tvd))
+        slot.bias = bias_fwd_raw(slot.batch, Rc, Pc, Ec, Wc.view(-1), tc.view(-1), torch.bfloat16)
+        ctx.slot, ctx.num_bins = slot, Ppos.shape[0]
+        ctx.save_for_backward(Ec, Wc)
         return tok.view_as(tok)
 
     @staticmethod
     def backward(ctx, dtok):
         slot = ctx.slot
         planes, slot.planes = slot.planes, None
-        if planes is None:
-            return dtok, None, None
+        if planes is None:                      # no attention layer took part in this backward
+            return dtok, None, None, None, None, None, None
         for l in range(slot.n_layers):          # a layer whose backward never ran contributes nothing
             if l not in slot.written:
                 planes[l].zero_()
-        slot.batch.__dict__["_ds_planes"] = planes
-        return dtok, planes[0], None            # a correctly shaped stand-in; AttnBias.backward picks up the whole stack
+        E, W = ctx.saved_tensors
+        dR, dP, dE, dW, dt = bias_bwd_raw(slot.batch, planes, E, W.view(-1), ctx.num_bins)
+        dR[0].zero_()                           # padding_idx rows (never indexed by a packed pair anyway)
+        dP[0].zero_()
+        return dtok, None, dR, dP, dE, dW.view(-1, 1), dt.view(1, -1)
 
 
 # ----------------------------------------------------------------------------------------------- K4
@@ -226,8 +241,10 @@ class EmbedGather(torch.autograd.Function):
     """[Gd[x-1] | Tm[slot] | Gc[cat_of_poi[x-1]-1]] per packed node (model_fqandtoyo.py:1259-1264)."""
 
     @staticmethod
-    def forward(ctx, batch, cat_of_poi, Gd, Tm, Gc, out_dtype):
-        ctx.batch, ctx.cat_of_poi = batch, cat_of_poi
+    def forward(ctx, batch, cat_of_poi, Gd, Tm, Gc, out_dtype, time_pad=None):
+        """time_pad: padding_idx of the time-slot table (nn.Embedding(..., padding_idx=0) for foursquaregraph / gowalla,
+        model_fqandtoyo.py:654, 796; None for toyotagraph, :915): that row receives no gradient."""
+        ctx.batch, ctx.cat_of_poi, ctx.time_pad = batch, cat_of_poi, time_pad
         ctx.shapes = (Gd.shape, Tm.shape, Gc.shape)
         return embed_gather_raw(batch, cat_of_poi, Gd.detach().float().contiguous(), Tm.detach().float().contiguous(),
                                 Gc.detach().float().contiguous(), out_dtype)
@@ -245,7 +262,9 @@ class EmbedGather(torch.autograd.Function):
         dGd = segment_sum_raw(dout, 0, Dp, plans["poi"], P)
         dTm = segment_sum_raw(dout, Dp, Dt, plans["slot"], Tr)
         dGc = segment_sum_raw(dout, Dp + Dt, Dc, plans["cat"], C)
-        return None, None, dGd, dTm, dGc, None
+        if ctx.time_pad is not None:
+            dTm[ctx.time_pad].zero_()
+        return None, None, dGd, dTm, dGc, None, None
 
 
 class EmbedSum(torch.autograd.Function):
@@ -528,6 +547,84 @@ def linear_gelu_bf16(x, lin, w16=None, b16=None):
     if w16 is None:
         w16, b16 = lin.weight.detach().to(torch.bfloat16), lin.bias.detach().to(torch.bfloat16)
     return LinearGeluFn.apply(x, w16, b16, lin.weight, lin.bias)
+
+
+# ----------------------------------------------------------------------------------------------- K7
+def enable_tf32():
+    """The few GEMMs that stay in fp32 storage (GCN dense parts modelGNN.py:39, user fuse, cat_decoder, out_proj) run on the
+    TF32 tensor cores.  This is cuBLAS's process-wide switch: it is set once, when a model asks for it (Graphormer(tf32=True)),
+    not inside forward."""
+    torch.backends.cuda.matmul.allow_tf32 = True
+
+
+def _loss_ws(B, V, dev):
+    n = int(_C.lib().mobgt_loss_workspace_bytes(B, V))
+    if n < 0:
+        raise _C.MobgtError(f"mobgt_loss_workspace_bytes rejected B={B} V={V}")
+    return torch.empty(max(n, 16), dtype=torch.uint8, device=dev), n
+
+
+class LogSoftmaxNllFn(torch.autograd.Function):
+    """mean_{rows: target != ignore_index} -log_softmax(logits)[target]  (model_fqandtoyo.py:1425, 1470-1471; data.py:165)."""
+
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index):
+        assert logits.dim() == 2 and logits.stride(1) == 1
+        B, V = logits.shape
+        target = target.contiguous().long()
+        ws, nws = _loss_ws(B, V, logits.device)
+        lse = torch.empty(B, dtype=torch.float32, device=logits.device)
+        loss = torch.empty(2, dtype=torch.float32, device=logits.device)
+        _C.call("mobgt_lsm_nll_fwd", logits.data_ptr(), _dt(logits), logits.stride(0), _C.ptr(target), int(ignore_index), B, V,
+                _C.ptr(ws), nws, _C.ptr(lse), _C.ptr(loss), _C.stream_ptr())
+        ctx.save_for_backward(logits, target, lse, loss)
+        ctx.ignore_index = int(ignore_index)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, target, lse, loss = ctx.saved_tensors
+        B, V = logits.shape
+        g = g.detach().float().contiguous().view(1)
+        dl = torch.empty(B, V, dtype=logits.dtype, device=logits.device)
+        _C.call("mobgt_lsm_nll_bwd", logits.data_ptr(), _dt(logits), logits.stride(0), _C.ptr(target), ctx.ignore_index, B, V,
+                _C.ptr(lse), _C.ptr(loss), _C.ptr(g), _C.ptr(dl), V, _C.stream_ptr())
+        return dl, None, None
+
+
+def log_softmax_nll_loss(logits, target, ignore_index=0):
+    return LogSoftmaxNllFn.apply(logits, target, ignore_index)
+
+
+class GradientTailLossFn(torch.autograd.Function):
+    """GradientTailLoss(inputs, targets, alpha) with beta = k = 1 (model_fqandtoyo.py:545-550)."""
+
+    @staticmethod
+    def forward(ctx, logits, target, alpha):
+        assert logits.dim() == 2 and logits.stride(1) == 1
+        B, V = logits.shape
+        target = target[:B].contiguous().long()              # :547 `targets[:len(inputs)]`
+        ws, nws = _loss_ws(B, V, logits.device)
+        loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+        _C.call("mobgt_gtl_fwd", logits.data_ptr(), _dt(logits), logits.stride(0), _C.ptr(target), float(alpha), B, V, _C.ptr(ws),
+                nws, _C.ptr(loss), _C.stream_ptr())
+        ctx.save_for_backward(logits, target)
+        ctx.alpha = float(alpha)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, target = ctx.saved_tensors
+        B, V = logits.shape
+        g = g.detach().float().contiguous().view(1)
+        dl = torch.empty(B, V, dtype=logits.dtype, device=logits.device)
+        _C.call("mobgt_gtl_bwd", logits.data_ptr(), _dt(logits), logits.stride(0), _C.ptr(target), ctx.alpha, B, V, _C.ptr(g),
+                _C.ptr(dl), V, _C.stream_ptr())
+        return dl, None, None
+
+
+def gradient_tail_loss(logits, target, alpha=0.25):
+    return GradientTailLossFn.apply(logits, target, alpha)
 
 
 # ----------------------------------------------------------------------------------------------- K5

@@ -22,9 +22,22 @@ def _world(group=None):
     return 1, 0
 
 
-def shard_graphs(num_graphs, rank, world):
-    """Indices of the graphs rank `rank` owns: g = rank (mod world) — DistributedSampler without shuffling."""
-    return list(range(rank, num_graphs, world))
+def is_rank0(group=None):
+    return _world(group)[1] == 0
+
+
+def shard_graphs(num_graphs, rank, world, order=None, pad=True):
+    """Indices of the graphs rank `rank` owns: positions rank, rank + world, ... of `order` (default 0..num_graphs-1).
+    pad=True (torch's DistributedSampler(drop_last=False), what Lightning's DDP gives the reference, entry.py:141): the order
+    is extended by wrapping around to a multiple of `world`, so EVERY rank gets the same number of graphs — hence the same
+    number of batches and of gradient all-reduces per epoch (unequal counts would dead-lock the collective).  pad=False
+    (evaluation): no graph is counted twice; ranks may differ by one graph, which is harmless because the metric exchange
+    (`reduce_metric_sums`) happens once per epoch."""
+    order = list(range(num_graphs)) if order is None else list(order)
+    if pad and world > 1 and len(order) % world and len(order) > 0:
+        need = world - len(order) % world
+        order = order + [order[i % len(order)] for i in range(need)]
+    return order[rank::world]
 
 
 def shard_vocab(V, rank, world):
@@ -80,6 +93,35 @@ def sharded_head_topk(kernels, z, W_shard, bias_shard, target, k, vocab_offset, 
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
     val, idx = kernels.topk_merge_lists(gv.permute(1, 0, 2).contiguous(), gi.permute(1, 0, 2).contiguous())
     return dict(val=val, idx=idx, rank=cnt, st=st)
+
+
+def vocab_parallel_eval_head(kernels, z, W, bias, target, k, group=None):
+    """The evaluation head with out_proj sharded by vocabulary rows over the ranks of `group` (BASELINE
+    configs[4]).  Every rank brings the z rows / targets of ITS graphs; the rows of all ranks are all-gathered (padded to the
+    largest per-rank count), every rank scores them against its row range of W (replicated weights: a slice, no copy of the
+    rest), and the top-k lists / rank counts are merged by `sharded_head_topk`.  Returns this rank's rows:
+    dict(idx [Br,k] global ids, val [Br,k], rank [Br])."""
+    world, rank = _world(group)
+    Br, K = z.shape
+    V = W.shape[0]
+    off, size = shard_vocab(V, rank, world)
+    Ws, bs = W[off:off + size].contiguous(), (bias[off:off + size].contiguous() if bias is not None else None)
+    if world == 1:
+        r = sharded_head_topk(kernels, z, Ws, bs, target, k, off, group)
+        return dict(idx=r["idx"], val=r["val"], rank=r["rank"])
+    nb = torch.tensor([Br], dtype=torch.int64, device=z.device)
+    dist.all_reduce(nb, op=dist.ReduceOp.MAX, group=group)
+    Bm = int(nb.item())
+    zp = torch.zeros(Bm, K, dtype=z.dtype, device=z.device)
+    tp = torch.zeros(Bm, dtype=target.dtype, device=z.device)
+    zp[:Br], tp[:Br] = z, target
+    zg = torch.empty(world * Bm, K, dtype=z.dtype, device=z.device)
+    tg = torch.empty(world * Bm, dtype=target.dtype, device=z.device)
+    dist.all_gather_into_tensor(zg, zp, group=group)
+    dist.all_gather_into_tensor(tg, tp, group=group)
+    r = sharded_head_topk(kernels, zg, Ws, bs, tg, k, off, group)
+    lo = rank * Bm
+    return dict(idx=r["idx"][lo:lo + Br], val=r["val"][lo:lo + Br], rank=r["rank"][lo:lo + Br])
 
 
 def reduce_metric_sums(sums, n_samples, group=None, device=None):

@@ -71,12 +71,23 @@ def fill(model):
 # golden cases: name -> (dataset branch, graphs, node cap, item seed).  `toyotagraph_n40`: longer trajectories (up to 40 nodes:
 # walks longer than multi_hop_max_dist, the clamp of model_fqandtoyo.py:1168-1176, more unreachable pairs)
 CASES = {"toyotagraph": ("toyotagraph", B, CAP, SEED), "gowalla_nevda": ("gowalla_nevda", B, CAP, SEED),
-         "foursquaregraph": ("foursquaregraph", B, CAP, SEED), "toyotagraph_n40": ("toyotagraph", 4, 40, 12)}
+         "foursquaregraph": ("foursquaregraph", B, CAP, SEED), "toyotagraph_n40": ("toyotagraph", 4, 40, 12),
+         # BASELINE shapes: graphs AT the node cap of configs[1] (128 nodes -> T = 129 = 128 + 1: the single-token tail of K3)
+         # and of configs[3] (256 nodes -> T = 257: two key blocks, the fold path), each next to a short graph in the same batch
+         "toyotagraph_n128": ("toyotagraph", [(128, 1, 13), (9, 1, 14), (128, 1, 15)], 128, None),
+         "gowalla_nevda_n256": ("gowalla_nevda", [(256, 1, 16), (31, 1, 17)], 256, None)}
+MID_WORLD = dict(P=400, C=11, U=13, cap=256, batch=4)          # a world with enough POIs for 256 distinct nodes per graph
 
 
 def make_world_and_items(case="toyotagraph"):
     from mobgt_b200 import synth
     dataset_name, nb, cap, seed = CASES[case]
+    if isinstance(nb, list):          # [(exact node count, graphs, item seed), ...]
+        world = synth.make_world(dict(MID_WORLD, dataset_name=dataset_name), seed=1, U=DATASETS[dataset_name][0])
+        items = []
+        for n_fixed, cnt, sd in nb:
+            items += synth.make_items(world, cnt, cap, seed=sd, n_fixed=n_fixed, start=len(items))
+        return world, items
     world = synth.make_world("tiny", seed=1, U=DATASETS[dataset_name][0], dataset_name=dataset_name)   # hard-coded user counts
     items = synth.make_items(world, nb, cap, seed=seed)
     return world, items
@@ -179,8 +190,9 @@ def run_dataset(case, tmp, ref_model, ref_collator, ref_wrapper, mo):
     import copy
     dataset_name = CASES[case][0]
     world, items = make_world_and_items(case)
-    if not os.path.exists(os.path.join(tmp, "dataset", dataset_name)):
-        write_dataset(world, tmp, dataset_name)
+    import shutil
+    shutil.rmtree(os.path.join(tmp, "dataset", dataset_name), ignore_errors=True)     # the world differs between cases
+    write_dataset(world, tmp, dataset_name)
     torch.manual_seed(0)
     rm = ref_model.Graphormer(dataset_name=dataset_name, **HP).eval()
     # the shipped pickle is missing; the table only has to cover the bins the stand-in produces
@@ -198,6 +210,10 @@ def run_dataset(case, tmp, ref_model, ref_collator, ref_wrapper, mo):
         out = rm(copy.deepcopy(rb))
     poi, cat = out[0].detach(), out[1].detach()
     cat_target = rm.cat_target.clone().view(-1).long()
+    # the evaluation targets of the reference's own steps (model_fqandtoyo.py:1484-1496, 1530-1544)
+    with torch.no_grad():
+        y_true_test = rm.test_step(copy.deepcopy(rb), 0)["y_true"].view(-1).long()
+        y_true_val = rm.validation_step(copy.deepcopy(rb), 0)["y_true"].view(-1).long()
 
     def gtl(inputs, targets, alpha):      # GradientTailLoss :545-550 with its `.to("cuda")` dropped
         one_hot = torch.zeros_like(inputs)
@@ -224,6 +240,7 @@ def run_dataset(case, tmp, ref_model, ref_collator, ref_wrapper, mo):
     path = os.path.join(HERE, f"model_golden_{case}.npz")
     np.savez_compressed(path, poi_logits=poi.numpy(), cat_logits=cat.numpy(), cat_target=cat_target.numpy(),
                         loss=np.array([float(loss)], np.float64), grad_names=np.array(gnames), grad_norms=gnorm,
+                        y_true_test=y_true_test.numpy(), y_true_val=y_true_val.numpy(),
                         state_shapes_json=np.array(__import__("json").dumps({k: list(v.shape) for k, v in rm.state_dict().items()},
                                                                             sort_keys=True)),
                         **{"g_" + k: v for k, v in full.items()}, **{"f_" + k: v.numpy() for k, v in fields.items()})

@@ -48,7 +48,7 @@ def test_no_cpu_fallback_without_gpu(lib_built):
 def test_bad_arguments_return_status_not_crash(lib_built):
     from mobgt_b200 import _C
     L = _C.lib()
-    rc = L.mobgt_apsp_edge_input(None, None, None, None, 1, 4, 20, 0, None, None, None, None, None)
+    rc = L.mobgt_apsp_edge_input(None, None, None, None, 1, 4, 20, 20, 0, None, None, None, None, None)
     assert rc == -6                                       # MOBGT_ERR_NULL
     assert "null" in _C.last_error()
 

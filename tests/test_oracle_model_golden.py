@@ -22,7 +22,7 @@ def _gen():
     return m
 
 
-DATASETS = ("toyotagraph", "gowalla_nevda", "foursquaregraph", "toyotagraph_n40")      # golden cases
+DATASETS = ("toyotagraph", "gowalla_nevda", "foursquaregraph", "toyotagraph_n40", "toyotagraph_n128", "gowalla_nevda_n256")      # golden cases
 
 
 def _setup(dataset_name):
@@ -91,7 +91,8 @@ def test_oracle_gradients_equal_reference_backward(dataset_name):
         assert abs(got - ref_norm) <= 2e-3 * ref_norm + 1e-6 * top, (n, got, ref_norm)
     for n in g.GRAD_FULL:
         ref = torch.from_numpy(gold["g_" + n])
-        tol = 1e-3 if n in ("edge_encoder.weight", "edge_dis_encoder.weight") else 1e-5      # fp16 round trips amplify
+        # fp16 round trips amplify (n = 256: 65 k pairs summed behind an fp16 bmm -> 1.2e-3 on a gradient of 5e-5)
+        tol = 2e-3 if n in ("edge_encoder.weight", "edge_dis_encoder.weight") else 1e-5
         assert (grads[n] - ref).abs().max().item() <= tol * ref.abs().max().item(), n
 
 
@@ -195,3 +196,20 @@ def test_product_state_dict_keys_load_from_reference(dataset_name):
     for k, shp in mine.items():
         assert k in ref_shapes, k
         assert ref_shapes[k] == shp, (k, ref_shapes[k], shp)
+
+
+@pytest.mark.parametrize("dataset_name", DATASETS)
+def test_eval_targets_match_reference_steps(dataset_name):
+    """y_true of validation_step / test_step (model_fqandtoyo.py:1484-1496, 1530-1544): `y - 1` for the datasets in the
+    reference's list, plain `y` for toyotagraph — frozen from the reference's own steps."""
+    from mobgt_b200 import model
+    g = _gen()
+    gold = np.load(os.path.join(HERE, "golden", f"model_golden_{dataset_name}.npz"))
+    world, _ = g.make_world_and_items(dataset_name)
+    pm = model.Graphormer(dataset_name=g.CASES[dataset_name][0], world=world, **g.HP)        # CPU construction: no kernels involved
+
+    class B:
+        y = torch.from_numpy(gold["f_y"])
+
+    assert torch.equal(pm.eval_targets(B), torch.from_numpy(gold["y_true_test"]))
+    assert torch.equal(pm.eval_targets(B), torch.from_numpy(gold["y_true_val"]))

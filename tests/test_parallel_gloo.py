@@ -73,7 +73,7 @@ def _worker(rank, world, port, q):
         out["head"] = bool(torch.equal(r["idx"], full["idx"]) and torch.equal(r["val"], full["val"]) and
                            torch.equal(r["rank"], full["cnt"]) and torch.equal(r["st"], st_full))
         # ---- metric sums: each rank evaluates its own rows, the reduced sums equal the single-process sums
-        rows = parallel.shard_graphs(M, rank, world)
+        rows = parallel.shard_graphs(M, rank, world, pad=False)        # evaluation: no graph counted twice
         mine = metrics_from_rank(full["cnt"][rows], target[rows].long() + 1)
         tot, n = parallel.reduce_metric_sums(mine, len(rows))
         ref = metrics_from_rank(full["cnt"], target.long() + 1)
@@ -93,9 +93,10 @@ def _worker(rank, world, port, q):
                             all(p.grad.data_ptr() >= fg.flat.data_ptr() for p in lin.parameters()) and
                             torch.equal(lin[0].weight.grad.reshape(-1), fg.flat[:35]))
         # ---- sharding arithmetic
-        cover = sorted(sum((parallel.shard_graphs(11, r_, world) for r_ in range(world)), []))
+        cover = sorted(sum((parallel.shard_graphs(11, r_, world, pad=False) for r_ in range(world)), []))
+        padded = [parallel.shard_graphs(11, r_, world) for r_ in range(world)]       # training: equal counts on every rank
         spans = [parallel.shard_vocab(1001, r_, world) for r_ in range(world)]
-        out["shards"] = bool(cover == list(range(11)) and spans[0][0] == 0 and sum(s for _, s in spans) == 1001 and
+        out["shards"] = bool(cover == list(range(11)) and len({len(p_) for p_ in padded}) == 1 and spans[0][0] == 0 and sum(s for _, s in spans) == 1001 and
                              all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(world - 1)))
         q.put((rank, out))
     finally:

@@ -1,0 +1,82 @@
+"""CPU: host logic added in round 2 — equal-length graph shards, packing validation, hop stride, dense -> packed conversion."""
+import numpy as np
+import pytest
+import torch
+
+import model_oracle as mo
+
+
+def test_shard_graphs_equal_lengths_and_coverage():
+    from mobgt_b200 import parallel
+    for n, world in ((2049, 2), (10, 4), (7, 8), (16, 4), (1, 2)):
+        order = list(np.random.default_rng(n).permutation(n))
+        shards = [parallel.shard_graphs(n, r, world, order=order, pad=True) for r in range(world)]
+        assert len({len(s) for s in shards}) == 1, (n, world)                   # same number of batches / all-reduces per rank
+        assert set(i for s in shards for i in s) == set(range(n))               # every graph is seen
+        assert sum(len(s) for s in shards) - n < world                           # at most world-1 repeats (DistributedSampler)
+        ev = [parallel.shard_graphs(n, r, world, order=order, pad=False) for r in range(world)]
+        assert sorted(i for s in ev for i in s) == list(range(n))               # evaluation: no graph counted twice
+
+
+def test_hop_stride():
+    from mobgt_b200.algos import hop_stride
+    assert [hop_stride(d) for d in (1, 4, 5, 8, 20, 32)] == [4, 4, 8, 8, 20, 32]
+    for bad in (0, 33, -1):
+        with pytest.raises(ValueError):
+            hop_stride(bad)
+
+
+def test_pack_host_rejects_out_of_table_indices():
+    """The reference raises IndexError when edge_input / degree indices leave the 128-row embedding tables; pack_host does too
+    (instead of wrapping in uint8 or reading out of bounds on the device)."""
+    from mobgt_b200 import collator, synth
+    w = synth.make_world("tiny", seed=1)
+    items = synth.make_items(w, 2, 12, seed=1)
+    collator.pack_host(items)                                                    # fine
+    bad = synth.make_items(w, 2, 12, seed=1)
+    bad[0].edge_attr = bad[0].edge_attr.copy()
+    bad[0].edge_attr[0] = 125                                                    # 125 + 3 = 128
+    with pytest.raises(IndexError):
+        collator.pack_host(bad)
+    # a hub with 127 out-going edges: degree + 1 = 128
+    n = 130
+    src = np.zeros(127, np.int64)
+    dst = np.arange(1, 128, dtype=np.int64)
+    hub = synth.Data(idx=0, x=np.arange(1, n + 1).reshape(-1, 1) % w.P + 1, edge_index=np.stack([src, dst]),
+                     edge_attr=np.ones(127, np.int64), y=np.array([1]), time=np.zeros((n, 1), np.int64),
+                     time_normal=np.zeros((n, 1), np.float32), user=np.array([[0]]), cat=np.ones((n, 1), np.int64))
+    with pytest.raises(IndexError):
+        collator.pack_host([hub])
+
+
+@pytest.mark.parametrize("dk", [20, 5])
+def test_from_dense_matches_oracle_collation(dk):
+    """Batch1.from_dense on a reference-shaped dense batch (the oracle's collator, pinned to the reference's) gives the packed
+    fields pack_host + K1 produce: checked here against the oracle's own per-graph arrays, on the CPU."""
+    from mobgt_b200 import collator, synth
+    w = synth.make_world("tiny", seed=1)
+    items = synth.make_items(w, 5, 12, seed=3)
+    pre = [mo.preprocess_item(it, hop_cap=20) for it in items]
+    ob = mo.collate(pre, w, multi_hop_max_dist=dk, rel_pos_max=1024)
+    b = collator.Batch1.from_dense(ob, multi_hop_max_dist=dk, device="cpu")
+    hp = collator.pack_host(items)
+    assert b.B == 5 and b.N == int(hp.N) and b.dk == dk and b.hops % 4 == 0 and b.hops >= dk
+    assert np.array_equal(b.n_host, hp.ns)
+    views = {k: np.frombuffer(hp.buf[off:off + nb].tobytes(), dtype=np.dtype(dt)).reshape(shape)
+             for k, (off, shape, dt, nb) in hp.layout.items()}
+    for k in ("n", "sq_off", "node_off", "tok_off", "tok_graph", "tok_pos", "feat8", "x_nodes", "slot", "in_deg", "out_deg", "user",
+              "y", "node_rows"):
+        assert np.array_equal(getattr(b, k).numpy().astype(np.int64), views[k].astype(np.int64)), k
+    for g, it in enumerate(pre):
+        n = int(hp.ns[g])
+        lo, hi = int(b.sq_off[g]), int(b.sq_off[g + 1])
+        assert np.array_equal(b.rel_pos16[lo:hi].numpy().reshape(n, n), it.rel_pos.numpy() + 1)
+        e = it.edge_input.numpy()[:, :, :dk, 0] + 1
+        got = b.edge_in8[lo:hi].numpy().reshape(n, n, b.hops)
+        h = min(dk, e.shape[2])
+        assert np.array_equal(got[:, :, :h], e[:, :, :h]) and (got[:, :, h:] == 0).all()
+        assert int(b.maxdist[g]) == int(it.rel_pos.max())
+    # the dense views of the converted batch reproduce the dense batch it came from
+    for name in ("x", "rel_pos", "in_degree", "out_degree", "poi_pos", "attn_bias"):
+        assert torch.equal(getattr(b, name), getattr(ob, name)), name
+    assert torch.equal(b.edge_input, ob.edge_input[:, :, :, :b.edge_input.shape[3]])

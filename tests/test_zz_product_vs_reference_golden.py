@@ -13,7 +13,7 @@ import model_oracle as mo
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
-DATASETS = ("toyotagraph", "gowalla_nevda", "foursquaregraph", "toyotagraph_n40")      # golden cases
+DATASETS = ("toyotagraph", "gowalla_nevda", "foursquaregraph", "toyotagraph_n40", "toyotagraph_n128", "gowalla_nevda_n256")      # golden cases
 
 
 def _gen():
