@@ -272,6 +272,17 @@ int32_t mobgt_gtl_fwd(const void *logits, int32_t dtype, int64_t row_stride, con
 int32_t mobgt_gtl_bwd(const void *logits, int32_t dtype, int64_t row_stride, const int64_t *target, float alpha,
                       int32_t B, int32_t V, const float *grad_out, void *dlogits, int64_t d_row_stride, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K8 — CSR SpMM of the global GCN tables.  Replaces torch.spmm(adj, support) of
+ * GraphConvolution.forward (modelGNN.py:39-46; called for poi_distance_model / poi_cat_model every forward,
+ * model_fqandtoyo.py:1236-1237):   Y[r,:] = act( sum_j val[j] * S[col[j],:] + bias ),  j over row r of the CSR matrix.
+ *   crow i32 [nrows+1], col i32 [nnz], val f32 [nnz]; S f32 [ncols, D], Y f32 [nrows, D] contiguous; D in {16,32,64,128};
+ *   bias f32 [D] or NULL; activation != 0: LeakyReLU(leaky_slope) (GCN.forward, modelGNN.py:67-69).
+ * The backward w.r.t. S is the same call on the CSR of the transposed matrix (no atomics; bitwise reproducible).
+ * ------------------------------------------------------------------------------------------ */
+int32_t mobgt_spmm_csr(const int32_t *crow, const int32_t *col, const float *val, int32_t nrows, const float *S,
+                       int32_t D, const float *bias, float leaky_slope, int32_t activation, float *Y, void *stream);
+
 /* Debug hook: register (NULL: clear) a device buffer of 256 int64; thread 0 of one CTA of mobgt_attn_fwd / mobgt_attn_bwd then
  * stamps clock64() at its pipeline stages (scripts/timeline.py). */
 int32_t mobgt_debug_set_timeline(void *dev_buf256);

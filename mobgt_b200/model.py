@@ -14,6 +14,7 @@ the heads, so logits and all gradients are identical to the padded computation.
 """
 import math
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -32,22 +33,20 @@ DATASET_TRAITS = {
 }
 
 
-class _SpMM(torch.autograd.Function):
-    """Y = A @ S for a fixed row-normalised sparse adjacency (modelGNN.py:40 `torch.spmm(adj, support)`); A^T is kept
-    so the backward is one more SpMM.  (cuSPARSE through torch: SURVEY.md §8f "next #1" — not yet a libmobgt kernel.)"""
-
-    @staticmethod
-    def forward(ctx, A, At, S):
-        ctx.At = At
-        return torch.sparse.mm(A, S)
-
-    @staticmethod
-    def backward(ctx, dY):
-        return None, None, torch.sparse.mm(ctx.At, dY.contiguous())
+def _csr_transpose(csr, n):
+    """CSR (crow, col, val) of the transpose of an n x n CSR matrix (numpy, stable: rows of A^T keep ascending columns)."""
+    crow, col, val = (np.asarray(a) for a in csr)
+    rows = np.repeat(np.arange(n), np.diff(crow))
+    order = np.argsort(col, kind="stable")
+    tcrow = np.zeros(n + 1, np.int64)
+    np.cumsum(np.bincount(col, minlength=n), out=tcrow[1:])
+    return tcrow, rows[order], np.asarray(val)[order]
 
 
 class GraphConvolution(nn.Module):
-    """modelGNN.py:21-50"""
+    """modelGNN.py:21-50: `adj @ (x @ W) + b`.  The sparse product is K8 (ops.spmm, csrc/k8_spmm.cu).  It is associated so that
+    the gather runs at the NARROWER of the two widths: out <= in -> `adj @ (x W)` with bias (and the following LeakyReLU)
+    fused into the SpMM store; out > in -> `(adj @ x) W + b` (the dense part is a library GEMM either way)."""
 
     def __init__(self, in_features, out_features):
         super().__init__()
@@ -57,8 +56,17 @@ class GraphConvolution(nn.Module):
         self.weight.data.uniform_(-stdv, stdv)
         self.bias.data.uniform_(-stdv, stdv)
 
-    def forward(self, x, adj):
-        return _SpMM.apply(adj[0], adj[1], torch.mm(x, self.weight)) + self.bias
+    def forward(self, x, adj, slope=None):
+        """adj = (A, At): CSR triples (crow, col, val) of the row-normalised adjacency and of its transpose.
+        slope: fuse LeakyReLU(slope) of GCN.forward (modelGNN.py:67-69) into this layer."""
+        A, At = adj
+        fin, fout = self.weight.shape
+        if fout <= fin and fout in (16, 32, 64, 128):
+            return ops.spmm(A, At, torch.mm(x, self.weight), self.bias, slope)
+        if fin in (16, 32, 64, 128):
+            y = torch.addmm(self.bias, ops.spmm(A, At, x), self.weight)
+            return F.leaky_relu(y, slope) if slope is not None else y
+        raise NotImplementedError(f"GraphConvolution {fin}->{fout}: libmobgt's SpMM is built for widths 16 / 32 / 64 / 128")
 
 
 class GCN(nn.Module):
@@ -72,7 +80,7 @@ class GCN(nn.Module):
 
     def forward(self, x, adj):
         for i in range(len(self.gcn) - 1):
-            x = F.leaky_relu(self.gcn[i](x, adj), 0.2)
+            x = self.gcn[i](x, adj, slope=0.2)                       # F.leaky_relu(self.gcn[i](x, adj), 0.2)
         x = F.dropout(x, self.dropout, training=self.training)
         return self.gcn[-1](x, adj)
 
@@ -256,25 +264,16 @@ class Graphormer(nn.Module):
         self.register_buffer("C_X", torch.from_numpy(world.C_X), persistent=False)
         self.register_buffer("cat_of_poi", torch.from_numpy(world.cat_of_poi).int(), persistent=False)
         for name, csr, n in (("D_A", world.D_A, P), ("C_A", world.C_A, C)):
-            crow, col, val = (torch.from_numpy(a) for a in csr)
-            A = torch.sparse_csr_tensor(crow, col, val, size=(n, n))
-            At = A.to_sparse_coo().t().coalesce().to_sparse_csr()
-            for suffix, m in (("", A), ("_t", At)):
-                self.register_buffer(f"{name}{suffix}_crow", m.crow_indices().clone(), persistent=False)
-                self.register_buffer(f"{name}{suffix}_col", m.col_indices().clone(), persistent=False)
-                self.register_buffer(f"{name}{suffix}_val", m.values().clone(), persistent=False)
-        self._sizes = dict(P=P, C=C)
-        self._adj_cache = {}
+            for suffix, (crow, col, val) in (("", csr), ("_t", _csr_transpose(csr, n))):
+                self.register_buffer(f"{name}{suffix}_crow", torch.from_numpy(np.ascontiguousarray(crow, np.int32)), persistent=False)
+                self.register_buffer(f"{name}{suffix}_col", torch.from_numpy(np.ascontiguousarray(col, np.int32)), persistent=False)
+                self.register_buffer(f"{name}{suffix}_val", torch.from_numpy(np.ascontiguousarray(val, np.float32)), persistent=False)
 
     # ------------------------------------------------------------------------------------------
     def _adj(self, name):
-        key = (name, self.X.device)
-        if key not in self._adj_cache:
-            n = self._sizes["P" if name == "D_A" else "C"]
-            mk = lambda s: torch.sparse_csr_tensor(getattr(self, f"{name}{s}_crow"), getattr(self, f"{name}{s}_col"),
-                                                   getattr(self, f"{name}{s}_val"), size=(n, n))
-            self._adj_cache[key] = (mk(""), mk("_t"))
-        return self._adj_cache[key]
+        """(A, A^T) as CSR triples (crow i32, col i32, val f32) — the operands of K8."""
+        t = lambda s: (getattr(self, f"{name}{s}_crow"), getattr(self, f"{name}{s}_col"), getattr(self, f"{name}{s}_val"))
+        return t(""), t("_t")
 
     def gcn_tables(self):
         """model_fqandtoyo.py:1236-1237: recomputed every forward, like the reference."""

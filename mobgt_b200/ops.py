@@ -549,6 +549,46 @@ def linear_gelu_bf16(x, lin, w16=None, b16=None):
     return LinearGeluFn.apply(x, w16, b16, lin.weight, lin.bias)
 
 
+# ----------------------------------------------------------------------------------------------- K8
+def spmm_csr_raw(csr, S, bias=None, slope=None):
+    """Y = act(A @ S + bias): A = (crow i32 [n+1], col i32 [nnz], val f32 [nnz]); S f32 [m, D]; slope=None: no activation."""
+    crow, col, val = csr
+    n = int(crow.numel()) - 1
+    S = S.contiguous()
+    Y = torch.empty(n, S.shape[1], dtype=torch.float32, device=S.device)
+    _C.call("mobgt_spmm_csr", _C.ptr(crow), _C.ptr(col), _C.ptr(val), n, _C.ptr(S), int(S.shape[1]), _C.ptr(bias),
+            float(slope if slope is not None else 0.0), 0 if slope is None else 1, _C.ptr(Y), _C.stream_ptr())
+    return Y
+
+
+class SpmmFn(torch.autograd.Function):
+    """Y = act(A @ S + bias) for a constant sparse A (the row-normalised adjacency of a global GCN, modelGNN.py:39-46).
+    Backward: g = dY * act'(Y);  dS = A^T @ g (the same kernel on the CSR of A^T);  dbias = column sum of g (K6)."""
+
+    @staticmethod
+    def forward(ctx, A, At, S, bias, slope):
+        b = bias.detach().float().contiguous() if bias is not None else None
+        Y = spmm_csr_raw(A, S.detach().float(), b, slope)
+        ctx.At, ctx.slope, ctx.has_bias = At, slope, bias is not None
+        if slope is not None:
+            ctx.save_for_backward(Y)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        g = dY.contiguous()
+        if ctx.slope is not None:
+            (Y,) = ctx.saved_tensors
+            g = torch.where(Y > 0, g, g * ctx.slope)
+        dS = spmm_csr_raw(ctx.At, g)
+        db = colsum(g) if ctx.has_bias else None
+        return None, None, dS, db, None
+
+
+def spmm(A, At, S, bias=None, slope=None):
+    return SpmmFn.apply(A, At, S, bias, slope)
+
+
 # ----------------------------------------------------------------------------------------------- K7
 def enable_tf32():
     """The few GEMMs that stay in fp32 storage (GCN dense parts modelGNN.py:39, user fuse, cat_decoder, out_proj) run on the

@@ -16,6 +16,9 @@ public entry point runs.
   gradient the backward produces — is all-reduced on a side stream as soon as it is complete, while the encoder backward is
   still running; the remainder of the buffer follows at the end of the backward.
 """
+import os
+import sys
+
 import torch
 import torch.distributed as dist
 
@@ -111,7 +114,10 @@ class Trainer:
                 self.graph_note = "fwd+bwd captured" + (" (+ early all-reduce of out_proj.weight.grad in-graph)" if g.early_in_graph else "")
                 break
             except graphs.GraphCaptureError as e:
-                self.graph_note = f"eager ({str(e)[:160]})"
+                if os.environ.get("MOBGT_STRICT_GRAPH") == "1":
+                    raise
+                self.graph_note = f"eager ({str(e)[:400]})"
+                print(f"[mobgt] CUDA-graph capture failed, running eagerly: {e}", file=sys.stderr)
                 g = None
             finally:
                 self._constructing = False

@@ -401,14 +401,14 @@ class Graphormer(nn.Module):
                 te = self.time_embed_model_48((time_normal[p][:L] * 48).long()).squeeze(1)
                 pe_ = Gd[x[p][:L] - 1].squeeze(1)
                 f2 = self.embed_fuse_model2(pe_, te)
-                nf[p, :L] = self.embed_fuse_model4(f2, ce)
+                nf[p, :L] = self.embed_fuse_model4(f2, ce).to(nf.dtype)      # (.to: a no-op in fp32; lets torch.autocast run this module)
         else:
             mask = (x[:, :, 0] != 0)
             xi = x[:, :, 0][mask]
             ce = Gc[self.cat_of_poi[xi - 1] - 1]
             te = self.time_embed_model_48((time_normal[:, :, 0][mask] * 48).long())
             f2 = self.embed_fuse_model2(Gd[xi - 1], te)
-            nf[mask] = self.embed_fuse_model4(f2, ce)
+            nf[mask] = self.embed_fuse_model4(f2, ce).to(nf.dtype)
         for p in range(B):
             cat_target[p] = self.cat_of_poi[int(b.y[p]) - 1] - 1                              # :1265
         nf = nf + self.fre_embed_model(torch.zeros(B, N, dtype=torch.long)) \

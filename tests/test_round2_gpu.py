@@ -70,6 +70,46 @@ def test_k7_gradient_tail_loss(lib_built, B, V, alpha, dtype):
     assert (xg.grad.float().cpu() - gr).abs().max().item() <= tol * gr.abs().max().item() + 1e-12
 
 
+# ------------------------------------------------------------------------------------------------------- K8
+@pytest.mark.parametrize("n,D,density", [(300, 16, 0.2), (3679, 64, 0.01), (60000, 16, 0.0005), (5000, 128, 0.004), (253, 32, 0.2)])
+def test_k8_spmm_csr_forward_backward(lib_built, n, D, density):
+    """Y = LeakyReLU(A @ S + b) and its gradients against torch on the dense matrix (fp32; sums in a different order: 1e-5)."""
+    from mobgt_b200 import ops
+    from mobgt_b200.model import _csr_transpose
+    rng = np.random.default_rng(n + D)
+    nnz_row = np.maximum(1, rng.poisson(density * n, size=n))
+    nnz_row[rng.integers(0, n, 3)] = 0                                           # empty rows
+    crow = np.zeros(n + 1, np.int64)
+    np.cumsum(nnz_row, out=crow[1:])
+    col = np.concatenate([np.sort(rng.choice(n, size=k, replace=False)) for k in nnz_row]).astype(np.int64)
+    val = rng.random(len(col)).astype(np.float32)
+    A = tuple(torch.from_numpy(np.ascontiguousarray(a, dt)).cuda() for a, dt in zip((crow, col, val), (np.int32, np.int32, np.float32)))
+    At = tuple(torch.from_numpy(np.ascontiguousarray(a, dt)).cuda() for a, dt in zip(_csr_transpose((crow, col, val), n), (np.int32, np.int32, np.float32)))
+    g = torch.Generator().manual_seed(1)
+    S = torch.randn(n, D, generator=g)
+    b = torch.randn(D, generator=g)
+    dY = torch.randn(n, D, generator=g)
+    dense = torch.sparse_csr_tensor(torch.from_numpy(crow), torch.from_numpy(col), torch.from_numpy(val), size=(n, n)).to_dense() \
+        if n <= 6000 else None
+    for slope in (None, 0.2):
+        Sg, bg = S.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+        Y = ops.spmm(A, At, Sg, bg, slope)
+        (Y * dY.cuda()).sum().backward()
+        Sr, br = S.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        if dense is not None:
+            Z = dense @ Sr + br
+        else:
+            Z = torch.sparse.mm(torch.sparse_csr_tensor(torch.from_numpy(crow), torch.from_numpy(col), torch.from_numpy(val), size=(n, n)), Sr) + br
+        Yr = F.leaky_relu(Z, slope) if slope is not None else Z
+        (Yr * dY).sum().backward()
+        for got, ref, name in ((Y, Yr, "Y"), (Sg.grad, Sr.grad, "dS"), (bg.grad, br.grad, "db")):
+            err = (got.detach().cpu() - ref.detach()).abs().max().item()
+            assert err <= 2e-5 * max(1.0, ref.abs().max().item()), (name, slope, err)
+    # no bias, bitwise reproducible
+    Y1, Y2 = ops.spmm_csr_raw(A, S.cuda()), ops.spmm_csr_raw(A, S.cuda())
+    assert torch.equal(Y1, Y2)
+
+
 # ------------------------------------------------------------------------------------------------------- multi_hop_max_dist
 def _tables(H=8, bins=64, seed=0):
     g = torch.Generator().manual_seed(seed)
@@ -265,23 +305,19 @@ def test_k5_topk_and_rank_vs_independent_fp32(lib_built):
 
 
 # ------------------------------------------------------------------------------------------------------- canonical shapes
-def _grad_table(om, pm):
-    """per-parameter (norm-wise relative error, reference norm) of the product gradients against the oracle's"""
-    ref_g = {k: p.grad for k, p in om.named_parameters() if p.grad is not None}
+def _grad_table(ref_g, got_g):
+    """per-parameter norm-wise relative error of `got_g` against `ref_g` (dicts name -> CPU fp32 gradient)"""
     gmax = max(r.abs().max().item() for r in ref_g.values())
     table = {}
-    for k, p in pm.named_parameters():
-        if k not in ref_g:
-            continue
-        r = ref_g[k]
-        if p.grad is None:
+    for k, r in ref_g.items():
+        g = got_g.get(k)
+        if g is None:
             assert r.abs().max().item() == 0.0, k
             continue
-        g = p.grad.float().cpu()
         if r.abs().max().item() < 1e-6 * gmax:            # mathematically-zero gradients (softmax ignores a per-row constant)
             assert g.abs().max().item() < 1e-3 * gmax, k
             continue
-        table[k] = ((g - r).norm().item() / r.norm().item(), r.norm().item())
+        table[k] = (g - r).norm().item() / r.norm().item()
     return table
 
 
@@ -295,9 +331,13 @@ CANONICAL = {
 
 @pytest.mark.parametrize("case", ["c2", "c4"])
 def test_canonical_model_on_baseline_shapes(lib_built, case):
-    """6 layers, ffn 1024, hidden 128, 8 heads, multi_hop_max_dist 20 (README.md:62) on BASELINE-shaped batches: logits and
-    loss within 2e-2 of the fp32 oracle; EVERY parameter gradient within 2e-2 norm-wise, except the tensors listed with their
-    own measured bound in tests/golden/grad_tolerance_table.json (each with the reason)."""
+    """6 layers, ffn 1024, hidden 128, 8 heads, multi_hop_max_dist 20 (README.md:62) on BASELINE-shaped batches against the fp32
+    oracle: logits and loss within 2e-2; EVERY parameter gradient within 2e-2 norm-wise — or, where twelve chained bf16 GEMM
+    layers make that unreachable for ANY bf16 implementation, no worse than 1.5 x the error of the oracle itself run under
+    torch.autocast(bfloat16) (the reference's `--precision 16` mixed-precision mode: Linear / matmul in 16 bit, softmax /
+    LayerNorm / losses in fp32) on the same batch.  The measured table (ours | autocast) goes to gpurun_out/ and is committed
+    under profiles/."""
+    import copy
     dataset_name, cfg, spec = CANONICAL[case]
     w, items, om, pm, ob, pb = _pair(dataset_name, cfg, spec, n_layers=6, ffn=1024, seed=2)
     with torch.no_grad():
@@ -306,25 +346,32 @@ def test_canonical_model_on_baseline_shapes(lib_built, case):
     for a, r in zip(got, ref):
         assert a.shape == r.shape
         assert (a.float().cpu() - r).abs().max().item() <= 2e-2 * max(1.0, r.abs().max().item())
-    for m_ in (om, pm):
+    om16 = copy.deepcopy(om)
+    for m_ in (om, om16, pm):
         m_.train()
         m_.poi_distance_model.eval()
         m_.poi_cat_model.eval()
     pm.pos_embed.p = 0.0
     lref = om.training_loss(ob)
     lref.backward()
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        l16 = om16.training_loss(ob)
+    l16.backward()
     lgot = pm.training_step(pb)
     lgot.backward()
     assert abs(lgot.item() - lref.item()) <= 2e-2 * abs(lref.item()), (lgot.item(), lref.item())
-    table = _grad_table(om, pm)
-    assert len(table) > 100
+    ref_g = {k: p.grad for k, p in om.named_parameters() if p.grad is not None}
+    ours = _grad_table(ref_g, {k: p.grad.float().cpu() for k, p in pm.named_parameters() if p.grad is not None})
+    auto = _grad_table(ref_g, {k: p.grad.float() for k, p in om16.named_parameters() if p.grad is not None})
+    assert len(ours) > 100
     out_dir = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out_dir):
-        json.dump({k: [float(e), float(n)] for k, (e, n) in sorted(table.items(), key=lambda kv: -kv[1][0])},
+        rows = sorted(ours, key=lambda k: -ours[k])
+        json.dump({"case": case, "loss": [lgot.item(), lref.item(), l16.item()],
+                   "columns": ["ours vs fp32 oracle", "oracle under torch.autocast(bf16) vs fp32 oracle"],
+                   "rows": {k: [round(ours[k], 5), round(auto.get(k, float("nan")), 5)] for k in rows}},
                   open(os.path.join(out_dir, f"grad_errors_{case}.json"), "w"), indent=0)
-    tol_path = os.path.join(HERE, "golden", "grad_tolerance_table.json")
-    exceptions = json.load(open(tol_path)).get(case, {}) if os.path.exists(tol_path) else {}
-    bad = {k: e for k, (e, _) in table.items() if e > float(exceptions.get(k, {}).get("bound", 2e-2))}
+    bad = {k: (e, auto.get(k)) for k, e in ours.items() if e > max(2e-2, 1.5 * auto.get(k, 0.0))}
     assert not bad, bad
 
 
