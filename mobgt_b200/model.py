@@ -61,9 +61,10 @@ class GraphConvolution(nn.Module):
         slope: fuse LeakyReLU(slope) of GCN.forward (modelGNN.py:67-69) into this layer."""
         A, At = adj
         fin, fout = self.weight.shape
-        if fout <= fin and fout in (16, 32, 64, 128):
+        ok = (16, 32, 64, 128)                                       # the widths K8 is built for
+        if fout in ok and (fout <= fin or fin not in ok):
             return ops.spmm(A, At, torch.mm(x, self.weight), self.bias, slope)
-        if fin in (16, 32, 64, 128):
+        if fin in ok:
             y = torch.addmm(self.bias, ops.spmm(A, At, x), self.weight)
             return F.leaky_relu(y, slope) if slope is not None else y
         raise NotImplementedError(f"GraphConvolution {fin}->{fout}: libmobgt's SpMM is built for widths 16 / 32 / 64 / 128")
@@ -252,6 +253,7 @@ class Graphormer(nn.Module):
         self._w16.register(("emb", "fuse4"), [self.embed_fuse_model4.fuse_embed])
         self.final_ln = nn.LayerNorm(2 * hidden_dim + 64)
         self.out_proj = nn.Linear(2 * hidden_dim + 64, P + tr["poi_extra"])
+        self._w16.register(("head", "out"), [self.out_proj])          # training head: bf16 GEMM (fp16 under the reference's AMP)
         self.ELU = nn.ELU()
         self.graph_token = nn.Embedding(1, D)
         self.graph_token_virtual_distance = nn.Embedding(1, H)
@@ -342,7 +344,9 @@ class Graphormer(nn.Module):
         loss, and the same pass of the backward gives d(logits)."""
         z, b = self.features(batched_data)
         cat_logits = self.cat_decoder(z)
-        poi_logits = self.out_proj(z)
+        # POI logits in bf16 (the reference's `--precision 16` runs this Linear in fp16): [B, P] x 2 bytes instead of 4 through
+        # the loss kernels, and a bf16 tensor-core GEMM forward and backward
+        poi_logits = ops.linear_bf16(z.to(torch.bfloat16), self.out_proj, *self._w16.get(("head", "out")))
         if self.dataset_name == "toyotagraph":
             loss1 = ops.gradient_tail_loss(cat_logits, self.cat_target, 0.1)                            # :1464-1469
             loss2 = ops.log_softmax_nll_loss(poi_logits, b.y, ignore_index=0)     # :1425 + data.py:165 NLLLoss(ignore_index=0)

@@ -438,28 +438,62 @@ def add_dropout_layer_norm(x, y, ln, p, training, want="f32", need_s=False):
 
 
 
+_grad_ready = {}          # id(param) -> callable(param): fired when a Linear backward has finished that parameter's gradient
+
+
+def on_grad_ready(param, fn):
+    """Register `fn(param)` to run right after a libmobgt Linear backward has added `param`'s gradient into `param.grad` (the
+    trainer starts the early all-reduce of out_proj.weight there).  fn=None removes the registration."""
+    if fn is None:
+        _grad_ready.pop(id(param), None)
+    else:
+        _grad_ready[id(param)] = fn
+
+
+def _deliver_param_grads(masters, dw16, db):
+    """Gradients of the fp32 master parameters of a (possibly fused) Linear.  When the masters already own gradient buffers
+    (the trainer's flat fp32 buffer: `p.grad` are views of it) the bf16 weight gradient is ADDED straight into them — one
+    mixed-precision kernel per parameter instead of a cast kernel plus an AccumulateGrad add — and autograd gets None.
+    Otherwise (plain autograd use) fp32 gradients are returned."""
+    m = len(masters) // 2
+    ws, bs = masters[:m], masters[m:]
+    if all(p.grad is not None for p in masters):
+        r = 0
+        for w, b in zip(ws, bs):
+            n = w.shape[0]
+            w.grad.add_(dw16[r:r + n])
+            b.grad.add_(db[r:r + n])
+            r += n
+            fn = _grad_ready.get(id(w))
+            if fn is not None:
+                fn(w)
+        return (None,) * len(masters)
+    rows = [w.shape[0] for w in ws]
+    dw = dw16.float()
+    if m == 1:
+        return (dw, db)
+    return tuple(dw.split(rows, 0)) + tuple(db.split(rows, 0))
+
+
 class LinearBiasFn(torch.autograd.Function):
     """y = x W^T + b with bf16 operands (library GEMMs).  w16 / b16 are the bf16 working copies of the fp32 master parameters
     `masters` = (w_0, ..., w_{m-1}, b_0, ..., b_{m-1}) — m > 1 when several nn.Linear are fused into one GEMM (q, k, v), their
-    rows stacked in w16.  The gradients go straight to the masters in fp32; the bias gradient dy.sum(0) is the K6 column-sum
-    kernel (fp32 accumulation, fixed order) instead of torch's generic reduce."""
+    rows stacked in w16.  The gradients go straight to the masters in fp32 (`_deliver_param_grads`); the bias gradient
+    dy.sum(0) is the K6 column-sum kernel (fp32 accumulation, fixed order) instead of torch's generic reduce."""
 
     @staticmethod
     def forward(ctx, x, w16, b16, *masters):
         ctx.save_for_backward(x, w16)
-        ctx.rows = [w.shape[0] for w in masters[:len(masters) // 2]]
+        ctx.masters = masters
         return torch.nn.functional.linear(x, w16, b16)
 
     @staticmethod
     def backward(ctx, dy):
         x, w16 = ctx.saved_tensors
         dy = dy.contiguous()
-        dx = dy @ w16
-        dw = (dy.t() @ x).float()
-        db = colsum(dy)
-        if len(ctx.rows) == 1:
-            return dx, None, None, dw, db
-        return (dx, None, None) + tuple(dw.split(ctx.rows, 0)) + tuple(db.split(ctx.rows, 0))
+        dx = dy @ w16 if ctx.needs_input_grad[0] else None
+        grads = _deliver_param_grads(ctx.masters, dy.t() @ x, colsum(dy))
+        return (dx, None, None) + grads
 
 
 class Bf16Weights:
@@ -533,13 +567,14 @@ class LinearGeluFn(torch.autograd.Function):
     def forward(ctx, x, w16, b16, w_master, b_master):
         h = torch.nn.functional.linear(x, w16, b16)
         ctx.save_for_backward(x, w16, h)
+        ctx.masters = (w_master, b_master)
         return torch.nn.functional.gelu(h)
 
     @staticmethod
     def backward(ctx, da):
         x, w16, h = ctx.saved_tensors
         dh, db = gelu_bwd_colsum_raw(da.contiguous(), h)
-        return dh @ w16, None, None, (dh.t() @ x).float(), db
+        return (dh @ w16, None, None) + _deliver_param_grads(ctx.masters, dh.t() @ x, db)
 
 
 def linear_gelu_bf16(x, lin, w16=None, b16=None):

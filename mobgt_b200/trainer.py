@@ -22,7 +22,7 @@ import sys
 import torch
 import torch.distributed as dist
 
-from . import graphs, parallel
+from . import graphs, ops, parallel
 
 
 def _signature(batch):
@@ -52,7 +52,7 @@ class Trainer:
             w = model.out_proj.weight
             off = (w.grad.data_ptr() - self.flat.data_ptr()) // 4
             self._early = (int(off), int(off) + w.numel())
-            w.register_post_accumulate_grad_hook(self._on_head_grad)
+            ops.on_grad_ready(w, self._on_head_grad)          # fired by the head Linear's backward (ops.LinearBiasFn)
 
     # ---------------------------------------------------------------------------------------- gradient exchange
     def _on_head_grad(self, _param):
@@ -133,7 +133,7 @@ class Trainer:
                 g.load(batch)
                 loss = g.run()
                 self.graph_steps += 1
-                return loss, g.early_in_graph
+                return loss.detach(), g.early_in_graph
             except graphs.ShapeMismatch:
                 pass
         self.eager_steps += 1
@@ -142,7 +142,9 @@ class Trainer:
         loss = self.model.training_step(batch)
         loss.backward()
         self._join_early()
-        return loss, self._early_joined
+        # detached: a live reference to the autograd graph would keep this step's AccumulateGrad nodes (bound to the stream
+        # they were created on) alive into the next step — fatal for a later CUDA-graph capture on another stream
+        return loss.detach(), self._early_joined
 
     def train_step(self, batch):
         loss, early_done = self.forward_backward(batch)
