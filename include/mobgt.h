@@ -258,7 +258,9 @@ int32_t mobgt_gelu_bwd_colsum(const void *da_bf16, const void *h_bf16, int32_t N
  *            lse f32 [B] (saved for backward), loss f32 [2] = {loss, number of live rows}.
  *   gtl:     GradientTailLoss(alpha, beta = 1, k = 1), model_fqandtoyo.py:545-550: mean over [B, V] of
  *            -alpha (1-p) log p on the target class and -p log(1-p) elsewhere, p = sigmoid(logit).  loss f32 [1].
- * dlogits has the dtype of logits.
+ * dlogits has the dtype of logits.  Rows may be PADDED: row_stride >= V, and when d_row_stride exceeds V by fewer than 16 elements the
+ * padding columns of dlogits are zero-filled (a head whose class count is padded to a multiple of 8 for the GEMMs: the padding
+ * classes take no part in the loss and get no gradient).
  * ------------------------------------------------------------------------------------------ */
 int64_t mobgt_loss_workspace_bytes(int32_t B, int32_t V);
 int32_t mobgt_lsm_nll_fwd(const void *logits, int32_t dtype, int64_t row_stride, const int64_t *target,

@@ -102,7 +102,8 @@ template <typename T>
 __global__ void __launch_bounds__(kLossThreads) k7_nll_bwd_kernel(const T *__restrict__ x, int64_t stride, int V,
                                                                  const int64_t *__restrict__ target, int64_t ignore_index,
                                                                  const float *__restrict__ lse, const float *__restrict__ aux,
-                                                                 const float *__restrict__ gout, T *__restrict__ dx, int64_t dstride) {
+                                                                 const float *__restrict__ gout, T *__restrict__ dx, int64_t dstride,
+                                                                 int Vpad) {
     const int row = blockIdx.y;
     const int64_t t = target[row];
     const bool live = t != ignore_index && t >= 0 && t < V;
@@ -117,6 +118,8 @@ __global__ void __launch_bounds__(kLossThreads) k7_nll_bwd_kernel(const T *__res
         if (c < V) {
             const float p = live ? __expf(ldf(xr + c) - l) : 0.f;
             stf(dr + c, (p - (c == (int)t ? 1.f : 0.f)) * scale);
+        } else if (c < Vpad) {
+            stf(dr + c, 0.f);          // padding classes of a row (see mobgt.h): no gradient
         }
     }
 }
@@ -173,7 +176,8 @@ __global__ void __launch_bounds__(kLossThreads) k7_sum_finish_kernel(const float
 template <typename T>
 __global__ void __launch_bounds__(kLossThreads) k7_gtl_bwd_kernel(const T *__restrict__ x, int64_t stride, int V,
                                                                  const int64_t *__restrict__ target, float alpha, float inv_count,
-                                                                 const float *__restrict__ gout, T *__restrict__ dx, int64_t dstride) {
+                                                                 const float *__restrict__ gout, T *__restrict__ dx, int64_t dstride,
+                                                                 int Vpad) {
     const int row = blockIdx.y;
     const int t = (int)target[row];
     const float scale = __ldg(gout) * inv_count;
@@ -184,6 +188,7 @@ __global__ void __launch_bounds__(kLossThreads) k7_gtl_bwd_kernel(const T *__res
     for (int u = 0; u < 8; ++u) {
         const int c = c0 + u * kLossThreads + threadIdx.x;
         if (c < V) stf(dr + c, gtl_df(ldf(xr + c), c == t, alpha) * scale);
+        else if (c < Vpad) stf(dr + c, 0.f);
     }
 }
 
@@ -246,14 +251,16 @@ extern "C" int32_t mobgt_lsm_nll_bwd(const void *logits, int32_t dtype, int64_t 
     MOBGT_LOSS_COMMON("mobgt_lsm_nll_bwd");
     MOBGT_REQUIRE(d_row_stride >= V, MOBGT_ERR_BAD_SHAPE, "mobgt_lsm_nll_bwd: d_row_stride=%lld", (long long)d_row_stride);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    dim3 grid((unsigned)ceil_div(V, kLossThreads * 8), (unsigned)B);
+    // a d_row_stride slightly larger than V (classes padded to a multiple of 8 / 16 for the GEMMs): the padding is zero-filled
+    const int Vpad = (d_row_stride - V < 16) ? (int)d_row_stride : V;
+    dim3 grid((unsigned)ceil_div(Vpad, kLossThreads * 8), (unsigned)B);
     if (dtype == MOBGT_F32)
         k7_nll_bwd_kernel<float><<<grid, kLossThreads, 0, s>>>(static_cast<const float *>(logits), row_stride, V, target, ignore_index,
-                                                              lse, loss, grad_out, static_cast<float *>(dlogits), d_row_stride);
+                                                              lse, loss, grad_out, static_cast<float *>(dlogits), d_row_stride, Vpad);
     else
         k7_nll_bwd_kernel<__nv_bfloat16><<<grid, kLossThreads, 0, s>>>(static_cast<const __nv_bfloat16 *>(logits), row_stride, V, target,
                                                                       ignore_index, lse, loss, grad_out,
-                                                                      static_cast<__nv_bfloat16 *>(dlogits), d_row_stride);
+                                                                      static_cast<__nv_bfloat16 *>(dlogits), d_row_stride, Vpad);
     MOBGT_LAUNCH_OK("k7_nll_bwd_kernel");
     return MOBGT_OK;
 }
@@ -288,15 +295,16 @@ extern "C" int32_t mobgt_gtl_bwd(const void *logits, int32_t dtype, int64_t row_
     MOBGT_LOSS_COMMON("mobgt_gtl_bwd");
     MOBGT_REQUIRE(d_row_stride >= V, MOBGT_ERR_BAD_SHAPE, "mobgt_gtl_bwd: d_row_stride=%lld", (long long)d_row_stride);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    dim3 grid((unsigned)ceil_div(V, kLossThreads * 8), (unsigned)B);
+    const int Vpad = (d_row_stride - V < 16) ? (int)d_row_stride : V;
+    dim3 grid((unsigned)ceil_div(Vpad, kLossThreads * 8), (unsigned)B);
     const float inv = 1.0f / ((float)B * (float)V);
     if (dtype == MOBGT_F32)
         k7_gtl_bwd_kernel<float><<<grid, kLossThreads, 0, s>>>(static_cast<const float *>(logits), row_stride, V, target, alpha, inv,
-                                                              grad_out, static_cast<float *>(dlogits), d_row_stride);
+                                                              grad_out, static_cast<float *>(dlogits), d_row_stride, Vpad);
     else
         k7_gtl_bwd_kernel<__nv_bfloat16><<<grid, kLossThreads, 0, s>>>(static_cast<const __nv_bfloat16 *>(logits), row_stride, V, target,
                                                                       alpha, inv, grad_out, static_cast<__nv_bfloat16 *>(dlogits),
-                                                                      d_row_stride);
+                                                                      d_row_stride, Vpad);
     MOBGT_LAUNCH_OK("k7_gtl_bwd_kernel");
     return MOBGT_OK;
 }

@@ -253,7 +253,7 @@ class Graphormer(nn.Module):
         self._w16.register(("emb", "fuse4"), [self.embed_fuse_model4.fuse_embed])
         self.final_ln = nn.LayerNorm(2 * hidden_dim + 64)
         self.out_proj = nn.Linear(2 * hidden_dim + 64, P + tr["poi_extra"])
-        self._w16.register(("head", "out"), [self.out_proj])          # training head: bf16 GEMM (fp16 under the reference's AMP)
+        self._w16.register(("head", "out"), [self.out_proj], pad_rows_to=8)   # training head: bf16 GEMM (fp16 under the reference's AMP)
         self.ELU = nn.ELU()
         self.graph_token = nn.Embedding(1, D)
         self.graph_token_virtual_distance = nn.Embedding(1, H)
@@ -346,12 +346,14 @@ class Graphormer(nn.Module):
         cat_logits = self.cat_decoder(z)
         # POI logits in bf16 (the reference's `--precision 16` runs this Linear in fp16): [B, P] x 2 bytes instead of 4 through
         # the loss kernels, and a bf16 tensor-core GEMM forward and backward
+        # (class count padded to a multiple of 8 with zero weight rows; the loss kernels ignore the padding columns)
+        V = self.out_proj.weight.shape[0]
         poi_logits = ops.linear_bf16(z.to(torch.bfloat16), self.out_proj, *self._w16.get(("head", "out")))
         if self.dataset_name == "toyotagraph":
             loss1 = ops.gradient_tail_loss(cat_logits, self.cat_target, 0.1)                            # :1464-1469
-            loss2 = ops.log_softmax_nll_loss(poi_logits, b.y, ignore_index=0)     # :1425 + data.py:165 NLLLoss(ignore_index=0)
+            loss2 = ops.log_softmax_nll_loss(poi_logits, b.y, ignore_index=0, n_classes=V)   # :1425 + data.py:165 NLLLoss(ignore_index=0)
             return loss1 + loss2
-        return ops.gradient_tail_loss(poi_logits, b.y - 1, 0.2)                                         # :1447-1460
+        return ops.gradient_tail_loss(poi_logits, b.y - 1, 0.2, n_classes=V)                            # :1447-1460
 
     def eval_targets(self, batched_data):
         """y_true of validation_step / test_step (model_fqandtoyo.py:1485-1493, 1531-1539): `y - 1` for the datasets in the

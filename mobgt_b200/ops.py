@@ -469,7 +469,8 @@ def _deliver_param_grads(masters, dw16, db):
                 fn(w)
         return (None,) * len(masters)
     rows = [w.shape[0] for w in ws]
-    dw = dw16.float()
+    tot = sum(rows)                           # (the working copy may carry zero padding rows behind the real ones)
+    dw, db = dw16[:tot].float(), db[:tot]
     if m == 1:
         return (dw, db)
     return tuple(dw.split(rows, 0)) + tuple(db.split(rows, 0))
@@ -502,17 +503,22 @@ class Bf16Weights:
 
     def __init__(self):
         self.groups = []          # (key, [linears])
+        self.pad = {}
         self.bufs = {}
         self.stamp = None
 
-    def register(self, key, linears):
+    def register(self, key, linears, pad_rows_to=1):
+        """pad_rows_to: round the row count of the working copy up to a multiple (zero rows / zero bias) — the head, whose
+        class count (P + 1) is odd, is padded to a multiple of 8 so that its GEMMs and column sums stay 16-byte aligned."""
         self.groups.append((key, list(linears)))
+        self.pad[key] = int(pad_rows_to)
 
     def _alloc(self, dev):
         for key, lins in self.groups:
             rows = sum(l.weight.shape[0] for l in lins)
-            w = torch.empty(rows, lins[0].weight.shape[1], dtype=torch.bfloat16, device=dev)
-            b = torch.empty(rows, dtype=torch.bfloat16, device=dev)
+            rows = (rows + self.pad[key] - 1) // self.pad[key] * self.pad[key]
+            w = torch.zeros(rows, lins[0].weight.shape[1], dtype=torch.bfloat16, device=dev)
+            b = torch.zeros(rows, dtype=torch.bfloat16, device=dev)
             self.bufs[key] = (w, b)
         self.dst, self.src = [], []
         for key, lins in self.groups:
@@ -643,63 +649,68 @@ class LogSoftmaxNllFn(torch.autograd.Function):
     """mean_{rows: target != ignore_index} -log_softmax(logits)[target]  (model_fqandtoyo.py:1425, 1470-1471; data.py:165)."""
 
     @staticmethod
-    def forward(ctx, logits, target, ignore_index):
-        assert logits.dim() == 2 and logits.stride(1) == 1
-        B, V = logits.shape
+    def forward(ctx, logits, target, ignore_index, n_classes=None):
+        assert logits.dim() == 2 and logits.is_contiguous()
+        B, Vp = logits.shape
+        V = int(n_classes) if n_classes is not None else Vp          # columns [V, Vp) are row padding: not classes
+        assert V <= Vp < V + 16
         target = target.contiguous().long()
         ws, nws = _loss_ws(B, V, logits.device)
         lse = torch.empty(B, dtype=torch.float32, device=logits.device)
         loss = torch.empty(2, dtype=torch.float32, device=logits.device)
-        _C.call("mobgt_lsm_nll_fwd", logits.data_ptr(), _dt(logits), logits.stride(0), _C.ptr(target), int(ignore_index), B, V,
+        _C.call("mobgt_lsm_nll_fwd", logits.data_ptr(), _dt(logits), Vp, _C.ptr(target), int(ignore_index), B, V,
                 _C.ptr(ws), nws, _C.ptr(lse), _C.ptr(loss), _C.stream_ptr())
         ctx.save_for_backward(logits, target, lse, loss)
-        ctx.ignore_index = int(ignore_index)
+        ctx.ignore_index, ctx.V = int(ignore_index), V
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
         logits, target, lse, loss = ctx.saved_tensors
-        B, V = logits.shape
+        B, Vp = logits.shape
         g = g.detach().float().contiguous().view(1)
-        dl = torch.empty(B, V, dtype=logits.dtype, device=logits.device)
-        _C.call("mobgt_lsm_nll_bwd", logits.data_ptr(), _dt(logits), logits.stride(0), _C.ptr(target), ctx.ignore_index, B, V,
-                _C.ptr(lse), _C.ptr(loss), _C.ptr(g), _C.ptr(dl), V, _C.stream_ptr())
-        return dl, None, None
+        dl = torch.empty(B, Vp, dtype=logits.dtype, device=logits.device)
+        _C.call("mobgt_lsm_nll_bwd", logits.data_ptr(), _dt(logits), Vp, _C.ptr(target), ctx.ignore_index, B, ctx.V,
+                _C.ptr(lse), _C.ptr(loss), _C.ptr(g), _C.ptr(dl), Vp, _C.stream_ptr())
+        return dl, None, None, None
 
 
-def log_softmax_nll_loss(logits, target, ignore_index=0):
-    return LogSoftmaxNllFn.apply(logits, target, ignore_index)
+def log_softmax_nll_loss(logits, target, ignore_index=0, n_classes=None):
+    """n_classes < logits.shape[1]: the trailing columns are row padding (not classes)."""
+    return LogSoftmaxNllFn.apply(logits, target, ignore_index, n_classes)
 
 
 class GradientTailLossFn(torch.autograd.Function):
     """GradientTailLoss(inputs, targets, alpha) with beta = k = 1 (model_fqandtoyo.py:545-550)."""
 
     @staticmethod
-    def forward(ctx, logits, target, alpha):
-        assert logits.dim() == 2 and logits.stride(1) == 1
-        B, V = logits.shape
+    def forward(ctx, logits, target, alpha, n_classes=None):
+        assert logits.dim() == 2 and logits.is_contiguous()
+        B, Vp = logits.shape
+        V = int(n_classes) if n_classes is not None else Vp
+        assert V <= Vp < V + 16
         target = target[:B].contiguous().long()              # :547 `targets[:len(inputs)]`
         ws, nws = _loss_ws(B, V, logits.device)
         loss = torch.empty(1, dtype=torch.float32, device=logits.device)
-        _C.call("mobgt_gtl_fwd", logits.data_ptr(), _dt(logits), logits.stride(0), _C.ptr(target), float(alpha), B, V, _C.ptr(ws),
+        _C.call("mobgt_gtl_fwd", logits.data_ptr(), _dt(logits), Vp, _C.ptr(target), float(alpha), B, V, _C.ptr(ws),
                 nws, _C.ptr(loss), _C.stream_ptr())
         ctx.save_for_backward(logits, target)
-        ctx.alpha = float(alpha)
+        ctx.alpha, ctx.V = float(alpha), V
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
         logits, target = ctx.saved_tensors
-        B, V = logits.shape
+        B, Vp = logits.shape
         g = g.detach().float().contiguous().view(1)
-        dl = torch.empty(B, V, dtype=logits.dtype, device=logits.device)
-        _C.call("mobgt_gtl_bwd", logits.data_ptr(), _dt(logits), logits.stride(0), _C.ptr(target), ctx.alpha, B, V, _C.ptr(g),
-                _C.ptr(dl), V, _C.stream_ptr())
-        return dl, None, None
+        dl = torch.empty(B, Vp, dtype=logits.dtype, device=logits.device)
+        _C.call("mobgt_gtl_bwd", logits.data_ptr(), _dt(logits), Vp, _C.ptr(target), ctx.alpha, B, ctx.V, _C.ptr(g),
+                _C.ptr(dl), Vp, _C.stream_ptr())
+        return dl, None, None, None
 
 
-def gradient_tail_loss(logits, target, alpha=0.25):
-    return GradientTailLossFn.apply(logits, target, alpha)
+def gradient_tail_loss(logits, target, alpha=0.25, n_classes=None):
+    return GradientTailLossFn.apply(logits, target, alpha, n_classes)
 
 
 # ----------------------------------------------------------------------------------------------- K5
