@@ -634,6 +634,434 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     MOBGT_STAMP(p.timeline, 4);
 }
 
+
+// =====================================================================================================================
+// Single-box variant: every graph of the launch has at most 128 + 1 tokens (BASELINE configs[1]: graphs <= 128 nodes; also
+// the natural node-count law, median 4 nodes) and dS goes to the layer's bf16 plane (mode 2, the training path).
+//
+// The general kernel above keeps S and dP in separate TMEM columns (352 columns with the three accumulators), both score
+// tiles in registers (246 registers / thread) and double-buffered operand tiles (177 KB): ONE CTA per SM, whose life is a
+// serial chain prologue -> tail -> tile -> epilogue with nothing to overlap it (profiles/r04_k3_timeline.txt).  With a single
+// (query tile, key block) per CTA none of that buffering buys anything, so this variant is sized for TWO CTAs per SM — one
+// CTA's TMA / MMA / TMEM round trips hide behind the other's softmax-gradient math:
+//   * S and dP are produced one after the other into the SAME 128 TMEM columns (P is taken to registers in between):
+//     128 + 3 x 32 = 224 columns -> a 256-column allocation;
+//   * the bias tile is consumed into P before dS exists, so the dS operand image reuses the bias tile's 32 KB;
+//     no double buffers: 97 KB of dynamic shared memory;
+//   * one score tile (64 fp32 P values) in registers at a time: <= 128 registers / thread.
+// Arithmetic, operand layouts, the dropout mask and the single-token tail are those of the general kernel.
+template <bool kDrop>
+__global__ void __launch_bounds__(256, 2)
+k3_attn_bwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                    const __grid_constant__ CUtensorMap tmBias, const __grid_constant__ CUtensorMap tmDS,
+                    const AttnBwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int kRows = kTile + 4;
+    __shared__ __align__(8) uint64_t bar_ld, bar_bias, bar_s, bar_mma;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float sLse[kRows], sDelta[kRows];
+    __shared__ float sA_ds[kRows], sA_pd[kRows];   // tail: dS / dropped P of (row sp, key c)
+    __shared__ float sB_ds[kRows], sB_pd[kRows];   // tail: dS / dropped P of (row r, key sp)
+    __shared__ float sSp[4][kAttD];                // q, k, v, dO of token sp
+    __shared__ float sRed[3][10][kAttD];
+
+    const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, t128 = tid & 127;
+    const bool warp0 = warp_index_uniform() == 0;
+    const int g = blockIdx.x / p.H, h = blockIdx.x - g * p.H;
+    const int t0 = p.tok_off[g];
+    const int Tg = p.tok_off[g + 1] - t0;            // <= 129
+    const bool fold = Tg == kTile + 1;
+    const int nv = fold ? kTile : Tg;                // query rows == key columns covered by the MMA tile
+    const int sp = Tg - 1;                           // the tail token (fold only)
+    const int HD = p.H * kAttD;
+    const int plane = g * p.H + h;
+
+    // ---- global loads issued at the very top (consumed after the barrier / TMA set-up): one row per thread (Tg <= 129 < 256)
+    float lse_pre = 0.f;
+    uint4 o_pre[3], d_pre[3];
+    if (tid < Tg) {
+        lse_pre = p.lse[(size_t)(t0 + tid) * p.H + h];
+        const uint4 *po = reinterpret_cast<const uint4 *>(p.o + (size_t)(t0 + tid) * HD + h * kAttD);
+        const uint4 *pd = reinterpret_cast<const uint4 *>(p.dout + (size_t)(t0 + tid) * HD + h * kAttD);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            o_pre[q] = po[q];
+            d_pre[q] = pd[q];
+        }
+    }
+    float b_row = 0.f, b_col = 0.f;
+    const __nv_bfloat16 *bias_pl = p.bias + (size_t)plane * p.T * p.Tp;
+    if (fold) {
+        if (tid < Tg) b_row = bf16_at(bias_pl + (size_t)sp * p.Tp + tid);
+        if (tid < sp) b_col = bf16_at(bias_pl + (size_t)tid * p.Tp + sp);
+    }
+    float sp_val = 0.f;
+    if (fold && tid < 4 * kAttD) {
+        const int which = tid / kAttD, e = tid - which * kAttD;
+        const __nv_bfloat16 *src = which == 0 ? p.q : which == 1 ? p.k : which == 2 ? p.v : p.dout;
+        const int64_t stride = which == 3 ? (int64_t)HD : p.qkv_stride;
+        sp_val = bf16_at(src + (size_t)(t0 + sp) * stride + h * kAttD + e);
+    }
+    uint8_t *sBD = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // bias tile (128-byte swizzle), later the dS operand image
+    uint8_t *sP = sBD + kBiasTileBytes;
+    uint8_t *sQ = sP + kPBytes;
+    uint8_t *sdO = sQ + kBoxBytes;
+    uint8_t *sK = sdO + kBoxBytes;
+    uint8_t *sV = sK + kBoxBytes;
+
+    if (tid == 0) {
+        mbar_init(&bar_ld, 1);
+        mbar_init(&bar_bias, 1);
+        mbar_init(&bar_s, 1);
+        mbar_init(&bar_mma, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        tma_prefetch_desc(&tmdO);
+        tma_prefetch_desc(&tmBias);
+        tma_prefetch_desc(&tmDS);
+        mbar_expect_tx(&bar_ld, 4 * kBoxTxBytes);
+        tma_load_3d(sK, &tmK, &bar_ld, 0, t0, h * kAttChunks);
+        tma_load_3d(sV, &tmV, &bar_ld, 0, t0, h * kAttChunks);
+        tma_load_3d(sQ, &tmQ, &bar_ld, 0, t0, h * kAttChunks);
+        tma_load_3d(sdO, &tmdO, &bar_ld, 0, t0, h * kAttChunks);
+        mbar_expect_tx(&bar_bias, kBiasTileBytes);
+        tma_load_3d(sBD, &tmBias, &bar_bias, 0, 0, plane);
+        tma_load_3d(sBD + kTile * 128, &tmBias, &bar_bias, 64, 0, plane);
+    }
+    {   // zero the K-padding chunk (d = 24..31) of the four operand boxes
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>((wg == 0 ? sQ : sdO) + 3 * kTile * 16 + t128 * 16) = z;
+        *reinterpret_cast<uint4 *>((wg == 0 ? sK : sV) + 3 * kTile * 16 + t128 * 16) = z;
+    }
+    if (tid < kRows) {   // lse (log2 units; +inf past the graph so that p = 0 there) and D = rowsum(dO * O)
+        float lse2 = INFINITY, dl = 0.f;
+        if (tid < Tg) {
+            lse2 = lse_pre * 1.4426950408889634f;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const uint32_t aw[4] = {o_pre[q].x, o_pre[q].y, o_pre[q].z, o_pre[q].w};
+                const uint32_t bw[4] = {d_pre[q].x, d_pre[q].y, d_pre[q].z, d_pre[q].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    dl += __uint_as_float(aw[e] << 16) * __uint_as_float(bw[e] << 16);
+                    dl += __uint_as_float(aw[e] & 0xFFFF0000u) * __uint_as_float(bw[e] & 0xFFFF0000u);
+                }
+            }
+        }
+        sLse[tid] = lse2;
+        sDelta[tid] = dl;
+    }
+    if (fold && tid < 4 * kAttD) sSp[tid / kAttD][tid % kAttD] = sp_val;
+    if (warp == 0) tmem_alloc<256>(&tmem_slot);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t tS = tmem, tdK = tmem + 128, tdV = tmem + 160, tdQ = tmem + 192;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const int nb = round_up(nv, 16);                 // MMA N / K extent along the keys (and along the queries)
+    const uint32_t id_sn = make_idesc_bf16(kTile, nb, 0, 0);
+
+    if (warp0 && elect_one()) {   // S = Q K^T
+        mbar_wait(&bar_ld, 0);
+        tc_fence_after();
+        const uint32_t aq = smem_u32(sQ), bk = smem_u32(sK);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+            umma_bf16(tS, make_smem_desc(aq + ks * 2 * kTile * 16, kTile * 16, 128),
+                      make_smem_desc(bk + ks * 2 * kTile * 16, kTile * 16, 128), id_sn, ks > 0);
+        umma_commit(&bar_s);
+    }
+    __syncwarp();
+    const float sl2 = p.scale * 1.4426950408889634f;
+    constexpr float kL2e = 1.4426950408889634f;
+    uint32_t seed_lo = 0, seed_hi = 0;
+    if (kDrop) attn_drop_fold_seed(p.drop, seed_lo, seed_hi);
+    const uint32_t th_hi = p.drop.th16 << 16;
+    const float ik = p.drop.inv_keep;
+
+    if (fold) {   // ---- the single-token tail, SIMT (overlaps the S MMA)
+        __nv_bfloat16 *ds16 = reinterpret_cast<__nv_bfloat16 *>(p.dbias) + (size_t)plane * p.T * p.Tp;
+        auto box_row = [&](const uint8_t *box, int row, float (&f)[24]) {
+            const uint8_t *b0 = box + row * 16;
+            unpack24(*reinterpret_cast<const uint4 *>(b0), *reinterpret_cast<const uint4 *>(b0 + kTile * 16),
+                     *reinterpret_cast<const uint4 *>(b0 + 2 * kTile * 16), f);
+        };
+        mbar_wait(&bar_ld, 0);
+        if (tid < Tg) {   // part A: query row sp against key c = tid (itself included)
+            const int c = tid;
+            const uint32_t rk = kDrop ? attn_drop_rowkey((uint32_t)plane, (uint32_t)sp, seed_lo, seed_hi) : 0u;
+            float dot = 0.f, dp = 0.f;
+            if (c < sp) {
+                float kf[24], vf[24];
+                box_row(sK, c, kf);
+                box_row(sV, c, vf);
+#pragma unroll
+                for (int e = 0; e < kAttD; ++e) {
+                    dot = fmaf(sSp[0][e], kf[e], dot);
+                    dp = fmaf(sSp[3][e], vf[e], dp);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < kAttD; ++e) {
+                    dot = fmaf(sSp[0][e], sSp[1][e], dot);
+                    dp = fmaf(sSp[3][e], sSp[2][e], dp);
+                }
+            }
+            const float pr = bwd_exp2(fmaf(dot, sl2, b_row * kL2e) - sLse[sp]);
+            bool kp = true;
+            if (kDrop) kp = (attn_drop_keep8(rk, (uint32_t)(c >> 3), p.drop.th16) >> (c & 7)) & 1u;
+            const float ds = pr * ((kDrop ? (kp ? dp * ik : 0.f) : dp) - sDelta[sp]);
+            sA_ds[c] = ds;
+            sA_pd[c] = kDrop ? (kp ? pr * ik : 0.f) : pr;
+            ds16[(size_t)sp * p.Tp + c] = __float2bfloat16_rn(ds);
+        }
+        if (tid < sp) {   // part B: query row r = tid against key sp
+            const int r = tid;
+            float qf[24], df[24];
+            box_row(sQ, r, qf);
+            box_row(sdO, r, df);
+            float dot = 0.f, dp = 0.f;
+#pragma unroll
+            for (int e = 0; e < kAttD; ++e) {
+                dot = fmaf(qf[e], sSp[1][e], dot);
+                dp = fmaf(df[e], sSp[2][e], dp);
+            }
+            const float pr = bwd_exp2(fmaf(dot, sl2, b_col * kL2e) - sLse[r]);
+            bool kp = true;
+            if (kDrop) {
+                const uint32_t rk = attn_drop_rowkey((uint32_t)plane, (uint32_t)r, seed_lo, seed_hi);
+                kp = (attn_drop_keep8(rk, (uint32_t)(sp >> 3), p.drop.th16) >> (sp & 7)) & 1u;
+            }
+            const float ds = pr * ((kDrop ? (kp ? dp * ik : 0.f) : dp) - sDelta[r]);
+            sB_ds[r] = ds;
+            sB_pd[r] = kDrop ? (kp ? pr * ik : 0.f) : pr;
+            ds16[(size_t)r * p.Tp + sp] = __float2bfloat16_rn(ds);
+        }
+        __syncthreads();
+        if (tid < 240) {   // dQ[sp] = sum_c dS[sp][c] k_c ; dK[sp] = sum_r dS[r][sp] q_r ; dV[sp] = sum_r P[r][sp] dO_r
+            const int seg = tid / kAttD, e = tid - seg * kAttD;
+            const int eo = (e >> 3) * (kTile * 16) + (e & 7) * 2;
+            float aq = 0.f, ak = 0.f, av = 0.f;
+            for (int c = seg; c < sp; c += 10) {
+                aq = fmaf(sA_ds[c], bf16_at(reinterpret_cast<const __nv_bfloat16 *>(sK + c * 16 + eo)), aq);
+                ak = fmaf(sB_ds[c], bf16_at(reinterpret_cast<const __nv_bfloat16 *>(sQ + c * 16 + eo)), ak);
+                av = fmaf(sB_pd[c], bf16_at(reinterpret_cast<const __nv_bfloat16 *>(sdO + c * 16 + eo)), av);
+            }
+            sRed[0][seg][e] = aq;
+            sRed[1][seg][e] = ak;
+            sRed[2][seg][e] = av;
+        }
+        __syncthreads();
+        if (tid < 3 * kAttD) {
+            const int which = tid / kAttD, e = tid - which * kAttD;
+            float a = 0.f;
+#pragma unroll
+            for (int sg = 0; sg < 10; ++sg) a += sRed[which][sg][e];
+            a += which == 0 ? sA_ds[sp] * sSp[1][e] : which == 1 ? sA_ds[sp] * sSp[0][e] : sA_pd[sp] * sSp[3][e];
+            if (which < 2) a *= p.scale;
+            __nv_bfloat16 *dst = (which == 0 ? p.dq : which == 1 ? p.dk : p.dv) + (size_t)(t0 + sp) * p.dqkv_stride + h * kAttD + e;
+            *dst = __float2bfloat16_rn(a);
+        }
+    }
+
+    // ---- the tile: thread (wg, t128) owns query row t128 and the 16-column chunks c0 = 16 wg + 32 cc
+    const int row = t128;
+    const bool row_ok = row < nv;
+    const bool warp_live = (warp & 3) * 32 < nv;
+    const float lse2 = sLse[row];
+    const float delta = sDelta[row];
+    uint32_t pv[4][16];        // raw S, then (in place) the fp32 probabilities P: the only per-tile register array
+    uint32_t keep[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};   // dropout keep bits, bit 16 (cc & 1) + 8 q8 + e of word cc >> 1
+    mbar_wait(&bar_s, 0);
+    mbar_wait(&bar_bias, 0);
+    tc_fence_after();
+    if (warp_live) {
+        const uint32_t rowkey = kDrop ? attn_drop_rowkey((uint32_t)plane, (uint32_t)row, seed_lo, seed_hi) : 0u;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+            if (wg * 16 + cc * 32 < nb) tmem_ld16(tS + lane_off + wg * 16 + cc * 32, pv[cc]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int c0 = wg * 16 + cc * 32;
+            if (c0 >= nb) continue;
+#pragma unroll
+            for (int q8 = 0; q8 < 2; ++q8) {
+                const int c8 = (c0 >> 3) + q8;
+                const int colb = c8 * 8;
+                const uint8_t *bp = sBD + (c8 >> 3) * (kTile * 128) + t128 * 128 + (((c8 & 7) ^ (t128 & 7)) << 4);
+                uint4 bvv = *reinterpret_cast<const uint4 *>(bp);
+                if (!row_ok) bvv = make_uint4(0, 0, 0, 0);       // bias rows past the graph are never written: not numbers
+                const uint32_t bw[4] = {bvv.x, bvv.y, bvv.z, bvv.w};
+                const bool full = colb + 8 <= nv;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float bias = __uint_as_float((e & 1) ? (bw[e >> 1] & 0xFFFF0000u) : (bw[e >> 1] << 16));
+                    const float s = fmaf(__uint_as_float(pv[cc][q8 * 8 + e]), sl2, bias * kL2e);
+                    float pr = bwd_exp2(s - lse2);               // rows past the graph: lse = +inf -> 0
+                    if (!full && colb + e >= nv) pr = 0.f;       // key columns past the graph
+                    pv[cc][q8 * 8 + e] = __float_as_uint(pr);
+                }
+                if (kDrop) {
+                    const AttnDropWords dw = attn_drop_words(rowkey, (uint32_t)c8);
+                    uint32_t m = 0;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) m |= attn_drop_keep(dw, e, th_hi) ? (1u << e) : 0u;
+                    const int sh = 16 * (cc & 1) + 8 * q8;
+                    keep[cc >> 1] = (keep[cc >> 1] & ~(0xFFu << sh)) | (m << sh);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();              // every thread has S (as P) in registers and is done with the bias tile
+    if (warp0 && elect_one()) {   // dP = dO V^T into the columns S occupied
+        tc_fence_after();
+        const uint32_t ado = smem_u32(sdO), bv = smem_u32(sV);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+            umma_bf16(tS, make_smem_desc(ado + ks * 2 * kTile * 16, kTile * 16, 128),
+                      make_smem_desc(bv + ks * 2 * kTile * 16, kTile * 16, 128), id_sn, ks > 0);
+        umma_commit(&bar_s);
+    }
+    __syncwarp();
+    if (warp_live) {              // the (dropped-out) P operand of dV, written while the dP MMA runs
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int c0 = wg * 16 + cc * 32;
+            if (c0 >= nb) continue;
+#pragma unroll
+            for (int q8 = 0; q8 < 2; ++q8) {
+                const int c8 = (c0 >> 3) + q8;
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float pr = __uint_as_float(pv[cc][q8 * 8 + e]);
+                    if (kDrop) f[e] = ((keep[cc >> 1] >> (16 * (cc & 1) + 8 * q8 + e)) & 1u) ? pr * ik : 0.f;
+                    else f[e] = pr;
+                }
+                uint4 pk;
+                pk.x = pack_bf16(f[0], f[1]); pk.y = pack_bf16(f[2], f[3]);
+                pk.z = pack_bf16(f[4], f[5]); pk.w = pack_bf16(f[6], f[7]);
+                *reinterpret_cast<uint4 *>(sP + c8 * (kTile * 16) + t128 * 16) = pk;
+            }
+        }
+    }
+    mbar_wait(&bar_s, 1);
+    tc_fence_after();
+    if (warp_live) {              // dS = P o (dP - D) -> bf16 operand image over the bias tile
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t dpv[2][16];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (wg * 16 + (2 * half + u) * 32 < nb) tmem_ld16(tS + lane_off + wg * 16 + (2 * half + u) * 32, dpv[u]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int cc = 2 * half + u;
+                const int c0 = wg * 16 + cc * 32;
+                if (c0 >= nb) continue;
+#pragma unroll
+                for (int q8 = 0; q8 < 2; ++q8) {
+                    const int c8 = (c0 >> 3) + q8;
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float pr = __uint_as_float(pv[cc][q8 * 8 + e]);
+                        float dp = __uint_as_float(dpv[u][q8 * 8 + e]);
+                        if (kDrop) dp = ((keep[cc >> 1] >> (16 * (cc & 1) + 8 * q8 + e)) & 1u) ? dp * ik : 0.f;
+                        f[e] = pr * (dp - delta);
+                    }
+                    uint4 dk;
+                    dk.x = pack_bf16(f[0], f[1]); dk.y = pack_bf16(f[2], f[3]);
+                    dk.z = pack_bf16(f[4], f[5]); dk.w = pack_bf16(f[6], f[7]);
+                    *reinterpret_cast<uint4 *>(sBD + c8 * (kTile * 16) + t128 * 16) = dk;
+                }
+            }
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (warp0 && elect_one()) {
+        tc_fence_after();
+        tma_store_4d(&tmDS, sBD, 0, 0, 0, plane);      // this layer's dS plane straight from the MMA operand image
+        tma_store_commit();
+        const uint32_t aP = smem_u32(sP), aS = smem_u32(sBD);
+        const uint32_t bQ = smem_u32(sQ), bdO = smem_u32(sdO), bK = smem_u32(sK);
+        const uint32_t id_t = make_idesc_bf16(kTile, 32, 1, 1);   // A = P^T / dS^T (MN-major), B MN-major
+        const uint32_t id_q = make_idesc_bf16(kTile, 32, 0, 1);   // A = dS (K-major),        B MN-major
+        for (int ks = 0; ks < nb / 16; ++ks)      // dV = P^T dO   (K = query rows)
+            umma_bf16(tdV, make_smem_desc(aP + ks * 256, 128, kTile * 16), make_smem_desc(bdO + ks * 256, 128, kTile * 16), id_t, ks > 0);
+        for (int ks = 0; ks < nb / 16; ++ks)      // dK = dS^T Q
+            umma_bf16(tdK, make_smem_desc(aS + ks * 256, 128, kTile * 16), make_smem_desc(bQ + ks * 256, 128, kTile * 16), id_t, ks > 0);
+        for (int ks = 0; ks < nb / 16; ++ks)      // dQ = dS K     (K = key rows)
+            umma_bf16(tdQ, make_smem_desc(aS + ks * 2 * kTile * 16, kTile * 16, 128), make_smem_desc(bK + ks * 256, 128, kTile * 16), id_q, ks > 0);
+        umma_commit(&bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(&bar_mma, 0);
+    tc_fence_after();
+    if (warp_live) {
+        {   // dK (warpgroup 0) / dV (warpgroup 1): key row = t128
+            uint32_t kvv[32];
+            tmem_ld32((wg == 0 ? tdK : tdV) + lane_off, kvv);
+            tmem_ld_wait();
+            if (row_ok) {
+                const float sc = wg == 0 ? p.scale : 1.0f;
+                if (fold) {   // + dS[sp][krow] q_sp (dK) / P[sp][krow] dO_sp (dV)
+                    const float a = wg == 0 ? sA_ds[row] : sA_pd[row];
+                    const float *vec = wg == 0 ? sSp[0] : sSp[3];
+#pragma unroll
+                    for (int e = 0; e < kAttD; ++e) kvv[e] = __float_as_uint(fmaf(a, vec[e], __uint_as_float(kvv[e])));
+                }
+                uint32_t w[12];
+#pragma unroll
+                for (int e = 0; e < 12; ++e)
+                    w[e] = pack_bf16(__uint_as_float(kvv[2 * e]) * sc, __uint_as_float(kvv[2 * e + 1]) * sc);
+                uint4 *dst = reinterpret_cast<uint4 *>((wg == 0 ? p.dk : p.dv) + (size_t)(t0 + row) * p.dqkv_stride + h * kAttD);
+                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+            }
+        }
+        {   // dQ: columns [0,16) by warpgroup 0, [16,24) by warpgroup 1
+            uint32_t qv[16];
+            tmem_ld16(tdQ + lane_off + wg * 16, qv);
+            tmem_ld_wait();
+            if (row_ok) {
+                if (fold) {   // + dS[row][sp] k_sp
+                    const float a = sB_ds[row];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (wg == 0 || e < 8) qv[e] = __float_as_uint(fmaf(a, sSp[1][wg * 16 + e], __uint_as_float(qv[e])));
+                }
+                uint32_t w[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    w[e] = pack_bf16(__uint_as_float(qv[2 * e]) * p.scale, __uint_as_float(qv[2 * e + 1]) * p.scale);
+                uint4 *dst = reinterpret_cast<uint4 *>(p.dq + (size_t)(t0 + row) * p.dqkv_stride + h * kAttD);
+                if (wg == 0) {
+                    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                } else {
+                    dst[2] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+    }
+    if (warp0) tma_store_wait_all();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
 }  // namespace mobgt
 
 using namespace mobgt;
@@ -710,6 +1138,15 @@ extern "C" int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, i
                     static_cast<const __nv_bfloat16 *>(v),
                     qkv_row_stride,
                     static_cast<const __nv_bfloat16 *>(bias)};
+    if (accumulate == 2 && t_max_host <= kTile + 1) {   // every graph fits one (query tile, key block): two CTAs per SM
+        const size_t smem1 = (size_t)kBiasTileBytes + kPBytes + 4 * kBoxBytes + 1024;
+        auto kern1 = drop.th16 ? k3_attn_bwd1_kernel<true> : k3_attn_bwd1_kernel<false>;
+        MOBGT_CUDA_OK(cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        MOBGT_CUDA_OK(cudaFuncSetAttribute(kern1, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        kern1<<<B * H, 256, smem1, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmdO, tmB, tmDS, p);
+        MOBGT_LAUNCH_OK("k3_attn_bwd1_kernel");
+        return MOBGT_OK;
+    }
     kern<<<B * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmdO, tmB, tmDS, p);
     MOBGT_LAUNCH_OK("k3_attn_bwd_kernel");
     return MOBGT_OK;

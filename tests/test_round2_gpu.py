@@ -110,6 +110,57 @@ def test_k8_spmm_csr_forward_backward(lib_built, n, D, density):
     assert torch.equal(Y1, Y2)
 
 
+# ------------------------------------------------------------------------------------------------------- K3 bwd, single-box variant
+@pytest.mark.parametrize("sizes", [(128, 128, 5, 128), (127, 100, 1, 64, 33, 17, 128), (12, 3, 7, 1, 9)])
+def test_attention_bwd_single_box_variant(lib_built, sizes):
+    """mobgt_attn_bwd in mode 2 (per-layer bf16 dS plane) on batches whose graphs all have <= 128 nodes takes the two-CTA-per-SM
+    single-box kernel (csrc/k3_attn_bwd.cu: k3_attn_bwd1_kernel).  dq / dk / dv and the dS plane against torch autograd with the
+    same dropout mask, and against the general kernel (mode 0, fp32 dS)."""
+    from mobgt_b200 import collator, ops, synth
+    from test_k2_k3_k4 import tables, torch_attention_diff
+    w = synth.make_world("c1", seed=1)
+    items = []
+    for k, n in enumerate(sizes):
+        items += synth.make_items(w, 1, 512, seed=70 + k, n_fixed=n, start=k)
+    b = collator.collator_toyota(items, max_node=512, multi_hop_max_dist=20, rel_pos_max=1024, world=w)
+    assert b.N <= 128
+    B = len(items)
+    R, Pp, E, W, t = tables(seed=4)
+    cu = [x.cuda().contiguous() for x in (R, Pp, E, W.view(-1), t.view(-1))]
+    bias = ops.bias_fwd_raw(b, *cu, out_dtype=torch.bfloat16)
+    ntok = int(b.tok_pos.numel())
+    gen = torch.Generator().manual_seed(13)
+    qkv = (torch.randn(ntok, 3 * 192, generator=gen) * 1.2).to(torch.bfloat16)
+    dout = torch.randn(ntok, 192, generator=gen).to(torch.bfloat16)
+    tok_off = b.tok_off.cpu().numpy()
+    for p, seed in ((0.0, 0), (0.1, 0x0123456789ABCDEF)):
+        out, lse = ops.attn_fwd_raw(qkv.cuda(), bias, b, drop_p=p, seed=seed)
+        plane = torch.full(bias.shape, float("nan"), dtype=torch.bfloat16, device="cuda")
+        dqkv = ops.attn_bwd_raw(qkv.cuda(), bias, out, dout.cuda(), lse, b, plane, 2, drop_p=p, seed=seed)        # single-box kernel
+        db32 = torch.full(bias.shape, float("nan"), dtype=torch.float32, device="cuda")
+        dqkv0 = ops.attn_bwd_raw(qkv.cuda(), bias, out, dout.cuda(), lse, b, db32, 0, drop_p=p, seed=seed)        # general kernel
+        torch.cuda.synchronize()
+        q32 = qkv.float().requires_grad_(True)
+        b32 = bias.float().cpu().requires_grad_(True)
+        ref, _ = torch_attention_diff(q32, b32, tok_off, drop=(p, seed) if p > 0 else None)
+        (ref * dout.float()).sum().backward()
+        gq = q32.grad
+        err = (dqkv.float().cpu() - gq).abs().max().item()
+        assert err <= 2e-2 * max(1.0, gq.abs().max().item()), f"p={p}: dqkv max err {err}"
+        assert (dqkv.float() - dqkv0.float()).abs().max().item() <= 1e-2 * max(1.0, gq.abs().max().item())
+        for g in range(B):
+            Tg = int(tok_off[g + 1] - tok_off[g])
+            gb = b32.grad[g, :, :Tg, :Tg]
+            got = plane[g, :, :Tg, :Tg].float().cpu()
+            assert torch.isfinite(got).all(), (p, g)
+            assert (got - gb).abs().max().item() <= 2e-2 * max(1.0, gb.abs().max().item()), (p, g)
+            assert (got - db32[g, :, :Tg, :Tg].cpu()).abs().max().item() <= 1e-2 * max(1.0, gb.abs().max().item()), (p, g)
+    # bitwise reproducible
+    plane2 = torch.empty_like(plane)
+    dq2 = ops.attn_bwd_raw(qkv.cuda(), bias, out, dout.cuda(), lse, b, plane2, 2, drop_p=p, seed=seed)
+    assert torch.equal(dq2, dqkv)
+
+
 # ------------------------------------------------------------------------------------------------------- multi_hop_max_dist
 def _tables(H=8, bins=64, seed=0):
     g = torch.Generator().manual_seed(seed)
