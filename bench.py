@@ -484,8 +484,9 @@ def run_ours(args):
                            "tokens_per_gpu": tokens, "distinct_batches": nbatches, "parallelism": f"dp{world_size}",
                            "cuda_graph": tr.graph_note, "graph_replays_of_timed_steps": f"{replays_value}/{args.steps}",
                            "e2e_graph_replays": f"{tr.graph_steps - eg0}/{e2e_steps}",
-                           "allreduce": ("out_proj bucket overlapped with backward + remainder" if (world_size > 1 and not args.no_overlap)
-                                         else ("single flat all-reduce" if world_size > 1 else "none")),
+                           "allreduce": ("none" if world_size == 1 else
+                                         "one NCCL all-reduce (AVG) of the flat fp32 gradient buffer after the graph replay; eager steps "
+                                         "start the out_proj bucket during the backward"),
                            "e2e_collate_stream": "side" if side else "training",
                            "l2": "per-step working set (activations + bias planes, > 1 GB) exceeds the 126 MB L2"},
                 "e2e": {"value": graphs * e2e_steps / (ms_e2e / 1e3), "unit": "graphs/s", "h2d_bytes_per_step": h2d,

@@ -285,6 +285,14 @@ int32_t mobgt_gtl_bwd(const void *logits, int32_t dtype, int64_t row_stride, con
 int32_t mobgt_spmm_csr(const int32_t *crow, const int32_t *col, const float *val, int32_t nrows, const float *S,
                        int32_t D, const float *bias, float leaky_slope, int32_t activation, float *Y, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K9 — AdamW over flat fp32 buffers (param, grad, exp_avg, exp_avg_sq: n elements each, n % 4 == 0, 16-byte aligned).
+ * Replaces torch.optim.AdamW of configure_optimizers (model_fqandtoyo.py:1599-1616) in the training loop: one pass,
+ * 28 B / parameter.  `step` is the 1-based update count (bias correction); decoupled weight decay, no amsgrad.
+ * ------------------------------------------------------------------------------------------ */
+int32_t mobgt_adamw_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
+                         float beta2, float eps, float weight_decay, int64_t step, void *stream);
+
 /* Debug hook: register (NULL: clear) a device buffer of 256 int64; thread 0 of one CTA of mobgt_attn_fwd / mobgt_attn_bwd then
  * stamps clock64() at its pipeline stages (scripts/timeline.py). */
 int32_t mobgt_debug_set_timeline(void *dev_buf256);

@@ -422,7 +422,12 @@ class Graphormer(nn.Module):
 
     def configure_optimizers(self):
         """model_fqandtoyo.py:1599-1616"""
-        optimizer = torch.optim.AdamW(self.parameters(), lr=self.peak_lr, weight_decay=self.weight_decay, fused=True)
+        params = list(self.parameters())
+        if params[0].is_cuda:        # K9: one kernel over flat parameter / gradient buffers (same arithmetic as torch's AdamW)
+            from .optim import FlatAdamW
+            optimizer = FlatAdamW(params, lr=self.peak_lr, weight_decay=self.weight_decay)
+        else:
+            optimizer = torch.optim.AdamW(params, lr=self.peak_lr, weight_decay=self.weight_decay)
         sched = PolynomialDecayLR(optimizer, warmup_updates=self.warmup_updates, tot_updates=self.tot_updates, lr=self.peak_lr,
                                   end_lr=self.end_lr, power=1.0)
         return [optimizer], [{"scheduler": sched, "name": "learning_rate", "interval": "step", "frequency": 1}]

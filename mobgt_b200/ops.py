@@ -497,6 +497,16 @@ class LinearBiasFn(torch.autograd.Function):
         return (dx, None, None) + grads
 
 
+_weight_epoch = 0
+
+
+def weights_changed():
+    """Called by an optimizer that writes parameters behind autograd's back (optim.FlatAdamW): invalidates every bf16
+    working copy (Bf16Weights compares this counter next to the tensors' version counters)."""
+    global _weight_epoch
+    _weight_epoch += 1
+
+
 class Bf16Weights:
     """bf16 working copies of a set of fp32 nn.Linear parameters, refreshed with ONE multi-tensor copy when an optimizer step
     has changed the masters (tensor version counters) — instead of a cast kernel + autograd node per parameter per step."""
@@ -538,11 +548,11 @@ class Bf16Weights:
         if not self.bufs or next(iter(self.bufs.values()))[0].device != dev:
             self._alloc(dev)
             self.stamp = None
-        stamp = sum(p._version for p in self.src)
+        stamp = (sum(p._version for p in self.src), _weight_epoch)
         if stamp != self.stamp:
             with torch.no_grad():
                 torch._foreach_copy_(self.dst, [p.detach() for p in self.src])
-            self.stamp = sum(p._version for p in self.src)
+            self.stamp = (sum(p._version for p in self.src), _weight_epoch)
 
 
 def linear_bf16(x, lin, w16=None, b16=None):

@@ -12,9 +12,12 @@ public entry point runs.
   `1 / world` is folded into it (ReduceOp.AVG).
 * Forward + backward of a batch shape that repeats is captured in a CUDA graph (`graphs.GraphedTrainStep`) and replayed;
   a shape is captured when it is seen for the second time, other shapes run eagerly (same kernels, ~550 launches).
-* With world_size > 1 and `overlap=True` the gradient of `out_proj.weight` — 77 of the 92 MB at P = 60 000 and the FIRST
-  gradient the backward produces — is all-reduced on a side stream as soon as it is complete, while the encoder backward is
-  still running; the remainder of the buffer follows at the end of the backward.
+* With world_size > 1 and `overlap=True` an EAGER step all-reduces the gradient of `out_proj.weight` — 77 of the 92 MB at
+  P = 60 000 and the FIRST gradient the backward produces — on a side stream as soon as it is complete, while the encoder
+  backward is still running; the remainder of the buffer follows at the end of the backward.  A graph-replayed step issues one
+  flat all-reduce after the replay: capturing the NCCL collective inside the graph (`overlap_in_graph=True`) was measured on
+  2 x B200 (profiles/r2/r2g_bench_n2_*.json): 6.68 ms/step against 6.65 ms without it, and the process then hung in
+  destroy_process_group — so it is off by default.
 """
 import os
 import sys
@@ -31,12 +34,15 @@ def _signature(batch):
 
 
 class Trainer:
-    def __init__(self, model, device, world_size=1, cuda_graph=True, overlap=True, overlap_in_graph=True, max_graphs=4, group=None):
+    def __init__(self, model, device, world_size=1, cuda_graph=True, overlap=True, overlap_in_graph=False, max_graphs=4, group=None):
         self.model, self.dev, self.world, self.group = model, torch.device(device), int(world_size), group
-        self.grads = parallel.FlatGrads(model.parameters(), self.dev)
-        self.flat = self.grads.flat
         (self.opt,), (cfg,) = model.configure_optimizers()
         self.sched = cfg["scheduler"]
+        if hasattr(self.opt, "flat_grad"):      # optim.FlatAdamW owns the flat buffers (p.data / p.grad are views of them)
+            self.flat = self.opt.flat_grad
+        else:
+            self.grads = parallel.FlatGrads(model.parameters(), self.dev)
+            self.flat = self.grads.flat
         self.use_graph, self.max_graphs = bool(cuda_graph), int(max_graphs)
         self._graphs, self._seen, self._no_capture = {}, {}, set()
         self.eager_steps = self.graph_steps = 0

@@ -70,6 +70,42 @@ def test_k7_gradient_tail_loss(lib_built, B, V, alpha, dtype):
     assert (xg.grad.float().cpu() - gr).abs().max().item() <= tol * gr.abs().max().item() + 1e-12
 
 
+# ------------------------------------------------------------------------------------------------------- K9
+def test_k9_flat_adamw_matches_torch(lib_built):
+    """optim.FlatAdamW (one kernel over flat buffers) against torch.optim.AdamW on the same parameters and gradients, five steps
+    with a changing learning rate; parameters stay views of the flat buffer and a bf16 working copy notices the update."""
+    from mobgt_b200 import ops
+    from mobgt_b200.optim import FlatAdamW
+    torch.manual_seed(0)
+    shapes = [(60001, 320), (320,), (192, 1024), (7,), (1, 8), (128 * 64, 1)]
+    ours = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    o1 = FlatAdamW(ours, lr=2e-4, weight_decay=0.01)
+    o2 = torch.optim.AdamW(ref, lr=2e-4, weight_decay=0.01)
+    lin = torch.nn.Linear(1024, 192).cuda()
+    w16 = ops.Bf16Weights()
+    holder = torch.nn.Linear(1024, 192).cuda()
+    holder.weight, holder.bias = ours[2], torch.nn.Parameter(torch.zeros(192, device="cuda"))
+    w16.register("k", [holder])
+    w16.refresh()
+    for step in range(5):
+        lr = 2e-4 * (step + 1) / 5
+        for grp in o1.param_groups + o2.param_groups:
+            grp["lr"] = lr
+        for a, b in zip(ours, ref):
+            gnew = torch.randn_like(a) * (0.1 + step)
+            a.grad.copy_(gnew)                      # gradients are views of the flat buffer: written in place
+            b.grad = gnew.clone()
+        o1.step()
+        o2.step()
+    for a, b in zip(ours, ref):
+        assert a.data_ptr() >= o1.flat_param.data_ptr() and a.data_ptr() < o1.flat_param.data_ptr() + o1.n * 4
+        assert (a.detach() - b.detach()).abs().max().item() <= 2e-6 * max(1.0, b.abs().max().item())
+    w16.refresh()
+    assert torch.equal(w16.get("k")[0], ours[2].detach().to(torch.bfloat16))
+    del lin
+
+
 # ------------------------------------------------------------------------------------------------------- K8
 @pytest.mark.parametrize("n,D,density", [(300, 16, 0.2), (3679, 64, 0.01), (60000, 16, 0.0005), (5000, 128, 0.004), (253, 32, 0.2)])
 def test_k8_spmm_csr_forward_backward(lib_built, n, D, density):
