@@ -191,7 +191,8 @@ int32_t mobgt_segment_sum(const void *src, int32_t src_dtype, int64_t src_stride
  *                  (u64 in device memory, optional) is folded into the seed at run time, so a CUDA graph that replays the
  *                  kernels with baked-in arguments draws a fresh mask per replay (increment it inside the graph).  Backward:
  *                  ds = LayerNorm-backward(dy [+ dy_bf16]) + ds_ext (gradient reaching s from its later uses, optional);
- *                  dx = ds ; dyb_out (bf16, optional) = ds * mask / (1 - p).
+ *                  dx = ds ; dyb_out (bf16, optional) = ds * mask / (1 - p) ; dyb_colsum (f32 [D], optional) = the column sums of
+ *                  dyb_out, i.e. the bias gradient of the nn.Linear whose output y was (no separate column-sum pass).
  *   colsum:        out[c] = sum_r src[r, c]  (src bf16 or f32, row stride in elements; fp32 accumulation, fixed order).
  *   D multiple of 32 with D/32 in {2,4,6,8,10,12,16}.
  * ------------------------------------------------------------------------------------------ */
@@ -206,8 +207,8 @@ int32_t mobgt_add_dropout_layernorm_fwd(const float *x, const void *y_bf16, floa
                                         float *mean, float *rstd, const void *seed_dev, void *stream);
 int32_t mobgt_add_dropout_layernorm_bwd(const float *dy, const void *dy_bf16, const float *ds_ext, const float *s_saved,
                                         const float *gamma, const float *mean, const float *rstd, int32_t N, int32_t D, float drop_p,
-                                        uint64_t seed, float *dx, void *dyb_out, float *dgamma, float *dbeta, void *workspace,
-                                        int64_t workspace_bytes, const void *seed_dev, void *stream);
+                                        uint64_t seed, float *dx, void *dyb_out, float *dgamma, float *dbeta, float *dyb_colsum,
+                                        void *workspace, int64_t workspace_bytes, const void *seed_dev, void *stream);
 int64_t mobgt_colsum_workspace_bytes(int32_t N, int32_t C);
 int32_t mobgt_colsum(const void *src, int32_t src_dtype, int64_t src_stride, int32_t N, int32_t C, float *out, void *workspace,
                      int64_t workspace_bytes, void *stream);

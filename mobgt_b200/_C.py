@@ -47,7 +47,7 @@ SIGNATURES = {
     "mobgt_layernorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_p, c_p, c_p, c_p, c_i64, c_p],
     "mobgt_add_dropout_layernorm_fwd": [c_p, c_p, c_f32, ctypes.c_uint64, c_p, c_p, c_f32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "mobgt_add_dropout_layernorm_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_f32, ctypes.c_uint64, c_p, c_p, c_p, c_p,
-                                        c_p, c_i64, c_p, c_p],
+                                        c_p, c_p, c_i64, c_p, c_p],
     "mobgt_colsum_workspace_bytes": [c_i32, c_i32],
     "mobgt_colsum": [c_p, c_i32, c_i64, c_i32, c_i32, c_p, c_p, c_i64, c_p],
     "mobgt_gelu_bwd_colsum": [c_p, c_p, c_i32, c_i32, c_p, c_p, c_p, c_i64, c_p],

@@ -119,15 +119,16 @@ __global__ void __launch_bounds__(kNormWarps * 32) k6_layernorm_bwd_kernel(const
                                                                           float *__restrict__ dx, __nv_bfloat16 *__restrict__ dyb_out,
                                                                           float *__restrict__ partial) {
     constexpr int D = PER * 32;
-    __shared__ float sred[kNormWarps][2 * D];
+    __shared__ float sred[kNormWarps][3 * D];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     mix_device_seed(seed_dev, seed_lo, seed_hi);
-    float g[PER], dg[PER], db[PER];
+    float g[PER], dg[PER], db[PER], dc[PER];     // dc: column sums of dyb_out = the bias gradient of the Linear that produced y
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         g[i] = gamma[i * 32 + lane];
         dg[i] = 0.f;
         db[i] = 0.f;
+        dc[i] = 0.f;
     }
     for (int row = blockIdx.x * kNormWarps + warp; row < N; row += gridDim.x * kNormWarps) {
         const size_t base = (size_t)row * D;
@@ -154,7 +155,9 @@ __global__ void __launch_bounds__(kNormWarps * 32) k6_layernorm_bwd_kernel(const
             dx[base + i * 32 + lane] = ds;
             if (dyb_out != nullptr) {
                 const bool keep = drop_thresh == 0u || drop_keep((uint32_t)(base + i * 32 + lane), seed_lo, seed_hi, drop_thresh);
-                dyb_out[base + i * 32 + lane] = __float2bfloat16_rn(keep ? ds * (drop_thresh == 0u ? 1.0f : drop_scale) : 0.f);
+                const __nv_bfloat16 yb = __float2bfloat16_rn(keep ? ds * (drop_thresh == 0u ? 1.0f : drop_scale) : 0.f);
+                dyb_out[base + i * 32 + lane] = yb;
+                dc[i] += __bfloat162float(yb);        // the sum of what a column-sum kernel would read back
             }
         }
     }
@@ -162,20 +165,22 @@ __global__ void __launch_bounds__(kNormWarps * 32) k6_layernorm_bwd_kernel(const
     for (int i = 0; i < PER; ++i) {
         sred[warp][i * 32 + lane] = dg[i];
         sred[warp][D + i * 32 + lane] = db[i];
+        sred[warp][2 * D + i * 32 + lane] = dc[i];
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+    for (int c = threadIdx.x; c < 3 * D; c += blockDim.x) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < kNormWarps; ++w) s += sred[w][c];
-        partial[(size_t)blockIdx.x * 2 * D + c] = s;
+        partial[(size_t)blockIdx.x * 3 * D + c] = s;
     }
 }
 
 // out[c] = sum over parts of partial[part][c]: block = 32 columns x 8 rows, row r sums the parts p = r (mod 8) in order, the
 // 8 row sums are folded in order (fixed summation tree: deterministic)
 __global__ void __launch_bounds__(256) k6_reduce_parts_kernel(const float *__restrict__ partial, int nparts, int C,
-                                                              float *__restrict__ out0, int C0, float *__restrict__ out1) {
+                                                              float *__restrict__ out0, int C0, float *__restrict__ out1,
+                                                              int C1 = 1 << 30, float *__restrict__ out2 = nullptr) {
     __shared__ float sfold[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -189,7 +194,8 @@ __global__ void __launch_bounds__(256) k6_reduce_parts_kernel(const float *__res
 #pragma unroll
         for (int r = 1; r < 8; ++r) t += sfold[r][tx];
         if (c < C0) out0[c] = t;
-        else out1[c - C0] = t;
+        else if (c < C0 + C1) out1[c - C0] = t;
+        else if (out2 != nullptr) out2[c - C0 - C1] = t;
     }
 }
 
@@ -320,7 +326,7 @@ using namespace mobgt;
 
 extern "C" int64_t mobgt_layernorm_bwd_workspace_bytes(int32_t D) {
     if (D <= 0 || D % 32 != 0 || D > 512) return -1;
-    return (int64_t)kNormCtas * 2 * D * (int64_t)sizeof(float);
+    return (int64_t)kNormCtas * 3 * D * (int64_t)sizeof(float);
 }
 
 static uint32_t drop_threshold(float p) {
@@ -358,12 +364,14 @@ extern "C" int32_t mobgt_layernorm_fwd(const float *x, const float *gamma, const
 extern "C" int32_t mobgt_add_dropout_layernorm_bwd(const float *dy, const void *dy_bf16, const float *ds_ext, const float *s_saved,
                                                    const float *gamma, const float *mean, const float *rstd, int32_t N, int32_t D,
                                                    float drop_p, uint64_t seed, float *dx, void *dyb_out, float *dgamma, float *dbeta,
-                                                   void *workspace, int64_t workspace_bytes, const void *seed_dev, void *stream) {
+                                                   float *dyb_colsum, void *workspace, int64_t workspace_bytes, const void *seed_dev,
+                                                   void *stream) {
     MOBGT_REQUIRE((dy || dy_bf16) && s_saved && gamma && mean && rstd && dx && dgamma && dbeta && workspace, MOBGT_ERR_NULL,
                   "mobgt_add_dropout_layernorm_bwd: null pointer");
     MOBGT_REQUIRE(D > 0 && D % 32 == 0 && D <= 512, MOBGT_ERR_BAD_SHAPE, "mobgt_add_dropout_layernorm_bwd: D=%d", D);
     MOBGT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, MOBGT_ERR_BAD_SHAPE, "mobgt_add_dropout_layernorm_bwd: p=%f", (double)drop_p);
-    MOBGT_REQUIRE(workspace_bytes >= (int64_t)kNormCtas * 2 * D * 4, MOBGT_ERR_WORKSPACE_TOO_SMALL, "mobgt_add_dropout_layernorm_bwd: workspace");
+    MOBGT_REQUIRE(workspace_bytes >= (int64_t)kNormCtas * 3 * D * 4, MOBGT_ERR_WORKSPACE_TOO_SMALL, "mobgt_add_dropout_layernorm_bwd: workspace");
+    MOBGT_REQUIRE(dyb_colsum == nullptr || dyb_out != nullptr, MOBGT_ERR_NULL, "mobgt_add_dropout_layernorm_bwd: dyb_colsum needs dyb_out");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int grid = N > 0 ? min(kNormCtasBwd, ceil_div(N, kNormWarps)) : 0;
     float *partial = static_cast<float *>(workspace);
@@ -375,7 +383,7 @@ extern "C" int32_t mobgt_add_dropout_layernorm_bwd(const float *dy, const void *
                                         partial)));
         MOBGT_LAUNCH_OK("k6_layernorm_bwd_kernel");
     }
-    k6_reduce_parts_kernel<<<ceil_div(2 * D, 32), 256, 0, s>>>(partial, grid, 2 * D, dgamma, D, dbeta);
+    k6_reduce_parts_kernel<<<ceil_div(3 * D, 32), 256, 0, s>>>(partial, grid, 3 * D, dgamma, D, dbeta, D, dyb_colsum);
     MOBGT_LAUNCH_OK("k6_reduce_parts_kernel");
     return MOBGT_OK;
 }
@@ -384,7 +392,7 @@ extern "C" int32_t mobgt_layernorm_bwd(const float *dy, const void *dy_bf16, con
                                        const float *rstd, int32_t N, int32_t D, float *dx, float *dgamma, float *dbeta, void *workspace,
                                        int64_t workspace_bytes, void *stream) {
     return mobgt_add_dropout_layernorm_bwd(dy, dy_bf16, nullptr, x, gamma, mean, rstd, N, D, 0.f, 0ull, dx, nullptr, dgamma, dbeta,
-                                           workspace, workspace_bytes, nullptr, stream);
+                                           nullptr, workspace, workspace_bytes, nullptr, stream);
 }
 
 extern "C" int64_t mobgt_colsum_workspace_bytes(int32_t N, int32_t C) {

@@ -158,8 +158,8 @@ class MultiHeadAttention(nn.Module):
             bq = torch.cat([q.bias, k.bias, v.bias], 0).detach().to(torch.bfloat16)
             wo = bo = None
         qkv = ops.LinearBiasFn.apply(x16, wq, bq, q.weight, k.weight, v.weight, q.bias, k.bias, v.bias)
-        a = ops.BiasedAttention.apply(qkv, bias_slot, layer, self.attention_dropout_rate if self.training else 0.0)   # :1704
-        return ops.linear_bf16(a, self.output_layer, wo, bo)
+        # attention output BEFORE output_layer: the caller fuses that Linear with the residual block (ops.LinearAddDropoutLNFn)
+        return ops.BiasedAttention.apply(qkv, bias_slot, layer, self.attention_dropout_rate if self.training else 0.0), wo, bo   # :1704
 
 
 class EncoderLayer(nn.Module):
@@ -179,13 +179,15 @@ class EncoderLayer(nn.Module):
         """x: fp32 residual stream [ntok, hidden]; x16: its bf16 copy.  Residual stream and LayerNorms in fp32, GEMMs /
         attention in bf16 (the reference's --precision 16 AMP split).  Each residual add + dropout + LayerNorm is one K6 kernel
         per direction; the Linear bias gradients are the K6 column sum."""
-        y = self.self_attention(x16, bias_slot, layer, w16)
-        x1, y16 = ops.add_dropout_layer_norm(x, y, self.ffn_norm1, self.self_attention_dropout.p, self.training, "bf16", need_s=True)
+        a, wo, bo = self.self_attention(x16, bias_slot, layer, w16)
+        x1, y16 = ops.linear_add_dropout_layer_norm(a, self.self_attention.output_layer, wo, bo, x, self.ffn_norm1,
+                                                    self.self_attention_dropout.p, self.training, "bf16", need_s=True)   # :1708, :1731-1735
         f = self.ffn
         w1, b1 = w16.get((layer, "f1")) if w16 is not None else (None, None)
         w2, b2 = w16.get((layer, "f2")) if w16 is not None else (None, None)
-        y = ops.linear_bf16(ops.linear_gelu_bf16(y16, f.layer1, w1, b1), f.layer2, w2, b2)
-        return ops.add_dropout_layer_norm(x1, y, self.ffn_norm2, self.ffn_dropout.p, self.training, "both")
+        h = ops.linear_gelu_bf16(y16, f.layer1, w1, b1)
+        return ops.linear_add_dropout_layer_norm(h, f.layer2, w2, b2, x1, self.ffn_norm2, self.ffn_dropout.p, self.training,
+                                                 "both")                                                               # :1655, :1737-1741
 
 
 def gradient_tail_loss(inputs, targets, alpha=0.25, beta=1, k=1):

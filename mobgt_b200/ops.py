@@ -378,6 +378,55 @@ def _next_drop_seed():
     return (torch.initial_seed() * 0x9E3779B97F4A7C15 + _drop_calls * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
 
 
+def _adln_fwd(x, y, gamma, beta, eps, p, want):
+    """s = x + dropout(y) ; out = LayerNorm(s)  -> (s, out f32 | None, out bf16 | None, saved tensors, seed)"""
+    x, y = x.contiguous(), y.contiguous()
+    N, D = x.shape
+    dev = x.device
+    s = torch.empty(N, D, dtype=torch.float32, device=dev)
+    out = torch.empty(N, D, dtype=torch.float32, device=dev) if want != "bf16" else None
+    out16 = torch.empty(N, D, dtype=torch.bfloat16, device=dev) if want != "f32" else None
+    mean = torch.empty(N, dtype=torch.float32, device=dev)
+    rstd = torch.empty(N, dtype=torch.float32, device=dev)
+    g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+    seed = _next_drop_seed() if p > 0 else 0
+    _C.call("mobgt_add_dropout_layernorm_fwd", _C.ptr(x), _C.ptr(y), float(p), seed, _C.ptr(g), _C.ptr(b), float(eps), N, D,
+            _C.ptr(s), _C.ptr(out), _C.ptr(out16), _C.ptr(mean), _C.ptr(rstd), _C.ptr(_seed_dev), _C.stream_ptr())
+    return s, out, out16, (s, g, mean, rstd), seed
+
+
+def _adln_bwd(saved, grads, p, seed, want, need_s, seed_dev, want_colsum=False):
+    """-> (dx f32, dy bf16, dgamma, dbeta, column sums of dy | None)"""
+    s, g, mean, rstd = saved
+    N, D = s.shape
+    grads = list(grads)
+    ds_ext = grads.pop(0) if need_s else None
+    if want == "f32":
+        dy32, dy16 = grads[0], None
+    elif want == "bf16":
+        dy32, dy16 = None, grads[0]
+    else:
+        dy32, dy16 = grads
+    if dy32 is None and dy16 is None:          # only the residual branch carries a gradient
+        dy32 = torch.zeros_like(s)
+    c = lambda t: t.contiguous() if t is not None else None
+    dy32, dy16, ds_ext = c(dy32), c(dy16), c(ds_ext)
+    dx = torch.empty_like(s)
+    dyb = torch.empty(N, D, dtype=torch.bfloat16, device=s.device)
+    dgb = torch.empty(3 if want_colsum else 2, D, dtype=torch.float32, device=s.device)
+    ws_bytes = int(_C.lib().mobgt_layernorm_bwd_workspace_bytes(D))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=s.device)
+    _C.call("mobgt_add_dropout_layernorm_bwd", _C.ptr(dy32), _C.ptr(dy16), _C.ptr(ds_ext), _C.ptr(s), _C.ptr(g), _C.ptr(mean),
+            _C.ptr(rstd), N, D, p, seed, _C.ptr(dx), _C.ptr(dyb), dgb[0].data_ptr(), dgb[1].data_ptr(),
+            dgb[2].data_ptr() if want_colsum else None, _C.ptr(ws), ws_bytes, _C.ptr(seed_dev), _C.stream_ptr())
+    return dx, dyb, dgb[0], dgb[1], (dgb[2] if want_colsum else None)
+
+
+def _adln_outputs(s, out, out16, want, need_s):
+    outs = {"f32": (out,), "bf16": (out16,), "both": (out, out16)}[want]
+    return ((s,) + outs) if need_s else outs if len(outs) > 1 else outs[0]
+
+
 class AddDropoutLayerNormFn(torch.autograd.Function):
     """The post-LN residual block of EncoderLayer.forward (model_fqandtoyo.py:1731-1743) in one kernel each way:
         s = x + dropout(y) ;  out = LayerNorm(s)
@@ -386,51 +435,50 @@ class AddDropoutLayerNormFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, y, gamma, beta, eps, p, want, need_s):
-        x, y = x.contiguous(), y.contiguous()
-        N, D = x.shape
-        dev = x.device
-        s = torch.empty(N, D, dtype=torch.float32, device=dev)
-        out = torch.empty(N, D, dtype=torch.float32, device=dev) if want != "bf16" else None
-        out16 = torch.empty(N, D, dtype=torch.bfloat16, device=dev) if want != "f32" else None
-        mean = torch.empty(N, dtype=torch.float32, device=dev)
-        rstd = torch.empty(N, dtype=torch.float32, device=dev)
-        g, b = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
-        seed = _next_drop_seed() if p > 0 else 0
-        _C.call("mobgt_add_dropout_layernorm_fwd", _C.ptr(x), _C.ptr(y), float(p), seed, _C.ptr(g), _C.ptr(b), float(eps), N, D,
-                _C.ptr(s), _C.ptr(out), _C.ptr(out16), _C.ptr(mean), _C.ptr(rstd), _C.ptr(_seed_dev), _C.stream_ptr())
-        ctx.save_for_backward(s, g, mean, rstd)
+        s, out, out16, saved, seed = _adln_fwd(x, y, gamma, beta, eps, p, want)
+        ctx.save_for_backward(*saved)
         ctx.cfg = (float(p), seed, want, need_s)
         ctx.seed_dev = _seed_dev
-        outs = {"f32": (out,), "bf16": (out16,), "both": (out, out16)}[want]
-        return ((s,) + outs) if need_s else outs if len(outs) > 1 else outs[0]
+        return _adln_outputs(s, out, out16, want, need_s)
 
     @staticmethod
     def backward(ctx, *grads):
-        s, g, mean, rstd = ctx.saved_tensors
         p, seed, want, need_s = ctx.cfg
-        N, D = s.shape
-        grads = list(grads)
-        ds_ext = grads.pop(0) if need_s else None
-        if want == "f32":
-            dy32, dy16 = grads[0], None
-        elif want == "bf16":
-            dy32, dy16 = None, grads[0]
-        else:
-            dy32, dy16 = grads
-        if dy32 is None and dy16 is None:          # only the residual branch carries a gradient
-            dy32 = torch.zeros_like(s)
-        c = lambda t: t.contiguous() if t is not None else None
-        dy32, dy16, ds_ext = c(dy32), c(dy16), c(ds_ext)
-        dx = torch.empty_like(s)
-        dyb = torch.empty(N, D, dtype=torch.bfloat16, device=s.device)
-        dgamma = torch.empty(D, dtype=torch.float32, device=s.device)
-        dbeta = torch.empty(D, dtype=torch.float32, device=s.device)
-        ws_bytes = int(_C.lib().mobgt_layernorm_bwd_workspace_bytes(D))
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=s.device)
-        _C.call("mobgt_add_dropout_layernorm_bwd", _C.ptr(dy32), _C.ptr(dy16), _C.ptr(ds_ext), _C.ptr(s), _C.ptr(g), _C.ptr(mean),
-                _C.ptr(rstd), N, D, p, seed, _C.ptr(dx), _C.ptr(dyb), _C.ptr(dgamma), _C.ptr(dbeta), _C.ptr(ws), ws_bytes,
-                _C.ptr(ctx.seed_dev), _C.stream_ptr())
+        dx, dyb, dgamma, dbeta, _ = _adln_bwd(ctx.saved_tensors, grads, p, seed, want, need_s, ctx.seed_dev)
         return dx, dyb, dgamma, dbeta, None, None, None, None
+
+
+class LinearAddDropoutLNFn(torch.autograd.Function):
+    """A sub-layer's closing Linear fused with the residual block that follows it (model_fqandtoyo.py:1708 + :1731-1735,
+    :1655 + :1737-1741):   y = x16 W^T + b ;  s = resid + dropout(y) ;  out = LayerNorm(s).
+    The GEMMs are the library's; fusing the two autograd nodes lets the LayerNorm-backward kernel hand the bias gradient of the
+    Linear (the column sums of dy, accumulated while dy is written) straight to the parameter: no column-sum pass over dy."""
+
+    @staticmethod
+    def forward(ctx, x16, w16, b16, resid, gamma, beta, eps, p, want, need_s, *masters):
+        y = torch.nn.functional.linear(x16, w16, b16)
+        s, out, out16, saved, seed = _adln_fwd(resid, y, gamma, beta, eps, p, want)
+        ctx.save_for_backward(x16, w16, *saved)
+        ctx.cfg = (float(p), seed, want, need_s)
+        ctx.seed_dev, ctx.masters = _seed_dev, masters
+        return _adln_outputs(s, out, out16, want, need_s)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        x16, w16 = ctx.saved_tensors[:2]
+        p, seed, want, need_s = ctx.cfg
+        dres, dy, dgamma, dbeta, dcol = _adln_bwd(ctx.saved_tensors[2:], grads, p, seed, want, need_s, ctx.seed_dev, want_colsum=True)
+        dx16 = dy @ w16
+        pg = _deliver_param_grads(ctx.masters, dy.t() @ x16, dcol)
+        return (dx16, None, None, dres, dgamma, dbeta, None, None, None, None) + pg
+
+
+def linear_add_dropout_layer_norm(x16, lin, w16, b16, resid, ln, p, training, want="f32", need_s=False):
+    """LayerNorm(resid + dropout(lin(x16)))  with lin's bf16 working copies w16 / b16 (None: cast on the fly)."""
+    if w16 is None:
+        w16, b16 = lin.weight.detach().to(torch.bfloat16), lin.bias.detach().to(torch.bfloat16)
+    return LinearAddDropoutLNFn.apply(x16, w16, b16, resid, ln.weight, ln.bias, ln.eps, float(p) if training else 0.0, want, need_s,
+                                      lin.weight, lin.bias)
 
 
 def add_dropout_layer_norm(x, y, ln, p, training, want="f32", need_s=False):

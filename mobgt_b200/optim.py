@@ -17,8 +17,10 @@ class FlatAdamW(torch.optim.Optimizer):
             raise _C.MobgtError("FlatAdamW needs fp32 CUDA parameters (there is no CPU fallback)")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         dev = params[0].device
-        n = sum(p.numel() for p in params)
-        self.n = (n + 3) // 4 * 4                       # float4 granularity of the kernel
+        # every parameter starts on a 16-byte boundary of the flat buffers (the kernels read tables with 128-bit loads); the
+        # padding elements in between stay zero (zero gradient, zero moments -> AdamW leaves them at zero)
+        n = sum((p.numel() + 3) // 4 * 4 for p in params)
+        self.n = n
         self.flat_param = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(self.n, dtype=torch.float32, device=dev)
@@ -35,7 +37,7 @@ class FlatAdamW(torch.optim.Optimizer):
                 p.grad = self.flat_grad[off:off + k].view_as(p)
                 if old is not None:
                     p.grad.copy_(old)
-                off += k
+                off += (k + 3) // 4 * 4
 
     @torch.no_grad()
     def step(self, closure=None):

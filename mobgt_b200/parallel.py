@@ -53,11 +53,12 @@ class FlatGrads:
     def __init__(self, params, device=None):
         self.params = [p for p in params]
         device = device if device is not None else self.params[0].device
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=device)
+        # every gradient starts on a 16-byte boundary (kernels may use 128-bit accesses); the padding stays zero
+        self.flat = torch.zeros(sum((p.numel() + 3) // 4 * 4 for p in self.params), dtype=torch.float32, device=device)
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            off += (p.numel() + 3) // 4 * 4
 
     def zero_(self):
         self.flat.zero_()

@@ -100,6 +100,7 @@ def test_k9_flat_adamw_matches_torch(lib_built):
         o2.step()
     for a, b in zip(ours, ref):
         assert a.data_ptr() >= o1.flat_param.data_ptr() and a.data_ptr() < o1.flat_param.data_ptr() + o1.n * 4
+        assert a.data_ptr() % 16 == 0 and a.grad.data_ptr() % 16 == 0          # kernels read parameters with 128-bit loads
         assert (a.detach() - b.detach()).abs().max().item() <= 2e-6 * max(1.0, b.abs().max().item())
     w16.refresh()
     assert torch.equal(w16.get("k")[0], ours[2].detach().to(torch.bfloat16))
