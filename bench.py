@@ -261,6 +261,7 @@ def time_kernel(fn, flush, iters=8, warm=2):
 
 def kernel_report(model, batch, pk, iters=8, head_c5=True):
     """Per-kernel device time at the workload's shapes + algorithmic bytes -> roofline."""
+    import torch.nn.functional as F_
     from mobgt_b200 import ops
     from mobgt_b200.algos import apsp_edge_input_packed
     dev = torch.device("cuda")
@@ -343,6 +344,20 @@ def kernel_report(model, batch, pk, iters=8, head_c5=True):
     add("k6_colsum_1024", tk(lambda: ops.colsum(wide)), ntok * 1024 * 2, 0)
     add("k6_colsum_192", tk(lambda: ops.colsum(dy16)), ntok * 192 * 2, 12)
     del wide
+    # K10 — encoder GEMMs on tcgen05 with fused epilogues: the three FFN shapes of a layer
+    x16 = torch.randn(ntok, 192, device=dev).to(torch.bfloat16)
+    w1_ = (torch.randn(1024, 192, device=dev) * 0.07).to(torch.bfloat16)
+    w2_ = (torch.randn(192, 1024, device=dev) * 0.03).to(torch.bfloat16)
+    b1_, b2_ = torch.randn(1024, device=dev) * 0.1, torch.randn(192, device=dev) * 0.1
+    a16 = ops.gemm_bf16(x16, w1_, b1_, mode=1)
+    w2t_ = w2_.t().contiguous()
+    gflop = 2.0 * ntok * 192 * 1024
+    add("k10_ffn1_gelu_fwd", tk(lambda: ops.gemm_bf16(x16, w1_, b1_, mode=1)), ntok * (192 + 1024) * 2 + 1024 * 192 * 2, 6, gflop)
+    add("lib_ffn2_fwd", tk(lambda: F_.linear(a16, w2_, b2_.to(torch.bfloat16))), ntok * (192 + 1024) * 2 + 1024 * 192 * 2, 0, gflop)
+    add("k10_ffn_bwd_dh", tk(lambda: ops.gemm_bf16(dy16, w2t_, b1_, mode=2, a2=x16, w2=w1_, want_colsum=True)),
+        ntok * (192 + 192 + 1024) * 2 + 2 * 1024 * 192 * 2, 6, 2 * gflop)
+    add("lib_ffn1_gemm_plus_gelu", tk(lambda: F_.gelu(F_.linear(x16, w1_, b1_.to(torch.bfloat16)))), ntok * (192 + 3 * 1024) * 2, 0, gflop)
+    del x16, a16
     # K5 — the evaluation head (not part of the training step): c2 shape, and one GPU's shard of the c5 shape
     for name, Mh, Vh in (("k5_head_c2", 256, 60001),) + ((("k5_head_c5_shard", 4096, 125000),) if head_c5 else ()):
         g_ = torch.Generator(device=dev).manual_seed(5)

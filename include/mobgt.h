@@ -294,6 +294,21 @@ int32_t mobgt_spmm_csr(const int32_t *crow, const int32_t *col, const float *val
 int32_t mobgt_adamw_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
                          float beta2, float eps, float weight_decay, int64_t step, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K10 — encoder GEMMs on tcgen05 / TMEM / TMA with fused epilogues.  Replaces the nn.Linear calls of
+ * the encoder layers and the element-wise kernels behind them (model_fqandtoyo.py:1644-1656, 1683-1685, 1708, 1731-1743).
+ *   A bf16 [M, K] (row stride lda), B bf16 [N, K] (the nn.Linear weight layout, row stride ldb), bias f32 [N] or NULL,
+ *   C bf16 [M, N] (row stride ldc).  N % 128 == 0, K % 16 == 0, strides % 8 == 0, 16-byte aligned pointers.
+ *   mode 0: C = A B^T + bias ;  mode 1: C = gelu(A B^T + bias)  (nn.GELU(), exact erf form) ;
+ *   mode 2: C = (A B^T) o gelu'(A2 B2^T + bias), A2 bf16 [M, K2], B2 bf16 [N, K2] — the FFN backward
+ *           dh = (dy W2) o gelu'(x W1^T + b1) with the pre-activation recomputed; colsum f32 [N] (optional) = column sums
+ *           of C, i.e. the bias gradient of layer1 (workspace: mobgt_gemm_workspace_bytes(M, N, 2)).
+ * ------------------------------------------------------------------------------------------ */
+int64_t mobgt_gemm_workspace_bytes(int32_t M, int32_t N, int32_t mode);
+int32_t mobgt_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t ldb, const float *bias, void *C, int64_t ldc,
+                        int32_t M, int32_t N, int32_t K, int32_t mode, const void *A2, int64_t lda2, const void *B2,
+                        int64_t ldb2, int32_t K2, float *colsum, void *workspace, int64_t workspace_bytes, void *stream);
+
 /* Debug hook: register (NULL: clear) a device buffer of 256 int64; thread 0 of one CTA of mobgt_attn_fwd / mobgt_attn_bwd then
  * stamps clock64() at its pipeline stages (scripts/timeline.py). */
 int32_t mobgt_debug_set_timeline(void *dev_buf256);

@@ -58,6 +58,9 @@ SIGNATURES = {
     "mobgt_gtl_bwd": [c_p, c_i32, c_i64, c_p, c_f32, c_i32, c_i32, c_p, c_p, c_i64, c_p],
     "mobgt_spmm_csr": [c_p, c_p, c_p, c_i32, c_p, c_i32, c_p, c_f32, c_i32, c_p, c_p],
     "mobgt_adamw_step": [c_p, c_p, c_p, c_p, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_p],
+    "mobgt_gemm_workspace_bytes": [c_i32, c_i32, c_i32],
+    "mobgt_gemm_bf16": [c_p, c_i64, c_p, c_i64, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_i64, c_p, c_i64, c_i32, c_p, c_p,
+                        c_i64, c_p],
     "mobgt_debug_set_timeline": [c_p],
     "mobgt_selftest_umma": [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p],
 }

@@ -1,0 +1,338 @@
+// K10 — encoder GEMMs on tcgen05 / TMEM fed by TMA, with the element-wise work of the layer fused into the epilogue
+// (sm_100a).  SURVEY.md §8(f) #2.
+//
+// Replaces the nn.Linear calls of EncoderLayer / MultiHeadAttention / FeedForwardNetwork (model_fqandtoyo.py:1644-1656,
+// 1683-1685, 1708, 1731-1743) together with the element-wise kernels that follow them in the reference:
+//     mode 0   C = A B^T + bias                                   (q/k/v projection, output_layer, FFN layer2)
+//     mode 1   C = gelu(A B^T + bias)                             (FFN layer1 + nn.GELU: the pre-activation never reaches HBM)
+//     mode 2   C = (A B^T) o gelu'(A2 B2^T + bias)   + column sums of C
+//              (FFN backward: dh = (dy W2) o gelu'(x W1^T + b1) with the pre-activation RECOMPUTED by a second MMA chain
+//               instead of being stored by the forward, and the bias gradient of layer1 accumulated from the output tile)
+// A [M, K], B [N, K] (the nn.Linear weight layout), A2 [M, K2], B2 [N, K2]: bf16, K-contiguous.  C [M, N] bf16.
+//
+// Persistent, warp-specialised CTAs (one per SM), 128 x 128 output tiles (N % 128 == 0):
+//   warp 0      TMA producer: one stage = a [128 rows][64 K] box of A and a [128 rows][64 K] box of B (128-byte swizzle),
+//               through a ring of `ring` stages
+//   warp 1      MMA issuer: tcgen05.mma M=128 N=128 K=16, accumulators double-buffered in TMEM (mode 2: two accumulators
+//               per buffer); tcgen05.commit releases a stage / publishes an accumulator
+//   warp 2      TMEM allocation
+//   warps 4-19  four epilogue warpgroups = (accumulator buffer t & 1, column half), thread = output row: tcgen05.ld 16 columns at a time,
+//               + bias, activation, bf16, staged 64 columns at a time through a swizzled shared-memory tile so that the
+//               global stores are full 128-byte lines (8 threads per row) and, in mode 2, the column sums come out of
+//               the staged tile (fixed order: deterministic).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace mobgt {
+using namespace sm100;
+
+constexpr int kGemmThreads = 640;                 // 4 service warps + 4 epilogue warpgroups
+constexpr int kGemmBM = 128;
+constexpr int kGemmBN = 128;                      // output tile: 128 x 128
+constexpr int kGemmKB = 64;                       // K columns per stage = one 128-byte swizzle row
+constexpr int kGemmABytes = kGemmBM * 128;        // 16 KB
+constexpr int kGemmStage = kGemmABytes + kGemmBN * 128;   // 32 KB: A block + B block
+constexpr int kGemmMaxRing = 8;
+constexpr int kGemmStageTile = kGemmBM * 128;     // staging: [128 rows][64 bf16], 128-byte swizzle
+
+struct GemmParams {
+    const float *bias;        // [N] or null
+    __nv_bfloat16 *C;         // [M, ldc]
+    int64_t ldc;
+    float *colsum_part;       // mode 2: [2 * tiles_m, N]
+    int M, N, K, K2, mode, ring, tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ void gemm_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void gemm_wait_relaxed(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(20);
+}
+// nn.GELU() (exact erf form, model_fqandtoyo.py:1650): gelu(x) = x Phi(x), gelu'(x) = Phi(x) + x phi(x).
+// Phi(x) = 0.5 (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7 + the 2^-22 of the two
+// approximate MUFU ops; branch-free: rcp.approx, ex2.approx and five FMAs) — the library erff costs ~3x the instructions and diverges inside a warp, and the epilogue is
+// instruction-bound.  e = exp(-x^2 / 2) is shared between erf(x / sqrt 2) and phi(x).
+__device__ __forceinline__ void gelu_parts(float x, float &Phi, float &e) {
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164188824f, fabsf(x), 1.0f)));     // 1 / (1 + p |x| / sqrt 2)
+    const float xs = x * 0.84932180028f;                                                          // sqrt(log2(e) / 2) x
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-xs * xs));                                  // exp(-x^2 / 2)
+    float poly = fmaf(0.5307027145f, t, -0.7265760135f);         // the A&S coefficients, halved
+    poly = fmaf(poly, t, 0.7107068705f);
+    poly = fmaf(poly, t, -0.142248368f);
+    poly = fmaf(poly, t, 0.127414796f);
+    const float h = poly * t * e;                                // 0.5 (1 - erf(|x| / sqrt 2))
+    Phi = 0.5f + copysignf(0.5f - h, x);
+}
+__device__ __forceinline__ float gelu_f(float x) {
+    float Phi, e;
+    gelu_parts(x, Phi, e);
+    return x * Phi;
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+    float Phi, e;
+    gelu_parts(x, Phi, e);
+    return fmaf(x * 0.3989422804014327f, e, Phi);
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k10_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[kGemmMaxRing], bar_empty[kGemmMaxRing], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float sBias[4][64];
+
+    const int tid = threadIdx.x;
+    const int warp = warp_index_uniform();
+    const int lane = tid & 31;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sRing = smem;
+    uint8_t *sStage = sRing + (size_t)p.ring * kGemmStage;             // [4][16 KB]
+    const int ntiles = p.tiles_m * p.tiles_n;
+    const int nprob = p.mode == 2 ? 2 : 1;
+    const int kb0 = ceil_div(p.K, kGemmKB), kb1 = nprob == 2 ? ceil_div(p.K2, kGemmKB) : 0;
+    const int acc_stride = nprob * kGemmBN;                             // TMEM columns per accumulator buffer
+
+    if (tid == 0) {
+        for (int s = 0; s < kGemmMaxRing; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 8);          // one arrival per epilogue warp of the buffer (2 warpgroups x 4 warps)
+        }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        if (nprob == 2) {
+            tma_prefetch_desc(&tmA2);
+            tma_prefetch_desc(&tmB2);
+        }
+    }
+    if (warp == 2) tmem_alloc<512>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int m = tile / p.tiles_n, n = tile - m * p.tiles_n;
+                for (int pr = 0; pr < nprob; ++pr) {
+                    const CUtensorMap *ma = pr ? &tmA2 : &tmA, *mb = pr ? &tmB2 : &tmB;
+                    const int kbs = pr ? kb1 : kb0;
+                    for (int kb = 0; kb < kbs; ++kb, ++it) {
+                        const int s = it % p.ring;
+                        gemm_wait_relaxed(&bar_empty[s], ((uint32_t)(it / p.ring) & 1u) ^ 1u);
+                        uint8_t *st = sRing + (size_t)s * kGemmStage;
+                        mbar_expect_tx(&bar_full[s], (uint32_t)kGemmStage);
+                        tma_load_2d(st, ma, &bar_full[s], kb * kGemmKB, m * kGemmBM);
+                        tma_load_2d(st + kGemmABytes, mb, &bar_full[s], kb * kGemmKB, n * kGemmBN);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(kGemmBM, kGemmBN, 0, 0);
+            const uint32_t r0 = smem_u32(sRing);
+            int it = 0, t = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+                const int a = t & 1;
+                gemm_wait_relaxed(&acc_empty[a], ((uint32_t)(t >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                for (int pr = 0; pr < nprob; ++pr) {
+                    const int kbs = pr ? kb1 : kb0, Kp = pr ? p.K2 : p.K;
+                    const uint32_t acc = tmem + (uint32_t)(a * acc_stride + pr * kGemmBN);
+                    for (int kb = 0; kb < kbs; ++kb, ++it) {
+                        const int s = it % p.ring;
+                        gemm_wait_relaxed(&bar_full[s], (uint32_t)(it / p.ring) & 1u);
+                        tc_fence_after();
+                        const uint32_t sa = r0 + (uint32_t)s * kGemmStage, sb = sa + kGemmABytes;
+                        const int ksteps = ceil_div(min(kGemmKB, Kp - kb * kGemmKB), 16);
+                        for (int j = 0; j < ksteps; ++j)
+                            umma_bf16(acc, make_smem_desc_sw128(sa + j * 32), make_smem_desc_sw128(sb + j * 32), idesc, (kb | j) != 0);
+                        umma_commit(&bar_empty[s]);
+                    }
+                }
+                umma_commit(&acc_full[a]);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue: 4 warpgroups = (accumulator e, column half ch)
+        const int w4 = (warp - 4) >> 2;
+        const int e = w4 & 1, ch = w4 >> 1;
+        const int wt = (tid - 128) & 127;                   // thread index inside the warpgroup
+        const int r = ((warp & 3) << 5) | lane;             // row inside the tile == TMEM lane  (== wt)
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        uint8_t *stg = sStage + (size_t)w4 * kGemmStageTile;
+        float *sb = sBias[w4];
+        const int bar_id = 1 + w4;
+        int t = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+            if ((t & 1) != e) continue;
+            const int m = tile / p.tiles_n, n = tile - m * p.tiles_n;
+            const int col0 = n * kGemmBN + ch * 64;          // this warpgroup's 64 output columns
+            if (wt < 64) sb[wt] = p.bias ? __ldg(p.bias + col0 + wt) : 0.f;
+            gemm_bar_sync(bar_id, 128);                      // bias visible; the previous tile's staging reads are done
+            mbar_wait(&acc_full[e], (uint32_t)(t >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t acc = tmem + lane_off + (uint32_t)(e * acc_stride + ch * 64);
+#pragma unroll
+            for (int q16 = 0; q16 < 4; ++q16) {              // 4 x 16 columns
+                const int c0 = q16 * 16;
+                uint32_t v0[16];
+                float f[16], bb[16];
+                tmem_ld16(acc + (uint32_t)c0, v0);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {          // the 16 bias values: four broadcast 128-bit loads
+                    const float4 b4 = *reinterpret_cast<const float4 *>(sb + c0 + 4 * q4);
+                    bb[4 * q4] = b4.x; bb[4 * q4 + 1] = b4.y; bb[4 * q4 + 2] = b4.z; bb[4 * q4 + 3] = b4.w;
+                }
+                if (p.mode == 2) {
+                    uint32_t v1[16];
+                    tmem_ld16(acc + (uint32_t)(kGemmBN + c0), v1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v0[q]) * gelu_grad_f(__uint_as_float(v1[q]) + bb[q]);
+                } else {
+                    tmem_ld_wait();
+                    if (p.mode == 1) {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) f[q] = gelu_f(__uint_as_float(v0[q]) + bb[q]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v0[q]) + bb[q];
+                    }
+                }
+                if (q16 == 3) {   // this warp has read its share of the accumulator: hand the buffer back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[e]);
+                }
+#pragma unroll
+                for (int q8 = 0; q8 < 2; ++q8) {   // 2 x 16 B of this row into the swizzled staging tile
+                    uint4 pk;
+                    pk.x = pack_bf16(f[8 * q8], f[8 * q8 + 1]);
+                    pk.y = pack_bf16(f[8 * q8 + 2], f[8 * q8 + 3]);
+                    pk.z = pack_bf16(f[8 * q8 + 4], f[8 * q8 + 5]);
+                    pk.w = pack_bf16(f[8 * q8 + 6], f[8 * q8 + 7]);
+                    const int c = q16 * 2 + q8;
+                    *reinterpret_cast<uint4 *>(stg + r * 128 + ((c ^ (r & 7)) << 4)) = pk;
+                }
+            }
+            gemm_bar_sync(bar_id, 128);
+            // ---- staged [128 rows][64 columns] -> global: 8 threads per row, full 128-byte lines
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int id = wt + 128 * i;
+                const int rr = id >> 3, c = id & 7;
+                const int grow = m * kGemmBM + rr;
+                if (grow < p.M) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(stg + rr * 128 + ((c ^ (rr & 7)) << 4));
+                    *reinterpret_cast<uint4 *>(p.C + (size_t)grow * p.ldc + col0 + c * 8) = v;
+                }
+            }
+            if (p.mode == 2 && p.colsum_part != nullptr) {   // column sums of the staged tile: thread = (column, row half)
+                const int cc = wt & 63, hh = wt >> 6;
+                float s = 0.f;
+                for (int rr = hh * 64; rr < hh * 64 + 64; ++rr) {
+                    const __nv_bfloat16 *row = reinterpret_cast<const __nv_bfloat16 *>(stg + rr * 128 + (((cc >> 3) ^ (rr & 7)) << 4));
+                    s += __bfloat162float(row[cc & 7]);
+                }
+                p.colsum_part[(size_t)(m * 2 + hh) * p.N + col0 + cc] = s;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+// sum of the 2 * tiles_m partial rows of the column sums (fixed order)
+__global__ void __launch_bounds__(256) k10_colsum_finish_kernel(const float *__restrict__ part, int rows, int N, float *__restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += part[(size_t)r * N + c];
+    out[c] = s;
+}
+
+}  // namespace mobgt
+
+using namespace mobgt;
+
+extern "C" int64_t mobgt_gemm_workspace_bytes(int32_t M, int32_t N, int32_t mode) {
+    if (M < 0 || N <= 0) return -1;
+    return mode == 2 ? (int64_t)2 * ceil_div(M, kGemmBM) * N * (int64_t)sizeof(float) : 0;
+}
+
+extern "C" int32_t mobgt_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t ldb, const float *bias, void *C,
+                                   int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t mode, const void *A2, int64_t lda2,
+                                   const void *B2, int64_t ldb2, int32_t K2, float *colsum, void *workspace,
+                                   int64_t workspace_bytes, void *stream) {
+    MOBGT_REQUIRE(A && B && C, MOBGT_ERR_NULL, "mobgt_gemm_bf16: null pointer");
+    MOBGT_REQUIRE(mode >= 0 && mode <= 2, MOBGT_ERR_BAD_SHAPE, "mobgt_gemm_bf16: mode=%d", mode);
+    MOBGT_REQUIRE(M >= 0 && N > 0 && K > 0 && K % 16 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && lda >= K && ldb >= K &&
+                      ldc >= N, MOBGT_ERR_BAD_SHAPE, "mobgt_gemm_bf16: M=%d N=%d K=%d lda=%lld ldb=%lld ldc=%lld", M, N, K,
+                  (long long)lda, (long long)ldb, (long long)ldc);
+    const int BN = kGemmBN;
+    MOBGT_REQUIRE(N % BN == 0, MOBGT_ERR_UNSUPPORTED, "mobgt_gemm_bf16: N=%d must be a multiple of %d", N, BN);
+    if (mode == 2) {
+        MOBGT_REQUIRE(A2 && B2 && K2 > 0 && K2 % 16 == 0 && lda2 % 8 == 0 && ldb2 % 8 == 0 && lda2 >= K2 && ldb2 >= K2, MOBGT_ERR_BAD_SHAPE,
+                      "mobgt_gemm_bf16: mode 2 needs A2 / B2 (K2=%d)", K2);
+        MOBGT_REQUIRE(colsum == nullptr || (workspace && workspace_bytes >= mobgt_gemm_workspace_bytes(M, N, 2)),
+                      MOBGT_ERR_WORKSPACE_TOO_SMALL, "mobgt_gemm_bf16: workspace %lld bytes", (long long)workspace_bytes);
+    }
+    MOBGT_REQUIRE((((uintptr_t)A | (uintptr_t)B | (uintptr_t)C | (uintptr_t)A2 | (uintptr_t)B2) & 15) == 0, MOBGT_ERR_BAD_SHAPE,
+                  "mobgt_gemm_bf16: operands must be 16-byte aligned");
+    if (M == 0) return MOBGT_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CUtensorMap tmA, tmB, tmA2, tmB2;
+    auto enc = [&](CUtensorMap *tm, const void *ptr, int64_t ld, int rows, int Kd, int box_rows) -> int32_t {
+        uint64_t dims[2] = {(uint64_t)Kd, (uint64_t)rows};
+        uint64_t str[1] = {(uint64_t)ld * 2};
+        uint32_t box[2] = {(uint32_t)kGemmKB, (uint32_t)box_rows};
+        return encode_tmap_bf16(tm, ptr, 2, dims, str, box, 1);
+    };
+    int32_t rc;
+    if ((rc = enc(&tmA, A, lda, M, K, kGemmBM))) return rc;
+    if ((rc = enc(&tmB, B, ldb, N, K, BN))) return rc;
+    tmA2 = tmA;
+    tmB2 = tmB;
+    if (mode == 2) {
+        if ((rc = enc(&tmA2, A2, lda2, M, K2, kGemmBM))) return rc;
+        if ((rc = enc(&tmB2, B2, ldb2, N, K2, BN))) return rc;
+    }
+    GemmParams p;
+    p.bias = bias;
+    p.C = static_cast<__nv_bfloat16 *>(C);
+    p.ldc = ldc;
+    p.colsum_part = (mode == 2 && colsum) ? static_cast<float *>(workspace) : nullptr;
+    p.M = M; p.N = N; p.K = K; p.K2 = mode == 2 ? K2 : 0; p.mode = mode;
+    p.tiles_m = ceil_div(M, kGemmBM);
+    p.tiles_n = N / BN;
+    p.ring = 4;
+    const size_t smem = (size_t)p.ring * kGemmStage + 4 * kGemmStageTile + 1024;
+    MOBGT_CUDA_OK(cudaFuncSetAttribute(k10_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = p.tiles_m * p.tiles_n;
+    const int grid = ntiles < kNumSMs ? ntiles : kNumSMs;
+    k10_gemm_kernel<<<grid, kGemmThreads, smem, s>>>(tmA, tmB, tmA2, tmB2, p);
+    MOBGT_LAUNCH_OK("k10_gemm_kernel");
+    if (p.colsum_part != nullptr) {
+        k10_colsum_finish_kernel<<<ceil_div(N, 256), 256, 0, s>>>(p.colsum_part, 2 * p.tiles_m, N, colsum);
+        MOBGT_LAUNCH_OK("k10_colsum_finish_kernel");
+    }
+    return MOBGT_OK;
+}

@@ -182,12 +182,9 @@ class EncoderLayer(nn.Module):
         a, wo, bo = self.self_attention(x16, bias_slot, layer, w16)
         x1, y16 = ops.linear_add_dropout_layer_norm(a, self.self_attention.output_layer, wo, bo, x, self.ffn_norm1,
                                                     self.self_attention_dropout.p, self.training, "bf16", need_s=True)   # :1708, :1731-1735
-        f = self.ffn
-        w1, b1 = w16.get((layer, "f1")) if w16 is not None else (None, None)
+        w1 = w16.get((layer, "f1"))[0] if w16 is not None else None
         w2, b2 = w16.get((layer, "f2")) if w16 is not None else (None, None)
-        h = ops.linear_gelu_bf16(y16, f.layer1, w1, b1)
-        return ops.linear_add_dropout_layer_norm(h, f.layer2, w2, b2, x1, self.ffn_norm2, self.ffn_dropout.p, self.training,
-                                                 "both")                                                               # :1655, :1737-1741
+        return ops.ffn_block(y16, self.ffn, w1, w2, b2, x1, self.ffn_norm2, self.ffn_dropout.p, self.training, "both")   # :1644-1656, :1737-1741
 
 
 def gradient_tail_loss(inputs, targets, alpha=0.25, beta=1, k=1):

@@ -473,6 +473,75 @@ class LinearAddDropoutLNFn(torch.autograd.Function):
         return (dx16, None, None, dres, dgamma, dbeta, None, None, None, None) + pg
 
 
+# ----------------------------------------------------------------------------------------------- K10
+def gemm_bf16(a, w, bias=None, mode=0, a2=None, w2=None, want_colsum=False):
+    """C = epi(a w^T [, a2 w2^T], bias) on tcgen05 (csrc/k10_gemm.cu).  a bf16 [M, K], w bf16 [N, K] (nn.Linear layout), bias f32
+    [N].  mode 0: + bias; 1: gelu(. + bias); 2: (a w^T) o gelu'(a2 w2^T + bias) [+ column sums].  -> C bf16 [M, N] (, colsum f32 [N])"""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    C = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    colsum, ws, nws = None, None, 0
+    if mode == 2:
+        assert a2 is not None and w2 is not None and a2.stride(1) == 1 and w2.stride(1) == 1
+        if want_colsum:
+            nws = int(_C.lib().mobgt_gemm_workspace_bytes(M, N, 2))
+            ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=a.device)
+            colsum = torch.empty(N, dtype=torch.float32, device=a.device)
+    b = bias.detach().float().contiguous() if bias is not None else None
+    _C.call("mobgt_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _C.ptr(b), _C.ptr(C), N, M, N, K, int(mode),
+            a2.data_ptr() if a2 is not None else None, a2.stride(0) if a2 is not None else 0,
+            w2.data_ptr() if w2 is not None else None, w2.stride(0) if w2 is not None else 0,
+            int(a2.shape[1]) if a2 is not None else 0, _C.ptr(colsum), _C.ptr(ws), nws, _C.stream_ptr())
+    return (C, colsum) if mode == 2 else C
+
+
+class FfnBlockFn(torch.autograd.Function):
+    """FeedForwardNetwork + the residual block behind it (model_fqandtoyo.py:1644-1656, 1737-1741) as ONE autograd node:
+        a = gelu(x W1^T + b1)            K10 mode 1: GEMM + bias + GELU in one kernel, the pre-activation never reaches HBM
+        y = a W2^T + b2                  library GEMM (192 output columns)
+        s = resid + dropout(y) ; out = LayerNorm(s)                                   K6
+    backward:
+        (dres, dy, dgamma, dbeta, db2)   K6 LayerNorm backward, db2 = column sums of dy from the same pass
+        dh, db1 = (dy W2) o gelu'(x W1^T + b1), its column sums                       K10 mode 2 (pre-activation recomputed)
+        dW2 = dy^T a ; dW1 = dh^T x ; dx = dh W1                                      library GEMMs (reductions over tokens)"""
+
+    @staticmethod
+    def forward(ctx, x16, w1, w2, b2, resid, gamma, beta, eps, p, want, need_s, m_w1, m_b1, m_w2, m_b2):
+        a = gemm_bf16(x16, w1, m_b1, mode=1)
+        y = torch.nn.functional.linear(a, w2, b2)            # N = hidden (192): below K10's 128-column tile granularity
+        s, out, out16, saved, seed = _adln_fwd(resid, y, gamma, beta, eps, p, want)
+        ctx.save_for_backward(x16, w1, w2, a, *saved)
+        ctx.cfg = (float(p), seed, want, need_s)
+        ctx.seed_dev, ctx.masters = _seed_dev, (m_w1, m_b1, m_w2, m_b2)
+        return _adln_outputs(s, out, out16, want, need_s)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        x16, w1, w2, a = ctx.saved_tensors[:4]
+        p, seed, want, need_s = ctx.cfg
+        m_w1, m_b1, m_w2, m_b2 = ctx.masters
+        dres, dy, dgamma, dbeta, db2 = _adln_bwd(ctx.saved_tensors[4:], grads, p, seed, want, need_s, ctx.seed_dev, want_colsum=True)
+        w2t = w2.t().contiguous()                                       # [ffn, hidden]: the B operand of dy W2
+        dh, db1 = gemm_bf16(dy, w2t, m_b1, mode=2, a2=x16, w2=w1, want_colsum=True)
+        g_w2, g_b2 = _deliver_param_grads((m_w2, m_b2), dy.t() @ a, db2)
+        g_w1, g_b1 = _deliver_param_grads((m_w1, m_b1), dh.t() @ x16, db1)
+        dx16 = dh @ w1
+        return (dx16, None, None, None, dres, dgamma, dbeta, None, None, None, None, g_w1, g_b1, g_w2, g_b2)
+
+
+def ffn_block(x16, ffn, w1, w2, b2, resid, ln, p, training, want="f32", need_s=False):
+    """LayerNorm(resid + dropout(ffn(x16))) with ffn = FeedForwardNetwork(layer1, GELU, layer2); w1 / w2 / b2: bf16 working
+    copies (layer1's bias is applied in fp32 inside the K10 epilogue)."""
+    if w1 is None:
+        w1, w2 = ffn.layer1.weight.detach().to(torch.bfloat16), ffn.layer2.weight.detach().to(torch.bfloat16)
+        b2 = ffn.layer2.bias.detach().to(torch.bfloat16)
+    if w1.shape[0] % 128 != 0:
+        raise NotImplementedError(f"ffn_dim={w1.shape[0]}: libmobgt's FFN kernels are built for multiples of 128")
+    return FfnBlockFn.apply(x16, w1, w2, b2, resid, ln.weight, ln.bias, ln.eps, float(p) if training else 0.0, want, need_s,
+                            ffn.layer1.weight, ffn.layer1.bias, ffn.layer2.weight, ffn.layer2.bias)
+
+
 def linear_add_dropout_layer_norm(x16, lin, w16, b16, resid, ln, p, training, want="f32", need_s=False):
     """LayerNorm(resid + dropout(lin(x16)))  with lin's bf16 working copies w16 / b16 (None: cast on the fly)."""
     if w16 is None:

@@ -70,6 +70,44 @@ def test_k7_gradient_tail_loss(lib_built, B, V, alpha, dtype):
     assert (xg.grad.float().cpu() - gr).abs().max().item() <= tol * gr.abs().max().item() + 1e-12
 
 
+# ------------------------------------------------------------------------------------------------------- K10
+@pytest.mark.parametrize("M,N,K,mode", [(1000, 640, 192, 0), (33024, 1024, 192, 1), (4100, 256, 1024, 0), (130, 256, 192, 1),
+                                        (5, 128, 192, 0), (3000, 1024, 192, 2), (33024, 1024, 192, 2), (77, 256, 192, 2),
+                                        (640, 128, 64, 0), (300, 128, 576, 0)])
+def test_k10_gemm_epilogues(lib_built, M, N, K, mode):
+    """tcgen05 GEMM with fused epilogues against torch fp32 on the same bf16 operands: mode 0 (+ bias), mode 1 (+ bias, GELU),
+    mode 2 (FFN backward: (a w^T) o gelu'(a2 w2^T + bias) and its column sums).  bf16 output: 2^-8 relative."""
+    from mobgt_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + mode)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g) * 0.5
+    if mode < 2:
+        got = ops.gemm_bf16(a, w, bias, mode=mode)
+        ref = a.float() @ w.float().t() + bias
+        if mode == 1:
+            ref = F.gelu(ref)
+        err = (got.float() - ref).abs().max().item()
+        assert err <= 1e-2 * max(1.0, ref.abs().max().item()), err
+        assert torch.equal(got, ops.gemm_bf16(a, w, bias, mode=mode))                  # bitwise reproducible
+        # the same result through a strided A (a column slice of a wider matrix)
+        wide = torch.cat([a, a], 1)
+        assert torch.equal(got, ops.gemm_bf16(wide[:, K:], w, bias, mode=mode))
+        return
+    K2 = 192
+    a2 = torch.randn(M, K2, device="cuda", generator=g).to(torch.bfloat16)
+    w2 = (torch.randn(N, K2, device="cuda", generator=g) / K2 ** 0.5).to(torch.bfloat16)
+    got, cs = ops.gemm_bf16(a, w, bias, mode=2, a2=a2, w2=w2, want_colsum=True)
+    h = (a2.float() @ w2.float().t() + bias).requires_grad_(True)
+    up = a.float() @ w.float().t()
+    F.gelu(h).backward(up)
+    ref = h.grad
+    err = (got.float() - ref).abs().max().item()
+    assert err <= 1e-2 * max(1.0, ref.abs().max().item()), err
+    cref = got.float().sum(0)                                                         # column sums of what was stored
+    assert (cs - cref).abs().max().item() <= 1e-3 * max(1.0, cref.abs().max().item())
+
+
 # ------------------------------------------------------------------------------------------------------- K9
 def test_k9_flat_adamw_matches_torch(lib_built):
     """optim.FlatAdamW (one kernel over flat buffers) against torch.optim.AdamW on the same parameters and gradients, five steps
