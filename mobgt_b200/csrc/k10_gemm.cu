@@ -41,7 +41,7 @@ struct GemmParams {
     const float *bias;        // [N] or null
     __nv_bfloat16 *C;         // [M, ldc]
     int64_t ldc;
-    float *colsum_part;       // mode 2: [2 * tiles_m, N]
+    float *colsum_part;       // mode 2: [tiles_m, N]
     int M, N, K, K2, mode, ring, tiles_m, tiles_n;
 };
 
@@ -85,6 +85,7 @@ k10_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __shared__ __align__(8) uint64_t bar_full[kGemmMaxRing], bar_empty[kGemmMaxRing], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float sBias[4][64];
+    __shared__ float sCol[4][256];
 
     const int tid = threadIdx.x;
     const int warp = warp_index_uniform();
@@ -233,25 +234,40 @@ k10_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 }
             }
             gemm_bar_sync(bar_id, 128);
-            // ---- staged [128 rows][64 columns] -> global: 8 threads per row, full 128-byte lines
+            // ---- staged [128 rows][64 columns] -> global: 8 threads per row, full 128-byte lines.  Mode 2: the same 16-byte
+            //      words feed the column sums (thread = 8 columns x the 8 rows it copies; then lanes, then warps are folded)
+            float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int id = wt + 128 * i;
                 const int rr = id >> 3, c = id & 7;
                 const int grow = m * kGemmBM + rr;
-                if (grow < p.M) {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(stg + rr * 128 + ((c ^ (rr & 7)) << 4));
-                    *reinterpret_cast<uint4 *>(p.C + (size_t)grow * p.ldc + col0 + c * 8) = v;
+                const uint4 v = *reinterpret_cast<const uint4 *>(stg + rr * 128 + ((c ^ (rr & 7)) << 4));
+                if (grow < p.M) *reinterpret_cast<uint4 *>(p.C + (size_t)grow * p.ldc + col0 + c * 8) = v;
+                if (p.mode == 2) {            // rows past M were computed from zero-filled operands: they add zeros
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        cs[2 * q] += __uint_as_float(w[q] << 16);
+                        cs[2 * q + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
+                    }
                 }
             }
-            if (p.mode == 2 && p.colsum_part != nullptr) {   // column sums of the staged tile: thread = (column, row half)
-                const int cc = wt & 63, hh = wt >> 6;
-                float s = 0.f;
-                for (int rr = hh * 64; rr < hh * 64 + 64; ++rr) {
-                    const __nv_bfloat16 *row = reinterpret_cast<const __nv_bfloat16 *>(stg + rr * 128 + (((cc >> 3) ^ (rr & 7)) << 4));
-                    s += __bfloat162float(row[cc & 7]);
+            if (p.mode == 2 && p.colsum_part != nullptr) {
+                // lanes l, l ^ 8, l ^ 16 hold the same 8 columns (c = lane & 7) for other rows
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 8);
+                    cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 16);
                 }
-                p.colsum_part[(size_t)(m * 2 + hh) * p.N + col0 + cc] = s;
+                float *red = sCol[w4];                        // [4 warps][64 columns]
+                if (lane < 8) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) red[(warp & 3) * 64 + lane * 8 + q] = cs[q];
+                }
+                gemm_bar_sync(bar_id, 128);
+                if (wt < 64)
+                    p.colsum_part[(size_t)m * p.N + col0 + wt] = (red[wt] + red[64 + wt]) + (red[128 + wt] + red[192 + wt]);
             }
         }
     }
@@ -260,7 +276,7 @@ k10_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 2) tmem_dealloc<512>(tmem);
 }
 
-// sum of the 2 * tiles_m partial rows of the column sums (fixed order)
+// sum of the tiles_m partial rows of the column sums (fixed order)
 __global__ void __launch_bounds__(256) k10_colsum_finish_kernel(const float *__restrict__ part, int rows, int N, float *__restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= N) return;
@@ -275,7 +291,7 @@ using namespace mobgt;
 
 extern "C" int64_t mobgt_gemm_workspace_bytes(int32_t M, int32_t N, int32_t mode) {
     if (M < 0 || N <= 0) return -1;
-    return mode == 2 ? (int64_t)2 * ceil_div(M, kGemmBM) * N * (int64_t)sizeof(float) : 0;
+    return mode == 2 ? (int64_t)ceil_div(M, kGemmBM) * N * (int64_t)sizeof(float) : 0;
 }
 
 extern "C" int32_t mobgt_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t ldb, const float *bias, void *C,
@@ -331,7 +347,7 @@ extern "C" int32_t mobgt_gemm_bf16(const void *A, int64_t lda, const void *B, in
     k10_gemm_kernel<<<grid, kGemmThreads, smem, s>>>(tmA, tmB, tmA2, tmB2, p);
     MOBGT_LAUNCH_OK("k10_gemm_kernel");
     if (p.colsum_part != nullptr) {
-        k10_colsum_finish_kernel<<<ceil_div(N, 256), 256, 0, s>>>(p.colsum_part, 2 * p.tiles_m, N, colsum);
+        k10_colsum_finish_kernel<<<ceil_div(N, 256), 256, 0, s>>>(p.colsum_part, p.tiles_m, N, colsum);
         MOBGT_LAUNCH_OK("k10_colsum_finish_kernel");
     }
     return MOBGT_OK;

@@ -33,14 +33,41 @@ DATASET_TRAITS = {
 }
 
 
-def _csr_transpose(csr, n):
-    """CSR (crow, col, val) of the transpose of an n x n CSR matrix (numpy, stable: rows of A^T keep ascending columns)."""
+def _csr_transpose(csr, n, ncols=None):
+    """CSR (crow, col, val) of the transpose of an n x ncols CSR matrix (numpy, stable: rows of A^T keep ascending columns)."""
+    ncols = n if ncols is None else ncols
     crow, col, val = (np.asarray(a) for a in csr)
     rows = np.repeat(np.arange(n), np.diff(crow))
     order = np.argsort(col, kind="stable")
-    tcrow = np.zeros(n + 1, np.int64)
-    np.cumsum(np.bincount(col, minlength=n), out=tcrow[1:])
+    tcrow = np.zeros(ncols + 1, np.int64)
+    np.cumsum(np.bincount(col, minlength=ncols), out=tcrow[1:])
     return tcrow, rows[order], np.asarray(val)[order]
+
+
+def _csr_split_rows(csr, chunk=128):
+    """Cut the rows of a CSR matrix into chunks of <= `chunk` non-zeros -> (chunked CSR, fold CSR): the chunked matrix has one
+    row per chunk (K8 is row-parallel: a 60 000-entry row of a transposed feature matrix would serialise one sub-warp), the
+    fold matrix [rows, chunks] of ones adds the chunks of every original row back together (a second K8 call, fixed order)."""
+    crow, col, val = (np.asarray(a) for a in csr)
+    n = len(crow) - 1
+    starts, owner = [], []
+    for r in range(n):
+        a, b = int(crow[r]), int(crow[r + 1])
+        for s0 in range(a, max(b, a + 1), chunk):
+            starts.append(min(s0, b))
+            owner.append(r)
+    vcrow = np.array(starts + [int(crow[-1])], np.int64)
+    owner = np.array(owner, np.int64)
+    fcrow = np.zeros(n + 1, np.int64)
+    np.cumsum(np.bincount(owner, minlength=n), out=fcrow[1:])
+    return (vcrow, col, val), (fcrow, np.arange(len(owner), dtype=np.int64), np.ones(len(owner), np.float32))
+
+
+def _dense_to_csr(d):
+    rows, cols = np.nonzero(d)
+    crow = np.zeros(d.shape[0] + 1, np.int64)
+    np.cumsum(np.bincount(rows, minlength=d.shape[0]), out=crow[1:])
+    return crow, cols.astype(np.int64), d[rows, cols].astype(np.float32)
 
 
 class GraphConvolution(nn.Module):
@@ -56,14 +83,18 @@ class GraphConvolution(nn.Module):
         self.weight.data.uniform_(-stdv, stdv)
         self.bias.data.uniform_(-stdv, stdv)
 
-    def forward(self, x, adj, slope=None):
+    def forward(self, x, adj, slope=None, x_csr=None):
         """adj = (A, At): CSR triples (crow, col, val) of the row-normalised adjacency and of its transpose.
-        slope: fuse LeakyReLU(slope) of GCN.forward (modelGNN.py:67-69) into this layer."""
+        slope: fuse LeakyReLU(slope) of GCN.forward (modelGNN.py:67-69) into this layer.
+        x_csr = (X, Xt): the layer INPUT as CSR triples, when it is a sparse constant of the dataset (the POI feature matrix:
+        check-in frequency, one-hot category, lat, lon — 4 non-zeros in 3 + C columns, model_fqandtoyo.py:816-832): `x @ W`
+        and its weight gradient `x^T dY` are then K8 gathers instead of dense GEMMs that stream the [P, 3 + C] fp32 matrix."""
         A, At = adj
         fin, fout = self.weight.shape
         ok = (16, 32, 64, 128)                                       # the widths K8 is built for
         if fout in ok and (fout <= fin or fin not in ok):
-            return ops.spmm(A, At, torch.mm(x, self.weight), self.bias, slope)
+            xw = ops.spmm(x_csr[0], x_csr[1], self.weight) if x_csr is not None else torch.mm(x, self.weight)
+            return ops.spmm(A, At, xw, self.bias, slope)
         if fin in ok:
             y = torch.addmm(self.bias, ops.spmm(A, At, x), self.weight)
             return F.leaky_relu(y, slope) if slope is not None else y
@@ -79,9 +110,9 @@ class GCN(nn.Module):
         self.gcn = nn.ModuleList([GraphConvolution(ch[i], ch[i + 1]) for i in range(len(ch) - 1)])
         self.dropout = dropout
 
-    def forward(self, x, adj):
+    def forward(self, x, adj, x_csr=None):
         for i in range(len(self.gcn) - 1):
-            x = self.gcn[i](x, adj, slope=0.2)                       # F.leaky_relu(self.gcn[i](x, adj), 0.2)
+            x = self.gcn[i](x, adj, slope=0.2, x_csr=x_csr if i == 0 else None)   # F.leaky_relu(self.gcn[i](x, adj), 0.2)
         x = F.dropout(x, self.dropout, training=self.training)
         return self.gcn[-1](x, adj)
 
@@ -263,6 +294,17 @@ class Graphormer(nn.Module):
         # dataset tables (non-trainable)
         self.register_buffer("X", torch.from_numpy(world.X), persistent=False)
         self.register_buffer("C_X", torch.from_numpy(world.C_X), persistent=False)
+        self._x_sparse = {}
+        for name, dense in (("X", world.X), ("C_X", world.C_X)):     # constant, mostly-zero input features -> CSR for K8
+            d = np.asarray(dense, np.float32)
+            if (d != 0).mean() <= 0.125:
+                csr = _dense_to_csr(d)
+                chunked, fold = _csr_split_rows(_csr_transpose(csr, d.shape[0], d.shape[1]))   # X^T has a few very long rows
+                for suffix, (crow, col, val) in (("", csr), ("_t", chunked), ("_f", fold)):
+                    self.register_buffer(f"{name}s{suffix}_crow", torch.from_numpy(np.ascontiguousarray(crow, np.int32)), persistent=False)
+                    self.register_buffer(f"{name}s{suffix}_col", torch.from_numpy(np.ascontiguousarray(col, np.int32)), persistent=False)
+                    self.register_buffer(f"{name}s{suffix}_val", torch.from_numpy(np.ascontiguousarray(val, np.float32)), persistent=False)
+                self._x_sparse[name] = True
         self.register_buffer("cat_of_poi", torch.from_numpy(world.cat_of_poi).int(), persistent=False)
         for name, csr, n in (("D_A", world.D_A, P), ("C_A", world.C_A, C)):
             for suffix, (crow, col, val) in (("", csr), ("_t", _csr_transpose(csr, n))):
@@ -278,7 +320,9 @@ class Graphormer(nn.Module):
 
     def gcn_tables(self):
         """model_fqandtoyo.py:1236-1237: recomputed every forward, like the reference."""
-        return (self.poi_distance_model(self.X, self._adj("D_A")), self.poi_cat_model(self.C_X, self._adj("C_A")))
+        t = lambda n, sfx: tuple(getattr(self, f"{n}s{sfx}_{k}") for k in ("crow", "col", "val"))
+        xs = lambda n: (t(n, ""), (t(n, "_t"), t(n, "_f"))) if self._x_sparse.get(n) else None
+        return (self.poi_distance_model(self.X, self._adj("D_A"), xs("X")), self.poi_cat_model(self.C_X, self._adj("C_A"), xs("C_X")))
 
     def attn_bias(self, b, dtype=torch.bfloat16):
         """K2 (model_fqandtoyo.py:1143-1216)"""

@@ -748,7 +748,11 @@ class SpmmFn(torch.autograd.Function):
         if ctx.slope is not None:
             (Y,) = ctx.saved_tensors
             g = torch.where(Y > 0, g, g * ctx.slope)
-        dS = spmm_csr_raw(ctx.At, g)
+        At = ctx.At
+        if len(At) == 2:          # (chunked A^T, fold): long rows of A^T were cut into chunks, summed by a second tiny SpMM
+            dS = spmm_csr_raw(At[1], spmm_csr_raw(At[0], g))
+        else:
+            dS = spmm_csr_raw(At, g)
         db = colsum(g) if ctx.has_bias else None
         return None, None, dS, db, None
 
