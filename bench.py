@@ -495,8 +495,9 @@ def run_ours(args):
             e2e_step()
         e2e_flush()
         torch.cuda.synchronize()
-        chunk_ms.append((time.perf_counter() - t0) * 200.0)
-        stable = stable + 1 if chunk_ms[-1] <= 1.15 * min(chunk_ms) else 0
+        cur = (time.perf_counter() - t0) * 200.0
+        stable = stable + 1 if (chunk_ms and abs(cur - min(chunk_ms)) <= 0.15 * min(chunk_ms)) else 0
+        chunk_ms.append(cur)
     if rank == 0:
         print("[bench] e2e warm-up chunks (ms/step): " + " ".join(f"{x:.2f}" for x in chunk_ms), file=sys.stderr)
     e2e_steps = max(4, args.steps)
