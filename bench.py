@@ -430,7 +430,8 @@ def run_ours(args):
     tr = Trainer(model, dev, world_size, cuda_graph=args.cuda_graph, overlap=not args.no_overlap)
     latlon = torch.from_numpy(world.latlon).to(dev)
     ckw = dict(world=world, latlon_dev=latlon, multi_hop_max_dist=HP["multi_hop_max_dist"], rel_pos_max=1024, device=dev)
-    batches = [collator.collate_packed(its, max_node=512, **ckw) for its in item_sets]
+    bucket = nbatches > 1 and args.cuda_graph          # varying shapes: pad to size buckets so the captured graphs replay
+    batches = [collator.collate_packed(its, max_node=512, bucket=bucket, **ckw) for its in item_sets]
     state = dict(i=0)
 
     def resident_step():
@@ -459,7 +460,7 @@ def run_ours(args):
     # one-batch-ahead loader (the reference's DataLoader-worker role, data.py:255-267): numpy packing in worker processes, ONE
     # pinned buffer + ONE H2D copy per batch, collation kernels on a side stream gated behind the previous step
     side = not args.no_side_stream
-    loader = collator.PackedLoader(endless(), num_workers=args.loader_workers, side_stream=side, **ckw)
+    loader = collator.PackedLoader(endless(), num_workers=args.loader_workers, side_stream=side, bucket=bucket, **ckw)
     loss_pin = torch.empty(2, dtype=torch.float32).pin_memory()
     st = dict(pending=None, k=0, last=None)
 
@@ -512,7 +513,7 @@ def run_ours(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": args.workload, "world": WORLD_NOTE[cfg], "hidden": 128, "layers": 6,
                            "heads": 8, "ffn": 1024, "multi_hop_max_dist": 20, "graphs_per_gpu": B,
-                           "tokens_per_gpu": tokens, "distinct_batches": nbatches, "parallelism": f"dp{world_size}",
+                           "tokens_per_gpu": tokens, "distinct_batches": nbatches, "size_buckets": bool(bucket), "parallelism": f"dp{world_size}",
                            "cuda_graph": tr.graph_note, "graph_replays_of_timed_steps": f"{replays_value}/{args.steps}",
                            "e2e_graph_replays": f"{tr.graph_steps - eg0}/{e2e_steps}",
                            "allreduce": ("none" if world_size == 1 else

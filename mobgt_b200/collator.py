@@ -52,16 +52,17 @@ _staging = {}
 class _PackStream(torch.utils.data.IterableDataset):
     """Worker-side half of PackedLoader: worker w packs the batches i = w (mod num_workers) of the stream."""
 
-    def __init__(self, batches, max_node):
-        self.batches, self.max_node = batches, max_node
+    def __init__(self, batches, max_node, bucket=False):
+        self.batches, self.max_node, self.bucket = batches, max_node, bucket
 
     def __iter__(self):
         info = torch.utils.data.get_worker_info()
         w, nw = (info.id, info.num_workers) if info is not None else (0, 1)
         for i, items in enumerate(self.batches):
             if i % nw == w:
-                hp = pack_host(items, self.max_node)
-                yield dict(buf=torch.from_numpy(hp.buf), layout=hp.layout, B=hp.B, N=hp.N, ns=torch.from_numpy(hp.ns), cells=hp.cells)
+                hp = pack_host(items, self.max_node, bucket=self.bucket)
+                yield dict(buf=torch.from_numpy(hp.buf), layout=hp.layout, B=hp.B, N=hp.N, ns=torch.from_numpy(hp.ns), cells=hp.cells,
+                           padded=hp.padded)
 
 
 class PackedLoader:
@@ -77,19 +78,23 @@ class PackedLoader:
     `current()` makes the consumer's stream wait for the batch (event) and registers the batch's memory with that stream.
     """
 
-    def __init__(self, batches, collate_fn=None, num_workers=0, max_node=512, side_stream=True, **collate_kw):
+    def __init__(self, batches, collate_fn=None, num_workers=0, max_node=512, side_stream=True, bucket=False, **collate_kw):
+        """bucket=True: every batch is padded to a few size buckets (see `pack_host`), so that batches of different graphs
+        share packed shapes and the trainer's CUDA graphs replay instead of re-capturing / running eagerly."""
         self._kw = collate_kw
         self._stream = torch.cuda.Stream() if (side_stream and torch.cuda.is_available()) else None
         self._gate = None
         if num_workers > 0:
-            ds = _PackStream(batches, max_node)
+            ds = _PackStream(batches, max_node, bucket)
             dl = torch.utils.data.DataLoader(ds, batch_size=None, num_workers=num_workers, pin_memory=False, prefetch_factor=2,
                                              persistent_workers=False)
             self._it = iter(dl)
-            self._collate = lambda d: collate_from_host(HostPack(d["buf"], d["layout"], d["B"], d["N"], d["ns"], d["cells"]), **self._kw)
+            self._collate = lambda d: collate_from_host(HostPack(d["buf"], d["layout"], d["B"], d["N"], d["ns"], d["cells"], d["padded"]),
+                                                        **self._kw)
         else:
             self._it = iter(batches)
-            self._collate = collate_fn if collate_fn is not None else (lambda items: collate_packed(items, max_node=max_node, **self._kw))
+            self._collate = collate_fn if collate_fn is not None else (
+                lambda items: collate_packed(items, max_node=max_node, bucket=bucket, **self._kw))
         self._next = self._pull()
 
     def _pull(self):
@@ -344,12 +349,30 @@ class HostPack:
     plus the few Python scalars the device half needs.  Pure numpy: safe to build in DataLoader worker processes, cheap to
     ship through shared memory, and uploaded with a single H2D copy."""
 
-    def __init__(self, buf, layout, B, N, ns, cells):
-        self.buf, self.layout, self.B, self.N, self.ns, self.cells = buf, layout, B, N, ns, cells
+    def __init__(self, buf, layout, B, N, ns, cells, padded=False):
+        self.buf, self.layout, self.B, self.N, self.ns, self.cells, self.padded = buf, layout, B, N, ns, cells, padded
 
 
-def pack_host(items, max_node=512):
-    """raw dataset items (owndata.py:340-349 fields; numpy or torch) -> HostPack.  No CUDA, no torch ops on the hot path."""
+def _bucket_sizes(ntok, cells, nmax, B):
+    """Bucketed (tokens, cells, max nodes): tokens to a multiple of 512 (GEMM rows: the cost that scales), cells to a power
+    of two (memory only), the node cap to a power of two (tile counts of K2 / K3)."""
+    ntok_b = max(512, (ntok + 511) // 512 * 512)
+    cells_b = 4096
+    while cells_b < cells:
+        cells_b *= 2
+    n_b = 8
+    while n_b < nmax:
+        n_b *= 2
+    return ntok_b, cells_b, min(n_b, 512)
+
+
+def pack_host(items, max_node=512, bucket=False):
+    """raw dataset items (owndata.py:340-349 fields; numpy or torch) -> HostPack.  No CUDA, no torch ops on the hot path.
+
+    bucket=True pads the per-token / per-node / per-cell arrays to bucket sizes (`_bucket_sizes`): padding tokens are extra
+    "graph tokens" that belong to no graph (no tok_off range covers them, so attention never reads or writes them and their
+    gradient is exactly zero), padding nodes map to them one to one with padding-row indices, padding cells are never indexed.
+    Per-graph sizes (n, offsets) are untouched, so every result for the real graphs is identical to the unpadded batch."""
     items = [it for it in items if it is not None and len(_to_np(it.x)) <= max_node]     # collator.py:313
     B = len(items)
     ns = np.array([len(_to_np(it.x)) for it in items], np.int32)
@@ -395,14 +418,28 @@ def pack_host(items, max_node=512):
     tok_graph[rows] = g_of_node
     tok_pos[rows] = pos_of_node
     tok_graph[tok_off[:-1]] = np.arange(B)
+    in_deg, out_deg, node_rows = indeg + 1, outdeg + 1, rows.astype(np.int64)    # pad_1d_unsqueeze "+1" (collator.py:12)
+    N_out, cells_alloc, padded = (int(ns.max()) if B else 0), cells, False
+    if bucket and B:
+        ntok_b, cells_alloc, N_out = _bucket_sizes(Ntok, cells, int(ns.max()), B)
+        pad = ntok_b - Ntok                                   # padding tokens == padding nodes (Ntok = Nn + B)
+        if pad or cells_alloc != cells or N_out != int(ns.max()):
+            padded = True
+            z32 = np.zeros(pad, np.int32)
+            tok_graph, tok_pos = np.concatenate([tok_graph, z32]), np.concatenate([tok_pos, z32])
+            x_nodes = np.concatenate([x_nodes, np.ones(pad, np.int32)])
+            slot, time_nodes = np.concatenate([slot, z32]), np.concatenate([time_nodes, z32])
+            tn = np.concatenate([tn, np.zeros(pad, np.float32)])
+            cat_nodes = np.concatenate([cat_nodes, np.ones(pad, np.int32)])
+            in_deg, out_deg = np.concatenate([in_deg, z32]), np.concatenate([out_deg, z32])      # 0 = the padding row
+            node_rows = np.concatenate([node_rows, Ntok + np.arange(pad, dtype=np.int64)])
     host = dict(n=ns, sq_off=sq, node_off=no, tok_off=tok_off, tok_graph=tok_graph, tok_pos=tok_pos, feat8=None,
                 x_nodes=x_nodes, slot=slot, time_nodes=time_nodes, time_normal_nodes=tn, cat_nodes=cat_nodes,
-                in_deg=indeg + 1, out_deg=outdeg + 1,                          # pad_1d_unsqueeze "+1" (collator.py:12)
-                user=user, y=y, idx=idx, node_rows=rows.astype(np.int64))
+                in_deg=in_deg, out_deg=out_deg, user=user, y=y, idx=idx, node_rows=node_rows)
     layout, total = {}, 0
     for k, a in host.items():
         if k == "feat8":
-            shape, dt, nbytes = (cells,), np.dtype(np.uint8), cells
+            shape, dt, nbytes = (cells_alloc,), np.dtype(np.uint8), cells_alloc
         else:
             a = np.ascontiguousarray(a)
             host[k] = a
@@ -417,7 +454,7 @@ def pack_host(items, max_node=512):
     # the edge-type plane is scattered straight into its segment of the buffer
     off = layout["feat8"][0]
     buf[off + sq[:-1][eg] + ei[0] * ns.astype(np.int64)[eg] + ei[1]] = ea + 2     # wrapper.py:49-53: convert_to_single_emb(+1) then +1
-    return HostPack(buf, layout, B, int(ns.max()) if B else 0, ns, cells)
+    return HostPack(buf, layout, B, N_out, ns, cells_alloc, padded)
 
 
 def _upload_pack(hp, dev):
@@ -445,7 +482,7 @@ def collate_from_host(hp, world=None, latlon_dev=None, multi_hop_max_dist=20, re
     ns = hp.ns.numpy() if isinstance(hp.ns, torch.Tensor) else hp.ns
     dk = int(multi_hop_max_dist)
     hops = hop_stride(dk)                  # bytes per edge_in8 row; slots [dk, hops) are padding
-    b = Batch1(B=hp.B, N=hp.N, hops=hops, dk=dk, rel_pos_max=int(rel_pos_max), n_host=ns, h2d_bytes=0, **views)
+    b = Batch1(B=hp.B, N=hp.N, hops=hops, dk=dk, rel_pos_max=int(rel_pos_max), n_host=ns, h2d_bytes=0, padded=bool(hp.padded), **views)
     b.h2d_bytes = int(sum(v.numel() * v.element_size() for v in views.values()))
     b.build_plans()
     k1 = apsp_edge_input_packed(b.feat8, b.n, b.sq_off, ns, hops=hops, shift=1, want_path=want_path, dk=dk)
@@ -463,11 +500,13 @@ def collate_from_host(hp, world=None, latlon_dev=None, multi_hop_max_dist=20, re
 
 
 def collate_packed(items, world=None, latlon_dev=None, max_node=512, multi_hop_max_dist=20, rel_pos_max=1024,
-                   device="cuda", want_path=False):
+                   device="cuda", want_path=False, bucket=False):
     """Shared body of the three POI collators.  items: raw dataset items (owndata.py:340-349 fields; numpy or
-    torch).  Returns a device-resident Batch1."""
+    torch).  Returns a device-resident Batch1.  bucket: see `pack_host` (training loaders; the reference-shaped dense views
+    of a bucketed batch are padded to the bucket's node cap instead of the batch maximum)."""
     _C.require_cuda()
-    return collate_from_host(pack_host(items, max_node), world, latlon_dev, multi_hop_max_dist, rel_pos_max, device, want_path)
+    return collate_from_host(pack_host(items, max_node, bucket=bucket), world, latlon_dev, multi_hop_max_dist, rel_pos_max, device,
+                             want_path)
 
 
 def collator_foursquare(items, max_node=512, multi_hop_max_dist=20, rel_pos_max=20, world=None, latlon_dev=None, **kw):

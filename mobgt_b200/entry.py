@@ -114,8 +114,10 @@ def cli_main(argv=None):
             yield [items[j] for j in mine[i:i + args.batch_size]]
 
     def loader(items, shuffle, epoch, pad):
-        # one batch ahead: host packing in --num_workers processes, H2D + K1 + poi_pos + sort plans on a side stream
-        return collator.PackedLoader(item_batches(items, shuffle, epoch, pad), num_workers=args.num_workers, max_node=512, **ckw)
+        # one batch ahead: host packing in --num_workers processes, H2D + K1 + poi_pos + sort plans on a side stream; training
+        # batches are padded to size buckets so that the captured CUDA graphs replay across batches of different graphs
+        return collator.PackedLoader(item_batches(items, shuffle, epoch, pad), num_workers=args.num_workers, max_node=512,
+                                     bucket=shuffle and not args.no_cuda_graph, **ckw)
 
     model = Graphormer(
         n_layers=args.n_layers, num_heads=args.num_heads, hidden_dim=args.hidden_dim,

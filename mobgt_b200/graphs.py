@@ -36,7 +36,7 @@ def _tensor_fields(batch):
 
 
 class GraphedTrainStep:
-    def __init__(self, model, flat_grads, example_batch, warmup=3, after_backward=None):
+    def __init__(self, model, flat_grads, example_batch, warmup=3, after_backward=None, pool=None):
         """after_backward: optional callable run right after loss.backward() inside the captured region (the trainer joins
         the side stream of its early gradient all-reduce there, so the collective is part of the graph)."""
         self.model, self.flat = model, flat_grads
@@ -61,7 +61,7 @@ class GraphedTrainStep:
             if hasattr(model, "_w16"):
                 model._w16.stamp = None          # the bf16 re-cast of the weights must be part of the captured work
             n0 = _C.launch_count()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, pool=pool):          # pool: memory shared by graphs that never run concurrently
                 self.loss = self._body()
             self.launches = _C.launch_count() - n0       # libmobgt kernel nodes in the graph = launches per replay
             torch.cuda.synchronize()
@@ -101,6 +101,7 @@ class GraphedTrainStep:
             for d, s in zip(dst_plans["cat"], cat):
                 d.copy_(s, non_blocking=True)
         self.static.n_host = batch.n_host
+        self.static.padded = getattr(batch, "padded", False)
 
     def run(self):
         self.graph.replay()

@@ -101,8 +101,11 @@ def attn_fwd_raw(qkv, bias, batch, scale=None, drop_p=0.0, seed=0):
     B, H, T, Tp = bias.shape
     D = H * HEAD_DIM
     assert qkv.dtype == torch.bfloat16 and bias.dtype == torch.bfloat16 and qkv.shape[1] == 3 * D and qkv.is_contiguous()
-    out = torch.empty(ntok, D, dtype=torch.bfloat16, device=qkv.device)
-    lse = torch.empty(ntok, H, dtype=torch.float32, device=qkv.device)
+    # a bucketed batch carries padding token rows no graph owns: the kernels never touch them, and they must hold finite values
+    # (they flow through the row-wise layers and meet their zero gradients in the weight-gradient GEMMs)
+    alloc = torch.zeros if getattr(batch, "padded", False) else torch.empty
+    out = alloc(ntok, D, dtype=torch.bfloat16, device=qkv.device)
+    lse = alloc(ntok, H, dtype=torch.float32, device=qkv.device)
     scale = float(HEAD_DIM ** -0.5) if scale is None else float(scale)
     base = qkv.data_ptr()
     _C.call("mobgt_attn_fwd", base, base + 2 * D, base + 4 * D, 3 * D, _C.ptr(bias), _C.ptr(batch.tok_off), B, H, ntok, T, Tp,
@@ -119,7 +122,7 @@ def attn_bwd_raw(qkv, bias, out, dout, lse, batch, dbias, accumulate, scale=None
     D = H * HEAD_DIM
     assert dout.is_contiguous() and out.is_contiguous() and dbias.shape == bias.shape and dbias.is_contiguous()
     assert dbias.dtype == (torch.bfloat16 if accumulate == 2 else torch.float32)
-    dqkv = torch.empty_like(qkv)
+    dqkv = torch.zeros_like(qkv) if getattr(batch, "padded", False) else torch.empty_like(qkv)    # padding rows: zero gradient
     scale = float(HEAD_DIM ** -0.5) if scale is None else float(scale)
     base, dbase = qkv.data_ptr(), dqkv.data_ptr()
     _C.call("mobgt_attn_bwd", base, base + 2 * D, base + 4 * D, 3 * D, _C.ptr(bias), _C.ptr(out), _C.ptr(dout), _C.ptr(lse),

@@ -30,11 +30,11 @@ from . import graphs, ops, parallel
 
 def _signature(batch):
     return (int(batch.B), int(batch.N), int(batch.tok_pos.numel()), int(batch.rel_pos16.numel()), int(batch.hops),
-            int(getattr(batch, "dk", batch.hops)))
+            int(getattr(batch, "dk", batch.hops)), bool(getattr(batch, "padded", False)))
 
 
 class Trainer:
-    def __init__(self, model, device, world_size=1, cuda_graph=True, overlap=True, overlap_in_graph=False, max_graphs=4, group=None):
+    def __init__(self, model, device, world_size=1, cuda_graph=True, overlap=True, overlap_in_graph=False, max_graphs=16, group=None):
         self.model, self.dev, self.world, self.group = model, torch.device(device), int(world_size), group
         (self.opt,), (cfg,) = model.configure_optimizers()
         self.sched = cfg["scheduler"]
@@ -45,6 +45,7 @@ class Trainer:
             self.flat = self.grads.flat
         self.use_graph, self.max_graphs = bool(cuda_graph), int(max_graphs)
         self._graphs, self._seen, self._no_capture = {}, {}, set()
+        self._pool = torch.cuda.graph_pool_handle() if cuda_graph else None      # one memory pool for all captured shapes
         self.eager_steps = self.graph_steps = 0
         self.step_count = 0
         self.graph_note = "off" if not cuda_graph else "eager (no shape repeated yet)"
@@ -114,7 +115,7 @@ class Trainer:
             self._early_done, self._early_joined = None, False
             self._constructing = True
             try:
-                g = graphs.GraphedTrainStep(self.model, self.flat, batch, after_backward=self._join_early)
+                g = graphs.GraphedTrainStep(self.model, self.flat, batch, after_backward=self._join_early, pool=self._pool)
                 g.early_in_graph = bool(self._early_joined)
                 self._graphs[sig] = g
                 self.graph_note = "fwd+bwd captured" + (" (+ early all-reduce of out_proj.weight.grad in-graph)" if g.early_in_graph else "")

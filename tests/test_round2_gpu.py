@@ -508,6 +508,37 @@ def test_canonical_model_on_baseline_shapes(lib_built, case):
     assert not bad, bad
 
 
+def test_bucketed_batch_matches_unpadded(lib_built):
+    """A batch padded to size buckets (collator.pack_host(bucket=True): what the training loaders feed the CUDA graphs) gives
+    the loss and the gradients of the unpadded batch: padding tokens belong to no graph and carry exactly zero gradient."""
+    from mobgt_b200 import collator, model, synth
+    w = synth.make_world("c1", seed=1, dataset_name="gowalla_nevda")
+    items = synth.make_items(w, 9, 60, seed=8)
+    hp = dict(n_layers=2, num_heads=8, hidden_dim=128, dropout_rate=0.0, intput_dropout_rate=0.0, weight_decay=0.01, ffn_dim=256,
+              warmup_updates=10, tot_updates=100, peak_lr=2e-4, end_lr=1e-9, edge_type="multi_hop", multi_hop_max_dist=20,
+              attention_dropout_rate=0.0)
+    torch.manual_seed(4)
+    m = model.Graphormer(dataset_name="gowalla_nevda", world=w, **hp).cuda().train()
+    m.pos_embed.p = 0.0
+    m.poi_distance_model.eval()
+    m.poi_cat_model.eval()
+    res = []
+    for bucket in (False, True):
+        b = collator.collate_packed(items, w, None, 512, 20, 1024, bucket=bucket)
+        assert b.padded == bucket
+        m.zero_grad(set_to_none=True)
+        loss = m.training_step(b)
+        loss.backward()
+        res.append((loss.item(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+    (l0, g0), (l1, g1) = res
+    assert abs(l0 - l1) <= 1e-5 * abs(l0)
+    assert g0.keys() == g1.keys()
+    for k in g0:
+        assert torch.isfinite(g1[k]).all(), k
+        scale = g0[k].abs().max().item()
+        assert (g0[k] - g1[k]).abs().max().item() <= 2e-3 * scale + 1e-8, k      # other GEMM row counts -> other split-K orders
+
+
 # ------------------------------------------------------------------------------------------------------- entry point
 def test_entry_cli_main_reference_flags(lib_built, tmp_path, capsys):
     """`python entry.py` with the flags of the reference's README.md:62 (synthetic world instead of ../dataset): three training

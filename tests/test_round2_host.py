@@ -80,3 +80,29 @@ def test_from_dense_matches_oracle_collation(dk):
     for name in ("x", "rel_pos", "in_degree", "out_degree", "poi_pos", "attn_bias"):
         assert torch.equal(getattr(b, name), getattr(ob, name)), name
     assert torch.equal(b.edge_input, ob.edge_input[:, :, :, :b.edge_input.shape[3]])
+
+
+def test_pack_host_buckets_pad_only_the_tails():
+    """pack_host(bucket=True): per-graph sizes and the real prefix of every array are those of the unpadded pack; padding tokens
+    are graph-token rows (pos 0) that no tok_off range covers, padding nodes map to them one to one with padding-row indices."""
+    from mobgt_b200 import collator, synth
+    w = synth.make_world("tiny", seed=1)
+    items = synth.make_items(w, 7, 12, seed=5)
+    a, b = collator.pack_host(items), collator.pack_host(items, bucket=True)
+    view = lambda hp: {k: np.frombuffer(hp.buf[off:off + nb].tobytes(), dtype=np.dtype(dt)).reshape(shape)
+                       for k, (off, shape, dt, nb) in hp.layout.items()}
+    va, vb = view(a), view(b)
+    assert b.padded and not a.padded and b.B == a.B and np.array_equal(a.ns, b.ns)
+    ntok = len(va["tok_pos"])
+    assert len(vb["tok_pos"]) % 512 == 0 and len(vb["tok_pos"]) >= ntok
+    assert b.N >= a.N and (b.N & (b.N - 1)) == 0 and (b.cells & (b.cells - 1)) == 0 and b.cells >= a.cells
+    for k in ("n", "sq_off", "node_off", "tok_off", "user", "y", "idx"):
+        assert np.array_equal(va[k], vb[k]), k
+    for k in ("tok_graph", "tok_pos", "x_nodes", "slot", "in_deg", "out_deg", "node_rows", "time_normal_nodes"):
+        assert np.array_equal(va[k], vb[k][:len(va[k])]), k
+    assert np.array_equal(va["feat8"], vb["feat8"][:a.cells]) and not vb["feat8"][a.cells:].any()
+    pad = len(vb["tok_pos"]) - ntok
+    assert len(vb["x_nodes"]) - len(va["x_nodes"]) == pad                       # padding nodes == padding tokens
+    assert not vb["tok_pos"][ntok:].any() and not vb["in_deg"][len(va["in_deg"]):].any()
+    assert np.array_equal(vb["node_rows"][len(va["node_rows"]):], ntok + np.arange(pad))
+    assert int(vb["tok_off"][-1]) == ntok                                         # no graph owns a padding token
