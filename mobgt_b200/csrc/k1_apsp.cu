@@ -75,7 +75,7 @@ __host__ inline size_t k1_smem_bytes(int n, int C, bool with_path, int nthreads,
 }
 
 template <bool WITH_PATH>
-__global__ void __launch_bounds__(512) k1_apsp_kernel(const K1Params p, const int C) {
+__global__ void __launch_bounds__(1024) k1_apsp_kernel(const K1Params p, const int C) {
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (C > 1) ? (int)cluster.block_rank() : 0;
     const int gl = blockIdx.x / C;
@@ -331,11 +331,18 @@ __global__ void k1_degree_kernel(const uint8_t *__restrict__ feat, const int32_t
     }
 }
 
-static int pick_cluster(int n, bool with_path, int hops, int *nthreads_out, size_t *smem_out) {
+// Threads per CTA: 8 tasks (8-cell chunks) per thread and k-step when the launch has enough graphs to fill the GPU with that
+// (the preprocessing bench: thousands of graphs per launch); a launch of few graphs (one training batch of 256) is latency-
+// bound per k-step — one barrier per k — so it spreads every graph over up to 1024 threads (>= 2 tasks per thread) until the
+// launch offers ~48 warps per SM.
+static int pick_cluster(int n, int G, bool with_path, int hops, int *nthreads_out, size_t *smem_out) {
     for (int C = 1; C <= 8; C *= 2) {
         const int W = k1_W(n, C);
         const int ntask = n * (W / 8);
-        const int nt = ntask <= 32 ? 32 : ntask <= 128 ? 64 : ntask <= 512 ? 128 : ntask <= 2048 ? 256 : 512;
+        int nt = ntask <= 32 ? 32 : ntask <= 128 ? 64 : ntask <= 512 ? 128 : ntask <= 2048 ? 256 : 512;
+        while (nt < 1024 && 2 * nt <= ntask / 2 + 31 && (long long)G * C * (nt / 32) < (long long)kNumSMs * 48 &&
+               k1_smem_bytes(n, C, with_path, 2 * nt, hops) <= 227 * 1024)
+            nt *= 2;
         const size_t sm = k1_smem_bytes(n, C, with_path, nt, hops);
         if (sm <= 227 * 1024) {
             *nthreads_out = nt;
@@ -371,7 +378,7 @@ extern "C" int32_t mobgt_apsp_edge_input(const uint8_t *feat, const int32_t *n, 
     const bool with_path = path != nullptr || n_max_host > MOBGT_UNREACHABLE;   // see skip510 in the kernel
     int nt = 0;
     size_t smem = 0;
-    const int C = pick_cluster(n_max_host, with_path, hops, &nt, &smem);
+    const int C = pick_cluster(n_max_host, G_launch, with_path, hops, &nt, &smem);
     MOBGT_REQUIRE(C > 0, MOBGT_ERR_UNSUPPORTED, "mobgt_apsp_edge_input: no shared-memory plan for n=%d", n_max_host);
 
     K1Params p{feat, n, sq_off, gids, hops, dk, shift, dist, path, edge_in, maxdist};
