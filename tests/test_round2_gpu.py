@@ -568,3 +568,34 @@ def test_entry_cli_main_reference_flags(lib_built, tmp_path, capsys):
     # the reference's default multi_hop_max_dist
     r3 = entry.cli_main(common + ["--default_root_dir", str(tmp_path / "d5"), "--limit_train_steps", "2"])
     assert r3["steps"] == 2 and np.isfinite(r3["loss"])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
+def test_entry_two_ranks_report_the_one_rank_metrics(lib_built, tmp_path):
+    """`entry --test` under torch.distributed.run with 2 ranks prints the metrics of the WHOLE test set (every rank evaluates its
+    share, the metric sums are all-reduced) — the same numbers as the 1-rank run of the same checkpoint; and a 2-rank training
+    run of an epoch whose graph count does not split evenly finishes (equal batch counts per rank: no dead-locked all-reduce)."""
+    import re
+    import subprocess
+    import sys
+    common = ["--dataset_name", "toyotagraph", "--accelerator", "ddp", "--batch_size", "16", "--hidden_dim", "128", "--num_heads", "8",
+              "--n_layers", "2", "--ffn_dim", "256", "--edge_type", "multi_hop", "--multi_hop_max_dist", "20", "--seed", "1",
+              "--max_epochs", "1", "--synthetic", "tiny", "--train_graphs", "70", "--test_graphs", "41", "--default_root_dir",
+              str(tmp_path)]
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    run1 = lambda extra: subprocess.run([sys.executable, "-m", "mobgt_b200.entry"] + common + extra, capture_output=True, text=True,
+                                        env=env, cwd=ROOT, timeout=600)
+    run2 = lambda extra: subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                                         "--master-addr", "127.0.0.1", "--master-port", "29577", "-m", "mobgt_b200.entry"] + common + extra,
+                                        capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+    tr = run2([])                                                   # 70 graphs, 2 ranks, batch 16: 35 per rank -> 3 batches each
+    assert tr.returncode == 0, tr.stderr[-2000:]
+    assert "trained 3 steps" in tr.stdout
+    ck = os.path.join(str(tmp_path), "lightning_logs", "checkpoints", "last.ckpt")
+    a, b = run1(["--test", "--checkpoint_path", ck]), run2(["--test", "--checkpoint_path", ck])
+    assert a.returncode == 0 and b.returncode == 0, (a.stderr[-1500:], b.stderr[-1500:])
+    nums = lambda out: [float(x) for line in out.splitlines() if line.startswith(("ACC", "NDCG", "MRR")) for x in re.findall(r"[-+]?\d*\.\d+", line)]
+    na, nb = nums(a.stdout), nums(b.stdout)
+    assert len(na) == 7 and len(nb) == 7, (a.stdout, b.stdout)
+    assert all(abs(x - y) <= 2e-3 for x, y in zip(na, nb)), (na, nb)
+    assert "'n': 41" in a.stdout and "'n': 41" in b.stdout            # all 41 test graphs counted once
