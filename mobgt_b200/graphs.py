@@ -75,6 +75,7 @@ class GraphedTrainStep:
     def _body(self):
         self.seed_dev.add_(1)
         self.flat.zero_()
+        ops.grads_zeroed(self.flat)
         loss = self.model.training_step(self.static)
         loss.backward()
         if self._after_backward is not None:

@@ -463,9 +463,20 @@ class Graphormer(nn.Module):
 
     validation_epoch_end = test_epoch_end
 
+    def _flat_param_order(self):
+        """All parameters, with the q / k / v weights (and biases) of every attention layer next to each other: their gradients
+        then lie back to back in the flat gradient buffer, and the fused QKV backward writes dW [3 x hidden, hidden] and db with
+        ONE GEMM / column-sum output (ops._claim)."""
+        fused, seen = [], set()
+        for layer in self.layers:
+            a = layer.self_attention
+            fused += [a.linear_q.weight, a.linear_k.weight, a.linear_v.weight, a.linear_q.bias, a.linear_k.bias, a.linear_v.bias]
+        seen = {id(p) for p in fused}
+        return fused + [p for p in self.parameters() if id(p) not in seen]
+
     def configure_optimizers(self):
         """model_fqandtoyo.py:1599-1616"""
-        params = list(self.parameters())
+        params = self._flat_param_order()
         if params[0].is_cuda:        # K9: one kernel over flat parameter / gradient buffers (same arithmetic as torch's AdamW)
             from .optim import FlatAdamW
             optimizer = FlatAdamW(params, lr=self.peak_lr, weight_decay=self.weight_decay)

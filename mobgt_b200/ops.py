@@ -302,13 +302,15 @@ class EmbedSum(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------- K6
-def colsum(src):
-    """out[c] = sum_r src[r, c] in fp32 (src bf16 / f32 [N, C], last dim contiguous): the bias gradient of a Linear."""
+def colsum(src, out=None):
+    """out[c] = sum_r src[r, c] in fp32 (src bf16 / f32 [N, C], last dim contiguous): the bias gradient of a Linear.
+    out: optional f32 [C] destination (e.g. the parameter's slice of the flat gradient buffer)."""
     assert src.dim() == 2 and src.stride(1) == 1
     N, C = src.shape
     ws_bytes = int(_C.lib().mobgt_colsum_workspace_bytes(N, C))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=src.device)
-    out = torch.empty(C, dtype=torch.float32, device=src.device)
+    if out is None:
+        out = torch.empty(C, dtype=torch.float32, device=src.device)
     _C.call("mobgt_colsum", src.data_ptr(), _dt(src), src.stride(0), N, C, _C.ptr(out), _C.ptr(ws), ws_bytes, _C.stream_ptr())
     return out
 
@@ -331,7 +333,7 @@ class LayerNormFn(torch.autograd.Function):
         _C.call("mobgt_layernorm_fwd", _C.ptr(x), _C.ptr(g), _C.ptr(b), float(eps), N, D, _C.ptr(out), _C.ptr(out16), _C.ptr(mean),
                 _C.ptr(rstd), _C.stream_ptr())
         ctx.save_for_backward(x, g, mean, rstd)
-        ctx.want = want
+        ctx.want, ctx.masters = want, (gamma, beta)
         if want == "f32":
             return out
         if want == "bf16":
@@ -351,13 +353,14 @@ class LayerNormFn(torch.autograd.Function):
         dy32 = dy32.contiguous() if dy32 is not None else None
         dy16 = dy16.contiguous() if dy16 is not None else None
         dx = torch.empty_like(x)
-        dgamma = torch.empty(D, dtype=torch.float32, device=x.device)
-        dbeta = torch.empty(D, dtype=torch.float32, device=x.device)
+        tg, tb = _claim_vec(ctx.masters[0]), _claim_vec(ctx.masters[1])      # written in place when the flat buffer is fresh
+        dgamma = tg if tg is not None else torch.empty(D, dtype=torch.float32, device=x.device)
+        dbeta = tb if tb is not None else torch.empty(D, dtype=torch.float32, device=x.device)
         ws_bytes = int(_C.lib().mobgt_layernorm_bwd_workspace_bytes(D))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         _C.call("mobgt_layernorm_bwd", _C.ptr(dy32), _C.ptr(dy16), _C.ptr(x), _C.ptr(g), _C.ptr(mean), _C.ptr(rstd), N, D, _C.ptr(dx),
                 _C.ptr(dgamma), _C.ptr(dbeta), _C.ptr(ws), ws_bytes, _C.stream_ptr())
-        return dx, dgamma, dbeta, None, None
+        return dx, (None if tg is not None else dgamma), (None if tb is not None else dbeta), None, None
 
 
 def layer_norm(x, ln, want="f32"):
@@ -398,8 +401,10 @@ def _adln_fwd(x, y, gamma, beta, eps, p, want):
     return s, out, out16, (s, g, mean, rstd), seed
 
 
-def _adln_bwd(saved, grads, p, seed, want, need_s, seed_dev, want_colsum=False):
-    """-> (dx f32, dy bf16, dgamma, dbeta, column sums of dy | None)"""
+def _adln_bwd(saved, grads, p, seed, want, need_s, seed_dev, want_colsum=False, ln_masters=None, bias_masters=None):
+    """-> (dx f32, dy bf16, dgamma, dbeta, column sums of dy | None).  ln_masters = (gamma, beta) / bias_masters = the bias
+    parameter(s) of the Linear that produced y: when their gradient storage is fresh (`_claim`) the kernel writes dgamma / dbeta /
+    the column sums straight into it and the corresponding return value is None."""
     s, g, mean, rstd = saved
     N, D = s.shape
     grads = list(grads)
@@ -417,12 +422,16 @@ def _adln_bwd(saved, grads, p, seed, want, need_s, seed_dev, want_colsum=False):
     dx = torch.empty_like(s)
     dyb = torch.empty(N, D, dtype=torch.bfloat16, device=s.device)
     dgb = torch.empty(3 if want_colsum else 2, D, dtype=torch.float32, device=s.device)
+    tg = _claim_vec(ln_masters[0]) if ln_masters is not None else None
+    tb = _claim_vec(ln_masters[1]) if ln_masters is not None else None
+    tc = _claim(bias_masters) if (bias_masters is not None and want_colsum) else None
+    og, ob, oc = (tg if tg is not None else dgb[0]), (tb if tb is not None else dgb[1]), (tc if tc is not None else (dgb[2] if want_colsum else None))
     ws_bytes = int(_C.lib().mobgt_layernorm_bwd_workspace_bytes(D))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=s.device)
     _C.call("mobgt_add_dropout_layernorm_bwd", _C.ptr(dy32), _C.ptr(dy16), _C.ptr(ds_ext), _C.ptr(s), _C.ptr(g), _C.ptr(mean),
-            _C.ptr(rstd), N, D, p, seed, _C.ptr(dx), _C.ptr(dyb), dgb[0].data_ptr(), dgb[1].data_ptr(),
-            dgb[2].data_ptr() if want_colsum else None, _C.ptr(ws), ws_bytes, _C.ptr(seed_dev), _C.stream_ptr())
-    return dx, dyb, dgb[0], dgb[1], (dgb[2] if want_colsum else None)
+            _C.ptr(rstd), N, D, p, seed, _C.ptr(dx), _C.ptr(dyb), og.data_ptr(), ob.data_ptr(),
+            oc.data_ptr() if want_colsum else None, _C.ptr(ws), ws_bytes, _C.ptr(seed_dev), _C.stream_ptr())
+    return dx, dyb, (None if tg is not None else og), (None if tb is not None else ob), (_IN_PLACE if tc is not None else oc)
 
 
 def _adln_outputs(s, out, out16, want, need_s):
@@ -441,13 +450,13 @@ class AddDropoutLayerNormFn(torch.autograd.Function):
         s, out, out16, saved, seed = _adln_fwd(x, y, gamma, beta, eps, p, want)
         ctx.save_for_backward(*saved)
         ctx.cfg = (float(p), seed, want, need_s)
-        ctx.seed_dev = _seed_dev
+        ctx.seed_dev, ctx.ln_masters = _seed_dev, (gamma, beta)
         return _adln_outputs(s, out, out16, want, need_s)
 
     @staticmethod
     def backward(ctx, *grads):
         p, seed, want, need_s = ctx.cfg
-        dx, dyb, dgamma, dbeta, _ = _adln_bwd(ctx.saved_tensors, grads, p, seed, want, need_s, ctx.seed_dev)
+        dx, dyb, dgamma, dbeta, _ = _adln_bwd(ctx.saved_tensors, grads, p, seed, want, need_s, ctx.seed_dev, ln_masters=ctx.ln_masters)
         return dx, dyb, dgamma, dbeta, None, None, None, None
 
 
@@ -463,21 +472,23 @@ class LinearAddDropoutLNFn(torch.autograd.Function):
         s, out, out16, saved, seed = _adln_fwd(resid, y, gamma, beta, eps, p, want)
         ctx.save_for_backward(x16, w16, *saved)
         ctx.cfg = (float(p), seed, want, need_s)
-        ctx.seed_dev, ctx.masters = _seed_dev, masters
+        ctx.seed_dev, ctx.masters, ctx.ln_masters = _seed_dev, masters, (gamma, beta)
         return _adln_outputs(s, out, out16, want, need_s)
 
     @staticmethod
     def backward(ctx, *grads):
         x16, w16 = ctx.saved_tensors[:2]
         p, seed, want, need_s = ctx.cfg
-        dres, dy, dgamma, dbeta, dcol = _adln_bwd(ctx.saved_tensors[2:], grads, p, seed, want, need_s, ctx.seed_dev, want_colsum=True)
+        m = len(ctx.masters) // 2
+        dres, dy, dgamma, dbeta, dcol = _adln_bwd(ctx.saved_tensors[2:], grads, p, seed, want, need_s, ctx.seed_dev, want_colsum=True,
+                                                  ln_masters=ctx.ln_masters, bias_masters=ctx.masters[m:])
         dx16 = dy @ w16
-        pg = _deliver_param_grads(ctx.masters, dy.t() @ x16, dcol)
+        pg = _deliver_param_grads(ctx.masters, dy.t(), x16, dcol)
         return (dx16, None, None, dres, dgamma, dbeta, None, None, None, None) + pg
 
 
 # ----------------------------------------------------------------------------------------------- K10
-def gemm_bf16(a, w, bias=None, mode=0, a2=None, w2=None, want_colsum=False):
+def gemm_bf16(a, w, bias=None, mode=0, a2=None, w2=None, want_colsum=False, colsum_out=None):
     """C = epi(a w^T [, a2 w2^T], bias) on tcgen05 (csrc/k10_gemm.cu).  a bf16 [M, K], w bf16 [N, K] (nn.Linear layout), bias f32
     [N].  mode 0: + bias; 1: gelu(. + bias); 2: (a w^T) o gelu'(a2 w2^T + bias) [+ column sums].  -> C bf16 [M, N] (, colsum f32 [N])"""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.stride(1) == 1 and w.stride(1) == 1
@@ -490,7 +501,7 @@ def gemm_bf16(a, w, bias=None, mode=0, a2=None, w2=None, want_colsum=False):
         if want_colsum:
             nws = int(_C.lib().mobgt_gemm_workspace_bytes(M, N, 2))
             ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=a.device)
-            colsum = torch.empty(N, dtype=torch.float32, device=a.device)
+            colsum = colsum_out if colsum_out is not None else torch.empty(N, dtype=torch.float32, device=a.device)
     b = bias.detach().float().contiguous() if bias is not None else None
     _C.call("mobgt_gemm_bf16", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _C.ptr(b), _C.ptr(C), N, M, N, K, int(mode),
             a2.data_ptr() if a2 is not None else None, a2.stride(0) if a2 is not None else 0,
@@ -516,7 +527,7 @@ class FfnBlockFn(torch.autograd.Function):
         s, out, out16, saved, seed = _adln_fwd(resid, y, gamma, beta, eps, p, want)
         ctx.save_for_backward(x16, w1, w2, a, *saved)
         ctx.cfg = (float(p), seed, want, need_s)
-        ctx.seed_dev, ctx.masters = _seed_dev, (m_w1, m_b1, m_w2, m_b2)
+        ctx.seed_dev, ctx.masters, ctx.ln_masters = _seed_dev, (m_w1, m_b1, m_w2, m_b2), (gamma, beta)
         return _adln_outputs(s, out, out16, want, need_s)
 
     @staticmethod
@@ -524,11 +535,13 @@ class FfnBlockFn(torch.autograd.Function):
         x16, w1, w2, a = ctx.saved_tensors[:4]
         p, seed, want, need_s = ctx.cfg
         m_w1, m_b1, m_w2, m_b2 = ctx.masters
-        dres, dy, dgamma, dbeta, db2 = _adln_bwd(ctx.saved_tensors[4:], grads, p, seed, want, need_s, ctx.seed_dev, want_colsum=True)
+        dres, dy, dgamma, dbeta, db2 = _adln_bwd(ctx.saved_tensors[4:], grads, p, seed, want, need_s, ctx.seed_dev, want_colsum=True,
+                                                 ln_masters=ctx.ln_masters, bias_masters=(m_b2,))
         w2t = w2.t().contiguous()                                       # [ffn, hidden]: the B operand of dy W2
-        dh, db1 = gemm_bf16(dy, w2t, m_b1, mode=2, a2=x16, w2=w1, want_colsum=True)
-        g_w2, g_b2 = _deliver_param_grads((m_w2, m_b2), dy.t() @ a, db2)
-        g_w1, g_b1 = _deliver_param_grads((m_w1, m_b1), dh.t() @ x16, db1)
+        t1 = _claim((m_b1,))
+        dh, db1 = gemm_bf16(dy, w2t, m_b1, mode=2, a2=x16, w2=w1, want_colsum=True, colsum_out=t1)
+        g_w2, g_b2 = _deliver_param_grads((m_w2, m_b2), dy.t(), a, db2)
+        g_w1, g_b1 = _deliver_param_grads((m_w1, m_b1), dh.t(), x16, _IN_PLACE if t1 is not None else db1)
         dx16 = dh @ w1
         return (dx16, None, None, None, dres, dgamma, dbeta, None, None, None, None, g_w1, g_b1, g_w2, g_b2)
 
@@ -570,30 +583,98 @@ def on_grad_ready(param, fn):
         _grad_ready[id(param)] = fn
 
 
-def _deliver_param_grads(masters, dw16, db):
-    """Gradients of the fp32 master parameters of a (possibly fused) Linear.  When the masters already own gradient buffers
-    (the trainer's flat fp32 buffer: `p.grad` are views of it) the bf16 weight gradient is ADDED straight into them — one
-    mixed-precision kernel per parameter instead of a cast kernel plus an AccumulateGrad add — and autograd gets None.
-    Otherwise (plain autograd use) fp32 gradients are returned."""
+# ---- gradients written in place ------------------------------------------------------------------------------------------
+# The trainer keeps every parameter gradient as a view of ONE flat fp32 buffer that it zeroes before each backward and tells
+# this module about (`grads_zeroed`).  The FIRST gradient a parameter receives after that may simply be WRITTEN into its slice:
+# the weight-gradient GEMM stores fp32 straight into the buffer (`torch.mm(..., out_dtype=float32, out=view)`: no bf16 rounding
+# of dW, no cast, no add kernel) and the column-sum / LayerNorm-backward kernels get the slice as their output pointer.  A later
+# gradient of the same parameter (a module applied twice, gradient accumulation without zeroing) is added, as autograd would.
+_IN_PLACE = object()      # marker: "this gradient has already been written into the parameter's .grad"
+_zero_epoch = 0
+_zeroed_ranges = {}       # data_ptr of a zeroed flat buffer -> (lo, hi byte range, epoch of its last zeroing)
+_last_written = {}        # id(param) -> epoch of its last in-place write
+
+
+def grads_zeroed(flat):
+    """The caller has just zeroed the flat gradient buffer `flat` (p.grad of its parameters are views of it)."""
+    global _zero_epoch
+    _zero_epoch += 1
+    lo = flat.data_ptr()
+    _zeroed_ranges[lo] = (lo, lo + flat.numel() * flat.element_size(), _zero_epoch)
+
+
+def _claim(ps):
+    """A writable fp32 tensor [sum of rows, ...] over the gradient storage of the parameters `ps` when (a) they own gradient
+    views that lie back to back inside a flat buffer zeroed by `grads_zeroed` and (b) none of them has been written since that
+    zeroing; else None (the caller then takes the accumulate path)."""
+    if _zero_epoch == 0 or any(not (isinstance(p, torch.Tensor) and p.is_leaf) or p.grad is None for p in ps):
+        return None
+    g0 = ps[0].grad
+    ptr = lo = g0.data_ptr()
+    if lo % 16:           # (the kernels store with 128-bit accesses; optim.FlatAdamW / parallel.FlatGrads align every parameter)
+        return None
+    for p in ps:
+        g = p.grad
+        if g.dtype != torch.float32 or not g.is_contiguous() or g.data_ptr() != ptr or g.shape[1:] != g0.shape[1:]:
+            return None
+        ptr += g.numel() * 4
+    epoch = max((e for a, b, e in _zeroed_ranges.values() if a <= lo and ptr <= b), default=0)
+    if epoch == 0 or any(_last_written.get(id(p), -1) >= epoch for p in ps):
+        return None
+    for p in ps:
+        _last_written[id(p)] = epoch
+    if len(ps) == 1:
+        return g0
+    rows = sum(p.shape[0] for p in ps)
+    shape = (rows,) + tuple(g0.shape[1:])
+    stride, acc = [], 1
+    for d in reversed(shape):
+        stride.insert(0, acc)
+        acc *= d
+    return torch.as_strided(g0, shape, stride)
+
+
+def _claim_vec(p):
+    return _claim((p,))
+
+
+def _deliver_param_grads(masters, at, bm, db):
+    """Gradients of the fp32 master parameters of a (possibly fused) Linear: dW = at @ bm (at = dy^T [rows, tokens], bm = x
+    [tokens, in], both bf16), db = the bias gradient f32 [rows] (or _IN_PLACE: a kernel has already written it).
+    masters = (w_0, ..., w_{m-1}, b_0, ..., b_{m-1}).  With fresh flat gradient storage (`_claim`) dW is the fp32 output of the
+    GEMM itself; with gradient views that have already been written it is added; without gradient buffers (plain autograd use)
+    fp32 gradients are returned."""
     m = len(masters) // 2
     ws, bs = masters[:m], masters[m:]
+    rows = [w.shape[0] for w in ws]
+    tot = sum(rows)                           # (the working copy may carry zero padding rows behind the real ones)
     if all(p.grad is not None for p in masters):
-        r = 0
-        for w, b in zip(ws, bs):
-            n = w.shape[0]
-            w.grad.add_(dw16[r:r + n])
-            b.grad.add_(db[r:r + n])
-            r += n
+        tw = _claim(ws)
+        if tw is not None:
+            torch.mm(at[:tot], bm, out_dtype=torch.float32, out=tw)
+        else:
+            dw16 = at @ bm
+            r = 0
+            for w in ws:
+                w.grad.add_(dw16[r:r + w.shape[0]])
+                r += w.shape[0]
+        if db is not _IN_PLACE:
+            tb = _claim(bs)
+            if tb is not None:
+                tb.copy_(db[:tot])
+            else:
+                r = 0
+                for b in bs:
+                    b.grad.add_(db[r:r + b.shape[0]])
+                    r += b.shape[0]
+        for w in ws:
             fn = _grad_ready.get(id(w))
             if fn is not None:
                 fn(w)
         return (None,) * len(masters)
-    rows = [w.shape[0] for w in ws]
-    tot = sum(rows)                           # (the working copy may carry zero padding rows behind the real ones)
-    dw, db = dw16[:tot].float(), db[:tot]
-    if m == 1:
-        return (dw, db)
-    return tuple(dw.split(rows, 0)) + tuple(db.split(rows, 0))
+    dw = (at @ bm)[:tot].float()
+    dbs = (None,) * m if db is _IN_PLACE else tuple(db[:tot].split(rows, 0))
+    return tuple(dw.split(rows, 0)) + dbs
 
 
 class LinearBiasFn(torch.autograd.Function):
@@ -613,7 +694,11 @@ class LinearBiasFn(torch.autograd.Function):
         x, w16 = ctx.saved_tensors
         dy = dy.contiguous()
         dx = dy @ w16 if ctx.needs_input_grad[0] else None
-        grads = _deliver_param_grads(ctx.masters, dy.t() @ x, colsum(dy))
+        m = len(ctx.masters) // 2
+        tot = sum(b.shape[0] for b in ctx.masters[m:])
+        tb = _claim(ctx.masters[m:]) if tot == dy.shape[1] else None     # (a padded working copy: column sums via a temporary)
+        db = colsum(dy, out=tb)
+        grads = _deliver_param_grads(ctx.masters, dy.t(), x, _IN_PLACE if tb is not None else db)
         return (dx, None, None) + grads
 
 
@@ -710,7 +795,7 @@ class LinearGeluFn(torch.autograd.Function):
     def backward(ctx, da):
         x, w16, h = ctx.saved_tensors
         dh, db = gelu_bwd_colsum_raw(da.contiguous(), h)
-        return (dh @ w16, None, None) + _deliver_param_grads(ctx.masters, dh.t() @ x, db)
+        return (dh @ w16, None, None) + _deliver_param_grads(ctx.masters, dh.t(), x, db)
 
 
 def linear_gelu_bf16(x, lin, w16=None, b16=None):

@@ -50,7 +50,9 @@ class FlatAdamW(torch.optim.Optimizer):
         ops.weights_changed()           # the kernel wrote through the flat buffer: tensor version counters did not move
 
     def zero_grad(self, set_to_none=False):
+        from . import ops
         self.flat_grad.zero_()          # gradients stay views of the flat buffer
+        ops.grads_zeroed(self.flat_grad)
 
     def state_dict(self):
         return {"flat": True, "steps": self.steps, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,

@@ -62,6 +62,9 @@ class FlatGrads:
 
     def zero_(self):
         self.flat.zero_()
+        if self.flat.is_cuda:
+            from . import ops
+            ops.grads_zeroed(self.flat)      # the Linear backwards may now WRITE their gradients (ops._claim)
 
     def all_reduce_mean(self, group=None):
         world, _ = _world(group)

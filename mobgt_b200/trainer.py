@@ -145,6 +145,7 @@ class Trainer:
                 pass
         self.eager_steps += 1
         self.flat.zero_()
+        ops.grads_zeroed(self.flat)
         self._early_done, self._early_joined = None, False
         loss = self.model.training_step(batch)
         loss.backward()

@@ -107,7 +107,7 @@ def test_cuda_graph_step_matches_eager(lib_built):
     """graphs.GraphedTrainStep: replaying the captured forward + backward on a freshly loaded batch gives the same loss and
     the same gradients as the eager step (eval mode: no dropout, so the comparison is exact up to atomics-free determinism)."""
     import torch
-    from mobgt_b200 import collator, graphs, model as M, synth
+    from mobgt_b200 import collator, graphs, model as M, ops, synth
     world = synth.make_world("tiny", seed=1)
     dev = torch.device("cuda")
     torch.manual_seed(3)
@@ -132,6 +132,7 @@ def test_cuda_graph_step_matches_eager(lib_built):
         loss_g = float(g.run())
         grad_g = flat.clone()
         flat.zero_()
+        ops.grads_zeroed(flat)       # same gradient-delivery path as the captured step (fp32 weight gradients written in place)
         loss_e = model.training_step(b)
         loss_e.backward()
         assert abs(loss_g - float(loss_e)) <= 1e-5 * max(1.0, abs(float(loss_e)))

@@ -539,6 +539,43 @@ def test_bucketed_batch_matches_unpadded(lib_built):
         assert (g0[k] - g1[k]).abs().max().item() <= 2e-3 * scale + 1e-8, k      # other GEMM row counts -> other split-K orders
 
 
+@pytest.mark.parametrize("dataset_name", ["toyotagraph", "gowalla_nevda"])
+def test_gradients_written_in_place_match_autograd(lib_built, dataset_name):
+    """The trainer's gradient path — every parameter gradient is a view of the flat buffer of optim.FlatAdamW; after the buffer is
+    zeroed the Linear backwards WRITE into it (fp32 output of the weight-gradient GEMM, column sums and LayerNorm gradients as
+    kernel outputs: ops._claim) — gives the gradients plain autograd accumulates for the same model and batch.  A second backward
+    without zeroing in between ADDS (gradient accumulation keeps working)."""
+    from mobgt_b200 import collator, model, ops, synth
+    w = synth.make_world("c1", seed=1, dataset_name=dataset_name)
+    items = synth.make_items(w, 7, 40, seed=11)
+    hp = dict(n_layers=2, num_heads=8, hidden_dim=128, dropout_rate=0.0, intput_dropout_rate=0.0, weight_decay=0.01, ffn_dim=256,
+              warmup_updates=10, tot_updates=100, peak_lr=2e-4, end_lr=1e-9, edge_type="multi_hop", multi_hop_max_dist=20,
+              attention_dropout_rate=0.0)
+    torch.manual_seed(5)
+    m = model.Graphormer(dataset_name=dataset_name, world=w, **hp).cuda().train()
+    m.pos_embed.p = 0.0
+    m.poi_distance_model.eval()
+    m.poi_cat_model.eval()
+    b = collator.collate_packed(items, w, None, 512, 20, 1024)
+    m.zero_grad(set_to_none=True)
+    m.training_step(b).backward()                                 # plain autograd: gradients returned, bf16 dW cast to fp32
+    ref = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    (opt,), _ = m.configure_optimizers()                          # FlatAdamW: p.grad become views of opt.flat_grad
+    a = m.layers[0].self_attention
+    assert a.linear_k.weight.grad.data_ptr() == a.linear_q.weight.grad.data_ptr() + a.linear_q.weight.numel() * 4   # q | k | v back to back
+    opt.zero_grad()
+    m.training_step(b).backward()
+    got = {k: p.grad.clone() for k, p in m.named_parameters()}
+    assert ops._last_written.get(id(a.linear_q.weight)) == ops._zero_epoch      # the in-place path was taken
+    for k, r in ref.items():
+        scale = r.abs().max().item()
+        assert (got[k] - r).abs().max().item() <= 6e-3 * scale + 1e-8, k         # bf16 rounding of dW on the autograd path only
+    m.training_step(b).backward()                                 # no zeroing: accumulate
+    for k, r in ref.items():
+        scale = r.abs().max().item()
+        assert (m.get_parameter(k).grad - 2 * r).abs().max().item() <= 1.5e-2 * scale + 1e-8, k
+
+
 # ------------------------------------------------------------------------------------------------------- entry point
 def test_entry_cli_main_reference_flags(lib_built, tmp_path, capsys):
     """`python entry.py` with the flags of the reference's README.md:62 (synthetic world instead of ../dataset): three training
