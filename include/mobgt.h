@@ -139,11 +139,20 @@ int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const int16_t *r
  *          probabilities; training only — pass drop_p = 0 in eval).  The keep mask is a counter-based hash of
  *          (seed, plane, row, column), regenerated by the backward from the SAME seed: nothing is stored.  seed_dev (u64 in
  *          device memory, optional) is folded into the seed at run time (CUDA-graph replays draw fresh masks).
+ *   t_max_host / t_min_host: the largest / smallest token count (n + 1) of a graph of the batch, known on the host.  Graphs of
+ *          at most 16 tokens (9 in 10 of a trajectory data set: median 4 nodes) are computed by a SIMT kernel (one 64-thread
+ *          CTA per (graph, 4 heads), fp32 math, only the live bias cells are read), larger ones by the tensor-core kernel; both
+ *          kernels select their graphs ON THE DEVICE from tok_off, the two host numbers only let the entry point skip a launch
+ *          that would find no graph.  t_min_host = 0: unknown (both kernels are launched — e.g. when the call is captured
+ *          in a CUDA graph that is replayed for other batches).
+ *   graph_order: i32 [B] (optional) — the graph ids in launch order, largest graph first: CTA b works on graph
+ *          graph_order[b / H], so the long-running CTAs start at once and the ones that find nothing to do are dispatched
+ *          behind them.  NULL: identity.
  * ------------------------------------------------------------------------------------------ */
 int32_t mobgt_attn_fwd(const void *q, const void *k, const void *v, int64_t qkv_row_stride, const void *bias,
-                       const int32_t *tok_off, int32_t B, int32_t H, int32_t ntok, int32_t T, int32_t Tp,
-                       int32_t t_max_host, float scale, float drop_p, uint64_t seed, const void *seed_dev, void *out,
-                       float *lse, void *stream);
+                       const int32_t *tok_off, const int32_t *graph_order, int32_t B, int32_t H, int32_t ntok, int32_t T, int32_t Tp,
+                       int32_t t_max_host, int32_t t_min_host, float scale, float drop_p, uint64_t seed, const void *seed_dev,
+                       void *out, float *lse, void *stream);
 
 /* Backward of mobgt_attn_fwd.  o, dout: bf16 [ntok, H*24] contiguous; lse from the forward.
  * dq, dk, dv: bf16 with a common row stride (usually slices of one [ntok, 3*H*24] buffer).
@@ -154,10 +163,10 @@ int32_t mobgt_attn_fwd(const void *q, const void *k, const void *v, int64_t qkv_
  *           tokens receive unspecified values and are never read).
  * Scores / probabilities are recomputed in-tile and never stored in HBM. */
 int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, int64_t qkv_row_stride, const void *bias,
-                       const void *o, const void *dout, const float *lse, const int32_t *tok_off, int32_t B,
-                       int32_t H, int32_t ntok, int32_t T, int32_t Tp, int32_t t_max_host, float scale, void *dq,
-                       void *dk, void *dv, int64_t dqkv_row_stride, void *dbias, int32_t mode, float drop_p, uint64_t seed,
-                       const void *seed_dev, void *stream);
+                       const void *o, const void *dout, const float *lse, const int32_t *tok_off, const int32_t *graph_order,
+                       int32_t B, int32_t H, int32_t ntok, int32_t T, int32_t Tp, int32_t t_max_host, int32_t t_min_host, float scale,
+                       void *dq, void *dk, void *dv, int64_t dqkv_row_stride, void *dbias, int32_t mode, float drop_p,
+                       uint64_t seed, const void *seed_dev, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4 — node-embedding gather / sum and the deterministic segmented scatter-add backward.

@@ -247,6 +247,8 @@ class Batch1:
         outd[self.node_rows] = self.out_deg
         plans["ind"] = sort_plan(ind)
         plans["outd"] = sort_plan(outd)
+        # launch order of the attention kernels (mobgt_attn_fwd / _bwd `graph_order`): largest graph first
+        self.size_order = torch.argsort(self.n, descending=True, stable=True).int()
         return plans
 
     def to(self, device):

@@ -2,6 +2,8 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <map>
+#include <mutex>
 
 namespace mobgt {
 static thread_local char g_err[512] = "";
@@ -14,6 +16,29 @@ void set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// A side stream + two events per (device, slot): lets an entry point run two INDEPENDENT kernels next to each other —
+// fork: the side stream waits for everything enqueued on the caller's stream so far; join: the caller's stream waits for the
+// side stream.  Nothing synchronises with the host, and the pattern is legal inside a stream capture (the side stream joins the
+// capture between fork and join).  The objects are created on first use, which must not fall inside a capture (the trainer
+// warms every captured step up eagerly first).
+int32_t get_fork_join(int slot, ForkJoin *out) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, ForkJoin> cache;
+    int dev = 0;
+    MOBGT_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find({dev, slot});
+    if (it == cache.end()) {
+        ForkJoin fj{};
+        MOBGT_CUDA_OK(cudaStreamCreateWithFlags(&fj.side, cudaStreamNonBlocking));
+        MOBGT_CUDA_OK(cudaEventCreateWithFlags(&fj.fork, cudaEventDisableTiming));
+        MOBGT_CUDA_OK(cudaEventCreateWithFlags(&fj.join, cudaEventDisableTiming));
+        it = cache.emplace(std::make_pair(dev, slot), fj).first;
+    }
+    *out = it->second;
+    return MOBGT_OK;
 }
 }  // namespace mobgt
 

@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "k3_small.cuh"
 #include "umma.cuh"
 
 namespace mobgt {
@@ -50,6 +51,8 @@ struct AttnBwdParams {
     const __nv_bfloat16 *q, *k, *v;   // raw views of the operands (row stride qkv_stride) for the single-token tail
     int64_t qkv_stride;
     const __nv_bfloat16 *bias;        // [B,H,T,Tp]
+    int small_t;                      // graphs of at most this many tokens belong to the SIMT kernel (k3_attn_small.cu); 0: none
+    const int32_t *order;             // [B] graph ids in launch order (descending size) or NULL
 };
 
 // 24 bf16 (three 16-byte words) -> fp32
@@ -107,9 +110,11 @@ k3_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     MOBGT_STAMP(p.timeline, 0);
     const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, t128 = tid & 127;
     const bool warp0 = warp_index_uniform() == 0;   // the issuing warp (one elected lane issues TMA / MMA)
-    const int g = blockIdx.x / p.H, h = blockIdx.x - g * p.H;
+    const int gi = blockIdx.x / p.H, h = blockIdx.x - gi * p.H;
+    const int g = p.order ? p.order[gi] : gi;       // largest graphs first: the CTAs that return at once are dispatched behind them
     const int t0 = p.tok_off[g];
     const int Tg = p.tok_off[g + 1] - t0;
+    if (Tg <= p.small_t) return;                           // the whole CTA: nothing has been set up yet
     const bool fold = Tg > kTile && (Tg % kTile) == 1;     // single-token tail handled by SIMT (see above)
     const int NB = fold ? Tg / kTile : ceil_div(Tg, kTile);
     const int sp = Tg - 1;                                 // the tail token (fold only)
@@ -668,9 +673,11 @@ k3_attn_bwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
     const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, t128 = tid & 127;
     const bool warp0 = warp_index_uniform() == 0;
-    const int g = blockIdx.x / p.H, h = blockIdx.x - g * p.H;
+    const int gi = blockIdx.x / p.H, h = blockIdx.x - gi * p.H;
+    const int g = p.order ? p.order[gi] : gi;       // largest graphs first: the CTAs that return at once are dispatched behind them
     const int t0 = p.tok_off[g];
     const int Tg = p.tok_off[g + 1] - t0;            // <= 129
+    if (Tg <= p.small_t) return;                     // the whole CTA: nothing has been set up yet
     const bool fold = Tg == kTile + 1;
     const int nv = fold ? kTile : Tg;                // query rows == key columns covered by the MMA tile
     const int sp = Tg - 1;                           // the tail token (fold only)
@@ -1070,8 +1077,9 @@ using namespace mobgt;
 // row stride (usually slices of one [ntok, 3*H*24] buffer, so the fused projection's backward gets a single tensor);
 // dbias f32 [B,H,T,Tp]: overwritten (accumulate = 0) or accumulated into (accumulate = 1).
 extern "C" int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, int64_t qkv_row_stride, const void *bias,
-                                  const void *o, const void *dout, const float *lse, const int32_t *tok_off, int32_t B,
-                                  int32_t H, int32_t ntok, int32_t T, int32_t Tp, int32_t t_max_host, float scale, void *dq,
+                                  const void *o, const void *dout, const float *lse, const int32_t *tok_off,
+                                  const int32_t *graph_order, int32_t B, int32_t H, int32_t ntok, int32_t T, int32_t Tp, int32_t t_max_host, int32_t t_min_host,
+                                  float scale, void *dq,
                                   void *dk, void *dv, int64_t dqkv_row_stride, void *dbias, int32_t accumulate, float drop_p,
                                   uint64_t seed, const void *seed_dev, void *stream) {
     MOBGT_REQUIRE(q && k && v && bias && o && dout && lse && tok_off && dq && dk && dv && dbias, MOBGT_ERR_NULL,
@@ -1081,6 +1089,41 @@ extern "C" int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, i
     MOBGT_REQUIRE(t_max_host >= 1 && t_max_host <= T && T <= MOBGT_MAX_NODES + 1, MOBGT_ERR_BAD_SHAPE,
                   "mobgt_attn_bwd: t_max=%d T=%d", t_max_host, T);
     if (B == 0 || ntok == 0) return MOBGT_OK;
+    MOBGT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, MOBGT_ERR_BAD_SHAPE, "mobgt_attn_bwd: drop_p=%f must be in [0, 1)", drop_p);
+    // the same device-side split by graph size as the forward (k3_attn_small.cu)
+    const bool any_small = (t_min_host <= 0 || t_min_host <= kSmallT) && H % 4 == 0;
+    const bool any_large = t_max_host > kSmallT;
+    ForkJoin fj{};
+    bool forked = false;
+    if (any_small) {
+        SmallAttnParams sp{};
+        sp.tok_off = tok_off;
+        sp.order = graph_order;
+        sp.q = static_cast<const __nv_bfloat16 *>(q); sp.k = static_cast<const __nv_bfloat16 *>(k); sp.v = static_cast<const __nv_bfloat16 *>(v);
+        sp.qkv_stride = qkv_row_stride;
+        sp.bias = static_cast<const __nv_bfloat16 *>(bias);
+        sp.H = H; sp.T = T; sp.Tp = Tp; sp.scale = scale; sp.small_t = kSmallT;
+        sp.drop = make_attn_drop(drop_p, seed, seed_dev);
+        sp.lse = const_cast<float *>(lse);
+        sp.o = static_cast<const __nv_bfloat16 *>(o); sp.dout = static_cast<const __nv_bfloat16 *>(dout);
+        sp.dq = static_cast<__nv_bfloat16 *>(dq); sp.dk = static_cast<__nv_bfloat16 *>(dk); sp.dv = static_cast<__nv_bfloat16 *>(dv);
+        sp.dqkv_stride = dqkv_row_stride;
+        sp.dbias = dbias; sp.accumulate = accumulate;
+        if (!any_large) return launch_small_attn_bwd(sp, B, static_cast<cudaStream_t>(stream));
+        // both kernels: they work on disjoint graphs, so the SIMT one runs on a side stream next to the tensor-core one
+        int32_t rc = get_fork_join(1, &fj);
+        if (rc) return rc;
+        MOBGT_CUDA_OK(cudaEventRecord(fj.fork, static_cast<cudaStream_t>(stream)));
+        MOBGT_CUDA_OK(cudaStreamWaitEvent(fj.side, fj.fork, 0));
+        rc = launch_small_attn_bwd(sp, B, fj.side);
+        MOBGT_CUDA_OK(cudaEventRecord(fj.join, fj.side));
+        forked = true;
+        if (rc) {
+            cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), fj.join, 0);
+            return rc;
+        }
+    }
+    auto run_tensor_core = [&]() -> int32_t {
     CUtensorMap tmQ, tmK, tmV, tmdO, tmB;
     const void *ptrs[4] = {q, k, v, dout};
     CUtensorMap *maps[4] = {&tmQ, &tmK, &tmV, &tmdO};
@@ -1137,7 +1180,8 @@ extern "C" int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, i
                     static_cast<const __nv_bfloat16 *>(k),
                     static_cast<const __nv_bfloat16 *>(v),
                     qkv_row_stride,
-                    static_cast<const __nv_bfloat16 *>(bias)};
+                    static_cast<const __nv_bfloat16 *>(bias),
+                    any_small ? kSmallT : 0, graph_order};
     if (accumulate == 2 && t_max_host <= kTile + 1) {   // every graph fits one (query tile, key block): two CTAs per SM
         const size_t smem1 = (size_t)kBiasTileBytes + kPBytes + 4 * kBoxBytes + 1024;
         auto kern1 = drop.th16 ? k3_attn_bwd1_kernel<true> : k3_attn_bwd1_kernel<false>;
@@ -1150,4 +1194,8 @@ extern "C" int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, i
     kern<<<B * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmdO, tmB, tmDS, p);
     MOBGT_LAUNCH_OK("k3_attn_bwd_kernel");
     return MOBGT_OK;
+    };
+    const int32_t rc = run_tensor_core();
+    if (forked) cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), fj.join, 0);   // join on every path
+    return rc;
 }

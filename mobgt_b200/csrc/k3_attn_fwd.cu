@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "k3_small.cuh"
 #include "umma.cuh"
 
 namespace mobgt {
@@ -41,6 +42,8 @@ struct AttnFwdParams {
     int64_t qkv_stride;
     const __nv_bfloat16 *bias;        // [B,H,T,Tp]
     int T, Tp;
+    int small_t;                      // graphs of at most this many tokens belong to the SIMT kernel (k3_attn_small.cu); 0: none
+    const int32_t *order;             // [B] graph ids in launch order (descending size) or NULL
 };
 
 __device__ __forceinline__ void fwd_unpack24(const uint4 &a, const uint4 &b, const uint4 &c, float (&f)[24]) {
@@ -88,9 +91,11 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     MOBGT_STAMP(p.timeline, 0);
     const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, t128 = tid & 127;
     const bool warp0 = warp_index_uniform() == 0;   // the issuing warp (one elected lane issues TMA / MMA)
-    const int g = blockIdx.x / p.H, h = blockIdx.x - g * p.H;
+    const int gi = blockIdx.x / p.H, h = blockIdx.x - gi * p.H;
+    const int g = p.order ? p.order[gi] : gi;       // largest graphs first: the CTAs that return at once are dispatched behind them
     const int t0 = p.tok_off[g];
     const int Tg = p.tok_off[g + 1] - t0;
+    if (Tg <= p.small_t) return;                           // the whole CTA: nothing has been set up yet
     const bool fold = Tg > kTile && (Tg % kTile) == 1;     // single-token tail handled by SIMT (see above)
     const int NB = fold ? Tg / kTile : ceil_div(Tg, kTile);
     const int sp = Tg - 1;                                 // the tail token (fold only)
@@ -482,9 +487,9 @@ using namespace mobgt;
 // qkv: three bf16 matrices of [ntok, H*24] with a common row stride (elements); typically slices of one fused
 // [ntok, 3*H*24] projection.  bias: bf16 [B, H, T, Tp].  out: bf16 [ntok, H*24] (contiguous).  lse: f32 [ntok, H].
 extern "C" int32_t mobgt_attn_fwd(const void *q, const void *k, const void *v, int64_t qkv_row_stride, const void *bias,
-                                  const int32_t *tok_off, int32_t B, int32_t H, int32_t ntok, int32_t T, int32_t Tp,
-                                  int32_t t_max_host, float scale, float drop_p, uint64_t seed, const void *seed_dev,
-                                  void *out, float *lse, void *stream) {
+                                  const int32_t *tok_off, const int32_t *graph_order, int32_t B, int32_t H, int32_t ntok,
+                                  int32_t T, int32_t Tp, int32_t t_max_host, int32_t t_min_host, float scale, float drop_p, uint64_t seed,
+                                  const void *seed_dev, void *out, float *lse, void *stream) {
     MOBGT_REQUIRE(q && k && v && bias && tok_off && out && lse, MOBGT_ERR_NULL, "mobgt_attn_fwd: null pointer");
     MOBGT_REQUIRE(H >= 1 && B >= 0 && ntok >= 0, MOBGT_ERR_BAD_SHAPE, "mobgt_attn_fwd: B=%d H=%d ntok=%d", B, H, ntok);
     MOBGT_REQUIRE(qkv_row_stride % 8 == 0 && Tp % 8 == 0 && Tp >= T, MOBGT_ERR_BAD_SHAPE,
@@ -493,6 +498,37 @@ extern "C" int32_t mobgt_attn_fwd(const void *q, const void *k, const void *v, i
                   "mobgt_attn_fwd: t_max=%d T=%d", t_max_host, T);
     MOBGT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, MOBGT_ERR_BAD_SHAPE, "mobgt_attn_fwd: drop_p=%f must be in [0, 1)", drop_p);
     if (B == 0 || ntok == 0) return MOBGT_OK;
+    // graphs of <= kSmallT tokens: SIMT kernel; the others: tensor cores.  Both kernels select their graphs on the device, so
+    // the host only decides which launches can be skipped (t_min_host = 0: unknown, e.g. a CUDA graph shared by many batches).
+    const bool any_small = (t_min_host <= 0 || t_min_host <= kSmallT) && H % 4 == 0;
+    const bool any_large = t_max_host > kSmallT;
+    ForkJoin fj{};
+    bool forked = false;
+    if (any_small) {
+        SmallAttnParams sp{};
+        sp.tok_off = tok_off;
+        sp.order = graph_order;
+        sp.q = static_cast<const __nv_bfloat16 *>(q); sp.k = static_cast<const __nv_bfloat16 *>(k); sp.v = static_cast<const __nv_bfloat16 *>(v);
+        sp.qkv_stride = qkv_row_stride;
+        sp.bias = static_cast<const __nv_bfloat16 *>(bias);
+        sp.H = H; sp.T = T; sp.Tp = Tp; sp.scale = scale; sp.small_t = kSmallT;
+        sp.drop = make_attn_drop(drop_p, seed, seed_dev);
+        sp.out = static_cast<__nv_bfloat16 *>(out); sp.lse = lse;
+        if (!any_large) return launch_small_attn_fwd(sp, B, static_cast<cudaStream_t>(stream));
+        // both kernels: they work on disjoint graphs, so the SIMT one runs on a side stream next to the tensor-core one
+        int32_t rc = get_fork_join(0, &fj);
+        if (rc) return rc;
+        MOBGT_CUDA_OK(cudaEventRecord(fj.fork, static_cast<cudaStream_t>(stream)));
+        MOBGT_CUDA_OK(cudaStreamWaitEvent(fj.side, fj.fork, 0));
+        rc = launch_small_attn_fwd(sp, B, fj.side);
+        MOBGT_CUDA_OK(cudaEventRecord(fj.join, fj.side));
+        forked = true;
+        if (rc) {
+            cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), fj.join, 0);
+            return rc;
+        }
+    }
+    auto run_tensor_core = [&]() -> int32_t {
     CUtensorMap tmQ, tmK, tmV, tmB;
     const void *ptrs[3] = {q, k, v};
     CUtensorMap *maps[3] = {&tmQ, &tmK, &tmV};
@@ -516,10 +552,15 @@ extern "C" int32_t mobgt_attn_fwd(const void *q, const void *k, const void *v, i
     AttnFwdParams p{tok_off, static_cast<__nv_bfloat16 *>(out), lse, H, scale, max_boxes, g_timeline_dev,
                     make_attn_drop(drop_p, seed, seed_dev),
                     static_cast<const __nv_bfloat16 *>(q), static_cast<const __nv_bfloat16 *>(k),
-                    static_cast<const __nv_bfloat16 *>(v), qkv_row_stride, static_cast<const __nv_bfloat16 *>(bias), T, Tp};
+                    static_cast<const __nv_bfloat16 *>(v), qkv_row_stride, static_cast<const __nv_bfloat16 *>(bias), T, Tp,
+                    any_small ? kSmallT : 0, graph_order};
     auto kern = p.drop.th16 ? k3_attn_fwd_kernel<true> : k3_attn_fwd_kernel<false>;
     MOBGT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<B * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmB, p);
     MOBGT_LAUNCH_OK("k3_attn_fwd_kernel");
     return MOBGT_OK;
+    };
+    const int32_t rc = run_tensor_core();
+    if (forked) cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), fj.join, 0);   // join on every path
+    return rc;
 }

@@ -48,6 +48,7 @@ class GraphedTrainStep:
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self._fields = _tensor_fields(example_batch)
         self._meta = (int(example_batch.B), int(example_batch.N), {k: tuple(v.shape) for k, v in self._fields.items()})
+        self._all_large = ops.all_large(example_batch)     # decides which attention kernels the capture contains
         self.graph = torch.cuda.CUDAGraph()
         ops.set_device_seed(self.seed_dev)
         try:
@@ -87,7 +88,8 @@ class GraphedTrainStep:
         if batch is self.static:
             return
         f = _tensor_fields(batch)
-        if (int(batch.B), int(batch.N)) != self._meta[:2] or {k: tuple(v.shape) for k, v in f.items()} != self._meta[2]:
+        if (int(batch.B), int(batch.N)) != self._meta[:2] or {k: tuple(v.shape) for k, v in f.items()} != self._meta[2] \
+                or ops.all_large(batch) != self._all_large:
             raise ShapeMismatch("batch shapes differ from the captured ones")
         for k, dst in self._fields.items():
             dst.copy_(f[k], non_blocking=True)

@@ -94,6 +94,22 @@ class AttnBias(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------- K3
+SMALL_T = 16     # csrc/k3_small.cuh kSmallT: graphs of at most this many tokens take the SIMT attention kernels
+
+
+def all_large(batch):
+    """True when every graph of the batch has more than SMALL_T tokens (then the small-graph attention launch is skipped).
+    A bucketed batch never claims it: its CUDA graph is replayed for other batches of the same bucket."""
+    if getattr(batch, "padded", False) or getattr(batch, "n_host", None) is None or len(batch.n_host) == 0:
+        return False
+    return int(min(batch.n_host)) + 1 > SMALL_T
+
+
+def _t_min(batch):
+    """t_min_host of mobgt_attn_fwd / _bwd: the smallest token count of the batch, 0 = unknown (launch both kernels)."""
+    return int(min(batch.n_host)) + 1 if all_large(batch) else 0
+
+
 def attn_fwd_raw(qkv, bias, batch, scale=None, drop_p=0.0, seed=0):
     """qkv bf16 [ntok, 3*H*24] (fused projection) ; bias bf16 [B,H,T,Tp] -> (out bf16 [ntok, H*24], lse f32 [ntok,H]).
     drop_p > 0: attention dropout on the probabilities (model_fqandtoyo.py:1704), mask = hash(seed, plane, row, col)."""
@@ -108,9 +124,9 @@ def attn_fwd_raw(qkv, bias, batch, scale=None, drop_p=0.0, seed=0):
     lse = alloc(ntok, H, dtype=torch.float32, device=qkv.device)
     scale = float(HEAD_DIM ** -0.5) if scale is None else float(scale)
     base = qkv.data_ptr()
-    _C.call("mobgt_attn_fwd", base, base + 2 * D, base + 4 * D, 3 * D, _C.ptr(bias), _C.ptr(batch.tok_off), B, H, ntok, T, Tp,
-            int(batch.N) + 1, scale, float(drop_p), int(seed), _C.ptr(_seed_dev) if drop_p > 0 else None, _C.ptr(out), _C.ptr(lse),
-            _C.stream_ptr())
+    _C.call("mobgt_attn_fwd", base, base + 2 * D, base + 4 * D, 3 * D, _C.ptr(bias), _C.ptr(batch.tok_off), _C.ptr(getattr(batch, "size_order", None)), B, H,
+            ntok, T, Tp, int(batch.N) + 1, _t_min(batch), scale, float(drop_p), int(seed), _C.ptr(_seed_dev) if drop_p > 0 else None, _C.ptr(out),
+            _C.ptr(lse), _C.stream_ptr())
     return out, lse
 
 
@@ -126,7 +142,7 @@ def attn_bwd_raw(qkv, bias, out, dout, lse, batch, dbias, accumulate, scale=None
     scale = float(HEAD_DIM ** -0.5) if scale is None else float(scale)
     base, dbase = qkv.data_ptr(), dqkv.data_ptr()
     _C.call("mobgt_attn_bwd", base, base + 2 * D, base + 4 * D, 3 * D, _C.ptr(bias), _C.ptr(out), _C.ptr(dout), _C.ptr(lse),
-            _C.ptr(batch.tok_off), B, H, ntok, T, Tp, int(batch.N) + 1, scale, dbase, dbase + 2 * D, dbase + 4 * D, 3 * D,
+            _C.ptr(batch.tok_off), _C.ptr(getattr(batch, "size_order", None)), B, H, ntok, T, Tp, int(batch.N) + 1, _t_min(batch), scale, dbase, dbase + 2 * D, dbase + 4 * D, 3 * D,
             _C.ptr(dbias), int(accumulate), float(drop_p), int(seed), _C.ptr(_seed_dev) if drop_p > 0 else None, _C.stream_ptr())
     return dqkv
 

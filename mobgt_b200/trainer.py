@@ -30,7 +30,7 @@ from . import graphs, ops, parallel
 
 def _signature(batch):
     return (int(batch.B), int(batch.N), int(batch.tok_pos.numel()), int(batch.rel_pos16.numel()), int(batch.hops),
-            int(getattr(batch, "dk", batch.hops)), bool(getattr(batch, "padded", False)))
+            int(getattr(batch, "dk", batch.hops)), bool(getattr(batch, "padded", False)), ops.all_large(batch))
 
 
 class Trainer:

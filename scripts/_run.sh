@@ -1,4 +1,6 @@
-O=gpurun_out/r3c; mkdir -p $O
-timeout 900 python -m pytest tests -m gpu -x -q -k "in_place or cuda_graph or canonical or bucketed or entry_cli or k6 or layer_norm or linear or ffn or k10 or model_parity or loss_and_gradients" > $O/pytest_sub.log 2>&1; echo "pytest rc=$?"; tail -15 $O/pytest_sub.log
-timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-kernel-report > $O/bench_c2.json 2> $O/bench_c2.err; echo "bench rc=$?"; cat $O/bench_c2.json | cut -c1-600
-timeout 300 python scripts/step_kernels.py c2-dense128 > $O/step_kernels_c2.txt 2>&1; echo rc=$?
+O=gpurun_out/r3i; mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -x -q -k "attention or attn or k3 or canonical or bucketed or golden or cuda_graph or entry_cli" > $O/pytest_sub.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_sub.log
+timeout 300 python scripts/step_kernels.py c2-natural > $O/step_kernels_nat.txt 2>&1; echo rc=$?
+for w in c2-natural c4-gowalla256; do
+timeout 600 python bench.py --workload $w --steps 20 --warmup 5 --no-cpu-baseline --no-kernel-report > $O/bench_$w.json 2> $O/bench_$w.err; echo "bench $w rc=$?"; cut -c1-200 $O/bench_$w.json
+done
