@@ -227,7 +227,7 @@ int32_t mobgt_colsum(const void *src, int32_t src_dtype, int64_t src_stride, int
  * (model_fqandtoyo.py:1396-1428, :48-90, :122-131).  logits = z W^T + bias are produced tile by tile in TMEM and
  * consumed in the epilogue; they are only written to HBM when logits_dump != NULL (tests).
  *   z bf16 [M,K] ; W bf16 [V,K] = this rank's vocabulary shard (global index of row 0 = vocab_offset) ; bias f32 [V]|NULL
- *   target i32 [M] global vocabulary index (<0: none) ; K multiple of 16, <= 320 ; k <= 32 ; nsplit <= 64
+ *   target i32 [M] global vocabulary index (<0: none) ; K multiple of 16, <= 320 ; k <= 32 ; nsplit even, <= 160
  *   mode 0: st[row] = logit of the row's target, written by the shard that owns it (initialise st to -inf; across
  *           shards: all-reduce MAX)
  *   mode 1: per (row, split): sorted top-k (value, global index), count(s > st), count(s == st and idx < target)
@@ -321,6 +321,9 @@ int32_t mobgt_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t ldb, 
 /* Debug hook: register (NULL: clear) a device buffer of 256 int64; thread 0 of one CTA of mobgt_attn_fwd / mobgt_attn_bwd then
  * stamps clock64() at its pipeline stages (scripts/timeline.py). */
 int32_t mobgt_debug_set_timeline(void *dev_buf256);
+/* Measurement switch of mobgt_head_topk: 0 = never pair adjacent row tiles into 2-CTA clusters (TMA multicast of the W stages),
+ * 1 = default (paired whenever the number of 128-row tiles is even). */
+int32_t mobgt_debug_head_cluster(int32_t on);
 
 #ifdef __cplusplus
 }

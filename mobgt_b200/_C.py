@@ -62,6 +62,7 @@ SIGNATURES = {
     "mobgt_gemm_bf16": [c_p, c_i64, c_p, c_i64, c_p, c_p, c_i64, c_i32, c_i32, c_i32, c_i32, c_p, c_i64, c_p, c_i64, c_i32, c_p, c_p,
                         c_i64, c_p],
     "mobgt_debug_set_timeline": [c_p],
+    "mobgt_debug_head_cluster": [c_i32],
     "mobgt_selftest_umma": [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p],
 }
 

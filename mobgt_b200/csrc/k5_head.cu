@@ -6,9 +6,9 @@
 //
 // mode 1 (k5_head_kernel) — warp-specialised, one CTA per (128-row tile of z, vocabulary split):
 //   warp 0      TMA producer: z tile once (resident, K/64 blocks of [128 rows][128 B]); W tiles stream through a ring of
-//               16 KB stages, one stage = 128 vocabulary rows x 64 K-columns, 2-D boxes with the 128-byte swizzle
-//   warp 1      MMA issuer: tcgen05.mma M=128 N=128 K=16, K/16 steps per tile, accumulators double-buffered in TMEM
-//               (2 x 128 columns); a stage is released by tcgen05.commit, a finished accumulator is published the same way
+//               32 KB stages, one stage = 256 vocabulary rows x 64 K-columns, 2-D boxes with the 128-byte swizzle
+//   warp 1      MMA issuer: tcgen05.mma M=128 N=256 K=16, K/16 steps per tile, accumulators double-buffered in TMEM
+//               (2 x 256 columns); a stage is released by tcgen05.commit, a finished accumulator is published the same way
 //   warp 2      TMEM allocation;  warp 3 idle
 //   warps 4-11  two epilogue warpgroups, one per accumulator buffer (tile t goes to group t & 1).  Thread = row.  Per element:
 //               + bias, one compare for the rank count, a 4-wide max against the running k-th value.  The rank
@@ -35,10 +35,15 @@ constexpr int kHeadTile = 128;
 constexpr int kHeadMaxK = 320;     // 2*hidden + 64 (model_fqandtoyo.py:1059-1068)
 constexpr int kHeadMaxTop = 32;
 constexpr int kKB = 64;                          // K columns per stage = one 128-byte swizzle row
-constexpr int kBlkBytes = kHeadTile * 128;       // 16 KB: [128 rows][128 B]
-constexpr int kMaxRing = 8;
-constexpr int kCandCap = 8;
+constexpr int kBlkBytes = kHeadTile * 128;       // 16 KB: [128 rows][128 B] (one K block of the resident z tile)
+constexpr int kNT = 256;                         // vocabulary rows per tile = MMA N.  With both operands in shared memory an
+                                                 // M = 128, N = 128, K = 16 MMA reads 8 KB per 64 tensor cycles = the whole
+                                                 // 128 B/clk of the SM's shared memory; N = 256 reads 12 KB per 128 cycles.
+constexpr int kStageBytes = kNT * 128;           // 32 KB: [256 vocabulary rows][128 B]
+constexpr int kMaxRing = 4;
+constexpr int kCandCap = 16;
 constexpr int kHeadThreads = 384;                // 4 service warps + 2 epilogue warpgroups
+bool g_head_no_cluster = false;                  // mobgt_debug_head_cluster(0): measurement switch (scripts/k5bench.py)
 
 struct HeadParams {
     const float *bias;       // [V] or null
@@ -123,6 +128,10 @@ __device__ __forceinline__ void cand_append(uint32_t addr, uint32_t cb, float v)
         ::"r"(addr), "r"(cb), "n"(Q), "r"(__float_as_uint(v))
         : "memory");
 }
+// Harvest the top-k candidates of a 32-column chunk, group of 4 columns by group.  The caller (all 32 lanes together) has made
+// room for 8 entries in every lane's buffer; a lane that finds more in one chunk (a list without a useful bound yet) drains on
+// the spot.  The column and the 64-bit entry are formed INSIDE the store's asm block, so nothing of the rare path is hoisted
+// into the common one.
 template <int LK, int G>
 __device__ __forceinline__ void harvest_groups(const float (&v)[32], const float (&m4)[8], unsigned long long (&list)[LK],
                                                float &thr, int &ncand, uint32_t cd, uint32_t cb, long long vocab_offset) {
@@ -146,7 +155,11 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity
     while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
 }
 
-template <int LK>
+// kCluster = 2: the CTAs of two adjacent row tiles (same vocabulary split, so the same sequence of W tiles) form a cluster; each
+// loads HALF of every W stage and multicasts it into both CTAs' rings, which halves the L2 -> SM traffic of the operand every
+// row tile of a split streams.  A ring slot may be refilled only when BOTH CTAs' MMAs have consumed it: bar_empty counts two
+// arrivals, delivered by a multicast tcgen05.commit.
+template <int LK, int kCluster>
 __global__ void __launch_bounds__(kHeadThreads, 1)
 k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmW, const HeadParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -164,9 +177,9 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
     uint8_t *sB = sA + (size_t)kblocks * kBlkBytes;
-    unsigned long long *cand = reinterpret_cast<unsigned long long *>(sB + (size_t)p.ring * kBlkBytes);   // [2][cap][128]
+    unsigned long long *cand = reinterpret_cast<unsigned long long *>(sB + (size_t)p.ring * kStageBytes);   // [2][cap][128]
 
-    const int ntiles = ceil_div(p.V, kHeadTile);
+    const int ntiles = ceil_div(p.V, kNT);
     const int gs = gridDim.y;
     const int tps = ceil_div(ntiles, gs);
     const int n_begin = sp * tps, n_end = min(ntiles, n_begin + tps);
@@ -176,7 +189,7 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
         mbar_init(&bar_a, 1);
         for (int s = 0; s < kMaxRing; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_empty[s], 1);
+            mbar_init(&bar_empty[s], kCluster);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&acc_full[a], 1);
@@ -186,11 +199,14 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
         tma_prefetch_desc(&tmZ);
         tma_prefetch_desc(&tmW);
     }
-    if (warp == 2) tmem_alloc<256>(&tmem_slot);
+    if (warp == 2) tmem_alloc<2 * kNT>(&tmem_slot);
     tc_fence_before();
     __syncthreads();
+    if (kCluster > 1) cluster_sync_all();      // the peer's barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0u;
+    constexpr uint16_t kMask = (uint16_t)((1u << kCluster) - 1u);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -204,8 +220,12 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
                     const int s = it % p.ring;
                     const uint32_t ph = (uint32_t)(it / p.ring) & 1u;
                     mbar_wait_relaxed(&bar_empty[s], ph ^ 1u, spin_ns);
-                    mbar_expect_tx(&bar_full[s], (uint32_t)kBlkBytes);
-                    tma_load_2d(sB + (size_t)s * kBlkBytes, &tmW, &bar_full[s], kb * kKB, n * kHeadTile);
+                    mbar_expect_tx(&bar_full[s], (uint32_t)kStageBytes);     // own half + the peer's half
+                    if (kCluster == 1)
+                        tma_load_2d(sB + (size_t)s * kStageBytes, &tmW, &bar_full[s], kb * kKB, n * kNT);
+                    else
+                        tma_load_2d_mc(sB + (size_t)s * kStageBytes + crank * (kStageBytes / kCluster), &tmW, &bar_full[s], kb * kKB,
+                                       n * kNT + (int)crank * (kNT / kCluster), kMask);
                 }
             }
         }
@@ -213,7 +233,7 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
         if (elect_one()) {
-            const uint32_t idesc = make_idesc_bf16(kHeadTile, kHeadTile, 0, 0);
+            const uint32_t idesc = make_idesc_bf16(kHeadTile, kNT, 0, 0);
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
             mbar_wait(&bar_a, 0);
             int it = 0;
@@ -230,9 +250,10 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
                     tc_fence_after();
                     const int ksteps = min(kKB, p.K - kb * kKB) / 16;
                     for (int j = 0; j < ksteps; ++j)
-                        umma_bf16(tmem + (uint32_t)(a * kHeadTile), make_smem_desc_sw128(a0 + kb * kBlkBytes + j * 32),
-                                  make_smem_desc_sw128(b0 + s * kBlkBytes + j * 32), idesc, (kb | j) != 0);
-                    umma_commit(&bar_empty[s]);
+                        umma_bf16(tmem + (uint32_t)(a * kNT), make_smem_desc_sw128(a0 + kb * kBlkBytes + j * 32),
+                                  make_smem_desc_sw128(b0 + s * kStageBytes + j * 32), idesc, (kb | j) != 0);
+                    if (kCluster == 1) umma_commit(&bar_empty[s]);
+                    else umma_commit_mc(&bar_empty[s], kMask);
                     if (stamp && kb == kblocks - 1) p.timeline[16 + 4 * t + 2] = clock64();
                 }
                 umma_commit(&acc_full[a]);
@@ -252,31 +273,35 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
         const float st = row_ok ? p.st[row] : 0.f;
         const float st_prev = prev_float(st);
         const uint32_t cd = smem_u32(cand + (size_t)e * kCandCap * kHeadTile + r);
-        const uint32_t sbias = smem_u32(cand + (size_t)2 * kCandCap * kHeadTile) + (uint32_t)e * 2 * kHeadTile * 4;   // [2][128] f32
+        const uint32_t sbias = smem_u32(cand + (size_t)2 * kCandCap * kHeadTile) + (uint32_t)e * 2 * kNT * 4;   // [2][256] f32
         unsigned long long list[LK];
 #pragma unroll
         for (int j = 0; j < LK; ++j) list[j] = 0ull;
         float thr = -INFINITY;
         int ncand = 0, cnt = 0;
         uint32_t last_pub = 0u;
-        // bias of column col_base + r of the tile (one element per thread, coalesced): -inf past the vocabulary, so the
-        // zero accumulators of the TMA-zero-filled tail rows neither count nor qualify
-        auto tile_bias = [&](int t) -> float {
-            const int col = (n_begin + t) * kHeadTile + r;
+        // bias of columns col_base + r and col_base + 128 + r of the tile (two elements per thread, coalesced): -inf past the
+        // vocabulary, so the zero accumulators of the TMA-zero-filled tail rows neither count nor qualify
+        auto tile_bias = [&](int t, int half) -> float {
+            const int col = (n_begin + t) * kNT + half * kHeadTile + r;
             return col < p.V ? (p.bias ? __ldg(p.bias + col) : 0.f) : -INFINITY;
         };
-        float bnext = e < T ? tile_bias(e) : 0.f;
+        float bnext0 = e < T ? tile_bias(e, 0) : 0.f, bnext1 = e < T ? tile_bias(e, 1) : 0.f;
 
         int it = 0;
         for (int t = e; t < T; t += 2, ++it) {
             const int n = n_begin + t;
-            const int col_base = n * kHeadTile;
-            // the best k-th value any list of this row has published so far: a lower bound of the row's final k-th value, so
-            // every list may use it as its threshold (>= : ties must survive, hence prev_float)
+            const int col_base = n * kNT;
+            // the best k-th value any list of this row has published so far: a lower bound
+            // of the row's final k-th value, so every list may use it as its threshold (>= : ties must survive, hence prev_float)
             const uint32_t gshare = (p.thr_share != nullptr && row_ok) ? __ldcg(p.thr_share + row) : 0u;
-            const uint32_t sb = sbias + (uint32_t)(it & 1) * kHeadTile * 4;
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb + (uint32_t)r * 4), "f"(bnext) : "memory");
-            if (t + 2 < T) bnext = tile_bias(t + 2);
+            const uint32_t sb = sbias + (uint32_t)(it & 1) * kNT * 4;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb + (uint32_t)r * 4), "f"(bnext0) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb + (uint32_t)(kHeadTile + r) * 4), "f"(bnext1) : "memory");
+            if (t + 2 < T) {
+                bnext0 = tile_bias(t + 2, 0);
+                bnext1 = tile_bias(t + 2, 1);
+            }
             named_bar_sync(1 + e, kHeadTile);
             mbar_wait(&acc_full[e], (uint32_t)(t >> 1) & 1u);
             tc_fence_after();
@@ -284,11 +309,11 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
             const bool estamp = p.timeline != nullptr && blockIdx.x == 1 && blockIdx.y == 1 && t < 14 && r == 0;
             if (estamp) p.timeline[80 + 4 * t] = clock64();
 #pragma unroll 1
-            for (int c0 = 0; c0 < kHeadTile; c0 += 32) {
+            for (int c0 = 0; c0 < kNT; c0 += 32) {
                 uint32_t acc[32];
                 float v[32];
                 const int cb = col_base + c0;
-                tmem_ld32(tmem + lane_off + (uint32_t)(e * kHeadTile + c0), acc);
+                tmem_ld32(tmem + lane_off + (uint32_t)(e * kNT + c0), acc);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {          // same address in every lane: broadcast reads
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -296,7 +321,7 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
                                  : "r"(sb + (uint32_t)(c0 + 4 * q) * 4));
                 }
                 tmem_ld_wait();
-                if (c0 == kHeadTile - 32) {   // accumulator fully read: hand it back to the MMA warp
+                if (c0 == kNT - 32) {   // accumulator fully read: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[e]);
@@ -336,7 +361,16 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
                 // harvest the top-k candidates of the chunk, group by group (rare after the first tiles).  The column and the
                 // 64-bit entry are formed INSIDE the store's asm block, so nothing of the rare path is hoisted into the
                 // common one; a buffer without room for 4 more entries is drained on the spot.
-                if (!(dbg & 1)) harvest_groups<LK, 0>(v, m4, list, thr, ncand, cd, (uint32_t)cb, p.vocab_offset);
+                if (!(dbg & 1)) {
+                    // one vote per 32-column chunk: in steady state no lane holds a candidate in 9 chunks out of 10
+                    const float mx = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
+                    if (__any_sync(0xffffffffu, mx > thr)) {
+                        // all 32 lanes: whoever is short of room makes EVERY lane drain now — the unrolled insertion chain then
+                        // runs once per warp, each lane on its own list, instead of once per lane at 32 different moments
+                        if (__any_sync(0xffffffffu, ncand > kCandCap - 8)) thr = fmaxf(thr, list_drain<LK>(list, cd, ncand, p.vocab_offset));
+                        harvest_groups<LK, 0>(v, m4, list, thr, ncand, cd, (uint32_t)cb, p.vocab_offset);
+                    }
+                }
                 __syncwarp();     // tcgen05.ld is warp-collective: reconverge before the next chunk
             }
             {   // all lanes together; fresh threshold for the next tile (never below a bound taken from thr_share)
@@ -367,7 +401,8 @@ k5_head_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc<256>(tmem);
+    if (kCluster > 1) cluster_sync_all();      // no CTA leaves while its peer may still multicast into it / arrive on its barriers
+    if (warp == 2) tmem_dealloc<2 * kNT>(tmem);
 }
 
 // mode 0: st[row] = z[row] . W[target[row]] + bias[target[row]] through the same tcgen05 arithmetic as mode 1
@@ -500,10 +535,10 @@ k5_topk_merge_kernel(const float *__restrict__ val, const int32_t *__restrict__ 
     }
 }
 
-static int32_t encode_rows_sw128(CUtensorMap *tm, const void *base, int rows, int K) {
+static int32_t encode_rows_sw128(CUtensorMap *tm, const void *base, int rows, int K, int box_rows = kHeadTile) {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)rows};
     uint64_t str[1] = {(uint64_t)K * 2};
-    uint32_t box[2] = {kKB, kHeadTile};
+    uint32_t box[2] = {kKB, (uint32_t)box_rows};
     return encode_tmap_bf16(tm, base, 2, dims, str, box, 1);
 }
 
@@ -519,8 +554,8 @@ extern "C" int32_t mobgt_head_topk(const void *z, const void *W, const float *bi
     MOBGT_REQUIRE(mode == 0 || (topk_val && topk_idx && cnt_gt && cnt_eq), MOBGT_ERR_NULL, "mobgt_head_topk: null output");
     MOBGT_REQUIRE(K % 16 == 0 && K >= 16 && K <= kHeadMaxK, MOBGT_ERR_BAD_SHAPE, "mobgt_head_topk: K=%d", K);
     MOBGT_REQUIRE(k >= 1 && k <= kHeadMaxTop, MOBGT_ERR_BAD_SHAPE, "mobgt_head_topk: k=%d", k);
-    MOBGT_REQUIRE(mode == 0 || (nsplit >= 2 && nsplit <= 64 && nsplit % 2 == 0), MOBGT_ERR_BAD_SHAPE,
-                  "mobgt_head_topk: nsplit=%d must be even, in [2,64] (two epilogue groups per vocabulary split)", nsplit);
+    MOBGT_REQUIRE(mode == 0 || (nsplit >= 2 && nsplit <= 160 && nsplit % 2 == 0), MOBGT_ERR_BAD_SHAPE,
+                  "mobgt_head_topk: nsplit=%d must be even, in [2,160] (two epilogue groups per vocabulary split)", nsplit);
     MOBGT_REQUIRE(((uintptr_t)z & 15) == 0 && ((uintptr_t)W & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0), MOBGT_ERR_BAD_SHAPE,
                   "mobgt_head_topk: z, W and bias must be 16-byte aligned");
     if (M <= 0 || V <= 0) return MOBGT_OK;
@@ -537,26 +572,55 @@ extern "C" int32_t mobgt_head_topk(const void *z, const void *W, const float *bi
         MOBGT_LAUNCH_OK("k5_target_logit_kernel");
         return MOBGT_OK;
     }
-    rc = encode_rows_sw128(&tmW, W, V, K);
+    // two adjacent row tiles share their W stream through a 2-CTA cluster (multicast halves) whenever the tile count is even
+    const int cluster = (ceil_div(M, kHeadTile) % 2 == 0 && !g_head_no_cluster) ? 2 : 1;
+    rc = encode_rows_sw128(&tmW, W, V, K, kNT / cluster);
     if (rc) return rc;
-    const size_t fixed = (size_t)kblocks * kBlkBytes + (size_t)2 * kCandCap * kHeadTile * 8 + (size_t)4 * kHeadTile * 4 + 1024;
-    int ring = (int)((227 * 1024 - 512 - (long long)fixed) / kBlkBytes);
+    const size_t fixed = (size_t)kblocks * kBlkBytes + (size_t)2 * kCandCap * kHeadTile * 8 + (size_t)4 * kNT * 4 + 1024;
+    int ring = (int)((227 * 1024 - 512 - (long long)fixed) / kStageBytes);
     ring = ring > kMaxRing ? kMaxRing : ring;
     MOBGT_REQUIRE(ring >= 2, MOBGT_ERR_UNSUPPORTED, "mobgt_head_topk: no shared-memory plan for K=%d k=%d", K, k);
-    const size_t smem = fixed + (size_t)ring * kBlkBytes;
-    HeadParams p{bias, target, st, topk_val, topk_idx, cnt_gt, cnt_eq, logits_dump, M, V, K, k, nsplit, mode, ring, g_timeline_dev, static_cast<uint32_t *>(thr_share), vocab_offset};
+    const size_t smem = fixed + (size_t)ring * kStageBytes;
+    HeadParams p{bias, target, st, topk_val, topk_idx, cnt_gt, cnt_eq, logits_dump, M, V, K, k, nsplit, mode, ring, g_timeline_dev,
+                 static_cast<uint32_t *>(thr_share), vocab_offset};
     dim3 grid((unsigned)ceil_div(M, kHeadTile), (unsigned)(nsplit / 2));
     // the list length is a compile-time constant (register-resident list): the smallest built size >= k
-    auto launch = [&](auto kern) -> int32_t {
+    auto launch = [&](auto kern, const HeadParams &hp, dim3 grid) -> int32_t {
         MOBGT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kHeadThreads, smem, s>>>(tmZ, tmW, p);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(kHeadThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cluster;       // two adjacent row tiles of the same vocabulary split
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MOBGT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmZ, tmW, hp));
         return MOBGT_OK;
     };
-    if (k <= 10) rc = launch(k5_head_kernel<10>);
-    else if (k <= 20) rc = launch(k5_head_kernel<20>);
-    else rc = launch(k5_head_kernel<32>);
+    auto run = [&](const HeadParams &hp, dim3 grid) -> int32_t {
+        if (cluster == 2) {
+            if (k <= 10) return launch(k5_head_kernel<10, 2>, hp, grid);
+            if (k <= 20) return launch(k5_head_kernel<20, 2>, hp, grid);
+            return launch(k5_head_kernel<32, 2>, hp, grid);
+        }
+        if (k <= 10) return launch(k5_head_kernel<10, 1>, hp, grid);
+        if (k <= 20) return launch(k5_head_kernel<20, 1>, hp, grid);
+        return launch(k5_head_kernel<32, 1>, hp, grid);
+    };
+    rc = run(p, grid);
     if (rc) return rc;
     MOBGT_LAUNCH_OK("k5_head_kernel");
+    return MOBGT_OK;
+}
+
+// Debug / measurement switches of mobgt_head_topk; 1 = defaults.
+extern "C" int32_t mobgt_debug_head_cluster(int32_t on) {
+    mobgt::g_head_no_cluster = (on & 1) == 0;      // bit 0: pair row tiles into clusters (1 = default)
     return MOBGT_OK;
 }
 
@@ -565,7 +629,7 @@ extern "C" int32_t mobgt_topk_merge(const float *val, const int32_t *idx, const 
                                     void *stream) {
     MOBGT_REQUIRE(val && idx && out_val && out_idx, MOBGT_ERR_NULL, "mobgt_topk_merge: null pointer");
     MOBGT_REQUIRE(!rank || (cnt_gt && cnt_eq), MOBGT_ERR_NULL, "mobgt_topk_merge: rank needs the counts");
-    MOBGT_REQUIRE(S >= 1 && S <= 64 && k >= 1 && k <= kHeadMaxTop, MOBGT_ERR_BAD_SHAPE, "mobgt_topk_merge: S=%d k=%d", S, k);
+    MOBGT_REQUIRE(S >= 1 && S <= 160 && k >= 1 && k <= kHeadMaxTop, MOBGT_ERR_BAD_SHAPE, "mobgt_topk_merge: S=%d k=%d", S, k);
     if (M <= 0) return MOBGT_OK;
     const size_t smem = (size_t)kMergeWarps * S * k * sizeof(unsigned long long);
     MOBGT_CUDA_OK(cudaFuncSetAttribute(k5_topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

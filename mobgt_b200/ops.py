@@ -955,11 +955,11 @@ def head_split(M, V):
     B200, c5 shard: 9 splits x 32 row tiles in two waves (573 us) beat 4 splits in one 86 %-full wave (638 us): the warm-up
     of a fresh top-k list costs ~8 tiles once the lists of a row share their pruning bound.)"""
     mt = (M + 127) // 128
-    nt = (V + 127) // 128
+    nt = (V + 255) // 256          # vocabulary tiles of 256 rows (csrc/k5_head.cu kNT)
     best, best_cost = 1, None
-    for gs in range(1, min(32, nt) + 1):
+    for gs in range(1, min(80, nt) + 1):
         waves = (mt * gs + 147) // 148
-        cost = waves * ((nt + gs - 1) // gs + 8)
+        cost = waves * ((nt + gs - 1) // gs + 4)
         if best_cost is None or cost < best_cost:
             best, best_cost = gs, cost
     return 2 * best

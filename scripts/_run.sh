@@ -1,6 +1,3 @@
-O=gpurun_out/r3i; mkdir -p $O
-timeout 900 python -m pytest tests -m gpu -x -q -k "attention or attn or k3 or canonical or bucketed or golden or cuda_graph or entry_cli" > $O/pytest_sub.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_sub.log
-timeout 300 python scripts/step_kernels.py c2-natural > $O/step_kernels_nat.txt 2>&1; echo rc=$?
-for w in c2-natural c4-gowalla256; do
-timeout 600 python bench.py --workload $w --steps 20 --warmup 5 --no-cpu-baseline --no-kernel-report > $O/bench_$w.json 2> $O/bench_$w.err; echo "bench $w rc=$?"; cut -c1-200 $O/bench_$w.json
-done
+O=gpurun_out/r3m; mkdir -p $O
+timeout 300 python -m pytest tests -m gpu -x -q -k "k5 or head or eval" > $O/pytest_k5.log 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest_k5.log
+timeout 300 python scripts/k5bench.py > $O/k5bench.log 2>&1; echo "k5bench rc=$?"; grep -v Warn $O/k5bench.log | grep -v "no cluster" | tail -8

@@ -7,7 +7,7 @@ import bench
 from mobgt_b200 import ops
 
 pk = bench.peaks()
-_share = torch.zeros(8192, dtype=torch.int32, device='cuda')
+_share = torch.zeros(32 * 8192, dtype=torch.int32, device='cuda')
 
 
 def share_zero():
@@ -17,7 +17,10 @@ def share_zero():
 
 dev = torch.device("cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for name, M, V, k in (("c2", 256, 60001, 10), ("c5_shard", 4096, 125000, 10), ("c5_shard_k20", 4096, 125000, 20), ("mid", 1024, 125000, 10)):
+from mobgt_b200 import _C as _C0
+for cl, (name, M, V, k) in [(c, t) for c in (1, 0) for t in (("c2", 256, 60001, 10), ("c5_shard", 4096, 125000, 10), ("c5_shard_k20", 4096, 125000, 20), ("mid", 1024, 125000, 10))]:
+    _C0.call("mobgt_debug_head_cluster", cl)          # 1: adjacent row tiles paired into 2-CTA clusters (W stages multicast), 0: off
+    name = f"{name}{'' if cl else ' (no cluster)'}"
     g = torch.Generator(device=dev).manual_seed(5)
     z = torch.randn(M, 320, device=dev, generator=g).to(torch.bfloat16)
     W = (torch.randn(V, 320, device=dev, generator=g) * 0.02).to(torch.bfloat16)
@@ -42,6 +45,7 @@ for name, M, V, k in (("c2", 256, 60001, 10), ("c5_shard", 4096, 125000, 10), ("
     print(f"{name:14s} M={M} V={V} k={k} nsplit={ops.head_split(M, V)}: mode1+merge {t1*1e3:8.1f} us = {fl/t1/1e9:7.1f} TF/s "
           f"({100*fl/t1/1e9/pk['tc']:.1f}% of bf16 peak) ; mode0 {t0*1e3:7.1f} us ; head kernel alone {th*1e3:8.1f} us = {fl/th/1e9:7.1f} TF/s ({100*fl/th/1e9/pk['tc']:.1f}%) ; merge alone {tm*1e3:6.1f} us")
 
+_C0.call("mobgt_debug_head_cluster", 1)
 if "--dbg" in sys.argv:
     # timing experiments on the c5 shard shape: which part of the head kernel bounds it (results of dbg runs are NOT valid top-k)
     M, V, k = 4096, 125000, 10
@@ -76,7 +80,7 @@ if "--timeline" in sys.argv:
     tv = torch.empty(M, ns, k, dtype=torch.float32, device=dev); ti = torch.empty(M, ns, k, dtype=torch.int32, device=dev)
     cg = torch.empty(M, ns, dtype=torch.int32, device=dev); ce = torch.empty(M, ns, dtype=torch.int32, device=dev)
     tl = torch.zeros(256, dtype=torch.int64, device=dev)
-    for name, mode in (("full", 1), ("ld + release only", 1 | (2 << 8))):
+    for name, mode in (("full", 1), ("no harvest", 1 | (1 << 8)), ("ld + release only", 1 | (2 << 8))):
         tl.zero_()
         _C.call("mobgt_debug_set_timeline", tl.data_ptr())
         _C.call("mobgt_head_topk", _C.ptr(z), _C.ptr(W), _C.ptr(b), _C.ptr(tgt), M, V, 320, 0, k, ns, mode,
