@@ -25,6 +25,7 @@
 //   * the walk writes only the first `hops` hop slots (collator.py:323 slices the rest away),
 //     staged per warp in shared memory and stored as coalesced 32-bit words.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -55,27 +56,35 @@ __device__ __forceinline__ uint32_t pick16(const uint4 &v, int e) {
     return (e & 1) ? (x >> 16) : (x & 0xFFFFu);
 }
 
-// one packed relaxation of 2 cells: returns the "strictly improved" half-word mask
+// one packed relaxation of 2 cells: m = min(m, rk + mik2) per half-word in ONE instruction (VIADDMNMX.U16x2; the halves are
+// <= 1020, no carry across the half-word boundary); returns old ^ new — a half-word is non-zero iff that cell STRICTLY improved
+// (algos.pyx:41 `>`).  The full 0xFFFF / 0 select masks are only built on the rare path (half_masks): the packed compare
+// __vcmpltu2 is emulated with six instructions per word on sm_100 and used to be 60 % of the inner loop.
 __device__ __forceinline__ uint32_t relax2(uint32_t &m, uint32_t rk, uint32_t mik2) {
-    const uint32_t cost = rk + mik2;  // halves are <= 1020: no carry across the half-word boundary
-    const uint32_t lt = __vcmpltu2(cost, m);
-    m = __vminu2(m, cost);
-    return lt;
+    const uint32_t nm = __viaddmin_u16x2(rk, mik2, m);
+    const uint32_t diff = nm ^ m;
+    m = nm;
+    return diff;
+}
+__device__ __forceinline__ uint32_t half_masks(uint32_t diff) {
+    return ((diff & 0xFFFFu) ? 0xFFFFu : 0u) | ((diff >> 16) ? 0xFFFF0000u : 0u);
 }
 
 __host__ __device__ inline int k1_W(int n, int C) { return round_up(ceil_div(n, C), 8); }
 
-__host__ inline size_t k1_smem_bytes(int n, int C, bool with_path, int nthreads, int hops) {
+__host__ inline size_t k1_smem_bytes(int n, int C, bool with_path, int nthreads, int hops, bool with_feat) {
     const int W = k1_W(n, C);
     const int n8 = round_up(n, 8);
     size_t b = (size_t)n * W * 2 * (with_path ? 3 : 2);
     b += (size_t)4 * n8 * 2;                       // colM[2][n8], colX[2][n8]
     b += (size_t)(nthreads / 32) * 32 * hops;      // per-warp walk staging
+    b = (b + 15) / 16 * 16;
+    if (with_feat) b += (size_t)round_up(n * n, 16);   // the graph's edge-feature bytes for the walk
     return b + 16;
 }
 
 template <bool WITH_PATH>
-__global__ void __launch_bounds__(1024) k1_apsp_kernel(const K1Params p, const int C) {
+__global__ void __launch_bounds__(1024) k1_apsp_kernel(const K1Params p, const int C, const int feat_in_smem) {
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (C > 1) ? (int)cluster.block_rank() : 0;
     const int gl = blockIdx.x / C;
@@ -96,9 +105,26 @@ __global__ void __launch_bounds__(1024) k1_apsp_kernel(const K1Params p, const i
     uint16_t *colM = WITH_PATH ? (Psh + (size_t)n * W) : Psh;  // [2][n8]
     uint16_t *colX = colM + 2 * n8;                             // [2][n8]
     uint8_t *stage = reinterpret_cast<uint8_t *>(colX + 2 * n8);
+    // the walk reads one edge-feature byte per hop at a data-dependent address: a chain of up to `dk` dependent loads per pair.
+    // With the n x n bytes of the graph staged in shared memory each link of the chain is an LDS (~30 cycles) instead of a
+    // global load (several hundred); the launch provisions the space whenever it fits next to the Floyd-Warshall state.
+    uint8_t *featS = nullptr;
+    if (feat_in_smem) {
+        const size_t so = (((size_t)(stage - smem_raw) + (size_t)(blockDim.x / 32) * 32 * p.hops) + 15) / 16 * 16;
+        featS = smem_raw + so;
+    }
 
     const uint8_t *feat = p.feat + off;
     const int ntask = n * cpr;
+    if (featS != nullptr) {
+        const int nb = n * n;
+        if (((uintptr_t)feat & 15) == 0) {
+            for (int t = tid; t < (nb >> 4); t += NT) reinterpret_cast<uint4 *>(featS)[t] = __ldg(reinterpret_cast<const uint4 *>(feat) + t);
+            for (int t = (nb & ~15) + tid; t < nb; t += NT) featS[t] = __ldg(feat + t);
+        } else {
+            for (int t = tid; t < nb; t += NT) featS[t] = __ldg(feat + t);
+        }
+    }
 
     // ---- init (algos.pyx:27-32): diag 0, edge 1, else 510; X[i][j] = j; P = 0 ----------------
     for (int t = tid; t < ntask; t += NT) {
@@ -160,13 +186,14 @@ __global__ void __launch_bounds__(1024) k1_apsp_kernel(const K1Params p, const i
                 if (mik < kInf) {
                     const uint4 r4 = *reinterpret_cast<const uint4 *>(rowk + q * 8);
                     const uint32_t mik2 = mik * 0x10001u;
-                    const uint32_t l0 = relax2(m4.x, r4.x, mik2);
-                    const uint32_t l1 = relax2(m4.y, r4.y, mik2);
-                    const uint32_t l2 = relax2(m4.z, r4.z, mik2);
-                    const uint32_t l3 = relax2(m4.w, r4.w, mik2);
-                    if (l0 | l1 | l2 | l3) {
+                    const uint32_t d0 = relax2(m4.x, r4.x, mik2);
+                    const uint32_t d1 = relax2(m4.y, r4.y, mik2);
+                    const uint32_t d2 = relax2(m4.z, r4.z, mik2);
+                    const uint32_t d3 = relax2(m4.w, r4.w, mik2);
+                    if (d0 | d1 | d2 | d3) {
                         *reinterpret_cast<uint4 *>(mp) = m4;
                         if (k != 0) {  // k == 0: path stays 0 == "direct" (algos.pyx:59-60) -> X untouched
+                            const uint32_t l0 = half_masks(d0), l1 = half_masks(d1), l2 = half_masks(d2), l3 = half_masks(d3);
                             x4 = *reinterpret_cast<const uint4 *>(xp);
                             const uint32_t xik2 = (uint32_t)cX[i] * 0x10001u;
                             x4.x = (x4.x & ~l0) | (xik2 & l0);
@@ -263,7 +290,8 @@ __global__ void __launch_bounds__(1024) k1_apsp_kernel(const K1Params p, const i
                 int cur = i;
                 for (int h = 0; h < p.dk; ++h) {
                     const int nx = Xsh[(size_t)cur * W + jl] & (kNoWalk - 1);
-                    st[lane * hops + h] = (uint8_t)(__ldg(feat + (size_t)cur * n + nx) + p.shift);
+                    const uint8_t f = featS ? featS[cur * n + nx] : __ldg(feat + (size_t)cur * n + nx);
+                    st[lane * hops + h] = (uint8_t)(f + p.shift);
                     cur = nx;
                     if (cur == j) break;
                 }
@@ -335,18 +363,30 @@ __global__ void k1_degree_kernel(const uint8_t *__restrict__ feat, const int32_t
 // (the preprocessing bench: thousands of graphs per launch); a launch of few graphs (one training batch of 256) is latency-
 // bound per k-step — one barrier per k — so it spreads every graph over up to 1024 threads (>= 2 tasks per thread) until the
 // launch offers ~48 warps per SM.
-static int pick_cluster(int n, int G, bool with_path, int hops, int *nthreads_out, size_t *smem_out) {
+static int pick_cluster(int n, int G, bool with_path, int hops, bool want_feat, int *nthreads_out, size_t *smem_out, int *feat_out) {
     for (int C = 1; C <= 8; C *= 2) {
         const int W = k1_W(n, C);
         const int ntask = n * (W / 8);
-        int nt = ntask <= 32 ? 32 : ntask <= 128 ? 64 : ntask <= 512 ? 128 : ntask <= 2048 ? 256 : 512;
-        while (nt < 1024 && 2 * nt <= ntask / 2 + 31 && (long long)G * C * (nt / 32) < (long long)kNumSMs * 48 &&
-               k1_smem_bytes(n, C, with_path, 2 * nt, hops) <= 227 * 1024)
+        // measured (scripts/kbench.py --k1, MOBGT_K1_NT sweeps; n = 128: 2 048 tasks per k-step): 512 threads (4 tasks per thread,
+        // two CTAs per SM) beat 256 (8 tasks: 441 / 1 603 us for 256 / 1 024 graphs against 356 / 1 177 us) and 1 024 (one CTA
+        // per SM, 410 us); n = 64 is best at 128-256 threads
+        int nt = ntask <= 32 ? 32 : ntask <= 128 ? 64 : ntask <= 512 ? 128 : ntask <= 1024 ? 256 : 512;
+        // a launch of very few graphs (at most one CTA per SM anyway) is pure k-step latency: spread each graph further
+        while (nt < 1024 && 2 * nt <= ntask / 2 + 31 && (long long)G * C <= kNumSMs &&
+               k1_smem_bytes(n, C, with_path, 2 * nt, hops, false) <= 227 * 1024)
             nt *= 2;
-        const size_t sm = k1_smem_bytes(n, C, with_path, nt, hops);
+        if (const char *ev = getenv("MOBGT_K1_NT")) {      // measurement override (scripts/kbench.py)
+            const int f = atoi(ev);
+            if (f >= 32 && f <= 1024 && (f & (f - 1)) == 0 && f <= ntask * 1 + 31) nt = f;
+        }
+        const size_t sm = k1_smem_bytes(n, C, with_path, nt, hops, false);
         if (sm <= 227 * 1024) {
+            // the feature bytes ride along when they fit and do not halve the CTAs per SM of a small plan
+            const size_t smf = k1_smem_bytes(n, C, with_path, nt, hops, true);
+            const bool feat = want_feat && smf <= 227 * 1024 && (sm > 100 * 1024 || smf <= 113 * 1024);
             *nthreads_out = nt;
-            *smem_out = sm;
+            *smem_out = feat ? smf : sm;
+            *feat_out = feat ? 1 : 0;
             return C;
         }
     }
@@ -376,9 +416,9 @@ extern "C" int32_t mobgt_apsp_edge_input(const uint8_t *feat, const int32_t *n, 
     if (G_launch == 0) return MOBGT_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool with_path = path != nullptr || n_max_host > MOBGT_UNREACHABLE;   // see skip510 in the kernel
-    int nt = 0;
+    int nt = 0, feat_in_smem = 0;
     size_t smem = 0;
-    const int C = pick_cluster(n_max_host, G_launch, with_path, hops, &nt, &smem);
+    const int C = pick_cluster(n_max_host, G_launch, with_path, hops, edge_in != nullptr, &nt, &smem, &feat_in_smem);
     MOBGT_REQUIRE(C > 0, MOBGT_ERR_UNSUPPORTED, "mobgt_apsp_edge_input: no shared-memory plan for n=%d", n_max_host);
 
     K1Params p{feat, n, sq_off, gids, hops, dk, shift, dist, path, edge_in, maxdist};
@@ -396,7 +436,7 @@ extern "C" int32_t mobgt_apsp_edge_input(const uint8_t *feat, const int32_t *n, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MOBGT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p, C));
+    MOBGT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p, C, feat_in_smem));
     count_launch();
     return MOBGT_OK;
 }

@@ -1,3 +1,4 @@
-O=gpurun_out/r3m; mkdir -p $O
-timeout 300 python -m pytest tests -m gpu -x -q -k "k5 or head or eval" > $O/pytest_k5.log 2>&1; echo "pytest rc=$?"; tail -4 $O/pytest_k5.log
-timeout 300 python scripts/k5bench.py > $O/k5bench.log 2>&1; echo "k5bench rc=$?"; grep -v Warn $O/k5bench.log | grep -v "no cluster" | tail -8
+O=gpurun_out/r3q; mkdir -p $O
+for nt in 128 256 512; do
+MOBGT_K1_NT=$nt timeout 600 python scripts/kbench.py c2-dense128 --k1 > $O/kbench_$nt.log 2>&1; echo "nt=$nt rc=$?"; grep "^k1 n= 128\|^k1 n=  64\|^k1 n= 256" $O/kbench_$nt.log
+done
