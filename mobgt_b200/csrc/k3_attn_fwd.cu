@@ -44,6 +44,7 @@ struct AttnFwdParams {
     int T, Tp;
     int small_t;                      // graphs of at most this many tokens belong to the SIMT kernel (k3_attn_small.cu); 0: none
     const int32_t *order;             // [B] graph ids in launch order (descending size) or NULL
+    int n_items;                      // B * H work items; CTA b works on items b, b + gridDim.x, ... (persistent CTAs)
 };
 
 __device__ __forceinline__ void fwd_unpack24(const uint4 &a, const uint4 &b, const uint4 &c, float (&f)[24]) {
@@ -91,33 +92,23 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     MOBGT_STAMP(p.timeline, 0);
     const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7, t128 = tid & 127;
     const bool warp0 = warp_index_uniform() == 0;   // the issuing warp (one elected lane issues TMA / MMA)
-    const int gi = blockIdx.x / p.H, h = blockIdx.x - gi * p.H;
-    const int g = p.order ? p.order[gi] : gi;       // largest graphs first: the CTAs that return at once are dispatched behind them
-    const int t0 = p.tok_off[g];
-    const int Tg = p.tok_off[g + 1] - t0;
-    if (Tg <= p.small_t) return;                           // the whole CTA: nothing has been set up yet
-    const bool fold = Tg > kTile && (Tg % kTile) == 1;     // single-token tail handled by SIMT (see above)
-    const int NB = fold ? Tg / kTile : ceil_div(Tg, kTile);
-    const int sp = Tg - 1;                                 // the tail token (fold only)
-
-    // fold: the bias row / column of the tail token and its q, k, v — global loads issued at the very top, consumed after the
-    // prologue (their latency hides behind the barrier / TMEM / TMA set-up)
-    float b_row[3] = {0.f, 0.f, 0.f}, b_col[2] = {0.f, 0.f};
-    if (fold) {
-        const __nv_bfloat16 *bias_pl0 = p.bias + (size_t)(g * p.H + h) * p.T * p.Tp;
-#pragma unroll
-        for (int u = 0; u < 3; ++u)
-            if (tid + u * 256 < Tg) b_row[u] = __bfloat162float(bias_pl0[(size_t)sp * p.Tp + tid + u * 256]);
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-            if (tid + u * 256 < sp) b_col[u] = __bfloat162float(bias_pl0[(size_t)(tid + u * 256) * p.Tp + sp]);
-    }
-    float sp_val = 0.f;
-    if (fold && tid < 3 * kAttD) {   // q, k, v of the tail token as fp32 (load issued here, stored before the first barrier)
-        const int which = tid / kAttD, e = tid - which * kAttD;
-        const __nv_bfloat16 *src = which == 0 ? p.q : which == 1 ? p.k : p.v;
-        sp_val = __bfloat162float(src[(size_t)(t0 + sp) * p.qkv_stride + h * kAttD + e]);
-    }
+    // ---- persistent CTA: work item = (graph, head) in launch order; items of small graphs (SIMT kernel) are skipped.
+    // next_item: the first item >= `from` (stepping by the grid) that this kernel owns, with its header.
+    struct Item { int idx, g, h, t0, Tg; };
+    auto next_item = [&](int from) -> Item {
+        Item it{from, 0, 0, 0, 0};
+        for (; it.idx < p.n_items; it.idx += (int)gridDim.x) {
+            const int gi = it.idx / p.H;
+            it.h = it.idx - gi * p.H;
+            it.g = p.order ? p.order[gi] : gi;      // largest graphs first
+            it.t0 = p.tok_off[it.g];
+            it.Tg = p.tok_off[it.g + 1] - it.t0;
+            if (it.Tg > p.small_t) break;
+        }
+        return it;
+    };
+    Item cur = next_item((int)blockIdx.x);
+    if (cur.idx >= p.n_items) return;                      // the whole CTA: nothing has been set up yet
     uint8_t *sBias = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);   // 32 KB, 1024-aligned (swizzle atom)
     uint8_t *sP = sBias + kBiasTileBytes;                    // 32 KB
     uint8_t *sQ = sP + kPBytes;                              // 8 KB
@@ -135,27 +126,15 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_prefetch_desc(&tmK);
         tma_prefetch_desc(&tmV);
         tma_prefetch_desc(&tmBias);
-        // first loads right away (this thread initialised the barriers)
-        mbar_expect_tx(&bar_kv, (uint32_t)(2 * NB * kBoxTxBytes));
-        for (int b = 0; b < NB; ++b) {
-            tma_load_3d(sK + (size_t)b * kBoxBytes, &tmK, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
-            tma_load_3d(sV + (size_t)b * kBoxBytes, &tmV, &bar_kv, 0, t0 + b * kTile, h * kAttChunks);
-        }
-        mbar_expect_tx(&bar_q, kBoxTxBytes);
-        tma_load_3d(sQ, &tmQ, &bar_q, 0, t0, h * kAttChunks);
-        mbar_expect_tx(&bar_bias, kBiasTileBytes);
-        tma_load_3d(sBias, &tmBias, &bar_bias, 0, 0, g * p.H + h);
-        tma_load_3d(sBias + kTile * 128, &tmBias, &bar_bias, 64, 0, g * p.H + h);
     }
     // zero the K-padding chunk (d = 24..31) of Q and of every K / V box: 128 rows x 16 B each
     {
         const uint4 z = make_uint4(0, 0, 0, 0);
         if (wg == 0) *reinterpret_cast<uint4 *>(sQ + 3 * kTile * 16 + t128 * 16) = z;
         uint8_t *kv = wg == 0 ? sK : sV;
-        for (int b = 0; b < NB; ++b) *reinterpret_cast<uint4 *>(kv + (size_t)b * kBoxBytes + 3 * kTile * 16 + t128 * 16) = z;
+        for (int b = 0; b < p.max_boxes; ++b) *reinterpret_cast<uint4 *>(kv + (size_t)b * kBoxBytes + 3 * kTile * 16 + t128 * 16) = z;
     }
     if (warp == 0) tmem_alloc<256>(&tmem_slot);
-    if (fold && tid < 3 * kAttD) sSp[tid / kAttD][tid % kAttD] = sp_val;
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -164,7 +143,57 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t tmem = tmem_slot;
     const uint32_t tS = tmem, tO = tmem + 128;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const float sl2 = p.scale * 1.4426950408889634f;  // scale * log2(e)
+    constexpr float kL2e = 1.4426950408889634f;
+    uint32_t seed_lo = 0, seed_hi = 0;
+    if (kDrop) attn_drop_fold_seed(p.drop, seed_lo, seed_hi);
+    const uint32_t th_hi = p.drop.th16 << 16;
+
+    // the first loads of an item (thread 0 only): all K / V boxes, query tile 0, bias tile (0, 0).  For the CTA's first item
+    // they are issued here; for every later item at the end of its predecessor (the operands' shared memory is free once the
+    // last P.V MMA has completed), so they fly under the predecessor's epilogue and the barrier / TMEM set-up is paid once.
+    auto load_item = [&](const Item &it) {
+        const bool ifold = it.Tg > kTile && (it.Tg % kTile) == 1;
+        const int inb = ifold ? it.Tg / kTile : ceil_div(it.Tg, kTile);
+        mbar_expect_tx(&bar_kv, (uint32_t)(2 * inb * kBoxTxBytes));
+        for (int b = 0; b < inb; ++b) {
+            tma_load_3d(sK + (size_t)b * kBoxBytes, &tmK, &bar_kv, 0, it.t0 + b * kTile, it.h * kAttChunks);
+            tma_load_3d(sV + (size_t)b * kBoxBytes, &tmV, &bar_kv, 0, it.t0 + b * kTile, it.h * kAttChunks);
+        }
+        mbar_expect_tx(&bar_q, kBoxTxBytes);
+        tma_load_3d(sQ, &tmQ, &bar_q, 0, it.t0, it.h * kAttChunks);
+        mbar_expect_tx(&bar_bias, kBiasTileBytes);
+        tma_load_3d(sBias, &tmBias, &bar_bias, 0, 0, it.g * p.H + it.h);
+        tma_load_3d(sBias + kTile * 128, &tmBias, &bar_bias, 64, 0, it.g * p.H + it.h);
+    };
+    if (tid == 0) load_item(cur);
+    uint32_t ph_bias = 0, ph_s = 0, ph_o = 0, ph_kv = 0, nq = 0;   // barrier phases run on across the items (nq: Q tiles loaded so far)
+
+  while (cur.idx < p.n_items) {
+    const int g = cur.g, h = cur.h, t0 = cur.t0, Tg = cur.Tg;
+    const bool fold = Tg > kTile && (Tg % kTile) == 1;     // single-token tail handled by SIMT (see above)
+    const int NB = fold ? Tg / kTile : ceil_div(Tg, kTile);
+    const int sp = Tg - 1;                                 // the tail token (fold only)
     const int plane = g * p.H + h;
+
+    // fold: the bias row / column of the tail token and its q, k, v — global loads issued at the very top of the item
+    float b_row[3] = {0.f, 0.f, 0.f}, b_col[2] = {0.f, 0.f};
+    if (fold) {
+        const __nv_bfloat16 *bias_pl0 = p.bias + (size_t)plane * p.T * p.Tp;
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+            if (tid + u * 256 < Tg) b_row[u] = __bfloat162float(bias_pl0[(size_t)sp * p.Tp + tid + u * 256]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (tid + u * 256 < sp) b_col[u] = __bfloat162float(bias_pl0[(size_t)(tid + u * 256) * p.Tp + sp]);
+    }
+    if (fold && tid < 3 * kAttD) {   // q, k, v of the tail token as fp32
+        const int which = tid / kAttD, e = tid - which * kAttD;
+        const __nv_bfloat16 *src = which == 0 ? p.q : which == 1 ? p.k : p.v;
+        sSp[which][e] = __bfloat162float(src[(size_t)(t0 + sp) * p.qkv_stride + h * kAttD + e]);
+    }
+    const Item nxt = next_item(cur.idx + (int)gridDim.x);   // its header is needed by thread 0 at the end of this item
+    __syncthreads();                                        // sSp of this item is visible
 
     auto load_bias = [&](int i, int j) {   // thread 0 only
         mbar_expect_tx(&bar_bias, kBiasTileBytes);
@@ -175,10 +204,9 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_expect_tx(&bar_q, kBoxTxBytes);
         tma_load_3d(sQ, &tmQ, &bar_q, 0, t0 + i * kTile, h * kAttChunks);
     };
-    uint32_t ph_bias = 0, ph_s = 0, ph_o = 0;
     // S = Q_i K_j^T into TMEM (thread 0 only); new_q: first block of a query tile -> wait for its Q box
     auto issue_s = [&](int j, int new_q_tile) {   // new_q_tile >= 0: first block of that query tile -> wait for its Q box
-        if (new_q_tile >= 0) mbar_wait(&bar_q, new_q_tile & 1);
+        if (new_q_tile >= 0) mbar_wait(&bar_q, (nq + (uint32_t)new_q_tile) & 1u);
         const int nbj = round_up(min(kTile, Tg - j * kTile), 16);
         const uint32_t idesc = make_idesc_bf16(kTile, nbj, 0, 0);
         const uint32_t aq = smem_u32(sQ), bk = smem_u32(sK + (size_t)j * kBoxBytes);
@@ -189,23 +217,18 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         umma_commit(&bar_s);
     };
     if (warp0 && elect_one()) {
-        mbar_wait(&bar_kv, 0);
+        mbar_wait(&bar_kv, ph_kv);
         tc_fence_after();
         MOBGT_STAMP(p.timeline, 2);
         issue_s(0, 0);
         MOBGT_STAMP(p.timeline, 3);
     }
     __syncwarp();
-    const float sl2 = p.scale * 1.4426950408889634f;  // scale * log2(e)
-    constexpr float kL2e = 1.4426950408889634f;
-    uint32_t seed_lo = 0, seed_hi = 0;
-    if (kDrop) attn_drop_fold_seed(p.drop, seed_lo, seed_hi);
-    const uint32_t th_hi = p.drop.th16 << 16;
 
     if (fold) {   // ---- the single-token tail, SIMT (overlaps the first S MMA)
         const __nv_bfloat16 *bias_pl = p.bias + (size_t)plane * p.T * p.Tp;
-        mbar_wait(&bar_kv, 0);                      // K / V boxes and the first Q tile have landed
-        mbar_wait(&bar_q, 0);                       // (every thread observes the phases; tile 0 stays put until the loop)
+        mbar_wait(&bar_kv, ph_kv);                  // K / V boxes and the first Q tile have landed
+        mbar_wait(&bar_q, nq & 1u);                 // (tile 0 stays put until the loop)
         // (1) every full-tile row r against key sp: the score joins the row's online softmax in the tile epilogue
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -434,6 +457,9 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(&bar_o, ph_o);
         ph_o ^= 1;
         tc_fence_after();
+        // last query tile: every MMA of this item has completed and the bias tile was consumed in pass 1, so K / V / Q / bias
+        // shared memory is free: the next item's first loads start now and fly under this epilogue
+        if (i + 1 == NB && tid == 0 && nxt.idx < p.n_items) load_item(nxt);
         __syncthreads();
         if (warp_live) {
             uint32_t ov[16];
@@ -474,6 +500,10 @@ k3_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_before();
         __syncthreads();   // every thread is done with TMEM S/O before the next tile's MMAs
     }
+    ph_kv ^= 1u;
+    nq += (uint32_t)NB;
+    cur = nxt;
+  }   // items
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<256>(tmem);
@@ -553,10 +583,11 @@ extern "C" int32_t mobgt_attn_fwd(const void *q, const void *k, const void *v, i
                     make_attn_drop(drop_p, seed, seed_dev),
                     static_cast<const __nv_bfloat16 *>(q), static_cast<const __nv_bfloat16 *>(k),
                     static_cast<const __nv_bfloat16 *>(v), qkv_row_stride, static_cast<const __nv_bfloat16 *>(bias), T, Tp,
-                    any_small ? kSmallT : 0, graph_order};
+                    any_small ? kSmallT : 0, graph_order, B * H};
     auto kern = p.drop.th16 ? k3_attn_fwd_kernel<true> : k3_attn_fwd_kernel<false>;
     MOBGT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<B * H, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmB, p);
+    const int grid = B * H < 2 * kNumSMs ? B * H : 2 * kNumSMs;     // persistent: two CTAs per SM, each loops over its items
+    kern<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, tmB, p);
     MOBGT_LAUNCH_OK("k3_attn_fwd_kernel");
     return MOBGT_OK;
     };
