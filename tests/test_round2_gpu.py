@@ -236,6 +236,69 @@ def test_attention_bwd_single_box_variant(lib_built, sizes):
     assert torch.equal(dq2, dqkv)
 
 
+# ------------------------------------------------------------------------------------------------------- K3: persistent CTAs, size classes
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_attention_many_items_all_size_classes(lib_built, p_drop):
+    """More (graph, head) work items than the forward kernel has persistent CTAs (2 x 148), with every size class in one
+    batch: graphs of <= 16 tokens (SIMT kernels, csrc/k3_attn_small.cu), single-box graphs, the 128 m + 1 single-token tails
+    (T = 129, 257), two- and three-box graphs.  Forward, lse and the backward (general kernel, fp32 dS, mode 0 then mode 1
+    accumulating on top) against torch autograd with the same dropout mask: the barrier phases of a persistent CTA run on across
+    items of different shapes, and the tensor-core and SIMT kernels split the batch on the device."""
+    from mobgt_b200 import collator, ops, synth
+    from test_k2_k3_k4 import tables, torch_attention_diff
+    w = synth.make_world("c1", seed=1)
+    sizes = [128, 5, 100, 256, 1, 15, 130, 16, 3, 128, 64, 300, 2, 33, 17, 127, 8, 200, 12, 256, 4, 90, 128, 6] + [3 + (i * 7) % 40 for i in range(24)]
+    items = []
+    for k, n in enumerate(sizes):
+        items += synth.make_items(w, 1, 512, seed=170 + k, n_fixed=n, start=k)
+    b = collator.collator_toyota(items, max_node=512, multi_hop_max_dist=20, rel_pos_max=1024, world=w)
+    B = len(items)
+    assert B * 8 > 2 * 148
+    R, Pp, E, W, t = tables(seed=4)
+    cu = [x.cuda().contiguous() for x in (R, Pp, E, W.view(-1), t.view(-1))]
+    bias = ops.bias_fwd_raw(b, *cu, out_dtype=torch.bfloat16)
+    ntok = int(b.tok_pos.numel())
+    gen = torch.Generator().manual_seed(21)
+    qkv = (torch.randn(ntok, 3 * 192, generator=gen) * 1.2).to(torch.bfloat16)
+    dout = torch.randn(ntok, 192, generator=gen).to(torch.bfloat16)
+    tok_off = b.tok_off.cpu().numpy()
+    seed = 0x0F1E2D3C4B5A6978
+    out, lse = ops.attn_fwd_raw(qkv.cuda(), bias, b, drop_p=p_drop, seed=seed)
+    db32 = torch.full(bias.shape, float("nan"), dtype=torch.float32, device="cuda")
+    dqkv = ops.attn_bwd_raw(qkv.cuda(), bias, out, dout.cuda(), lse, b, db32, 0, drop_p=p_drop, seed=seed)
+    torch.cuda.synchronize()
+    q32 = qkv.float().requires_grad_(True)
+    b32 = bias.float().cpu().requires_grad_(True)
+    ref, ref_lse = torch_attention_diff(q32, b32, tok_off, drop=(p_drop, seed) if p_drop > 0 else None)
+    (ref * dout.float()).sum().backward()
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    assert (out.float().cpu() - ref.detach()).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+    with torch.no_grad():                   # lse [ntok, H] = logsumexp of the biased scores (before the dropout mask)
+        for g in range(B):
+            a, e = int(tok_off[g]), int(tok_off[g + 1])
+            T = e - a
+            q = q32[a:e, :192].view(T, 8, 24).transpose(0, 1)
+            k = q32[a:e, 192:384].view(T, 8, 24).transpose(0, 1)
+            sc = (q * 24 ** -0.5) @ k.transpose(1, 2) + b32[g, :, :T, :T]
+            want = torch.logsumexp(sc, -1).transpose(0, 1)
+            assert (lse[a:e].cpu() - want).abs().max().item() <= 2e-2, g
+    gq = q32.grad
+    assert (dqkv.float().cpu() - gq).abs().max().item() <= 2e-2 * max(1.0, gq.abs().max().item())
+    acc = db32.clone()
+    for g in range(B):                      # unwritten cells of the fp32 plane are not numbers: accumulate on the live corner only
+        Tg = int(tok_off[g + 1] - tok_off[g])
+        gb = b32.grad[g, :, :Tg, :Tg]
+        got = db32[g, :, :Tg, :Tg].cpu()
+        assert torch.isfinite(got).all(), g
+        assert (got - gb).abs().max().item() <= 2e-2 * max(1.0, gb.abs().max().item()), (g, Tg)
+    acc = torch.nan_to_num(acc, nan=0.0)
+    ops.attn_bwd_raw(qkv.cuda(), bias, out, dout.cuda(), lse, b, acc, 1, drop_p=p_drop, seed=seed)     # mode 1: += dS
+    for g in range(B):
+        Tg = int(tok_off[g + 1] - tok_off[g])
+        gb = b32.grad[g, :, :Tg, :Tg]
+        assert (acc[g, :, :Tg, :Tg].cpu() - 2 * gb).abs().max().item() <= 4e-2 * max(1.0, gb.abs().max().item()), (g, Tg)
+
+
 # ------------------------------------------------------------------------------------------------------- multi_hop_max_dist
 def _tables(H=8, bins=64, seed=0):
     g = torch.Generator().manual_seed(seed)
