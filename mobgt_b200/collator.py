@@ -368,6 +368,14 @@ def _bucket_sizes(ntok, cells, nmax, B):
     return ntok_b, cells_b, min(n_b, 512)
 
 
+def _host_plan(keys):
+    """Stable sort of an int key stream -> (perm i32, sorted keys i32): ops.sort_plan on the host."""
+    k = np.ascontiguousarray(keys)
+    small = k.size == 0 or (int(k.min()) >= 0 and int(k.max()) < 65536)
+    perm = np.argsort(k.astype(np.uint16) if small else k.astype(np.int64), kind="stable").astype(np.int32)   # 16-bit keys: radix sort
+    return perm, k[perm].astype(np.int32)
+
+
 def pack_host(items, max_node=512, bucket=False):
     """raw dataset items (owndata.py:340-349 fields; numpy or torch) -> HostPack.  No CUDA, no torch ops on the hot path.
 
@@ -438,6 +446,18 @@ def pack_host(items, max_node=512, bucket=False):
     host = dict(n=ns, sq_off=sq, node_off=no, tok_off=tok_off, tok_graph=tok_graph, tok_pos=tok_pos, feat8=None,
                 x_nodes=x_nodes, slot=slot, time_nodes=time_nodes, time_normal_nodes=tn, cat_nodes=cat_nodes,
                 in_deg=in_deg, out_deg=out_deg, user=user, y=y, idx=idx, node_rows=node_rows)
+    # The fixed summation orders of the K4 backward (stable sorts of the batch's key streams, Batch1.build_plans) and the launch
+    # order of the attention kernels depend on the indices only: they are built HERE, in the loader's worker process (numpy radix
+    # sorts of 16-bit keys, ~1 ms per batch off the critical path), and ride along in the one H2D copy — instead of ~25 device
+    # sort / scatter kernels per batch running next to the training step.
+    ind_tok = np.zeros(len(tok_pos), np.int32)
+    ind_tok[node_rows] = in_deg
+    outd_tok = np.zeros(len(tok_pos), np.int32)
+    outd_tok[node_rows] = out_deg
+    for name, keys in (("poi", x_nodes - 1), ("slot", slot), ("pos", tok_pos), ("ind", ind_tok), ("outd", outd_tok)):
+        perm, ks = _host_plan(keys)
+        host[f"plan_{name}_perm"], host[f"plan_{name}_keys"] = perm, ks
+    host["size_order"] = np.argsort(-ns.astype(np.int64), kind="stable").astype(np.int32)
     layout, total = {}, 0
     for k, a in host.items():
         if k == "feat8":
@@ -484,9 +504,16 @@ def collate_from_host(hp, world=None, latlon_dev=None, multi_hop_max_dist=20, re
     ns = hp.ns.numpy() if isinstance(hp.ns, torch.Tensor) else hp.ns
     dk = int(multi_hop_max_dist)
     hops = hop_stride(dk)                  # bytes per edge_in8 row; slots [dk, hops) are padding
-    b = Batch1(B=hp.B, N=hp.N, hops=hops, dk=dk, rel_pos_max=int(rel_pos_max), n_host=ns, h2d_bytes=0, padded=bool(hp.padded), **views)
-    b.h2d_bytes = int(sum(v.numel() * v.element_size() for v in views.values()))
-    b.build_plans()
+    h2d_bytes = int(sum(v.numel() * v.element_size() for v in views.values()))
+    plans = {k[5:]: views.pop(k) for k in list(views) if k.startswith("plan_")}          # built by pack_host on the host
+    size_order = views.pop("size_order", None)
+    b = Batch1(B=hp.B, N=hp.N, hops=hops, dk=dk, rel_pos_max=int(rel_pos_max), n_host=ns, h2d_bytes=h2d_bytes, padded=bool(hp.padded), **views)
+    if plans:
+        b.__dict__["_plans"] = {name: (plans[f"{name}_perm"], plans[f"{name}_keys"]) for name in ("poi", "slot", "pos", "ind", "outd")}
+        b.__dict__["_plans"]["node_rows"] = b.node_rows
+        b.size_order = size_order
+    else:
+        b.build_plans()
     k1 = apsp_edge_input_packed(b.feat8, b.n, b.sq_off, ns, hops=hops, shift=1, want_path=want_path, dk=dk)
     b.rel_pos16, b.edge_in8, b.maxdist, b.path16 = k1["dist"], k1["edge_in"], k1["maxdist"], k1["path"]
     b.poi_pos16 = torch.empty(hp.cells, dtype=torch.int16, device=dev)

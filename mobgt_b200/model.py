@@ -96,7 +96,7 @@ class GraphConvolution(nn.Module):
             xw = ops.spmm(x_csr[0], x_csr[1], self.weight) if x_csr is not None else torch.mm(x, self.weight)
             return ops.spmm(A, At, xw, self.bias, slope)
         if fin in ok:
-            y = torch.addmm(self.bias, ops.spmm(A, At, x), self.weight)
+            y = ops.LinearF32BiasFn.apply(ops.spmm(A, At, x), self.weight, self.bias)
             return F.leaky_relu(y, slope) if slope is not None else y
         raise NotImplementedError(f"GraphConvolution {fin}->{fout}: libmobgt's SpMM is built for widths 16 / 32 / 64 / 128")
 

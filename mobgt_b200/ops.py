@@ -821,6 +821,29 @@ def linear_gelu_bf16(x, lin, w16=None, b16=None):
     return LinearGeluFn.apply(x, w16, b16, lin.weight, lin.bias)
 
 
+class LinearF32BiasFn(torch.autograd.Function):
+    """y = x W + b in fp32 storage (TF32 tensor cores when enabled): the dense half of a GraphConvolution whose output is wider
+    than its input (modelGNN.py:39-46 associated as (adj x) W + b).  Same GEMMs as torch.addmm; the bias gradient — a sum over
+    all P rows of the POI table — is the K6 column-sum kernel (fixed order) written straight into the parameter's gradient slice
+    instead of torch's generic reduce (23 us per layer at P = 60 000)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        ctx.save_for_backward(x, W)
+        ctx.bias = b
+        return torch.addmm(b, x, W)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dy @ W.t() if ctx.needs_input_grad[0] else None
+        dW = x.t() @ dy
+        tb = _claim((ctx.bias,))
+        db = colsum(dy, out=tb)
+        return dx, dW, (None if tb is not None else db)
+
+
 # ----------------------------------------------------------------------------------------------- K8
 def spmm_csr_raw(csr, S, bias=None, slope=None):
     """Y = act(A @ S + bias): A = (crow i32 [n+1], col i32 [nnz], val f32 [nnz]); S f32 [m, D]; slope=None: no activation."""
@@ -841,7 +864,7 @@ class SpmmFn(torch.autograd.Function):
     def forward(ctx, A, At, S, bias, slope):
         b = bias.detach().float().contiguous() if bias is not None else None
         Y = spmm_csr_raw(A, S.detach().float(), b, slope)
-        ctx.At, ctx.slope, ctx.has_bias = At, slope, bias is not None
+        ctx.At, ctx.slope, ctx.has_bias, ctx.bias = At, slope, bias is not None, bias
         if slope is not None:
             ctx.save_for_backward(Y)
         return Y
@@ -851,13 +874,18 @@ class SpmmFn(torch.autograd.Function):
         g = dY.contiguous()
         if ctx.slope is not None:
             (Y,) = ctx.saved_tensors
-            g = torch.where(Y > 0, g, g * ctx.slope)
+            g = torch.ops.aten.leaky_relu_backward(g, Y, float(ctx.slope), True)     # one kernel (sign taken from the output)
         At = ctx.At
         if len(At) == 2:          # (chunked A^T, fold): long rows of A^T were cut into chunks, summed by a second tiny SpMM
             dS = spmm_csr_raw(At[1], spmm_csr_raw(At[0], g))
         else:
             dS = spmm_csr_raw(At, g)
-        db = colsum(g) if ctx.has_bias else None
+        db = None
+        if ctx.has_bias:
+            tb = _claim((ctx.bias,))
+            db = colsum(g, out=tb)
+            if tb is not None:
+                db = None
         return None, None, dS, db, None
 
 

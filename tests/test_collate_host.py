@@ -66,3 +66,24 @@ def test_packed_loader_protocol_without_cuda():
         seen.append(b["items"][0])
     assert seen == [1, 2, 3, 4]
     assert loader.current() is None       # end of stream
+
+
+def test_host_sort_plans_equal_the_device_recipe():
+    """pack_host ships the K4-backward sort plans and the attention launch order: they equal what Batch1.build_plans computes
+    on the device (ops.sort_plan = torch.sort(stable=True) of the same key streams; stable sorts are unique), for a plain and a
+    bucketed (padded) batch."""
+    for bucket in (False, True):
+        hp = collator.pack_host(_case(B=9, cap=40), bucket=bucket)
+        tok_pos, rows = torch.from_numpy(_field(hp, "tok_pos").copy()), torch.from_numpy(_field(hp, "node_rows").copy())
+        ind = torch.zeros_like(tok_pos)
+        ind[rows] = torch.from_numpy(_field(hp, "in_deg").copy())
+        outd = torch.zeros_like(tok_pos)
+        outd[rows] = torch.from_numpy(_field(hp, "out_deg").copy())
+        keys = {"poi": torch.from_numpy(_field(hp, "x_nodes").copy()).long() - 1, "slot": torch.from_numpy(_field(hp, "slot").copy()),
+                "pos": tok_pos, "ind": ind, "outd": outd}
+        for name, k in keys.items():
+            ks, perm = torch.sort(k.long(), stable=True)
+            assert np.array_equal(_field(hp, f"plan_{name}_perm"), perm.int().numpy()), (bucket, name)
+            assert np.array_equal(_field(hp, f"plan_{name}_keys"), ks.int().numpy()), (bucket, name)
+        n = torch.from_numpy(_field(hp, "n").copy())
+        assert np.array_equal(_field(hp, "size_order"), torch.argsort(n, descending=True, stable=True).int().numpy())
