@@ -314,6 +314,10 @@ int32_t mobgt_adamw_step(float *param, const float *grad, float *exp_avg, float 
  *           of C, i.e. the bias gradient of layer1 (workspace: mobgt_gemm_workspace_bytes(M, N, 2)).
  * ------------------------------------------------------------------------------------------ */
 int64_t mobgt_gemm_workspace_bytes(int32_t M, int32_t N, int32_t mode);
+/* GELU of modes 1 / 2: 1 (default) = erf form (nn.GELU() to 1.5e-7); 0 = tanh form 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
+ * on the hardware tanh unit, within 4.8e-4 absolute of the erf form and ~15 % faster — not the default because its derivative
+ * error compounds over the layers (see csrc/k10_gemm.cu).  Forward and backward always use the same function.  Process-wide. */
+int32_t mobgt_gemm_exact_gelu(int32_t on);
 int32_t mobgt_gemm_bf16(const void *A, int64_t lda, const void *B, int64_t ldb, const float *bias, void *C, int64_t ldc,
                         int32_t M, int32_t N, int32_t K, int32_t mode, const void *A2, int64_t lda2, const void *B2,
                         int64_t ldb2, int32_t K2, float *colsum, void *workspace, int64_t workspace_bytes, void *stream);

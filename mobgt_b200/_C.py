@@ -63,6 +63,7 @@ SIGNATURES = {
                         c_i64, c_p],
     "mobgt_debug_set_timeline": [c_p],
     "mobgt_debug_head_cluster": [c_i32],
+    "mobgt_gemm_exact_gelu": [c_i32],
     "mobgt_selftest_umma": [c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_p],
 }
 

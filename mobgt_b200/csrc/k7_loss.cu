@@ -62,6 +62,51 @@ __global__ void __launch_bounds__(kLossThreads) k7_lse_partial_kernel(const T *_
     }
 }
 
+// The same partial for bf16 logits whose rows are 16-byte aligned (the training head: class count padded to a multiple of 8):
+// 8 logits per 16-byte load, the thread's running (m, s) updated once per 8 elements — local max first, then eight exp2 of
+// differences — instead of a 2-byte load, a branch and an exp per element (30 -> ~10 us on the [256, 60 008] logits of c2).
+__global__ void __launch_bounds__(kLossThreads) k7_lse_partial_bf16x8_kernel(const __nv_bfloat16 *__restrict__ x, int64_t stride, int V,
+                                                                            int chunk, float2 *__restrict__ part) {
+    const int row = blockIdx.y, c0 = blockIdx.x * chunk, c1 = min(V, c0 + chunk);        // chunk % 8 == 0
+    const uint4 *xr = reinterpret_cast<const uint4 *>(x + (size_t)row * stride);
+    constexpr float kL2e = 1.4426950408889634f;
+    float m = -INFINITY, s = 0.f;                                                       // m in log2 units
+    for (int c = c0 + threadIdx.x * 8; c < c1; c += kLossThreads * 8) {
+        const uint4 v = __ldg(xr + (c >> 3));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            f[2 * e] = __uint_as_float(w[e] << 16) * kL2e;
+            f[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u) * kL2e;
+        }
+        const int nv = min(8, c1 - c);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if (e >= nv) f[e] = -INFINITY;
+            mx = fmaxf(mx, f[e]);
+        }
+        if (mx == -INFINITY) continue;
+        const float mn = fmaxf(m, mx);
+        float a = s * exp2f(m - mn);                                                     // m == -inf: s == 0
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a += exp2f(f[e] - mn);
+        s = a;
+        m = mn;
+    }
+    m *= 0.6931471805599453f;                                                           // back to natural-log units for lse_merge
+    __shared__ float sm[kLossThreads / 32], ss[kLossThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lse_merge(m, s, __shfl_xor_sync(0xffffffffu, m, o), __shfl_xor_sync(0xffffffffu, s, o));
+    if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = m; ss[threadIdx.x >> 5] = s; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kLossThreads / 32; ++w) lse_merge(m, s, sm[w], ss[w]);
+        part[(size_t)row * gridDim.x + blockIdx.x] = make_float2(m, s);
+    }
+}
+
 // one CTA: lse[row] from the row's partials (fixed order), row loss = lse - x[target]; loss = sum / #valid rows
 template <typename T>
 __global__ void __launch_bounds__(kLossThreads) k7_nll_finish_kernel(const T *__restrict__ x, int64_t stride, int B, int V, int nchunk,
@@ -234,8 +279,13 @@ extern "C" int32_t mobgt_lsm_nll_fwd(const void *logits, int32_t dtype, int64_t 
         k7_nll_finish_kernel<float><<<1, kLossThreads, 0, s>>>(static_cast<const float *>(logits), row_stride, B, V, nchunk, part,
                                                               target, ignore_index, lse, loss);
     } else {
-        k7_lse_partial_kernel<__nv_bfloat16><<<grid, kLossThreads, 0, s>>>(static_cast<const __nv_bfloat16 *>(logits), row_stride, V,
-                                                                          chunk, part);
+        if (row_stride % 8 == 0 && ((uintptr_t)logits & 15) == 0) {
+            const int chunk8 = round_up(chunk, 8);          // (covers V with the same nchunk: chunk8 >= chunk)
+            k7_lse_partial_bf16x8_kernel<<<grid, kLossThreads, 0, s>>>(static_cast<const __nv_bfloat16 *>(logits), row_stride, V, chunk8, part);
+        } else {
+            k7_lse_partial_kernel<__nv_bfloat16><<<grid, kLossThreads, 0, s>>>(static_cast<const __nv_bfloat16 *>(logits), row_stride, V,
+                                                                              chunk, part);
+        }
         MOBGT_LAUNCH_OK("k7_lse_partial_kernel");
         k7_nll_finish_kernel<__nv_bfloat16><<<1, kLossThreads, 0, s>>>(static_cast<const __nv_bfloat16 *>(logits), row_stride, B, V,
                                                                       nchunk, part, target, ignore_index, lse, loss);

@@ -76,7 +76,18 @@ def test_k7_gradient_tail_loss(lib_built, B, V, alpha, dtype):
                                         (640, 128, 64, 0), (300, 128, 576, 0)])
 def test_k10_gemm_epilogues(lib_built, M, N, K, mode):
     """tcgen05 GEMM with fused epilogues against torch fp32 on the same bf16 operands: mode 0 (+ bias), mode 1 (+ bias, GELU),
-    mode 2 (FFN backward: (a w^T) o gelu'(a2 w2^T + bias) and its column sums).  bf16 output: 2^-8 relative."""
+    mode 2 (FFN backward: (a w^T) o gelu'(a2 w2^T + bias) and its column sums).  bf16 output: 2^-8 relative.  Both GELU forms
+    of the epilogue — the default erf form and the optional tanh form on MUFU.TANH — are compared with torch's exact nn.GELU."""
+    from mobgt_b200 import _C
+    try:
+        for exact in ((1, 0) if mode else (1,)):
+            _C.call("mobgt_gemm_exact_gelu", exact)
+            _k10_case(M, N, K, mode)
+    finally:
+        _C.call("mobgt_gemm_exact_gelu", 1)
+
+
+def _k10_case(M, N, K, mode):
     from mobgt_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(M + N + K + mode)
     a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
