@@ -106,3 +106,42 @@ def test_pack_host_buckets_pad_only_the_tails():
     assert not vb["tok_pos"][ntok:].any() and not vb["in_deg"][len(va["in_deg"]):].any()
     assert np.array_equal(vb["node_rows"][len(va["node_rows"]):], ntok + np.arange(pad))
     assert int(vb["tok_off"][-1]) == ntok                                         # no graph owns a padding token
+
+
+def test_gradient_claims_write_once_then_accumulate():
+    """ops._claim — the rule behind "gradients are written, not accumulated": a parameter whose gradient view lies in a flat
+    buffer the trainer has just zeroed (ops.grads_zeroed) may be WRITTEN once; a second gradient before the next zeroing, a
+    buffer that was never announced, a misaligned view or non-adjacent parameters fall back to accumulation.  Pure host logic
+    (pointer arithmetic on the gradient views): runs on CPU tensors."""
+    from mobgt_b200 import ops
+    q, k, v = (torch.nn.Parameter(torch.zeros(8, 4)) for _ in range(3))
+    b = torch.nn.Parameter(torch.zeros(8))
+    flat = torch.zeros(8 * 4 * 3 + 8 + 4)
+    off = 0
+    for p_ in (q, k, v, b):
+        p_.grad = flat[off:off + p_.numel()].view_as(p_)
+        off += p_.numel()
+    assert ops._claim((q,)) is None or ops._zero_epoch > 0          # never announced: no claim unless another test zeroed THIS range
+    ops.grads_zeroed(flat)
+    t = ops._claim((q, k, v))                                       # q | k | v back to back -> one [24, 4] view of the buffer
+    assert t is not None and tuple(t.shape) == (24, 4) and t.data_ptr() == q.grad.data_ptr()
+    t.fill_(1.0)
+    assert float(q.grad.sum() + k.grad.sum() + v.grad.sum()) == 96.0 and float(b.grad.abs().sum()) == 0.0
+    assert ops._claim((q,)) is None and ops._claim((k, v)) is None  # already written since the zeroing -> accumulate
+    assert ops._claim((b,)) is not None                             # independent parameter
+    ops.grads_zeroed(flat)
+    assert ops._claim((q, v)) is None                               # not adjacent
+    assert ops._claim((q, k)) is not None                           # (does not consume v)
+    assert ops._claim((v,)) is not None
+    other = torch.nn.Parameter(torch.zeros(4))
+    other.grad = torch.zeros(5)[1:]                                 # 4-byte aligned only, and outside every announced buffer
+    assert ops._claim((other,)) is None
+    detached = torch.zeros(4, requires_grad=True) * 2               # not a leaf
+    assert ops._claim((detached,)) is None
+
+
+def test_head_split_is_even_and_bounded():
+    from mobgt_b200 import ops
+    for M, V in ((256, 60001), (4096, 125000), (4096, 1000000), (1, 97), (1024, 125000), (130, 3680)):
+        ns = ops.head_split(M, V)
+        assert ns % 2 == 0 and 2 <= ns <= 160, (M, V, ns)
