@@ -93,35 +93,59 @@ __global__ void k4_segsum_a_kernel(const T *__restrict__ src, int64_t src_stride
                                    int32_t *__restrict__ tail_key) {
     const int c = blockIdx.x;
     const int r0 = c * kChunk, r1 = min(nrows, r0 + kChunk);
+    // the chunk's permutation and keys (with one key of context on either side) are fetched once, coalesced, into shared
+    // memory: the row loop below then issues nothing but independent row loads, four rows ahead — it used to pay a dependent
+    // perm[r] -> row -> keys[r + 1] chain of global loads per row (13 us per launch however small the batch)
+    __shared__ int sperm[kChunk], skey[kChunk + 2];
+    for (int i = threadIdx.x; i < kChunk + 2; i += blockDim.x) {
+        const int r = r0 - 1 + i;
+        skey[i] = (r >= 0 && r < nrows) ? keys[r] : -1;
+        if (i < kChunk) sperm[i] = (r0 + i < r1) ? perm[r0 + i] : 0;
+    }
+    __syncthreads();
     const int e0 = threadIdx.x * 4;
     if (e0 >= D) return;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int fl = 0, tkey = -1;
     int run_start = r0;
-    int key = keys[r0];
-    for (int r = r0; r < r1; ++r) {
-        const T *row = src + (size_t)perm[r] * src_stride + col0 + e0;
-        acc.x += to_f<T>(row[0]);
-        acc.y += to_f<T>(row[1]);
-        acc.z += to_f<T>(row[2]);
-        acc.w += to_f<T>(row[3]);
-        const int nkey = (r + 1 < nrows) ? keys[r + 1] : -1;
-        if (r + 1 == r1 || nkey != key) {  // run [run_start, r] ends here
-            const bool from_prev = (run_start == r0) && (r0 > 0) && (keys[r0 - 1] == key);
-            const bool to_next = (r + 1 == r1) && (nkey == key);
-            if (!from_prev && !to_next) {
-                if (key >= 0 && key < nkeys) *reinterpret_cast<float4 *>(table + (size_t)key * D + e0) = acc;
-            } else if (from_prev) {
-                *reinterpret_cast<float4 *>(part + ((size_t)c * 2 + 0) * D + e0) = acc;
-                fl |= kHasHead | (to_next ? kHeadContinues : 0);
-            } else {
-                *reinterpret_cast<float4 *>(part + ((size_t)c * 2 + 1) * D + e0) = acc;
-                fl |= kHasTail;
-                tkey = key;
+    int key = skey[1];
+    const int nr = r1 - r0;
+    auto load_row = [&](int i, float (&v)[4]) {
+        const T *row = src + (size_t)sperm[i] * src_stride + col0 + e0;
+        v[0] = to_f<T>(row[0]); v[1] = to_f<T>(row[1]); v[2] = to_f<T>(row[2]); v[3] = to_f<T>(row[3]);
+    };
+    for (int i0 = 0; i0 < nr; i0 += 4) {
+        float v[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + u < nr) load_row(i0 + u, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u;
+            if (i >= nr) break;
+            const int r = r0 + i;
+            acc.x += v[u][0];
+            acc.y += v[u][1];
+            acc.z += v[u][2];
+            acc.w += v[u][3];
+            const int nkey = skey[i + 2];                       // keys[r + 1], -1 past the end
+            if (r + 1 == r1 || nkey != key) {  // run [run_start, r] ends here
+                const bool from_prev = (run_start == r0) && (r0 > 0) && (skey[0] == key);
+                const bool to_next = (r + 1 == r1) && (nkey == key);
+                if (!from_prev && !to_next) {
+                    if (key >= 0 && key < nkeys) *reinterpret_cast<float4 *>(table + (size_t)key * D + e0) = acc;
+                } else if (from_prev) {
+                    *reinterpret_cast<float4 *>(part + ((size_t)c * 2 + 0) * D + e0) = acc;
+                    fl |= kHasHead | (to_next ? kHeadContinues : 0);
+                } else {
+                    *reinterpret_cast<float4 *>(part + ((size_t)c * 2 + 1) * D + e0) = acc;
+                    fl |= kHasTail;
+                    tkey = key;
+                }
+                acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                run_start = r + 1;
+                key = nkey;
             }
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            run_start = r + 1;
-            key = nkey;
         }
     }
     if (threadIdx.x == 0) {
