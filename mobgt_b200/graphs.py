@@ -36,11 +36,16 @@ def _tensor_fields(batch):
 
 
 class GraphedTrainStep:
-    def __init__(self, model, flat_grads, example_batch, warmup=3, after_backward=None, pool=None):
+    def __init__(self, model, flat_grads, example_batch, warmup=3, after_backward=None, pool=None, split_head=False):
         """after_backward: optional callable run right after loss.backward() inside the captured region (the trainer joins
-        the side stream of its early gradient all-reduce there, so the collective is part of the graph)."""
+        the side stream of its early gradient all-reduce there, so the collective is part of the graph).
+        split_head: capture TWO graphs — A = zero grads + forward + loss + the backward of the two heads (which completes the
+        gradient of out_proj), B = the encoder backward — so that the data-parallel trainer can start the all-reduce of the
+        out_proj bucket between them (`run_a()`, collective on a side stream, `run_b()`)."""
         self.model, self.flat = model, flat_grads
         self._after_backward = after_backward
+        self.split = bool(split_head)
+        self.graph_b = torch.cuda.CUDAGraph() if self.split else None
         self.static = example_batch
         self.dev = flat_grads.device
         if "_plans" not in example_batch.__dict__:
@@ -62,9 +67,18 @@ class GraphedTrainStep:
             if hasattr(model, "_w16"):
                 model._w16.stamp = None          # the bf16 re-cast of the weights must be part of the captured work
             n0 = _C.launch_count()
-            with torch.cuda.graph(self.graph, pool=pool):          # pool: memory shared by graphs that never run concurrently
-                self.loss = self._body()
-            self.launches = _C.launch_count() - n0       # libmobgt kernel nodes in the graph = launches per replay
+            if self.split:
+                if pool is None:
+                    pool = torch.cuda.graph_pool_handle()          # A's activations are read by B: one pool for both
+                with torch.cuda.graph(self.graph, pool=pool):
+                    self.loss, z, z_cut = self._body_a()
+                with torch.cuda.graph(self.graph_b, pool=pool):
+                    self._body_b(z, z_cut)
+                del z, z_cut
+            else:
+                with torch.cuda.graph(self.graph, pool=pool):      # pool: memory shared by graphs that never run concurrently
+                    self.loss = self._body()
+            self.launches = _C.launch_count() - n0       # libmobgt kernel nodes in the graph(s) = launches per replay
             torch.cuda.synchronize()
         except Exception as e:                   # noqa: BLE001 — anything that is illegal during capture: report, let the caller fall back
             ops.set_device_seed(None)
@@ -73,7 +87,24 @@ class GraphedTrainStep:
             # eager steps (other shapes) must not use the graph's counter
             ops.set_device_seed(None)
 
+    def _body_a(self):
+        self.seed_dev.add_(1)
+        self.flat.zero_()
+        ops.grads_zeroed(self.flat)
+        loss, z, z_cut = self.model.training_step(self.static, split=True)
+        loss.backward()                       # heads only: the graph is cut at z
+        return loss, z, z_cut
+
+    def _body_b(self, z, z_cut):
+        z.backward(z_cut.grad)                # encoder, embeddings, bias tables, GCNs
+        if self._after_backward is not None:
+            self._after_backward()
+
     def _body(self):
+        if self.split:
+            loss, z, z_cut = self._body_a()
+            self._body_b(z, z_cut)
+            return loss
         self.seed_dev.add_(1)
         self.flat.zero_()
         ops.grads_zeroed(self.flat)
@@ -108,4 +139,14 @@ class GraphedTrainStep:
 
     def run(self):
         self.graph.replay()
+        if self.split:
+            self.graph_b.replay()
         return self.loss
+
+    def run_a(self):
+        """split_head: zero + forward + loss + head backward; out_proj's gradient is final when this replay has finished."""
+        self.graph.replay()
+        return self.loss
+
+    def run_b(self):
+        self.graph_b.replay()

@@ -382,10 +382,21 @@ class Graphormer(nn.Module):
         return [output, cat_output]
 
     # ------------------------------------------------------------------------------------------ steps
-    def training_step(self, batched_data, batch_idx=0):
+    def training_step(self, batched_data, batch_idx=0, split=False):
         """model_fqandtoyo.py:1434-1478.  The losses are the K7 kernels (csrc/k7_loss.cu): one pass over the logits gives the
-        loss, and the same pass of the backward gives d(logits)."""
+        loss, and the same pass of the backward gives d(logits).
+        split=True -> (loss, z, z_cut): the autograd graph is cut at z, the [B, 2*hidden+64] input of the two heads.
+        `loss.backward()` then runs the head backward only (it completes the gradient of out_proj — 77 of the 92 MB of a c2 model —
+        and leaves d loss / d z in z_cut.grad), `z.backward(z_cut.grad)` the encoder backward: the data-parallel trainer captures
+        the two halves as two CUDA graphs and all-reduces the out_proj bucket while the second one runs."""
         z, b = self.features(batched_data)
+        z_full = z
+        if split:
+            z = z.detach().requires_grad_(True)
+        loss = self._heads_loss(z, b)
+        return (loss, z_full, z) if split else loss
+
+    def _heads_loss(self, z, b):
         cat_logits = self.cat_decoder(z)
         # POI logits in bf16 (the reference's `--precision 16` runs this Linear in fp16): [B, P] x 2 bytes instead of 4 through
         # the loss kernels, and a bf16 tensor-core GEMM forward and backward
@@ -471,8 +482,10 @@ class Graphormer(nn.Module):
         for layer in self.layers:
             a = layer.self_attention
             fused += [a.linear_q.weight, a.linear_k.weight, a.linear_v.weight, a.linear_q.bias, a.linear_k.bias, a.linear_v.bias]
-        seen = {id(p) for p in fused}
-        return fused + [p for p in self.parameters() if id(p) not in seen]
+        seen = {id(p) for p in fused} | {id(self.out_proj.weight)}
+        # out_proj.weight LAST: its gradient (77 of 92 MB at P = 60 000) is all-reduced on its own, early (trainer.Trainer); with
+        # the bucket at the end of the flat buffer the remainder is ONE contiguous all-reduce instead of two
+        return fused + [p for p in self.parameters() if id(p) not in seen] + [self.out_proj.weight]
 
     def configure_optimizers(self):
         """model_fqandtoyo.py:1599-1616"""

@@ -55,6 +55,9 @@ class Trainer:
         self._early = None
         self._early_done, self._early_joined, self._overlap_in_graph = None, False, bool(overlap_in_graph)
         self._constructing = False
+        # data parallel + CUDA graphs: the step is captured as two graphs cut behind the head backward, and the all-reduce of
+        # the out_proj bucket runs on the side stream under the second one (MOBGT_SPLIT_GRAPH=0: one graph, one flat all-reduce)
+        self._split_graph = self._overlap and hasattr(model, "out_proj") and os.environ.get("MOBGT_SPLIT_GRAPH", "1") != "0"
         if self._overlap and hasattr(model, "out_proj"):
             w = model.out_proj.weight
             off = (w.grad.data_ptr() - self.flat.data_ptr()) // 4
@@ -68,6 +71,18 @@ class Trainer:
         capturing = torch.cuda.is_current_stream_capturing()
         if not self._overlap or (capturing and not self._overlap_in_graph) or (self._constructing and not capturing):
             return          # (the eager warm-up passes of a graph capture issue no collective: capture stays rank-local)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._side.wait_event(ev)
+        a, b = self._early
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.AVG, group=self.group)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        self._early_done = done
+
+    def _start_early_allreduce(self):
+        """All-reduce the out_proj bucket on the side stream, ordered after everything enqueued on the training stream."""
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         self._side.wait_event(ev)
@@ -115,10 +130,12 @@ class Trainer:
             self._early_done, self._early_joined = None, False
             self._constructing = True
             try:
-                g = graphs.GraphedTrainStep(self.model, self.flat, batch, after_backward=self._join_early, pool=self._pool)
+                g = graphs.GraphedTrainStep(self.model, self.flat, batch, after_backward=self._join_early, pool=self._pool,
+                                            split_head=self._split_graph)
                 g.early_in_graph = bool(self._early_joined)
                 self._graphs[sig] = g
-                self.graph_note = "fwd+bwd captured" + (" (+ early all-reduce of out_proj.weight.grad in-graph)" if g.early_in_graph else "")
+                self.graph_note = "fwd+bwd captured" + (" (+ early all-reduce of out_proj.weight.grad in-graph)" if g.early_in_graph else "") \
+                    + (" as two graphs cut behind the head backward; the out_proj bucket is all-reduced under the second" if g.split else "")
                 break
             except graphs.GraphCaptureError as e:
                 if os.environ.get("MOBGT_STRICT_GRAPH") == "1":
@@ -138,6 +155,13 @@ class Trainer:
         if g is not None:
             try:
                 g.load(batch)
+                if g.split and self._early is not None:
+                    loss = g.run_a()
+                    self._start_early_allreduce()          # out_proj.weight.grad is final: its bucket leaves now ...
+                    g.run_b()                              # ... while the encoder backward runs
+                    self._join_early()
+                    self.graph_steps += 1
+                    return loss.detach(), True
                 loss = g.run()
                 self.graph_steps += 1
                 return loss.detach(), g.early_in_graph

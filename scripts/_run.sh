@@ -1,5 +1,5 @@
-O=gpurun_out/r3w; mkdir -p $O
-timeout 900 python -m pytest tests -m gpu -x -q -k "embed or segment or k4 or canonical or golden or in_place" > $O/pytest_sub.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_sub.log
-timeout 300 python scripts/step_kernels.py c2-natural > $O/step_nat.txt 2>&1; grep "k4_segsum" $O/step_nat.txt
-timeout 300 python scripts/step_kernels.py c2-dense128 > $O/step_c2.txt 2>&1; grep "k4_segsum\|workload" $O/step_c2.txt
-bash scripts/sanitize.sh gpurun_out/r3san > $O/sanitize.log 2>&1; grep -h "rc=" $O/sanitize.log
+O=gpurun_out/r3y; mkdir -p $O
+for sg in 1 0; do
+MOBGT_SPLIT_GRAPH=$sg timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 2952$sg bench.py --gpus 8 --steps 30 --warmup 6 --no-cpu-baseline --no-kernel-report > $O/bench_n8_split$sg.json 2> $O/bench_n8_split$sg.err; echo "bench n8 split=$sg rc=$?"; python -c "
+import json;d=json.loads(open('$O/bench_n8_split$sg.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['e2e']['value'])"
+done

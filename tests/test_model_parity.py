@@ -103,9 +103,12 @@ def test_metrics_match_reference_semantics(lib_built):
 
 
 @pytest.mark.gpu
-def test_cuda_graph_step_matches_eager(lib_built):
+@pytest.mark.parametrize("split_head", [False, True])
+def test_cuda_graph_step_matches_eager(lib_built, split_head):
     """graphs.GraphedTrainStep: replaying the captured forward + backward on a freshly loaded batch gives the same loss and
-    the same gradients as the eager step (eval mode: no dropout, so the comparison is exact up to atomics-free determinism)."""
+    the same gradients as the eager step (eval mode: no dropout, so the comparison is exact up to atomics-free determinism).
+    split_head: the step captured as TWO graphs cut behind the head backward (what the data-parallel trainer replays around
+    the early all-reduce of the out_proj bucket)."""
     import torch
     from mobgt_b200 import collator, graphs, model as M, ops, synth
     world = synth.make_world("tiny", seed=1)
@@ -124,7 +127,7 @@ def test_cuda_graph_step_matches_eager(lib_built):
     mk = lambda seed: collator.collate_packed(synth.make_items(world, 6, 12, seed=seed, cfg_id=2, n_fixed=12), world, latlon, 512, 20, 1024)
     b0, b1 = mk(1), mk(2)
     try:
-        g = graphs.GraphedTrainStep(model, flat, b0)
+        g = graphs.GraphedTrainStep(model, flat, b0, split_head=split_head)
     except graphs.GraphCaptureError as e:
         pytest.skip(f"not capturable here: {e}")
     for b in (b1, mk(1)):
