@@ -1,5 +1,5 @@
-O=gpurun_out/r3y; mkdir -p $O
-for sg in 1 0; do
-MOBGT_SPLIT_GRAPH=$sg timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 2952$sg bench.py --gpus 8 --steps 30 --warmup 6 --no-cpu-baseline --no-kernel-report > $O/bench_n8_split$sg.json 2> $O/bench_n8_split$sg.err; echo "bench n8 split=$sg rc=$?"; python -c "
-import json;d=json.loads(open('$O/bench_n8_split$sg.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['e2e']['value'])"
-done
+O=gpurun_out/r3f2; mkdir -p $O
+timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu.log; tail -4 $O/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/smoke.log
+timeout 600 python bench.py --steps 20 --warmup 5 > $O/bench_c2-dense128.json 2> $O/bench.err; echo "bench rc=$?"; python -c "
+import json;d=json.loads(open('$O/bench_c2-dense128.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['e2e'],d['roofline'],d['gpu_launches'])"
