@@ -110,24 +110,53 @@ __global__ void k4_segsum_a_kernel(const T *__restrict__ src, int64_t src_stride
     int run_start = r0;
     int key = skey[1];
     const int nr = r1 - r0;
-    auto load_row = [&](int i, float (&v)[4]) {
-        const T *row = src + (size_t)sperm[i] * src_stride + col0 + e0;
-        v[0] = to_f<T>(row[0]); v[1] = to_f<T>(row[1]); v[2] = to_f<T>(row[2]); v[3] = to_f<T>(row[3]);
-    };
-    for (int i0 = 0; i0 < nr; i0 += 4) {
-        float v[4][4];
+    // all rows of the chunk are in flight at once (one global-memory latency per chunk): 8-byte loads of 4 bf16 — 2 registers
+    // per row, 32 rows — or 16-byte loads of 4 floats, 16 rows at a time; then the sums run in row order (fixed: reproducible)
+    constexpr int kBatch = sizeof(T) == 2 ? kChunk : kChunk / 2;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    for (int i0 = 0; i0 < nr; i0 += kBatch) {
+        float v[kBatch][sizeof(T) == 2 ? 2 : 4];        // bf16: two packed words per row; f32: four floats
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (i0 + u < nr) load_row(i0 + u, v[u]);
+        for (int u = 0; u < kBatch; ++u) {
+            if (i0 + u < nr) {
+                const T *row = src + (size_t)sperm[i0 + u] * src_stride + col0 + e0;
+                if constexpr (sizeof(T) == 2) {
+                    if (vec_ok) {
+                        const uint2 w = *reinterpret_cast<const uint2 *>(row);
+                        v[u][0] = __uint_as_float(w.x);
+                        v[u][1] = __uint_as_float(w.y);
+                    } else {
+                        const unsigned short *h = reinterpret_cast<const unsigned short *>(row);
+                        v[u][0] = __uint_as_float((uint32_t)h[0] | ((uint32_t)h[1] << 16));
+                        v[u][1] = __uint_as_float((uint32_t)h[2] | ((uint32_t)h[3] << 16));
+                    }
+                } else {
+                    if (vec_ok) {
+                        const float4 w = *reinterpret_cast<const float4 *>(row);
+                        v[u][0] = w.x; v[u][1] = w.y; v[u][2] = w.z; v[u][3] = w.w;
+                    } else {
+                        v[u][0] = to_f<T>(row[0]); v[u][1] = to_f<T>(row[1]); v[u][2] = to_f<T>(row[2]); v[u][3] = to_f<T>(row[3]);
+                    }
+                }
+            }
+        }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kBatch; ++u) {
             const int i = i0 + u;
             if (i >= nr) break;
             const int r = r0 + i;
-            acc.x += v[u][0];
-            acc.y += v[u][1];
-            acc.z += v[u][2];
-            acc.w += v[u][3];
+            if constexpr (sizeof(T) == 2) {
+                const uint32_t w0 = __float_as_uint(v[u][0]), w1 = __float_as_uint(v[u][1]);
+                acc.x += __uint_as_float(w0 << 16);
+                acc.y += __uint_as_float(w0 & 0xFFFF0000u);
+                acc.z += __uint_as_float(w1 << 16);
+                acc.w += __uint_as_float(w1 & 0xFFFF0000u);
+            } else {
+                acc.x += v[u][0];
+                acc.y += v[u][1];
+                acc.z += v[u][2];
+                acc.w += v[u][3];
+            }
             const int nkey = skey[i + 2];                       // keys[r + 1], -1 past the end
             if (r + 1 == r1 || nkey != key) {  // run [run_start, r] ends here
                 const bool from_prev = (run_start == r0) && (r0 > 0) && (skey[0] == key);

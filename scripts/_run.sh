@@ -1,5 +1,4 @@
-O=gpurun_out/r3f2; mkdir -p $O
-timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu.log; tail -4 $O/pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/smoke.log
-timeout 600 python bench.py --steps 20 --warmup 5 > $O/bench_c2-dense128.json 2> $O/bench.err; echo "bench rc=$?"; python -c "
-import json;d=json.loads(open('$O/bench_c2-dense128.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['e2e'],d['roofline'],d['gpu_launches'])"
+O=gpurun_out/r3k5; mkdir -p $O
+timeout 900 python -m pytest tests -m gpu -x -q -k "embed or segment or k4 or canonical or golden or in_place or bucketed" > $O/pytest_sub.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_sub.log
+timeout 300 python scripts/step_kernels.py c2-natural > $O/step_nat.txt 2>&1; grep "k4_segsum\|workload" $O/step_nat.txt
+timeout 300 python scripts/step_kernels.py c2-dense128 > $O/step_c2.txt 2>&1; grep "k4_segsum\|workload" $O/step_c2.txt
