@@ -169,6 +169,39 @@ __global__ void __launch_bounds__(kLossThreads) k7_nll_bwd_kernel(const T *__res
     }
 }
 
+// the same for bf16 logits / gradients with 16-byte aligned rows (both strides multiples of 8): 8 classes per 16-byte load / store
+__global__ void __launch_bounds__(kLossThreads) k7_nll_bwd_bf16x8_kernel(const __nv_bfloat16 *__restrict__ x, int64_t stride, int V,
+                                                                        const int64_t *__restrict__ target, int64_t ignore_index,
+                                                                        const float *__restrict__ lse, const float *__restrict__ aux,
+                                                                        const float *__restrict__ gout, __nv_bfloat16 *__restrict__ dx,
+                                                                        int64_t dstride, int Vpad) {
+    const int row = blockIdx.y;
+    const int64_t t = target[row];
+    const bool live = t != ignore_index && t >= 0 && t < V;
+    const float scale = live ? __ldg(gout) / __ldg(aux + 1) : 0.f;
+    constexpr float kL2e = 1.4426950408889634f;
+    const float l2 = lse[row] * kL2e;
+    const int c = (blockIdx.x * kLossThreads + threadIdx.x) * 8;
+    if (c >= Vpad) return;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(x + (size_t)row * stride + c));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float g[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int cc = c + 2 * e + h;
+            const float xv = __uint_as_float(h ? (w[e] & 0xFFFF0000u) : (w[e] << 16));
+            const float p = (live && cc < V) ? exp2f(fmaf(xv, kL2e, -l2)) : 0.f;      // padding classes (cc >= V): no gradient
+            g[h] = (p - ((live && cc == (int)t) ? 1.f : 0.f)) * scale;
+        }
+        __nv_bfloat162 pk = __floats2bfloat162_rn(g[0], g[1]);
+        o[e] = *reinterpret_cast<uint32_t *>(&pk);
+    }
+    *reinterpret_cast<uint4 *>(dx + (size_t)row * dstride + c) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // ---- GradientTailLoss (model_fqandtoyo.py:545-550, k = 1, beta = 1):
 //   f(x) = -alpha (1 - p) log p   on the target class,   -p log(1 - p)   elsewhere,   p = sigmoid(x) ;  loss = mean over [B,V]
 // (the reference evaluates both branches everywhere and multiplies by the one-hot mask; only the selected branch is evaluated
@@ -307,6 +340,10 @@ extern "C" int32_t mobgt_lsm_nll_bwd(const void *logits, int32_t dtype, int64_t 
     if (dtype == MOBGT_F32)
         k7_nll_bwd_kernel<float><<<grid, kLossThreads, 0, s>>>(static_cast<const float *>(logits), row_stride, V, target, ignore_index,
                                                               lse, loss, grad_out, static_cast<float *>(dlogits), d_row_stride, Vpad);
+    else if (row_stride % 8 == 0 && d_row_stride % 8 == 0 && Vpad % 8 == 0 && (((uintptr_t)logits | (uintptr_t)dlogits) & 15) == 0)
+        k7_nll_bwd_bf16x8_kernel<<<dim3((unsigned)ceil_div(Vpad, kLossThreads * 8), (unsigned)B), kLossThreads, 0, s>>>(
+            static_cast<const __nv_bfloat16 *>(logits), row_stride, V, target, ignore_index, lse, loss, grad_out,
+            static_cast<__nv_bfloat16 *>(dlogits), d_row_stride, Vpad);
     else
         k7_nll_bwd_kernel<__nv_bfloat16><<<grid, kLossThreads, 0, s>>>(static_cast<const __nv_bfloat16 *>(logits), row_stride, V, target,
                                                                       ignore_index, lse, loss, grad_out,
