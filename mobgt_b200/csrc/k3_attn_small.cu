@@ -4,8 +4,8 @@
 // Why: a trajectory graph has 4 nodes in the median (SURVEY.md §8d node-count law; 9 graphs in 10 have at most 16 tokens).  The
 // tensor-core kernels (k3_attn_fwd.cu / k3_attn_bwd.cu) spend one CTA, one 128 x 128 MMA tile, a 32 KB TMA bias tile and a
 // barrier / TMEM / TMA latency chain of ~20 k cycles on every (graph, head) — for a 5-token graph 99.8 % of that tile is
-// padding.  Here a 64-thread CTA works on one graph and four heads, thread = (row, head): query row in the forward and in the
-// dQ / dS pass, key column in the dK / dV pass; K, V (and Q, dO in the backward) and the live corner of the bias planes are
+// padding.  Here a 64-thread CTA (backward: 128 threads, the two passes side by side) works on one graph and four heads,
+// thread = (row, head): query row in the forward and in the dQ / dS pass, key column in the dK / dV pass; K, V (and Q, dO in the backward) and the live corner of the bias planes are
 // staged once in shared memory (every thread issues its loads back to back: one global-memory latency per CTA), operand rows
 // are read as broadcasts, and only the live cells of the dS plane are written.  The arithmetic is the tensor-core path's
 // (softmax in log2 units, denominator before the dropout mask, the SAME counter-based mask: common.cuh attn_drop_*), with fp32
@@ -91,8 +91,9 @@ constexpr int kOpFloats = kRows * kD + (kRows / 8) * 4;  // 392 = 8 (mod 32)
 constexpr int kBP = kRows + 8;                           // bias row pitch (bf16): 48 B, 8 consecutive rows hit distinct banks
 
 // rows [t0, t0 + Tg) x (4 heads x 24) bf16 of a [ntok, stride] matrix -> fp32 dst[head][row_off(row)]
-__device__ __forceinline__ void stage_heads(const __nv_bfloat16 *src, int64_t stride, int t0, int Tg, int h0, float *dst, int nthr) {
-    for (int i = threadIdx.x; i < Tg * 12; i += nthr) {
+__device__ __forceinline__ void stage_heads(const __nv_bfloat16 *src, int64_t stride, int t0, int Tg, int h0, float *dst, int nthr,
+                                            int tid0 = -1) {
+    for (int i = tid0 < 0 ? (int)threadIdx.x : tid0; i < Tg * 12; i += nthr) {
         const int r = i / 12, c = i - r * 12;            // 16-byte chunk c of the row's 192-byte slice: head c / 3, part c % 3
         float f[8];
         unpack8(__ldg(reinterpret_cast<const uint4 *>(src + (size_t)(t0 + r) * stride + h0 * kD) + c), f);
@@ -101,9 +102,10 @@ __device__ __forceinline__ void stage_heads(const __nv_bfloat16 *src, int64_t st
         d[1] = make_float4(f[4], f[5], f[6], f[7]);
     }
 }
-__device__ __forceinline__ void stage_bias4(const __nv_bfloat16 *bias, int T, int Tp, int plane0, int Tg, __nv_bfloat16 *dst, int nthr) {
+__device__ __forceinline__ void stage_bias4(const __nv_bfloat16 *bias, int T, int Tp, int plane0, int Tg, __nv_bfloat16 *dst, int nthr,
+                                            int tid0 = -1) {
     const int nch = (Tg + 7) >> 3;
-    for (int i = threadIdx.x; i < kHG * Tg * nch; i += nthr) {
+    for (int i = tid0 < 0 ? (int)threadIdx.x : tid0; i < kHG * Tg * nch; i += nthr) {
         const int hq = i / (Tg * nch), ii = i - hq * (Tg * nch);
         const int r = ii / nch, c8 = ii - r * nch;
         *reinterpret_cast<uint4 *>(dst + (hq * kRows + r) * kBP + c8 * 8) =
@@ -188,8 +190,11 @@ __global__ void __launch_bounds__(kThreads, 12) k3s_attn_fwd_kernel(const SmallA
 // pass 1, thread = (query row t, head): D = sum(dO_t * O_t); per key c: p = 2^(s - lse), dP = dO_t . V_c (masked, / keep),
 //         dS = p (dP - D) -> dS plane, dQ_t += dS K_c
 // pass 2, thread = (key column t, head): the same p / dS recomputed per query row r: dK_t += dS Q_r, dV_t += (mask p / keep) dO_r
+// The two passes read the same staged operands and write disjoint outputs, so they run SIDE BY SIDE: threads [0, 64) take
+// pass 1, threads [64, 128) pass 2 — the kernel is bound by the dependent-instruction chain of its largest graph, and the
+// chain is now the longer of the two passes instead of their sum.
 template <bool kDrop>
-__global__ void __launch_bounds__(kThreads, 8) k3s_attn_bwd_kernel(const SmallAttnParams p) {
+__global__ void __launch_bounds__(2 * kThreads, 4) k3s_attn_bwd_kernel(const SmallAttnParams p) {
     __shared__ __align__(16) float sQ[kHG * kOpFloats], sK[kHG * kOpFloats], sV[kHG * kOpFloats], sdO[kHG * kOpFloats];
     __shared__ float sLse[kHG * kRows], sDel[kHG * kRows];
     __shared__ __align__(16) __nv_bfloat16 sB[kHG * kRows * kBP];
@@ -199,23 +204,25 @@ __global__ void __launch_bounds__(kThreads, 8) k3s_attn_bwd_kernel(const SmallAt
     const int t0 = p.tok_off[g];
     const int Tg = p.tok_off[g + 1] - t0;
     if (Tg > p.small_t || Tg <= 0) return;                 // the tensor-core kernel's graph
-    const int nthr = min(kThreads, kHG * ((Tg + 7) & ~7));
-    if ((int)threadIdx.x >= nthr) return;
+    const int half = (int)threadIdx.x / kThreads, lt = (int)threadIdx.x - half * kThreads;
+    const int nhalf = min(kThreads, kHG * ((Tg + 7) & ~7));  // whole warps (8 rows each) that hold a live row, per pass
+    if (lt >= nhalf) return;
+    const int nthr = 2 * nhalf, sid = half * nhalf + lt;     // compact index of this thread among the live ones
     const int h0 = hg * kHG, plane0 = g * p.H + h0;
     const int HD = p.H * kD;
-    stage_bias4(p.bias, p.T, p.Tp, plane0, Tg, sB, nthr);
-    stage_heads(p.q, p.qkv_stride, t0, Tg, h0, sQ, nthr);
-    stage_heads(p.k, p.qkv_stride, t0, Tg, h0, sK, nthr);
-    stage_heads(p.v, p.qkv_stride, t0, Tg, h0, sV, nthr);
-    stage_heads(p.dout, HD, t0, Tg, h0, sdO, nthr);
-    const int t = threadIdx.x >> 2, hq = threadIdx.x & 3;
+    stage_bias4(p.bias, p.T, p.Tp, plane0, Tg, sB, nthr, sid);
+    stage_heads(p.q, p.qkv_stride, t0, Tg, h0, sQ, nthr, sid);
+    stage_heads(p.k, p.qkv_stride, t0, Tg, h0, sK, nthr, sid);
+    stage_heads(p.v, p.qkv_stride, t0, Tg, h0, sV, nthr, sid);
+    stage_heads(p.dout, HD, t0, Tg, h0, sdO, nthr, sid);
+    const int t = lt >> 2, hq = lt & 3;
     const bool live = t < Tg;
     const int h = h0 + hq, plane = plane0 + hq;
     const float sl2 = p.scale * kL2e;
     const float ik = kDrop ? p.drop.inv_keep : 1.0f;
     uint32_t seed_lo = 0, seed_hi = 0;
     if (kDrop) attn_drop_fold_seed(p.drop, seed_lo, seed_hi);
-    if (live) {
+    if (live && half == 0) {
         const uint4 *og = reinterpret_cast<const uint4 *>(p.o + (size_t)(t0 + t) * HD + h * kD);
         const uint4 *dg = reinterpret_cast<const uint4 *>(p.dout + (size_t)(t0 + t) * HD + h * kD);
         float d = 0.f;
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 8) k3s_attn_bwd_kernel(const SmallAt
     const float *Qh = sQ + hq * kOpFloats, *Kh = sK + hq * kOpFloats, *Vh = sV + hq * kOpFloats, *dOh = sdO + hq * kOpFloats;
     const float *Lh = sLse + hq * kRows, *Dh = sDel + hq * kRows;
     // ---- pass 1: row t
-    {
+    if (half == 0) {
         float q[kD], dO[kD], dq[kD];
 #pragma unroll
         for (int e = 0; e < kD; ++e) {
@@ -278,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 8) k3s_attn_bwd_kernel(const SmallAt
         store24(p.dq + (size_t)(t0 + t) * p.dqkv_stride + h * kD, dq, p.scale);
     }
     // ---- pass 2: column t
-    {
+    else {
         float k[kD], v[kD], dk[kD], dv[kD];
 #pragma unroll
         for (int e = 0; e < kD; ++e) {
@@ -315,8 +322,8 @@ int32_t launch_small_attn_fwd(const SmallAttnParams &p, int B, cudaStream_t s) {
 
 int32_t launch_small_attn_bwd(const SmallAttnParams &p, int B, cudaStream_t s) {
     const int grid = B * (p.H / kHG);
-    if (p.drop.th16) k3s_attn_bwd_kernel<true><<<grid, kThreads, 0, s>>>(p);
-    else k3s_attn_bwd_kernel<false><<<grid, kThreads, 0, s>>>(p);
+    if (p.drop.th16) k3s_attn_bwd_kernel<true><<<grid, 2 * kThreads, 0, s>>>(p);
+    else k3s_attn_bwd_kernel<false><<<grid, 2 * kThreads, 0, s>>>(p);
     MOBGT_LAUNCH_OK("k3s_attn_bwd_kernel");
     return MOBGT_OK;
 }
