@@ -145,3 +145,22 @@ def test_head_split_is_even_and_bounded():
     for M, V in ((256, 60001), (4096, 125000), (4096, 1000000), (1, 97), (1024, 125000), (130, 3680)):
         ns = ops.head_split(M, V)
         assert ns % 2 == 0 and 2 <= ns <= 160, (M, V, ns)
+
+
+def test_flat_parameter_order_groups_qkv_and_puts_the_head_last():
+    """Graphormer._flat_param_order (the layout of the flat parameter / gradient buffers): every parameter exactly once, the
+    q | k | v weights (and biases) of a layer adjacent — one GEMM / column-sum output writes all three gradients — and
+    out_proj.weight last, so that what remains after its early all-reduce is one contiguous range."""
+    from mobgt_b200 import model, synth
+    w = synth.make_world("tiny", seed=1)
+    m = model.Graphormer(dataset_name="toyotagraph", world=w, n_layers=2, num_heads=8, hidden_dim=128, dropout_rate=0.1,
+                         intput_dropout_rate=0.1, weight_decay=0.01, ffn_dim=256, warmup_updates=10, tot_updates=100, peak_lr=2e-4,
+                         end_lr=1e-9, edge_type="multi_hop", multi_hop_max_dist=20, attention_dropout_rate=0.1)
+    order = m._flat_param_order()
+    assert sorted(id(p) for p in order) == sorted(id(p) for p in m.parameters())
+    pos = {id(p): i for i, p in enumerate(order)}
+    for layer in m.layers:
+        a = layer.self_attention
+        assert pos[id(a.linear_k.weight)] == pos[id(a.linear_q.weight)] + 1 and pos[id(a.linear_v.weight)] == pos[id(a.linear_q.weight)] + 2
+        assert pos[id(a.linear_k.bias)] == pos[id(a.linear_q.bias)] + 1 and pos[id(a.linear_v.bias)] == pos[id(a.linear_q.bias)] + 2
+    assert order[-1] is m.out_proj.weight
