@@ -168,6 +168,22 @@ int32_t mobgt_attn_bwd(const void *q, const void *k, const void *v, int64_t qkv_
                        void *dq, void *dk, void *dv, int64_t dqkv_row_stride, void *dbias, int32_t mode, float drop_p,
                        uint64_t seed, const void *seed_dev, void *stream);
 
+/* K3 in fp32 mode: the same attention core (model_fqandtoyo.py:1693-1706) with fp32 q / k / v / bias / out and fp32 math
+ * (IEEE expf / logf, SIMT), for graphs of any size up to 513 tokens — the arithmetic of the reference's `--precision 32`
+ * (Lightning's default).  It exists for the first half of the parity contract ("within 1e-5 relative in fp32 mode"): the
+ * tensor-core kernels above round their operands to bf16 by construction.  Same packed layout, same dropout mask (seed, plane,
+ * row, column) as mobgt_attn_fwd; lse is the natural-log row normaliser.  dbias f32 [B,H,T,Tp]: mode 0 overwritten, mode 1
+ * added to (only the live cells of a graph are touched); feed it to mobgt_bias_bwd with dbias_dtype MOBGT_F32, n_layers 1.
+ * Bitwise reproducible (fixed-order shuffle reductions, no atomics). */
+int32_t mobgt_attn_f32_fwd(const float *q, const float *k, const float *v, int64_t qkv_row_stride, const float *bias,
+                           const int32_t *tok_off, int32_t B, int32_t H, int32_t ntok, int32_t T, int32_t Tp, int32_t t_max_host,
+                           float scale, float drop_p, uint64_t seed, const void *seed_dev, float *out, float *lse, void *stream);
+int32_t mobgt_attn_f32_bwd(const float *q, const float *k, const float *v, int64_t qkv_row_stride, const float *bias,
+                           const float *o, const float *dout, const float *lse, const int32_t *tok_off, int32_t B, int32_t H,
+                           int32_t ntok, int32_t T, int32_t Tp, int32_t t_max_host, float scale, float *dq, float *dk, float *dv,
+                           int64_t dqkv_row_stride, float *dbias, int32_t mode, float drop_p, uint64_t seed, const void *seed_dev,
+                           void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * K4 — node-embedding gather / sum and the deterministic segmented scatter-add backward.
  * Replaces model_fqandtoyo.py:1257-1269 (per-node table look-ups) and :1288-1344 (degree encoders,

@@ -37,6 +37,10 @@ SIGNATURES = {
                        c_p, c_p, c_p, c_p],
     "mobgt_attn_bwd": [c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_p,
                        c_p, c_p, c_i64, c_p, c_i32, c_f32, ctypes.c_uint64, c_p, c_p],
+    "mobgt_attn_f32_fwd": [c_p, c_p, c_p, c_i64, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, ctypes.c_uint64, c_p,
+                           c_p, c_p, c_p],
+    "mobgt_attn_f32_bwd": [c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_p, c_p, c_p,
+                           c_i64, c_p, c_i32, c_f32, ctypes.c_uint64, c_p, c_p],
     "mobgt_embed_gather_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_p, c_i32, c_p],
     "mobgt_embed_sum_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_p, c_i32, c_p],
     "mobgt_segment_sum": [c_p, c_i32, c_i64, c_i32, c_i32, c_p, c_p, c_i32, c_p, c_i32, c_p, c_i64, c_p],

@@ -38,7 +38,7 @@ def build_parser():
     t = parser.add_argument_group("pl.Trainer")                         # entry.py:53
     t.add_argument("--gpus", type=int, default=1)
     t.add_argument("--accelerator", type=str, default=None)             # "ddp" -> one rank per GPU (launched by torchrun)
-    t.add_argument("--precision", type=int, default=16)                 # 16 -> bf16 GEMMs/attention (the reference: fp16 AMP)
+    t.add_argument("--precision", type=int, default=16, choices=(16, 32))   # 16: bf16 GEMMs / attention (the reference: fp16 AMP); 32: fp32 path
     t.add_argument("--max_epochs", type=int, default=1)
     t.add_argument("--max_steps", type=int, default=None)               # overwritten from tot_updates (entry.py:57)
     t.add_argument("--check_val_every_n_epoch", type=int, default=1)
@@ -125,7 +125,7 @@ def cli_main(argv=None):
         intput_dropout_rate=args.intput_dropout_rate, weight_decay=args.weight_decay, ffn_dim=args.ffn_dim,
         dataset_name=args.dataset_name, warmup_updates=args.warmup_updates, tot_updates=args.tot_updates, peak_lr=args.peak_lr,
         end_lr=args.end_lr, edge_type=args.edge_type, multi_hop_max_dist=args.multi_hop_max_dist, flag=args.flag,
-        flag_m=args.flag_m, flag_step_size=args.flag_step_size, world=world).to(dev)
+        flag_m=args.flag_m, flag_step_size=args.flag_step_size, world=world, precision=args.precision).to(dev)
     if args.checkpoint_path != "":                                      # entry.py:71-93 (strict=False)
         sd = torch.load(args.checkpoint_path, map_location=dev)
         model.load_state_dict(sd.get("state_dict", sd), strict=False)

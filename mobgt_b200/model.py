@@ -217,6 +217,18 @@ class EncoderLayer(nn.Module):
         w2, b2 = w16.get((layer, "f2")) if w16 is not None else (None, None)
         return ops.ffn_block(y16, self.ffn, w1, w2, b2, x1, self.ffn_norm2, self.ffn_dropout.p, self.training, "both")   # :1644-1656, :1737-1741
 
+    def forward_f32(self, x, bias_slot, layer=0):
+        """precision=32: the same layer with fp32 operands everywhere (IEEE fp32 GEMMs, the fp32 attention kernels
+        csrc/k3_attn_f32.cu, K6 LayerNorm) — the arithmetic of the reference without AMP."""
+        a = self.self_attention
+        wq = torch.cat([a.linear_q.weight, a.linear_k.weight, a.linear_v.weight], 0)
+        bq = torch.cat([a.linear_q.bias, a.linear_k.bias, a.linear_v.bias], 0)
+        y = ops.BiasedAttentionF32.apply(F.linear(x, wq, bq), bias_slot, layer,
+                                         a.attention_dropout_rate if self.training else 0.0)             # :1693-1706
+        x = x + self.self_attention_dropout(a.output_layer(y))                                           # :1708, :1731-1735
+        x = x + self.ffn_dropout(self.ffn(ops.layer_norm(x, self.ffn_norm1)))                            # :1737-1740
+        return ops.layer_norm(x, self.ffn_norm2)                                                         # :1741
+
 
 def gradient_tail_loss(inputs, targets, alpha=0.25, beta=1, k=1):
     """model_fqandtoyo.py:545-550 — the K7 kernel (csrc/k7_loss.cu); only the reference's own beta = k = 1 is built."""
@@ -229,14 +241,20 @@ class Graphormer(nn.Module):
     def __init__(self, n_layers, num_heads, hidden_dim, dropout_rate, intput_dropout_rate, weight_decay, ffn_dim,
                  dataset_name, warmup_updates, tot_updates, peak_lr, end_lr, edge_type, multi_hop_max_dist,
                  attention_dropout_rate, flag=False, flag_m=3, flag_step_size=1e-3, flag_mag=1e-3, lr_step=2, world=None,
-                 tf32=True):
-        """tf32: run the GEMMs that stay in fp32 storage (GCN dense parts modelGNN.py:39, user fuse, cat_decoder, out_proj) on
+                 tf32=True, precision=16):
+        """precision: the pl.Trainer flag of the reference (README.md:62 runs `--precision 16`).  16: bf16 GEMMs / attention on
+        the tensor cores, fp32 residual stream, LayerNorms and losses (the AMP split; parity 2e-2).  32: fp32 operands and
+        arithmetic everywhere — IEEE fp32 GEMMs, fp32 attention kernels (csrc/k3_attn_f32.cu), fp32 bias; parity 1e-5 against
+        the reference's fp32 statement.  It is the full-precision / verification mode, not the benchmarked one.
+        tf32: run the GEMMs that stay in fp32 storage (GCN dense parts modelGNN.py:39, user fuse, cat_decoder, out_proj) on
         the TF32 tensor cores instead of SIMT FFMA.  The reference runs them in fp16 under `--precision 16` autocast
         (README.md:62), so TF32 (10-bit mantissa, fp32 range and accumulate) is at least as precise; tf32=False keeps IEEE fp32."""
         super().__init__()
-        self.tf32 = bool(tf32)
-        if self.tf32:
-            ops.enable_tf32()
+        if precision not in (16, 32):
+            raise NotImplementedError(f"precision={precision!r}: 16 (bf16 tensor-core path) or 32 (fp32 path)")
+        self.precision = int(precision)
+        self.tf32 = bool(tf32) and self.precision == 16
+        ops.enable_tf32(self.tf32)          # precision=32 asks for IEEE fp32 GEMMs (forward AND backward: a process-wide switch)
         if world is None:
             raise ValueError("Graphormer needs a PoiWorld (the dataset tables the reference reads from ../dataset/<name>/raw, "
                              "model_fqandtoyo.py:791-832)")
@@ -357,15 +375,20 @@ class Graphormer(nn.Module):
         """model_fqandtoyo.py:1143-1364 up to the input of the two heads: z [B, 2*hidden+64] fp32 (user fuse of token 0,
         final LayerNorm, ELU, output dropout) — the operand of `out_proj` / `cat_decoder` and of the fused K5 head."""
         b = self._packed(batched_data)
-        tok = self.node_tokens(b)
-        slot = ops.BiasSlot(b, len(self.layers))
+        f32 = self.precision == 32
+        tok = self.node_tokens(b, torch.float32 if f32 else torch.bfloat16)
+        slot = ops.BiasSlot(b, len(self.layers), dtype=torch.float32 if f32 else torch.bfloat16)
         x = ops.BiasLink.apply(self.input_dropout(tok).float(), slot, self.rel_pos_encoder.weight, self.poi_pos_encoder.weight,
                                self.edge_encoder.weight, self.edge_dis_encoder.weight,
                                self.graph_token_virtual_distance.weight)                                 # K2 (:1143-1216), :1347
-        x16 = x.to(torch.bfloat16)
-        self._w16.refresh()
-        for li, layer in enumerate(self.layers):                                                         # :1348-1352
-            x, x16 = layer(x, x16, slot, li, self._w16)
+        if f32:
+            for li, layer in enumerate(self.layers):                                                     # :1348-1352
+                x = layer.forward_f32(x, slot, li)
+        else:
+            x16 = x.to(torch.bfloat16)
+            self._w16.refresh()
+            for li, layer in enumerate(self.layers):                                                     # :1348-1352
+                x, x16 = layer(x, x16, slot, li, self._w16)
         z0 = x.index_select(0, b.tok_off[:-1].long()).float()                                            # output[:, 0, :]
         user_embedding = self.user_embed_model(b.user.view(-1) - 1)                                      # :1239
         z = self.embed_fuse_model3(z0, user_embedding)                                                   # :1356 (token 0 only)
@@ -402,7 +425,10 @@ class Graphormer(nn.Module):
         # the loss kernels, and a bf16 tensor-core GEMM forward and backward
         # (class count padded to a multiple of 8 with zero weight rows; the loss kernels ignore the padding columns)
         V = self.out_proj.weight.shape[0]
-        poi_logits = ops.linear_bf16(z.to(torch.bfloat16), self.out_proj, *self._w16.get(("head", "out")))
+        if self.precision == 32:
+            poi_logits = self.out_proj(z)                                                                # fp32 logits through K7
+        else:
+            poi_logits = ops.linear_bf16(z.to(torch.bfloat16), self.out_proj, *self._w16.get(("head", "out")))
         if self.dataset_name == "toyotagraph":
             loss1 = ops.gradient_tail_loss(cat_logits, self.cat_target, 0.1)                            # :1464-1469
             loss2 = ops.log_softmax_nll_loss(poi_logits, b.y, ignore_index=0, n_classes=V)   # :1425 + data.py:165 NLLLoss(ignore_index=0)

@@ -176,12 +176,69 @@ class BiasedAttention(torch.autograd.Function):
         return dqkv, None, None, None
 
 
+def attn_f32_fwd_raw(qkv, bias, batch, scale=None, drop_p=0.0, seed=0):
+    """fp32 mode of K3 (csrc/k3_attn_f32.cu): qkv f32 [ntok, 3*H*24], bias f32 [B,H,T,Tp] -> (out f32 [ntok, H*24], lse f32 [ntok,H])."""
+    ntok = qkv.shape[0]
+    B, H, T, Tp = bias.shape
+    D = H * HEAD_DIM
+    assert qkv.dtype == torch.float32 and bias.dtype == torch.float32 and qkv.shape[1] == 3 * D and qkv.is_contiguous()
+    alloc = torch.zeros if getattr(batch, "padded", False) else torch.empty
+    out = alloc(ntok, D, dtype=torch.float32, device=qkv.device)
+    lse = alloc(ntok, H, dtype=torch.float32, device=qkv.device)
+    scale = float(HEAD_DIM ** -0.5) if scale is None else float(scale)
+    base = qkv.data_ptr()
+    _C.call("mobgt_attn_f32_fwd", base, base + 4 * D, base + 8 * D, 3 * D, _C.ptr(bias), _C.ptr(batch.tok_off), B, H, ntok, T, Tp,
+            int(batch.N) + 1, scale, float(drop_p), int(seed), _C.ptr(_seed_dev) if drop_p > 0 else None, _C.ptr(out), _C.ptr(lse),
+            _C.stream_ptr())
+    return out, lse
+
+
+def attn_f32_bwd_raw(qkv, bias, out, dout, lse, batch, dbias, accumulate, scale=None, drop_p=0.0, seed=0):
+    """-> dqkv f32 [ntok, 3*H*24]; dbias f32 [B,H,T,Tp] overwritten (accumulate=0) or added to (accumulate=1), live cells only."""
+    B, H, T, Tp = bias.shape
+    D = H * HEAD_DIM
+    assert dout.is_contiguous() and out.is_contiguous() and dbias.shape == bias.shape and dbias.is_contiguous()
+    assert dbias.dtype == torch.float32 and dout.dtype == torch.float32 and accumulate in (0, 1)
+    dqkv = torch.zeros_like(qkv) if getattr(batch, "padded", False) else torch.empty_like(qkv)
+    scale = float(HEAD_DIM ** -0.5) if scale is None else float(scale)
+    base, dbase = qkv.data_ptr(), dqkv.data_ptr()
+    _C.call("mobgt_attn_f32_bwd", base, base + 4 * D, base + 8 * D, 3 * D, _C.ptr(bias), _C.ptr(out), _C.ptr(dout), _C.ptr(lse),
+            _C.ptr(batch.tok_off), B, H, qkv.shape[0], T, Tp, int(batch.N) + 1, scale, dbase, dbase + 4 * D, dbase + 8 * D, 3 * D,
+            _C.ptr(dbias), int(accumulate), float(drop_p), int(seed), _C.ptr(_seed_dev) if drop_p > 0 else None, _C.stream_ptr())
+    return dqkv
+
+
+class BiasedAttentionF32(torch.autograd.Function):
+    """BiasedAttention in fp32 mode (`Graphormer(precision=32)`): fp32 operands, bias and arithmetic.  The layers' dS are added
+    into ONE fp32 [B,H,T,Tp] buffer (each cell has one writer per layer and the layers' backwards run one after the other, so the
+    sum has a fixed order); BiasLink hands it to mobgt_bias_bwd."""
+
+    @staticmethod
+    def forward(ctx, qkv, bias_slot, layer, drop_p=0.0):
+        seed = _next_drop_seed() if drop_p > 0 else 0
+        out, lse = attn_f32_fwd_raw(qkv, bias_slot.bias, bias_slot.batch, drop_p=drop_p, seed=seed)
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.slot, ctx.layer, ctx.drop = bias_slot, layer, (drop_p, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse = ctx.saved_tensors
+        slot = ctx.slot
+        if slot.planes is None:
+            slot.planes = torch.zeros_like(slot.bias)
+        dqkv = attn_f32_bwd_raw(qkv, slot.bias, out, dout.contiguous(), lse, slot.batch, slot.planes, 1, drop_p=ctx.drop[0],
+                                seed=ctx.drop[1])
+        slot.written.add(ctx.layer)
+        return dqkv, None, None, None
+
+
 class BiasSlot:
     """What the six encoder layers of one forward share: the batch, the bias tensor (written once by K2) and, in backward,
-    the stack of per-layer bf16 dS planes."""
+    the stack of per-layer bf16 dS planes (dtype bf16) or the one fp32 sum of the layers' dS (dtype fp32: precision=32)."""
 
-    def __init__(self, batch, n_layers, bias=None):
-        self.bias, self.batch, self.n_layers, self.planes, self.written = bias, batch, n_layers, None, set()
+    def __init__(self, batch, n_layers, bias=None, dtype=torch.bfloat16):
+        self.bias, self.batch, self.n_layers, self.planes, self.written, self.dtype = bias, batch, n_layers, None, set(), dtype
 
 
 class BiasLink(torch.autograd.Function):
@@ -194,7 +251,7 @@ class BiasLink(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tok, slot, R, Ppos, E, W, tvd):
         Rc, Pc, Ec, Wc, tc = (t.detach().float().contiguous() for t in (R, Ppos, E, W, tvd))
-        slot.bias = bias_fwd_raw(slot.batch, Rc, Pc, Ec, Wc.view(-1), tc.view(-1), torch.bfloat16)
+        slot.bias = bias_fwd_raw(slot.batch, Rc, Pc, Ec, Wc.view(-1), tc.view(-1), slot.dtype)
         ctx.slot, ctx.num_bins = slot, Ppos.shape[0]
         ctx.save_for_backward(Ec, Wc)
         return tok.view_as(tok)
@@ -205,9 +262,10 @@ class BiasLink(torch.autograd.Function):
         planes, slot.planes = slot.planes, None
         if planes is None:                      # no attention layer took part in this backward
             return dtok, None, None, None, None, None, None
-        for l in range(slot.n_layers):          # a layer whose backward never ran contributes nothing
-            if l not in slot.written:
-                planes[l].zero_()
+        if planes.dtype == torch.bfloat16:
+            for l in range(slot.n_layers):      # a layer whose backward never ran contributes nothing
+                if l not in slot.written:
+                    planes[l].zero_()
         E, W = ctx.saved_tensors
         dR, dP, dE, dW, dt = bias_bwd_raw(slot.batch, planes, E, W.view(-1), ctx.num_bins)
         dR[0].zero_()                           # padding_idx rows (never indexed by a packed pair anyway)
@@ -894,11 +952,11 @@ def spmm(A, At, S, bias=None, slope=None):
 
 
 # ----------------------------------------------------------------------------------------------- K7
-def enable_tf32():
+def enable_tf32(on=True):
     """The few GEMMs that stay in fp32 storage (GCN dense parts modelGNN.py:39, user fuse, cat_decoder, out_proj) run on the
-    TF32 tensor cores.  This is cuBLAS's process-wide switch: it is set once, when a model asks for it (Graphormer(tf32=True)),
-    not inside forward."""
-    torch.backends.cuda.matmul.allow_tf32 = True
+    TF32 tensor cores.  This is cuBLAS's process-wide switch: it is set once, when a model asks for it (Graphormer(tf32=True);
+    Graphormer(precision=32) and tf32=False ask for IEEE fp32 instead), not inside forward."""
+    torch.backends.cuda.matmul.allow_tf32 = bool(on)
 
 
 def _loss_ws(B, V, dev):

@@ -373,7 +373,7 @@ def test_any_multi_hop_max_dist(lib_built, dk):
 
 
 # ------------------------------------------------------------------------------------------------------- model level
-def _pair(dataset_name, cfg, items_spec, n_layers=2, ffn=256, seed=1, dk=20, scale_tables=True):
+def _pair(dataset_name, cfg, items_spec, n_layers=2, ffn=256, seed=1, dk=20, scale_tables=True, **model_kw):
     """oracle model + product model with the same weights, oracle batch + product batch of the same items."""
     from mobgt_b200 import collator, model, synth
     w = synth.make_world(cfg, seed=seed, dataset_name=dataset_name)
@@ -391,7 +391,7 @@ def _pair(dataset_name, cfg, items_spec, n_layers=2, ffn=256, seed=1, dk=20, sca
                 emb.weight.mul_(0.3)
                 emb.weight[0].zero_()
             om.edge_dis_encoder.weight.mul_(0.3)
-    pm = model.Graphormer(dataset_name=dataset_name, world=w, **hp).cuda().eval()
+    pm = model.Graphormer(dataset_name=dataset_name, world=w, **hp, **model_kw).cuda().eval()
     missing, _ = pm.load_state_dict(om.state_dict(), strict=False)
     assert not missing, missing
     ob = mo.collate([mo.preprocess_item(it, hop_cap=max(20, dk)) for it in items], w, multi_hop_max_dist=dk, rel_pos_max=1024)
