@@ -14,6 +14,9 @@ Workloads (`--workload`, BASELINE.json configs):
                          through 8 DIFFERENT batches, so the shapes vary from step to step as in a real epoch
   c4-gowalla256          configs[3]: gowalla_nevda-shaped world (3 679 POIs, 253 categories), graphs <= 256 nodes (natural law),
                          GradientTailLoss, data parallel;  c4-dense256: every graph at 256 nodes (T = 257: the fold path of K3)
+  c4-gowalla-real        the same model on the REAL Gowalla-Nevada data set the reference ships (gowalla_nevda.7z: 3 679 POIs,
+                         4 970 train trajectories of 2 .. 512 nodes in the reference's queue order), frozen as
+                         tests/golden/gowalla_nevda_real.npz by the reference's own dataset code (tests/golden/make_gowalla_real.py)
   c5-eval                configs[4]: the evaluation head over a 1 M-POI vocabulary sharded across the N GPUs, 4 096 rows per
                          step, fused GEMM + top-10 + rank (K5), all-gather / merge over NVLink; metric = eval rows / s
   c3-preprocess          configs[2]: K1 (floyd_warshall + gen_edge_input) over 100 000 graphs <= 512 nodes; metric = graphs / s
@@ -104,13 +107,32 @@ TRAIN_WORKLOADS = {
     "c2-natural": ("c2", "toyotagraph", 128, None, 8),
     "c4-gowalla256": ("c4", "gowalla_nevda", 256, None, 8),
     "c4-dense256": ("c4", "gowalla_nevda", 256, 256, 1),
+    # the REAL Gowalla-Nevada data set the reference ships (gowalla_nevda.7z), frozen by tests/golden/make_gowalla_real.py through
+    # the reference's own owndata.GowallaGraph.process / calculate_laplacian_matrix: consecutive 256-graph batches of the train
+    # split in the reference's queue order (graphs of more than 512 nodes dropped, collator.py:313)
+    "c4-gowalla-real": ("real", "gowalla_nevda", 512, None, 8),
 }
-WORLD_NOTE = {"c2": "toyotagraph-shaped P=60000 C=300 U=995", "c4": "gowalla_nevda-shaped P=3679 C=253 U=1080"}
+WORLD_NOTE = {"c2": "toyotagraph-shaped P=60000 C=300 U=995", "c4": "gowalla_nevda-shaped P=3679 C=253 U=1080",
+              "real": "real Gowalla-Nevada (gowalla_nevda.7z of the reference): P=3679 C=253 U=1080, 4 970 train trajectories in the "
+                      "reference's queue order (tests/golden/gowalla_nevda_real.npz)"}
+DATA_NOTE = {"real": "real trajectories (the reference's gowalla_nevda.7z via tests/golden/gowalla_nevda_real.npz), random-init weights"}
+_REAL = {}
+
+
+def real_dataset():
+    """(PoiWorld, {split: items}) of the committed real-data fixture (mobgt_b200.owndata.unpack_dataset)."""
+    if not _REAL:
+        from mobgt_b200 import owndata
+        world, splits = owndata.unpack_dataset(np.load(os.path.join(ROOT, "tests", "golden", "gowalla_nevda_real.npz")))
+        _REAL.update(world=world, splits={k: [it for it in v if len(it.x) <= 512] for k, v in splits.items()})
+    return _REAL["world"], _REAL["splits"]
 
 
 def make_world_for(workload):
     from mobgt_b200 import synth
     cfg, ds, _, _, _ = TRAIN_WORKLOADS[workload]
+    if cfg == "real":
+        return real_dataset()[0]
     return synth.make_world(cfg, seed=1, dataset_name=ds)
 
 
@@ -118,6 +140,10 @@ def make_workload(workload, world, B, rank, seed=1, batch_id=0):
     """The raw items of batch `batch_id` of rank `rank` (disjoint across ranks and batches)."""
     from mobgt_b200 import synth
     cfg, _, cap, n_fixed, nb = TRAIN_WORKLOADS[workload]
+    if cfg == "real":                 # 19 batches of 256 in the split: ranks / batches past the end wrap around
+        items = real_dataset()[1]["train"]
+        start = (rank * nb + batch_id) * B
+        return [items[(start + j) % len(items)] for j in range(B)]
     return synth.make_items(world, B, cap, seed=seed, cfg_id=2 if cfg == "c2" else 4, n_fixed=n_fixed,
                             start=(rank * nb + batch_id) * B)
 
@@ -234,7 +260,7 @@ def run_reference(args):
     cfg = TRAIN_WORKLOADS[args.workload][0]
     line = {"metric": "train_graphs_per_sec", "value": r["value"], "unit": "graphs/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "dtype": "f32", "data": DATA_NOTE.get(cfg, "synthetic"), "impl": "reference",
             "config": {"workload": args.workload, "world": WORLD_NOTE[cfg], "hidden": 128, "layers": 6,
                        "heads": 8, "ffn": 1024, "multi_hop_max_dist": 20, "graphs_per_gpu": args.batch},
             "cpu_baseline": {"value": r["value"], "unit": "graphs/s", "cores": r["cores"], "kind": "port",
@@ -510,7 +536,7 @@ def run_ours(args):
         graphs = B * world_size
         line = {"metric": "train_graphs_per_sec", "value": graphs * args.steps / (ms / 1e3), "unit": "graphs/s",
                 "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": DATA_NOTE.get(cfg, "synthetic"),
                 "config": {"workload": args.workload, "world": WORLD_NOTE[cfg], "hidden": 128, "layers": 6,
                            "heads": 8, "ffn": 1024, "multi_hop_max_dist": 20, "graphs_per_gpu": B,
                            "tokens_per_gpu": tokens, "distinct_batches": nbatches, "size_buckets": bool(bucket), "parallelism": f"dp{world_size}",
@@ -781,7 +807,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2-dense128",
-                    choices=["c2-dense128", "c2-natural", "c4-gowalla256", "c4-dense256", "c5-eval", "c3-preprocess"])
+                    choices=["c2-dense128", "c2-natural", "c4-gowalla256", "c4-dense256", "c4-gowalla-real", "c5-eval", "c3-preprocess"])
     ap.add_argument("--vocab", type=int, default=1_000_000, help="c5-eval: POI vocabulary (sharded across the GPUs)")
     ap.add_argument("--rows", type=int, default=4096, help="c5-eval: z rows per step")
     ap.add_argument("--graphs", type=int, default=100_000, help="c3-preprocess: graphs per pass")

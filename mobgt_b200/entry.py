@@ -58,6 +58,12 @@ def build_parser():
     s.add_argument("--train_graphs", type=int, default=2048)
     s.add_argument("--test_graphs", type=int, default=512)
     s.add_argument("--n_fixed", type=int, default=None, help="every synthetic graph gets exactly this many nodes")
+    s.add_argument("--data_root", type=str, default=None,
+                   help="a dataset directory in the reference's on-disk format (<root>/raw/{train,test}.pickle, *_idx.pkl, "
+                        "Graph_{poi,dist,cat}.csv: ../dataset/<name> of the reference) instead of synthetic data")
+    s.add_argument("--data_npz", type=str, default=None,
+                   help="the same data set in the compact form of mobgt_b200.owndata.pack_dataset (e.g. the real Gowalla-Nevada "
+                        "fixture tests/golden/gowalla_nevda_real.npz)")
     s.add_argument("--limit_train_steps", type=int, default=None, help="stop after this many optimizer steps (smoke runs)")
     s.add_argument("--no_cuda_graph", action="store_true", help="never capture the step in a CUDA graph")
     s.add_argument("--eval_vocab_parallel", action="store_true",
@@ -96,11 +102,24 @@ def cli_main(argv=None):
     torch.manual_seed(args.seed)                                        # pl.seed_everything (entry.py:60)
     np.random.seed(args.seed)
 
-    shape = args.synthetic or DATASET_DEFAULT_SHAPE.get(args.dataset_name, "c2")
-    world = synth.make_world(shape, seed=args.seed, dataset_name=args.dataset_name)
-    cap = synth.CONFIGS[shape]["cap"]
-    train = synth.make_items(world, args.train_graphs, cap, seed=args.seed, cfg_id=11, n_fixed=args.n_fixed)
-    test = synth.make_items(world, args.test_graphs, cap, seed=args.seed, cfg_id=12, n_fixed=args.n_fixed)
+    if args.data_root or args.data_npz:                                 # the reference's data set (owndata.py, model ctor tables)
+        from . import owndata
+        if args.data_npz:
+            world, splits = owndata.unpack_dataset(np.load(args.data_npz))
+            world.dataset_name = args.dataset_name
+            train, test = splits["train"], splits["test"]
+        else:
+            raw = os.path.join(args.data_root, "raw")
+            world = owndata.load_world(raw, args.dataset_name)
+            train, test = owndata.load_items(raw, "train"), owndata.load_items(raw, "test")
+        if rank == 0:
+            print(f"data set: {len(train)} train / {len(test)} test trajectories, {world.P} POIs, {world.C} categories")
+    else:
+        shape = args.synthetic or DATASET_DEFAULT_SHAPE.get(args.dataset_name, "c2")
+        world = synth.make_world(shape, seed=args.seed, dataset_name=args.dataset_name)
+        cap = synth.CONFIGS[shape]["cap"]
+        train = synth.make_items(world, args.train_graphs, cap, seed=args.seed, cfg_id=11, n_fixed=args.n_fixed)
+        test = synth.make_items(world, args.test_graphs, cap, seed=args.seed, cfg_id=12, n_fixed=args.n_fixed)
     latlon = torch.from_numpy(world.latlon).to(dev)
     ckw = dict(world=world, latlon_dev=latlon, multi_hop_max_dist=args.multi_hop_max_dist, rel_pos_max=args.rel_pos_max, device=dev)
 

@@ -35,3 +35,37 @@ def sessions(blob):
         for s in d[u]:
             flat.append(d[u][s])
     return flat
+
+
+# ---- digests shared by make_gowalla_real.py (computed there from the REFERENCE's own outputs) and tests/test_owndata.py
+ITEM_FIELDS = (("x", "int64"), ("edge_index", "int64"), ("edge_attr", "int64"), ("y", "int64"), ("time", "int64"),
+               ("time_normal", "float32"), ("user", "int64"), ("cat", "int64"))
+
+
+def items_digest(items):
+    """sha256 over every field of every item (shape + little-endian bytes), in order."""
+    import hashlib
+    import numpy as np
+    h = hashlib.sha256()
+    for it in items:
+        for name, dt in ITEM_FIELDS:
+            v = getattr(it, name)
+            a = np.ascontiguousarray(v.numpy() if hasattr(v, "numpy") else v).astype(dt)
+            h.update(name.encode() + str(a.shape).encode())
+            h.update(a.tobytes())
+    return h.hexdigest()
+
+
+def csr_dense_digest(csr, n):
+    """sha256 of the dense float32 [n, n] matrix a CSR triple stands for (row by row: never holds more than one row block)."""
+    import hashlib
+    import numpy as np
+    crow, col, val = (np.asarray(a) for a in csr)
+    h = hashlib.sha256()
+    for r0 in range(0, n, 256):
+        r1 = min(n, r0 + 256)
+        blk = np.zeros((r1 - r0, n), np.float32)
+        for r in range(r0, r1):
+            blk[r - r0, col[crow[r]:crow[r + 1]]] = val[crow[r]:crow[r + 1]]
+        h.update(blk.tobytes())
+    return h.hexdigest()
