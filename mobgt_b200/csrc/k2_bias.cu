@@ -252,8 +252,10 @@ __global__ void __launch_bounds__(512, 2) k2_bias_fwd_kernel(const K2Common c, c
 //   3. histogram   — lanes = (table: R | P) x (2 cells) x (8 heads): ONE read-modify-write per lane and step into
 //                    warp-private histograms laid out [key][cell slot][head] — no atomics, no cross-lane hazards; two
 //                    steps are in flight per lane (equal keys are merged in registers).
-//   Deviating bytes: shared-memory atomics into the CTA's small dEW table (features < 16), global atomics otherwise.
-// Per-CTA totals go to a partial buffer and are reduced in a fixed order (reproducible except for the rare-path atomics).
+//   Deviating bytes (the rare path): 64-bit FIXED-POINT integer atomics (value * 2^38) into the CTA's own small dEW table in
+//   global memory (features < 16) or into the launch-wide table (other features, rel_pos keys outside the plan).  Integer
+//   addition is associative, so the sums do not depend on the order in which the atomics land.
+// Per-CTA totals go to a partial buffer and are reduced in a fixed order: the whole backward is bitwise reproducible.
 constexpr int kSmallVocab = 16;   // edge features kept in the CTA's shared dEW table
 
 struct K2BwdPlan {
@@ -274,11 +276,18 @@ __host__ __device__ inline K2BwdPlan k2_bwd_plan(int T, int Tp, int hops, int nu
     p.stride = p.nEWs + p.nR + p.nP + kH;
     p.pitch = ((Tp + 27) / 32) * 32 + 4;
     p.per_warp = 2 * (p.nR + kH) + 2 * (p.nP + kH) + kH * p.pitch + 3 * p.pitch + kH;   // hR+trash | hP+trash | dsum | cinfo | cdev | dlist | t
-    p.cta_words = p.nEWs + (hops + 1) * 8 + 40;                            // sEW | XW | 1/sp table
+    p.cta_words = (hops + 1) * 8 + 40;                                     // XW | 1/sp table
     int w = (int)((227 * 1024 - 2048 - p.cta_words * 4) / (p.per_warp * 4));
     p.warps = w > 16 ? 16 : w;
     return p;
 }
+
+// rare-path accumulators: signed 64-bit fixed point, 38 fractional bits (resolution 3.6e-12, range +-3.3e7)
+constexpr double kFxScale = 274877906944.0, kFxInv = 1.0 / 274877906944.0;
+__device__ __forceinline__ void fx_add(long long *dst, float v) {
+    atomicAdd(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)__double2ll_rn((double)v * kFxScale));
+}
+__device__ __forceinline__ float fx_to_float(long long v) { return (float)((double)v * kFxInv); }
 
 constexpr uint32_t kInfoPair = 1u << 21, kInfoDev = 1u << 20, kInfoCol0 = 1u << 22, kInfoOvf = 1u << 23, kInfoUnreach = 1u << 24;
 
@@ -302,13 +311,14 @@ template <typename DT>
 __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, const DT *__restrict__ dB, int nlayers,
                                                              int64_t layer_stride, int num_bins,
                                                              const K2BwdPlan pl, float *__restrict__ partial,
-                                                             float *__restrict__ dEWfull, float *__restrict__ dR_overflow) {
+                                                             long long *__restrict__ ews64, long long *__restrict__ dEWfull64,
+                                                             long long *__restrict__ dR64) {
     extern __shared__ __align__(16) float sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int ty = lane >> 4, c2 = (lane >> 3) & 1, h = lane & 7;      // table (0 = R, 1 = P), cell slot, head
-    float *sEW = sm;                                              // [hops][16][8]
-    uint32_t *XW = reinterpret_cast<uint32_t *>(sm + pl.nEWs);    // [hops + 1][8]
-    float *invT = sm + pl.nEWs + (c.hops + 1) * 8;                // [40]: 1 / sp
+    long long *sEW = ews64 + (size_t)blockIdx.x * pl.nEWs;        // this CTA's [hops][16][8] table (global memory, zeroed by the host)
+    uint32_t *XW = reinterpret_cast<uint32_t *>(sm);              // [hops + 1][8]
+    float *invT = sm + (c.hops + 1) * 8;                          // [40]: 1 / sp
     float *wbase = sm + pl.cta_words;
     const uint32_t s_warp = (uint32_t)__cvta_generic_to_shared(wbase + (size_t)warp * pl.per_warp);
     const uint32_t s_hR = s_warp;                                 // [Rrows + 1][2][8]   (last row: trash)
@@ -322,7 +332,6 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
     const uint32_t key_shift = ty ? 16u : 0u;
     const uint32_t trashR = (uint32_t)pl.Rrows, trashP = (uint32_t)num_bins;
     const int hopw = c.hops >> 2;
-    for (int i = threadIdx.x; i < pl.nEWs; i += blockDim.x) sEW[i] = 0.f;
     for (int i = threadIdx.x; i < (c.hops + 1) * 8; i += blockDim.x) XW[i] = (i & 7) < hopw ? expected_word(i >> 3, i & 7) : 0u;
     for (int i = threadIdx.x; i < 40; i += blockDim.x) invT[i] = 1.0f / (float)max(i, 1);
     for (int i = threadIdx.x; i < nwarp * pl.per_warp; i += blockDim.x) wbase[i] = 0.f;
@@ -472,7 +481,7 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
             const uint32_t ent = lds_u32(s_dlist + (uint32_t)e * 4u);
             const int b = ent & 0xFFF;
             const float d = lds_f32(s_dsum + (uint32_t)h * pitch4 + (uint32_t)b * 4u);
-            if (ent & (1u << 12)) atomicAdd(dR_overflow + min(max((int)c.rel_pos[rowp + b], 0), kRelRows - 1) * kH + h, d);
+            if (ent & (1u << 12)) fx_add(dR64 + min(max((int)c.rel_pos[rowp + b], 0), kRelRows - 1) * kH + h, d);
             if (!(ent & (1u << 14))) continue;
             const uint32_t cd = lds_u32(s_cdev + (uint32_t)b * 4u);
             const int L = (cd >> 2) & 63, nd = cd & 3;
@@ -482,10 +491,10 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
                     const uint32_t en = (cd >> (8 + 12 * j)) & 4095u;
                     const int k = en >> 7, v = en & 127, x = k < L ? kDomEdge : 0;
                     if (v != 0) {
-                        if (v < kSmallVocab) atomicAdd(sEW + (k * kSmallVocab + v) * kH + h, dinv);
-                        else atomicAdd(dEWfull + ((size_t)k * kEdgeVocab + v) * kH + h, dinv);
+                        if (v < kSmallVocab) fx_add(sEW + (k * kSmallVocab + v) * kH + h, dinv);
+                        else fx_add(dEWfull64 + ((size_t)k * kEdgeVocab + v) * kH + h, dinv);
                     }
-                    if (x != 0) atomicAdd(sEW + (k * kSmallVocab + x) * kH + h, -dinv);
+                    if (x != 0) fx_add(sEW + (k * kSmallVocab + x) * kH + h, -dinv);
                 }
             } else {
                 const uint32_t *ei = reinterpret_cast<const uint32_t *>(c.edge_in + (rowp + b) * c.hops);
@@ -497,10 +506,10 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
                         const int v = (ew >> (8 * eb)) & 0xFF, x = (xw >> (8 * eb)) & 0xFF;
                         const int k = q * 4 + eb;
                         if (v != 0) {
-                            if (v < kSmallVocab) atomicAdd(sEW + (k * kSmallVocab + v) * kH + h, dinv);
-                            else atomicAdd(dEWfull + ((size_t)k * kEdgeVocab + min(v, kEdgeVocab - 1)) * kH + h, dinv);
+                            if (v < kSmallVocab) fx_add(sEW + (k * kSmallVocab + v) * kH + h, dinv);
+                            else fx_add(dEWfull64 + ((size_t)k * kEdgeVocab + min(v, kEdgeVocab - 1)) * kH + h, dinv);
                         }
-                        if (x != 0) atomicAdd(sEW + (k * kSmallVocab + x) * kH + h, -dinv);
+                        if (x != 0) fx_add(sEW + (k * kSmallVocab + x) * kH + h, -dinv);
                         df &= ~(0xFFu << (8 * eb));
                     }
                 }
@@ -513,7 +522,6 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
     __syncthreads();
     // CTA totals -> partial[blockIdx]
     float *out = partial + (size_t)blockIdx.x * pl.stride;
-    for (int i = threadIdx.x; i < pl.nEWs; i += blockDim.x) out[i] = sEW[i];
     for (int i = threadIdx.x; i < pl.nR; i += blockDim.x) {
         const int key = i / kH, hh = i % kH;
         float s = 0.f;
@@ -535,13 +543,27 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
     }
 }
 
-// tot[i] = sum over CTAs (fixed order) of partial[cta][i]
-__global__ void k2_bias_bwd_reduce_kernel(const float *__restrict__ partial, int nparts, int stride, float *__restrict__ tot) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= stride) return;
-    float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * stride + i];
-    tot[i] = s;
+// tot[i] = sum over CTAs of partial[cta][i] (fixed order); the EWsmall part [0, nEWs) is the exact integer sum of the CTAs'
+// fixed-point tables.  The same launch converts the launch-wide fixed-point tables: dEWfull (threads [stride, stride + nEW))
+// and the rel_pos overflow rows into dR (the next kRelRows * kH threads).
+__global__ void k2_bias_bwd_reduce_kernel(const float *__restrict__ partial, int nparts, int stride, int nEWs,
+                                          const long long *__restrict__ ews64, float *__restrict__ tot,
+                                          const long long *__restrict__ dEWfull64, int nEW, float *__restrict__ dEWfull,
+                                          const long long *__restrict__ dR64, float *__restrict__ dR) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nEWs) {
+        long long s = 0;
+        for (int p = 0; p < nparts; ++p) s += ews64[(size_t)p * nEWs + i];
+        tot[i] = fx_to_float(s);
+    } else if (i < stride) {
+        float s = 0.f;
+        for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * stride + i];
+        tot[i] = s;
+    } else if ((i -= stride) < nEW) {
+        dEWfull[i] = fx_to_float(dEWfull64[i]);
+    } else if ((i -= nEW) < kRelRows * kH) {
+        dR[i] = fx_to_float(dR64[i]);
+    }
 }
 
 // totals -> dR, dPpos, dt, and the full dEW[k][v][h] (which already holds the global rare-path atomics):
@@ -655,10 +677,16 @@ extern "C" int32_t mobgt_bias_fwd(const int32_t *n, const int64_t *sq_off, const
     return MOBGT_OK;
 }
 
+// 64-bit words of the fixed-point rare-path tables: per-CTA EWsmall | launch-wide dEW | rel_pos overflow rows
+static int64_t k2_bwd_fx_words(int hops, const K2BwdPlan &pl) {
+    return (int64_t)kNumSMs * pl.nEWs + (int64_t)hops * kEdgeVocab * kH + (int64_t)kRelRows * kH;
+}
+
 extern "C" int64_t mobgt_bias_bwd_workspace_bytes(int32_t T, int32_t hops, int32_t num_bins) {
     if (T < 2 || hops < 4 || hops > MOBGT_MAX_HOPS || num_bins < 1 || num_bins > 1024) return -1;
     const K2BwdPlan pl = k2_bwd_plan(T, round_up(T, 8), hops, num_bins);
-    return ((int64_t)hops * kEdgeVocab * kH + (int64_t)(kNumSMs + 1) * pl.stride) * (int64_t)sizeof(float);
+    return ((int64_t)hops * kEdgeVocab * kH + (int64_t)(kNumSMs + 1) * pl.stride) * (int64_t)sizeof(float) + 16 +
+           k2_bwd_fx_words(hops, pl) * (int64_t)sizeof(long long);
 }
 
 extern "C" int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const int16_t *rel_pos, const int16_t *poi_pos,
@@ -681,15 +709,20 @@ extern "C" int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const
     const K2BwdPlan pl = k2_bwd_plan(T, Tp, hops, num_bins);
     MOBGT_REQUIRE(pl.warps >= 1, MOBGT_ERR_UNSUPPORTED, "mobgt_bias_bwd: no shared-memory plan for T=%d bins=%d", T, num_bins);
     const int64_t nEW = (int64_t)hops * kEdgeVocab * kH;
-    const int64_t need = (nEW + (int64_t)(kNumSMs + 1) * pl.stride) * (int64_t)sizeof(float);
+    const int64_t nfloat = nEW + (int64_t)(kNumSMs + 1) * pl.stride;
+    const int64_t fx_off = (nfloat * (int64_t)sizeof(float) + 15) / 16 * 16;
+    const int64_t need = fx_off + k2_bwd_fx_words(hops, pl) * (int64_t)sizeof(long long);
     MOBGT_REQUIRE(workspace_bytes >= need, MOBGT_ERR_WORKSPACE_TOO_SMALL, "mobgt_bias_bwd: workspace %lld < %lld bytes",
                   (long long)workspace_bytes, (long long)need);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     float *dEWfull = static_cast<float *>(workspace);      // [hops][128][8], then [stride] totals, then [kNumSMs][stride] partials
     float *tot = dEWfull + nEW;
     float *partial = tot + pl.stride;
-    MOBGT_CUDA_OK(cudaMemsetAsync(dR, 0, kRelRows * kH * 4, s));
-    MOBGT_CUDA_OK(cudaMemsetAsync(dEWfull, 0, (size_t)nEW * 4, s));
+    MOBGT_REQUIRE(((uintptr_t)workspace & 15) == 0, MOBGT_ERR_BAD_SHAPE, "mobgt_bias_bwd: workspace must be 16-byte aligned");
+    long long *ews64 = reinterpret_cast<long long *>(static_cast<char *>(workspace) + fx_off);   // [kNumSMs][nEWs]
+    long long *dEWfull64 = ews64 + (size_t)kNumSMs * pl.nEWs;                                     // [hops][128][8]
+    long long *dR64 = dEWfull64 + nEW;                                                            // [512][8]
+    MOBGT_CUDA_OK(cudaMemsetAsync(ews64, 0, (size_t)k2_bwd_fx_words(hops, pl) * sizeof(long long), s));
     const int nparts = B > 0 ? kNumSMs : 0;
     if (B > 0) {
         K2Common c{n, sq_off, rel_pos, poi_pos, edge_in, B, T, Tp, hops, rel_pos_max, dk};
@@ -697,16 +730,17 @@ extern "C" int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const
         if (dbias_dtype == MOBGT_F32) {
             MOBGT_CUDA_OK(cudaFuncSetAttribute(k2_bias_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k2_bias_bwd_kernel<float><<<kNumSMs, pl.warps * 32, smem, s>>>(c, static_cast<const float *>(dBias), 1, 0, num_bins, pl,
-                                                                          partial, dEWfull, dR);
+                                                                          partial, ews64, dEWfull64, dR64);
         } else {
             MOBGT_CUDA_OK(cudaFuncSetAttribute(k2_bias_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)smem));
             k2_bias_bwd_kernel<__nv_bfloat16><<<kNumSMs, pl.warps * 32, smem, s>>>(
-                c, static_cast<const __nv_bfloat16 *>(dBias), n_layers, layer_stride, num_bins, pl, partial, dEWfull, dR);
+                c, static_cast<const __nv_bfloat16 *>(dBias), n_layers, layer_stride, num_bins, pl, partial, ews64, dEWfull64, dR64);
         }
         MOBGT_LAUNCH_OK("k2_bias_bwd_kernel");
     }
-    k2_bias_bwd_reduce_kernel<<<ceil_div(pl.stride, 256), 256, 0, s>>>(partial, nparts, pl.stride, tot);
+    k2_bias_bwd_reduce_kernel<<<ceil_div(pl.stride + (int)nEW + kRelRows * kH, 256), 256, 0, s>>>(
+        partial, nparts, pl.stride, pl.nEWs, ews64, tot, dEWfull64, (int)nEW, dEWfull, dR64, dR);
     MOBGT_LAUNCH_OK("k2_bias_bwd_reduce_kernel");
     k2_bias_bwd_scatter_kernel<<<ceil_div(max(max(kRelRows, num_bins) * kH, hops * kH * 32), 256), 256, 0, s>>>(tot, pl, hops, dk, num_bins, dEWfull, dR, dPpos, dtvd);
     MOBGT_LAUNCH_OK("k2_bias_bwd_scatter_kernel");
