@@ -258,10 +258,16 @@ __global__ void __launch_bounds__(512, 2) k2_bias_fwd_kernel(const K2Common c, c
 // Per-CTA totals go to a partial buffer and are reduced in a fixed order: the whole backward is bitwise reproducible.
 constexpr int kSmallVocab = 16;   // edge features kept in the CTA's shared dEW table
 
+// 12 warps at most: 384 threads leave 170 registers per thread, which the sum phase (18 x 16-byte loads in flight per lane)
+// and the index phase (the indices of up to 160 cells of the row loaded before any is decoded) are sized for
+constexpr int kK2BwdMaxWarps = 12;
+constexpr int kSumItems = 3;     // 16-byte chunks per lane and round of the sum phase
+constexpr int kIdxUnroll = 5;    // 32-cell groups whose index loads are issued together
+
 struct K2BwdPlan {
     int Rrows;      // rel_pos histogram rows: keys 0..Rrows-2 direct, key 511 -> row Rrows-1
     int nEWs, nR, nP, stride;   // floats; partial row = [EWsmall | R | P | t(8)]
-    int pitch;      // floats per head in the dsum strip: >= Tp, == 4 (mod 32)
+    int pitch;      // floats per head in the dsum strip: >= T rounded up to 4, == 4 (mod 32)
     int per_warp;   // floats of warp-private shared memory
     int cta_words;  // floats of CTA-wide shared memory in front of the warp strips
     int warps;
@@ -274,11 +280,13 @@ __host__ __device__ inline K2BwdPlan k2_bwd_plan(int T, int Tp, int hops, int nu
     p.nR = p.Rrows * kH;
     p.nP = num_bins * kH;
     p.stride = p.nEWs + p.nR + p.nP + kH;
-    p.pitch = ((Tp + 27) / 32) * 32 + 4;
+    // cells b < (T + 3) & ~3 are the ones the index / histogram phases touch; the sum phase clips its 8-cell stores at the pitch
+    (void)Tp;
+    p.pitch = ((((T + 3) & ~3) + 27) / 32) * 32 + 4;
     p.per_warp = 2 * (p.nR + kH) + 2 * (p.nP + kH) + kH * p.pitch + 3 * p.pitch + kH;   // hR+trash | hP+trash | dsum | cinfo | cdev | dlist | t
     p.cta_words = (hops + 1) * 8 + 40;                                     // XW | 1/sp table
     int w = (int)((227 * 1024 - 2048 - p.cta_words * 4) / (p.per_warp * 4));
-    p.warps = w > 16 ? 16 : w;
+    p.warps = w > kK2BwdMaxWarps ? kK2BwdMaxWarps : w;
     return p;
 }
 
@@ -307,8 +315,8 @@ __device__ __forceinline__ void sts_f32x4(uint32_t a, float x, float y, float z,
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 
-template <typename DT>
-__global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, const DT *__restrict__ dB, int nlayers,
+template <typename DT, int HOPW>
+__global__ void __launch_bounds__(kK2BwdMaxWarps * 32, 1) k2_bias_bwd_kernel(const K2Common c, const DT *__restrict__ dB, int nlayers,
                                                              int64_t layer_stride, int num_bins,
                                                              const K2BwdPlan pl, float *__restrict__ partial,
                                                              long long *__restrict__ ews64, long long *__restrict__ dEWfull64,
@@ -331,7 +339,7 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
     const uint32_t s_hist = (ty ? s_hP : s_hR) + (uint32_t)(c2 * kH + h) * 4u;      // + key * 64 B
     const uint32_t key_shift = ty ? 16u : 0u;
     const uint32_t trashR = (uint32_t)pl.Rrows, trashP = (uint32_t)num_bins;
-    const int hopw = c.hops >> 2;
+    constexpr int hopw = HOPW;                                   // 32-bit words per walk (hops / 4)
     for (int i = threadIdx.x; i < (c.hops + 1) * 8; i += blockDim.x) XW[i] = (i & 7) < hopw ? expected_word(i >> 3, i & 7) : 0u;
     for (int i = threadIdx.x; i < 40; i += blockDim.x) invT[i] = 1.0f / (float)max(i, 1);
     for (int i = threadIdx.x; i < nwarp * pl.per_warp; i += blockDim.x) wbase[i] = 0.f;
@@ -349,32 +357,32 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
         const DT *rowbase = dB + ((size_t)g * kH * c.T + a) * c.Tp;
         constexpr int kPer = 16 / (int)sizeof(DT);           // cells per 16-byte load
         const int nitems = ceil_div(Tg, kPer) * kH;
-        for (int i0 = 0; i0 < nitems; i0 += 64) {
-            float accv[2][8];
+        for (int i0 = 0; i0 < nitems; i0 += 32 * kSumItems) {
+            float accv[kSumItems][8];
 #pragma unroll
-            for (int s = 0; s < 2; ++s)
+            for (int s = 0; s < kSumItems; ++s)
 #pragma unroll
                 for (int q = 0; q < 8; ++q) accv[s][q] = 0.f;
-            const DT *src[2];
-            bool ok[2];
+            const DT *src[kSumItems];
+            bool ok[kSumItems];
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < kSumItems; ++s) {
                 const int i = i0 + 32 * s + lane;
                 ok[s] = i < nitems;
                 src[s] = rowbase + (size_t)(i & 7) * hs + (i >> 3) * kPer;
             }
             for (int l0 = 0; l0 < nlayers; l0 += 6) {
-                uint4 v[2][6];
+                uint4 v[kSumItems][6];
                 if (l0 + 6 <= nlayers) {
 #pragma unroll
-                    for (int s = 0; s < 2; ++s)
+                    for (int s = 0; s < kSumItems; ++s)
 #pragma unroll
                         for (int j = 0; j < 6; ++j)
                             v[s][j] = ok[s] ? __ldg(reinterpret_cast<const uint4 *>(src[s] + (size_t)(l0 + j) * layer_stride))
                                             : make_uint4(0u, 0u, 0u, 0u);
                 } else {
 #pragma unroll
-                    for (int s = 0; s < 2; ++s)
+                    for (int s = 0; s < kSumItems; ++s)
 #pragma unroll
                         for (int j = 0; j < 6; ++j)
                             v[s][j] = (ok[s] && l0 + j < nlayers)
@@ -382,7 +390,7 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
                                           : make_uint4(0u, 0u, 0u, 0u);
                 }
 #pragma unroll
-                for (int s = 0; s < 2; ++s)
+                for (int s = 0; s < kSumItems; ++s)
 #pragma unroll
                     for (int j = 0; j < 6; ++j) {
                         const uint32_t w4[4] = {v[s][j].x, v[s][j].y, v[s][j].z, v[s][j].w};
@@ -399,12 +407,14 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
                     }
             }
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < kSumItems; ++s) {
                 const int i = i0 + 32 * s + lane;
                 if (ok[s]) {
                     const uint32_t dst = s_dsum + (uint32_t)(i & 7) * pitch4 + (uint32_t)((i >> 3) * kPer) * 4u;
                     sts_f32x4(dst, accv[s][0], accv[s][1], accv[s][2], accv[s][3]);
-                    if constexpr (sizeof(DT) == 2) sts_f32x4(dst + 16u, accv[s][4], accv[s][5], accv[s][6], accv[s][7]);
+                    if constexpr (sizeof(DT) == 2) {         // cells past the pitch lie beyond the graph's last token: never read
+                        if ((i >> 3) * kPer + 8 <= pl.pitch) sts_f32x4(dst + 16u, accv[s][4], accv[s][5], accv[s][6], accv[s][7]);
+                    }
                 }
             }
         }
@@ -412,16 +422,35 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
         //         cdev[b] = up to two deviating bytes ;  dlist = the cells that need the slow path
         int ndl = 0;
         const int Tg4 = (Tg + 3) & ~3;
-        for (int b0 = 0; b0 < Tg4; b0 += 32) {
+        for (int bg = 0; bg < Tg4; bg += 32 * kIdxUnroll) {
+          // the index bytes of up to kIdxUnroll x 32 cells are fetched before the first one is decoded: one memory latency per
+          // group instead of one per 32 cells
+          int rpv[kIdxUnroll], ppv[kIdxUnroll];
+          uint32_t ewv[kIdxUnroll][HOPW];
+#pragma unroll
+          for (int u = 0; u < kIdxUnroll; ++u) {
+              const int b = bg + 32 * u + lane;
+              rpv[u] = ppv[u] = 0;
+#pragma unroll
+              for (int q = 0; q < HOPW; ++q) ewv[u][q] = 0u;
+              if (b >= 1 && b < Tg) {
+                  const int64_t pc = rowp + b;
+                  rpv[u] = c.rel_pos[pc];
+                  ppv[u] = c.poi_pos[pc];
+                  const uint32_t *ei = reinterpret_cast<const uint32_t *>(c.edge_in + pc * c.hops);
+#pragma unroll
+                  for (int q = 0; q < HOPW; ++q) ewv[u][q] = __ldg(ei + q);
+              }
+          }
+#pragma unroll
+          for (int u = 0; u < kIdxUnroll; ++u) {
+            const int b0 = bg + 32 * u;
+            if (b0 >= Tg4) break;                                // warp-uniform
             const int b = b0 + lane;
             uint32_t info = trashR | (trashP << 16), dev = 0u, slow = 0u;
             if (b >= 1 && b < Tg) {
-                const int64_t pc = rowp + b;
-                const int rp = c.rel_pos[pc], pp = c.poi_pos[pc];
-                const uint32_t *ei = reinterpret_cast<const uint32_t *>(c.edge_in + pc * c.hops);
-                uint32_t ew[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) ew[q] = q < hopw ? __ldg(ei + q) : 0u;
+                const int rp = rpv[u], pp = ppv[u];
+                const uint32_t(&ew)[HOPW] = ewv[u];
                 const int rk = min(max(rp, 0), kRelRows - 1);
                 const int L = expected_walk(rk, c.dk);
                 const int row = (rk == 511) ? pl.Rrows - 1 : (rk < pl.Rrows - 1 ? rk : -1);
@@ -430,7 +459,7 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
                     int ndev = 0;
                     dev = (uint32_t)L << 2;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
+                    for (int q = 0; q < HOPW; ++q) {
                         uint32_t df = ew[q] ^ XW[L * 8 + q];
                         while (df != 0u) {
                             const int e = (__ffs(df) - 1) >> 3;
@@ -451,6 +480,7 @@ __global__ void __launch_bounds__(512, 1) k2_bias_bwd_kernel(const K2Common c, c
             const uint32_t bal = __ballot_sync(0xffffffffu, slow != 0u);
             if (slow) sts_u32(s_dlist + (uint32_t)(ndl + __popc(bal & ((1u << lane) - 1u))) * 4u, slow);
             ndl += __popc(bal);
+          }
         }
         __syncwarp();
         // ---- 3. histogram phase: lane = (table, cell slot c2, head h); adjacent cells b0 + 2 c2, b0 + 2 c2 + 1 per step.
@@ -727,16 +757,25 @@ extern "C" int32_t mobgt_bias_bwd(const int32_t *n, const int64_t *sq_off, const
     if (B > 0) {
         K2Common c{n, sq_off, rel_pos, poi_pos, edge_in, B, T, Tp, hops, rel_pos_max, dk};
         const size_t smem = (size_t)(pl.cta_words + pl.warps * pl.per_warp) * sizeof(float);
-        if (dbias_dtype == MOBGT_F32) {
-            MOBGT_CUDA_OK(cudaFuncSetAttribute(k2_bias_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k2_bias_bwd_kernel<float><<<kNumSMs, pl.warps * 32, smem, s>>>(c, static_cast<const float *>(dBias), 1, 0, num_bins, pl,
-                                                                          partial, ews64, dEWfull64, dR64);
-        } else {
-            MOBGT_CUDA_OK(cudaFuncSetAttribute(k2_bias_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)smem));
-            k2_bias_bwd_kernel<__nv_bfloat16><<<kNumSMs, pl.warps * 32, smem, s>>>(
-                c, static_cast<const __nv_bfloat16 *>(dBias), n_layers, layer_stride, num_bins, pl, partial, ews64, dEWfull64, dR64);
+        auto launch = [&](auto kern, auto *db, int nl, int64_t ls) -> int32_t {
+            MOBGT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<kNumSMs, pl.warps * 32, smem, s>>>(c, db, nl, ls, num_bins, pl, partial, ews64, dEWfull64, dR64);
+            return MOBGT_OK;
+        };
+        int32_t rc = MOBGT_OK;
+#define MOBGT_K2B_CASE(HW)                                                                                                   \
+    case HW:                                                                                                                 \
+        rc = (dbias_dtype == MOBGT_F32)                                                                                      \
+                 ? launch(k2_bias_bwd_kernel<float, HW>, static_cast<const float *>(dBias), 1, (int64_t)0)                   \
+                 : launch(k2_bias_bwd_kernel<__nv_bfloat16, HW>, static_cast<const __nv_bfloat16 *>(dBias), n_layers, layer_stride); \
+        break;
+        switch (hops / 4) {
+            MOBGT_K2B_CASE(1) MOBGT_K2B_CASE(2) MOBGT_K2B_CASE(3) MOBGT_K2B_CASE(4) MOBGT_K2B_CASE(5) MOBGT_K2B_CASE(6)
+            MOBGT_K2B_CASE(7) MOBGT_K2B_CASE(8)
+            default: MOBGT_REQUIRE(false, MOBGT_ERR_BAD_SHAPE, "mobgt_bias_bwd: hops=%d", hops);
         }
+#undef MOBGT_K2B_CASE
+        if (rc) return rc;
         MOBGT_LAUNCH_OK("k2_bias_bwd_kernel");
     }
     k2_bias_bwd_reduce_kernel<<<ceil_div(pl.stride + (int)nEW + kRelRows * kH, 256), 256, 0, s>>>(
