@@ -13,7 +13,7 @@ if [[ $ST == *t* ]]; then
 fi
 if [[ $ST == *b* ]]; then
   timeout 900 python bench.py --steps 20 --warmup 5 > $O/bench_c2-dense128.json 2> $O/bench_c2-dense128.err; echo "bench rc=$?"; tail -c 3000 $O/bench_c2-dense128.json
-  for w in c2-natural c4-gowalla256 c4-dense256 c5-eval; do
+  for w in c2-natural c4-gowalla256 c4-gowalla-real c4-dense256 c5-eval; do
     timeout 600 python bench.py --workload $w --steps 20 --warmup 5 --no-cpu-baseline > $O/bench_$w.json 2> $O/bench_$w.err; echo "bench $w rc=$?"; cut -c1-160 $O/bench_$w.json
   done
   timeout 600 python bench.py --workload c3-preprocess --steps 5 --warmup 3 > $O/bench_c3-preprocess.json 2> $O/bench_c3-preprocess.err; echo "bench c3 rc=$?"; cut -c1-160 $O/bench_c3-preprocess.json
@@ -33,8 +33,9 @@ if [[ $ST == *l* ]]; then
   python scripts/launch_summary.py $O/launches.csv > $O/launches_summary.txt 2>&1; gzip -f $O/launches.csv
 fi
 if [[ $ST == *n* ]]; then
-  for spec in "k2_bias_fwd_kernel:k2_fwd" "k2_bias_bwd_kernel:k2_bwd" "k3_attn_fwd:k3_fwd" "k3_attn_bwd:k3_bwd" "k1_apsp_kernel:k1" \
-              "k4_:k4" "k5_head_kernel:k5" "k10_gemm_kernel:k10"; do
+  # NCU_SPECS="regex:name ..." restricts the captures (e.g. to the kernels that changed since the last pass)
+  for spec in ${NCU_SPECS:-k2_bias_fwd_kernel:k2_fwd k2_bias_bwd_kernel:k2_bwd k3_attn_fwd:k3_fwd k3_attn_bwd:k3_bwd k1_apsp_kernel:k1 \
+              k4_:k4 k5_head_kernel:k5 k10_gemm_kernel:k10}; do
     k=${spec%%:*}; n=${spec##*:}
     timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$k" -c 4 -o $O/$n -f \
         python scripts/kbench.py c2-dense128 --iters=1 > $O/$n.log 2>&1; echo "ncu $n rc=$?"
@@ -42,10 +43,12 @@ if [[ $ST == *n* ]]; then
     (echo "== $n (ncu --set full --clock-control none; scripts/ncu_summary.py --stalls)"; python scripts/ncu_summary.py $O/$n.ncu-rep --stalls) >> $O/ncu_kernels.txt 2>&1
     if [[ $n != k3_bwd && $n != k5 ]]; then rm -f $O/$n.ncu-rep; fi
   done
+  if [[ -z "$NCU_SPECS" ]]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k3s_attn" -c 4 -o $O/k3s -f \
       python scripts/step_kernels.py c2-natural --steps=1 > $O/k3s.log 2>&1; echo "ncu k3s rc=$?"
   (echo "== k3s: SIMT attention for graphs of <= 16 tokens, c2-natural batch"; python scripts/ncu_summary.py $O/k3s.ncu-rep --stalls) >> $O/ncu_kernels.txt 2>&1
   rm -f $O/k3s.ncu-rep
+  fi
 fi
 if [[ $ST == *s* ]]; then
   bash scripts/sanitize.sh $O > $O/sanitize.log 2>&1; echo "sanitize rc=$?"; grep -h "rc=" $O/sanitize.log

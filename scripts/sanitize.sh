@@ -8,7 +8,7 @@ CS=/usr/local/cuda/bin/compute-sanitizer
 timeout 900 $CS --tool memcheck --error-exitcode 9 --print-limit 20 python scripts/sanitize_cases.py > $O/sanitizer_memcheck.txt 2>&1
 echo "memcheck rc=$?" | tee -a $O/sanitizer_memcheck.txt
 tail -4 $O/sanitizer_memcheck.txt
-for fam in k1 k3 k5 k10; do
+for fam in ${RACE_FAMS:-k1 k3 k3f k5 k10}; do
   timeout 600 $CS --tool racecheck --racecheck-report analysis --error-exitcode 9 --print-limit 20 python scripts/sanitize_cases.py $fam > $O/sanitizer_racecheck_$fam.txt 2>&1
   echo "racecheck $fam rc=$?" | tee -a $O/sanitizer_racecheck_$fam.txt
   tail -3 $O/sanitizer_racecheck_$fam.txt

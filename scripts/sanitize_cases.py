@@ -1,5 +1,5 @@
 """Small instances of every libmobgt kernel family, for compute-sanitizer (scripts/sanitize.sh): K1 (cluster / DSMEM column
-broadcast), K2 fwd / bwd, K3 fwd / bwd (general kernel incl. fold path, single-box two-CTA kernel), K4, K5 (mbarrier ring),
+broadcast), K2 fwd / bwd, K3 fwd / bwd (general kernel incl. fold path, single-box two-CTA kernel), K3 in fp32 mode, K4, K5 (mbarrier ring),
 K6, K7, K8, K9, K10 (TMA ring + TMEM double buffering), one training step of a 2-layer model."""
 import os
 import sys
@@ -12,7 +12,7 @@ import torch
 from mobgt_b200 import collator, model as M, ops, synth
 from mobgt_b200.optim import FlatAdamW
 
-which = set(sys.argv[1:]) or {"k1", "k2", "k3", "k5", "k7", "k8", "k9", "k10", "step"}
+which = set(sys.argv[1:]) or {"k1", "k2", "k3", "k3f", "k5", "k7", "k8", "k9", "k10", "step"}
 dev = torch.device("cuda")
 w = synth.make_world("tiny", seed=1)
 sizes = (12, 3, 129, 128, 40, 1, 257)            # fold tails at 129 (T = 130: no), 128 (T = 129), 256 + 1
@@ -60,6 +60,22 @@ if "k3" in which:
             ops.attn_bwd_raw(qkv, bs, out, dout, lse, bb, d32, 0, drop_p=p, seed=77)           # general kernel
         torch.cuda.synchronize()
     print("k3 ok")
+if "k3f" in which:          # fp32-mode attention (csrc/k3_attn_f32.cu): dynamic shared memory sized by the largest graph
+    big = synth.make_world("c1", seed=1)
+    its = []
+    for k, n in enumerate((70, 5, 1, 33)):
+        its += synth.make_items(big, 1, 512, seed=40 + k, n_fixed=n, start=k)
+    bb = collator.collator_toyota(its, max_node=512, multi_hop_max_dist=20, rel_pos_max=1024, world=big)
+    bs = ops.bias_fwd_raw(bb, *cu, out_dtype=torch.float32)
+    nt = int(bb.tok_pos.numel())
+    qkv = torch.randn(nt, 576, device=dev)
+    dout = torch.randn(nt, 192, device=dev)
+    for p in (0.0, 0.1):
+        out, lse = ops.attn_f32_fwd_raw(qkv, bs, bb, drop_p=p, seed=78)
+        d32 = torch.zeros_like(bs)
+        ops.attn_f32_bwd_raw(qkv, bs, out, dout, lse, bb, d32, 1, drop_p=p, seed=78)
+    torch.cuda.synchronize()
+    print("k3f ok")
 if "k5" in which:
     z = torch.randn(200, 320, device=dev).to(torch.bfloat16)
     W = (torch.randn(3001, 320, device=dev) * 0.05).to(torch.bfloat16)
