@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(kK2BwdMaxWarps * 32, 1) k2_bias_bwd_kernel(con
         constexpr int kPer = 16 / (int)sizeof(DT);           // cells per 16-byte load
         const int nitems = ceil_div(Tg, kPer) * kH;
         for (int i0 = 0; i0 < nitems; i0 += 32 * kSumItems) {
+            const int ns = min(kSumItems, (nitems - i0 + 31) >> 5);   // 32-item slots of this round that hold an item (warp-uniform)
             float accv[kSumItems][8];
 #pragma unroll
             for (int s = 0; s < kSumItems; ++s)
@@ -369,39 +370,45 @@ __global__ void __launch_bounds__(kK2BwdMaxWarps * 32, 1) k2_bias_bwd_kernel(con
             for (int s = 0; s < kSumItems; ++s) {
                 const int i = i0 + 32 * s + lane;
                 ok[s] = i < nitems;
-                src[s] = rowbase + (size_t)(i & 7) * hs + (i >> 3) * kPer;
+                const int ic = min(i, nitems - 1);           // lanes past the last item re-read it (no predicate on the loads)
+                src[s] = rowbase + (size_t)(ic & 7) * hs + (ic >> 3) * kPer;
             }
             for (int l0 = 0; l0 < nlayers; l0 += 6) {
                 uint4 v[kSumItems][6];
                 if (l0 + 6 <= nlayers) {
 #pragma unroll
                     for (int s = 0; s < kSumItems; ++s)
+                        if (s < ns) {
+                            const DT *pl0 = src[s] + (size_t)l0 * layer_stride;
 #pragma unroll
-                        for (int j = 0; j < 6; ++j)
-                            v[s][j] = ok[s] ? __ldg(reinterpret_cast<const uint4 *>(src[s] + (size_t)(l0 + j) * layer_stride))
-                                            : make_uint4(0u, 0u, 0u, 0u);
+                            for (int j = 0; j < 6; ++j) v[s][j] = __ldg(reinterpret_cast<const uint4 *>(pl0 + (size_t)j * layer_stride));
+                        }
                 } else {
 #pragma unroll
                     for (int s = 0; s < kSumItems; ++s)
+                        if (s < ns) {
 #pragma unroll
-                        for (int j = 0; j < 6; ++j)
-                            v[s][j] = (ok[s] && l0 + j < nlayers)
-                                          ? __ldg(reinterpret_cast<const uint4 *>(src[s] + (size_t)(l0 + j) * layer_stride))
-                                          : make_uint4(0u, 0u, 0u, 0u);
+                            for (int j = 0; j < 6; ++j)
+                                v[s][j] = (l0 + j < nlayers)
+                                              ? __ldg(reinterpret_cast<const uint4 *>(src[s] + (size_t)(l0 + j) * layer_stride))
+                                              : make_uint4(0u, 0u, 0u, 0u);
+                        }
                 }
 #pragma unroll
                 for (int s = 0; s < kSumItems; ++s)
+                    if (s < ns) {
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        const uint32_t w4[4] = {v[s][j].x, v[s][j].y, v[s][j].z, v[s][j].w};
-                        if constexpr (sizeof(DT) == 4) {
+                        for (int j = 0; j < 6; ++j) {
+                            const uint32_t w4[4] = {v[s][j].x, v[s][j].y, v[s][j].z, v[s][j].w};
+                            if constexpr (sizeof(DT) == 4) {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) accv[s][q] += __uint_as_float(w4[q]);
-                        } else {
+                                for (int q = 0; q < 4; ++q) accv[s][q] += __uint_as_float(w4[q]);
+                            } else {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                accv[s][2 * q] += bf16lo(w4[q]);
-                                accv[s][2 * q + 1] += __uint_as_float(w4[q] & 0xFFFF0000u);
+                                for (int q = 0; q < 4; ++q) {
+                                    accv[s][2 * q] += bf16lo(w4[q]);
+                                    accv[s][2 * q + 1] += __uint_as_float(w4[q] & 0xFFFF0000u);
+                                }
                             }
                         }
                     }
