@@ -590,11 +590,13 @@ __global__ void k2_bias_bwd_reduce_kernel(const float *__restrict__ partial, int
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nEWs) {
         long long s = 0;
-        for (int p = 0; p < nparts; ++p) s += ews64[(size_t)p * nEWs + i];
+#pragma unroll 8
+        for (int p = 0; p < nparts; ++p) s += ews64[(size_t)p * nEWs + i];     // eight loads in flight; integer sum: any order
         tot[i] = fx_to_float(s);
     } else if (i < stride) {
         float s = 0.f;
-        for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * stride + i];
+#pragma unroll 8
+        for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * stride + i];  // loads hoisted, additions in part order
         tot[i] = s;
     } else if ((i -= stride) < nEW) {
         dEWfull[i] = fx_to_float(dEWfull64[i]);
