@@ -67,7 +67,10 @@ def load_world(raw_dir, dataset_name, num_bins=64):
     X[:, C + 2] = raw_x[:, 3]
     latlon = np.ascontiguousarray(raw_x[:, 2:4], np.float32)
     span = latlon.max(0) - latlon.min(0)
-    return PoiWorld(P=P, C=C, U=NUM_USERS.get(dataset_name, 0), dataset_name=dataset_name, cat_of_poi=cat, latlon=latlon,
+    if dataset_name not in NUM_USERS:
+        raise ValueError(f"dataset_name={dataset_name!r}: the reference sizes its user table per data set (model_fqandtoyo.py:721-723, "
+                         f"852, 981); known: {sorted(NUM_USERS)}")
+    return PoiWorld(P=P, C=C, U=NUM_USERS[dataset_name], dataset_name=dataset_name, cat_of_poi=cat, latlon=latlon,
                     check_freq=raw_x[:, 1].astype(np.int64), num_bins=num_bins, dist_max=float(np.sqrt((span ** 2).sum())) + 1e-6,
                     D_A=hat_rw_normd_csr(raw_d), C_A=hat_rw_normd_csr(raw_c), X=X, C_X=np.eye(C, dtype=np.float32))
 
