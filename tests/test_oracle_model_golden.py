@@ -213,3 +213,51 @@ def test_eval_targets_match_reference_steps(dataset_name):
 
     assert torch.equal(pm.eval_targets(B), torch.from_numpy(gold["y_true_test"]))
     assert torch.equal(pm.eval_targets(B), torch.from_numpy(gold["y_true_val"]))
+
+
+# ------------------------------------------------------------------------------------------------------- real data
+def test_oracle_equals_reference_on_real_data():
+    """The REAL Gowalla-Nevada data set of the reference (tests/golden/make_model_golden_real.py: the unmodified reference
+    constructor on the archive's own Graph_*.csv — dense calculate_laplacian_matrix, dense GCN products — its preprocess_item,
+    collator_gowalla, forward, GradientTailLoss and backward on real train trajectories): the oracle on the world that
+    mobgt_b200.owndata builds from the same files (CSR adjacency; here through the committed packed fixture) reproduces the
+    collated fields bit for bit, the logits and the loss within 1e-5, and the gradient norms."""
+    from mobgt_b200 import owndata
+    g = _gen()
+    spec = importlib.util.spec_from_file_location("make_model_golden_real", os.path.join(HERE, "golden", "make_model_golden_real.py"))
+    gr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gr)
+    gold = np.load(os.path.join(HERE, "golden", "model_golden_gowalla_real.npz"))
+    world, splits = owndata.unpack_dataset(np.load(os.path.join(HERE, "golden", "gowalla_nevda_real.npz")))
+    items = gr.real_items(splits)
+    assert [it.idx for it in items] == gold["item_idx"].tolist()
+    ob = mo.collate([mo.preprocess_item(it, hop_cap=20) for it in items], world, multi_hop_max_dist=20, rel_pos_max=1024)
+    for name in ("x", "rel_pos", "edge_input", "in_degree", "out_degree", "y", "user"):
+        ref = torch.from_numpy(gold["f_" + name])
+        got = getattr(ob, name)
+        assert tuple(got.shape) == tuple(ref.shape), (name, got.shape, ref.shape)
+        assert torch.equal(got.long(), ref.long()), name
+    assert torch.equal(ob.attn_bias, torch.from_numpy(gold["f_attn_bias"]))
+    om = mo.Graphormer(world, n_layers=g.HP["n_layers"], ffn_dim=g.HP["ffn_dim"], dataset_name="gowalla_nevda").eval()
+    with torch.no_grad():
+        for name, p in om.named_parameters():
+            p.copy_(g.golden_weights(name, tuple(p.shape)))
+        poi, cat = om(ob)
+        loss = om.training_loss(ob)
+    rp, rc = torch.from_numpy(gold["poi_logits"]), torch.from_numpy(gold["cat_logits"])
+    assert tuple(poi.shape) == tuple(rp.shape) and tuple(cat.shape) == tuple(rc.shape)
+    assert (poi - rp).abs().max().item() <= 1e-5 * max(1.0, rp.abs().max().item()), (poi - rp).abs().max().item()
+    assert (cat - rc).abs().max().item() <= 1e-5 * max(1.0, rc.abs().max().item()), (cat - rc).abs().max().item()
+    assert abs(float(loss) - float(gold["loss"][0])) <= 1e-5 * abs(float(gold["loss"][0]))
+    om.training_loss(ob, bias_mode="ref_half").backward()
+    grads = {n: p.grad for n, p in om.named_parameters() if p.grad is not None}
+    names = [str(n) for n in gold["grad_names"]]
+    assert len(names) > 40
+    top = float(gold["grad_norms"].max())
+    for n, ref_norm in zip(names, gold["grad_norms"]):
+        got = float(grads[n].double().norm())
+        assert abs(got - ref_norm) <= 2e-3 * ref_norm + 1e-6 * top, (n, got, ref_norm)
+    for n in g.GRAD_FULL:
+        ref = torch.from_numpy(gold["g_" + n])
+        tol = 2e-3 if n in ("edge_encoder.weight", "edge_dis_encoder.weight") else 1e-5
+        assert (grads[n] - ref).abs().max().item() <= tol * ref.abs().max().item(), n
