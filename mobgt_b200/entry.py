@@ -136,7 +136,7 @@ def cli_main(argv=None):
         # one batch ahead: host packing in --num_workers processes, H2D + K1 + poi_pos + sort plans on a side stream; training
         # batches are padded to size buckets so that the captured CUDA graphs replay across batches of different graphs
         return collator.PackedLoader(item_batches(items, shuffle, epoch, pad), num_workers=args.num_workers, max_node=512,
-                                     bucket=shuffle and not args.no_cuda_graph, **ckw)
+                                     bucket=shuffle and not args.no_cuda_graph and args.precision == 16, **ckw)
 
     model = Graphormer(
         n_layers=args.n_layers, num_heads=args.num_heads, hidden_dim=args.hidden_dim,
@@ -151,7 +151,10 @@ def cli_main(argv=None):
     if rank == 0:
         print("total params:", sum(p.numel() for p in model.parameters()))
 
-    tr = Trainer(model, dev, world_size, cuda_graph=not args.no_cuda_graph)
+    # the fp32 mode is the full-precision / verification mode: it runs eagerly (CUDA-graph capture is exercised, and measured,
+    # on the bf16 path only)
+    use_graph = not args.no_cuda_graph and args.precision == 16
+    tr = Trainer(model, dev, world_size, cuda_graph=use_graph)
     ckdir = _ckpt_dir(args)
     last = os.path.join(ckdir, "last.ckpt")
     epoch0 = 0
