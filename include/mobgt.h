@@ -114,6 +114,9 @@ int32_t mobgt_poi_pos(const int32_t *x, const int32_t *n, const int64_t *sq_off,
  *   dbias_dtype MOBGT_F32:  one f32 [B,H,T,Tp] buffer holding the sum over layers (n_layers = 1);
  *   dbias_dtype MOBGT_BF16: n_layers bf16 [B,H,T,Tp] planes, layer_stride elements apart (mobgt_attn_bwd mode 2),
  *                           summed in fp32 inside the kernel.
+ *   The result is bitwise reproducible (fixed-order histogram reductions; the rare path — walk bytes that deviate from the
+ *   expected walk — accumulates in 64-bit fixed point, where the order of the atomics is immaterial).  `workspace` must be
+ *   16-byte aligned.
  * ------------------------------------------------------------------------------------------ */
 /* bytes of `workspace` mobgt_bias_fwd needs; < 0 on bad arguments */
 int64_t mobgt_bias_fwd_workspace_bytes(int32_t hops, int32_t H);
