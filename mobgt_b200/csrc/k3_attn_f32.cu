@@ -67,6 +67,8 @@ __device__ __forceinline__ bool keep_bit(bool on, uint32_t rowkey, int col, uint
     return !on || ((attn_drop_keep8(rowkey, (uint32_t)(col >> 3), th16) >> (col & 7)) & 1u);
 }
 
+}  // namespace
+
 // ---------------------------------------------------------------------------------------------------------------- forward
 __global__ void __launch_bounds__(kThreadsF) k3f_attn_fwd_kernel(const F32AttnParams p) {
     extern __shared__ __align__(16) float smem[];
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(kThreadsF) k3f_attn_bwd_kernel(const F32AttnPa
     }
 }
 
+namespace {
 int32_t check_common(const void *q, const void *k, const void *v, const void *bias, const int32_t *tok_off, int32_t B, int32_t H,
                      int32_t ntok, int32_t T, int32_t Tp, int32_t t_max_host, float drop_p) {
     MOBGT_REQUIRE(q && k && v && bias && tok_off, MOBGT_ERR_NULL, "mobgt_attn_f32: null pointer");
