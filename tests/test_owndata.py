@@ -127,3 +127,22 @@ def test_real_batches_pack_and_match_the_oracle_collator(real):
     assert np.array_equal(padded(field("out_deg"), np.int64), ob.out_degree.numpy())
     assert np.array_equal(field("user").reshape(-1), ob.user.numpy().reshape(-1))
     assert np.array_equal(field("y").reshape(-1), ob.y.numpy().reshape(-1))
+
+
+def test_hat_rw_normd_csr_equals_the_dense_formula():
+    """(D + I)^-1 (A + I) of calculate_laplacian_matrix(..., 'hat_rw_normd_lap_mat') (model_fqandtoyo.py:476-484), restated with
+    numpy's dense inverse as the reference writes it, on random weighted / binary / empty-row adjacency matrices."""
+    from mobgt_b200 import owndata
+    rng = np.random.default_rng(0)
+    for n, density, weighted in ((1, 0.0, False), (7, 0.3, False), (40, 0.1, True), (64, 0.0, False), (33, 0.9, True)):
+        a = (rng.random((n, n)) < density).astype(np.float64)
+        if weighted:
+            a *= rng.integers(1, 9, size=(n, n))
+        deg = np.asmatrix(np.diag(a.sum(1)))
+        ident = np.asmatrix(np.identity(n))
+        ref = np.asarray(np.matmul(np.linalg.matrix_power(deg + ident, -1), np.asmatrix(a) + ident)).astype(np.float32)
+        crow, col, val = owndata.hat_rw_normd_csr(a)
+        got = np.zeros((n, n), np.float32)
+        got[np.repeat(np.arange(n), np.diff(crow)), col] = val
+        assert np.array_equal(got, ref), (n, density, weighted)
+        assert np.all(np.diff(crow) >= 1)                                 # the self loop is always there
